@@ -1,0 +1,260 @@
+/*
+ * kbotstep.h -- C-ABI of libkbotstep.so: the B200-native (sm_100a) rollout control step of the
+ * kbot-joystick task.  Plain pointers and sizes; no torch / JAX types.  Every entry point cites the
+ * reference interface (file:line under kscalelabs/kbot-joystick) it replaces.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller unless stated otherwise.  The library owns
+ *    only the packed weights and scratch held by the opaque handle.
+ *  - Work is enqueued on the caller's stream (a cudaStream_t passed as void*); calls are asynchronous.
+ *  - Return value: 0 ok; <0 invalid argument (KBS_E_*); >0 a cudaError_t.  Nothing throws; there is no
+ *    CPU fallback.
+ *  - Layout "SoA[F][ld]": feature-major, env index contiguous, row f at base + f*ld.  ld >= n_envs,
+ *    ld % 4 == 0, base 16-byte aligned (float4 access).  Trajectories are [T][F][ld]: step t at
+ *    base + t*F*ld.
+ *  - Layout "AoS[n][W]": row-major per env (used for recurrent carries, K-major GEMM operands).
+ *  - fp32 everywhere; termination codes int32; done/success uint8 (0/1).
+ */
+#ifndef KBOTSTEP_H_
+#define KBOTSTEP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KBS_VERSION 100
+#define KBS_NUM_JOINTS 20
+#define KBS_NUM_COMMANDS 16
+#define KBS_ACTOR_OBS 65    /* train.py:1290-1295 */
+#define KBS_CRITIC_OBS 475  /* train.py:1297-1312 */
+#define KBS_ACTOR_OUT 40
+#define KBS_MAX_DEPTH 4
+#define KBS_NUM_REWARDS 12
+#define KBS_NQ 27
+#define KBS_NV 26
+#define KBS_NBODY 24
+#define KBS_NSENSORDATA 49
+#define KBS_NUM_COMPUTED_OBS 78
+
+/* error codes */
+#define KBS_OK 0
+#define KBS_E_NULL (-1)       /* required pointer is NULL */
+#define KBS_E_SHAPE (-2)      /* n_envs / ld / T / hidden size not supported */
+#define KBS_E_ALIGN (-3)      /* pointer not 16-byte aligned or ld % 4 != 0 */
+#define KBS_E_STATE (-4)      /* weights not packed / handle not ready */
+#define KBS_E_PARAM (-5)      /* bad scalar parameter */
+
+enum { KBS_NET_ACTOR = 0, KBS_NET_CRITIC = 1 };
+/* GEMM datapath for the LSTM/MLP contractions.  Both are sm_100a CUDA in this library (no vendor
+ * library, no fallback): TC = tcgen05 3xTF32 with fp32 TMEM accumulators; SIMT = fp32 FFMA. */
+enum { KBS_GEMM_TC_3XTF32 = 0, KBS_GEMM_SIMT_FP32 = 1 };
+
+/* Scalars of the path.  Defaults = the reference launch config (train.py:1761-1791) and tables
+ * train.py:22-70, 1206-1269; robot/kbot/metadata.json; robot/kbot/robot.mjcf. */
+typedef struct kbs_params {
+  int32_t hidden_size;          /* train.py:1773 (256); 128 also supported */
+  int32_t depth;                /* train.py:82 (2) */
+  int32_t gemm_path;            /* KBS_GEMM_* */
+  int32_t normalize_advantages; /* ksim compute_ppo_inputs flag [unverified]: 0 none, 1 per-trajectory a/(std+eps) */
+  float ctrl_dt;                /* train.py:1776 */
+  float min_std, max_std, var_scale; /* train.py:1320-1322 */
+  float lpf_alpha;              /* ksim.lowpass_one_pole coefficient, y' = y + alpha (x - y) */
+  float gamma, lam, adv_eps;    /* train.py:1769-1770 */
+  float jpos_noise_mag, jvel_noise_mag, gyro_noise_std, pg_noise_std; /* train.py:1160,1162,1176,1194 */
+  float gravity, eps_quat;
+  float unhealthy_z, max_tilt, max_length_sec; /* train.py:1265-1268 */
+  float switch_prob;            /* train.py:1220 */
+  float cmd_lo[6], cmd_hi[6];   /* vx vy wz bh rx ry, train.py:1212-1217 */
+  float joint_bias[KBS_NUM_JOINTS];   /* train.py:24-45 */
+  float joint_range[KBS_NUM_JOINTS];  /* max(bias-min, max-bias), train.py:1332 */
+  float arm_lo[10], arm_hi[10];       /* JOINT_LIMITS[10:20], train.py:1207-1209 */
+  float kp[KBS_NUM_JOINTS], kd[KBS_NUM_JOINTS], ctrl_limit[KBS_NUM_JOINTS];
+  float reward_scale[KBS_NUM_REWARDS]; /* train.py:1224-1256 table order */
+  float linvel_es, angvel_es, rp_es, rp_es_zero, bh_es, bh_standard, bh_foot_origin, arm_es;
+  float grace_period, touchdown_penalty, feet_es, com_es, acc_es, torque_es;
+  int32_t body_base, body_lfoot, body_rfoot;           /* 1, 7, 12 */
+  int32_t sd_gyro, sd_imu_quat, sd_touch_l, sd_touch_r; /* 19, 28, 47, 48 */
+} kbs_params;
+
+/* One control step of physics state, SoA[F][ld] per field (ksim PhysicsData fields the Task reads). */
+typedef struct kbs_state_view {
+  const float* qpos;           /* [27][ld] */
+  const float* qvel;           /* [26][ld] */
+  const float* sensordata;     /* [49][ld] */
+  const float* xpos;           /* [72][ld]  row 3*body+k */
+  const float* xquat;          /* [96][ld]  row 4*body+k, (w,x,y,z) */
+  const float* cinert;         /* [240][ld] row 10*body+k */
+  const float* cvel;           /* [144][ld] row 6*body+k */
+  const float* actuator_force; /* [20][ld] */
+  const float* com_distance;   /* [ld]  COMDistanceObservation consumed as a recorded scalar */
+  const float* time;           /* [ld]  episode time, seconds */
+  int64_t ld;
+} kbs_state_view;
+
+/* PRNG-derived noise, supplied explicitly (parity mode: "identical inputs and PRNG-derived noise"). */
+typedef struct kbs_noise_view {
+  const float* eps_jpos;   /* [20][ld] U(-1,1)  AdditiveUniformNoise train.py:1160 */
+  const float* eps_jvel;   /* [20][ld] U(-1,1)  train.py:1162 */
+  const float* eps_gyro;   /* [3][ld]  N(0,1)   train.py:1176 */
+  const float* eps_pg;     /* [3][ld]  N(0,1)   train.py:1194 */
+} kbs_noise_view;
+
+/* Per-episode randomisation: any pointer may be NULL = nominal / zero. */
+typedef struct kbs_episode_view {
+  const float* jpos_bias;  /* [20][ld] BiasedJointPositionObservation train.py:1158 */
+  const float* pg_lag;     /* [ld]     ProjectedGravityObservation lag, train.py:1195-1196 */
+  const float* pg_bias;    /* [3][ld]  train.py:1197 */
+  const float* kp;         /* [20][ld] PositionActuators kp_scale etc., train.py:1097-1105 */
+  const float* kd;         /* [20][ld] */
+  const float* tau_limit;  /* [20][ld] */
+  const float* action_bias;/* [20][ld] */
+  const float* torque_bias;/* [20][ld] */
+} kbs_episode_view;
+
+/* eqx-layout weights of one network (device pointers). Linear.weight [out][in], LSTMCell.weight_ih
+ * [4H][H], weight_hh [4H][H], bias [4H], gate order i,f,g,o (train.py:878-903, 964-989). */
+typedef struct kbs_net_weights {
+  const float* w_in;  const float* b_in;
+  const float* w_ih[KBS_MAX_DEPTH]; const float* w_hh[KBS_MAX_DEPTH]; const float* b[KBS_MAX_DEPTH];
+  const float* w_out; const float* b_out;
+} kbs_net_weights;
+
+/* Outputs of the actor head (any pointer may be NULL = not written). */
+typedef struct kbs_actor_out {
+  float* action;    /* [20][ld]  mode() or mean + std*eps      train.py:1564 */
+  float* mean;      /* [20][ld]  low-pass-filtered mean        train.py:933-936 */
+  float* std;       /* [20][ld]  train.py:929, PPOVariables.action_std 1487 */
+  float* log_prob;  /* [ld]      of `action` (or of action_in) train.py:1452 */
+  float* entropy;   /* [ld]      train.py:1486 */
+} kbs_actor_out;
+
+typedef struct kbs_handle kbs_handle;
+
+int kbs_version(void);
+const char* kbs_error_string(int code);
+/* Fill *p with the reference launch configuration. */
+int kbs_default_params(kbs_params* p);
+int kbs_create(const kbs_params* p, kbs_handle** out);
+int kbs_destroy(kbs_handle* h);
+int kbs_get_params(const kbs_handle* h, kbs_params* out);
+
+/* Replaces: equinox parameter pytrees of Actor/Critic (train.py:847-1004), loaded by
+ * task.load_ckpt (convert.py:36-39).  Repacks into the kernel layouts (gate-interleaved, hi/lo split). */
+int kbs_weights_pack(kbs_handle* h, int net, const kbs_net_weights* w, void* stream);
+
+/* Replaces: HumanoidWalkingTask.get_observations + every Observation.observe (train.py:1155-1204, 682-707)
+ * and the obs concatenations of run_actor / run_critic (train.py:1351-1431).
+ *   computed   [78][ld] or NULL: rows 0-19 biased_joint_position, 20-39 noisy_biased_joint_position,
+ *              40-59 noisy_joint_velocity, 60-62 noisy_imu_gyro, 63-68 feet_position, 69-71 projected_gravity,
+ *              72-74 imu_projected_gravity, 75-77 noisy_imu_projected_gravity  (all other table entries are
+ *              row slices of kbs_state_view and are not copied)
+ *   actor_obs  [65][ld] or NULL;  critic_obs [475][ld] or NULL
+ *   pg_carry   [3][ld] in/out lagged projected gravity state (may be NULL when episode->pg_lag is NULL)
+ *   noise may be NULL (then noisy twins = clean values). */
+int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_view* noise,
+                     const kbs_episode_view* ep, const float* command, float* pg_carry,
+                     float* computed, float* actor_obs, float* critic_obs, int64_t n_envs, void* stream);
+
+/* Replaces: UnifiedCommand.__call__/initial_command (train.py:724-785).  Randomness explicit:
+ *   u_switch [ld] U[0,1); mode int32 [ld] in 0..5; u6 [6][ld]; u_arms [10][ld].  u_switch NULL = always
+ *   resample (initial_command).  command [16][ld] in/out. */
+int kbs_command_update(kbs_handle* h, float* command, const float* u_switch, const int32_t* mode,
+                       const float* u6, const float* u_arms, int64_t ld, int64_t n_envs, void* stream);
+
+/* Replaces: sample_action -> run_actor -> Actor.forward (train.py:1545-1572, 1351-1379, 913-941) and the
+ * actor half of _ppo_scan_fn (train.py:1443-1452, 1486-1487).
+ *   obs [65][ld]; carry AoS [depth][2][n][H] in/out; lpf [20][ld] in/out; eps [20][ld] or NULL (argmax);
+ *   action_in [20][ld] or NULL: if given, log_prob is evaluated at action_in (stored transition);
+ *   done [ld] or NULL: carries and lpf reset to initial (zeros) where done (train.py:1502-1506). */
+int kbs_actor_step(kbs_handle* h, const float* obs, int64_t ld, float* carry, float* lpf, const float* eps,
+                   const float* action_in, const uint8_t* done, const kbs_actor_out* out, int64_t n_envs,
+                   void* stream);
+
+/* Replaces: run_critic -> Critic.forward (train.py:1381-1433, 993-1004). obs [475][ld]; value [ld]. */
+int kbs_critic_step(kbs_handle* h, const float* obs, int64_t ld, float* carry, const uint8_t* done,
+                    float* value, int64_t n_envs, void* stream);
+
+/* Replaces: get_actuators -> ksim.PositionActuators.get_ctrl (train.py:1091-1105).
+ *   action, ctrl_out [20][ld]; q = qpos rows 7.., qd = qvel rows 6.. of the state view. */
+int kbs_torque(kbs_handle* h, const float* action, const kbs_state_view* s, const kbs_episode_view* ep,
+               float* ctrl_out, int64_t n_envs, void* stream);
+
+/* Replaces: get_terminations + TerrainBadZTermination.__call__ (train.py:1258-1269, 817-823) and ksim's
+ * done/success reduction.  codes int32 [3][ld] (bad_z, not_upright, episode_length); done/success u8 [ld];
+ * pre [2][ld] or NULL: pre-threshold values (height, tilt) for tolerance-based checking. */
+int kbs_terminate(kbs_handle* h, const kbs_state_view* s, int32_t* codes, uint8_t* done, uint8_t* success,
+                  float* pre, int64_t n_envs, void* stream);
+
+/* Trajectory-wise inputs of get_rewards: T steps of state plus the recorded command / ctrl / done. */
+typedef struct kbs_traj_view {
+  kbs_state_view state;   /* each field [T][F][ld] */
+  const float* command;   /* [T][16][ld] */
+  const float* ctrl;      /* [T][20][ld]  Trajectory.ctrl (train.py:504) */
+  const uint8_t* done;    /* [T][ld] */
+  int64_t T;
+} kbs_traj_view;
+
+/* Reward carries (train.py:135-136, 175-178), in/out: t_single [ld], airtime [2][ld], prev_contact u8 [2][ld]. */
+typedef struct kbs_reward_carry {
+  float* t_single; float* airtime; uint8_t* prev_contact;
+} kbs_reward_carry;
+
+/* Replaces: get_rewards table + the 12 Reward.get_reward[_stateful] (train.py:125-506, 1224-1256) and
+ * ksim's scale-and-sum.  total [T][ld]; components [T][12][ld] or NULL. */
+int kbs_rewards(kbs_handle* h, const kbs_traj_view* traj, const kbs_reward_carry* carry, float* total,
+                float* components, int64_t n_envs, void* stream);
+
+/* Replaces: ksim.compute_ppo_inputs (GAE; PPOConfig gamma/lam train.py:1769-1770).
+ * values, rewards [T][ld]; done, success u8 [T][ld]; advantages, value_targets [T][ld]. */
+int kbs_gae(kbs_handle* h, const float* values, const float* rewards, const uint8_t* done,
+            const uint8_t* success, float* advantages, float* value_targets, int64_t T, int64_t ld,
+            int64_t n_envs, void* stream);
+
+/* Replaces: convert.py:84-119 step_fn (kinfer policy step).  AoS inputs as the exported function takes them:
+ * joint_angles [n][20], joint_vel [n][20], projected_gravity [n][3], gyro [n][3], command [n][16],
+ * carry [n][depth*2*H+20] in -> carry_out; action_out [n][20] = dist.mode(). */
+int kbs_policy_step(kbs_handle* h, const float* joint_angles, const float* joint_vel,
+                    const float* projected_gravity, const float* gyro, const float* command,
+                    const float* carry_in, float* carry_out, float* action_out, int64_t n_envs, void* stream);
+
+/* Fused rollout control step over T recorded steps (T=1: the per-step call ksim's engine loop makes):
+ * observations -> actor -> sample -> torque -> terminations -> command update -> carry reset on done,
+ * and (if critic_value != NULL) critic obs -> critic -> value.  Replaces the body of ksim's step_engine
+ * around mjx.step for recorded/synthetic state.
+ * All per-step arrays are trajectories [T][...][ld]. */
+typedef struct kbs_rollout_io {
+  kbs_state_view state;           /* [T][F][ld] */
+  kbs_noise_view noise;           /* [T][..][ld] */
+  kbs_episode_view episode;       /* per-env, no time axis */
+  const float* eps_action;        /* [T][20][ld] N(0,1) or NULL (argmax) */
+  const float* u_switch;          /* [T][ld] */
+  const int32_t* cmd_mode;        /* [T][ld] */
+  const float* cmd_u6;            /* [T][6][ld] */
+  const float* cmd_u_arms;        /* [T][10][ld] */
+  float* command;                 /* [T+1][16][ld]: row 0 = command at step 0 (input); row t+1 written */
+  float* pg_carry;                /* [3][ld] in/out */
+  float* actor_carry;             /* AoS [depth][2][n][H] in/out */
+  float* critic_carry;            /* AoS [depth][2][n][H] in/out (used if value != NULL) */
+  float* lpf;                     /* [20][ld] in/out */
+  float* actor_obs;               /* [T][65][ld] or NULL (stored for the PPO pass) */
+  float* action;                  /* [T][20][ld] */
+  float* log_prob;                /* [T][ld] or NULL */
+  float* ctrl;                    /* [T][20][ld] */
+  int32_t* term_codes;            /* [T][3][ld] or NULL */
+  uint8_t* done;                  /* [T][ld] */
+  uint8_t* success;               /* [T][ld] */
+  float* value;                   /* [T][ld] or NULL */
+  int64_t T;
+} kbs_rollout_io;
+
+int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n_envs, void* stream);
+
+/* Number of kernel launches this library has enqueued since the handle was created (bench bookkeeping). */
+int64_t kbs_launch_count(const kbs_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KBOTSTEP_H_ */

@@ -1,0 +1,153 @@
+"""ctypes binding of libkbotstep.so (include/kbotstep.h).
+
+PyTorch is used only for device memory and streams; every compute call goes through the C-ABI.  There is no
+CPU fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = _PKG_DIR / "libkbotstep.so"
+
+NUM_JOINTS = 20
+NUM_COMMANDS = 16
+ACTOR_OBS = 65
+CRITIC_OBS = 475
+MAX_DEPTH = 4
+NUM_REWARDS = 12
+NET_ACTOR, NET_CRITIC = 0, 1
+GEMM_TC_3XTF32, GEMM_SIMT_FP32 = 0, 1
+
+_f, _i32, _i64, _vp = C.c_float, C.c_int32, C.c_int64, C.c_void_p
+
+
+class KbsParams(C.Structure):
+    _fields_ = [
+        ("hidden_size", _i32), ("depth", _i32), ("gemm_path", _i32), ("normalize_advantages", _i32),
+        ("ctrl_dt", _f), ("min_std", _f), ("max_std", _f), ("var_scale", _f), ("lpf_alpha", _f),
+        ("gamma", _f), ("lam", _f), ("adv_eps", _f),
+        ("jpos_noise_mag", _f), ("jvel_noise_mag", _f), ("gyro_noise_std", _f), ("pg_noise_std", _f),
+        ("gravity", _f), ("eps_quat", _f),
+        ("unhealthy_z", _f), ("max_tilt", _f), ("max_length_sec", _f), ("switch_prob", _f),
+        ("cmd_lo", _f * 6), ("cmd_hi", _f * 6),
+        ("joint_bias", _f * 20), ("joint_range", _f * 20), ("arm_lo", _f * 10), ("arm_hi", _f * 10),
+        ("kp", _f * 20), ("kd", _f * 20), ("ctrl_limit", _f * 20), ("reward_scale", _f * 12),
+        ("linvel_es", _f), ("angvel_es", _f), ("rp_es", _f), ("rp_es_zero", _f), ("bh_es", _f),
+        ("bh_standard", _f), ("bh_foot_origin", _f), ("arm_es", _f), ("grace_period", _f),
+        ("touchdown_penalty", _f), ("feet_es", _f), ("com_es", _f), ("acc_es", _f), ("torque_es", _f),
+        ("body_base", _i32), ("body_lfoot", _i32), ("body_rfoot", _i32),
+        ("sd_gyro", _i32), ("sd_imu_quat", _i32), ("sd_touch_l", _i32), ("sd_touch_r", _i32),
+    ]
+
+
+class KbsStateView(C.Structure):
+    _fields_ = [(k, _vp) for k in ("qpos", "qvel", "sensordata", "xpos", "xquat", "cinert", "cvel",
+                                   "actuator_force", "com_distance", "time")] + [("ld", _i64)]
+
+
+class KbsNoiseView(C.Structure):
+    _fields_ = [(k, _vp) for k in ("eps_jpos", "eps_jvel", "eps_gyro", "eps_pg")]
+
+
+class KbsEpisodeView(C.Structure):
+    _fields_ = [(k, _vp) for k in ("jpos_bias", "pg_lag", "pg_bias", "kp", "kd", "tau_limit", "action_bias",
+                                   "torque_bias")]
+
+
+class KbsNetWeights(C.Structure):
+    _fields_ = [("w_in", _vp), ("b_in", _vp), ("w_ih", _vp * MAX_DEPTH), ("w_hh", _vp * MAX_DEPTH),
+                ("b", _vp * MAX_DEPTH), ("w_out", _vp), ("b_out", _vp)]
+
+
+class KbsActorOut(C.Structure):
+    _fields_ = [(k, _vp) for k in ("action", "mean", "std", "log_prob", "entropy")]
+
+
+class KbsTrajView(C.Structure):
+    _fields_ = [("state", KbsStateView), ("command", _vp), ("ctrl", _vp), ("done", _vp), ("T", _i64)]
+
+
+class KbsRewardCarry(C.Structure):
+    _fields_ = [("t_single", _vp), ("airtime", _vp), ("prev_contact", _vp)]
+
+
+class KbsRolloutIO(C.Structure):
+    _fields_ = [("state", KbsStateView), ("noise", KbsNoiseView), ("episode", KbsEpisodeView)] + [
+        (k, _vp) for k in ("eps_action", "u_switch", "cmd_mode", "cmd_u6", "cmd_u_arms", "command", "pg_carry",
+                           "actor_carry", "critic_carry", "lpf", "actor_obs", "action", "log_prob", "ctrl",
+                           "term_codes", "done", "success", "value")] + [("T", _i64)]
+
+
+# every symbol include/kbotstep.h declares (tests check the .so exports all of them)
+EXPORTS = (
+    "kbs_version", "kbs_error_string", "kbs_default_params", "kbs_create", "kbs_destroy", "kbs_get_params",
+    "kbs_weights_pack", "kbs_observations", "kbs_command_update", "kbs_actor_step", "kbs_critic_step",
+    "kbs_torque", "kbs_terminate", "kbs_rewards", "kbs_gae", "kbs_policy_step", "kbs_rollout",
+    "kbs_launch_count",
+)
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libkbotstep.so.  Raises (never falls back) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make`). kbot-joystick_b200 has no CPU fallback.")
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    P = C.POINTER
+    lib.kbs_version.restype = C.c_int
+    lib.kbs_error_string.restype = C.c_char_p
+    lib.kbs_error_string.argtypes = [C.c_int]
+    lib.kbs_default_params.argtypes = [P(KbsParams)]
+    lib.kbs_create.argtypes = [P(KbsParams), P(_vp)]
+    lib.kbs_destroy.argtypes = [_vp]
+    lib.kbs_get_params.argtypes = [_vp, P(KbsParams)]
+    lib.kbs_weights_pack.argtypes = [_vp, C.c_int, P(KbsNetWeights), _vp]
+    lib.kbs_observations.argtypes = [_vp, P(KbsStateView), P(KbsNoiseView), P(KbsEpisodeView), _vp, _vp, _vp, _vp,
+                                     _vp, _i64, _vp]
+    lib.kbs_command_update.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]
+    lib.kbs_actor_step.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, P(KbsActorOut), _i64, _vp]
+    lib.kbs_critic_step.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]
+    lib.kbs_torque.argtypes = [_vp, _vp, P(KbsStateView), P(KbsEpisodeView), _vp, _i64, _vp]
+    lib.kbs_terminate.argtypes = [_vp, P(KbsStateView), _vp, _vp, _vp, _vp, _i64, _vp]
+    lib.kbs_rewards.argtypes = [_vp, P(KbsTrajView), P(KbsRewardCarry), _vp, _vp, _i64, _vp]
+    lib.kbs_gae.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]
+    lib.kbs_policy_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
+    lib.kbs_rollout.argtypes = [_vp, P(KbsRolloutIO), _i64, _vp]
+    lib.kbs_launch_count.argtypes = [_vp]
+    lib.kbs_launch_count.restype = _i64
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("kbs_error_string", "kbs_launch_count"):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().kbs_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed: [{rc}] {msg}")
+
+
+def default_params() -> KbsParams:
+    p = KbsParams()
+    check(load().kbs_default_params(C.byref(p)), "kbs_default_params")
+    return p
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "kbotstep takes contiguous CUDA tensors"
+    return t.data_ptr()

@@ -1,0 +1,373 @@
+// kbs_api.cu -- the extern "C" boundary of libkbotstep.so (include/kbotstep.h): argument validation, scratch
+// management and stage orchestration.  No CPU fallback: every entry point enqueues sm_100a kernels or fails.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "kbs_common.cuh"
+
+namespace {
+
+inline int64_t round_up4(int64_t n) { return (n + 3) / 4 * 4; }
+
+int check_ld(int64_t ld, int64_t n) {
+  if (n <= 0) return KBS_E_SHAPE;
+  if (ld < round_up4(n)) return KBS_E_SHAPE;
+  if (ld % 4) return KBS_E_ALIGN;
+  return KBS_OK;
+}
+
+#define REQ(p)            \
+  do {                    \
+    if (!(p)) return KBS_E_NULL; \
+  } while (0)
+#define AL(p)                                     \
+  do {                                            \
+    if ((p) && !kbs_aligned16(p)) return KBS_E_ALIGN; \
+  } while (0)
+
+int check_state(const kbs_state_view* s, int64_t n, bool need_priv) {
+  REQ(s);
+  REQ(s->qpos); REQ(s->qvel);
+  int rc = check_ld(s->ld, n);
+  if (rc) return rc;
+  AL(s->qpos); AL(s->qvel); AL(s->sensordata); AL(s->xpos); AL(s->xquat); AL(s->cinert); AL(s->cvel);
+  AL(s->actuator_force); AL(s->com_distance); AL(s->time);
+  if (need_priv) { REQ(s->sensordata); REQ(s->xpos); REQ(s->xquat); }
+  return KBS_OK;
+}
+
+kbs_state_view state_at(const kbs_state_view& s, int64_t t) {
+  kbs_state_view o = s;
+  const int64_t ld = s.ld;
+  if (s.qpos) o.qpos = s.qpos + t * KBS_NQ * ld;
+  if (s.qvel) o.qvel = s.qvel + t * KBS_NV * ld;
+  if (s.sensordata) o.sensordata = s.sensordata + t * KBS_NSENSORDATA * ld;
+  if (s.xpos) o.xpos = s.xpos + t * 3 * KBS_NBODY * ld;
+  if (s.xquat) o.xquat = s.xquat + t * 4 * KBS_NBODY * ld;
+  if (s.cinert) o.cinert = s.cinert + t * 10 * KBS_NBODY * ld;
+  if (s.cvel) o.cvel = s.cvel + t * 6 * KBS_NBODY * ld;
+  if (s.actuator_force) o.actuator_force = s.actuator_force + t * KBS_NUM_JOINTS * ld;
+  if (s.com_distance) o.com_distance = s.com_distance + t * ld;
+  if (s.time) o.time = s.time + t * ld;
+  return o;
+}
+
+kbs_noise_view noise_at(const kbs_noise_view& z, int64_t t, int64_t ld) {
+  kbs_noise_view o = z;
+  if (z.eps_jpos) o.eps_jpos = z.eps_jpos + t * 20 * ld;
+  if (z.eps_jvel) o.eps_jvel = z.eps_jvel + t * 20 * ld;
+  if (z.eps_gyro) o.eps_gyro = z.eps_gyro + t * 3 * ld;
+  if (z.eps_pg) o.eps_pg = z.eps_pg + t * 3 * ld;
+  return o;
+}
+
+int trunk(kbs_handle* h, int net, const float* obs, int64_t ld, float* carry, const uint8_t* done, float* out_rm,
+          int64_t n, cudaStream_t st) {
+  if (h->p.gemm_path == KBS_GEMM_TC_3XTF32) return kbs_tc_trunk(h, net, obs, ld, carry, done, out_rm, n, st);
+  return kbs_simt_trunk(h, net, obs, ld, carry, done, out_rm, n, st);
+}
+
+constexpr int kOutLd = 64;  // row stride of the trunk output buffer
+
+}  // namespace
+
+int kbs_scratch_reserve(kbs_handle* h, size_t floats) {
+  if (floats <= h->scratch_floats) return KBS_OK;
+  if (h->scratch) { KBS_CUDA_TRY(cudaFree(h->scratch)); h->scratch = nullptr; h->scratch_floats = 0; }
+  const size_t want = floats + floats / 8 + 1024;
+  KBS_CUDA_TRY(cudaMalloc(&h->scratch, want * sizeof(float)));
+  h->scratch_floats = want;
+  return KBS_OK;
+}
+
+extern "C" {
+
+int kbs_version(void) { return KBS_VERSION; }
+
+const char* kbs_error_string(int code) {
+  switch (code) {
+    case KBS_OK: return "ok";
+    case KBS_E_NULL: return "required pointer is NULL";
+    case KBS_E_SHAPE: return "unsupported shape (n_envs / ld / T / hidden_size)";
+    case KBS_E_ALIGN: return "pointer not 16-byte aligned or ld % 4 != 0";
+    case KBS_E_STATE: return "handle not ready (weights not packed, or datapath unavailable)";
+    case KBS_E_PARAM: return "bad scalar parameter";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown kbs error";
+  }
+}
+
+int kbs_default_params(kbs_params* p) {
+  REQ(p);
+  memset(p, 0, sizeof(*p));
+  p->hidden_size = 256; p->depth = 2; p->gemm_path = KBS_GEMM_SIMT_FP32; p->normalize_advantages = 0;
+  p->ctrl_dt = 0.02f; p->min_std = 0.01f; p->max_std = 1.0f; p->var_scale = 0.5f;
+  {
+    const double w = 2.0 * M_PI * 10.0, dt = 0.02;   // cutoff_frequency = 10 Hz, train.py:90-93
+    p->lpf_alpha = (float)(w * dt / (1.0 + w * dt));
+  }
+  p->gamma = 0.94f; p->lam = 0.94f; p->adv_eps = 1e-6f;
+  p->jpos_noise_mag = (float)(3.0 * M_PI / 180.0); p->jvel_noise_mag = (float)(15.0 * M_PI / 180.0);
+  p->gyro_noise_std = (float)(10.0 * M_PI / 180.0); p->pg_noise_std = (float)(3.0 * M_PI / 180.0);
+  p->gravity = 9.81f; p->eps_quat = 1e-6f;
+  p->unhealthy_z = 0.4f; p->max_tilt = (float)(45.0 * M_PI / 180.0); p->max_length_sec = 12.0f;
+  p->switch_prob = (float)(0.02 / 5);
+  const float lo[6] = {-0.5f, -0.5f, -1.0f, -0.25f, -0.25f, -0.25f};
+  const float hi[6] = {1.2f, 0.5f, 1.0f, 0.05f, 0.25f, 0.25f};
+  memcpy(p->cmd_lo, lo, sizeof(lo)); memcpy(p->cmd_hi, hi, sizeof(hi));
+  const double deg[20] = {20, 0, 0, 50, -30, -20, -0.0, 0, -50, 30, 0, -10, 0, 90, 0, 0, 10, 0, -90, 0};
+  const double lim[20][2] = {{-1.047198, 2.216568}, {-0.20944, 2.268928}, {-1.570796, 1.570796}, {0.0, 2.70526},
+                             {-1.134464, 0.261799}, {-2.216568, 1.047198}, {-2.268928, 0.20944}, {-1.570796, 1.570796},
+                             {-2.70526, 0.0}, {-0.261799, 1.134464}, {-3.490658, 1.047198}, {-1.658063, 0.436332},
+                             {-1.671886, 1.671886}, {0.0, 2.478368}, {-1.37881, 1.37881}, {-1.047198, 3.490658},
+                             {-0.436332, 1.658063}, {-1.671886, 1.671886}, {-2.478368, 0.0}, {-1.37881, 1.37881}};
+  for (int j = 0; j < 20; ++j) {
+    const float b = (float)(deg[j] * M_PI / 180.0), mn = (float)lim[j][0], mx = (float)lim[j][1];
+    p->joint_bias[j] = b;
+    p->joint_range[j] = fmaxf(b - mn, mx - b);   // evaluated in fp32 like jnp (train.py:1332)
+    if (j >= 10) { p->arm_lo[j - 10] = mn; p->arm_hi[j - 10] = mx; }
+  }
+  const float kp[20] = {150, 200, 100, 150, 40, 150, 200, 100, 150, 40, 100, 100, 40, 40, 20, 100, 100, 40, 40, 20};
+  const float kd[20] = {24.722f, 26.387f, 3.419f, 8.654f, 0.990f, 24.722f, 26.387f, 3.419f, 8.654f, 0.990f,
+                        8.284f, 8.257f, 0.945f, 1.266f, 0.295f, 8.284f, 8.257f, 0.945f, 1.266f, 0.295f};
+  const float cl[20] = {120, 60, 60, 120, 17, 120, 60, 60, 120, 17, 60, 60, 17, 17, 14, 60, 60, 17, 17, 14};
+  memcpy(p->kp, kp, sizeof(kp)); memcpy(p->kd, kd, sizeof(kd)); memcpy(p->ctrl_limit, cl, sizeof(cl));
+  const float rs[12] = {0.2f, 0.1f, 0.2f, 0.2f, 0.2f, 0.1f, 0.1f, 1.5f, 0.1f, 0.05f, 0.1f, 0.1f};
+  memcpy(p->reward_scale, rs, sizeof(rs));
+  p->linvel_es = 0.2f; p->angvel_es = 0.2f; p->rp_es = 0.03f; p->rp_es_zero = 0.01f; p->bh_es = 0.02f;
+  p->bh_standard = 0.80f; p->bh_foot_origin = 0.06f; p->arm_es = 0.1f; p->grace_period = 2.0f;
+  p->touchdown_penalty = 0.4f; p->feet_es = 0.02f; p->com_es = 0.04f; p->acc_es = 5.0f; p->torque_es = 5.0f;
+  p->body_base = 1; p->body_lfoot = 7; p->body_rfoot = 12;
+  p->sd_gyro = 19; p->sd_imu_quat = 28; p->sd_touch_l = 47; p->sd_touch_r = 48;
+  return KBS_OK;
+}
+
+int kbs_create(const kbs_params* p, kbs_handle** out) {
+  REQ(p); REQ(out);
+  if (p->hidden_size != 128 && p->hidden_size != 256) return KBS_E_SHAPE;
+  if (p->depth < 1 || p->depth > KBS_MAX_DEPTH) return KBS_E_SHAPE;
+  if (p->gemm_path != KBS_GEMM_TC_3XTF32 && p->gemm_path != KBS_GEMM_SIMT_FP32) return KBS_E_PARAM;
+  int dev = 0;
+  KBS_CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  KBS_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    fprintf(stderr, "libkbotstep: device %d is sm_%d%d; this library is built for sm_100a only\n", dev, prop.major,
+            prop.minor);
+    return (int)cudaErrorNoKernelImageForDevice;
+  }
+  kbs_handle* h = new (std::nothrow) kbs_handle();
+  if (!h) return (int)cudaErrorMemoryAllocation;
+  h->p = *p;
+  h->device = dev;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return KBS_OK;
+}
+
+int kbs_destroy(kbs_handle* h) {
+  if (!h) return KBS_OK;
+  for (int k = 0; k < 2; ++k) {
+    KbsNet& N = h->net[k];
+    cudaFree(N.w_in); cudaFree(N.b_in); cudaFree(N.w_out); cudaFree(N.b_out); cudaFree(N.tc_image);
+    for (int l = 0; l < KBS_MAX_DEPTH; ++l) { cudaFree(N.w_ih[l]); cudaFree(N.w_hh[l]); cudaFree(N.b[l]); }
+  }
+  cudaFree(h->scratch);
+  delete h;
+  return KBS_OK;
+}
+
+int kbs_get_params(const kbs_handle* h, kbs_params* out) {
+  REQ(h); REQ(out);
+  *out = h->p;
+  return KBS_OK;
+}
+
+int64_t kbs_launch_count(const kbs_handle* h) { return h ? h->launches : -1; }
+
+int kbs_weights_pack(kbs_handle* h, int net, const kbs_net_weights* w, void* stream) {
+  REQ(h); REQ(w);
+  if (net != KBS_NET_ACTOR && net != KBS_NET_CRITIC) return KBS_E_PARAM;
+  REQ(w->w_in); REQ(w->b_in); REQ(w->w_out); REQ(w->b_out);
+  for (int l = 0; l < h->p.depth; ++l) { REQ(w->w_ih[l]); REQ(w->w_hh[l]); REQ(w->b[l]); }
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = kbs_simt_pack(h, net, w, st);
+  if (rc) return rc;
+  if (h->p.gemm_path == KBS_GEMM_TC_3XTF32) rc = kbs_tc_pack(h, net, st);
+  return rc;
+}
+
+int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_view* noise,
+                     const kbs_episode_view* ep, const float* command, float* pg_carry, float* computed,
+                     float* actor_obs, float* critic_obs, int64_t n, void* stream) {
+  REQ(h); REQ(command);
+  int rc = check_state(s, n, true);
+  if (rc) return rc;
+  if (critic_obs) { REQ(s->cinert); REQ(s->cvel); REQ(s->actuator_force); }
+  if (noise && noise->eps_jpos) { REQ(noise->eps_jvel); REQ(noise->eps_gyro); REQ(noise->eps_pg); }
+  AL(command); AL(pg_carry); AL(computed); AL(actor_obs); AL(critic_obs);
+  if (!computed && !actor_obs && !critic_obs) return KBS_E_NULL;
+  return kbs_launch_observations(h, *s, noise, ep, command, pg_carry, computed, actor_obs, critic_obs, n,
+                                 (cudaStream_t)stream);
+}
+
+int kbs_command_update(kbs_handle* h, float* command, const float* u_switch, const int32_t* mode, const float* u6,
+                       const float* u_arms, int64_t ld, int64_t n, void* stream) {
+  REQ(h); REQ(command); REQ(mode); REQ(u6); REQ(u_arms);
+  int rc = check_ld(ld, n);
+  if (rc) return rc;
+  AL(command); AL(u_switch); AL(mode); AL(u6); AL(u_arms);
+  return kbs_launch_command(h, command, command, u_switch, mode, u6, u_arms, nullptr, ld, n, (cudaStream_t)stream);
+}
+
+int kbs_actor_step(kbs_handle* h, const float* obs, int64_t ld, float* carry, float* lpf, const float* eps,
+                   const float* action_in, const uint8_t* done, const kbs_actor_out* out, int64_t n, void* stream) {
+  REQ(h); REQ(obs); REQ(carry); REQ(lpf); REQ(out);
+  int rc = check_ld(ld, n);
+  if (rc) return rc;
+  AL(obs); AL(carry); AL(lpf); AL(eps); AL(action_in);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ts = kbs_simt_scratch_floats(h, n);
+  if ((rc = kbs_scratch_reserve(h, ts + size_t(n) * kOutLd))) return rc;
+  float* out_rm = h->scratch + ts;
+  if ((rc = trunk(h, KBS_NET_ACTOR, obs, ld, carry, done, out_rm, n, st))) return rc;
+  return kbs_launch_actor_head(h, out_rm, kOutLd, obs, ld, lpf, eps, action_in, done, *out, n, st);
+}
+
+int kbs_critic_step(kbs_handle* h, const float* obs, int64_t ld, float* carry, const uint8_t* done, float* value,
+                    int64_t n, void* stream) {
+  REQ(h); REQ(obs); REQ(carry); REQ(value);
+  int rc = check_ld(ld, n);
+  if (rc) return rc;
+  AL(obs); AL(carry);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ts = kbs_simt_scratch_floats(h, n);
+  if ((rc = kbs_scratch_reserve(h, ts + size_t(n) * kOutLd))) return rc;
+  float* out_rm = h->scratch + ts;
+  if ((rc = trunk(h, KBS_NET_CRITIC, obs, ld, carry, done, out_rm, n, st))) return rc;
+  return kbs_launch_critic_head(h, out_rm, kOutLd, value, n, st);
+}
+
+int kbs_torque(kbs_handle* h, const float* action, const kbs_state_view* s, const kbs_episode_view* ep,
+               float* ctrl_out, int64_t n, void* stream) {
+  REQ(h); REQ(action); REQ(ctrl_out);
+  int rc = check_state(s, n, false);
+  if (rc) return rc;
+  AL(action); AL(ctrl_out);
+  return kbs_launch_torque(h, action, *s, ep, ctrl_out, n, (cudaStream_t)stream);
+}
+
+int kbs_terminate(kbs_handle* h, const kbs_state_view* s, int32_t* codes, uint8_t* done, uint8_t* success, float* pre,
+                  int64_t n, void* stream) {
+  REQ(h);
+  int rc = check_state(s, n, false);
+  if (rc) return rc;
+  REQ(s->xpos); REQ(s->time);
+  AL(codes); AL(pre);
+  if ((reinterpret_cast<uintptr_t>(done) & 3u) || (reinterpret_cast<uintptr_t>(success) & 3u)) return KBS_E_ALIGN;
+  return kbs_launch_terminate(h, *s, codes, done, success, pre, n, (cudaStream_t)stream);
+}
+
+int kbs_rewards(kbs_handle* h, const kbs_traj_view* traj, const kbs_reward_carry* carry, float* total,
+                float* components, int64_t n, void* stream) {
+  REQ(h); REQ(traj); REQ(carry); REQ(total);
+  if (traj->T <= 0 || traj->T > 65535) return KBS_E_SHAPE;
+  int rc = check_state(&traj->state, n, true);
+  if (rc) return rc;
+  REQ(traj->state.com_distance); REQ(traj->command); REQ(traj->ctrl); REQ(traj->done);
+  REQ(carry->t_single); REQ(carry->airtime); REQ(carry->prev_contact);
+  AL(traj->command); AL(traj->ctrl); AL(total); AL(components);
+  if (reinterpret_cast<uintptr_t>(traj->done) & 3u) return KBS_E_ALIGN;
+  return kbs_launch_rewards(h, *traj, *carry, total, components, n, (cudaStream_t)stream);
+}
+
+int kbs_gae(kbs_handle* h, const float* values, const float* rewards, const uint8_t* done, const uint8_t* success,
+            float* advantages, float* value_targets, int64_t T, int64_t ld, int64_t n, void* stream) {
+  REQ(h); REQ(values); REQ(rewards); REQ(done); REQ(success); REQ(advantages); REQ(value_targets);
+  if (T <= 0) return KBS_E_SHAPE;
+  if (n <= 0 || ld < n) return KBS_E_SHAPE;
+  return kbs_launch_gae(h, values, rewards, done, success, advantages, value_targets, T, ld, n, (cudaStream_t)stream);
+}
+
+int kbs_policy_step(kbs_handle* h, const float* joint_angles, const float* joint_vel, const float* projected_gravity,
+                    const float* gyro, const float* command, const float* carry_in, float* carry_out,
+                    float* action_out, int64_t n, void* stream) {
+  REQ(h); REQ(joint_angles); REQ(joint_vel); REQ(projected_gravity); REQ(gyro); REQ(command); REQ(carry_in);
+  REQ(carry_out); REQ(action_out);
+  if (n <= 0) return KBS_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = h->p.hidden_size, d2 = 2 * h->p.depth;
+  const int64_t ld = round_up4(n);
+  const size_t ts = kbs_simt_scratch_floats(h, n);
+  const size_t need = ts + size_t(n) * kOutLd + size_t(KBS_ACTOR_OBS + 20 + 20) * ld + size_t(d2) * n * H + 64;
+  int rc = kbs_scratch_reserve(h, need);
+  if (rc) return rc;
+  float* out_rm = h->scratch + ts;
+  float* obs = out_rm + size_t(n) * kOutLd;
+  float* lpf = obs + size_t(KBS_ACTOR_OBS) * ld;
+  float* mean = lpf + 20 * ld;
+  float* carry = mean + 20 * ld;
+  if ((rc = kbs_launch_policy_pack(h, joint_angles, joint_vel, projected_gravity, gyro, command, carry_in, obs, carry,
+                                   lpf, ld, n, st)))
+    return rc;
+  if ((rc = trunk(h, KBS_NET_ACTOR, obs, ld, carry, nullptr, out_rm, n, st))) return rc;
+  kbs_actor_out o{};
+  o.mean = mean;
+  if ((rc = kbs_launch_actor_head(h, out_rm, kOutLd, obs, ld, lpf, nullptr, nullptr, nullptr, o, n, st))) return rc;
+  return kbs_launch_policy_unpack(h, carry, lpf, mean, carry_out, action_out, ld, n, st);
+}
+
+int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n, void* stream) {
+  REQ(h); REQ(io);
+  if (io->T <= 0) return KBS_E_SHAPE;
+  int rc = check_state(&io->state, n, true);
+  if (rc) return rc;
+  REQ(io->state.time); REQ(io->command); REQ(io->actor_carry); REQ(io->lpf); REQ(io->action); REQ(io->ctrl);
+  REQ(io->done); REQ(io->success); REQ(io->cmd_mode); REQ(io->cmd_u6); REQ(io->cmd_u_arms); REQ(io->u_switch);
+  if (io->value) { REQ(io->critic_carry); REQ(io->state.cinert); REQ(io->state.cvel); REQ(io->state.actuator_force); }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ld = io->state.ld;
+  const size_t ts = kbs_simt_scratch_floats(h, n);
+  const size_t need = ts + size_t(n) * kOutLd + size_t(KBS_ACTOR_OBS + KBS_CRITIC_OBS) * ld + 64;
+  if ((rc = kbs_scratch_reserve(h, need))) return rc;
+  float* out_rm = h->scratch + ts;
+  float* aobs_scratch = out_rm + size_t(n) * kOutLd;
+  float* cobs = aobs_scratch + size_t(KBS_ACTOR_OBS) * ld;
+
+  for (int64_t t = 0; t < io->T; ++t) {
+    const kbs_state_view s = state_at(io->state, t);
+    const kbs_noise_view nz = noise_at(io->noise, t, ld);
+    const float* cmd_t = io->command + t * KBS_NUM_COMMANDS * ld;
+    float* cmd_n = io->command + (t + 1) * KBS_NUM_COMMANDS * ld;
+    float* aobs = io->actor_obs ? io->actor_obs + t * KBS_ACTOR_OBS * ld : aobs_scratch;
+    uint8_t* done_t = io->done + t * ld;
+    // terminations of the recorded state decide which carries reset after this step (train.py:1502-1506)
+    if ((rc = kbs_launch_terminate(h, s, io->term_codes ? io->term_codes + t * 3 * ld : nullptr, done_t,
+                                   io->success + t * ld, nullptr, n, st)))
+      return rc;
+    if ((rc = kbs_launch_observations(h, s, &nz, &io->episode, cmd_t, io->pg_carry, nullptr, aobs,
+                                      io->value ? cobs : nullptr, n, st)))
+      return rc;
+    if ((rc = trunk(h, KBS_NET_ACTOR, aobs, ld, io->actor_carry, done_t, out_rm, n, st))) return rc;
+    kbs_actor_out o{};
+    o.action = io->action + t * KBS_NUM_JOINTS * ld;
+    o.log_prob = io->log_prob ? io->log_prob + t * ld : nullptr;
+    if ((rc = kbs_launch_actor_head(h, out_rm, kOutLd, aobs, ld, io->lpf,
+                                    io->eps_action ? io->eps_action + t * KBS_NUM_JOINTS * ld : nullptr, nullptr, done_t,
+                                    o, n, st)))
+      return rc;
+    if ((rc = kbs_launch_torque(h, o.action, s, &io->episode, io->ctrl + t * KBS_NUM_JOINTS * ld, n, st))) return rc;
+    if (io->value) {
+      if ((rc = trunk(h, KBS_NET_CRITIC, cobs, ld, io->critic_carry, done_t, out_rm, n, st))) return rc;
+      if ((rc = kbs_launch_critic_head(h, out_rm, kOutLd, io->value + t * ld, n, st))) return rc;
+    }
+    if ((rc = kbs_launch_command(h, cmd_t, cmd_n, io->u_switch + t * ld, io->cmd_mode + t * ld,
+                                 io->cmd_u6 + t * 6 * ld, io->cmd_u_arms + t * 10 * ld, done_t, ld, n, st)))
+      return rc;
+  }
+  return KBS_OK;
+}
+
+}  // extern "C"

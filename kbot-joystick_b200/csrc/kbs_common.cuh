@@ -1,0 +1,113 @@
+// kbs_common.cuh -- shared definitions for libkbotstep (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kbotstep.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libkbotstep is written for sm_100a (B200) only"
+#endif
+
+#define KBS_CUDA_TRY(expr)                      \
+  do {                                          \
+    cudaError_t _e = (expr);                    \
+    if (_e != cudaSuccess) return (int)_e;      \
+  } while (0)
+
+#define KBS_LAUNCH_CHECK()                      \
+  do {                                          \
+    cudaError_t _e = cudaPeekAtLastError();     \
+    if (_e != cudaSuccess) return (int)_e;      \
+  } while (0)
+
+// Packed network held by the handle.
+struct KbsNet {
+  bool packed = false;
+  int num_in = 0, num_out = 0;  // logical sizes (65/40, 475/1)
+  int kin_pad = 0;              // num_in rounded up to 16
+  int nout_pad = 0;             // num_out rounded up to 64 (SIMT) / 16 (TC)
+  // fp32 copies in eqx [out][in] layout, K padded (SIMT path + source for the TC pack)
+  float* w_in = nullptr;   // [H][kin_pad]
+  float* b_in = nullptr;   // [H]
+  float* w_ih[KBS_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};  // [4H][H]
+  float* w_hh[KBS_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};  // [4H][H]
+  float* b[KBS_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};     // [4H]
+  float* w_out = nullptr;  // [nout_pad][H]
+  float* b_out = nullptr;  // [nout_pad]
+  // tcgen05 path: one contiguous image of UMMA-ready operand tiles (see kbs_net_tc.cu)
+  float* tc_image = nullptr;
+  size_t tc_image_floats = 0;
+};
+
+struct kbs_handle {
+  kbs_params p;
+  int device = 0;
+  int num_sms = 148;
+  KbsNet net[2];
+  // scratch, grown on demand (never during stream capture: warm up first)
+  float* scratch = nullptr;
+  size_t scratch_floats = 0;
+  int64_t launches = 0;
+};
+
+// scratch management (kbs_api.cu)
+int kbs_scratch_reserve(kbs_handle* h, size_t floats);
+
+// ---- stage launchers implemented across the translation units -------------------------------------
+// kbs_elementwise.cu
+int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_noise_view* nz,
+                            const kbs_episode_view* ep, const float* command, float* pg_carry, float* computed,
+                            float* actor_obs, float* critic_obs, int64_t n, cudaStream_t st);
+int kbs_launch_command(kbs_handle* h, const float* cmd_in, float* cmd_out, const float* u_switch,
+                       const int32_t* mode, const float* u6, const float* u_arms, const uint8_t* done, int64_t ld,
+                       int64_t n, cudaStream_t st);
+int kbs_launch_torque(kbs_handle* h, const float* action, const kbs_state_view& s, const kbs_episode_view* ep,
+                      float* ctrl, int64_t n, cudaStream_t st);
+int kbs_launch_terminate(kbs_handle* h, const kbs_state_view& s, int32_t* codes, uint8_t* done, uint8_t* success,
+                         float* pre, int64_t n, cudaStream_t st);
+int kbs_launch_rewards(kbs_handle* h, const kbs_traj_view& tr, const kbs_reward_carry& carry, float* total,
+                       float* components, int64_t n, cudaStream_t st);
+int kbs_launch_gae(kbs_handle* h, const float* values, const float* rewards, const uint8_t* done,
+                   const uint8_t* success, float* adv, float* targets, int64_t T, int64_t ld, int64_t n,
+                   cudaStream_t st);
+int kbs_launch_policy_pack(kbs_handle* h, const float* ja, const float* jv, const float* pg, const float* gyro,
+                           const float* cmd, const float* carry_in, float* obs_soa, float* carry_aos, float* lpf_soa,
+                           int64_t ld, int64_t n, cudaStream_t st);
+int kbs_launch_policy_unpack(kbs_handle* h, const float* carry_aos, const float* lpf_soa, const float* mean_soa,
+                             float* carry_out, float* action_out, int64_t ld, int64_t n, cudaStream_t st);
+
+// kbs_net_simt.cu : fp32 FFMA datapath
+int kbs_simt_pack(kbs_handle* h, int net, const kbs_net_weights* w, cudaStream_t st);
+int kbs_simt_trunk(kbs_handle* h, int net, const float* obs_soa, int64_t ld, float* carry, const uint8_t* done,
+                   float* out_rowmajor /*[n][nout_pad]*/, int64_t n, cudaStream_t st);
+size_t kbs_simt_scratch_floats(const kbs_handle* h, int64_t n);
+
+// kbs_net_tc.cu : tcgen05 3xTF32 datapath
+int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st);
+int kbs_tc_trunk(kbs_handle* h, int net, const float* obs_soa, int64_t ld, float* carry, const uint8_t* done,
+                 float* out_rowmajor, int64_t n, cudaStream_t st);
+
+// heads (kbs_net_simt.cu): consume out_rowmajor
+int kbs_launch_actor_head(kbs_handle* h, const float* out_rm, int ldo, const float* obs_soa, int64_t ld, float* lpf,
+                          const float* eps, const float* action_in, const uint8_t* done, const kbs_actor_out& o,
+                          int64_t n, cudaStream_t st);
+int kbs_launch_critic_head(kbs_handle* h, const float* out_rm, int ldo, float* value, int64_t n, cudaStream_t st);
+
+// ---- device helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void kbs_ld4(const float* __restrict__ base, int64_t row, int64_t ld, int64_t n0,
+                                        float (&v)[4]) {
+  const float4 t = __ldcs(reinterpret_cast<const float4*>(base + row * ld + n0));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void kbs_st4(float* __restrict__ base, int64_t row, int64_t ld, int64_t n0,
+                                        const float (&v)[4]) {
+  __stcs(reinterpret_cast<float4*>(base + row * ld + n0), make_float4(v[0], v[1], v[2], v[3]));
+}
+__device__ __forceinline__ void kbs_copy4(const float* __restrict__ src, int64_t srow, float* __restrict__ dst,
+                                          int64_t drow, int64_t ld, int64_t n0) {
+  __stcs(reinterpret_cast<float4*>(dst + drow * ld + n0),
+         __ldcs(reinterpret_cast<const float4*>(src + srow * ld + n0)));
+}
+
+static inline bool kbs_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

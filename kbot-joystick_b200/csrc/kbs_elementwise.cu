@@ -1,0 +1,838 @@
+// kbs_elementwise.cu -- HBM-bound stages of the control step: observations, command law, PD torque map,
+// terminations, the 12 reward terms and the GAE scan.  Env-major SoA, float4 per thread (4 consecutive envs),
+// streaming loads/stores.  Compiled with -fmad=false so the operation order is exactly the one written here
+// (the reference's jnp expressions, train.py line ranges cited per kernel); HBM-bound, FMA rate is irrelevant.
+#include <math.h>
+
+#include "kbs_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr float kHalfPi = 1.57079632679489662f;
+constexpr float kPi = 3.14159265358979324f;
+
+// ---- xax quaternion helpers, (w,x,y,z) -------------------------------------------
+__device__ __forceinline__ void quat_norm_eps(float (&q)[4], float eps) {
+  const float n = sqrtf(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]) + eps;
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+
+__device__ __forceinline__ void quat_to_euler(const float (&qin)[4], float eps, float (&e)[3]) {
+  float q[4] = {qin[0], qin[1], qin[2], qin[3]};
+  quat_norm_eps(q, eps);
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  e[0] = atan2f(2.0f * (w * x + y * z), 1.0f - 2.0f * (x * x + y * y));
+  const float sinp = 2.0f * (w * y - z * x);
+  e[1] = (fabsf(sinp) >= 1.0f) ? copysignf(kHalfPi, sinp) : asinf(sinp);
+  e[2] = atan2f(2.0f * (w * z + x * y), 1.0f - 2.0f * (y * y + z * z));
+}
+
+__device__ __forceinline__ void euler_to_quat(float roll, float pitch, float yaw, float (&q)[4]) {
+  const float r = roll * 0.5f, p = pitch * 0.5f, y = yaw * 0.5f;
+  const float cr = cosf(r), sr = sinf(r), cp = cosf(p), sp = sinf(p), cy = cosf(y), sy = sinf(y);
+  q[0] = cr * cp * cy + sr * sp * sy;
+  q[1] = sr * cp * cy - cr * sp * sy;
+  q[2] = cr * sp * cy + sr * cp * sy;
+  q[3] = cr * cp * sy - sr * sp * cy;
+  const float n = sqrtf(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+
+__device__ __forceinline__ void rotate_vec(const float (&v)[3], const float (&qin)[4], bool inverse, float eps,
+                                           float (&o)[3]) {
+  float q[4] = {qin[0], qin[1], qin[2], qin[3]};
+  quat_norm_eps(q, eps);
+  const float w = q[0];
+  const float x = inverse ? -q[1] : q[1], y = inverse ? -q[2] : q[2], z = inverse ? -q[3] : q[3];
+  const float vx = v[0], vy = v[1], vz = v[2];
+  const float t = 2.0f;
+  o[0] = w * w * vx + t * y * w * vz - t * z * w * vy + x * x * vx + t * y * x * vy + t * z * x * vz - z * z * vx - y * y * vx;
+  o[1] = t * x * y * vx + y * y * vy + t * z * y * vz + t * w * z * vx - z * z * vy + w * w * vy - t * w * x * vz - x * x * vy;
+  o[2] = t * x * z * vx + t * y * z * vy + z * z * vz - t * w * y * vx + w * w * vz + t * w * x * vy - y * y * vz - x * x * vz;
+}
+
+__device__ __forceinline__ bool zero_cmd(float c0, float c1, float c2) {
+  return sqrtf((c0 * c0 + c1 * c1) + c2 * c2) < 1e-3f;
+}
+
+// encode_projected_gravity, train.py:1338-1349
+__device__ __forceinline__ void encode_pg(const float (&g)[3], float (&o)[5]) {
+  o[0] = atan2f(g[1], -g[2]);
+  o[1] = atan2f(-g[0], sqrtf(g[1] * g[1] + g[2] * g[2]));
+  const float n = sqrtf((g[0] * g[0] + g[1] * g[1]) + g[2] * g[2]);
+  o[2] = g[0] / n; o[3] = g[1] / n; o[4] = g[2] / n;
+}
+
+// =====================================================================================================
+// observations: get_observations table + run_actor / run_critic concats.
+// train.py:1155-1204, 682-707, 1329-1431.  grid = (env groups, 1 + copy sections).
+// =====================================================================================================
+constexpr int kCopyRowsPerSection = 46;  // 368 pure-copy rows (cinert 230 + cvel 138) in 8 sections
+
+__global__ void __launch_bounds__(kThreads)
+obs_kernel(const __grid_constant__ kbs_params P, const kbs_state_view s, const kbs_noise_view nz,
+           const kbs_episode_view ep, const float* __restrict__ command, float* __restrict__ pg_carry,
+           float* __restrict__ computed, float* __restrict__ actor_obs, float* __restrict__ critic_obs, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  const int64_t ld = s.ld;
+
+  if (blockIdx.y > 0) {
+    // critic privileged dump: center_of_mass_inertia = cinert[1:], center_of_mass_velocity = cvel[1:]
+    const int i0 = (blockIdx.y - 1) * kCopyRowsPerSection;
+#pragma unroll 8
+    for (int i = i0; i < i0 + kCopyRowsPerSection; ++i) {
+      if (i < 230) kbs_copy4(s.cinert, 10 + i, critic_obs, 80 + i, ld, n0);
+      else if (i < 368) kbs_copy4(s.cvel, 6 + (i - 230), critic_obs, 310 + (i - 230), ld, n0);
+    }
+    return;
+  }
+
+  const bool has_noise = nz.eps_jpos != nullptr;
+  float c[16][4];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) kbs_ld4(command, k, ld, n0, c[k]);
+  float zc[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) zc[l] = zero_cmd(c[0][l], c[1][l], c[2][l]) ? 1.0f : 0.0f;
+
+  // joints: slots 0-19 / 20-39
+#pragma unroll 4
+  for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+    float q[4], qd[4], jb[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0}, e2[4] = {0, 0, 0, 0};
+    kbs_ld4(s.qpos, 7 + j, ld, n0, q);
+    kbs_ld4(s.qvel, 6 + j, ld, n0, qd);
+    if (ep.jpos_bias) kbs_ld4(ep.jpos_bias, j, ld, n0, jb);
+    if (has_noise) { kbs_ld4(nz.eps_jpos, j, ld, n0, e1); kbs_ld4(nz.eps_jvel, j, ld, n0, e2); }
+    float bj[4], nbj[4], nv[4], a0[4], a1[4], c0[4], c1[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      bj[l] = q[l] + jb[l];
+      nbj[l] = bj[l] + P.jpos_noise_mag * e1[l];
+      nv[l] = qd[l] + P.jvel_noise_mag * e2[l];
+      a0[l] = (nbj[l] - P.joint_bias[j]) / P.joint_range[j];
+      a1[l] = nv[l] / 10.0f;
+      c0[l] = (q[l] - P.joint_bias[j]) / P.joint_range[j];
+      c1[l] = qd[l] / 10.0f;
+    }
+    if (computed) { kbs_st4(computed, j, ld, n0, bj); kbs_st4(computed, 20 + j, ld, n0, nbj); kbs_st4(computed, 40 + j, ld, n0, nv); }
+    if (actor_obs) { kbs_st4(actor_obs, j, ld, n0, a0); kbs_st4(actor_obs, 20 + j, ld, n0, a1); }
+    if (critic_obs) { kbs_st4(critic_obs, j, ld, n0, c0); kbs_st4(critic_obs, 20 + j, ld, n0, c1); }
+  }
+
+  // IMU: projected gravity (clean + lagged/biased/noisy twin) and gyro
+  {
+    float iq[4][4], gy[3][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) kbs_ld4(s.sensordata, P.sd_imu_quat + k, ld, n0, iq[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) kbs_ld4(s.sensordata, P.sd_gyro + k, ld, n0, gy[k]);
+    float lag[4] = {0, 0, 0, 0}, pgb[3][4] = {}, epg[3][4] = {}, egy[3][4] = {}, prev[3][4];
+    if (ep.pg_lag) kbs_ld4(ep.pg_lag, 0, ld, n0, lag);
+    if (ep.pg_bias) { for (int k = 0; k < 3; ++k) kbs_ld4(ep.pg_bias, k, ld, n0, pgb[k]); }
+    if (has_noise) {
+      for (int k = 0; k < 3; ++k) { kbs_ld4(nz.eps_pg, k, ld, n0, epg[k]); kbs_ld4(nz.eps_gyro, k, ld, n0, egy[k]); }
+    }
+    if (pg_carry) { for (int k = 0; k < 3; ++k) kbs_ld4(pg_carry, k, ld, n0, prev[k]); }
+    float o_pg[3][4], o_ipg[3][4], o_nipg[3][4], o_ngy[3][4], o_carry[3][4], enc_a[5][4], enc_c[5][4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float q[4] = {iq[0][l], iq[1][l], iq[2][l], iq[3][l]};
+      const float g[3] = {0.0f, 0.0f, -P.gravity};
+      float gb[3];
+      rotate_vec(g, q, true, P.eps_quat, gb);
+      float na[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float pv = pg_carry ? prev[k][l] : gb[k];
+        const float nc = lag[l] * pv + (1.0f - lag[l]) * gb[k];
+        o_carry[k][l] = nc;
+        o_pg[k][l] = gb[k];
+        o_ipg[k][l] = nc + pgb[k][l];
+        o_nipg[k][l] = o_ipg[k][l] + P.pg_noise_std * epg[k][l];
+        o_ngy[k][l] = gy[k][l] + P.gyro_noise_std * egy[k][l];
+        na[k] = o_nipg[k][l];
+      }
+      float ea[5], ec[5];
+      encode_pg(na, ea);
+      encode_pg(gb, ec);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) { enc_a[k][l] = ea[k]; enc_c[k][l] = ec[k]; }
+    }
+    if (pg_carry) { for (int k = 0; k < 3; ++k) kbs_st4(pg_carry, k, ld, n0, o_carry[k]); }
+    if (computed) {
+      for (int k = 0; k < 3; ++k) {
+        kbs_st4(computed, 60 + k, ld, n0, o_ngy[k]);
+        kbs_st4(computed, 69 + k, ld, n0, o_pg[k]);
+        kbs_st4(computed, 72 + k, ld, n0, o_ipg[k]);
+        kbs_st4(computed, 75 + k, ld, n0, o_nipg[k]);
+      }
+    }
+    if (actor_obs) {
+      for (int k = 0; k < 5; ++k) kbs_st4(actor_obs, 40 + k, ld, n0, enc_a[k]);
+      for (int k = 0; k < 3; ++k) kbs_st4(actor_obs, 45 + k, ld, n0, o_ngy[k]);
+    }
+    if (critic_obs) {
+      for (int k = 0; k < 5; ++k) kbs_st4(critic_obs, 40 + k, ld, n0, enc_c[k]);
+      for (int k = 0; k < 3; ++k) kbs_st4(critic_obs, 45 + k, ld, n0, gy[k]);
+    }
+  }
+
+  // zero_cmd flag + command: slots 48, 49-64
+  if (actor_obs) {
+    kbs_st4(actor_obs, 48, ld, n0, zc);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) kbs_st4(actor_obs, 49 + k, ld, n0, c[k]);
+  }
+  if (critic_obs) {
+    kbs_st4(critic_obs, 48, ld, n0, zc);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) kbs_st4(critic_obs, 49 + k, ld, n0, c[k]);
+  }
+
+  if (computed || critic_obs) {
+    // FeetPositionObservation train.py:682-699
+    float bp[3][4], lp[3][4], rp[3][4], bq[4][4], fpos[6][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      kbs_ld4(s.xpos, 3 * P.body_base + k, ld, n0, bp[k]);
+      kbs_ld4(s.xpos, 3 * P.body_lfoot + k, ld, n0, lp[k]);
+      kbs_ld4(s.xpos, 3 * P.body_rfoot + k, ld, n0, rp[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) kbs_ld4(s.xquat, 4 * P.body_base + k, ld, n0, bq[k]);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float q[4] = {bq[0][l], bq[1][l], bq[2][l], bq[3][l]};
+      float e[3], qy[4], o[3];
+      quat_to_euler(q, P.eps_quat, e);
+      euler_to_quat(0.0f, 0.0f, e[2], qy);
+      const float dl[3] = {lp[0][l] - bp[0][l], lp[1][l] - bp[1][l], lp[2][l] - bp[2][l]};
+      rotate_vec(dl, qy, true, P.eps_quat, o);
+      fpos[0][l] = o[0]; fpos[1][l] = o[1]; fpos[2][l] = o[2];
+      const float dr[3] = {rp[0][l] - bp[0][l], rp[1][l] - bp[1][l], rp[2][l] - bp[2][l]};
+      rotate_vec(dr, qy, true, P.eps_quat, o);
+      fpos[3][l] = o[0]; fpos[4][l] = o[1]; fpos[5][l] = o[2];
+    }
+    if (computed) { for (int k = 0; k < 6; ++k) kbs_st4(computed, 63 + k, ld, n0, fpos[k]); }
+    if (critic_obs) {
+      for (int k = 0; k < 6; ++k) kbs_st4(critic_obs, 67 + k, ld, n0, fpos[k]);
+      kbs_copy4(s.sensordata, P.sd_touch_l, critic_obs, 65, ld, n0);
+      kbs_copy4(s.sensordata, P.sd_touch_r, critic_obs, 66, ld, n0);
+      for (int k = 0; k < 7; ++k) kbs_copy4(s.qpos, k, critic_obs, 73 + k, ld, n0);   // base pos + quat
+      for (int k = 0; k < 6; ++k) kbs_copy4(s.qvel, k, critic_obs, 448 + k, ld, n0);  // base lin + ang vel
+#pragma unroll 4
+      for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+        float f[4];
+        kbs_ld4(s.actuator_force, j, ld, n0, f);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) f[l] = f[l] / 4.0f;
+        kbs_st4(critic_obs, 454 + j, ld, n0, f);
+      }
+      kbs_st4(critic_obs, 474, ld, n0, bp[2]);  // base_height = xpos[1, 2]
+    }
+  }
+}
+
+// =====================================================================================================
+// UnifiedCommand train.py:724-785
+// =====================================================================================================
+__global__ void __launch_bounds__(kThreads)
+command_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ cmd_in, float* __restrict__ cmd_out,
+               const float* __restrict__ u_switch, const int32_t* __restrict__ mode, const float* __restrict__ u6,
+               const float* __restrict__ u_arms, const uint8_t* __restrict__ done, int64_t ld, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  float us[4] = {-1.f, -1.f, -1.f, -1.f};  // NULL u_switch: always resample (initial_command)
+  if (u_switch) kbs_ld4(u_switch, 0, ld, n0, us);
+  if (done) {  // episode ended: ksim draws initial_command for the new episode
+    const uchar4 d4 = *reinterpret_cast<const uchar4*>(done + n0);
+    if (d4.x) us[0] = -1.f;
+    if (d4.y) us[1] = -1.f;
+    if (d4.z) us[2] = -1.f;
+    if (d4.w) us[3] = -1.f;
+  }
+  const int4 m4 = *reinterpret_cast<const int4*>(mode + n0);
+  const int md[4] = {m4.x, m4.y, m4.z, m4.w};
+  float v[6][4];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float u[4];
+    kbs_ld4(u6, k, ld, n0, u);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) v[k][l] = P.cmd_lo[k] + u[l] * (P.cmd_hi[k] - P.cmd_lo[k]);
+  }
+  // slots 0..5
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float prev[4], o[4];
+    kbs_ld4(cmd_in, k, ld, n0, prev);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int m = md[l];
+      bool on;
+      if (k == 0) on = (m == 0) || (m == 3);
+      else if (k == 1) on = (m == 1) || (m == 3);
+      else if (k == 2) on = (m == 2) || (m == 3);
+      else on = (m == 4);
+      const float nw = on ? v[k][l] : 0.0f;
+      o[l] = (us[l] < P.switch_prob) ? nw : prev[l];
+    }
+    kbs_st4(cmd_out, k, ld, n0, o);
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    float u[4], prev[4], o[4];
+    kbs_ld4(u_arms, k, ld, n0, u);
+    kbs_ld4(cmd_in, 6 + k, ld, n0, prev);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      // train.py:734-738: uniform() and bernoulli() share key rng_h => mask = (u < 0.5) on the same draw
+      const float arm = (P.arm_lo[k] + u[l] * (P.arm_hi[k] - P.arm_lo[k])) * ((u[l] < 0.5f) ? 1.0f : 0.0f);
+      const float nw = (md[l] == 3 || md[l] == 4) ? arm : 0.0f;
+      o[l] = (us[l] < P.switch_prob) ? nw : prev[l];
+    }
+    kbs_st4(cmd_out, 6 + k, ld, n0, o);
+  }
+}
+
+// =====================================================================================================
+// PositionActuators.get_ctrl (ksim fork) train.py:1091-1105
+// =====================================================================================================
+__global__ void __launch_bounds__(kThreads)
+torque_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ action, const kbs_state_view s,
+              const kbs_episode_view ep, float* __restrict__ ctrl, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  const int64_t ld = s.ld;
+#pragma unroll 5
+  for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+    float a[4], q[4], qd[4], o[4];
+    float kp[4] = {P.kp[j], P.kp[j], P.kp[j], P.kp[j]}, kd[4] = {P.kd[j], P.kd[j], P.kd[j], P.kd[j]};
+    float lim[4] = {P.ctrl_limit[j], P.ctrl_limit[j], P.ctrl_limit[j], P.ctrl_limit[j]};
+    float ab[4] = {0, 0, 0, 0}, tb[4] = {0, 0, 0, 0};
+    kbs_ld4(action, j, ld, n0, a);
+    kbs_ld4(s.qpos, 7 + j, ld, n0, q);
+    kbs_ld4(s.qvel, 6 + j, ld, n0, qd);
+    if (ep.kp) kbs_ld4(ep.kp, j, ld, n0, kp);
+    if (ep.kd) kbs_ld4(ep.kd, j, ld, n0, kd);
+    if (ep.tau_limit) kbs_ld4(ep.tau_limit, j, ld, n0, lim);
+    if (ep.action_bias) kbs_ld4(ep.action_bias, j, ld, n0, ab);
+    if (ep.torque_bias) kbs_ld4(ep.torque_bias, j, ld, n0, tb);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float target = ep.action_bias ? a[l] + ab[l] : a[l];
+      float tau = kp[l] * (target - q[l]) - kd[l] * qd[l];
+      if (ep.torque_bias) tau = tau + tb[l];
+      o[l] = fminf(fmaxf(tau, -lim[l]), lim[l]);
+    }
+    kbs_st4(ctrl, j, ld, n0, o);
+  }
+}
+
+// =====================================================================================================
+// Terminations train.py:1258-1269, 817-823 (+ ksim NotUpright / EpisodeLength / done-success reduce)
+// =====================================================================================================
+__global__ void __launch_bounds__(kThreads)
+terminate_kernel(const __grid_constant__ kbs_params P, const kbs_state_view s, int32_t* __restrict__ codes,
+                 uint8_t* __restrict__ done, uint8_t* __restrict__ success, float* __restrict__ pre, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  const int64_t ld = s.ld;
+  float bz[4], lz[4], rz[4], q[4][4], tm[4];
+  kbs_ld4(s.xpos, 3 * P.body_base + 2, ld, n0, bz);
+  kbs_ld4(s.xpos, 3 * P.body_lfoot + 2, ld, n0, lz);
+  kbs_ld4(s.xpos, 3 * P.body_rfoot + 2, ld, n0, rz);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) kbs_ld4(s.qpos, 3 + k, ld, n0, q[k]);
+  kbs_ld4(s.time, 0, ld, n0, tm);
+  int c0[4], c1[4], c2[4];
+  float hgt[4], tilt[4];
+  uchar4 d, sc;
+  unsigned char* dp = reinterpret_cast<unsigned char*>(&d);
+  unsigned char* sp = reinterpret_cast<unsigned char*>(&sc);
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    hgt[l] = bz[l] - fminf(lz[l], rz[l]);
+    c0[l] = (hgt[l] < P.unhealthy_z) ? -1 : 0;
+    float qq[4] = {q[0][l], q[1][l], q[2][l], q[3][l]};
+    quat_norm_eps(qq, P.eps_quat);
+    const float cz = 1.0f - 2.0f * (qq[1] * qq[1] + qq[2] * qq[2]);
+    tilt[l] = acosf(fminf(fmaxf(cz, -1.0f), 1.0f));
+    c1[l] = (tilt[l] > P.max_tilt) ? -1 : 0;
+    c2[l] = (tm[l] > P.max_length_sec) ? 1 : 0;
+    const bool dn = (c0[l] != 0) || (c1[l] != 0) || (c2[l] != 0);
+    dp[l] = dn ? 1 : 0;
+    sp[l] = (dn && c0[l] != -1 && c1[l] != -1 && c2[l] != -1) ? 1 : 0;
+  }
+  if (codes) {
+    *reinterpret_cast<int4*>(codes + 0 * ld + n0) = make_int4(c0[0], c0[1], c0[2], c0[3]);
+    *reinterpret_cast<int4*>(codes + 1 * ld + n0) = make_int4(c1[0], c1[1], c1[2], c1[3]);
+    *reinterpret_cast<int4*>(codes + 2 * ld + n0) = make_int4(c2[0], c2[1], c2[2], c2[3]);
+  }
+  if (done) *reinterpret_cast<uchar4*>(done + n0) = d;
+  if (success) *reinterpret_cast<uchar4*>(success + n0) = sc;
+  if (pre) { kbs_st4(pre, 0, ld, n0, hgt); kbs_st4(pre, 1, ld, n0, tilt); }
+}
+
+// =====================================================================================================
+// Rewards train.py:125-506, table 1224-1256.
+//   reward_rot_kernel   : per env, sqrt(sum_t wz_t^2) > 1e-3  (train.py:455 reduces over TIME as written)
+//   reward_terms_kernel : the 10 stateless terms, fully parallel over (t, env); emits contact/zero flags
+//   reward_scan_kernel  : the 2 stateful scans (single_contact, feet_airtime) over T per env + final sum
+// =====================================================================================================
+__global__ void __launch_bounds__(kThreads)
+reward_rot_kernel(const float* __restrict__ command, uint8_t* __restrict__ is_rot, int64_t T, int64_t ld, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  float acc[4] = {0, 0, 0, 0};
+  for (int64_t t = 0; t < T; ++t) {
+    float wz[4];
+    kbs_ld4(command + t * KBS_NUM_COMMANDS * ld, 2, ld, n0, wz);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) acc[l] = acc[l] + wz[l] * wz[l];
+  }
+  uchar4 o;
+  o.x = sqrtf(acc[0]) > 1e-3f; o.y = sqrtf(acc[1]) > 1e-3f; o.z = sqrtf(acc[2]) > 1e-3f; o.w = sqrtf(acc[3]) > 1e-3f;
+  *reinterpret_cast<uchar4*>(is_rot + n0) = o;
+}
+
+__device__ __forceinline__ float quat_dot(const float (&a)[4], const float (&b)[4]) {
+  return ((a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]) + a[3] * b[3];
+}
+
+__global__ void __launch_bounds__(kThreads)
+reward_terms_kernel(const __grid_constant__ kbs_params P, const kbs_traj_view tr, const uint8_t* __restrict__ is_rot,
+                    float* __restrict__ total, float* __restrict__ comp, uint8_t* __restrict__ flags, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  const int64_t t = blockIdx.y;
+  const int64_t ld = tr.state.ld;
+  const float* xquat = tr.state.xquat + t * 4 * KBS_NBODY * ld;
+  const float* xpos = tr.state.xpos + t * 3 * KBS_NBODY * ld;
+  const float* qpos = tr.state.qpos + t * KBS_NQ * ld;
+  const float* qvel = tr.state.qvel + t * KBS_NV * ld;
+  const float* sd = tr.state.sensordata + t * KBS_NSENSORDATA * ld;
+  const float* cmdp = tr.command + t * KBS_NUM_COMMANDS * ld;
+  const float* ctrl = tr.ctrl + t * KBS_NUM_JOINTS * ld;
+  float* comp_t = comp ? comp + t * KBS_NUM_REWARDS * ld : nullptr;
+
+  float c[16][4];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) kbs_ld4(cmdp, k, ld, n0, c[k]);
+  float bq[4][4], lq[4][4], rq[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    kbs_ld4(xquat, 4 * P.body_base + k, ld, n0, bq[k]);
+    kbs_ld4(xquat, 4 * P.body_lfoot + k, ld, n0, lq[k]);
+    kbs_ld4(xquat, 4 * P.body_rfoot + k, ld, n0, rq[k]);
+  }
+  float v[6][4], bz[4], lz[4], rz[4], tl[4], trr[4], cd[4];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) kbs_ld4(qvel, k, ld, n0, v[k]);
+  kbs_ld4(xpos, 3 * P.body_base + 2, ld, n0, bz);
+  kbs_ld4(xpos, 3 * P.body_lfoot + 2, ld, n0, lz);
+  kbs_ld4(xpos, 3 * P.body_rfoot + 2, ld, n0, rz);
+  kbs_ld4(sd, P.sd_touch_l, ld, n0, tl);
+  kbs_ld4(sd, P.sd_touch_r, ld, n0, trr);
+  kbs_ld4(tr.state.com_distance + t * ld, 0, ld, n0, cd);
+  const uchar4 rot4 = *reinterpret_cast<const uchar4*>(is_rot + n0);
+  const unsigned char rot[4] = {rot4.x, rot4.y, rot4.z, rot4.w};
+
+  float r[KBS_NUM_REWARDS][4];
+  bool zc[4];
+  uchar4 fl;
+  unsigned char* flp = reinterpret_cast<unsigned char*>(&fl);
+
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    zc[l] = zero_cmd(c[0][l], c[1][l], c[2][l]);
+    const float q[4] = {bq[0][l], bq[1][l], bq[2][l], bq[3][l]};
+    float e[3];
+    quat_to_euler(q, P.eps_quat, e);
+    // R1 linvel train.py:274-292
+    {
+      float qz[4], g[3];
+      euler_to_quat(0.0f, 0.0f, e[2], qz);
+      const float vc[3] = {c[0][l], c[1][l], 0.0f};
+      rotate_vec(vc, qz, false, P.eps_quat, g);
+      const float dx = v[0][l] - g[0], dy = v[1][l] - g[1];
+      const float verr = sqrtf(dx * dx + dy * dy);
+      const float err = zc[l] ? verr : verr * verr;
+      r[0][l] = expf(-err / P.linvel_es);
+    }
+    // R2 angvel train.py:301-306
+    r[1][l] = expf(-fabsf(v[5][l] - c[2][l]) / P.angvel_es);
+    // R3 roll_pitch train.py:316-334
+    {
+      float qxy[4], qc[4];
+      euler_to_quat(e[0], e[1], 0.0f, qxy);
+      euler_to_quat(c[4][l], c[5][l], 0.0f, qc);
+      const float d = quat_dot(qc, qxy);
+      const float qerr = 1.0f - d * d;
+      r[2][l] = expf(-qerr / (zc[l] ? P.rp_es_zero : P.rp_es));
+    }
+    // R4 base_height train.py:377-388
+    {
+      const float h = bz[l] - fminf(lz[l] - P.bh_foot_origin, rz[l] - P.bh_foot_origin);
+      r[3][l] = expf(-fabsf(h - (c[3][l] + P.bh_standard)) / P.bh_es);
+    }
+    // contacts train.py:139-140
+    const bool cl = tl[l] > 0.1f, cr = trr[l] > 0.1f;
+    flp[l] = (cl ? 1 : 0) | (cr ? 2 : 0) | (zc[l] ? 4 : 0);
+    // R7 no_contact_p train.py:161-165
+    r[6][l] = zc[l] ? 0.0f : ((cl || cr) ? 0.0f : 1.0f);
+    // R9 feet_orient train.py:418-457
+    {
+      const float yaw = e[2];
+      float tq[2][4], tq0[2][4];
+      euler_to_quat(-kHalfPi, 0.0f, yaw - kPi, tq[0]);
+      euler_to_quat(kHalfPi, 0.0f, yaw - kPi, tq[1]);
+      euler_to_quat(-kHalfPi, 0.0f, 0.0f, tq0[0]);
+      euler_to_quat(kHalfPi, 0.0f, 0.0f, tq0[1]);
+      const float fq[2][4] = {{lq[0][l], lq[1][l], lq[2][l], lq[3][l]}, {rq[0][l], rq[1][l], rq[2][l], rq[3][l]}};
+      float rpy = 0.0f, rp = 0.0f;
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        const float d = quat_dot(tq[f], fq[f]);
+        rpy = rpy + (1.0f - d * d);
+        float fe[3], fq0[4];
+        quat_to_euler(fq[f], P.eps_quat, fe);
+        euler_to_quat(fe[0], fe[1], 0.0f, fq0);
+        const float d0 = quat_dot(tq0[f], fq0);
+        rp = rp + (1.0f - d0 * d0);
+      }
+      r[8][l] = expf(-(rot[l] ? rp : rpy) / P.feet_es);
+    }
+    // R10 com_distance train.py:466-478
+    r[9][l] = (cd[l] >= 0.0f) ? (zc[l] ? expf(-cd[l] / P.com_es) : 0.0f) : 0.0f;
+    r[5][l] = 0.0f;  // single_contact: scan kernel
+    r[7][l] = 0.0f;  // feet_airtime: scan kernel
+  }
+
+  // R5 arm_pos train.py:261-265
+  {
+    float err[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      float q[4];
+      kbs_ld4(qpos, 17 + k, ld, n0, q);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const float d = q[l] - (c[6 + k][l] + P.joint_bias[10 + k]);
+        err[l] = err[l] + d * d;
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) r[4][l] = expf(-err[l] / P.arm_es);
+  }
+  // R11 base_accel train.py:487-494 (edge pad: t = 0 has zero difference)
+  {
+    float err[4] = {0, 0, 0, 0};
+    if (t > 0) {
+      const uchar4 pd4 = *reinterpret_cast<const uchar4*>(tr.done + (t - 1) * ld + n0);
+      const unsigned char pd[4] = {pd4.x, pd4.y, pd4.z, pd4.w};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        float pv[4];
+        kbs_ld4(qvel - KBS_NV * ld, k, ld, n0, pv);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) err[l] = err[l] + fabsf(pd[l] ? 0.0f : (v[k][l] - pv[l]));
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) r[10][l] = expf(-err[l] / P.acc_es);
+  }
+  // R12 torque train.py:503-506
+  {
+    float acc[4] = {0, 0, 0, 0};
+#pragma unroll 5
+    for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+      float u[4];
+      kbs_ld4(ctrl, j, ld, n0, u);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) acc[l] = acc[l] + expf(-fabsf(u[l]) / P.torque_es);
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) r[11][l] = zc[l] ? acc[l] / 20.0f : 1.0f;
+  }
+
+  float tot[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KBS_NUM_REWARDS; ++k) s = s + P.reward_scale[k] * r[k][l];
+    tot[l] = s;
+  }
+  kbs_st4(total + t * ld, 0, ld, n0, tot);
+  *reinterpret_cast<uchar4*>(flags + t * ld + n0) = fl;
+  if (comp_t) {
+#pragma unroll
+    for (int k = 0; k < KBS_NUM_REWARDS; ++k) kbs_st4(comp_t, k, ld, n0, r[k]);
+  }
+}
+
+// Stateful terms R6 (train.py:138-154) and R8 (train.py:197-213): sequential in T per env, exactly the
+// reference's scan order (t + dt accumulated step by step in fp32, compared against grace_period).
+__global__ void __launch_bounds__(kThreads)
+reward_scan_kernel(const __grid_constant__ kbs_params P, const uint8_t* __restrict__ flags,
+                   const uint8_t* __restrict__ done, kbs_reward_carry carry, float* __restrict__ total,
+                   float* __restrict__ comp, int64_t T, int64_t ld, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  if (e >= n) return;
+  float t_sc = carry.t_single[e];
+  float air0 = carry.airtime[e], air1 = carry.airtime[ld + e];
+  bool pc0 = carry.prev_contact[e] != 0, pc1 = carry.prev_contact[ld + e] != 0;
+  for (int64_t t = 0; t < T; ++t) {
+    const unsigned f = flags[t * ld + e];
+    const bool dn = done[t * ld + e] != 0;
+    const bool cl = f & 1, cr = (f & 2) != 0, zc = (f & 4) != 0;
+    const bool single = cl != cr;
+    t_sc = single ? 0.0f : t_sc + P.ctrl_dt;
+    t_sc = zc ? P.grace_period : t_sc;
+    const float r6 = zc ? 1.0f : ((t_sc < P.grace_period) ? 1.0f : 0.0f);
+    const bool f0 = cl && !pc0 && !dn, f1 = cr && !pc1 && !dn;
+    float r8 = (air0 - P.touchdown_penalty) * (f0 ? 1.0f : 0.0f) + (air1 - P.touchdown_penalty) * (f1 ? 1.0f : 0.0f);
+    r8 = zc ? 0.0f : r8;
+    air0 = (cl || dn) ? 0.0f : air0 + P.ctrl_dt;
+    air1 = (cr || dn) ? 0.0f : air1 + P.ctrl_dt;
+    pc0 = cl; pc1 = cr;
+    total[t * ld + e] = total[t * ld + e] + (P.reward_scale[5] * r6 + P.reward_scale[7] * r8);
+    if (comp) {
+      comp[(t * KBS_NUM_REWARDS + 5) * ld + e] = r6;
+      comp[(t * KBS_NUM_REWARDS + 7) * ld + e] = r8;
+    }
+  }
+  carry.t_single[e] = t_sc;
+  carry.airtime[e] = air0; carry.airtime[ld + e] = air1;
+  carry.prev_contact[e] = pc0; carry.prev_contact[ld + e] = pc1;
+}
+
+// =====================================================================================================
+// GAE: ksim.compute_ppo_inputs.  Block = 32 envs x 4 warps.  Time is walked backwards in chunks of kGaeChunk
+// steps: all 4 warps stage the chunk (delta, gamma*lam*mask) into shared memory with coalesced row loads,
+// warp 0 runs the sequential reverse scan out of shared memory, all warps store the chunk back.
+// =====================================================================================================
+constexpr int kGaeChunk = 32;
+constexpr int kGaeEnvs = 32;
+
+__global__ void __launch_bounds__(128)
+gae_kernel(float gamma, float lam, const float* __restrict__ values, const float* __restrict__ rewards,
+           const uint8_t* __restrict__ done, const uint8_t* __restrict__ success, float* __restrict__ adv,
+           float* __restrict__ targets, int64_t T, int64_t ld, int64_t n) {
+  __shared__ float s_delta[kGaeChunk][kGaeEnvs];
+  __shared__ float s_k[kGaeChunk][kGaeEnvs];
+  __shared__ float s_v[kGaeChunk][kGaeEnvs];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t e = int64_t(blockIdx.x) * kGaeEnvs + lane;
+  const bool live = e < n;
+  const float gl = gamma * lam;
+  float a = 0.0f;  // A_{t+1}, carried by warp 0 across chunks
+  for (int64_t t_hi = T; t_hi > 0; t_hi -= kGaeChunk) {
+    const int64_t t_lo = (t_hi > kGaeChunk) ? t_hi - kGaeChunk : 0;
+    const int len = int(t_hi - t_lo);
+    for (int i = warp; i < len; i += 4) {
+      const int64_t t = t_lo + i;
+      float v = 0.f, vn = 0.f, r = 0.f, mask = 1.f, sc = 0.f;
+      if (live) {
+        v = values[t * ld + e];
+        vn = (t + 1 < T) ? values[(t + 1) * ld + e] : v;
+        r = rewards[t * ld + e];
+        mask = done[t * ld + e] ? 0.0f : 1.0f;
+        sc = success[t * ld + e] ? 1.0f : 0.0f;
+      }
+      const float rt = r + gamma * v * sc;
+      s_delta[i][lane] = rt + gamma * vn * mask - v;
+      s_k[i][lane] = gl * mask;
+      s_v[i][lane] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int i = len - 1; i >= 0; --i) {
+        a = s_delta[i][lane] + s_k[i][lane] * a;
+        s_delta[i][lane] = a;
+      }
+    }
+    __syncthreads();
+    if (live) {
+      for (int i = warp; i < len; i += 4) {
+        const int64_t t = t_lo + i;
+        const float av = s_delta[i][lane];
+        adv[t * ld + e] = av;
+        targets[t * ld + e] = av + s_v[i][lane];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// per-trajectory advantage normalisation a / (std_t(a) + eps)  [ksim flag, unverified]
+__global__ void __launch_bounds__(kThreads)
+adv_norm_kernel(float eps, float* __restrict__ adv, int64_t T, int64_t ld, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  if (e >= n) return;
+  float s = 0.0f;
+  for (int64_t t = 0; t < T; ++t) s = s + adv[t * ld + e];
+  const float mean = s / float(T);
+  float q = 0.0f;
+  for (int64_t t = 0; t < T; ++t) { const float d = adv[t * ld + e] - mean; q = q + d * d; }
+  const float sd = sqrtf(q / float(T)) + eps;
+  for (int64_t t = 0; t < T; ++t) adv[t * ld + e] = adv[t * ld + e] / sd;
+}
+
+// =====================================================================================================
+// convert.py:84-119 policy step marshalling (AoS <-> kernel layouts)
+// =====================================================================================================
+__global__ void __launch_bounds__(kThreads)
+policy_pack_obs_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ ja, const float* __restrict__ jv,
+                       const float* __restrict__ pg, const float* __restrict__ gyro, const float* __restrict__ cmd,
+                       const float* __restrict__ carry_in, int carry_w, float* __restrict__ obs, float* __restrict__ lpf,
+                       int64_t ld, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  if (e >= n) return;
+  for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+    obs[j * ld + e] = (ja[e * 20 + j] - P.joint_bias[j]) / P.joint_range[j];
+    obs[(20 + j) * ld + e] = jv[e * 20 + j] / 10.0f;
+    lpf[j * ld + e] = carry_in[e * carry_w + (carry_w - 20) + j];
+  }
+  const float g[3] = {pg[e * 3 + 0], pg[e * 3 + 1], pg[e * 3 + 2]};
+  float enc[5];
+  encode_pg(g, enc);
+  for (int k = 0; k < 5; ++k) obs[(40 + k) * ld + e] = enc[k];
+  for (int k = 0; k < 3; ++k) obs[(45 + k) * ld + e] = gyro[e * 3 + k];
+  obs[48 * ld + e] = zero_cmd(cmd[e * 16 + 0], cmd[e * 16 + 1], cmd[e * 16 + 2]) ? 1.0f : 0.0f;
+  for (int k = 0; k < 16; ++k) obs[(49 + k) * ld + e] = cmd[e * 16 + k];
+}
+
+// carry_flat [n][D2H + 20]  <->  AoS [depth*2][n][H]
+__global__ void __launch_bounds__(256)
+policy_carry_kernel(const float* __restrict__ src, float* __restrict__ dst, int d2, int H, int carry_w, int64_t n,
+                    bool to_kernel_layout) {
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t per_env = int64_t(d2) * H;
+  if (idx >= n * per_env) return;
+  const int64_t e = idx / per_env;
+  const int rem = int(idx - e * per_env);
+  const int slot = rem / H, k = rem - slot * H;
+  const int64_t flat = e * carry_w + rem;
+  const int64_t aos = (int64_t(slot) * n + e) * H + k;
+  if (to_kernel_layout) dst[aos] = src[flat];
+  else dst[flat] = src[aos];
+}
+
+__global__ void __launch_bounds__(kThreads)
+policy_unpack_kernel(const float* __restrict__ lpf, const float* __restrict__ mean, float* __restrict__ carry_out,
+                     int carry_w, float* __restrict__ action_out, int64_t ld, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  if (e >= n) return;
+  for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+    carry_out[e * carry_w + (carry_w - 20) + j] = lpf[j * ld + e];
+    action_out[e * 20 + j] = mean[j * ld + e];
+  }
+}
+
+inline unsigned groups4(int64_t n) { return unsigned((((n + 3) / 4) + kThreads - 1) / kThreads); }
+
+}  // namespace
+
+// ---- launchers ------------------------------------------------------------------------------------
+int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_noise_view* nz,
+                            const kbs_episode_view* ep, const float* command, float* pg_carry, float* computed,
+                            float* actor_obs, float* critic_obs, int64_t n, cudaStream_t st) {
+  kbs_noise_view z{};
+  kbs_episode_view e{};
+  if (nz) z = *nz;
+  if (ep) e = *ep;
+  dim3 grid(groups4(n), critic_obs ? 1 + 368 / kCopyRowsPerSection : 1);
+  obs_kernel<<<grid, kThreads, 0, st>>>(h->p, s, z, e, command, pg_carry, computed, actor_obs, critic_obs, n);
+  h->launches++;
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_command(kbs_handle* h, const float* cmd_in, float* cmd_out, const float* u_switch,
+                       const int32_t* mode, const float* u6, const float* u_arms, const uint8_t* done, int64_t ld,
+                       int64_t n, cudaStream_t st) {
+  command_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, cmd_in, cmd_out, u_switch, mode, u6, u_arms, done, ld, n);
+  h->launches++;
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_torque(kbs_handle* h, const float* action, const kbs_state_view& s, const kbs_episode_view* ep,
+                      float* ctrl, int64_t n, cudaStream_t st) {
+  kbs_episode_view e{};
+  if (ep) e = *ep;
+  torque_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, action, s, e, ctrl, n);
+  h->launches++;
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_terminate(kbs_handle* h, const kbs_state_view& s, int32_t* codes, uint8_t* done, uint8_t* success,
+                         float* pre, int64_t n, cudaStream_t st) {
+  terminate_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, s, codes, done, success, pre, n);
+  h->launches++;
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_rewards(kbs_handle* h, const kbs_traj_view& tr, const kbs_reward_carry& carry, float* total,
+                       float* components, int64_t n, cudaStream_t st) {
+  const int64_t ld = tr.state.ld, T = tr.T;
+  // scratch: is_rot [ld] + flags [T][ld] bytes
+  const size_t bytes = size_t(ld) * size_t(T + 1);
+  int rc = kbs_scratch_reserve(h, (bytes + 3) / 4 + 4);
+  if (rc) return rc;
+  uint8_t* is_rot = reinterpret_cast<uint8_t*>(h->scratch);
+  uint8_t* flags = is_rot + ld;
+  reward_rot_kernel<<<groups4(n), kThreads, 0, st>>>(tr.command, is_rot, T, ld, n);
+  dim3 grid(groups4(n), unsigned(T));
+  reward_terms_kernel<<<grid, kThreads, 0, st>>>(h->p, tr, is_rot, total, components, flags, n);
+  reward_scan_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(h->p, flags, tr.done, carry, total,
+                                                                                 components, T, ld, n);
+  h->launches += 3;
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_gae(kbs_handle* h, const float* values, const float* rewards, const uint8_t* done,
+                   const uint8_t* success, float* adv, float* targets, int64_t T, int64_t ld, int64_t n,
+                   cudaStream_t st) {
+  gae_kernel<<<unsigned((n + kGaeEnvs - 1) / kGaeEnvs), 128, 0, st>>>(h->p.gamma, h->p.lam, values, rewards, done,
+                                                                      success, adv, targets, T, ld, n);
+  h->launches++;
+  if (h->p.normalize_advantages == 1) {
+    adv_norm_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(h->p.adv_eps, adv, T, ld, n);
+    h->launches++;
+  }
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_policy_pack(kbs_handle* h, const float* ja, const float* jv, const float* pg, const float* gyro,
+                           const float* cmd, const float* carry_in, float* obs_soa, float* carry_aos, float* lpf_soa,
+                           int64_t ld, int64_t n, cudaStream_t st) {
+  const int H = h->p.hidden_size, d2 = 2 * h->p.depth, cw = d2 * H + 20;
+  policy_pack_obs_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(h->p, ja, jv, pg, gyro, cmd,
+                                                                                     carry_in, cw, obs_soa, lpf_soa, ld, n);
+  const int64_t tot = n * int64_t(d2) * H;
+  policy_carry_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(carry_in, carry_aos, d2, H, cw, n, true);
+  h->launches += 2;
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_policy_unpack(kbs_handle* h, const float* carry_aos, const float* lpf_soa, const float* mean_soa,
+                             float* carry_out, float* action_out, int64_t ld, int64_t n, cudaStream_t st) {
+  const int H = h->p.hidden_size, d2 = 2 * h->p.depth, cw = d2 * H + 20;
+  const int64_t tot = n * int64_t(d2) * H;
+  policy_carry_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(carry_aos, carry_out, d2, H, cw, n, false);
+  policy_unpack_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(lpf_soa, mean_soa, carry_out, cw,
+                                                                                   action_out, ld, n);
+  h->launches += 2;
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}

@@ -1,0 +1,250 @@
+// kbs_net_simt.cu -- fp32 FFMA datapath for the actor/critic trunk (input_proj -> depth x LSTMCell ->
+// output_proj, train.py:913-922, 993-1002) plus the actor / critic heads shared by both datapaths.
+// This is the exact-fp32 path (summation order aside); the tcgen05 3xTF32 path lives in kbs_net_tc.cu.
+#include <math.h>
+
+#include "kbs_common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+
+// C[m][n] (+)= sum_k A(m,k) W[n][k] + bias[n].   A: row-major [M][lda] or SoA [K][lda] (env contiguous).
+// W: [Npad][ldw] row-major, Npad % 64 == 0, K % 16 == 0 (zero padded by the pack step).
+template <bool A_SOA>
+__global__ void __launch_bounds__(256)
+gemm_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int ldw,
+               const float* __restrict__ bias, float* __restrict__ C, int ldc, int64_t M, int K, int Kvalid,
+               int accumulate) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Ws[BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int64_t m0 = int64_t(blockIdx.x) * BM;
+  const int n0 = blockIdx.y * BN;
+  float acc[4][4] = {};
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    if (A_SOA) {
+      const int k = tid >> 4, m4 = (tid & 15) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < Kvalid && m0 + m4 < M) v = *reinterpret_cast<const float4*>(A + int64_t(k0 + k) * lda + m0 + m4);
+      *reinterpret_cast<float4*>(&As[k][m4]) = v;
+    } else {
+      const int r = tid >> 2, kq = (tid & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M) v = *reinterpret_cast<const float4*>(A + (m0 + r) * lda + k0 + kq);
+      As[kq + 0][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
+    }
+    {
+      const int r = tid >> 2, kq = (tid & 3) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(W + int64_t(n0 + r) * ldw + k0 + kq);
+      Ws[kq + 0][r] = v.x; Ws[kq + 1][r] = v.y; Ws[kq + 2][r] = v.z; Ws[kq + 3][r] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bb = *reinterpret_cast<const float4*>(bias + n0 + tx * 4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    float4* cp = reinterpret_cast<float4*>(C + m * ldc + n0 + tx * 4);
+    float4 o = make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
+    if (accumulate) { const float4 c = *cp; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+    *cp = o;
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// eqx LSTMCell: i,f,g,o = split(lin, 4); c' = s(f) c + s(i) tanh(g); h' = s(o) tanh(c').
+// gates [n][4H] (bias already added).  h_next: un-reset output for the next layer; carry_h/c: reset where done
+// (train.py:1502-1506).
+__global__ void __launch_bounds__(256)
+lstm_cell_kernel(const float* __restrict__ gates, float* __restrict__ carry_h, float* __restrict__ carry_c,
+                 float* __restrict__ h_next, const uint8_t* __restrict__ done, int H, int64_t n) {
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int hq = H / 4;
+  if (idx >= n * hq) return;
+  const int64_t e = idx / hq;
+  const int k = int(idx - e * hq) * 4;
+  const float* g = gates + e * 4 * H + k;
+  const float4 gi = *reinterpret_cast<const float4*>(g);
+  const float4 gf = *reinterpret_cast<const float4*>(g + H);
+  const float4 gg = *reinterpret_cast<const float4*>(g + 2 * H);
+  const float4 go = *reinterpret_cast<const float4*>(g + 3 * H);
+  const float4 c4 = *reinterpret_cast<const float4*>(carry_c + e * H + k);
+  const float iv[4] = {gi.x, gi.y, gi.z, gi.w}, fv[4] = {gf.x, gf.y, gf.z, gf.w};
+  const float gv[4] = {gg.x, gg.y, gg.z, gg.w}, ov[4] = {go.x, go.y, go.z, go.w};
+  const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+  float hn[4], cn[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    cn[l] = sigmoidf_(fv[l]) * cv[l] + sigmoidf_(iv[l]) * tanhf(gv[l]);
+    hn[l] = sigmoidf_(ov[l]) * tanhf(cn[l]);
+  }
+  *reinterpret_cast<float4*>(h_next + e * H + k) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+  const bool rst = done && done[e];
+  *reinterpret_cast<float4*>(carry_h + e * H + k) = rst ? make_float4(0, 0, 0, 0) : make_float4(hn[0], hn[1], hn[2], hn[3]);
+  *reinterpret_cast<float4*>(carry_c + e * H + k) = rst ? make_float4(0, 0, 0, 0) : make_float4(cn[0], cn[1], cn[2], cn[3]);
+}
+
+// Actor head, train.py:924-939 + distrax MultivariateNormalDiag (log_prob / entropy / sample / mode).
+// One thread per env; reads out[n][ldo] row-major, writes env-major SoA (coalesced across the warp).
+__global__ void __launch_bounds__(128)
+actor_head_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ out, int ldo,
+                  const float* __restrict__ obs, int64_t ld, float* __restrict__ lpf, const float* __restrict__ eps,
+                  const float* __restrict__ action_in, const uint8_t* __restrict__ done, kbs_actor_out o, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (e >= n) return;
+  const float* row = out + e * ldo;
+  float v[KBS_ACTOR_OUT];
+#pragma unroll
+  for (int k = 0; k < KBS_ACTOR_OUT; k += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(row + k);
+    v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
+  }
+  const bool rst = done && done[e];
+  float s_z = 0.0f, s_log = 0.0f;
+  constexpr float kHalfLog2Pi = 0.918938533204672742f;
+#pragma unroll
+  for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+    // std = clip((softplus(s) + min_std) * var_scale, max=max_std)
+    const float sraw = v[KBS_NUM_JOINTS + j];
+    const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
+    const float sd = fminf((sp + P.min_std) * P.var_scale, P.max_std);
+    // mean = out + JOINT_BIASES + [0 x 10, obs[-10:]]   (obs slots 55..64 = arm command)
+    float m = v[j] + P.joint_bias[j];
+    m = m + ((j >= 10) ? obs[(55 + (j - 10)) * ld + e] : 0.0f);
+    // ksim.lowpass_one_pole: y' = y + alpha (x - y)
+    const float y = lpf[j * ld + e];
+    const float yn = y + P.lpf_alpha * (m - y);
+    lpf[j * ld + e] = rst ? 0.0f : yn;
+    float a = yn;                                       // mode()
+    if (eps) a = yn + sd * eps[j * ld + e];             // sample(seed)
+    const float a_eval = action_in ? action_in[j * ld + e] : a;
+    const float z = (a_eval - yn) / sd;
+    s_z = s_z + (-0.5f * z * z - kHalfLog2Pi);
+    s_log = s_log + logf(sd);
+    if (o.action) o.action[j * ld + e] = a;
+    if (o.mean) o.mean[j * ld + e] = yn;
+    if (o.std) o.std[j * ld + e] = sd;
+  }
+  if (o.log_prob) o.log_prob[e] = s_z - s_log;
+  if (o.entropy) o.entropy[e] = s_log + float(KBS_NUM_JOINTS) * (0.5f + kHalfLog2Pi);
+}
+
+__global__ void __launch_bounds__(128)
+critic_head_kernel(const float* __restrict__ out, int ldo, float* __restrict__ value, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (e < n) value[e] = out[e * ldo];
+}
+
+// zero-padded copy [rows][cols] -> [rows_pad][cols_pad]
+__global__ void pad_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int rows_pad,
+                                int cols_pad) {
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= int64_t(rows_pad) * cols_pad) return;
+  const int r = int(idx / cols_pad), c = int(idx % cols_pad);
+  dst[idx] = (r < rows && c < cols) ? src[int64_t(r) * cols + c] : 0.0f;
+}
+
+int pad_copy(const float* src, float** dst, int rows, int cols, int rows_pad, int cols_pad, cudaStream_t st) {
+  if (*dst) { KBS_CUDA_TRY(cudaFree(*dst)); *dst = nullptr; }
+  KBS_CUDA_TRY(cudaMalloc(dst, sizeof(float) * size_t(rows_pad) * cols_pad));
+  const int64_t tot = int64_t(rows_pad) * cols_pad;
+  pad_copy_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(src, *dst, rows, cols, rows_pad, cols_pad);
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+int kbs_simt_pack(kbs_handle* h, int net, const kbs_net_weights* w, cudaStream_t st) {
+  KbsNet& N = h->net[net];
+  const int H = h->p.hidden_size;
+  N.num_in = (net == KBS_NET_ACTOR) ? KBS_ACTOR_OBS : KBS_CRITIC_OBS;
+  N.num_out = (net == KBS_NET_ACTOR) ? KBS_ACTOR_OUT : 1;
+  N.kin_pad = round_up(N.num_in, 16);
+  N.nout_pad = 64;
+  int rc;
+  if ((rc = pad_copy(w->w_in, &N.w_in, H, N.num_in, H, N.kin_pad, st))) return rc;
+  if ((rc = pad_copy(w->b_in, &N.b_in, 1, H, 1, H, st))) return rc;
+  for (int l = 0; l < h->p.depth; ++l) {
+    if ((rc = pad_copy(w->w_ih[l], &N.w_ih[l], 4 * H, H, 4 * H, H, st))) return rc;
+    if ((rc = pad_copy(w->w_hh[l], &N.w_hh[l], 4 * H, H, 4 * H, H, st))) return rc;
+    if ((rc = pad_copy(w->b[l], &N.b[l], 1, 4 * H, 1, 4 * H, st))) return rc;
+  }
+  if ((rc = pad_copy(w->w_out, &N.w_out, N.num_out, H, N.nout_pad, H, st))) return rc;
+  if ((rc = pad_copy(w->b_out, &N.b_out, 1, N.num_out, 1, N.nout_pad, st))) return rc;
+  h->launches += 4 + 3 * h->p.depth;
+  N.packed = true;
+  return KBS_OK;
+}
+
+size_t kbs_simt_scratch_floats(const kbs_handle* h, int64_t n) {
+  const size_t H = size_t(h->p.hidden_size);
+  return size_t(n) * (H + 4 * H + H) + 64;
+}
+
+// out_rowmajor: [n][nout_pad = 64]
+int kbs_simt_trunk(kbs_handle* h, int net, const float* obs_soa, int64_t ld, float* carry, const uint8_t* done,
+                   float* out_rm, int64_t n, cudaStream_t st) {
+  const KbsNet& N = h->net[net];
+  if (!N.packed) return KBS_E_STATE;
+  const int H = h->p.hidden_size;
+  float* x = h->scratch;
+  float* gates = x + size_t(n) * H;
+  float* hbuf = gates + size_t(n) * 4 * H;
+  const unsigned mb = unsigned((n + BM - 1) / BM);
+  gemm_nt_kernel<true><<<dim3(mb, H / BN), 256, 0, st>>>(obs_soa, ld, N.w_in, N.kin_pad, N.b_in, x, H, n, N.kin_pad,
+                                                        N.num_in, 0);
+  h->launches++;
+  const float* in = x;
+  for (int l = 0; l < h->p.depth; ++l) {
+    float* ch = carry + (size_t(l) * 2 + 0) * size_t(n) * H;
+    float* cc = carry + (size_t(l) * 2 + 1) * size_t(n) * H;
+    gemm_nt_kernel<false><<<dim3(mb, 4 * H / BN), 256, 0, st>>>(in, H, N.w_ih[l], H, N.b[l], gates, 4 * H, n, H, H, 0);
+    gemm_nt_kernel<false><<<dim3(mb, 4 * H / BN), 256, 0, st>>>(ch, H, N.w_hh[l], H, nullptr, gates, 4 * H, n, H, H, 1);
+    const int64_t tot = n * (H / 4);
+    lstm_cell_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(gates, ch, cc, hbuf, done, H, n);
+    h->launches += 3;
+    in = hbuf;
+  }
+  gemm_nt_kernel<false><<<dim3(mb, N.nout_pad / BN), 256, 0, st>>>(in, H, N.w_out, H, N.b_out, out_rm, N.nout_pad, n, H,
+                                                                  H, 0);
+  h->launches++;
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_actor_head(kbs_handle* h, const float* out_rm, int ldo, const float* obs_soa, int64_t ld, float* lpf,
+                          const float* eps, const float* action_in, const uint8_t* done, const kbs_actor_out& o,
+                          int64_t n, cudaStream_t st) {
+  actor_head_kernel<<<unsigned((n + 127) / 128), 128, 0, st>>>(h->p, out_rm, ldo, obs_soa, ld, lpf, eps, action_in, done,
+                                                               o, n);
+  h->launches++;
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_critic_head(kbs_handle* h, const float* out_rm, int ldo, float* value, int64_t n, cudaStream_t st) {
+  critic_head_kernel<<<unsigned((n + 127) / 128), 128, 0, st>>>(out_rm, ldo, value, n);
+  h->launches++;
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}

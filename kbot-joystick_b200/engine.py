@@ -1,0 +1,202 @@
+"""Host-side driver of libkbotstep.so: torch tensors in, C-ABI calls out.
+
+Layouts (see include/kbotstep.h): per-env fields are SoA `[F, ld]` (env contiguous, `ld` = n_envs rounded
+up to a multiple of 4); trajectories are `[T, F, ld]`; recurrent carries are AoS `[depth, 2, n, H]`.
+torch is plumbing only (allocation + current stream); all arithmetic happens inside the CUDA library.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib as L
+
+STATE_ROWS = {"qpos": 27, "qvel": 26, "sensordata": 49, "xpos": 72, "xquat": 96, "cinert": 240, "cvel": 144,
+              "actuator_force": 20, "com_distance": 1, "time": 1}
+NOISE_ROWS = {"eps_jpos": 20, "eps_jvel": 20, "eps_gyro": 3, "eps_pg": 3}
+EPISODE_ROWS = {"jpos_bias": 20, "pg_lag": 1, "pg_bias": 3, "kp": 20, "kd": 20, "tau_limit": 20,
+                "action_bias": 20, "torque_bias": 20}
+COMPUTED_OBS_ROWS = {  # rows of the `computed` block written by kbs_observations
+    "biased_joint_position": (0, 20), "noisy_biased_joint_position": (20, 40), "noisy_joint_velocity": (40, 60),
+    "noisy_imu_gyro": (60, 63), "feet_position": (63, 69), "projected_gravity": (69, 72),
+    "imu_projected_gravity": (72, 75), "noisy_imu_projected_gravity": (75, 78)}
+
+
+def round_up4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _view(cls, rows: dict, tensors: dict | None, ld: int | None = None):
+    v = cls()
+    if tensors:
+        for k in rows:
+            t = tensors.get(k)
+            if t is not None:
+                setattr(v, k, L.ptr(t))
+    if ld is not None:
+        v.ld = ld
+    return v
+
+
+@dataclass
+class KbotStep:
+    """One handle of the B200 control-step library bound to the current CUDA device."""
+
+    hidden_size: int = 256
+    depth: int = 2
+    gemm_path: int = L.GEMM_SIMT_FP32
+    overrides: dict = field(default_factory=dict)
+
+    def __post_init__(self) -> None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("kbot-joystick_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        p = L.default_params()
+        p.hidden_size, p.depth, p.gemm_path = self.hidden_size, self.depth, self.gemm_path
+        for k, v in self.overrides.items():
+            setattr(p, k, v)
+        self.params = p
+        h = C.c_void_p()
+        L.check(self.lib.kbs_create(C.byref(p), C.byref(h)), "kbs_create")
+        self._h = h
+        self._keep: list = []
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.kbs_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.kbs_launch_count(self._h))
+
+    # ---- weights -------------------------------------------------------------------------------------
+    def pack_weights(self, net: int, w: dict) -> None:
+        """w: eqx-layout CUDA tensors {w_in,b_in,w_out,b_out, layers:[{w_ih,w_hh,b}]} (train.py:847-1004)."""
+        s = L.KbsNetWeights()
+        s.w_in, s.b_in, s.w_out, s.b_out = (L.ptr(w[k]) for k in ("w_in", "b_in", "w_out", "b_out"))
+        for i, lw in enumerate(w["layers"]):
+            s.w_ih[i], s.w_hh[i], s.b[i] = L.ptr(lw["w_ih"]), L.ptr(lw["w_hh"]), L.ptr(lw["b"])
+        L.check(self.lib.kbs_weights_pack(self._h, net, C.byref(s), _stream()), "kbs_weights_pack")
+        torch.cuda.current_stream().synchronize()
+
+    # ---- stages --------------------------------------------------------------------------------------
+    def observations(self, state: dict, command, noise: dict | None = None, episode: dict | None = None,
+                     pg_carry=None, computed=None, actor_obs=None, critic_obs=None, n_envs: int | None = None):
+        ld = state["qpos"].shape[-1]
+        n = n_envs or ld
+        sv = _view(L.KbsStateView, STATE_ROWS, state, ld)
+        nv = _view(L.KbsNoiseView, NOISE_ROWS, noise)
+        ev = _view(L.KbsEpisodeView, EPISODE_ROWS, episode)
+        L.check(self.lib.kbs_observations(self._h, C.byref(sv), C.byref(nv), C.byref(ev), L.ptr(command),
+                                          L.ptr(pg_carry), L.ptr(computed), L.ptr(actor_obs), L.ptr(critic_obs), n,
+                                          _stream()), "kbs_observations")
+
+    def command_update(self, command, mode, u6, u_arms, u_switch=None, n_envs: int | None = None) -> None:
+        ld = command.shape[-1]
+        L.check(self.lib.kbs_command_update(self._h, L.ptr(command), L.ptr(u_switch), L.ptr(mode), L.ptr(u6),
+                                            L.ptr(u_arms), ld, n_envs or ld, _stream()), "kbs_command_update")
+
+    def actor_step(self, obs, carry, lpf, eps=None, action_in=None, done=None, out: dict | None = None,
+                   n_envs: int | None = None) -> dict:
+        ld = obs.shape[-1]
+        n = n_envs or ld
+        if out is None:
+            out = {k: torch.empty((20, ld), device=obs.device) for k in ("action", "mean", "std")}
+            out["log_prob"] = torch.empty((ld,), device=obs.device)
+            out["entropy"] = torch.empty((ld,), device=obs.device)
+        o = L.KbsActorOut()
+        for k in ("action", "mean", "std", "log_prob", "entropy"):
+            setattr(o, k, L.ptr(out.get(k)))
+        L.check(self.lib.kbs_actor_step(self._h, L.ptr(obs), ld, L.ptr(carry), L.ptr(lpf), L.ptr(eps),
+                                        L.ptr(action_in), L.ptr(done), C.byref(o), n, _stream()), "kbs_actor_step")
+        return out
+
+    def critic_step(self, obs, carry, done=None, value=None, n_envs: int | None = None):
+        ld = obs.shape[-1]
+        if value is None:
+            value = torch.empty((ld,), device=obs.device)
+        L.check(self.lib.kbs_critic_step(self._h, L.ptr(obs), ld, L.ptr(carry), L.ptr(done), L.ptr(value),
+                                         n_envs or ld, _stream()), "kbs_critic_step")
+        return value
+
+    def torque(self, action, state: dict, episode: dict | None = None, ctrl=None, n_envs: int | None = None):
+        ld = action.shape[-1]
+        if ctrl is None:
+            ctrl = torch.empty_like(action)
+        sv = _view(L.KbsStateView, STATE_ROWS, state, ld)
+        ev = _view(L.KbsEpisodeView, EPISODE_ROWS, episode)
+        L.check(self.lib.kbs_torque(self._h, L.ptr(action), C.byref(sv), C.byref(ev), L.ptr(ctrl), n_envs or ld,
+                                    _stream()), "kbs_torque")
+        return ctrl
+
+    def terminate(self, state: dict, n_envs: int | None = None, want_pre: bool = False) -> dict:
+        ld = state["qpos"].shape[-1]
+        dev = state["qpos"].device
+        out = {"codes": torch.empty((3, ld), dtype=torch.int32, device=dev),
+               "done": torch.empty((ld,), dtype=torch.uint8, device=dev),
+               "success": torch.empty((ld,), dtype=torch.uint8, device=dev),
+               "pre": torch.empty((2, ld), device=dev) if want_pre else None}
+        sv = _view(L.KbsStateView, STATE_ROWS, state, ld)
+        L.check(self.lib.kbs_terminate(self._h, C.byref(sv), L.ptr(out["codes"]), L.ptr(out["done"]),
+                                       L.ptr(out["success"]), L.ptr(out["pre"]), n_envs or ld, _stream()),
+                "kbs_terminate")
+        return out
+
+    def rewards(self, traj_state: dict, command, ctrl, done, carry: dict, total=None, components=None,
+                n_envs: int | None = None):
+        T, _, ld = command.shape
+        tv = L.KbsTrajView()
+        tv.state = _view(L.KbsStateView, STATE_ROWS, traj_state, ld)
+        tv.command, tv.ctrl, tv.done, tv.T = L.ptr(command), L.ptr(ctrl), L.ptr(done), T
+        cv = L.KbsRewardCarry()
+        cv.t_single, cv.airtime, cv.prev_contact = (L.ptr(carry[k]) for k in ("t_single", "airtime", "prev_contact"))
+        if total is None:
+            total = torch.empty((T, ld), device=command.device)
+        L.check(self.lib.kbs_rewards(self._h, C.byref(tv), C.byref(cv), L.ptr(total), L.ptr(components),
+                                     n_envs or ld, _stream()), "kbs_rewards")
+        return total
+
+    def gae(self, values, rewards, done, success, adv=None, targets=None, n_envs: int | None = None):
+        T, ld = values.shape
+        adv = torch.empty_like(values) if adv is None else adv
+        targets = torch.empty_like(values) if targets is None else targets
+        L.check(self.lib.kbs_gae(self._h, L.ptr(values), L.ptr(rewards), L.ptr(done), L.ptr(success), L.ptr(adv),
+                                 L.ptr(targets), T, ld, n_envs or ld, _stream()), "kbs_gae")
+        return adv, targets
+
+    def policy_step(self, joint_angles, joint_vel, projected_gravity, gyro, command, carry):
+        n = joint_angles.shape[0]
+        carry_out = torch.empty_like(carry)
+        action = torch.empty((n, 20), device=carry.device)
+        L.check(self.lib.kbs_policy_step(self._h, L.ptr(joint_angles), L.ptr(joint_vel), L.ptr(projected_gravity),
+                                         L.ptr(gyro), L.ptr(command), L.ptr(carry), L.ptr(carry_out), L.ptr(action),
+                                         n, _stream()), "kbs_policy_step")
+        return action, carry_out
+
+    def rollout(self, io: dict, n_envs: int) -> None:
+        """io: tensors named as the fields of kbs_rollout_io (state/noise/episode are nested dicts)."""
+        r = L.KbsRolloutIO()
+        ld = io["state"]["qpos"].shape[-1]
+        r.state = _view(L.KbsStateView, STATE_ROWS, io["state"], ld)
+        r.noise = _view(L.KbsNoiseView, NOISE_ROWS, io.get("noise"))
+        r.episode = _view(L.KbsEpisodeView, EPISODE_ROWS, io.get("episode"))
+        for k, _ in L.KbsRolloutIO._fields_:
+            if k in ("state", "noise", "episode", "T"):
+                continue
+            setattr(r, k, L.ptr(io.get(k)))
+        r.T = io["T"]
+        L.check(self.lib.kbs_rollout(self._h, C.byref(r), n_envs, _stream()), "kbs_rollout")
