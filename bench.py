@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- env control-steps/s of the kbot-joystick rollout control step on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic recorded state: a rollout of T control steps
+(observations -> LSTM actor -> sample -> PD torque -> terminations -> command update, critic value) over n_envs
+environments, followed by the 12 reward terms and the GAE scan -- BASELINE.json configs[1] (4096 envs, H = 256) at
+the reference's rollout length T = 100 (train.py:1766,1776).  Environments shard across ranks with no data-path
+collective (weak scaling: every rank owns `--envs` environments).
+
+  value   device-resident inputs (CUDA events, max over ranks)
+  e2e     the same step through the C-ABI with HOST (pinned) inputs: H2D of every input + D2H of the results
+          inside the timed region, copies pipelined against compute on a second stream
+  --impl reference   the CPU oracle restatement of the reference's JAX path (JAX/ksim are not installable here;
+          see DESIGN.md) on the host cores, bounded sample of the same workload
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "env-steps/sec (obs + LSTM actor/critic + torque + terminations + rewards + GAE)"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--T", type=int, default=100, help="control steps per rollout")
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--gemm", default="tc", choices=["tc", "simt"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def config_dict(a, world):
+    return {"workload": "BASELINE configs[1]: kbot-headless joystick control step, 4096 envs/GPU, LSTM(2x256) "
+                        "actor+critic fwd, rewards, GAE; rollout of T recorded steps",
+            "n_envs_per_gpu": a.envs, "T": a.T, "hidden": a.hidden, "depth": 2, "n_gpus": world,
+            "sharding": "envs (independent), weights replicated, no data-path collective",
+            "l2": "inputs exceed L2 (recorded state is %.2f GB per step per GPU)" % (input_bytes(a.envs, a.T) / 1e9)}
+
+
+def input_bytes(n, T):
+    ld = (n + 3) // 4 * 4
+    rows = 27 + 26 + 49 + 72 + 96 + 240 + 144 + 20 + 1 + 1 + 46 + 20 + 1 + 1 + 6 + 10
+    return rows * 4 * ld * T
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle restatement; see module docstring)
+# ------------------------------------------------------------------------------------------------------------------
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def oracle_step(n, T, hidden, seed=4321):
+    """Build a closure running one bounded sample (n envs x T steps) of the whole path in the CPU oracle."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import numpy as np
+    import kbot_oracle as O
+    from kbot_joystick_b200 import synth
+
+    p = O.OracleParams(hidden_size=hidden)
+    b = synth.make_batch(seed, T, n)
+    wa = synth.make_weights(77, 65, 40, hidden, 2)
+    wc = synth.make_weights(78, 475, 1, hidden, 2)
+    r0 = b["cmd0_rand"]
+    cmd0 = O.initial_command(r0["mode"], r0["u6"], r0["u_arms"], p)
+    st = b["state"]
+
+    def run():
+        carry = {"actor": np.zeros((n, 2, 2, hidden), np.float32), "critic": np.zeros((n, 2, 2, hidden), np.float32),
+                 "lpf_params": np.zeros((n, 20), np.float32)}
+        r = O.rollout_control_steps(wa, wc, st, b["noise"], b["episode"], b["cmd_rand"], cmd0, carry,
+                                    np.zeros((n, 3), np.float32), p)
+        tr = {"xquat": st["xquat"], "xpos": st["xpos"], "qpos": st["qpos"], "qvel": st["qvel"], "ctrl": r["ctrl"],
+              "command": r["command"], "touch_l": st["sensordata"][..., O.SD_TOUCH_L],
+              "touch_r": st["sensordata"][..., O.SD_TOUCH_R], "com_distance": st["com_distance"], "done": r["done"]}
+        _, total, _ = O.rewards(tr, O.reward_initial_carry((n,)), p)
+        adv, tgt = O.compute_ppo_inputs(r["value"], total, r["done"], r["success"], p)
+        return float(adv.sum())
+
+    return run
+
+
+def time_oracle(a, seconds, steps=None, warmup=1):
+    n, T = 512, 10
+    run = oracle_step(n, T, a.hidden)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    k = 0
+    while True:
+        run()
+        k += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and k >= steps) or (steps is None and el >= seconds):
+            break
+    return {"value": n * T * k / el, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+            "sample": f"{k} x ({n} envs x {T} control steps + rewards + GAE), NumPy oracle restatement of train.py "
+                      f"(JAX/ksim not installable), BLAS threads = host cores", "seconds": el, "n": n, "T": T, "k": k}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t = time_oracle(a, None, steps=max(a.steps, 1), warmup=max(min(a.warmup, 2), 1))
+    ms = 1e3 * t["seconds"] / t["k"]
+    line = {"metric": METRIC, "value": t["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus,
+            "steps": t["k"], "warmup": max(min(a.warmup, 2), 1), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(a, a.gpus),
+            "cpu_baseline": {k: t[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": t["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi fields via NVML)
+# ------------------------------------------------------------------------------------------------------------------
+
+class Clocks:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop, self.max_mhz, self.th = [], set(), False, None, None
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+
+    def finish(self):
+        self.stop = True
+        if self.th:
+            self.th.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    import kbot_joystick_b200  # noqa: F401
+    from kbot_joystick_b200 import _lib as L
+    from kbot_joystick_b200 import spec, synth
+    from kbot_joystick_b200.engine import KbotStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    N, T, H = a.envs, a.T, a.hidden
+    ld = (N + 3) // 4 * 4
+    path = L.GEMM_TC_3XTF32 if a.gemm == "tc" else L.GEMM_SIMT_FP32
+    eng = KbotStep(hidden_size=H, depth=2, gemm_path=path)
+    eng.pack_weights(L.NET_ACTOR, synth.weights_to_device(synth.make_weights(77, 65, 40, H, 2), dev))
+    eng.pack_weights(L.NET_CRITIC, synth.weights_to_device(synth.make_weights(78, 475, 1, H, 2), dev))
+
+    d = synth.make_batch_device(1234 + 2 + 100 * rank, T, N, dev)      # seed = 1234 + config number
+    f32 = dict(device=dev, dtype=torch.float32)
+    command = torch.zeros((T + 1, 16, ld), **f32)
+    cmd0 = torch.zeros((16, ld), **f32)
+    eng.command_update(cmd0, d["cmd_mode"][0], d["cmd_u6"][0], d["cmd_u_arms"][0], None, N)
+    command[0] = cmd0
+    io = {"state": d["state"], "noise": d["noise"], "episode": d["episode"], "eps_action": d["eps_action"],
+          "u_switch": d["u_switch"], "cmd_mode": d["cmd_mode"], "cmd_u6": d["cmd_u6"], "cmd_u_arms": d["cmd_u_arms"],
+          "command": command, "pg_carry": torch.zeros((3, ld), **f32),
+          "actor_carry": torch.zeros((2, 2, N, H), **f32), "critic_carry": torch.zeros((2, 2, N, H), **f32),
+          "lpf": torch.zeros((20, ld), **f32), "actor_obs": None, "action": torch.zeros((T, 20, ld), **f32),
+          "log_prob": torch.zeros((T, ld), **f32), "ctrl": torch.zeros((T, 20, ld), **f32), "term_codes": None,
+          "done": torch.zeros((T, ld), device=dev, dtype=torch.uint8),
+          "success": torch.zeros((T, ld), device=dev, dtype=torch.uint8), "value": torch.zeros((T, ld), **f32), "T": T}
+    rcarry = {"t_single": torch.zeros(ld, **f32), "airtime": torch.zeros((2, ld), **f32),
+              "prev_contact": torch.ones((2, ld), device=dev, dtype=torch.uint8)}
+    total = torch.zeros((T, ld), **f32)
+    adv = torch.zeros((T, ld), **f32)
+    tgt = torch.zeros((T, ld), **f32)
+
+    def step(io_=io):
+        eng.rollout(io_, N)
+        eng.rewards(io_["state"], io_["command"][:T], io_["ctrl"], io_["done"], rcarry, total=total, n_envs=N)
+        eng.gae(io_["value"], total, io_["done"], io_["success"], adv=adv, targets=tgt, n_envs=N)
+        io_["command"][0].copy_(io_["command"][T])       # next rollout continues from the last command
+
+    # ---- device-resident timing ------------------------------------------------------------------------------------
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    clocks = Clocks(local)
+    clocks.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ck = clocks.finish()
+    ms_total = max_ranks(e0.elapsed_time(e1))
+    launches = int(sum_ranks(eng.launches - l0))
+    ms_step = ms_total / a.steps
+    value = world * N * T / (ms_step * 1e-3)
+    assert torch.isfinite(adv).all() and torch.isfinite(total).all(), "non-finite outputs"
+
+    # ---- per-kernel pass (CUDA events around every launch, same step) -> roofline of the dominant kernel ----------
+    eng.profile(True)
+    step()
+    torch.cuda.synchronize()
+    prof = eng.profile_read()
+    eng.profile(False)
+    overflow = prof.pop("_overflow")
+    tot_prof = sum(v[0] for v in prof.values())
+    dom_name, (dom_ms, dom_n) = max(prof.items(), key=lambda kv: kv[1][0])
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    bf16_sus = peaks.get("bf16_tflops_sustained", 1400.0)
+    which = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    flops_actor, flops_critic = spec.net_flops(65, 40, H, 2), spec.net_flops(475, 1, H, 2)
+    lstm_layer_flops = 2 * (2 * H) * (4 * H)                      # one layer-step per env: [x|h] (2H) x 4H gates
+    roof = None
+    if dom_name in ("lstm_layer_tc_kernel", "gemm_nt_kernel(simt)"):
+        if dom_name == "lstm_layer_tc_kernel":
+            flops_per_launch = lstm_layer_flops * N
+            peak = bf16_sus / 6.0                                 # 3xTF32: TF32 = bf16 / 2, three MMAs per product
+            note = "fp32-accurate 3xTF32: peak = sustained bf16 / 6"
+        else:
+            flops_per_launch = (2 * (flops_actor + flops_critic) * N * T) / max(dom_n, 1) / 2   # avg per SIMT GEMM launch
+            peak = 72.0                                           # fp32 FFMA: 148 SMs x 128 lanes x 2 x ~1.9 GHz
+            note = "fp32 FFMA path: peak = nominal FFMA rate (interim SIMT datapath)"
+        ach = flops_per_launch / (dom_ms / dom_n * 1e-3) / 1e12
+        roof = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "launches": dom_n, "avg_launch_us": 1e3 * dom_ms / dom_n,
+                "share_of_step": dom_ms / tot_prof, "peak_source": which, "note": note}
+    else:
+        roof = {"kernel": dom_name, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
+                "traffic": None, "launches": dom_n, "avg_launch_us": 1e3 * dom_ms / dom_n,
+                "share_of_step": dom_ms / tot_prof, "peak_source": which}
+    breakdown = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+
+    # ---- end-to-end: host (pinned) inputs -> H2D -> step -> D2H of the results -------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        t = time_oracle(a, a.cpu_seconds)
+        cpu = {k: t[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)" if a.gemm == "tc" else "f32",
+                "data": "synthetic", "config": config_dict(a, world), "clocks": ck, "gpu_launches": launches,
+                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernel_breakdown_ms": breakdown,
+                "profile_overflow": overflow, "gemm_path": a.gemm}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world):
+    """Same step with every input in pinned host memory.  The recorded state is uploaded in chunks of time steps on
+    a copy stream while the compute stream runs kbs_rollout on the chunks already resident (the C-ABI takes plain
+    device pointers + T, so a chunk is just an offset view); results come back with a D2H copy."""
+    import torch
+
+    N, T = a.envs, a.T
+    chunk = 10 if T % 10 == 0 else T
+    host, h2d = {}, 0
+
+    def pin(t):
+        nonlocal h2d
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        h2d += t.numel() * t.element_size()
+        return h
+
+    for grp in ("state", "noise"):
+        host[grp] = {k: pin(v) for k, v in io[grp].items()}
+    for k in ("eps_action", "u_switch", "cmd_mode", "cmd_u6", "cmd_u_arms"):
+        host[k] = pin(io[k])
+    host["episode"] = {k: pin(v) for k, v in io["episode"].items()}
+    outs = {"adv": adv, "tgt": tgt, "total": total, "done": io["done"], "action": io["action"], "log_prob": io["log_prob"],
+            "value": io["value"]}
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in outs.items()}
+    d2h = sum(v.numel() * v.element_size() for v in outs.values())
+    copy_s = torch.cuda.Stream(device=dev)
+    comp_s = torch.cuda.current_stream()
+
+    def sub_io(t0, t1):
+        s = dict(io)
+        s["state"] = {k: v[t0:t1] for k, v in io["state"].items()}
+        s["noise"] = {k: v[t0:t1] for k, v in io["noise"].items()}
+        for k in ("eps_action", "u_switch", "cmd_mode", "cmd_u6", "cmd_u_arms", "action", "log_prob", "ctrl", "done",
+                  "success", "value"):
+            s[k] = io[k][t0:t1]
+        s["command"] = io["command"][t0:t1 + 1]
+        s["T"] = t1 - t0
+        return s
+
+    def step():
+        evs = []
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_stream(comp_s)                      # previous step's readers are done with the buffers
+            for k, v in host["episode"].items():
+                io["episode"][k].copy_(v, non_blocking=True)
+            for t0 in range(0, T, chunk):
+                t1 = t0 + chunk
+                for grp in ("state", "noise"):
+                    for k, v in host[grp].items():
+                        io[grp][k][t0:t1].copy_(v[t0:t1], non_blocking=True)
+                for k in ("eps_action", "u_switch", "cmd_mode", "cmd_u6", "cmd_u_arms"):
+                    io[k][t0:t1].copy_(host[k][t0:t1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+                evs.append(ev)
+        for i, t0 in enumerate(range(0, T, chunk)):
+            comp_s.wait_event(evs[i])
+            eng.rollout(sub_io(t0, t0 + chunk), N)
+        eng.rewards(io["state"], io["command"][:T], io["ctrl"], io["done"], rcarry, total=total, n_envs=N)
+        eng.gae(io["value"], total, io["done"], io["success"], adv=adv, targets=tgt, n_envs=N)
+        io["command"][0].copy_(io["command"][T])
+        for k, v in outs.items():
+            host_out[k].copy_(v, non_blocking=True)
+
+    for _ in range(2):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    k = max(2, min(a.steps, 5))
+    for _ in range(k):
+        step()
+    e1.record()
+    barrier()
+    ms = max_ranks(e0.elapsed_time(e1)) / k
+    assert torch.isfinite(host_out["adv"]).all()
+    return {"value": world * N * T / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": ms, "steps": k, "pipeline": f"H2D in {chunk}-step chunks on a copy stream, overlapped"}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

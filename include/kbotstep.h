@@ -152,10 +152,12 @@ int kbs_weights_pack(kbs_handle* h, int net, const kbs_net_weights* w, void* str
  *              row slices of kbs_state_view and are not copied)
  *   actor_obs  [65][ld] or NULL;  critic_obs [475][ld] or NULL
  *   pg_carry   [3][ld] in/out lagged projected gravity state (may be NULL when episode->pg_lag is NULL)
+ *   pg_reset   u8 [ld] or NULL: 1 = first step of a new episode, the lag state restarts at the current value
  *   noise may be NULL (then noisy twins = clean values). */
 int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_view* noise,
                      const kbs_episode_view* ep, const float* command, float* pg_carry,
-                     float* computed, float* actor_obs, float* critic_obs, int64_t n_envs, void* stream);
+                     const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs,
+                     int64_t n_envs, void* stream);
 
 /* Replaces: UnifiedCommand.__call__/initial_command (train.py:724-785).  Randomness explicit:
  *   u_switch [ld] U[0,1); mode int32 [ld] in 0..5; u6 [6][ld]; u_arms [10][ld].  u_switch NULL = always
@@ -253,6 +255,20 @@ int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n_envs, void* s
 
 /* Number of kernel launches this library has enqueued since the handle was created (bench bookkeeping). */
 int64_t kbs_launch_count(const kbs_handle* h);
+
+/* Per-kernel device timing for bench.py's roofline line: while enabled, every kernel launch of this handle is
+ * bracketed by CUDA events on its launch stream (up to 8192 launches; do not enable during stream capture).
+ * kbs_profile_read sums elapsed ms and launch counts per kernel id (ids 0..KBS_NUM_KERNEL_IDS-1, names from
+ * kbs_kernel_name); returns 1 if the event pool overflowed (totals partial), 0 ok. */
+/* Test hook of the tcgen05 datapath: pre-activation gates [n][4H] (eqx order i,f,g,o, bias added) of LSTM layer
+ * `layer` of `net` for row-major x [n][H], h [n][H].  Needs gemm_path = KBS_GEMM_TC_3XTF32 and packed weights. */
+int kbs_debug_tc_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,
+                       int64_t n_envs, void* stream);
+
+#define KBS_NUM_KERNEL_IDS 17
+int kbs_profile_enable(kbs_handle* h, int on);
+int kbs_profile_read(kbs_handle* h, int max_ids, double* total_ms, int64_t* launches);
+const char* kbs_kernel_name(int id);
 
 #ifdef __cplusplus
 }

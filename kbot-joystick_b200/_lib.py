@@ -87,8 +87,9 @@ EXPORTS = (
     "kbs_version", "kbs_error_string", "kbs_default_params", "kbs_create", "kbs_destroy", "kbs_get_params",
     "kbs_weights_pack", "kbs_observations", "kbs_command_update", "kbs_actor_step", "kbs_critic_step",
     "kbs_torque", "kbs_terminate", "kbs_rewards", "kbs_gae", "kbs_policy_step", "kbs_rollout",
-    "kbs_launch_count",
+    "kbs_launch_count", "kbs_profile_enable", "kbs_profile_read", "kbs_kernel_name", "kbs_debug_tc_gates",
 )
+NUM_KERNEL_IDS = 17
 
 _lib = None
 
@@ -113,7 +114,7 @@ def load() -> C.CDLL:
     lib.kbs_get_params.argtypes = [_vp, P(KbsParams)]
     lib.kbs_weights_pack.argtypes = [_vp, C.c_int, P(KbsNetWeights), _vp]
     lib.kbs_observations.argtypes = [_vp, P(KbsStateView), P(KbsNoiseView), P(KbsEpisodeView), _vp, _vp, _vp, _vp,
-                                     _vp, _i64, _vp]
+                                     _vp, _vp, _i64, _vp]
     lib.kbs_command_update.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]
     lib.kbs_actor_step.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, P(KbsActorOut), _i64, _vp]
     lib.kbs_critic_step.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]
@@ -125,9 +126,14 @@ def load() -> C.CDLL:
     lib.kbs_rollout.argtypes = [_vp, P(KbsRolloutIO), _i64, _vp]
     lib.kbs_launch_count.argtypes = [_vp]
     lib.kbs_launch_count.restype = _i64
+    lib.kbs_profile_enable.argtypes = [_vp, C.c_int]
+    lib.kbs_profile_read.argtypes = [_vp, C.c_int, P(C.c_double), P(_i64)]
+    lib.kbs_debug_tc_gates.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _i64, _vp]
+    lib.kbs_kernel_name.argtypes = [C.c_int]
+    lib.kbs_kernel_name.restype = C.c_char_p
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("kbs_error_string", "kbs_launch_count"):
+        if name not in ("kbs_error_string", "kbs_launch_count", "kbs_kernel_name"):
             fn.restype = C.c_int
     _lib = lib
     return lib

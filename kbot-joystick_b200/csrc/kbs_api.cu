@@ -64,10 +64,23 @@ kbs_noise_view noise_at(const kbs_noise_view& z, int64_t t, int64_t ld) {
   return o;
 }
 
+// Scratch layout of one trunk evaluation: [trunk workspace (path dependent) | out_rm [n][64]].
+size_t trunk_scratch_floats(const kbs_handle* h, int64_t n) {
+  return h->p.gemm_path == KBS_GEMM_TC_3XTF32 ? kbs_tc_scratch_floats(h, n) : kbs_simt_scratch_floats(h, n);
+}
+
 int trunk(kbs_handle* h, int net, const float* obs, int64_t ld, float* carry, const uint8_t* done, float* out_rm,
           int64_t n, cudaStream_t st) {
-  if (h->p.gemm_path == KBS_GEMM_TC_3XTF32) return kbs_tc_trunk(h, net, obs, ld, carry, done, out_rm, n, st);
-  return kbs_simt_trunk(h, net, obs, ld, carry, done, out_rm, n, st);
+  if (h->p.gemm_path != KBS_GEMM_TC_3XTF32) return kbs_simt_trunk(h, net, obs, ld, carry, done, out_rm, n, st);
+  // tensor-core path: input_proj (FFMA, K = 65 / 475) -> LSTM stack on tcgen05 -> output_proj (FFMA, N = 40 / 1)
+  const size_t H = size_t(h->p.hidden_size);
+  float* ws = h->scratch;
+  float* x_rm = ws + kbs_tc_scratch_floats(h, n) - 2 * size_t(n) * H - 256;   // tail of the TC workspace
+  float* hbuf = x_rm + size_t(n) * H;
+  int rc;
+  if ((rc = kbs_simt_in_proj(h, net, obs, ld, x_rm, n, st))) return rc;
+  if ((rc = kbs_tc_lstm_stack(h, net, x_rm, carry, done, hbuf, ws, n, false, st))) return rc;
+  return kbs_simt_out_proj(h, net, hbuf, out_rm, n, st);
 }
 
 constexpr int kOutLd = 64;  // row stride of the trunk output buffer
@@ -175,6 +188,10 @@ int kbs_destroy(kbs_handle* h) {
     for (int l = 0; l < KBS_MAX_DEPTH; ++l) { cudaFree(N.w_ih[l]); cudaFree(N.w_hh[l]); cudaFree(N.b[l]); }
   }
   cudaFree(h->scratch);
+  if (h->prof_ev) {
+    for (int i = 0; i < 2 * kKbsProfMaxPairs; ++i) cudaEventDestroy(h->prof_ev[i]);
+    delete[] h->prof_ev; delete[] h->prof_id;
+  }
   delete h;
   return KBS_OK;
 }
@@ -186,6 +203,50 @@ int kbs_get_params(const kbs_handle* h, kbs_params* out) {
 }
 
 int64_t kbs_launch_count(const kbs_handle* h) { return h ? h->launches : -1; }
+
+int kbs_debug_tc_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,
+                       int64_t n, void* stream) {
+  REQ(h); REQ(x_rm); REQ(h_rm); REQ(gates_out);
+  if (n <= 0 || layer < 0 || layer >= h->p.depth) return KBS_E_SHAPE;
+  int rc = kbs_scratch_reserve(h, kbs_tc_scratch_floats(h, n));
+  if (rc) return rc;
+  return kbs_tc_debug_gates(h, net, layer, x_rm, h_rm, gates_out, h->scratch, n, (cudaStream_t)stream);
+}
+
+int kbs_profile_enable(kbs_handle* h, int on) {
+  REQ(h);
+  if (on && !h->prof_ev) {
+    h->prof_ev = new (std::nothrow) cudaEvent_t[2 * kKbsProfMaxPairs];
+    h->prof_id = new (std::nothrow) int8_t[kKbsProfMaxPairs];
+    if (!h->prof_ev || !h->prof_id) return (int)cudaErrorMemoryAllocation;
+    for (int i = 0; i < 2 * kKbsProfMaxPairs; ++i) KBS_CUDA_TRY(cudaEventCreate(&h->prof_ev[i]));
+  }
+  h->prof_on = on != 0;
+  if (on) h->prof_n = 0;
+  return KBS_OK;
+}
+
+int kbs_profile_read(kbs_handle* h, int max_ids, double* total_ms, int64_t* launches) {
+  REQ(h); REQ(total_ms); REQ(launches);
+  for (int i = 0; i < max_ids; ++i) { total_ms[i] = 0.0; launches[i] = 0; }
+  for (int i = 0; i < h->prof_n; ++i) {
+    float ms = 0.f;
+    KBS_CUDA_TRY(cudaEventSynchronize(h->prof_ev[2 * i + 1]));
+    KBS_CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    const int id = h->prof_id[i];
+    if (id >= 0 && id < max_ids) { total_ms[id] += ms; launches[id]++; }
+  }
+  return h->prof_n >= kKbsProfMaxPairs ? 1 : 0;   // 1 = event pool exhausted, totals are partial
+}
+
+const char* kbs_kernel_name(int id) {
+  static const char* names[KBS_K_COUNT] = {
+      "obs_kernel", "command_kernel", "torque_kernel", "terminate_kernel", "reward_rot_kernel", "reward_terms_kernel",
+      "reward_scan_kernel", "gae_kernel", "adv_norm_kernel", "policy_io_kernels", "gemm_nt_kernel(simt)",
+      "lstm_cell_kernel", "actor_head_kernel", "critic_head_kernel", "pack_kernels", "lstm_layer_tc_kernel",
+      "proj_tc_kernel"};
+  return (id >= 0 && id < KBS_K_COUNT) ? names[id] : "?";
+}
 
 int kbs_weights_pack(kbs_handle* h, int net, const kbs_net_weights* w, void* stream) {
   REQ(h); REQ(w);
@@ -200,8 +261,9 @@ int kbs_weights_pack(kbs_handle* h, int net, const kbs_net_weights* w, void* str
 }
 
 int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_view* noise,
-                     const kbs_episode_view* ep, const float* command, float* pg_carry, float* computed,
-                     float* actor_obs, float* critic_obs, int64_t n, void* stream) {
+                     const kbs_episode_view* ep, const float* command, float* pg_carry,
+                     const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n,
+                     void* stream) {
   REQ(h); REQ(command);
   int rc = check_state(s, n, true);
   if (rc) return rc;
@@ -209,7 +271,8 @@ int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_vie
   if (noise && noise->eps_jpos) { REQ(noise->eps_jvel); REQ(noise->eps_gyro); REQ(noise->eps_pg); }
   AL(command); AL(pg_carry); AL(computed); AL(actor_obs); AL(critic_obs);
   if (!computed && !actor_obs && !critic_obs) return KBS_E_NULL;
-  return kbs_launch_observations(h, *s, noise, ep, command, pg_carry, computed, actor_obs, critic_obs, n,
+  if (reinterpret_cast<uintptr_t>(pg_reset) & 3u) return KBS_E_ALIGN;
+  return kbs_launch_observations(h, *s, noise, ep, command, pg_carry, pg_reset, computed, actor_obs, critic_obs, n,
                                  (cudaStream_t)stream);
 }
 
@@ -229,7 +292,7 @@ int kbs_actor_step(kbs_handle* h, const float* obs, int64_t ld, float* carry, fl
   if (rc) return rc;
   AL(obs); AL(carry); AL(lpf); AL(eps); AL(action_in);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t ts = kbs_simt_scratch_floats(h, n);
+  const size_t ts = trunk_scratch_floats(h, n);
   if ((rc = kbs_scratch_reserve(h, ts + size_t(n) * kOutLd))) return rc;
   float* out_rm = h->scratch + ts;
   if ((rc = trunk(h, KBS_NET_ACTOR, obs, ld, carry, done, out_rm, n, st))) return rc;
@@ -243,7 +306,7 @@ int kbs_critic_step(kbs_handle* h, const float* obs, int64_t ld, float* carry, c
   if (rc) return rc;
   AL(obs); AL(carry);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t ts = kbs_simt_scratch_floats(h, n);
+  const size_t ts = trunk_scratch_floats(h, n);
   if ((rc = kbs_scratch_reserve(h, ts + size_t(n) * kOutLd))) return rc;
   float* out_rm = h->scratch + ts;
   if ((rc = trunk(h, KBS_NET_CRITIC, obs, ld, carry, done, out_rm, n, st))) return rc;
@@ -300,7 +363,7 @@ int kbs_policy_step(kbs_handle* h, const float* joint_angles, const float* joint
   cudaStream_t st = (cudaStream_t)stream;
   const int H = h->p.hidden_size, d2 = 2 * h->p.depth;
   const int64_t ld = round_up4(n);
-  const size_t ts = kbs_simt_scratch_floats(h, n);
+  const size_t ts = trunk_scratch_floats(h, n);
   const size_t need = ts + size_t(n) * kOutLd + size_t(KBS_ACTOR_OBS + 20 + 20) * ld + size_t(d2) * n * H + 64;
   int rc = kbs_scratch_reserve(h, need);
   if (rc) return rc;
@@ -329,7 +392,7 @@ int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n, void* stream
   if (io->value) { REQ(io->critic_carry); REQ(io->state.cinert); REQ(io->state.cvel); REQ(io->state.actuator_force); }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ld = io->state.ld;
-  const size_t ts = kbs_simt_scratch_floats(h, n);
+  const size_t ts = trunk_scratch_floats(h, n);
   const size_t need = ts + size_t(n) * kOutLd + size_t(KBS_ACTOR_OBS + KBS_CRITIC_OBS) * ld + 64;
   if ((rc = kbs_scratch_reserve(h, need))) return rc;
   float* out_rm = h->scratch + ts;
@@ -347,7 +410,8 @@ int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n, void* stream
     if ((rc = kbs_launch_terminate(h, s, io->term_codes ? io->term_codes + t * 3 * ld : nullptr, done_t,
                                    io->success + t * ld, nullptr, n, st)))
       return rc;
-    if ((rc = kbs_launch_observations(h, s, &nz, &io->episode, cmd_t, io->pg_carry, nullptr, aobs,
+    if ((rc = kbs_launch_observations(h, s, &nz, &io->episode, cmd_t, io->pg_carry, t > 0 ? done_t - ld : nullptr,
+                                      nullptr, aobs,
                                       io->value ? cobs : nullptr, n, st)))
       return rc;
     if ((rc = trunk(h, KBS_NET_ACTOR, aobs, ld, io->actor_carry, done_t, out_rm, n, st))) return rc;

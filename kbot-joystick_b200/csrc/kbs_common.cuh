@@ -40,6 +40,14 @@ struct KbsNet {
   size_t tc_image_floats = 0;
 };
 
+// kernel ids of the per-kernel CUDA-event profiler (kbs_profile_*): one id per __global__ of the library
+enum KbsKernelId {
+  KBS_K_OBS = 0, KBS_K_COMMAND, KBS_K_TORQUE, KBS_K_TERMINATE, KBS_K_REWARD_ROT, KBS_K_REWARD_TERMS, KBS_K_REWARD_SCAN,
+  KBS_K_GAE, KBS_K_ADV_NORM, KBS_K_POLICY_IO, KBS_K_GEMM_SIMT, KBS_K_LSTM_CELL, KBS_K_ACTOR_HEAD, KBS_K_CRITIC_HEAD,
+  KBS_K_PACK, KBS_K_LSTM_TC, KBS_K_PROJ_TC, KBS_K_COUNT
+};
+constexpr int kKbsProfMaxPairs = 8192;
+
 struct kbs_handle {
   kbs_params p;
   int device = 0;
@@ -49,7 +57,27 @@ struct kbs_handle {
   float* scratch = nullptr;
   size_t scratch_floats = 0;
   int64_t launches = 0;
+  // per-kernel event profiler (off by default; bench.py turns it on for a dedicated pass)
+  bool prof_on = false;
+  int prof_n = 0;
+  cudaEvent_t* prof_ev = nullptr;   // 2 * kKbsProfMaxPairs events, created on first enable
+  int8_t* prof_id = nullptr;        // kernel id of each pair
 };
+
+// Wraps one kernel launch: counts it and, when profiling, brackets it with events on the launch stream.
+struct KbsLaunchScope {
+  kbs_handle* h; cudaStream_t st; int slot;
+  KbsLaunchScope(kbs_handle* h_, int id, cudaStream_t st_) : h(h_), st(st_), slot(-1) {
+    h->launches++;
+    if (h->prof_on && h->prof_n < kKbsProfMaxPairs) {
+      slot = h->prof_n++;
+      h->prof_id[slot] = (int8_t)id;
+      cudaEventRecord(h->prof_ev[2 * slot], st);
+    }
+  }
+  ~KbsLaunchScope() { if (slot >= 0) cudaEventRecord(h->prof_ev[2 * slot + 1], st); }
+};
+#define KBS_LAUNCH(h, id, st, ...) do { KbsLaunchScope _ls((h), (id), (st)); __VA_ARGS__; } while (0)
 
 // scratch management (kbs_api.cu)
 int kbs_scratch_reserve(kbs_handle* h, size_t floats);
@@ -57,8 +85,8 @@ int kbs_scratch_reserve(kbs_handle* h, size_t floats);
 // ---- stage launchers implemented across the translation units -------------------------------------
 // kbs_elementwise.cu
 int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_noise_view* nz,
-                            const kbs_episode_view* ep, const float* command, float* pg_carry, float* computed,
-                            float* actor_obs, float* critic_obs, int64_t n, cudaStream_t st);
+                            const kbs_episode_view* ep, const float* command, float* pg_carry,
+                            const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n, cudaStream_t st);
 int kbs_launch_command(kbs_handle* h, const float* cmd_in, float* cmd_out, const float* u_switch,
                        const int32_t* mode, const float* u6, const float* u_arms, const uint8_t* done, int64_t ld,
                        int64_t n, cudaStream_t st);
@@ -83,10 +111,16 @@ int kbs_simt_trunk(kbs_handle* h, int net, const float* obs_soa, int64_t ld, flo
                    float* out_rowmajor /*[n][nout_pad]*/, int64_t n, cudaStream_t st);
 size_t kbs_simt_scratch_floats(const kbs_handle* h, int64_t n);
 
+int kbs_simt_in_proj(kbs_handle* h, int net, const float* obs_soa, int64_t ld, float* x_rm, int64_t n, cudaStream_t st);
+int kbs_simt_out_proj(kbs_handle* h, int net, const float* h_rm, float* out_rm, int64_t n, cudaStream_t st);
+
 // kbs_net_tc.cu : tcgen05 3xTF32 datapath
 int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st);
-int kbs_tc_trunk(kbs_handle* h, int net, const float* obs_soa, int64_t ld, float* carry, const uint8_t* done,
-                 float* out_rowmajor, int64_t n, cudaStream_t st);
+size_t kbs_tc_scratch_floats(const kbs_handle* h, int64_t n);
+int kbs_tc_lstm_stack(kbs_handle* h, int net, const float* x_rm, float* carry, const uint8_t* done, float* out_h_rm,
+                      float* ws, int64_t n, bool carry_sb_valid, cudaStream_t st);
+int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,
+                       float* ws, int64_t n, cudaStream_t st);
 
 // heads (kbs_net_simt.cu): consume out_rowmajor
 int kbs_launch_actor_head(kbs_handle* h, const float* out_rm, int ldo, const float* obs_soa, int64_t ld, float* lpf,

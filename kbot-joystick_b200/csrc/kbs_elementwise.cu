@@ -73,7 +73,7 @@ constexpr int kCopyRowsPerSection = 46;  // 368 pure-copy rows (cinert 230 + cve
 __global__ void __launch_bounds__(kThreads)
 obs_kernel(const __grid_constant__ kbs_params P, const kbs_state_view s, const kbs_noise_view nz,
            const kbs_episode_view ep, const float* __restrict__ command, float* __restrict__ pg_carry,
-           float* __restrict__ computed, float* __restrict__ actor_obs, float* __restrict__ critic_obs, int64_t n) {
+           const uint8_t* __restrict__ pg_reset, float* __restrict__ computed, float* __restrict__ actor_obs, float* __restrict__ critic_obs, int64_t n) {
   const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
   if (n0 >= n) return;
   const int64_t ld = s.ld;
@@ -135,6 +135,11 @@ obs_kernel(const __grid_constant__ kbs_params P, const kbs_state_view s, const k
       for (int k = 0; k < 3; ++k) { kbs_ld4(nz.eps_pg, k, ld, n0, epg[k]); kbs_ld4(nz.eps_gyro, k, ld, n0, egy[k]); }
     }
     if (pg_carry) { for (int k = 0; k < 3; ++k) kbs_ld4(pg_carry, k, ld, n0, prev[k]); }
+    bool rs[4] = {false, false, false, false};  // new episode: EMA state restarts at the current value
+    if (pg_reset) {
+      const uchar4 r4 = *reinterpret_cast<const uchar4*>(pg_reset + n0);
+      rs[0] = r4.x != 0; rs[1] = r4.y != 0; rs[2] = r4.z != 0; rs[3] = r4.w != 0;
+    }
     float o_pg[3][4], o_ipg[3][4], o_nipg[3][4], o_ngy[3][4], o_carry[3][4], enc_a[5][4], enc_c[5][4];
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
@@ -145,7 +150,7 @@ obs_kernel(const __grid_constant__ kbs_params P, const kbs_state_view s, const k
       float na[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const float pv = pg_carry ? prev[k][l] : gb[k];
+        const float pv = (pg_carry && !rs[l]) ? prev[k][l] : gb[k];
         const float nc = lag[l] * pv + (1.0f - lag[l]) * gb[k];
         o_carry[k][l] = nc;
         o_pg[k][l] = gb[k];
@@ -739,15 +744,15 @@ inline unsigned groups4(int64_t n) { return unsigned((((n + 3) / 4) + kThreads -
 
 // ---- launchers ------------------------------------------------------------------------------------
 int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_noise_view* nz,
-                            const kbs_episode_view* ep, const float* command, float* pg_carry, float* computed,
-                            float* actor_obs, float* critic_obs, int64_t n, cudaStream_t st) {
+                            const kbs_episode_view* ep, const float* command, float* pg_carry,
+                            const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n, cudaStream_t st) {
   kbs_noise_view z{};
   kbs_episode_view e{};
   if (nz) z = *nz;
   if (ep) e = *ep;
   dim3 grid(groups4(n), critic_obs ? 1 + 368 / kCopyRowsPerSection : 1);
-  obs_kernel<<<grid, kThreads, 0, st>>>(h->p, s, z, e, command, pg_carry, computed, actor_obs, critic_obs, n);
-  h->launches++;
+  KBS_LAUNCH(h, KBS_K_OBS, st, (obs_kernel<<<grid, kThreads, 0, st>>>(h->p, s, z, e, command, pg_carry, pg_reset,
+                                                                      computed, actor_obs, critic_obs, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -755,8 +760,8 @@ int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_no
 int kbs_launch_command(kbs_handle* h, const float* cmd_in, float* cmd_out, const float* u_switch,
                        const int32_t* mode, const float* u6, const float* u_arms, const uint8_t* done, int64_t ld,
                        int64_t n, cudaStream_t st) {
-  command_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, cmd_in, cmd_out, u_switch, mode, u6, u_arms, done, ld, n);
-  h->launches++;
+  KBS_LAUNCH(h, KBS_K_COMMAND, st, (command_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, cmd_in, cmd_out, u_switch,
+                                                                                    mode, u6, u_arms, done, ld, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -765,16 +770,15 @@ int kbs_launch_torque(kbs_handle* h, const float* action, const kbs_state_view& 
                       float* ctrl, int64_t n, cudaStream_t st) {
   kbs_episode_view e{};
   if (ep) e = *ep;
-  torque_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, action, s, e, ctrl, n);
-  h->launches++;
+  KBS_LAUNCH(h, KBS_K_TORQUE, st, (torque_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, action, s, e, ctrl, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
 
 int kbs_launch_terminate(kbs_handle* h, const kbs_state_view& s, int32_t* codes, uint8_t* done, uint8_t* success,
                          float* pre, int64_t n, cudaStream_t st) {
-  terminate_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, s, codes, done, success, pre, n);
-  h->launches++;
+  KBS_LAUNCH(h, KBS_K_TERMINATE, st,
+             (terminate_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, s, codes, done, success, pre, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -788,12 +792,13 @@ int kbs_launch_rewards(kbs_handle* h, const kbs_traj_view& tr, const kbs_reward_
   if (rc) return rc;
   uint8_t* is_rot = reinterpret_cast<uint8_t*>(h->scratch);
   uint8_t* flags = is_rot + ld;
-  reward_rot_kernel<<<groups4(n), kThreads, 0, st>>>(tr.command, is_rot, T, ld, n);
+  KBS_LAUNCH(h, KBS_K_REWARD_ROT, st, (reward_rot_kernel<<<groups4(n), kThreads, 0, st>>>(tr.command, is_rot, T, ld, n)));
   dim3 grid(groups4(n), unsigned(T));
-  reward_terms_kernel<<<grid, kThreads, 0, st>>>(h->p, tr, is_rot, total, components, flags, n);
-  reward_scan_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(h->p, flags, tr.done, carry, total,
-                                                                                 components, T, ld, n);
-  h->launches += 3;
+  KBS_LAUNCH(h, KBS_K_REWARD_TERMS, st,
+             (reward_terms_kernel<<<grid, kThreads, 0, st>>>(h->p, tr, is_rot, total, components, flags, n)));
+  KBS_LAUNCH(h, KBS_K_REWARD_SCAN, st,
+             (reward_scan_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+                 h->p, flags, tr.done, carry, total, components, T, ld, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -801,12 +806,12 @@ int kbs_launch_rewards(kbs_handle* h, const kbs_traj_view& tr, const kbs_reward_
 int kbs_launch_gae(kbs_handle* h, const float* values, const float* rewards, const uint8_t* done,
                    const uint8_t* success, float* adv, float* targets, int64_t T, int64_t ld, int64_t n,
                    cudaStream_t st) {
-  gae_kernel<<<unsigned((n + kGaeEnvs - 1) / kGaeEnvs), 128, 0, st>>>(h->p.gamma, h->p.lam, values, rewards, done,
-                                                                      success, adv, targets, T, ld, n);
-  h->launches++;
+  KBS_LAUNCH(h, KBS_K_GAE, st,
+             (gae_kernel<<<unsigned((n + kGaeEnvs - 1) / kGaeEnvs), 128, 0, st>>>(h->p.gamma, h->p.lam, values, rewards,
+                                                                                 done, success, adv, targets, T, ld, n)));
   if (h->p.normalize_advantages == 1) {
-    adv_norm_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(h->p.adv_eps, adv, T, ld, n);
-    h->launches++;
+    KBS_LAUNCH(h, KBS_K_ADV_NORM, st,
+               (adv_norm_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(h->p.adv_eps, adv, T, ld, n)));
   }
   KBS_LAUNCH_CHECK();
   return KBS_OK;
@@ -816,11 +821,12 @@ int kbs_launch_policy_pack(kbs_handle* h, const float* ja, const float* jv, cons
                            const float* cmd, const float* carry_in, float* obs_soa, float* carry_aos, float* lpf_soa,
                            int64_t ld, int64_t n, cudaStream_t st) {
   const int H = h->p.hidden_size, d2 = 2 * h->p.depth, cw = d2 * H + 20;
-  policy_pack_obs_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(h->p, ja, jv, pg, gyro, cmd,
-                                                                                     carry_in, cw, obs_soa, lpf_soa, ld, n);
+  KBS_LAUNCH(h, KBS_K_POLICY_IO, st,
+             (policy_pack_obs_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+                 h->p, ja, jv, pg, gyro, cmd, carry_in, cw, obs_soa, lpf_soa, ld, n)));
   const int64_t tot = n * int64_t(d2) * H;
-  policy_carry_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(carry_in, carry_aos, d2, H, cw, n, true);
-  h->launches += 2;
+  KBS_LAUNCH(h, KBS_K_POLICY_IO, st,
+             (policy_carry_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(carry_in, carry_aos, d2, H, cw, n, true)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -829,10 +835,11 @@ int kbs_launch_policy_unpack(kbs_handle* h, const float* carry_aos, const float*
                              float* carry_out, float* action_out, int64_t ld, int64_t n, cudaStream_t st) {
   const int H = h->p.hidden_size, d2 = 2 * h->p.depth, cw = d2 * H + 20;
   const int64_t tot = n * int64_t(d2) * H;
-  policy_carry_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(carry_aos, carry_out, d2, H, cw, n, false);
-  policy_unpack_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(lpf_soa, mean_soa, carry_out, cw,
-                                                                                   action_out, ld, n);
-  h->launches += 2;
+  KBS_LAUNCH(h, KBS_K_POLICY_IO, st,
+             (policy_carry_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(carry_aos, carry_out, d2, H, cw, n, false)));
+  KBS_LAUNCH(h, KBS_K_POLICY_IO, st,
+             (policy_unpack_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+                 lpf_soa, mean_soa, carry_out, cw, action_out, ld, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

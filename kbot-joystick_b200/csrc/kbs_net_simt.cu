@@ -161,11 +161,13 @@ __global__ void pad_copy_kernel(const float* __restrict__ src, float* __restrict
   dst[idx] = (r < rows && c < cols) ? src[int64_t(r) * cols + c] : 0.0f;
 }
 
-int pad_copy(const float* src, float** dst, int rows, int cols, int rows_pad, int cols_pad, cudaStream_t st) {
+int pad_copy(kbs_handle* h, const float* src, float** dst, int rows, int cols, int rows_pad, int cols_pad,
+             cudaStream_t st) {
   if (*dst) { KBS_CUDA_TRY(cudaFree(*dst)); *dst = nullptr; }
   KBS_CUDA_TRY(cudaMalloc(dst, sizeof(float) * size_t(rows_pad) * cols_pad));
   const int64_t tot = int64_t(rows_pad) * cols_pad;
-  pad_copy_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(src, *dst, rows, cols, rows_pad, cols_pad);
+  KBS_LAUNCH(h, KBS_K_PACK, st,
+             (pad_copy_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(src, *dst, rows, cols, rows_pad, cols_pad)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -182,16 +184,15 @@ int kbs_simt_pack(kbs_handle* h, int net, const kbs_net_weights* w, cudaStream_t
   N.kin_pad = round_up(N.num_in, 16);
   N.nout_pad = 64;
   int rc;
-  if ((rc = pad_copy(w->w_in, &N.w_in, H, N.num_in, H, N.kin_pad, st))) return rc;
-  if ((rc = pad_copy(w->b_in, &N.b_in, 1, H, 1, H, st))) return rc;
+  if ((rc = pad_copy(h, w->w_in, &N.w_in, H, N.num_in, H, N.kin_pad, st))) return rc;
+  if ((rc = pad_copy(h, w->b_in, &N.b_in, 1, H, 1, H, st))) return rc;
   for (int l = 0; l < h->p.depth; ++l) {
-    if ((rc = pad_copy(w->w_ih[l], &N.w_ih[l], 4 * H, H, 4 * H, H, st))) return rc;
-    if ((rc = pad_copy(w->w_hh[l], &N.w_hh[l], 4 * H, H, 4 * H, H, st))) return rc;
-    if ((rc = pad_copy(w->b[l], &N.b[l], 1, 4 * H, 1, 4 * H, st))) return rc;
+    if ((rc = pad_copy(h, w->w_ih[l], &N.w_ih[l], 4 * H, H, 4 * H, H, st))) return rc;
+    if ((rc = pad_copy(h, w->w_hh[l], &N.w_hh[l], 4 * H, H, 4 * H, H, st))) return rc;
+    if ((rc = pad_copy(h, w->b[l], &N.b[l], 1, 4 * H, 1, 4 * H, st))) return rc;
   }
-  if ((rc = pad_copy(w->w_out, &N.w_out, N.num_out, H, N.nout_pad, H, st))) return rc;
-  if ((rc = pad_copy(w->b_out, &N.b_out, 1, N.num_out, 1, N.nout_pad, st))) return rc;
-  h->launches += 4 + 3 * h->p.depth;
+  if ((rc = pad_copy(h, w->w_out, &N.w_out, N.num_out, H, N.nout_pad, H, st))) return rc;
+  if ((rc = pad_copy(h, w->b_out, &N.b_out, 1, N.num_out, 1, N.nout_pad, st))) return rc;
   N.packed = true;
   return KBS_OK;
 }
@@ -211,23 +212,52 @@ int kbs_simt_trunk(kbs_handle* h, int net, const float* obs_soa, int64_t ld, flo
   float* gates = x + size_t(n) * H;
   float* hbuf = gates + size_t(n) * 4 * H;
   const unsigned mb = unsigned((n + BM - 1) / BM);
-  gemm_nt_kernel<true><<<dim3(mb, H / BN), 256, 0, st>>>(obs_soa, ld, N.w_in, N.kin_pad, N.b_in, x, H, n, N.kin_pad,
-                                                        N.num_in, 0);
-  h->launches++;
+  KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+             (gemm_nt_kernel<true><<<dim3(mb, H / BN), 256, 0, st>>>(obs_soa, ld, N.w_in, N.kin_pad, N.b_in, x, H, n,
+                                                                    N.kin_pad, N.num_in, 0)));
   const float* in = x;
   for (int l = 0; l < h->p.depth; ++l) {
     float* ch = carry + (size_t(l) * 2 + 0) * size_t(n) * H;
     float* cc = carry + (size_t(l) * 2 + 1) * size_t(n) * H;
-    gemm_nt_kernel<false><<<dim3(mb, 4 * H / BN), 256, 0, st>>>(in, H, N.w_ih[l], H, N.b[l], gates, 4 * H, n, H, H, 0);
-    gemm_nt_kernel<false><<<dim3(mb, 4 * H / BN), 256, 0, st>>>(ch, H, N.w_hh[l], H, nullptr, gates, 4 * H, n, H, H, 1);
+    KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+               (gemm_nt_kernel<false><<<dim3(mb, 4 * H / BN), 256, 0, st>>>(in, H, N.w_ih[l], H, N.b[l], gates, 4 * H, n, H,
+                                                                           H, 0)));
+    KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+               (gemm_nt_kernel<false><<<dim3(mb, 4 * H / BN), 256, 0, st>>>(ch, H, N.w_hh[l], H, nullptr, gates, 4 * H, n,
+                                                                           H, H, 1)));
     const int64_t tot = n * (H / 4);
-    lstm_cell_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(gates, ch, cc, hbuf, done, H, n);
-    h->launches += 3;
+    KBS_LAUNCH(h, KBS_K_LSTM_CELL, st,
+               (lstm_cell_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(gates, ch, cc, hbuf, done, H, n)));
     in = hbuf;
   }
-  gemm_nt_kernel<false><<<dim3(mb, N.nout_pad / BN), 256, 0, st>>>(in, H, N.w_out, H, N.b_out, out_rm, N.nout_pad, n, H,
-                                                                  H, 0);
-  h->launches++;
+  KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+             (gemm_nt_kernel<false><<<dim3(mb, N.nout_pad / BN), 256, 0, st>>>(in, H, N.w_out, H, N.b_out, out_rm,
+                                                                              N.nout_pad, n, H, H, 0)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+// input_proj / output_proj alone (used by the tensor-core trunk around its LSTM stack)
+int kbs_simt_in_proj(kbs_handle* h, int net, const float* obs_soa, int64_t ld, float* x_rm, int64_t n, cudaStream_t st) {
+  const KbsNet& N = h->net[net];
+  if (!N.packed) return KBS_E_STATE;
+  const int H = h->p.hidden_size;
+  const unsigned mb = unsigned((n + BM - 1) / BM);
+  KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+             (gemm_nt_kernel<true><<<dim3(mb, H / BN), 256, 0, st>>>(obs_soa, ld, N.w_in, N.kin_pad, N.b_in, x_rm, H, n,
+                                                                    N.kin_pad, N.num_in, 0)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_simt_out_proj(kbs_handle* h, int net, const float* h_rm, float* out_rm, int64_t n, cudaStream_t st) {
+  const KbsNet& N = h->net[net];
+  if (!N.packed) return KBS_E_STATE;
+  const int H = h->p.hidden_size;
+  const unsigned mb = unsigned((n + BM - 1) / BM);
+  KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+             (gemm_nt_kernel<false><<<dim3(mb, N.nout_pad / BN), 256, 0, st>>>(h_rm, H, N.w_out, H, N.b_out, out_rm,
+                                                                              N.nout_pad, n, H, H, 0)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -235,16 +265,16 @@ int kbs_simt_trunk(kbs_handle* h, int net, const float* obs_soa, int64_t ld, flo
 int kbs_launch_actor_head(kbs_handle* h, const float* out_rm, int ldo, const float* obs_soa, int64_t ld, float* lpf,
                           const float* eps, const float* action_in, const uint8_t* done, const kbs_actor_out& o,
                           int64_t n, cudaStream_t st) {
-  actor_head_kernel<<<unsigned((n + 127) / 128), 128, 0, st>>>(h->p, out_rm, ldo, obs_soa, ld, lpf, eps, action_in, done,
-                                                               o, n);
-  h->launches++;
+  KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
+             (actor_head_kernel<<<unsigned((n + 127) / 128), 128, 0, st>>>(h->p, out_rm, ldo, obs_soa, ld, lpf, eps,
+                                                                          action_in, done, o, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
 
 int kbs_launch_critic_head(kbs_handle* h, const float* out_rm, int ldo, float* value, int64_t n, cudaStream_t st) {
-  critic_head_kernel<<<unsigned((n + 127) / 128), 128, 0, st>>>(out_rm, ldo, value, n);
-  h->launches++;
+  KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
+             (critic_head_kernel<<<unsigned((n + 127) / 128), 128, 0, st>>>(out_rm, ldo, value, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

@@ -83,6 +83,20 @@ class KbotStep:
     def launches(self) -> int:
         return int(self.lib.kbs_launch_count(self._h))
 
+    def profile(self, on: bool) -> None:
+        L.check(self.lib.kbs_profile_enable(self._h, 1 if on else 0), "kbs_profile_enable")
+
+    def profile_read(self) -> dict:
+        """{kernel name: (total ms, launches)} for the launches made while profiling was enabled."""
+        ms = (C.c_double * L.NUM_KERNEL_IDS)()
+        cnt = (C.c_int64 * L.NUM_KERNEL_IDS)()
+        rc = self.lib.kbs_profile_read(self._h, L.NUM_KERNEL_IDS, ms, cnt)
+        if rc not in (0, 1):
+            L.check(rc, "kbs_profile_read")
+        out = {self.lib.kbs_kernel_name(i).decode(): (ms[i], int(cnt[i])) for i in range(L.NUM_KERNEL_IDS) if cnt[i]}
+        out["_overflow"] = bool(rc)
+        return out
+
     # ---- weights -------------------------------------------------------------------------------------
     def pack_weights(self, net: int, w: dict) -> None:
         """w: eqx-layout CUDA tensors {w_in,b_in,w_out,b_out, layers:[{w_ih,w_hh,b}]} (train.py:847-1004)."""
@@ -95,14 +109,16 @@ class KbotStep:
 
     # ---- stages --------------------------------------------------------------------------------------
     def observations(self, state: dict, command, noise: dict | None = None, episode: dict | None = None,
-                     pg_carry=None, computed=None, actor_obs=None, critic_obs=None, n_envs: int | None = None):
+                     pg_carry=None, computed=None, actor_obs=None, critic_obs=None, n_envs: int | None = None,
+                     pg_reset=None):
         ld = state["qpos"].shape[-1]
         n = n_envs or ld
         sv = _view(L.KbsStateView, STATE_ROWS, state, ld)
         nv = _view(L.KbsNoiseView, NOISE_ROWS, noise)
         ev = _view(L.KbsEpisodeView, EPISODE_ROWS, episode)
         L.check(self.lib.kbs_observations(self._h, C.byref(sv), C.byref(nv), C.byref(ev), L.ptr(command),
-                                          L.ptr(pg_carry), L.ptr(computed), L.ptr(actor_obs), L.ptr(critic_obs), n,
+                                          L.ptr(pg_carry), L.ptr(pg_reset), L.ptr(computed), L.ptr(actor_obs),
+                                          L.ptr(critic_obs), n,
                                           _stream()), "kbs_observations")
 
     def command_update(self, command, mode, u6, u_arms, u_switch=None, n_envs: int | None = None) -> None:

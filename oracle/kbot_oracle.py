@@ -256,7 +256,7 @@ def feet_position_obs(xpos: np.ndarray, xquat: np.ndarray, p: OracleParams) -> n
 
 
 def get_observations(state: dict, noise: dict | None, episode: dict | None, pg_carry: np.ndarray | None,
-                     p: OracleParams) -> tuple[dict, np.ndarray | None]:
+                     p: OracleParams, reset: np.ndarray | None = None) -> tuple[dict, np.ndarray | None]:
     """[R]+[U] the get_observations table, train.py:1155-1204 (21 observations + 4 noisy twins).
 
     state: qpos[...,27] qvel[...,26] qacc[...,26] sensordata[...,49] xpos[...,24,3] xquat[...,24,4]
@@ -264,6 +264,8 @@ def get_observations(state: dict, noise: dict | None, episode: dict | None, pg_c
     noise: eps_jpos[...,20] eps_jvel[...,20] in U(-1,1); eps_gyro[...,3] eps_pg[...,3] ~ N(0,1)
     episode: jpos_bias[...,20], pg_lag[...], pg_bias[...,3]  (per-episode randomisation)
     pg_carry: [...,3] EMA state of the lagged projected gravity (O4)
+    reset: [...] bool or None -- where True the EMA state is re-initialised to the current projected gravity
+           (first step of a new episode; [U] ksim re-inits observation carries on done)
     Returns (obs dict, new pg_carry).  com_distance is consumed as a recorded scalar.
     """
     qpos, qvel, sd = state["qpos"], state["qvel"], state["sensordata"]
@@ -305,6 +307,8 @@ def get_observations(state: dict, noise: dict | None, episode: dict | None, pg_c
         lag = episode["pg_lag"][..., None] if episode is not None else np.zeros_like(g_b[..., :1])
         pgb = episode["pg_bias"] if episode is not None else np.zeros_like(g_b)
         prev = pg_carry if pg_carry is not None else g_b
+        if reset is not None:
+            prev = np.where(reset[..., None], g_b, prev)
         new_carry = lag * prev + (_c(x, 1.0) - lag) * g_b
         o["imu_projected_gravity"] = new_carry + pgb
         o["noisy_imu_projected_gravity"] = (new_carry + pgb) + _c(x, p.pg_noise_std) * noise["eps_pg"]
@@ -797,3 +801,55 @@ def compute_ppo_inputs(values, rewards_t, done, success, p: OracleParams):
     if p.normalize_advantages == 1:
         adv = adv / (np.std(adv, axis=0, keepdims=True) + _c(values, p.adv_eps))
     return adv, targets
+
+
+# --------------------------------------------------------------------------------------
+# The rollout control step on recorded state, stage order of ksim's step_engine around mjx.step
+# --------------------------------------------------------------------------------------
+
+
+def rollout_control_steps(w_actor, w_critic, state: dict, noise: dict, episode: dict, cmd_rand: dict, cmd0, carry: dict,
+                          pg_carry, p: OracleParams, argmax: bool = False, with_critic: bool = True) -> dict:
+    """T control steps over recorded state [T, N, ...]:  terminations -> observations -> sample_action ->
+    PD torque -> (critic value) -> command update, carries reset to initial where done (train.py:1502-1506,1526).
+
+    state/noise: dicts of [T, N, ...]; episode: dict of [N, ...]; cmd_rand: mode/u6/u_arms/u_switch [T, N, ...];
+    cmd0 [N,16]; carry: {"actor","critic" [N,depth,2,H], "lpf_params" [N,20]}; pg_carry [N,3].
+    Returns per-step stacks and the final carries.
+    """
+    T = state["qpos"].shape[0]
+    ac, cc, lpf = carry["actor"], carry["critic"], carry["lpf_params"]
+    cmd = cmd0
+    out = {k: [] for k in ("actor_obs", "action", "log_prob", "ctrl", "codes", "done", "success", "value", "command",
+                           "mean", "std")}
+    prev_done = None
+    for t in range(T):
+        st = {k: v[t] for k, v in state.items()}
+        nz = {k: v[t] for k, v in noise.items()}
+        codes, done, success = terminations(st["xpos"], st["qpos"][..., 3:7], st["time"], p)
+        o, pg_carry = get_observations(st, nz, episode, pg_carry, p, reset=prev_done)
+        a_obs = actor_obs_from_dict(o, cmd)
+        act, mean, std, ac, lpf = sample_action(w_actor, a_obs, ac, lpf, nz["eps_action"], argmax, p)
+        logp = mvn_log_prob(mean, std, act)
+        ctrl = position_actuator_torque(act, st["qpos"][..., 7:], st["qvel"][..., 6:], episode.get("kp"),
+                                        episode.get("kd"), episode.get("tau_limit"), episode.get("action_bias"),
+                                        episode.get("torque_bias"))
+        out["command"].append(cmd)
+        if with_critic:
+            value, cc = critic_forward(w_critic, critic_obs_from_dict(o, cmd), cc)
+            out["value"].append(value[..., 0])
+            cc = np.where(done[..., None, None, None], np.zeros_like(cc), cc)
+        ac = np.where(done[..., None, None, None], np.zeros_like(ac), ac)
+        lpf = np.where(done[..., None], np.zeros_like(lpf), lpf)
+        # a finished episode draws initial_command for the next one; otherwise the per-step switch law
+        u_sw = np.where(done, np.asarray(-1.0, cmd.dtype), cmd_rand["u_switch"][t])
+        cmd = command_step(cmd, u_sw, cmd_rand["mode"][t], cmd_rand["u6"][t], cmd_rand["u_arms"][t], p)
+        for k, v in (("actor_obs", a_obs), ("action", act), ("log_prob", logp), ("ctrl", ctrl), ("codes", codes),
+                     ("done", done), ("success", success), ("mean", mean), ("std", std)):
+            out[k].append(v)
+        prev_done = done
+    res = {k: np.stack(v, axis=0) for k, v in out.items() if v}
+    res["command_next"] = cmd
+    res["carry"] = {"actor": ac, "critic": cc, "lpf_params": lpf}
+    res["pg_carry"] = pg_carry
+    return res

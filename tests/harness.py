@@ -90,3 +90,86 @@ def carry_to_np(c: torch.Tensor, n: int) -> np.ndarray:
 
 def carry_from_np(c: np.ndarray, device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(np.moveaxis(c, 0, 2))).to(device)
+
+
+def scaled_err(gpu, ref, rtol=RTOL, atol=1e-6) -> float:
+    """max |gpu-ref| / (rtol |ref| + atol): <= 1 passes the north_star tolerance."""
+    gpu = np.asarray(gpu, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert gpu.shape == ref.shape, (gpu.shape, ref.shape)
+    if gpu.size == 0:
+        return 0.0
+    return float(np.max(np.abs(gpu - ref) / (rtol * np.abs(ref) + atol)))
+
+
+def rollout_buffers(b: "Batch", hidden: int, depth: int, with_critic: bool = True) -> dict:
+    """Device buffers of kbs_rollout_io for batch b (zero-initialised carries = get_initial_model_carry)."""
+    T, N, ld, dev = b.T, b.N, b.ld, b.dev
+    f = dict(device=dev, dtype=torch.float32)
+    command = torch.zeros((T + 1, 16, ld), **f)
+    command[0] = b.cmd0
+    io = {
+        "state": b.state, "noise": {k: v for k, v in b.noise.items() if k != "eps_action"}, "episode": b.episode,
+        "eps_action": b.noise["eps_action"], "u_switch": b.cmd_rand["u_switch"], "cmd_mode": b.cmd_rand["mode"],
+        "cmd_u6": b.cmd_rand["u6"], "cmd_u_arms": b.cmd_rand["u_arms"], "command": command,
+        "pg_carry": torch.zeros((3, ld), **f),
+        "actor_carry": torch.zeros((depth, 2, N, hidden), **f),
+        "critic_carry": torch.zeros((depth, 2, N, hidden), **f) if with_critic else None,
+        "lpf": torch.zeros((20, ld), **f),
+        "actor_obs": torch.zeros((T, 65, ld), **f), "action": torch.zeros((T, 20, ld), **f),
+        "log_prob": torch.zeros((T, ld), **f), "ctrl": torch.zeros((T, 20, ld), **f),
+        "term_codes": torch.zeros((T, 3, ld), device=dev, dtype=torch.int32),
+        "done": torch.zeros((T, ld), device=dev, dtype=torch.uint8),
+        "success": torch.zeros((T, ld), device=dev, dtype=torch.uint8),
+        "value": torch.zeros((T, ld), **f) if with_critic else None, "T": T,
+    }
+    return io
+
+
+def oracle_rollout(b: "Batch", wa, wc, hidden: int, depth: int, with_critic: bool = True, p=None) -> dict:
+    p = p or O.OracleParams(hidden_size=hidden, depth=depth)
+    N = b.N
+    carry = {"actor": np.zeros((N, depth, 2, hidden), np.float32), "critic": np.zeros((N, depth, 2, hidden), np.float32),
+             "lpf_params": np.zeros((N, 20), np.float32)}
+    return O.rollout_control_steps(wa, wc, b.np["state"], b.np["noise"], b.np["episode"], b.np["cmd_rand"], b.cmd0_np,
+                                   carry, np.zeros((N, 3), np.float32), p, with_critic=with_critic)
+
+
+def compare_rollout(io: dict, ref: dict, N: int, with_critic: bool = True) -> dict:
+    """scaled errors (<= 1 passes) of every float output; integer outputs must be bit-exact (raises otherwise)."""
+    s = synth.from_soa
+    exact(s(io["term_codes"], N, (3,)), ref["codes"], "term_codes")
+    exact(s(io["done"], N).astype(bool), ref["done"], "done")
+    exact(s(io["success"], N).astype(bool), ref["success"], "success")
+    e = {
+        "actor_obs": scaled_err(s(io["actor_obs"], N, (65,)), ref["actor_obs"]),
+        "action": scaled_err(s(io["action"], N, (20,)), ref["action"]),
+        "log_prob": scaled_err(s(io["log_prob"], N), ref["log_prob"], atol=1e-5),   # |log_prob| ~ 10-60
+        "ctrl": scaled_err(s(io["ctrl"], N, (20,)), ref["ctrl"], atol=1e-4),         # torques ~ 10-100 N m
+        "command": scaled_err(s(io["command"][:-1], N, (16,)), ref["command"]),
+        "command_next": scaled_err(s(io["command"][-1], N, (16,)), ref["command_next"]),
+        "actor_carry": scaled_err(carry_to_np(io["actor_carry"], N), ref["carry"]["actor"]),
+        "lpf": scaled_err(s(io["lpf"], N, (20,)), ref["carry"]["lpf_params"]),
+        "pg_carry": scaled_err(s(io["pg_carry"], N, (3,)), ref["pg_carry"], atol=1e-5),
+    }
+    if with_critic:
+        # critic inputs reach |x| ~ 50 (raw touch force, train.py:1413-1414): the fp32 rounding floor of its 475-term
+        # input projection is ~475 eps |w x| ~ 3e-6 for ANY summation order, hence the 1e-5 absolute floor here.
+        e["value"] = scaled_err(s(io["value"], N), ref["value"], atol=1e-5)
+        e["critic_carry"] = scaled_err(carry_to_np(io["critic_carry"], N), ref["carry"]["critic"], atol=1e-5)
+    return e
+
+
+def run_rollout_case(seed: int, T: int, N: int, hidden: int, device, gemm_path=L.GEMM_SIMT_FP32, depth: int = 2,
+                     with_critic: bool = True) -> dict:
+    b = Batch(seed, T, N, device)
+    eng, wa, wc = make_engine(hidden=hidden, depth=depth, gemm_path=gemm_path, device=device)
+    io = rollout_buffers(b, hidden, depth, with_critic)
+    l0 = eng.launches
+    eng.rollout(io, N)
+    torch.cuda.synchronize()
+    ref = oracle_rollout(b, wa, wc, hidden, depth, with_critic)
+    errs = compare_rollout(io, ref, N, with_critic)
+    out = {"errors": errs, "launches": eng.launches - l0, "done_count": ref["done"].sum()}
+    eng.close()
+    return out

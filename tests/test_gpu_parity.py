@@ -1,0 +1,386 @@
+"""GPU parity tests: every stage of the control step, called through the C-ABI of libkbotstep.so, against the CPU
+oracle on the same seeded inputs.  Bit-exact for termination codes / done / success / contact flags; 1e-5 relative
+(+ a stated absolute floor) for fp32 outputs.  Sizes cover BASELINE config 1 (N=32), ragged and tiny N."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import harness as Hn
+import kbot_oracle as O
+from harness import Batch, P, close, exact
+from kbot_joystick_b200 import _lib as L
+from kbot_joystick_b200 import synth
+from kbot_joystick_b200.engine import COMPUTED_OBS_ROWS
+
+pytestmark = pytest.mark.gpu
+
+S = synth.from_soa
+PATHS = [pytest.param(L.GEMM_SIMT_FP32, id="simt"), pytest.param(L.GEMM_TC_3XTF32, id="tc3xtf32")]
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_device, lib_built):
+    return cuda_device
+
+
+@pytest.fixture(scope="module")
+def eng(dev):
+    e, wa, wc = Hn.make_engine(device=dev)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("N", [1, 3, 32, 130, 1001])
+def test_observations(eng, dev, N):
+    b = Batch(100 + N, 2, N, dev)
+    ld = b.ld
+    pg = torch.zeros((3, ld), device=dev)
+    pg_np = np.zeros((N, 3), np.float32)
+    prev_done = None
+    for t in range(2):
+        comp = torch.zeros((78, ld), device=dev)
+        aobs = torch.zeros((65, ld), device=dev)
+        cobs = torch.zeros((475, ld), device=dev)
+        reset = None
+        if t == 1:
+            prev_done = (np.arange(N) % 3 == 0)
+            reset = synth.to_soa(prev_done.astype(np.uint8), 0, dev)
+        eng.observations(b.state_at(t), b.cmd0, b.noise_at(t), b.episode, pg, comp, aobs, cobs, N, pg_reset=reset)
+        o, pg_np = O.get_observations(b.np_state_at(t), b.np_noise_at(t), b.np["episode"], pg_np, P, reset=prev_done)
+        for name, (r0, r1) in COMPUTED_OBS_ROWS.items():
+            close(S(comp[r0:r1], N, (r1 - r0,)), o[name], name, atol=1e-5 if "gravity" in name else 1e-6)
+        close(S(aobs, N, (65,)), O.actor_obs_from_dict(o, b.cmd0_np), f"actor_obs t={t}")
+        close(S(cobs, N, (475,)), O.critic_obs_from_dict(o, b.cmd0_np), f"critic_obs t={t}")
+        close(S(pg, N, (3,)), pg_np, "pg_carry", atol=1e-5)
+    # pure slices of the table are bit-exact copies
+    exact(S(cobs[80:310], N, (230,)), o["center_of_mass_inertia"], "cinert dump")
+    exact(S(cobs[310:448], N, (138,)), o["center_of_mass_velocity"], "cvel dump")
+    exact(S(aobs[48], N), O.zero_cmd_mask(b.cmd0_np).astype(np.float32), "zero_cmd flag")
+
+
+def test_observations_without_noise_twins_equal_clean(eng, dev):
+    b = Batch(7, 1, 64, dev)
+    aobs = torch.zeros((65, b.ld), device=dev)
+    cobs = torch.zeros((475, b.ld), device=dev)
+    eng.observations(b.state_at(0), b.cmd0, None, None, None, None, aobs, cobs, 64)
+    exact(aobs.cpu().numpy(), cobs[:65].cpu().numpy(), "noise-free actor block == critic block")
+
+
+@pytest.mark.parametrize("N", [2, 32, 777])
+def test_command_update(eng, dev, N):
+    b = Batch(200 + N, 3, N, dev)
+    cmd = b.cmd0.clone()
+    ref = b.cmd0_np
+    # initial_command (u_switch NULL) reproduces cmd0
+    init = torch.zeros_like(cmd)
+    r0 = {k: synth.to_soa(v, 0, dev) for k, v in b.np["cmd0_rand"].items()}
+    eng.command_update(init, r0["mode"], r0["u6"], r0["u_arms"], None, N)
+    exact(S(init, N, (16,)), ref, "initial_command")
+    r = b.np["cmd_rand"]
+    for t in range(3):
+        us = (r["u_switch"][t] * 0.02).astype(np.float32)       # ~20 % of envs switch
+        eng.command_update(cmd, b.cmd_rand["mode"][t], b.cmd_rand["u6"][t], b.cmd_rand["u_arms"][t],
+                           synth.to_soa(us, 0, dev), N)
+        ref = O.command_step(ref, us, r["mode"][t], r["u6"][t], r["u_arms"][t], P)
+        exact(S(cmd, N, (16,)), ref, f"command t={t}")
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("hidden,N", [(256, 32), (256, 200), (128, 77), (256, 1)])
+def test_actor_and_critic_step(dev, path, hidden, N):
+    e, wa, wc = Hn.make_engine(hidden=hidden, gemm_path=path, device=dev)
+    p = O.OracleParams(hidden_size=hidden)
+    b = Batch(300 + N, 3, N, dev)
+    ld = b.ld
+    ac = torch.zeros((2, 2, N, hidden), device=dev)
+    cc = torch.zeros((2, 2, N, hidden), device=dev)
+    lpf = torch.zeros((20, ld), device=dev)
+    ac_np = np.zeros((N, 2, 2, hidden), np.float32)
+    cc_np = np.zeros_like(ac_np)
+    lpf_np = np.zeros((N, 20), np.float32)
+    rng = np.random.default_rng(9)
+    for t in range(3):
+        o, _ = O.get_observations(b.np_state_at(t), b.np_noise_at(t), b.np["episode"], None, P)
+        a_obs, c_obs = O.actor_obs_from_dict(o, b.cmd0_np), O.critic_obs_from_dict(o, b.cmd0_np)
+        done_np = rng.random(N) < 0.3
+        done = synth.to_soa(done_np.astype(np.uint8), 0, dev)
+        eps = b.noise["eps_action"][t]
+        out = e.actor_step(synth.to_soa(a_obs, 0, dev), ac, lpf, eps=eps, done=done, n_envs=N)
+        act, mean, std, ac_np, lpf_np = O.sample_action(wa, a_obs, ac_np, lpf_np, b.np["noise"]["eps_action"][t], False, p)
+        close(S(out["mean"], N, (20,)), mean, f"mean t={t}")
+        close(S(out["std"], N, (20,)), std, f"std t={t}")
+        close(S(out["action"], N, (20,)), act, f"action t={t}")
+        close(S(out["log_prob"], N), O.mvn_log_prob(mean, std, act), f"log_prob t={t}", atol=1e-5)
+        close(S(out["entropy"], N), O.mvn_entropy(std), f"entropy t={t}", atol=1e-5)
+        ac_np = np.where(done_np[:, None, None, None], 0, ac_np).astype(np.float32)
+        lpf_np = np.where(done_np[:, None], 0, lpf_np).astype(np.float32)
+        close(Hn.carry_to_np(ac, N), ac_np, f"actor carry t={t}")
+        close(S(lpf, N, (20,)), lpf_np, f"lpf t={t}")
+        val = e.critic_step(synth.to_soa(c_obs, 0, dev), cc, done=done, n_envs=N)
+        v_np, cc_np = O.critic_forward(wc, c_obs, cc_np)
+        close(S(val, N), v_np[:, 0], f"value t={t}", atol=1e-5)       # see harness.compare_rollout on the floor
+        cc_np = np.where(done_np[:, None, None, None], 0, cc_np).astype(np.float32)
+        close(Hn.carry_to_np(cc, N), cc_np, f"critic carry t={t}", atol=1e-5)
+    # stored-transition path of _ppo_scan_fn: log-prob of a given action, argmax mode
+    a_in = (mean + 0.3 * rng.standard_normal(mean.shape)).astype(np.float32)
+    ac2, lpf2 = ac.clone(), lpf.clone()
+    out = e.actor_step(synth.to_soa(a_obs, 0, dev), ac2, lpf2, eps=None, action_in=synth.to_soa(a_in, 0, dev), n_envs=N)
+    _, mean2, std2, _, _ = O.sample_action(wa, a_obs, ac_np, lpf_np, None, True, p)
+    close(S(out["action"], N, (20,)), mean2, "mode()")
+    close(S(out["log_prob"], N), O.mvn_log_prob(mean2, std2, a_in), "log_prob(action_in)", atol=1e-5)
+    e.close()
+
+
+@pytest.mark.parametrize("N", [5, 32, 515])
+def test_torque(eng, dev, N):
+    b = Batch(400 + N, 1, N, dev)
+    act_np = b.np["state"]["qpos"][0][:, 7:] + 0.2 * b.np["noise"]["eps_action"][0]
+    act = synth.to_soa(act_np, 0, dev)
+    ep = b.np["episode"]
+    q, qd = b.np["state"]["qpos"][0][:, 7:], b.np["state"]["qvel"][0][:, 6:]
+    ctrl = eng.torque(act, b.state_at(0), b.episode, n_envs=N)
+    ref = O.position_actuator_torque(act_np, q, qd, ep["kp"], ep["kd"], ep["tau_limit"], ep["action_bias"], ep["torque_bias"])
+    close(S(ctrl, N, (20,)), ref, "ctrl (randomised gains)", atol=1e-4)
+    assert (np.abs(ref) == ep["tau_limit"]).any(), "clip branch not exercised"
+    ctrl = eng.torque(act, b.state_at(0), None, n_envs=N)
+    close(S(ctrl, N, (20,)), O.position_actuator_torque(act_np, q, qd), "ctrl (nominal gains)", atol=1e-4)
+
+
+@pytest.mark.parametrize("N", [1, 32, 4099])
+def test_terminations_bit_exact(eng, dev, N):
+    b = Batch(500 + N, 1, N, dev)
+    out = eng.terminate(b.state_at(0), N, want_pre=True)
+    st = b.np_state_at(0)
+    codes, done, succ = O.terminations(st["xpos"], st["qpos"][:, 3:7], st["time"], P)
+    exact(S(out["codes"], N, (3,)), codes, "codes")
+    exact(S(out["done"], N).astype(bool), done, "done")
+    exact(S(out["success"], N).astype(bool), succ, "success")
+    close(S(out["pre"][0], N), O.bad_z_height(st["xpos"]), "height")
+    close(S(out["pre"][1], N), O.upright_tilt(st["qpos"][:, 3:7], P), "tilt", atol=1e-5)
+    if N >= 32:
+        assert done.any() and (~done).any()
+
+
+def _traj(b, seed=11):
+    """Recorded trajectory for the reward tests (command evolves by the command law; ~10 % done)."""
+    rng = np.random.default_rng(seed)
+    st = b.np["state"]
+    T, N = b.T, b.N
+    r = b.np["cmd_rand"]
+    cmd = np.empty((T, N, 16), np.float32)
+    c = b.cmd0_np
+    for t in range(T):
+        cmd[t] = c
+        c = O.command_step(c, (r["u_switch"][t] * 0.05).astype(np.float32), r["mode"][t], r["u6"][t], r["u_arms"][t], P)
+    return {"xquat": st["xquat"], "xpos": st["xpos"], "qpos": st["qpos"], "qvel": st["qvel"],
+            "ctrl": (20 * rng.standard_normal((T, N, 20))).astype(np.float32), "command": cmd,
+            "touch_l": st["sensordata"][..., O.SD_TOUCH_L], "touch_r": st["sensordata"][..., O.SD_TOUCH_R],
+            "com_distance": st["com_distance"], "done": rng.random((T, N)) < 0.1}
+
+
+# conditioning of 1 - (q.q)^2 with error scales 0.01-0.03 amplifies 1-ulp libm differences ~1e2-1e3x: these two terms
+# are checked at 2e-3 relative against the fp32 oracle (the fp32 oracle itself is only 2e-3 from fp64, see
+# tests/test_oracle_cpu.py::test_fp32_oracle_tracks_fp64) AND at the same bound against the fp64 oracle.
+ILL_CONDITIONED = {"roll_pitch": 2e-3, "feet_orient": 2e-3}
+
+
+@pytest.mark.parametrize("T,N", [(16, 32), (40, 130), (1, 7)])
+def test_rewards(eng, dev, T, N):
+    b = Batch(600 + N, T, N, dev)
+    tr = _traj(b)
+    ld = b.ld
+    c0 = O.reward_initial_carry((N,))
+    c0["t_single"] = (np.random.default_rng(3).random(N) * 3).astype(np.float32)
+    comp_np, total_np, c1 = O.rewards(tr, c0, P)
+    carry = {"t_single": synth.to_soa(c0["t_single"], 0, dev), "airtime": synth.to_soa(c0["airtime"], 0, dev),
+             "prev_contact": synth.to_soa(c0["prev_contact"].astype(np.uint8), 0, dev)}
+    comp = torch.zeros((T, 12, ld), device=dev)
+    total = eng.rewards(b.state, synth.to_soa(tr["command"], 1, dev), synth.to_soa(tr["ctrl"], 1, dev),
+                        synth.to_soa(tr["done"].astype(np.uint8), 1, dev), carry, components=comp, n_envs=N)
+    tr64 = {k: (v.astype(np.float64) if v.dtype == np.float32 else v) for k, v in tr.items()}
+    c064 = {k: (v.astype(np.float64) if v.dtype == np.float32 else v) for k, v in c0.items()}
+    comp64, total64, _ = O.rewards(tr64, c064, P)
+    for i, name in enumerate(O.REWARD_NAMES):
+        g = S(comp[:, i], N)
+        if name in ILL_CONDITIONED:
+            close(g, comp_np[name], name, rtol=ILL_CONDITIONED[name])
+            close(g, comp64[name], name + " vs fp64", rtol=ILL_CONDITIONED[name])
+        elif name in ("single_contact", "no_contact_p"):
+            exact(g, comp_np[name].astype(np.float32), name)
+        else:
+            close(g, comp_np[name], name)
+    close(S(total, N), total_np, "total", rtol=4e-4)     # bounded by the two ill-conditioned terms (scale 0.2, 0.1)
+    close(S(total, N), total64, "total vs fp64", rtol=4e-4)
+    close(S(carry["t_single"], N), c1["t_single"], "carry t_single")
+    close(S(carry["airtime"], N, (2,)), c1["airtime"], "carry airtime")
+    exact(S(carry["prev_contact"], N, (2,)).astype(bool), c1["prev_contact"], "carry prev_contact")
+
+
+def test_rewards_streaming_equivalence_full_size(eng, dev):
+    """Property at BASELINE config-2 size (4096 envs x 100 steps): two half-rollouts chained through the reward carry
+    reproduce the stateful terms of the whole rollout bit for bit."""
+    T, N = 100, 4096
+    d = synth.make_batch_device(21, T, N, dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    cmd = torch.zeros((T, 16, N), device=dev)
+    cmd[:, 0] = (torch.rand(T, N, generator=g, device=dev) < 0.6).float() * 0.7
+    ctrl = 20 * torch.randn(T, 20, N, generator=g, device=dev)
+    done = (torch.rand(T, N, generator=g, device=dev) < 0.02).to(torch.uint8)
+
+    def carry0():
+        return {"t_single": torch.zeros(N, device=dev), "airtime": torch.zeros((2, N), device=dev),
+                "prev_contact": torch.ones((2, N), device=dev, dtype=torch.uint8)}
+
+    cw = carry0()
+    comp_w = torch.zeros((T, 12, N), device=dev)
+    eng.rewards(d["state"], cmd, ctrl, done, cw, components=comp_w, n_envs=N)
+    ch = carry0()
+    h = T // 2
+    comp_a = torch.zeros((h, 12, N), device=dev)
+    comp_b = torch.zeros((T - h, 12, N), device=dev)
+    eng.rewards({k: v[:h].contiguous() for k, v in d["state"].items()}, cmd[:h].contiguous(), ctrl[:h].contiguous(),
+                done[:h].contiguous(), ch, components=comp_a, n_envs=N)
+    eng.rewards({k: v[h:].contiguous() for k, v in d["state"].items()}, cmd[h:].contiguous(), ctrl[h:].contiguous(),
+                done[h:].contiguous(), ch, components=comp_b, n_envs=N)
+    for i in (5, 7):   # single_contact, feet_airtime
+        assert torch.equal(torch.cat([comp_a[:, i], comp_b[:, i]]), comp_w[:, i]), O.REWARD_NAMES[i]
+    for k in cw:
+        assert torch.equal(cw[k], ch[k]), k
+    assert torch.isfinite(comp_w).all()
+
+
+@pytest.mark.parametrize("T,N,norm", [(4, 1, 0), (16, 32, 0), (100, 130, 0), (256, 33, 0), (16, 32, 1)])
+def test_gae(dev, T, N, norm):
+    e, _, _ = Hn.make_engine(device=dev, normalize_advantages=norm)
+    p = O.OracleParams(normalize_advantages=norm)
+    rng = np.random.default_rng(T * 1000 + N)
+    v = rng.standard_normal((T, N)).astype(np.float32)
+    r = (1.5 * rng.random((T, N))).astype(np.float32)
+    done = rng.random((T, N)) < 0.05
+    succ = done & (rng.random((T, N)) < 0.3)
+    adv, tgt = e.gae(synth.to_soa(v, 1, dev), synth.to_soa(r, 1, dev), synth.to_soa(done.astype(np.uint8), 1, dev),
+                     synth.to_soa(succ.astype(np.uint8), 1, dev), n_envs=N)
+    a_np, t_np = O.compute_ppo_inputs(v, r, done, succ, p)
+    close(S(adv, N), a_np, "advantages", atol=1e-5)
+    close(S(tgt, N), t_np, "value_targets", atol=1e-5)
+    e.close()
+
+
+def test_gae_golden_exact(dev):
+    from pathlib import Path
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "gae.npz")
+    e, _, _ = Hn.make_engine(device=dev, gamma=float(g["gamma"]), lam=float(g["lam"]))
+    f = lambda k, dt: synth.to_soa(g[k].astype(dt)[:, None], 1, dev)
+    adv, tgt = e.gae(f("values", np.float32), f("rewards", np.float32), f("done", np.uint8), f("success", np.uint8),
+                     n_envs=1)
+    exact(S(adv, 1)[:, 0], g["adv"].astype(np.float32), "golden adv")        # dyadic rationals: exact in fp32
+    exact(S(tgt, 1)[:, 0], g["targets"].astype(np.float32), "golden targets")
+    e.close()
+
+
+def test_gae_linearity_full_size(eng, dev):
+    """Property at 16384 envs x 256 steps (BASELINE config 3): with done = 0, GAE is linear in (values, rewards)."""
+    T, N = 256, 16384
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    v1, v2, r1, r2 = (torch.randn(T, N, generator=g, device=dev) for _ in range(4))
+    z = torch.zeros((T, N), device=dev, dtype=torch.uint8)
+    a1, _ = eng.gae(v1, r1, z, z)
+    a2, _ = eng.gae(v2, r2, z, z)
+    a12, t12 = eng.gae(v1 + v2, r1 + r2, z, z)
+    assert torch.allclose(a12, a1 + a2, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(t12, a12 + (v1 + v2), rtol=0, atol=1e-5)
+    # done everywhere: A_t = r_t - v_t exactly (mask kills bootstrap and recursion)
+    one = torch.ones_like(z)
+    a, _ = eng.gae(v1, r1, one, z)
+    assert torch.equal(a, r1 - v1)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("N", [1, 33, 1024])
+def test_policy_step(dev, path, N):
+    """convert.py step_fn: AoS inputs + flat carry -> (mode, carry)."""
+    e, wa, _ = Hn.make_engine(gemm_path=path, device=dev)
+    p = O.OracleParams()
+    b = Batch(700 + N, 2, N, dev)
+    flat = np.zeros((N, 2 * 2 * 256 + 20), np.float32)
+    flat_d = torch.from_numpy(flat).to(dev)
+    for t in range(2):
+        o, _ = O.get_observations(b.np_state_at(t), b.np_noise_at(t), b.np["episode"], None, P)
+        args = (o["noisy_biased_joint_position"], o["noisy_joint_velocity"], o["noisy_imu_projected_gravity"],
+                o["noisy_imu_gyro"], b.cmd0_np)
+        act, flat = O.policy_step(wa, *args, flat, p)
+        act_d, flat_d = e.policy_step(*(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in args), flat_d)
+        close(act_d.cpu().numpy(), act, f"policy action t={t}")
+        close(flat_d.cpu().numpy(), flat, f"policy carry t={t}")
+    e.close()
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("T,N,hidden", [(16, 32, 256), (6, 130, 256), (5, 50, 128)])
+def test_rollout_fused(dev, path, T, N, hidden):
+    """BASELINE config 1 shape (num_envs = 32, short rollout): the fused control step over T recorded steps."""
+    res = Hn.run_rollout_case(seed=800 + N, T=T, N=N, hidden=hidden, device=dev, gemm_path=path)
+    bad = {k: v for k, v in res["errors"].items() if not v <= 1.0}
+    assert not bad, f"scaled errors > 1: {bad} (all: {res['errors']})"
+    assert res["launches"] > 0
+
+
+def test_rollout_then_rewards_gae_chain(dev):
+    """Whole path once: rollout -> rewards -> GAE on its outputs, against the same chain in the oracle."""
+    T, N = 12, 64
+    b = Batch(901, T, N, dev)
+    e, wa, wc = Hn.make_engine(device=dev)
+    io = Hn.rollout_buffers(b, 256, 2)
+    e.rollout(io, N)
+    ref = Hn.oracle_rollout(b, wa, wc, 256, 2)
+    c0 = O.reward_initial_carry((N,))
+    st = b.np["state"]
+    tr = {"xquat": st["xquat"], "xpos": st["xpos"], "qpos": st["qpos"], "qvel": st["qvel"], "ctrl": ref["ctrl"],
+          "command": ref["command"], "touch_l": st["sensordata"][..., O.SD_TOUCH_L],
+          "touch_r": st["sensordata"][..., O.SD_TOUCH_R], "com_distance": st["com_distance"], "done": ref["done"]}
+    _, total_np, _ = O.rewards(tr, c0, P)
+    a_np, t_np = O.compute_ppo_inputs(ref["value"], total_np, ref["done"], ref["success"], P)
+    carry = {"t_single": torch.zeros(b.ld, device=dev), "airtime": torch.zeros((2, b.ld), device=dev),
+             "prev_contact": torch.ones((2, b.ld), device=dev, dtype=torch.uint8)}
+    total = e.rewards(b.state, io["command"][:T].contiguous(), io["ctrl"], io["done"], carry, n_envs=N)
+    adv, tgt = e.gae(io["value"], total, io["done"], io["success"], n_envs=N)
+    close(S(total, N), total_np, "total reward", rtol=4e-4)
+    close(S(adv, N), a_np, "advantages", rtol=4e-4, atol=1e-4)
+    close(S(tgt, N), t_np, "value targets", rtol=4e-4, atol=1e-4)
+    e.close()
+
+
+def test_error_codes(eng, dev):
+    lib = L.load()
+    assert lib.kbs_version() == 100
+    p = L.default_params()
+    p.hidden_size = 100
+    h = C.c_void_p()
+    assert lib.kbs_create(C.byref(p), C.byref(h)) == -2            # KBS_E_SHAPE
+    v = torch.zeros((4, 8), device=dev)
+    z = torch.zeros((4, 8), device=dev, dtype=torch.uint8)
+    assert lib.kbs_gae(eng._h, None, L.ptr(v), L.ptr(z), L.ptr(z), L.ptr(v), L.ptr(v), 4, 8, 8, None) == -1   # NULL
+    assert lib.kbs_gae(eng._h, L.ptr(v), L.ptr(v), L.ptr(z), L.ptr(z), L.ptr(v), L.ptr(v), 0, 8, 8, None) == -2  # T = 0
+    b = Batch(1, 1, 8, dev)
+    mis = torch.zeros(16 * 8 + 1, device=dev)[1:].view(16, 8)      # 4-byte offset: not 16-byte aligned
+    sv = L.KbsStateView()
+    for k, t in b.state_at(0).items():
+        setattr(sv, k, L.ptr(t))
+    sv.ld = 8
+    out = torch.zeros((65, 8), device=dev)
+    rc = lib.kbs_observations(eng._h, C.byref(sv), None, None, mis.data_ptr(), None, None, None, L.ptr(out), None, 8, None)
+    assert rc == -3                                                 # KBS_E_ALIGN
+    assert b"aligned" in lib.kbs_error_string(rc)
+    # weights not packed -> KBS_E_STATE, never a silent fallback
+    from kbot_joystick_b200.engine import KbotStep
+
+    e2 = KbotStep()
+    with pytest.raises(RuntimeError, match="not ready"):
+        e2.actor_step(out, torch.zeros((2, 2, 8, 256), device=dev), torch.zeros((20, 8), device=dev))
+    e2.close()
