@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--T", type=int, default=100, help="control steps per rollout")
     ap.add_argument("--hidden", type=int, default=256)
-    ap.add_argument("--gemm", default="tc", choices=["tc", "simt"])
+    ap.add_argument("--gemm", default="f16", choices=["f16", "tf32", "simt"],
+                    help="LSTM/MLP datapath: tcgen05 2xFP16-split (default), tcgen05 3xTF32, or fp32 FFMA")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -229,7 +230,7 @@ def run_b200(a):
 
     N, T, H = a.envs, a.T, a.hidden
     ld = (N + 3) // 4 * 4
-    path = L.GEMM_TC_3XTF32 if a.gemm == "tc" else L.GEMM_SIMT_FP32
+    path = {"f16": L.GEMM_TC_2XF16, "tf32": L.GEMM_TC_3XTF32, "simt": L.GEMM_SIMT_FP32}[a.gemm]
     eng = KbotStep(hidden_size=H, depth=2, gemm_path=path)
     eng.pack_weights(L.NET_ACTOR, synth.weights_to_device(synth.make_weights(77, 65, 40, H, 2), dev))
     eng.pack_weights(L.NET_CRITIC, synth.weights_to_device(synth.make_weights(78, 475, 1, H, 2), dev))
@@ -301,9 +302,13 @@ def run_b200(a):
     roof = None
     if dom_name in ("lstm_layer_tc_kernel", "gemm_nt_kernel(simt)"):
         if dom_name == "lstm_layer_tc_kernel":
-            flops_per_launch = lstm_layer_flops * N
-            peak = bf16_sus / 6.0                                 # 3xTF32: TF32 = bf16 / 2, three MMAs per product
-            note = "fp32-accurate 3xTF32: peak = sustained bf16 / 6"
+            flops_per_launch = lstm_layer_flops * N * 2          # one launch = one layer-step of BOTH nets
+            if a.gemm == "tf32":
+                peak = bf16_sus / 6.0                             # 3xTF32: TF32 = bf16 / 2, three MMAs per product
+                note = "fp32-accurate 3xTF32: peak = sustained bf16 / 6"
+            else:
+                peak = bf16_sus / 3.0                             # 2xFP16 split: f16 rate = bf16 rate, three MMAs per product
+                note = "fp32-accurate 2xFP16-split: peak = sustained bf16 / 3"
         else:
             flops_per_launch = (2 * (flops_actor + flops_critic) * N * T) / max(dom_n, 1) / 2   # avg per SIMT GEMM launch
             peak = 72.0                                           # fp32 FFMA: 148 SMs x 128 lanes x 2 x ~1.9 GHz
@@ -331,7 +336,8 @@ def run_b200(a):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)" if a.gemm == "tc" else "f32",
+                "vs_baseline": None, "dtype": {"f16": "f32 (tcgen05 2xFP16-split GEMMs, fp32 accumulate)",
+                          "tf32": "f32 (tcgen05 3xTF32 GEMMs, fp32 accumulate)", "simt": "f32"}[a.gemm],
                 "data": "synthetic", "config": config_dict(a, world), "clocks": ck, "gpu_launches": launches,
                 "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernel_breakdown_ms": breakdown,
                 "profile_overflow": overflow, "gemm_path": a.gemm}

@@ -47,9 +47,11 @@ extern "C" {
 #define KBS_E_PARAM (-5)      /* bad scalar parameter */
 
 enum { KBS_NET_ACTOR = 0, KBS_NET_CRITIC = 1 };
-/* GEMM datapath for the LSTM/MLP contractions.  Both are sm_100a CUDA in this library (no vendor
- * library, no fallback): TC = tcgen05 3xTF32 with fp32 TMEM accumulators; SIMT = fp32 FFMA. */
-enum { KBS_GEMM_TC_3XTF32 = 0, KBS_GEMM_SIMT_FP32 = 1 };
+/* GEMM datapath for the LSTM/MLP contractions.  All are sm_100a CUDA in this library (no vendor library, no
+ * fallback).  TC_* = tcgen05.mma with fp32 TMEM accumulators on operands split into two tensor-core-exact planes
+ * (fp32-accurate: hi.hi + hi.lo + lo.hi): 3XTF32 = TF32 planes, 2XF16 = FP16 planes (lo scaled by 2^11; operands must
+ * stay below 65504 in magnitude; half the bytes and twice the MMA rate).  SIMT = plain fp32 FFMA. */
+enum { KBS_GEMM_TC_3XTF32 = 0, KBS_GEMM_SIMT_FP32 = 1, KBS_GEMM_TC_2XF16 = 2 };
 
 /* Scalars of the path.  Defaults = the reference launch config (train.py:1761-1791) and tables
  * train.py:22-70, 1206-1269; robot/kbot/metadata.json; robot/kbot/robot.mjcf. */

@@ -20,7 +20,7 @@ CRITIC_OBS = 475
 MAX_DEPTH = 4
 NUM_REWARDS = 12
 NET_ACTOR, NET_CRITIC = 0, 1
-GEMM_TC_3XTF32, GEMM_SIMT_FP32 = 0, 1
+GEMM_TC_3XTF32, GEMM_SIMT_FP32, GEMM_TC_2XF16 = 0, 1, 2
 
 _f, _i32, _i64, _vp = C.c_float, C.c_int32, C.c_int64, C.c_void_p
 

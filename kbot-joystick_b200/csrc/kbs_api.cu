@@ -66,12 +66,12 @@ kbs_noise_view noise_at(const kbs_noise_view& z, int64_t t, int64_t ld) {
 
 // Scratch layout of one trunk evaluation: [trunk workspace (path dependent) | out_rm [n][64]].
 size_t trunk_scratch_floats(const kbs_handle* h, int64_t n) {
-  return h->p.gemm_path == KBS_GEMM_TC_3XTF32 ? kbs_tc_scratch_floats(h, n) : kbs_simt_scratch_floats(h, n);
+  return h->p.gemm_path != KBS_GEMM_SIMT_FP32 ? kbs_tc_scratch_floats(h, n) : kbs_simt_scratch_floats(h, n);
 }
 
 int trunk(kbs_handle* h, int net, const float* obs, int64_t ld, float* carry, const uint8_t* done, float* out_rm,
           int64_t n, cudaStream_t st) {
-  if (h->p.gemm_path != KBS_GEMM_TC_3XTF32) return kbs_simt_trunk(h, net, obs, ld, carry, done, out_rm, n, st);
+  if (h->p.gemm_path == KBS_GEMM_SIMT_FP32) return kbs_simt_trunk(h, net, obs, ld, carry, done, out_rm, n, st);
   // tensor-core path: input_proj (FFMA, K = 65 / 475) -> LSTM stack on tcgen05 -> output_proj (FFMA, N = 40 / 1)
   const size_t H = size_t(h->p.hidden_size);
   float* ws = h->scratch;
@@ -84,6 +84,59 @@ int trunk(kbs_handle* h, int net, const float* obs, int64_t ld, float* carry, co
 }
 
 constexpr int kOutLd = 64;  // row stride of the trunk output buffer
+
+// Fused rollout on the tensor-core path.  The state is recorded, so everything that does not depend on the networks
+// is evaluated for all T steps first (terminations, command law, lagged gravity, observations, input projections:
+// big HBM-/FFMA-bound launches), then the recurrence runs 3 launches per step (2 LSTM layers for both nets + head).
+int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStream_t st) {
+  const int64_t ld = io->state.ld, T = io->T;
+  const bool critic = io->value != nullptr;
+  const size_t sbf = size_t(kbs_tc_sb_floats(h, n));
+  const size_t ws_f = kbs_tc_rollout_ws_floats(h, n);
+  const size_t lag_f = io->pg_carry ? size_t(T) * 3 * ld : 0;
+  const size_t aobs_f = io->actor_obs ? 0 : size_t(T) * KBS_ACTOR_OBS * ld;
+  const size_t cobs_f = critic ? size_t(T) * KBS_CRITIC_OBS * ld : 0;
+  const size_t xsb_f = size_t(T) * sbf;
+  const size_t osb_a_f = size_t(kbs_tc_obs_sb_floats(h, KBS_NET_ACTOR, n, T));
+  const size_t osb_c_f = critic ? size_t(kbs_tc_obs_sb_floats(h, KBS_NET_CRITIC, n, T)) : 0;
+  int rc = kbs_scratch_reserve(h, ws_f + lag_f + aobs_f + cobs_f + xsb_f * (critic ? 2 : 1) + osb_a_f + osb_c_f + 64);
+  if (rc) return rc;
+  float* ws = h->scratch;
+  float* lagged = io->pg_carry ? ws + ws_f : nullptr;
+  float* aobs = io->actor_obs ? io->actor_obs : ws + ws_f + lag_f;
+  float* cobs = critic ? ws + ws_f + lag_f + aobs_f : nullptr;
+  float* xsb_a = ws + ws_f + lag_f + aobs_f + cobs_f;
+  float* xsb_c = critic ? xsb_a + xsb_f : nullptr;
+  float* osb_a = xsb_a + xsb_f * (critic ? 2 : 1);
+  float* osb_c = critic ? osb_a + osb_a_f : nullptr;
+
+  if ((rc = kbs_launch_terminate(h, io->state, io->term_codes, io->done, io->success, nullptr, n, st, T))) return rc;
+  if ((rc = kbs_launch_command_scan(h, io->command, io->u_switch, io->cmd_mode, io->cmd_u6, io->cmd_u_arms, io->done, T,
+                                    ld, n, st)))
+    return rc;
+  if (lagged &&
+      (rc = kbs_launch_pg_scan(h, io->state.sensordata, io->episode.pg_lag, io->done, io->pg_carry, lagged, T, ld, n, st)))
+    return rc;
+  if ((rc = kbs_launch_observations(h, io->state, &io->noise, &io->episode, io->command, nullptr, nullptr, nullptr, aobs,
+                                    cobs, n, st, T, lagged)))
+    return rc;
+  {
+    const float* obs_soa[2] = {aobs, cobs};
+    float* obs_sb[2] = {osb_a, osb_c};
+    float* xsb[2] = {xsb_a, xsb_c};
+    if ((rc = kbs_tc_input_proj_all(h, critic ? 2 : 1, obs_soa, obs_sb, xsb, ld, n, T, st))) return rc;
+  }
+
+  KbsTcRolloutArgs r{};
+  r.n = n; r.ld = ld; r.T = T; r.with_critic = critic;
+  r.x_sb_all[0] = xsb_a; r.x_sb_all[1] = xsb_c;
+  r.carry[0] = io->actor_carry; r.carry[1] = io->critic_carry;
+  r.done = io->done; r.actor_obs = aobs; r.lpf = io->lpf; r.eps_action = io->eps_action;
+  r.qpos = io->state.qpos; r.qvel = io->state.qvel; r.ep = io->episode;
+  r.action = io->action; r.log_prob = io->log_prob; r.ctrl = io->ctrl; r.value = io->value;
+  r.ws = ws;
+  return kbs_tc_rollout_recurrent(h, r, st);
+}
 
 }  // namespace
 
@@ -161,7 +214,8 @@ int kbs_create(const kbs_params* p, kbs_handle** out) {
   REQ(p); REQ(out);
   if (p->hidden_size != 128 && p->hidden_size != 256) return KBS_E_SHAPE;
   if (p->depth < 1 || p->depth > KBS_MAX_DEPTH) return KBS_E_SHAPE;
-  if (p->gemm_path != KBS_GEMM_TC_3XTF32 && p->gemm_path != KBS_GEMM_SIMT_FP32) return KBS_E_PARAM;
+  if (p->gemm_path != KBS_GEMM_TC_3XTF32 && p->gemm_path != KBS_GEMM_SIMT_FP32 && p->gemm_path != KBS_GEMM_TC_2XF16)
+    return KBS_E_PARAM;
   int dev = 0;
   KBS_CUDA_TRY(cudaGetDevice(&dev));
   cudaDeviceProp prop;
@@ -256,7 +310,7 @@ int kbs_weights_pack(kbs_handle* h, int net, const kbs_net_weights* w, void* str
   cudaStream_t st = (cudaStream_t)stream;
   int rc = kbs_simt_pack(h, net, w, st);
   if (rc) return rc;
-  if (h->p.gemm_path == KBS_GEMM_TC_3XTF32) rc = kbs_tc_pack(h, net, st);
+  if (h->p.gemm_path != KBS_GEMM_SIMT_FP32) rc = kbs_tc_pack(h, net, st);
   return rc;
 }
 
@@ -391,6 +445,7 @@ int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n, void* stream
   REQ(io->done); REQ(io->success); REQ(io->cmd_mode); REQ(io->cmd_u6); REQ(io->cmd_u_arms); REQ(io->u_switch);
   if (io->value) { REQ(io->critic_carry); REQ(io->state.cinert); REQ(io->state.cvel); REQ(io->state.actuator_force); }
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->p.gemm_path != KBS_GEMM_SIMT_FP32) return rollout_fused_tc(h, io, n, st);
   const int64_t ld = io->state.ld;
   const size_t ts = trunk_scratch_floats(h, n);
   const size_t need = ts + size_t(n) * kOutLd + size_t(KBS_ACTOR_OBS + KBS_CRITIC_OBS) * ld + 64;

@@ -86,14 +86,19 @@ int kbs_scratch_reserve(kbs_handle* h, size_t floats);
 // kbs_elementwise.cu
 int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_noise_view* nz,
                             const kbs_episode_view* ep, const float* command, float* pg_carry,
-                            const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n, cudaStream_t st);
+                            const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n,
+                            cudaStream_t st, int64_t T = 1, const float* pg_lagged = nullptr);
 int kbs_launch_command(kbs_handle* h, const float* cmd_in, float* cmd_out, const float* u_switch,
                        const int32_t* mode, const float* u6, const float* u_arms, const uint8_t* done, int64_t ld,
                        int64_t n, cudaStream_t st);
+int kbs_launch_command_scan(kbs_handle* h, float* command, const float* u_switch, const int32_t* mode, const float* u6,
+                            const float* u_arms, const uint8_t* done, int64_t T, int64_t ld, int64_t n, cudaStream_t st);
+int kbs_launch_pg_scan(kbs_handle* h, const float* sensordata, const float* lag, const uint8_t* done, float* pg_carry,
+                       float* lagged, int64_t T, int64_t ld, int64_t n, cudaStream_t st);
 int kbs_launch_torque(kbs_handle* h, const float* action, const kbs_state_view& s, const kbs_episode_view* ep,
                       float* ctrl, int64_t n, cudaStream_t st);
 int kbs_launch_terminate(kbs_handle* h, const kbs_state_view& s, int32_t* codes, uint8_t* done, uint8_t* success,
-                         float* pre, int64_t n, cudaStream_t st);
+                         float* pre, int64_t n, cudaStream_t st, int64_t T = 1);
 int kbs_launch_rewards(kbs_handle* h, const kbs_traj_view& tr, const kbs_reward_carry& carry, float* total,
                        float* components, int64_t n, cudaStream_t st);
 int kbs_launch_gae(kbs_handle* h, const float* values, const float* rewards, const uint8_t* done,
@@ -119,6 +124,28 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st);
 size_t kbs_tc_scratch_floats(const kbs_handle* h, int64_t n);
 int kbs_tc_lstm_stack(kbs_handle* h, int net, const float* x_rm, float* carry, const uint8_t* done, float* out_h_rm,
                       float* ws, int64_t n, bool carry_sb_valid, cudaStream_t st);
+// recurrent phase of the fused rollout (kbs_net_tc.cu)
+struct KbsTcRolloutArgs {
+  int64_t n, ld, T;
+  bool with_critic;
+  const float* x_sb_all[2];   // [T] x kbs_tc_sb_floats SB input-projection outputs per net (actor, critic)
+  float* carry[2];            // ABI carries [depth][2][n][H]
+  const uint8_t* done;        // [T][ld]
+  const float* actor_obs;     // [T][65][ld]
+  float* lpf;                 // [20][ld]
+  const float* eps_action;    // [T][20][ld] or nullptr
+  const float* qpos;          // [T][27][ld]
+  const float* qvel;          // [T][26][ld]
+  kbs_episode_view ep;
+  float* action; float* log_prob; float* ctrl; float* value;
+  float* ws;                  // kbs_tc_rollout_ws_floats
+};
+size_t kbs_tc_rollout_ws_floats(const kbs_handle* h, int64_t n);
+int64_t kbs_tc_sb_floats(const kbs_handle* h, int64_t n);
+int64_t kbs_tc_obs_sb_floats(const kbs_handle* h, int net, int64_t n, int64_t T);
+int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, float* const* obs_sb, float* const* x_sb_all,
+                          int64_t ld, int64_t n, int64_t T, cudaStream_t st);
+int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStream_t st);
 int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,
                        float* ws, int64_t n, cudaStream_t st);
 
@@ -143,5 +170,65 @@ __device__ __forceinline__ void kbs_copy4(const float* __restrict__ src, int64_t
   __stcs(reinterpret_cast<float4*>(dst + drow * ld + n0),
          __ldcs(reinterpret_cast<const float4*>(src + srow * ld + n0)));
 }
+
+constexpr int kKbsPanelRows = 128;   // rows of an activation panel (UMMA M)
+// ---- "SB" split-blocked operand format of the tcgen05 datapath (see kbs_net_tc.cu) -----------------------------------
+// An fp32 value travels as two tensor-core-exact planes:  KIND_TF32: hi = rn_tf32(x), lo = rn_tf32(x - hi)  (2 x 4 B)
+//                                                          KIND_F16 : hi = rn_f16(x),  lo = rn_f16((x - hi) * 2^11) (2 x 2 B)
+// A "chunk" is 16 bytes of consecutive K (4 tf32 / 8 f16 elements); a block = 4 chunks; layout of one panel (R rows):
+//   [k-block][hi|lo][chunk 0..3][row 0..R-1][16 B]   == UMMA canonical K-major SWIZZLE_NONE (LBO = R*16 B, SBO = 128 B)
+enum { KBS_KIND_TF32 = 0, KBS_KIND_F16 = 1 };
+constexpr float kKbsF16LoScale = 2048.0f;   // 2^11
+inline __host__ __device__ constexpr int kbs_chunk_elems(int kind) { return kind == KBS_KIND_TF32 ? 4 : 8; }
+inline __host__ __device__ constexpr int kbs_block_k(int kind) { return 4 * kbs_chunk_elems(kind); }   // 16 / 32
+// bytes of an SB buffer holding rows x K (rows padded to panels, K to blocks by the caller)
+inline size_t kbs_sb_bytes(int64_t rows_padded, int K) { return size_t(rows_padded) * size_t(K) * 2 * 4; }   // tf32
+inline size_t kbs_sb_bytes_kind(int kind, int64_t rows_padded, int K) {
+  return size_t(rows_padded) * size_t(K) * 2 * (kind == KBS_KIND_TF32 ? 4 : 2);
+}
+#ifdef __CUDACC__
+#include <cuda_fp16.h>
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// byte offset of the 16-byte chunk holding (row, k) in plane `part`
+template <int R, int KIND>
+__device__ __forceinline__ size_t sb_chunk_offset(int64_t row, int k, int kblocks, int part) {
+  constexpr int E = kbs_chunk_elems(KIND);
+  const int64_t panel = row / R;
+  const int r = int(row - panel * R);
+  const int b = k / (4 * E), kc = (k / E) & 3;
+  return ((((size_t(panel) * kblocks + b) * 2 + part) * 4 + kc) * size_t(R) + size_t(r)) * 16;
+}
+// store 4 consecutive K values (k % 4 == 0)
+template <int R, int KIND>
+__device__ __forceinline__ void sb_store4(void* __restrict__ sb, int64_t row, int k, int kblocks, const float (&x)[4]) {
+  char* base = reinterpret_cast<char*>(sb);
+  if (KIND == KBS_KIND_TF32) {
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i] = tf32_rn(x[i]); l[i] = tf32_rn(x[i] - h[i]); }
+    *reinterpret_cast<float4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 0)) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1)) = make_float4(l[0], l[1], l[2], l[3]);
+  } else {
+    __half h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = __float2half_rn(x[i]);
+      l[i] = __float2half_rn((x[i] - __half2float(h[i])) * kKbsF16LoScale);
+    }
+    const int sub = (k & 4) * 2;   // byte offset of the half-chunk inside the 16-byte chunk
+    __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+    __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 0) + sub) = hv;
+    *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1) + sub) = lv;
+  }
+}
+#endif  // __CUDACC__
 
 static inline bool kbs_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

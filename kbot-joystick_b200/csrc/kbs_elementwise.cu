@@ -71,12 +71,27 @@ __device__ __forceinline__ void encode_pg(const float (&g)[3], float (&o)[5]) {
 constexpr int kCopyRowsPerSection = 46;  // 368 pure-copy rows (cinert 230 + cvel 138) in 8 sections
 
 __global__ void __launch_bounds__(kThreads)
-obs_kernel(const __grid_constant__ kbs_params P, const kbs_state_view s, const kbs_noise_view nz,
+obs_kernel(const __grid_constant__ kbs_params P, kbs_state_view s, kbs_noise_view nz,
            const kbs_episode_view ep, const float* __restrict__ command, float* __restrict__ pg_carry,
-           const uint8_t* __restrict__ pg_reset, float* __restrict__ computed, float* __restrict__ actor_obs, float* __restrict__ critic_obs, int64_t n) {
+           const uint8_t* __restrict__ pg_reset, const float* __restrict__ pg_lagged, float* __restrict__ computed,
+           float* __restrict__ actor_obs, float* __restrict__ critic_obs, int64_t n) {
   const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
   if (n0 >= n) return;
   const int64_t ld = s.ld;
+  {  // time axis of a trajectory call: every [T][F][ld] array advances by t * F * ld
+    const int64_t t = blockIdx.z;
+    s.qpos += t * KBS_NQ * ld; s.qvel += t * KBS_NV * ld; s.sensordata += t * KBS_NSENSORDATA * ld;
+    s.xpos += t * 3 * KBS_NBODY * ld; s.xquat += t * 4 * KBS_NBODY * ld;
+    if (s.cinert) s.cinert += t * 10 * KBS_NBODY * ld;
+    if (s.cvel) s.cvel += t * 6 * KBS_NBODY * ld;
+    if (s.actuator_force) s.actuator_force += t * KBS_NUM_JOINTS * ld;
+    if (nz.eps_jpos) { nz.eps_jpos += t * 20 * ld; nz.eps_jvel += t * 20 * ld; nz.eps_gyro += t * 3 * ld; nz.eps_pg += t * 3 * ld; }
+    command += t * KBS_NUM_COMMANDS * ld;
+    if (pg_lagged) pg_lagged += t * 3 * ld;
+    if (computed) computed += t * KBS_NUM_COMPUTED_OBS * ld;
+    if (actor_obs) actor_obs += t * KBS_ACTOR_OBS * ld;
+    if (critic_obs) critic_obs += t * KBS_CRITIC_OBS * ld;
+  }
 
   if (blockIdx.y > 0) {
     // critic privileged dump: center_of_mass_inertia = cinert[1:], center_of_mass_velocity = cvel[1:]
@@ -135,6 +150,8 @@ obs_kernel(const __grid_constant__ kbs_params P, const kbs_state_view s, const k
       for (int k = 0; k < 3; ++k) { kbs_ld4(nz.eps_pg, k, ld, n0, epg[k]); kbs_ld4(nz.eps_gyro, k, ld, n0, egy[k]); }
     }
     if (pg_carry) { for (int k = 0; k < 3; ++k) kbs_ld4(pg_carry, k, ld, n0, prev[k]); }
+    float lagged[3][4];
+    if (pg_lagged) { for (int k = 0; k < 3; ++k) kbs_ld4(pg_lagged, k, ld, n0, lagged[k]); }
     bool rs[4] = {false, false, false, false};  // new episode: EMA state restarts at the current value
     if (pg_reset) {
       const uchar4 r4 = *reinterpret_cast<const uchar4*>(pg_reset + n0);
@@ -151,7 +168,7 @@ obs_kernel(const __grid_constant__ kbs_params P, const kbs_state_view s, const k
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const float pv = (pg_carry && !rs[l]) ? prev[k][l] : gb[k];
-        const float nc = lag[l] * pv + (1.0f - lag[l]) * gb[k];
+        const float nc = pg_lagged ? lagged[k][l] : lag[l] * pv + (1.0f - lag[l]) * gb[k];
         o_carry[k][l] = nc;
         o_pg[k][l] = gb[k];
         o_ipg[k][l] = nc + pgb[k][l];
@@ -340,11 +357,19 @@ torque_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ ac
 // Terminations train.py:1258-1269, 817-823 (+ ksim NotUpright / EpisodeLength / done-success reduce)
 // =====================================================================================================
 __global__ void __launch_bounds__(kThreads)
-terminate_kernel(const __grid_constant__ kbs_params P, const kbs_state_view s, int32_t* __restrict__ codes,
+terminate_kernel(const __grid_constant__ kbs_params P, kbs_state_view s, int32_t* __restrict__ codes,
                  uint8_t* __restrict__ done, uint8_t* __restrict__ success, float* __restrict__ pre, int64_t n) {
   const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
   if (n0 >= n) return;
   const int64_t ld = s.ld;
+  {
+    const int64_t t = blockIdx.y;
+    s.xpos += t * 3 * KBS_NBODY * ld; s.qpos += t * KBS_NQ * ld; s.time += t * ld;
+    if (codes) codes += t * 3 * ld;
+    if (done) done += t * ld;
+    if (success) success += t * ld;
+    if (pre) pre += t * 2 * ld;
+  }
   float bz[4], lz[4], rz[4], q[4][4], tm[4];
   kbs_ld4(s.xpos, 3 * P.body_base + 2, ld, n0, bz);
   kbs_ld4(s.xpos, 3 * P.body_lfoot + 2, ld, n0, lz);
@@ -738,6 +763,74 @@ policy_unpack_kernel(const float* __restrict__ lpf, const float* __restrict__ me
   }
 }
 
+// =====================================================================================================
+// Trajectory-wise scans of the fused rollout (recorded state: everything that does not depend on the networks is
+// evaluated for all T steps up front).  One thread per env, time walked sequentially; loads are env-coalesced.
+// =====================================================================================================
+// UnifiedCommand over T steps: command[t+1] = (done[t] or u_switch[t] < p) ? initial_command(rand[t]) : command[t]
+__global__ void __launch_bounds__(kThreads)
+command_scan_kernel(const __grid_constant__ kbs_params P, float* __restrict__ command /*[T+1][16][ld]*/,
+                    const float* __restrict__ u_switch, const int32_t* __restrict__ mode, const float* __restrict__ u6,
+                    const float* __restrict__ u_arms, const uint8_t* __restrict__ done, int64_t T, int64_t ld, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  if (e >= n) return;
+  float c[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) c[k] = command[k * ld + e];
+  for (int64_t t = 0; t < T; ++t) {
+    const bool sw = (done[t * ld + e] != 0) || (u_switch[t * ld + e] < P.switch_prob);
+    if (sw) {
+      const int m = mode[t * ld + e];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float v = P.cmd_lo[k] + u6[(t * 6 + k) * ld + e] * (P.cmd_hi[k] - P.cmd_lo[k]);
+        bool on;
+        if (k == 0) on = (m == 0) || (m == 3);
+        else if (k == 1) on = (m == 1) || (m == 3);
+        else if (k == 2) on = (m == 2) || (m == 3);
+        else on = (m == 4);
+        c[k] = on ? v : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        const float u = u_arms[(t * 10 + k) * ld + e];
+        const float arm = (P.arm_lo[k] + u * (P.arm_hi[k] - P.arm_lo[k])) * ((u < 0.5f) ? 1.0f : 0.0f);
+        c[6 + k] = (m == 3 || m == 4) ? arm : 0.0f;
+      }
+    }
+    float* out = command + (t + 1) * KBS_NUM_COMMANDS * ld + e;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) out[k * ld] = c[k];
+  }
+}
+
+// Lagged projected gravity (ProjectedGravityObservation min_lag/max_lag): x_t = lag x_{t-1} + (1-lag) g_b(t), restarted at
+// g_b(t) on the first step of a new episode (done[t-1]).  pg_carry in/out; lagged[T][3][ld] out.
+__global__ void __launch_bounds__(kThreads)
+pg_scan_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ sensordata, const float* __restrict__ lag_p,
+               const uint8_t* __restrict__ done, float* __restrict__ pg_carry, float* __restrict__ lagged, int64_t T,
+               int64_t ld, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  if (e >= n) return;
+  const float lag = lag_p ? lag_p[e] : 0.0f;
+  float x[3] = {pg_carry[e], pg_carry[ld + e], pg_carry[2 * ld + e]};
+  for (int64_t t = 0; t < T; ++t) {
+    const float* sd = sensordata + (t * KBS_NSENSORDATA + P.sd_imu_quat) * ld + e;
+    const float q[4] = {sd[0], sd[ld], sd[2 * ld], sd[3 * ld]};
+    const float g[3] = {0.0f, 0.0f, -P.gravity};
+    float gb[3];
+    rotate_vec(g, q, true, P.eps_quat, gb);
+    const bool rs = (t > 0) && (done[(t - 1) * ld + e] != 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float pv = rs ? gb[k] : x[k];
+      x[k] = lag * pv + (1.0f - lag) * gb[k];
+      lagged[(t * 3 + k) * ld + e] = x[k];
+    }
+  }
+  pg_carry[e] = x[0]; pg_carry[ld + e] = x[1]; pg_carry[2 * ld + e] = x[2];
+}
+
 inline unsigned groups4(int64_t n) { return unsigned((((n + 3) / 4) + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -745,13 +838,14 @@ inline unsigned groups4(int64_t n) { return unsigned((((n + 3) / 4) + kThreads -
 // ---- launchers ------------------------------------------------------------------------------------
 int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_noise_view* nz,
                             const kbs_episode_view* ep, const float* command, float* pg_carry,
-                            const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n, cudaStream_t st) {
+                            const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n,
+                            cudaStream_t st, int64_t T, const float* pg_lagged) {
   kbs_noise_view z{};
   kbs_episode_view e{};
   if (nz) z = *nz;
   if (ep) e = *ep;
-  dim3 grid(groups4(n), critic_obs ? 1 + 368 / kCopyRowsPerSection : 1);
-  KBS_LAUNCH(h, KBS_K_OBS, st, (obs_kernel<<<grid, kThreads, 0, st>>>(h->p, s, z, e, command, pg_carry, pg_reset,
+  dim3 grid(groups4(n), critic_obs ? 1 + 368 / kCopyRowsPerSection : 1, unsigned(T));
+  KBS_LAUNCH(h, KBS_K_OBS, st, (obs_kernel<<<grid, kThreads, 0, st>>>(h->p, s, z, e, command, pg_carry, pg_reset, pg_lagged,
                                                                       computed, actor_obs, critic_obs, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
@@ -766,6 +860,24 @@ int kbs_launch_command(kbs_handle* h, const float* cmd_in, float* cmd_out, const
   return KBS_OK;
 }
 
+int kbs_launch_command_scan(kbs_handle* h, float* command, const float* u_switch, const int32_t* mode, const float* u6,
+                            const float* u_arms, const uint8_t* done, int64_t T, int64_t ld, int64_t n, cudaStream_t st) {
+  KBS_LAUNCH(h, KBS_K_COMMAND, st,
+             (command_scan_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(h->p, command, u_switch, mode,
+                                                                                              u6, u_arms, done, T, ld, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_pg_scan(kbs_handle* h, const float* sensordata, const float* lag, const uint8_t* done, float* pg_carry,
+                       float* lagged, int64_t T, int64_t ld, int64_t n, cudaStream_t st) {
+  KBS_LAUNCH(h, KBS_K_OBS, st,
+             (pg_scan_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(h->p, sensordata, lag, done,
+                                                                                         pg_carry, lagged, T, ld, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
 int kbs_launch_torque(kbs_handle* h, const float* action, const kbs_state_view& s, const kbs_episode_view* ep,
                       float* ctrl, int64_t n, cudaStream_t st) {
   kbs_episode_view e{};
@@ -776,9 +888,9 @@ int kbs_launch_torque(kbs_handle* h, const float* action, const kbs_state_view& 
 }
 
 int kbs_launch_terminate(kbs_handle* h, const kbs_state_view& s, int32_t* codes, uint8_t* done, uint8_t* success,
-                         float* pre, int64_t n, cudaStream_t st) {
+                         float* pre, int64_t n, cudaStream_t st, int64_t T) {
   KBS_LAUNCH(h, KBS_K_TERMINATE, st,
-             (terminate_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, s, codes, done, success, pre, n)));
+             (terminate_kernel<<<dim3(groups4(n), unsigned(T)), kThreads, 0, st>>>(h->p, s, codes, done, success, pre, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

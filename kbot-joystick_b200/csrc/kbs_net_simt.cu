@@ -11,11 +11,14 @@ constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
 
 // C[m][n] (+)= sum_k A(m,k) W[n][k] + bias[n].   A: row-major [M][lda] or SoA [K][lda] (env contiguous).
 // W: [Npad][ldw] row-major, Npad % 64 == 0, K % 16 == 0 (zero padded by the pack step).
+// gridDim.z walks a time axis: A += z * a_tstride, C += z * c_tstride (floats).
 template <bool A_SOA>
 __global__ void __launch_bounds__(256)
 gemm_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int ldw,
                const float* __restrict__ bias, float* __restrict__ C, int ldc, int64_t M, int K, int Kvalid,
-               int accumulate) {
+               int accumulate, int64_t a_tstride = 0, int64_t c_tstride = 0) {
+  A += int64_t(blockIdx.z) * a_tstride;
+  C += int64_t(blockIdx.z) * c_tstride;
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Ws[BK][BN + PAD];
   const int tid = threadIdx.x;

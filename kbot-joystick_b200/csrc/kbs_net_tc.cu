@@ -6,6 +6,10 @@
 // Every fp32 operand x is carried as a pair of TF32-representable planes hi = rn_tf32(x), lo = rn_tf32(x - hi) and the
 // product is accumulated as hi.hi + hi.lo + lo.hi (the lo.lo term is below 2^-22 relative): three MMAs per K-step,
 // |error| ~ fp32 rounding, which is what the 1e-5 parity bound needs.
+// MEASURED (tools/tc_accum_probe.py, profiles/r01_tc_accumulation.md): tcgen05 adds each MMA's K=8 partial sum to the
+// fp32 accumulator with TRUNCATION (round toward zero), ~0.6 ulp of bias per instruction.  The small hi.lo / lo.hi
+// terms therefore go to their OWN accumulator (TMEM columns 256..511) and meet the hi.hi sum in the epilogue with a
+// round-to-nearest FADD: 64 instead of 192 truncations on the O(1) accumulator, and no small term is truncated away.
 //
 // Operand layout ("SB" = split-blocked): 128-row panels (A) / 256-column gate tiles (B), K cut into blocks of 16; a
 // block holds [hi|lo][4 k-chunks of 16 B][rows][4 floats] -- exactly the UMMA canonical K-major SWIZZLE_NONE layout
@@ -13,6 +17,7 @@
 // cp.async.bulk per operand per stage lands it in shared memory ready for the tensor core, no tensor map needed.
 // Weights are packed once (kbs_weights_pack); activations are written in SB form by the producing epilogue.
 #include <math.h>
+#include <stdlib.h>
 
 #include "kbs_common.cuh"
 
@@ -21,13 +26,20 @@ namespace {
 constexpr int kPanelRows = 128;          // UMMA M
 constexpr int kTileCols = 256;           // UMMA N: 64 hidden units x 4 gates (gate-interleaved)
 constexpr int kUnitsPerTile = 64;
-constexpr int kBlkK = 16;                // K per pipeline stage (2 MMA k-steps of 8)
+// One pipeline stage = one SB block of each operand = 4 chunks of 16 B along K (2 MMA k-steps): K = 16 for TF32
+// operands, 32 for F16 operands -- the BYTES (and therefore all shared-memory offsets / descriptors) are identical.
 constexpr int kStages = 4;
-constexpr int kABlockFloats = 2 * 4 * kPanelRows * 4;   // 4096 floats = 16 KB
-constexpr int kBBlockFloats = 2 * 4 * kTileCols * 4;    // 8192 floats = 32 KB
-constexpr int kStageBytes = (kABlockFloats + kBBlockFloats) * 4;   // 48 KB
+constexpr int kABlockBytes = 2 * 4 * kPanelRows * 16;   // [hi|lo][4 chunks][128 rows][16 B] = 16 KB
+constexpr int kBBlockBytes = 2 * 4 * kTileCols * 16;    // 32 KB
+constexpr int kStageBytes = kABlockBytes + kBBlockBytes;   // 48 KB
 constexpr int kEpiWarps = 8;
-constexpr int kThreadsTC = 64 + 32 * kEpiWarps;         // warp 0 = bulk-copy producer, warp 1 = MMA issuer
+// warp 0 = MMA issuer (+ TMEM allocation); warps 1..8 = epilogue.  Lane 0 of warps 1..4 doubles as a bulk-copy
+// producer during the K loop (the epilogue warps are idle then).  MEASURED (tools/bulk_copy_bench2.cu,
+// profiles/r01_bulk_copy_microbench.md): one thread can start a new stage only every ~735 cycles whatever its size,
+// so a single producer caps the fill rate at 48 KB / 735 clk = 65 B/clk/SM and, with two requests per stage, at ~32;
+// four producers reach the ~80 B/clk/SM port limit, above the 62.5 B/clk the MMA loop consumes.
+constexpr int kProducers = 4;
+constexpr int kThreadsTC = 32 + 32 * kEpiWarps;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
@@ -54,6 +66,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// multicast variant: the slice lands at the same CTA-relative offset in every CTA of `mask`, and completes `bytes` on
+// the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -64,20 +89,37 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
          (uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32) | (uint64_t(1) << 46);
 }
 // instruction descriptor: D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kTileCols >> 3) << 17) |
-                            (uint32_t(kPanelRows >> 4) << 24);
+// (F16 operands: format code 0, kind::f16, K = 16 per instruction)
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kTileCols >> 3) << 17) |
+                                (uint32_t(kPanelRows >> 4) << 24);
+constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | (uint32_t(kTileCols >> 3) << 17) |
+                               (uint32_t(kPanelRows >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate) : "memory");
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  if (KIND == KBS_KIND_TF32) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdescTf32), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdescF16), "r"(accumulate) : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -91,58 +133,44 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- fp32 -> (hi, lo) TF32 planes -------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// Epilogue activations on the SFU: ex2.approx / rcp.approx are accurate to ~2^-22 relative, i.e. sigma and tanh carry
+// an ABSOLUTE error below 4e-7 -- under the ~1e-6 the truncating tensor-core accumulation already costs -- at ~6
+// instructions instead of ~25 for expf/tanhf + IEEE division (the epilogue was ~20 % of the kernel).
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoidf_(float x) {
+  return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x));          // 1 / (1 + e^-x); e^-x -> inf gives 0
 }
-__device__ __forceinline__ void split4(const float (&x)[4], float4& hi, float4& lo) {
-  float h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { h[i] = tf32_rn(x[i]); l[i] = tf32_rn(x[i] - h[i]); }
-  hi = make_float4(h[0], h[1], h[2], h[3]);
-  lo = make_float4(l[0], l[1], l[2], l[3]);
+__device__ __forceinline__ float tanhf_(float x) {
+  // tanh x = (1 - e^-2|x|) / (1 + e^-2|x|), odd; no cancellation blow-up beyond the 4e-7 absolute bound
+  const float e = fast_ex2(-2.885390081777927f * fabsf(x));
+  return copysignf((1.0f - e) * fast_rcp(1.0f + e), x);
 }
-// SB address of (row, k) chunk start (k % 4 == 0) in a buffer of `kblocks` K-blocks per panel, rows per panel R.
-template <int R>
-__device__ __forceinline__ size_t sb_index(int64_t row, int k, int kblocks, int part) {
-  const int64_t panel = row / R;
-  const int r = int(row - panel * R);
-  const int b = k >> 4, kc = (k >> 2) & 3;
-  return (((size_t(panel) * kblocks + b) * 2 + part) * 4 + kc) * (size_t(R) * 4) + size_t(r) * 4;
-}
-template <int R>
-__device__ __forceinline__ void sb_store4(float* __restrict__ sb, int64_t row, int k, int kblocks, const float (&x)[4]) {
-  float4 hi, lo;
-  split4(x, hi, lo);
-  *reinterpret_cast<float4*>(sb + sb_index<R>(row, k, kblocks, 0)) = hi;
-  *reinterpret_cast<float4*>(sb + sb_index<R>(row, k, kblocks, 1)) = lo;
-}
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---- the layer kernel -----------------------------------------------------------------------------------------------
+enum { MODE_LSTM = 0, MODE_PROJ = 1, MODE_RAW = 2 };
 struct LayerArgs {
-  const float* x_sb;      // [panels][H/16] A blocks: layer input
-  const float* h_sb_in;   // [panels][H/16] A blocks: recurrent input (h_{t-1}, already reset where done_{t-1})
-  const float* w_sb;      // [H/64 tiles][2H/16] B blocks
-  const float* bias_t;    // [H/64][256] gate-interleaved bias
-  float* c;               // [n][H] row-major cell carry in/out (reset where done)
-  float* h_carry;         // [n][H] row-major hidden carry out (reset where done)
-  float* h_sb_out;        // SB recurrent state out (reset where done); must NOT alias h_sb_in
-  float* x_next_sb;       // SB input of the next layer (un-reset) or nullptr
-  float* h_next_rm;       // [n][H] row-major un-reset output (last layer) or nullptr
-  float* raw_gates;       // debug: [n][4H] pre-activation gates in eqx order (i,f,g,o), nullptr in production
+  const char* x_sb;       // A blocks, first K segment: [panels][kb_x] blocks (layer input / observation rows)
+  const char* h_sb_in;    // A blocks, second K segment: [panels][kb_h] blocks (h_{t-1}, reset where done_{t-1}); kb_h may be 0
+  const char* w_sb;       // B blocks: [tiles][kb_x + kb_h]
+  const float* bias_t;    // [tiles][256] bias in tile-column order
+  float* c;               // LSTM: [n][H] row-major cell carry in/out (reset where done)
+  float* h_carry;         // LSTM: [n][H] row-major hidden carry out (reset where done)
+  char* h_sb_out;         // LSTM: SB recurrent state out (reset where done); must NOT alias h_sb_in
+  char* x_next_sb;        // LSTM: SB input of the next layer (un-reset) or nullptr.  PROJ: SB output [rows][H]
+  float* h_next_rm;       // LSTM: [n][H] row-major un-reset output (last layer) or nullptr
+  float* raw;             // RAW: [n][4H] pre-activation gates in eqx order (i,f,g,o)
   const uint8_t* done;    // [n] or nullptr
-  int64_t n;
-  int H;
+  int64_t n;              // valid rows (LSTM/RAW: envs; PROJ: T * padded envs, all rows valid)
+  int H, kb_x, kb_h, mode;
 };
+struct LayerArgs2 { LayerArgs net[2]; };   // blockIdx.z selects the network (actor / critic share one launch)
 
-__global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const LayerArgs a) {
+template <int KIND>
+__global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __grid_constant__ LayerArgs2 args) {
+  const LayerArgs& a = args.net[blockIdx.z];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* stage_base = reinterpret_cast<float*>(smem);
   float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + 1024);
   uint64_t* full = bars;                 // [kStages]
@@ -153,142 +181,320 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const Laye
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int panel = blockIdx.x, tile = blockIdx.y;
   const int H = a.H;
-  const int kb_half = H / kBlkK;         // K blocks of the x part (= of the h part)
-  const int kb_total = 2 * kb_half;
+  const int kb_x = a.kb_x, kb_total = a.kb_x + a.kb_h;
+  constexpr int kBlk = kbs_block_k(KIND);        // K elements per block
+  const int kb_out = H / kBlk;                   // K blocks of an [.][H] SB activation buffer
+  // Thread-block cluster along the panel axis: the csz CTAs of a cluster share one weight tile, so every CTA fetches
+  // 1/csz of each weight block and multicasts it to all of them (optional, see launch_layer).
+  const uint32_t csz = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = uint16_t((1u << csz) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], csz); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: 256 fp32 accumulator columns x 128 lanes
+  if (warp == 0) {   // TMEM: 2 x 256 fp32 accumulator columns x 128 lanes (hi.hi sum | correction sum)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(uint32_t(kTileCols)));
+                 "r"(uint32_t(2 * kTileCols)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < kTileCols; i += 32 * kEpiWarps) bias_s[i] = a.bias_t[size_t(tile) * kTileCols + i];
+  if (warp >= 1) {
+    for (int i = threadIdx.x - 32; i < kTileCols; i += 32 * kEpiWarps) bias_s[i] = a.bias_t[size_t(tile) * kTileCols + i];
   }
   tc_fence_before();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts / commits into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== producer: one bulk copy per operand per stage =====
-      const float* xa = a.x_sb + size_t(panel) * kb_half * kABlockFloats;
-      const float* ha = a.h_sb_in + size_t(panel) * kb_half * kABlockFloats;
-      const float* wb = a.w_sb + size_t(tile) * kb_total * kBBlockFloats;
-      for (int b = 0; b < kb_total; ++b) {
-        const int s = b % kStages;
-        mbar_wait(&empty[s], ((b / kStages) & 1) ^ 1);
-        float* sa = stage_base + size_t(s) * (kStageBytes / 4);
-        float* sb = sa + kABlockFloats;
-        mbar_expect_tx(&full[s], kStageBytes);
-        const float* asrc = (b < kb_half) ? xa + size_t(b) * kABlockFloats : ha + size_t(b - kb_half) * kABlockFloats;
-        bulk_g2s(sa, asrc, kABlockFloats * 4, &full[s]);
-        bulk_g2s(sb, wb + size_t(b) * kBBlockFloats, kBBlockFloats * 4, &full[s]);
+  if (warp >= 1 && warp <= kProducers && lane == 0) {
+    // ===== producers: stage b belongs to producer b % kProducers; one bulk copy per operand per stage =====
+    const char* xa = a.x_sb + size_t(panel) * kb_x * kABlockBytes;
+    const char* ha = a.h_sb_in + size_t(panel) * a.kb_h * kABlockBytes;
+    const char* wb = a.w_sb + size_t(tile) * kb_total * kBBlockBytes;
+    for (int b = warp - 1; b < kb_total; b += kProducers) {
+      const int s = b % kStages;
+      mbar_wait(&empty[s], ((b / kStages) & 1) ^ 1);
+      uint8_t* sa = smem + size_t(s) * kStageBytes;
+      uint8_t* sb = sa + kABlockBytes;
+      mbar_expect_tx(&full[s], kStageBytes);
+      const char* asrc = (b < kb_x) ? xa + size_t(b) * kABlockBytes : ha + size_t(b - kb_x) * kABlockBytes;
+      bulk_g2s(sa, asrc, kABlockBytes, &full[s]);
+      if (csz == 1) {
+        bulk_g2s(sb, wb + size_t(b) * kBBlockBytes, kBBlockBytes, &full[s]);
+      } else {
+        const uint32_t slice = kBBlockBytes / csz;
+        bulk_g2s_mcast(sb + crank * slice, wb + size_t(b) * kBBlockBytes + crank * slice, slice, &full[s], cmask);
       }
     }
-  } else if (warp == 1) {
+  }
+  if (warp == 0) {
     if (lane == 0) {
-      // ===== MMA issuer: 2 k-steps x (hi.hi + hi.lo + lo.hi) per stage =====
+      // ===== MMA issuer: 2 k-steps x (lo.hi + hi.lo -> correction accumulator, hi.hi -> main accumulator) per stage =====
       for (int b = 0; b < kb_total; ++b) {
         const int s = b % kStages;
         mbar_wait(&full[s], (b / kStages) & 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(stage_base + size_t(s) * (kStageBytes / 4));
-        const uint32_t sb = sa + kABlockFloats * 4;
+        const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
+        const uint32_t sb = sa + kABlockBytes;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-          // A: [part][kc][128 rows][16 B]: part stride 8 KB, kc stride 2 KB.   B: part 16 KB, kc 4 KB.
+          // A: [part][chunk][128 rows][16 B]: part stride 8 KB, chunk stride 2 KB.   B: part 16 KB, chunk 4 KB.
           const uint64_t a_hi = umma_desc(sa + ks * 4096, 2048, 128);
           const uint64_t a_lo = umma_desc(sa + 8192 + ks * 4096, 2048, 128);
           const uint64_t b_hi = umma_desc(sb + ks * 8192, 4096, 128);
           const uint64_t b_lo = umma_desc(sb + 16384 + ks * 8192, 4096, 128);
-          umma_tf32(tmem_base, a_lo, b_hi, (b | ks) != 0);
-          umma_tf32(tmem_base, a_hi, b_lo, 1);
-          umma_tf32(tmem_base, a_hi, b_hi, 1);
+          umma<KIND>(tmem_base + kTileCols, a_lo, b_hi, (b | ks) != 0);
+          umma<KIND>(tmem_base + kTileCols, a_hi, b_lo, 1);
+          umma<KIND>(tmem_base, a_hi, b_hi, (b | ks) != 0);
         }
-        umma_commit(&empty[s]);          // frees the stage when these MMAs have read it
+        // frees the stage (in every CTA that multicasts into it) when these MMAs have read it
+        if (csz == 1) umma_commit(&empty[s]); else umma_commit_mcast(&empty[s], cmask);
       }
-      umma_commit(acc_full);             // accumulator complete
+      umma_commit(acc_full);             // accumulators complete
     }
   } else {
-    // ===== epilogue: 8 warps; warp%4 selects the TMEM lane quarter, (warp-2)/4 the half of the 64 units =====
-    const int q4 = warp & 3, half = (warp - 2) >> 2;
+    // ===== epilogue: 8 warps; warp%4 selects the TMEM lane quarter, (warp-1)/4 the column half =====
+    __syncwarp();
+    const int q4 = warp & 3, half = (warp - 1) >> 2;
     const int r = q4 * 32 + lane;
     const int64_t R = int64_t(panel) * kPanelRows + r;
     const bool live = R < a.n;
+    constexpr float kCorr = (KIND == KBS_KIND_F16) ? (1.0f / kKbsF16LoScale) : 1.0f;   // lo planes are scaled by 2^11
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const bool rst = live && a.done && a.done[R];
+    const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16);
+    if (a.mode == MODE_PROJ) {
+      // x = acc + bias for 128 plain columns of this thread's row -> SB planes of the LSTM input
 #pragma unroll 1
-    for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
-      const int uo = ch * 16;                              // unit offset inside the tile
-      const uint32_t t0 = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(uo);
-      float gi[16], gf[16], gg[16], go[16];
-      tmem_ld16(t0, gi);
-      tmem_ld16(t0 + 64, gf);
-      tmem_ld16(t0 + 128, gg);
-      tmem_ld16(t0 + 192, go);
-      tmem_ld_wait();
-      const int u0 = tile * kUnitsPerTile + uo;            // first hidden unit of this chunk
-      if (!live) continue;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        gi[i] += bias_s[uo + i]; gf[i] += bias_s[64 + uo + i]; gg[i] += bias_s[128 + uo + i]; go[i] += bias_s[192 + uo + i];
-      }
-      if (a.raw_gates) {
-        float* g = a.raw_gates + R * 4 * H + u0;
+      for (int cc = 0; cc < 8; ++cc) {
+        const int col = half * 128 + cc * 16;
+        float v[16], cr[16];
+        tmem_ld16(tq + col, v);
+        tmem_ld16(tq + kTileCols + col, cr);
+        tmem_ld_wait();
+        if (!live || col >= H) continue;
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          *reinterpret_cast<float4*>(g + i) = make_float4(gi[i], gi[i + 1], gi[i + 2], gi[i + 3]);
-          *reinterpret_cast<float4*>(g + H + i) = make_float4(gf[i], gf[i + 1], gf[i + 2], gf[i + 3]);
-          *reinterpret_cast<float4*>(g + 2 * H + i) = make_float4(gg[i], gg[i + 1], gg[i + 2], gg[i + 3]);
-          *reinterpret_cast<float4*>(g + 3 * H + i) = make_float4(go[i], go[i + 1], go[i + 2], go[i + 3]);
+          const float o[4] = {v[i] + kCorr * cr[i] + bias_s[col + i], v[i + 1] + kCorr * cr[i + 1] + bias_s[col + i + 1],
+                              v[i + 2] + kCorr * cr[i + 2] + bias_s[col + i + 2], v[i + 3] + kCorr * cr[i + 3] + bias_s[col + i + 3]};
+          sb_store4<kPanelRows, KIND>(a.x_next_sb, R, col + i, kb_out, o);
         }
-        continue;
       }
-      float* cp = a.c + R * H + u0;
-      float* hp = a.h_carry + R * H + u0;
+    } else {
+      const bool rst = live && a.done && a.done[R];
+#pragma unroll 1
+      for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
+        const int uo = ch * 16;                              // unit offset inside the tile
+        const uint32_t t0 = tq + uint32_t(uo);
+        float gi[16], gf[16], gg[16], go[16];
+        tmem_ld16(t0, gi);
+        tmem_ld16(t0 + 64, gf);
+        tmem_ld16(t0 + 128, gg);
+        tmem_ld16(t0 + 192, go);
+        tmem_ld_wait();
+        {  // + correction accumulator (hi.lo + lo.hi), round-to-nearest
+          float cr[16];
+          tmem_ld16(t0 + kTileCols, cr); tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 c4 = *reinterpret_cast<const float4*>(cp + i);
-        const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
-        float hn[4], cn[4], hr[4], cr[4];
+          for (int i = 0; i < 16; ++i) gi[i] += kCorr * cr[i];
+          tmem_ld16(t0 + kTileCols + 64, cr); tmem_ld_wait();
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          cn[l] = sigmoidf_(gf[i + l]) * cv[l] + sigmoidf_(gi[i + l]) * tanhf(gg[i + l]);
-          hn[l] = sigmoidf_(go[i + l]) * tanhf(cn[l]);
-          hr[l] = rst ? 0.0f : hn[l];
-          cr[l] = rst ? 0.0f : cn[l];
+          for (int i = 0; i < 16; ++i) gf[i] += kCorr * cr[i];
+          tmem_ld16(t0 + kTileCols + 128, cr); tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) gg[i] += kCorr * cr[i];
+          tmem_ld16(t0 + kTileCols + 192, cr); tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) go[i] += kCorr * cr[i];
         }
-        *reinterpret_cast<float4*>(cp + i) = make_float4(cr[0], cr[1], cr[2], cr[3]);
-        *reinterpret_cast<float4*>(hp + i) = make_float4(hr[0], hr[1], hr[2], hr[3]);
-        sb_store4<kPanelRows>(a.h_sb_out, R, u0 + i, kb_half, hr);
-        if (a.x_next_sb) sb_store4<kPanelRows>(a.x_next_sb, R, u0 + i, kb_half, hn);
-        if (a.h_next_rm) *reinterpret_cast<float4*>(a.h_next_rm + R * H + u0 + i) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        const int u0 = tile * kUnitsPerTile + uo;            // first hidden unit of this chunk
+        if (!live) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          gi[i] += bias_s[uo + i]; gf[i] += bias_s[64 + uo + i]; gg[i] += bias_s[128 + uo + i]; go[i] += bias_s[192 + uo + i];
+        }
+        if (a.mode == MODE_RAW) {
+          float* g = a.raw + R * 4 * H + u0;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            *reinterpret_cast<float4*>(g + i) = make_float4(gi[i], gi[i + 1], gi[i + 2], gi[i + 3]);
+            *reinterpret_cast<float4*>(g + H + i) = make_float4(gf[i], gf[i + 1], gf[i + 2], gf[i + 3]);
+            *reinterpret_cast<float4*>(g + 2 * H + i) = make_float4(gg[i], gg[i + 1], gg[i + 2], gg[i + 3]);
+            *reinterpret_cast<float4*>(g + 3 * H + i) = make_float4(go[i], go[i + 1], go[i + 2], go[i + 3]);
+          }
+          continue;
+        }
+        float* cp = a.c + R * H + u0;
+        float* hp = a.h_carry + R * H + u0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cp + i);
+          const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+          float hn[4], cn[4], hr[4], cr[4];
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            cn[l] = sigmoidf_(gf[i + l]) * cv[l] + sigmoidf_(gi[i + l]) * tanhf_(gg[i + l]);
+            hn[l] = sigmoidf_(go[i + l]) * tanhf_(cn[l]);
+            hr[l] = rst ? 0.0f : hn[l];
+            cr[l] = rst ? 0.0f : cn[l];
+          }
+          *reinterpret_cast<float4*>(cp + i) = make_float4(cr[0], cr[1], cr[2], cr[3]);
+          *reinterpret_cast<float4*>(hp + i) = make_float4(hr[0], hr[1], hr[2], hr[3]);
+          sb_store4<kPanelRows, KIND>(a.h_sb_out, R, u0 + i, kb_out, hr);
+          if (a.x_next_sb) sb_store4<kPanelRows, KIND>(a.x_next_sb, R, u0 + i, kb_out, hn);
+          if (a.h_next_rm) *reinterpret_cast<float4*>(a.h_next_rm + R * H + u0 + i) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(kTileCols)));
+  if (csz > 1) cluster_sync_all();     // no CTA leaves while peers may still signal its barriers
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(2 * kTileCols)));
+  }
+}
+
+// ---- fused output head of the rollout (FFMA: N = 40 / 1 is far below a tensor-core tile) ----------------------------
+// blockIdx.y = 0: actor  out = W_out h2 + b (train.py:922) -> std/mean/bias/low-pass/sample/log-prob (train.py:924-939,
+//                 1564, distrax MVN-diag) -> PD torque (train.py:1091-1105), all for 32 envs per block;
+// blockIdx.y = 1: critic value = w_out . h2 + b (train.py:1002).
+struct HeadArgs {
+  const float* h2[2];        // [n][H] row-major top-layer output (un-reset), actor / critic
+  const float* w_out[2];     // [64][H] zero-padded row-major
+  const float* b_out[2];     // [64]
+  const float* arm_cmd;      // actor_obs rows 55..64 of this step: [10][ld]
+  float* lpf;                // [20][ld] in/out
+  const float* eps;          // [20][ld] or nullptr (mode)
+  const uint8_t* done;       // [ld] or nullptr
+  const float* q;            // qpos rows 7.. [20][ld]
+  const float* qd;           // qvel rows 6.. [20][ld]
+  kbs_episode_view ep;
+  float* action; float* log_prob; float* ctrl; float* value;   // [20][ld], [ld], [20][ld], [ld]
+  int64_t n, ld;
+  int H;
+};
+constexpr int kHeadEnvs = 32;
+
+__global__ void __launch_bounds__(128)
+rollout_head_kernel(const __grid_constant__ kbs_params P, const __grid_constant__ HeadArgs a) {
+  extern __shared__ __align__(16) float hsm[];
+  const int H = a.H, hs = H + 4;                 // row stride keeps float4 alignment and spreads banks
+  float* h_s = hsm;                              // [32][H + 4]
+  float* w_s = hsm + kHeadEnvs * hs;             // [40][H]
+  float* out_s = w_s + KBS_ACTOR_OUT * H;        // [32][41]
+  float* part = out_s + kHeadEnvs * 41;          // [4][32][2]
+  const int net = blockIdx.y;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t e0 = int64_t(blockIdx.x) * kHeadEnvs;
+  const int nout = net == 0 ? KBS_ACTOR_OUT : 1;
+  // stage h2 tile and W_out with cp.async: all ~36 16-byte requests of a thread are in flight at once (a plain
+  // load/store loop exposed one L2 round trip per iteration: 26 us per launch, measured)
+  for (int i = threadIdx.x; i < kHeadEnvs * (H / 4); i += 128) {
+    const int r = i / (H / 4), c4 = i % (H / 4);
+    float* dst = h_s + r * hs + c4 * 4;
+    if (e0 + r < a.n) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(a.h2[net] + (e0 + r) * H + c4 * 4)
+                   : "memory");
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  for (int i = threadIdx.x; i < nout * (H / 4); i += 128)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(w_s + i * 4)), "l"(a.w_out[net] + i * 4) : "memory");
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  const int64_t e = e0 + lane;
+  if (net == 1) {
+    // critic: 4 warps split K, fixed-order combine
+    float s = 0.0f;
+    const int kq = H / 4;
+    for (int k = g * kq; k < (g + 1) * kq; k += 4) {
+      const float4 hv = *reinterpret_cast<const float4*>(h_s + lane * hs + k);
+      const float4 wv = *reinterpret_cast<const float4*>(w_s + k);
+      s = fmaf(hv.x, wv.x, s); s = fmaf(hv.y, wv.y, s); s = fmaf(hv.z, wv.z, s); s = fmaf(hv.w, wv.w, s);
+    }
+    part[g * 32 + lane] = s;
+    __syncthreads();
+    if (g == 0 && e < a.n) a.value[e] = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + a.b_out[1][0];
+    return;
+  }
+  // actor: thread (env = lane, outputs 10g .. 10g+9)
+  {
+    float acc[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = 0.0f;
+    const float* wr = w_s + (10 * g) * H;
+    for (int k = 0; k < H; k += 4) {
+      const float4 hv = *reinterpret_cast<const float4*>(h_s + lane * hs + k);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const float4 wv = *reinterpret_cast<const float4*>(wr + i * H + k);
+        acc[i] = fmaf(hv.x, wv.x, acc[i]); acc[i] = fmaf(hv.y, wv.y, acc[i]);
+        acc[i] = fmaf(hv.z, wv.z, acc[i]); acc[i] = fmaf(hv.w, wv.w, acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) out_s[lane * 41 + 10 * g + i] = acc[i] + a.b_out[0][10 * g + i];
+  }
+  __syncthreads();
+  // head: thread (env = lane, joints 5g .. 5g+4); all global accesses are env-contiguous rows
+  const bool live = e < a.n;
+  const int64_t ld = a.ld;
+  const bool rst = live && a.done && a.done[e];
+  float s_z = 0.0f, s_log = 0.0f;
+  constexpr float kHalfLog2Pi = 0.918938533204672742f;
+  if (live) {
+#pragma unroll
+    for (int jj = 0; jj < 5; ++jj) {
+      const int j = 5 * g + jj;
+      const float sraw = out_s[lane * 41 + KBS_NUM_JOINTS + j];
+      const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
+      const float sd = fminf((sp + P.min_std) * P.var_scale, P.max_std);
+      float m = out_s[lane * 41 + j] + P.joint_bias[j];
+      m = m + ((j >= 10) ? a.arm_cmd[(j - 10) * ld + e] : 0.0f);
+      const float y = a.lpf[j * ld + e];
+      const float yn = y + P.lpf_alpha * (m - y);
+      a.lpf[j * ld + e] = rst ? 0.0f : yn;
+      float act = yn;
+      if (a.eps) act = yn + sd * a.eps[j * ld + e];
+      const float z = (act - yn) / sd;
+      s_z = s_z + (-0.5f * z * z - kHalfLog2Pi);
+      s_log = s_log + logf(sd);
+      a.action[j * ld + e] = act;
+      // PositionActuators.get_ctrl
+      const float kp = a.ep.kp ? a.ep.kp[j * ld + e] : P.kp[j];
+      const float kd = a.ep.kd ? a.ep.kd[j * ld + e] : P.kd[j];
+      const float lim = a.ep.tau_limit ? a.ep.tau_limit[j * ld + e] : P.ctrl_limit[j];
+      const float target = a.ep.action_bias ? __fadd_rn(act, a.ep.action_bias[j * ld + e]) : act;
+      float tau = __fsub_rn(__fmul_rn(kp, __fsub_rn(target, a.q[j * ld + e])), __fmul_rn(kd, a.qd[j * ld + e]));
+      if (a.ep.torque_bias) tau = __fadd_rn(tau, a.ep.torque_bias[j * ld + e]);
+      a.ctrl[j * ld + e] = fminf(fmaxf(tau, -lim), lim);
+    }
+  }
+  part[(g * 32 + lane) * 2] = s_z;
+  part[(g * 32 + lane) * 2 + 1] = s_log;
+  __syncthreads();
+  if (g == 0 && live && a.log_prob) {
+    float z = 0.0f, l = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { z = z + part[(w * 32 + lane) * 2]; l = l + part[(w * 32 + lane) * 2 + 1]; }
+    a.log_prob[e] = z - l;
   }
 }
 
 // ---- packing kernels ------------------------------------------------------------------------------------------------
 // eqx LSTMCell weights [4H][H] x2 + bias [4H]  ->  gate-interleaved SB tiles (hi/lo) + interleaved bias.
+// tile j, column c: gate = c / 64, unit = 64 j + c % 64  (so one 256-column tile holds i,f,g,o of 64 units)
+template <int KIND>
 __global__ void __launch_bounds__(256)
 pack_lstm_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b,
-                         float* __restrict__ w_sb, float* __restrict__ bias_t, int H) {
-  const int kq = 2 * H / 4;                               // 16-byte chunks along K
+                         char* __restrict__ w_sb, float* __restrict__ bias_t, int H) {
+  const int kq = 2 * H / 4;
   const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  const int64_t total = int64_t(4 * H) * kq;
-  if (idx >= total) return;
+  if (idx >= int64_t(4 * H) * kq) return;
   const int col_g = int(idx / kq);                        // global packed column: tile * 256 + c
   const int k = int(idx % kq) * 4;
   const int tile = col_g / kTileCols, c = col_g % kTileCols;
@@ -296,17 +502,36 @@ pack_lstm_weights_kernel(const float* __restrict__ w_ih, const float* __restrict
   const int row = gate * H + u;                           // eqx row (i,f,g,o blocks of H)
   const float* src = (k < H) ? w_ih + size_t(row) * H + k : w_hh + size_t(row) * H + (k - H);
   const float x[4] = {src[0], src[1], src[2], src[3]};
-  sb_store4<kTileCols>(w_sb, col_g, k, 2 * H / kBlkK, x);
+  sb_store4<kTileCols, KIND>(w_sb, col_g, k, 2 * H / kbs_block_k(KIND), x);
   if (k == 0) bias_t[col_g] = b[row];
 }
 
-// row-major [n][K] fp32 -> SB (A operand, 128-row panels).  Rows >= n of the last panel are zero-filled.
+// eqx Linear weight [H][ldw] (K zero-padded to ldw) -> one 256-column SB tile (rows >= H zero) with K padded to Kp.
+template <int KIND>
 __global__ void __launch_bounds__(256)
-pack_rows_sb_kernel(const float* __restrict__ src, int64_t ld, float* __restrict__ sb, int64_t n, int64_t n_pad, int K) {
+pack_proj_weights_kernel(const float* __restrict__ w, int ldw, const float* __restrict__ b, char* __restrict__ w_sb,
+                         float* __restrict__ bias_t, int H, int Kp) {
+  const int kq = Kp / 4;
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= int64_t(kTileCols) * kq) return;
+  const int col = int(idx / kq), k = int(idx % kq) * 4;
+  float x[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col < H) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (k + i < ldw) ? w[size_t(col) * ldw + k + i] : 0.0f;
+  }
+  sb_store4<kTileCols, KIND>(w_sb, col, k, Kp / kbs_block_k(KIND), x);
+  if (k == 0) bias_t[col] = col < H ? b[col] : 0.0f;
+}
+
+// row-major [n][K] fp32 -> SB (A operand, 128-row panels).  Rows >= n of the last panel are zero-filled.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+pack_rows_sb_kernel(const float* __restrict__ src, int64_t ld, char* __restrict__ sb, int64_t n, int64_t n_pad, int K) {
   const int kq = K / 4;
   const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (idx >= n_pad * kq) return;
-  // consecutive threads -> consecutive rows of the same k-chunk: coalesced SB stores
+  // consecutive threads -> consecutive rows of the same 4-wide K group: coalesced SB stores
   const int64_t panel = idx / (int64_t(kPanelRows) * kq);
   const int rem = int(idx - panel * int64_t(kPanelRows) * kq);
   const int kc = rem / kPanelRows, r = rem % kPanelRows;
@@ -316,46 +541,155 @@ pack_rows_sb_kernel(const float* __restrict__ src, int64_t ld, float* __restrict
     const float4 v = *reinterpret_cast<const float4*>(src + row * ld + kc * 4);
     x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
   }
-  sb_store4<kPanelRows>(sb, row, kc * 4, K / kBlkK, x);
+  sb_store4<kPanelRows, KIND>(sb, row, kc * 4, K / kbs_block_k(KIND), x);
+}
+
+// env-major SoA observations [T][F][ld] -> SB rows [T * n_pad][Kp] (features beyond F and envs beyond n zero-filled).
+// thread = (t, panel, 4-feature group, row): reads 4 SoA rows at one env (coalesced over envs), writes 16 B / 8 B.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+pack_soa_sb_kernel(const float* __restrict__ soa, int F, int64_t ld, char* __restrict__ sb, int64_t n, int64_t n_pad,
+                   int Kp, int64_t T) {
+  const int kq = Kp / 4;
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t rows = T * n_pad;
+  if (idx >= rows * kq) return;
+  const int64_t panel = idx / (int64_t(kPanelRows) * kq);          // global panel over (t, env panel)
+  const int rem = int(idx - panel * int64_t(kPanelRows) * kq);
+  const int kc = rem / kPanelRows, r = rem % kPanelRows;
+  const int64_t row = panel * kPanelRows + r;
+  const int64_t t = row / n_pad, e = row - t * n_pad;
+  float x[4] = {0.f, 0.f, 0.f, 0.f};
+  if (e < n) {
+    const float* p = soa + (t * F + kc * 4) * ld + e;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (kc * 4 + i < F) ? __ldcs(p + i * ld) : 0.0f;
+  }
+  sb_store4<kPanelRows, KIND>(sb, row, kc * 4, Kp / kbs_block_k(KIND), x);
 }
 
 inline int64_t pad_rows(int64_t n) { return (n + kPanelRows - 1) / kPanelRows * kPanelRows; }
+inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+
+// launch the layer kernel with the largest allowed cluster size dividing the number of panels
+template <int KIND>
+cudaError_t launch_layer_k(const LayerArgs2& a2, dim3 grid, cudaStream_t st) {
+  static int max_csz = 0;
+  if (!max_csz) {   // KBS_TC_CLUSTER = 1 | 2 | 4 | 8 caps the cluster size (tuning / A-B profiling)
+    const char* e = getenv("KBS_TC_CLUSTER");
+    // default 1: the fill rate is bound by the per-SM inbound port, which multicast does not relieve (measured:
+    // cluster 2/4 = no gain, 8 = slower because 8 CTAs advance in lock-step); kept as an option for larger grids
+    max_csz = e ? atoi(e) : 1;
+    if (max_csz != 1 && max_csz != 2 && max_csz != 4 && max_csz != 8) max_csz = 1;
+  }
+  int csz = max_csz;
+  while (grid.x % csz) csz >>= 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreadsTC);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, lstm_layer_tc_kernel<KIND>, a2);
+}
+inline cudaError_t launch_layer(int kind, const LayerArgs2& a2, dim3 grid, cudaStream_t st) {
+  return kind == KBS_KIND_TF32 ? launch_layer_k<KBS_KIND_TF32>(a2, grid, st) : launch_layer_k<KBS_KIND_F16>(a2, grid, st);
+}
 
 }  // namespace
 
 // ---- host side --------------------------------------------------------------------------------------------------------
-// tc_image of one net: per layer [w_sb (4H x 2H x 2 floats) | bias_t (4H floats)]
-static size_t layer_image_floats(int H) { return size_t(4 * H) * (2 * H) * 2 + size_t(4 * H); }
+static inline int tc_kind(const kbs_handle* h) { return h->p.gemm_path == KBS_GEMM_TC_2XF16 ? KBS_KIND_F16 : KBS_KIND_TF32; }
+static inline int proj_kp(const kbs_handle* h, int net) {       // input width padded to whole K blocks
+  return round_up_i(h->net[net].num_in, kbs_block_k(tc_kind(h)));
+}
+// tc_image of one net (bytes): per layer [w_sb (4H x 2H SB) | bias_t (4H floats)], then proj [w_sb (256 x Kp SB) | bias (256)]
+static size_t layer_image_bytes(const kbs_handle* h) {
+  const int H = h->p.hidden_size;
+  return kbs_sb_bytes_kind(tc_kind(h), 4 * H, 2 * H) + size_t(4 * H) * 4;
+}
+static size_t proj_image_bytes(const kbs_handle* h, int net) {
+  return kbs_sb_bytes_kind(tc_kind(h), kTileCols, proj_kp(h, net)) + size_t(kTileCols) * 4;
+}
+static inline char* layer_w(const kbs_handle* h, int net, int l) {
+  return reinterpret_cast<char*>(h->net[net].tc_image) + layer_image_bytes(h) * l;
+}
+static inline float* layer_bias(const kbs_handle* h, int net, int l) {
+  const int H = h->p.hidden_size;
+  return reinterpret_cast<float*>(layer_w(h, net, l) + kbs_sb_bytes_kind(tc_kind(h), 4 * H, 2 * H));
+}
+static inline char* proj_w(const kbs_handle* h, int net) { return layer_w(h, net, h->p.depth); }
+static inline float* proj_bias(const kbs_handle* h, int net) {
+  return reinterpret_cast<float*>(proj_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), kTileCols, proj_kp(h, net)));
+}
 
 int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
   KbsNet& N = h->net[net];
-  const int H = h->p.hidden_size;
+  const int H = h->p.hidden_size, kind = tc_kind(h);
   if (H % kUnitsPerTile) return KBS_E_SHAPE;
   static bool attr_set = false;
   if (!attr_set) {
-    KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_tc_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_tc_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  const size_t per_layer = layer_image_floats(H);
   if (N.tc_image) { KBS_CUDA_TRY(cudaFree(N.tc_image)); N.tc_image = nullptr; }
-  N.tc_image_floats = per_layer * h->p.depth;
-  KBS_CUDA_TRY(cudaMalloc(&N.tc_image, N.tc_image_floats * sizeof(float)));
+  const size_t bytes = layer_image_bytes(h) * h->p.depth + proj_image_bytes(h, net);
+  N.tc_image_floats = (bytes + 3) / 4;
+  KBS_CUDA_TRY(cudaMalloc(&N.tc_image, bytes));
   for (int l = 0; l < h->p.depth; ++l) {
-    float* w_sb = N.tc_image + per_layer * l;
-    float* bias_t = w_sb + size_t(4 * H) * (2 * H) * 2;
     const int64_t total = int64_t(4 * H) * (2 * H / 4);
-    KBS_LAUNCH(h, KBS_K_PACK, st,
-               (pack_lstm_weights_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(N.w_ih[l], N.w_hh[l], N.b[l], w_sb,
-                                                                                      bias_t, H)));
+    const unsigned gb = unsigned((total + 255) / 256);
+    if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(
+                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w(h, net, l), layer_bias(h, net, l), H)));
+    else
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
+                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w(h, net, l), layer_bias(h, net, l), H)));
+  }
+  {
+    const int Kp = proj_kp(h, net);
+    const int64_t total = int64_t(kTileCols) * (Kp / 4);
+    const unsigned gb = unsigned((total + 255) / 256);
+    if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(
+                                        N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp)));
+    else
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
+                                        N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp)));
   }
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
 
-// scratch (floats) the TC trunk needs for n envs: x_sb ping/pong + h_sb per layer + x row-major + hbuf row-major
+static int pack_rows(kbs_handle* h, const float* src, int64_t ld, char* sb, int64_t n, int64_t np, int K, cudaStream_t st) {
+  const int64_t chunks = np * (K / 4);
+  const unsigned gb = unsigned((chunks + 255) / 256);
+  if (tc_kind(h) == KBS_KIND_TF32)
+    KBS_LAUNCH(h, KBS_K_PACK, st, (pack_rows_sb_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(src, ld, sb, n, np, K)));
+  else
+    KBS_LAUNCH(h, KBS_K_PACK, st, (pack_rows_sb_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(src, ld, sb, n, np, K)));
+  return KBS_OK;
+}
+
+// bytes of one [n][H] SB activation buffer
+static size_t act_sb_bytes(const kbs_handle* h, int64_t n) { return kbs_sb_bytes_kind(tc_kind(h), pad_rows(n), h->p.hidden_size); }
+
+// scratch (floats) of the per-step TC trunk: x_sb ping/pong + h_sb in/out per layer + x row-major + hbuf row-major
 size_t kbs_tc_scratch_floats(const kbs_handle* h, int64_t n) {
-  const size_t H = size_t(h->p.hidden_size), np = size_t(pad_rows(n));
-  return np * H * 2 * (2 + 2 * size_t(h->p.depth)) + 2 * size_t(n) * H + 256;
+  const size_t H = size_t(h->p.hidden_size);
+  return act_sb_bytes(h, n) / 4 * (2 + 2 * size_t(h->p.depth)) + 2 * size_t(n) * H + 256;
+}
+
+static void fill_lstm_args(const kbs_handle* h, int net, int l, LayerArgs& a) {
+  const int H = h->p.hidden_size, kb = H / kbs_block_k(tc_kind(h));
+  a.w_sb = layer_w(h, net, l);
+  a.bias_t = layer_bias(h, net, l);
+  a.H = H; a.kb_x = kb; a.kb_h = kb; a.mode = MODE_LSTM;
 }
 
 // Runs depth LSTM layers on the tensor cores.  x_rm: [n][H] row-major layer-0 input (input_proj output);
@@ -366,38 +700,31 @@ int kbs_tc_lstm_stack(kbs_handle* h, int net, const float* x_rm, float* carry, c
   if (!N.packed || !N.tc_image) return KBS_E_STATE;
   const int H = h->p.hidden_size, depth = h->p.depth;
   const int64_t np = pad_rows(n);
-  const size_t sbf = size_t(np) * H * 2;
-  float* x_sb[2] = {ws, ws + sbf};
-  float* h_sb = ws + 2 * sbf;   // [depth][2 (in, out)] x sbf: the 4 column-tile CTAs of a panel all read h_{t-1}
-                                // while their epilogues write h_t, so in and out must be distinct buffers
-  const int64_t chunks = np * (H / 4);
-  KBS_LAUNCH(h, KBS_K_PACK, st,
-             (pack_rows_sb_kernel<<<unsigned((chunks + 255) / 256), 256, 0, st>>>(x_rm, H, x_sb[0], n, np, H)));
+  const size_t sbb = act_sb_bytes(h, n);
+  char* wsb = reinterpret_cast<char*>(ws);
+  char* x_sb[2] = {wsb, wsb + sbb};
+  char* h_sb = wsb + 2 * sbb;   // [depth][2 (in, out)]: the column-tile CTAs of a panel all read h_{t-1} while their
+                                // epilogues write h_t, so in and out must be distinct buffers
+  pack_rows(h, x_rm, H, x_sb[0], n, np, H, st);
   if (!carry_sb_valid) {
-    for (int l = 0; l < depth; ++l) {
-      const float* ch = carry + (size_t(l) * 2 + 0) * size_t(n) * H;
-      KBS_LAUNCH(h, KBS_K_PACK, st,
-                 (pack_rows_sb_kernel<<<unsigned((chunks + 255) / 256), 256, 0, st>>>(ch, H, h_sb + sbf * (2 * l), n, np, H)));
-    }
+    for (int l = 0; l < depth; ++l)
+      pack_rows(h, carry + (size_t(l) * 2 + 0) * size_t(n) * H, H, h_sb + sbb * (2 * l), n, np, H, st);
   }
-  const size_t per_layer = layer_image_floats(H);
   for (int l = 0; l < depth; ++l) {
-    LayerArgs a{};
+    LayerArgs2 a2{};
+    LayerArgs& a = a2.net[0];
+    fill_lstm_args(h, net, l, a);
     a.x_sb = x_sb[l & 1];
-    a.h_sb_in = h_sb + sbf * (2 * l);
-    a.w_sb = N.tc_image + per_layer * l;
-    a.bias_t = a.w_sb + size_t(4 * H) * (2 * H) * 2;
+    a.h_sb_in = h_sb + sbb * (2 * l);
+    a.h_sb_out = h_sb + sbb * (2 * l + 1);
     a.c = carry + (size_t(l) * 2 + 1) * size_t(n) * H;
     a.h_carry = carry + (size_t(l) * 2 + 0) * size_t(n) * H;
-    a.h_sb_out = h_sb + sbf * (2 * l + 1);
     a.x_next_sb = (l + 1 < depth) ? x_sb[(l + 1) & 1] : nullptr;
     a.h_next_rm = (l + 1 < depth) ? nullptr : out_h_rm;
-    a.raw_gates = nullptr;
     a.done = done;
     a.n = n;
-    a.H = H;
     dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile));
-    KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (lstm_layer_tc_kernel<<<grid, kThreadsTC, kSmemBytes, st>>>(a)));
+    KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(tc_kind(h), a2, grid, st)));
   }
   KBS_LAUNCH_CHECK();
   return KBS_OK;
@@ -410,22 +737,129 @@ int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, con
   if (!N.packed || !N.tc_image) return KBS_E_STATE;
   const int H = h->p.hidden_size;
   const int64_t np = pad_rows(n);
-  const size_t sbf = size_t(np) * H * 2;
-  const int64_t chunks = np * (H / 4);
-  KBS_LAUNCH(h, KBS_K_PACK, st, (pack_rows_sb_kernel<<<unsigned((chunks + 255) / 256), 256, 0, st>>>(x_rm, H, ws, n, np, H)));
-  KBS_LAUNCH(h, KBS_K_PACK, st,
-             (pack_rows_sb_kernel<<<unsigned((chunks + 255) / 256), 256, 0, st>>>(h_rm, H, ws + sbf, n, np, H)));
-  const size_t per_layer = layer_image_floats(H);
-  LayerArgs a{};
-  a.x_sb = ws;
-  a.h_sb_in = ws + sbf;
-  a.w_sb = N.tc_image + per_layer * layer;
-  a.bias_t = a.w_sb + size_t(4 * H) * (2 * H) * 2;
-  a.raw_gates = gates_out;
+  const size_t sbb = act_sb_bytes(h, n);
+  char* wsb = reinterpret_cast<char*>(ws);
+  pack_rows(h, x_rm, H, wsb, n, np, H, st);
+  pack_rows(h, h_rm, H, wsb + sbb, n, np, H, st);
+  LayerArgs2 a2{};
+  LayerArgs& a = a2.net[0];
+  fill_lstm_args(h, net, layer, a);
+  a.x_sb = wsb;
+  a.h_sb_in = wsb + sbb;
+  a.raw = gates_out;
+  a.mode = MODE_RAW;
   a.n = n;
-  a.H = H;
   dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile));
-  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (lstm_layer_tc_kernel<<<grid, kThreadsTC, kSmemBytes, st>>>(a)));
+  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(tc_kind(h), a2, grid, st)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+// ---- fused rollout: tensor-core input projection of all T steps + the recurrent phase --------------------------------
+// Workspace per net: h_sb [depth][2 parity] | x_mid_sb [2] | h2_rm [n][H] (floats)
+static size_t rollout_ws_per_net_bytes(const kbs_handle* h, int64_t n) {
+  return act_sb_bytes(h, n) * (2 * size_t(h->p.depth) + 2) + size_t(n) * h->p.hidden_size * 4 + 256;
+}
+size_t kbs_tc_rollout_ws_floats(const kbs_handle* h, int64_t n) { return 2 * rollout_ws_per_net_bytes(h, n) / 4; }
+int64_t kbs_tc_sb_floats(const kbs_handle* h, int64_t n) { return int64_t(act_sb_bytes(h, n) / 4); }
+// floats of the SB observation staging buffer of `net` for T steps
+int64_t kbs_tc_obs_sb_floats(const kbs_handle* h, int net, int64_t n, int64_t T) {
+  return int64_t(kbs_sb_bytes_kind(tc_kind(h), T * pad_rows(n), proj_kp(h, net)) / 4);
+}
+
+// obs_soa[k]: [T][num_in][ld] observations of net k; obs_sb[k]: staging (kbs_tc_obs_sb_floats); x_sb_all[k]: [T] x act SB.
+int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, float* const* obs_sb, float* const* x_sb_all,
+                          int64_t ld, int64_t n, int64_t T, cudaStream_t st) {
+  const int H = h->p.hidden_size, kind = tc_kind(h);
+  const int64_t np = pad_rows(n);
+  LayerArgs2 a2{};
+  for (int k = 0; k < nets; ++k) {
+    const KbsNet& N = h->net[k];
+    if (!N.packed || !N.tc_image) return KBS_E_STATE;
+    const int Kp = proj_kp(h, k);
+    const int64_t total = T * np * (Kp / 4);
+    const unsigned gb = unsigned((total + 255) / 256);
+    char* osb = reinterpret_cast<char*>(obs_sb[k]);
+    if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T)));
+    else
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T)));
+    LayerArgs& a = a2.net[k];
+    a.x_sb = osb;
+    a.h_sb_in = osb;
+    a.w_sb = proj_w(h, k);
+    a.bias_t = proj_bias(h, k);
+    a.x_next_sb = reinterpret_cast<char*>(x_sb_all[k]);
+    a.n = T * np;                    // every staged row is written (pad rows carry the bias: harmless, never read back)
+    a.H = H; a.kb_x = Kp / kbs_block_k(kind); a.kb_h = 0; a.mode = MODE_PROJ;
+  }
+  dim3 grid(unsigned(T * np / kPanelRows), 1, unsigned(nets));
+  KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (launch_layer(kind, a2, grid, st)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStream_t st) {
+  const int H = h->p.hidden_size, depth = h->p.depth, kind = tc_kind(h);
+  const int nets = r.with_critic ? 2 : 1;
+  for (int k = 0; k < nets; ++k)
+    if (!h->net[k].packed || !h->net[k].tc_image) return KBS_E_STATE;
+  static bool attr_set = false;
+  const int head_smem = (kHeadEnvs * (H + 4) + KBS_ACTOR_OUT * H + kHeadEnvs * 41 + 4 * 32 * 2) * 4;
+  if (!attr_set) {
+    KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  const int64_t n = r.n, ld = r.ld, np = pad_rows(n);
+  const size_t sbb = act_sb_bytes(h, n), per_net = rollout_ws_per_net_bytes(h, n);
+  char* hsb[2]; char* xmid[2]; float* h2rm[2];
+  for (int k = 0; k < nets; ++k) {
+    char* base = reinterpret_cast<char*>(r.ws) + per_net * k;
+    hsb[k] = base;                                   // [depth][2] x sbb
+    xmid[k] = base + sbb * 2 * depth;                // [2] x sbb
+    h2rm[k] = reinterpret_cast<float*>(xmid[k] + 2 * sbb);
+    for (int l = 0; l < depth; ++l)                  // ABI carry h -> SB, parity 0
+      pack_rows(h, r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H, H, hsb[k] + sbb * (2 * l), n, np, H, st);
+  }
+  dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile), unsigned(nets));
+  for (int64_t t = 0; t < r.T; ++t) {
+    const int pin = int(t & 1), pout = pin ^ 1;
+    const uint8_t* done_t = r.done ? r.done + t * ld : nullptr;
+    for (int l = 0; l < depth; ++l) {
+      LayerArgs2 a2{};
+      for (int k = 0; k < nets; ++k) {
+        LayerArgs& a = a2.net[k];
+        fill_lstm_args(h, k, l, a);
+        a.x_sb = (l == 0) ? reinterpret_cast<const char*>(r.x_sb_all[k]) + size_t(t) * sbb : xmid[k] + sbb * ((l - 1) & 1);
+        a.h_sb_in = hsb[k] + sbb * (2 * l + pin);
+        a.h_sb_out = hsb[k] + sbb * (2 * l + pout);
+        a.c = r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H;
+        a.h_carry = r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H;
+        a.x_next_sb = (l + 1 < depth) ? xmid[k] + sbb * (l & 1) : nullptr;
+        a.h_next_rm = (l + 1 < depth) ? nullptr : h2rm[k];
+        a.done = done_t;
+        a.n = n;
+      }
+      KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(kind, a2, grid, st)));
+    }
+    HeadArgs ha{};
+    for (int k = 0; k < nets; ++k) { ha.h2[k] = h2rm[k]; ha.w_out[k] = h->net[k].w_out; ha.b_out[k] = h->net[k].b_out; }
+    ha.arm_cmd = r.actor_obs + (size_t(t) * KBS_ACTOR_OBS + 55) * ld;
+    ha.lpf = r.lpf;
+    ha.eps = r.eps_action ? r.eps_action + size_t(t) * KBS_NUM_JOINTS * ld : nullptr;
+    ha.done = done_t;
+    ha.q = r.qpos + (size_t(t) * KBS_NQ + 7) * ld;
+    ha.qd = r.qvel + (size_t(t) * KBS_NV + 6) * ld;
+    ha.ep = r.ep;
+    ha.action = r.action + size_t(t) * KBS_NUM_JOINTS * ld;
+    ha.log_prob = r.log_prob ? r.log_prob + size_t(t) * ld : nullptr;
+    ha.ctrl = r.ctrl + size_t(t) * KBS_NUM_JOINTS * ld;
+    ha.value = r.value ? r.value + size_t(t) * ld : nullptr;
+    ha.n = n; ha.ld = ld; ha.H = H;
+    KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
+               (rollout_head_kernel<<<dim3(unsigned((n + kHeadEnvs - 1) / kHeadEnvs), unsigned(nets)), 128, head_smem, st>>>(
+                   h->p, ha)));
+  }
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

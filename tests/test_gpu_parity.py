@@ -18,7 +18,8 @@ from kbot_joystick_b200.engine import COMPUTED_OBS_ROWS
 pytestmark = pytest.mark.gpu
 
 S = synth.from_soa
-PATHS = [pytest.param(L.GEMM_SIMT_FP32, id="simt"), pytest.param(L.GEMM_TC_3XTF32, id="tc3xtf32")]
+PATHS = [pytest.param(L.GEMM_SIMT_FP32, id="simt"), pytest.param(L.GEMM_TC_3XTF32, id="tc3xtf32"),
+         pytest.param(L.GEMM_TC_2XF16, id="tc2xf16")]
 
 
 @pytest.fixture(scope="module")

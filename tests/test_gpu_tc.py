@@ -27,10 +27,11 @@ def _ref(w, layer, x, h):
     return x.astype(f) @ lw["w_ih"].astype(f).T + h.astype(f) @ lw["w_hh"].astype(f).T + lw["b"].astype(f)
 
 
+@pytest.mark.parametrize("path", [pytest.param(L.GEMM_TC_3XTF32, id="tc3xtf32"), pytest.param(L.GEMM_TC_2XF16, id="tc2xf16")])
 @pytest.mark.parametrize("hidden", [256, 128])
-def test_tc_layer_gemm_probes_and_accuracy(cuda_device, lib_built, hidden):
+def test_tc_layer_gemm_probes_and_accuracy(cuda_device, lib_built, hidden, path):
     dev = cuda_device
-    e, wa, wc = Hn.make_engine(hidden=hidden, gemm_path=L.GEMM_TC_3XTF32, device=dev)
+    e, wa, wc = Hn.make_engine(hidden=hidden, gemm_path=path, device=dev)
     H = hidden
     rng = np.random.default_rng(0)
     # 1. one-hot probes: x = e_k in row r  =>  gates[r] - b = W_ih[:, k]; anything else pinpoints a layout error
@@ -63,7 +64,10 @@ def test_tc_layer_gemm_probes_and_accuracy(cuda_device, lib_built, hidden):
         ref = _ref(wc, 1, x, h)
         ref32 = (x @ wc["layers"][1]["w_ih"].T + h @ wc["layers"][1]["w_hh"].T + wc["layers"][1]["b"]).astype(np.float64)
         e_tc, e_32 = np.abs(g - ref).max(), np.abs(ref32 - ref).max()
-        print(f"H={H} n={n}: 3xTF32 max abs err vs fp64 {e_tc:.3e}; NumPy fp32 {e_32:.3e}")
+        m_tc = np.abs(g - ref).mean()
+        print(f"path={path} H={H} n={n}: split-MMA max/mean abs err vs fp64 {e_tc:.3e}/{m_tc:.3e}; NumPy fp32 max {e_32:.3e}")
         assert np.isfinite(g).all()
-        assert e_tc < 2e-6, (e_tc, e_32)            # gates are O(1): ~1e-6 relative
+        # tcgen05 adds every K=8 partial sum with truncation (tools/tc_accum_probe.py): K/8 = 64 truncations of the
+        # O(1) hi.hi accumulator bound the error at ~64 * 0.6 ulp; the hi.lo/lo.hi terms sit in their own accumulator.
+        assert e_tc < 8e-6 and m_tc < 1.5e-6, (e_tc, m_tc, e_32)
     e.close()
