@@ -267,6 +267,12 @@ int64_t kbs_launch_count(const kbs_handle* h);
 int kbs_debug_tc_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,
                        int64_t n_envs, void* stream);
 
+/* Profiling hook: one LSTM layer launch (both nets) with per-CTA clock64 stamps, trace_out device int64 [ctas][8]
+ * (start, setup done, first stage landed, MMAs issued, accumulators ready, epilogue done, smid, -). */
+int kbs_debug_tc_trace(kbs_handle* h, long long* trace_out, int64_t n_envs, void* stream);
+/* Same stamps for LSTM layer `layer` at step `step` of subsequent kbs_rollout calls (trace_out NULL detaches). */
+int kbs_debug_tc_trace_attach(kbs_handle* h, long long* trace_out, int64_t step, int layer);
+
 #define KBS_NUM_KERNEL_IDS 17
 int kbs_profile_enable(kbs_handle* h, int on);
 int kbs_profile_read(kbs_handle* h, int max_ids, double* total_ms, int64_t* launches);

@@ -258,6 +258,20 @@ int kbs_get_params(const kbs_handle* h, kbs_params* out) {
 
 int64_t kbs_launch_count(const kbs_handle* h) { return h ? h->launches : -1; }
 
+int kbs_debug_tc_trace_attach(kbs_handle* h, long long* trace_out, int64_t step, int layer) {
+  REQ(h);
+  h->trace_buf = trace_out; h->trace_step = step; h->trace_layer = layer;
+  return KBS_OK;
+}
+
+int kbs_debug_tc_trace(kbs_handle* h, long long* trace_out, int64_t n, void* stream) {
+  REQ(h); REQ(trace_out);
+  if (n <= 0) return KBS_E_SHAPE;
+  int rc = kbs_scratch_reserve(h, kbs_tc_rollout_ws_floats(h, n) + size_t(n + 128) * h->p.hidden_size * 8);
+  if (rc) return rc;
+  return kbs_tc_debug_trace(h, trace_out, h->scratch, n, (cudaStream_t)stream);
+}
+
 int kbs_debug_tc_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,
                        int64_t n, void* stream) {
   REQ(h); REQ(x_rm); REQ(h_rm); REQ(gates_out);

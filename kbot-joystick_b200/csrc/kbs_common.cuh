@@ -62,6 +62,10 @@ struct kbs_handle {
   int prof_n = 0;
   cudaEvent_t* prof_ev = nullptr;   // 2 * kKbsProfMaxPairs events, created on first enable
   int8_t* prof_id = nullptr;        // kernel id of each pair
+  // debug: per-CTA phase stamps of one LSTM launch inside kbs_rollout (kbs_debug_tc_trace_attach)
+  long long* trace_buf = nullptr;
+  int64_t trace_step = -1;
+  int trace_layer = 0;
 };
 
 // Wraps one kernel launch: counts it and, when profiling, brackets it with events on the launch stream.
@@ -146,6 +150,7 @@ int64_t kbs_tc_obs_sb_floats(const kbs_handle* h, int net, int64_t n, int64_t T)
 int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, float* const* obs_sb, float* const* x_sb_all,
                           int64_t ld, int64_t n, int64_t T, cudaStream_t st);
 int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStream_t st);
+int kbs_tc_debug_trace(kbs_handle* h, long long* trace_out, float* ws, int64_t n, cudaStream_t st);
 int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,
                        float* ws, int64_t n, cudaStream_t st);
 
@@ -202,32 +207,50 @@ __device__ __forceinline__ size_t sb_chunk_offset(int64_t row, int k, int kblock
   const int b = k / (4 * E), kc = (k / E) & 3;
   return ((((size_t(panel) * kblocks + b) * 2 + part) * 4 + kc) * size_t(R) + size_t(r)) * 16;
 }
-// store 4 consecutive K values (k % 4 == 0)
-template <int R, int KIND>
-__device__ __forceinline__ void sb_store4(void* __restrict__ sb, int64_t row, int k, int kblocks, const float (&x)[4]) {
-  char* base = reinterpret_cast<char*>(sb);
+// split 4 consecutive K values into the (hi, lo) planes: 16 B each for TF32, 8 B each for F16
+struct KbsSplit4 { uint4 hi, lo; };   // F16 uses .x/.y only
+template <int KIND>
+__device__ __forceinline__ KbsSplit4 sb_split4(const float (&x)[4]) {
+  KbsSplit4 s;
   if (KIND == KBS_KIND_TF32) {
     float h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { h[i] = tf32_rn(x[i]); l[i] = tf32_rn(x[i] - h[i]); }
-    *reinterpret_cast<float4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 0)) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1)) = make_float4(l[0], l[1], l[2], l[3]);
+    s.hi = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3]));
+    s.lo = make_uint4(__float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]), __float_as_uint(l[3]));
   } else {
-    __half h[4], l[4];
+    // hi = x rounded to 11 significant bits with integer ops (exactly an fp16 value for |x| in the normal range; below
+    // 6e-5 the conversion rounds once more, an absolute error < 3e-8 that nothing downstream resolves); the f32 -> f16
+    // conversions run on the quarter-rate XU pipe shared with ex2/rcp, so they are issued packed (cvt.rn.f16x2.f32).
+    float h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      h[i] = __float2half_rn(x[i]);
-      l[i] = __float2half_rn((x[i] - __half2float(h[i])) * kKbsF16LoScale);
+      h[i] = __uint_as_float((__float_as_uint(x[i]) + 0x1000u) & 0xFFFFE000u);
+      l[i] = (x[i] - h[i]) * kKbsF16LoScale;
     }
-    const int sub = (k & 4) * 2;   // byte offset of the half-chunk inside the 16-byte chunk
-    __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
-    __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
-    uint2 hv, lv;
-    hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
-    lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
-    *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 0) + sub) = hv;
-    *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1) + sub) = lv;
+    const __half2 h01 = __floats2half2_rn(h[0], h[1]), h23 = __floats2half2_rn(h[2], h[3]);
+    const __half2 l01 = __floats2half2_rn(l[0], l[1]), l23 = __floats2half2_rn(l[2], l[3]);
+    s.hi = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23), 0u, 0u);
+    s.lo = make_uint4(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23), 0u, 0u);
   }
+  return s;
+}
+template <int R, int KIND>
+__device__ __forceinline__ void sb_store_split(void* __restrict__ sb, int64_t row, int k, int kblocks, const KbsSplit4& s) {
+  char* base = reinterpret_cast<char*>(sb);
+  if (KIND == KBS_KIND_TF32) {
+    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 0)) = s.hi;
+    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1)) = s.lo;
+  } else {
+    const int sub = (k & 4) * 2;   // byte offset of the half-chunk inside the 16-byte chunk
+    *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 0) + sub) = make_uint2(s.hi.x, s.hi.y);
+    *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1) + sub) = make_uint2(s.lo.x, s.lo.y);
+  }
+}
+// store 4 consecutive K values (k % 4 == 0)
+template <int R, int KIND>
+__device__ __forceinline__ void sb_store4(void* __restrict__ sb, int64_t row, int k, int kblocks, const float (&x)[4]) {
+  sb_store_split<R, KIND>(sb, row, k, kblocks, sb_split4<KIND>(x));
 }
 #endif  // __CUDACC__
 

@@ -32,7 +32,8 @@ constexpr int kStages = 4;
 constexpr int kABlockBytes = 2 * 4 * kPanelRows * 16;   // [hi|lo][4 chunks][128 rows][16 B] = 16 KB
 constexpr int kBBlockBytes = 2 * 4 * kTileCols * 16;    // 32 KB
 constexpr int kStageBytes = kABlockBytes + kBBlockBytes;   // 48 KB
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 8;             // kEpiWarps/4 per TMEM lane quarter; a thread owns kEpiChunks x 16 of the tile's 64 units
+constexpr int kEpiChunks = 16 / kEpiWarps;   // (measured: 16 warps = same epilogue time as 8, but spills at the 96-register cap)
 // warp 0 = MMA issuer (+ TMEM allocation); warps 1..8 = epilogue.  Lane 0 of warps 1..4 doubles as a bulk-copy
 // producer during the K loop (the epilogue warps are idle then).  MEASURED (tools/bulk_copy_bench2.cu,
 // profiles/r01_bulk_copy_microbench.md): one thread can start a new stage only every ~735 cycles whatever its size,
@@ -141,10 +142,19 @@ __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ft
 __device__ __forceinline__ float sigmoidf_(float x) {
   return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x));          // 1 / (1 + e^-x); e^-x -> inf gives 0
 }
-__device__ __forceinline__ float tanhf_(float x) {
-  // tanh x = (1 - e^-2|x|) / (1 + e^-2|x|), odd; no cancellation blow-up beyond the 4e-7 absolute bound
-  const float e = fast_ex2(-2.885390081777927f * fabsf(x));
-  return copysignf((1.0f - e) * fast_rcp(1.0f + e), x);
+// s(a) * tanh(b) with ONE reciprocal: (1 - e_b) / ((1 + e_a)(1 + e_b)), e_a = e^-a (may be +inf -> 0), e_b = e^-2|b| <= 1
+__device__ __forceinline__ float sig_mul_tanh(float a, float b) {
+  const float ea = fast_ex2(-1.4426950408889634f * a);
+  const float eb = fast_ex2(-2.885390081777927f * fabsf(b));
+  return copysignf((1.0f - eb) * fast_rcp((1.0f + ea) * (1.0f + eb)), b);
+}
+
+// fp32 "FB" blocked layout of a [rows][H] state matrix: [panel][H/4][128 rows][4 floats] -- a thread that owns one row
+// reads/writes 16 B at consecutive addresses across the warp (the row-major ABI layout costs one sector per lane).
+__device__ __forceinline__ size_t fb_offset(int64_t row, int k, int H) {
+  const int64_t panel = row / kPanelRows;
+  const int r = int(row - panel * kPanelRows);
+  return ((size_t(panel) * (H / 4) + (k >> 2)) * kPanelRows + r) * 4;   // floats
 }
 
 // ---- the layer kernel -----------------------------------------------------------------------------------------------
@@ -154,13 +164,14 @@ struct LayerArgs {
   const char* h_sb_in;    // A blocks, second K segment: [panels][kb_h] blocks (h_{t-1}, reset where done_{t-1}); kb_h may be 0
   const char* w_sb;       // B blocks: [tiles][kb_x + kb_h]
   const float* bias_t;    // [tiles][256] bias in tile-column order
-  float* c;               // LSTM: [n][H] row-major cell carry in/out (reset where done)
-  float* h_carry;         // LSTM: [n][H] row-major hidden carry out (reset where done)
+  float* c;               // LSTM: cell carry in/out (reset where done), fp32 "FB" blocked layout (fb_offset)
+  float* h_carry;         // LSTM: hidden carry out (reset where done), FB layout
   char* h_sb_out;         // LSTM: SB recurrent state out (reset where done); must NOT alias h_sb_in
   char* x_next_sb;        // LSTM: SB input of the next layer (un-reset) or nullptr.  PROJ: SB output [rows][H]
   float* h_next_rm;       // LSTM: [n][H] row-major un-reset output (last layer) or nullptr
   float* raw;             // RAW: [n][4H] pre-activation gates in eqx order (i,f,g,o)
   const uint8_t* done;    // [n] or nullptr
+  long long* trace;       // debug: per-CTA clock64 stamps [ctas][8] or nullptr
   int64_t n;              // valid rows (LSTM/RAW: envs; PROJ: T * padded envs, all rows valid)
   int H, kb_x, kb_h, mode;
 };
@@ -181,6 +192,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int panel = blockIdx.x, tile = blockIdx.y;
   const int H = a.H;
+  long long* tr = a.trace ? a.trace + ((size_t(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
   const int kb_x = a.kb_x, kb_total = a.kb_x + a.kb_h;
   constexpr int kBlk = kbs_block_k(KIND);        // K elements per block
   const int kb_out = H / kBlk;                   // K blocks of an [.][H] SB activation buffer
@@ -207,6 +220,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
   if (csz > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts / commits into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tr && threadIdx.x == 0) tr[1] = clock64();    // setup done
 
   if (warp >= 1 && warp <= kProducers && lane == 0) {
     // ===== producers: stage b belongs to producer b % kProducers; one bulk copy per operand per stage =====
@@ -236,6 +250,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
         const int s = b % kStages;
         mbar_wait(&full[s], (b / kStages) & 1);
         tc_fence_after();
+        if (tr && b == 0) tr[2] = clock64();        // first stage landed
         const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
         const uint32_t sb = sa + kABlockBytes;
 #pragma unroll
@@ -253,23 +268,32 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
         if (csz == 1) umma_commit(&empty[s]); else umma_commit_mcast(&empty[s], cmask);
       }
       umma_commit(acc_full);             // accumulators complete
+      if (tr) tr[3] = clock64();                    // all MMAs issued
     }
+    __syncwarp();                        // lanes 1..31 must not reach the CTA barrier before lane 0 (bar.sync is warp-aligned)
   } else {
-    // ===== epilogue: 8 warps; warp%4 selects the TMEM lane quarter, (warp-1)/4 the column half =====
+    // ===== epilogue: warp%4 selects the TMEM lane quarter, (warp-1)/4 the group of kEpiChunks x 16 units =====
     __syncwarp();
-    const int q4 = warp & 3, half = (warp - 1) >> 2;
+    const int q4 = warp & 3, cg = (warp - 1) >> 2;
     const int r = q4 * 32 + lane;
     const int64_t R = int64_t(panel) * kPanelRows + r;
     const bool live = R < a.n;
     constexpr float kCorr = (KIND == KBS_KIND_F16) ? (1.0f / kKbsF16LoScale) : 1.0f;   // lo planes are scaled by 2^11
+    float4 cpre[4 * kEpiChunks];         // c_{t-1} of this thread's units, fetched under the MMA loop
+    if (a.mode == MODE_LSTM && live) {
+#pragma unroll
+      for (int j = 0; j < 4 * kEpiChunks; ++j)
+        cpre[j] = *reinterpret_cast<const float4*>(a.c + fb_offset(R, tile * kUnitsPerTile + cg * 16 * kEpiChunks + j * 4, H));
+    }
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (tr && threadIdx.x == 160) tr[4] = clock64();  // accumulators ready: epilogue starts (warp 5: pure epilogue warp)
     const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16);
     if (a.mode == MODE_PROJ) {
       // x = acc + bias for 128 plain columns of this thread's row -> SB planes of the LSTM input
 #pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        const int col = half * 128 + cc * 16;
+      for (int cc = 0; cc < 4 * kEpiChunks; ++cc) {
+        const int col = cg * 64 * kEpiChunks + cc * 16;
         float v[16], cr[16];
         tmem_ld16(tq + col, v);
         tmem_ld16(tq + kTileCols + col, cr);
@@ -284,9 +308,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
       }
     } else {
       const bool rst = live && a.done && a.done[R];
-#pragma unroll 1
-      for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
-        const int uo = ch * 16;                              // unit offset inside the tile
+      // the previous cell state of this thread's units was prefetched while the MMAs ran (cpre)
+#pragma unroll
+      for (int cj = 0; cj < kEpiChunks; ++cj) {
+        const int uo = (cg * kEpiChunks + cj) * 16;          // unit offset inside the tile
         const uint32_t t0 = tq + uint32_t(uo);
         float gi[16], gf[16], gg[16], go[16];
         tmem_ld16(t0, gi);
@@ -310,7 +335,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
           for (int i = 0; i < 16; ++i) go[i] += kCorr * cr[i];
         }
         const int u0 = tile * kUnitsPerTile + uo;            // first hidden unit of this chunk
-        if (!live) continue;
+        if (live) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           gi[i] += bias_s[uo + i]; gf[i] += bias_s[64 + uo + i]; gg[i] += bias_s[128 + uo + i]; go[i] += bias_s[192 + uo + i];
@@ -324,33 +349,37 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
             *reinterpret_cast<float4*>(g + 2 * H + i) = make_float4(gg[i], gg[i + 1], gg[i + 2], gg[i + 3]);
             *reinterpret_cast<float4*>(g + 3 * H + i) = make_float4(go[i], go[i + 1], go[i + 2], go[i + 3]);
           }
-          continue;
-        }
-        float* cp = a.c + R * H + u0;
-        float* hp = a.h_carry + R * H + u0;
+        } else {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 c4 = *reinterpret_cast<const float4*>(cp + i);
+          const float4 c4 = cpre[cj * 4 + (i >> 2)];
           const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
           float hn[4], cn[4], hr[4], cr[4];
 #pragma unroll
           for (int l = 0; l < 4; ++l) {
-            cn[l] = sigmoidf_(gf[i + l]) * cv[l] + sigmoidf_(gi[i + l]) * tanhf_(gg[i + l]);
-            hn[l] = sigmoidf_(go[i + l]) * tanhf_(cn[l]);
+            // c' = s(f) c + s(i) tanh(g);  h' = s(o) tanh(c')   (eqx LSTMCell)
+            cn[l] = sigmoidf_(gf[i + l]) * cv[l] + sig_mul_tanh(gi[i + l], gg[i + l]);
+            hn[l] = sig_mul_tanh(go[i + l], cn[l]);
             hr[l] = rst ? 0.0f : hn[l];
             cr[l] = rst ? 0.0f : cn[l];
           }
-          *reinterpret_cast<float4*>(cp + i) = make_float4(cr[0], cr[1], cr[2], cr[3]);
-          *reinterpret_cast<float4*>(hp + i) = make_float4(hr[0], hr[1], hr[2], hr[3]);
-          sb_store4<kPanelRows, KIND>(a.h_sb_out, R, u0 + i, kb_out, hr);
-          if (a.x_next_sb) sb_store4<kPanelRows, KIND>(a.x_next_sb, R, u0 + i, kb_out, hn);
+          *reinterpret_cast<float4*>(a.c + fb_offset(R, u0 + i, H)) = make_float4(cr[0], cr[1], cr[2], cr[3]);
+          *reinterpret_cast<float4*>(a.h_carry + fb_offset(R, u0 + i, H)) = make_float4(hr[0], hr[1], hr[2], hr[3]);
+          KbsSplit4 sp = sb_split4<KIND>(hn);               // one split serves the next layer (un-reset) ...
+          if (a.x_next_sb) sb_store_split<kPanelRows, KIND>(a.x_next_sb, R, u0 + i, kb_out, sp);
+          if (rst) { sp.hi = make_uint4(0u, 0u, 0u, 0u); sp.lo = sp.hi; }
+          sb_store_split<kPanelRows, KIND>(a.h_sb_out, R, u0 + i, kb_out, sp);   // ... and the recurrent input (reset)
           if (a.h_next_rm) *reinterpret_cast<float4*>(a.h_next_rm + R * H + u0 + i) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        }
+        }
         }
       }
     }
   }
+  if (tr && threadIdx.x == 160) tr[7] = clock64();   // this warp's epilogue done
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) { tr[5] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); tr[6] = sm; }
   if (csz > 1) cluster_sync_all();     // no CTA leaves while peers may still signal its barriers
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(2 * kTileCols)));
@@ -524,6 +553,24 @@ pack_proj_weights_kernel(const float* __restrict__ w, int ldw, const float* __re
   if (k == 0) bias_t[col] = col < H ? b[col] : 0.0f;
 }
 
+// ABI row-major [n][H] <-> FB blocked state.  to_fb: rows >= n of the last panel are zero-filled.
+__global__ void __launch_bounds__(256)
+fb_convert_kernel(float* __restrict__ rm, float* __restrict__ fb, int64_t n, int64_t n_pad, int H, int to_fb) {
+  const int hq = H / 4;
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= n_pad * hq) return;
+  const int64_t panel = idx / (int64_t(kPanelRows) * hq);
+  const int rem = int(idx - panel * int64_t(kPanelRows) * hq);
+  const int kc = rem / kPanelRows, r = rem % kPanelRows;
+  const int64_t row = panel * kPanelRows + r;
+  float4* f = reinterpret_cast<float4*>(fb + fb_offset(row, kc * 4, H));
+  if (to_fb) {
+    *f = row < n ? *reinterpret_cast<const float4*>(rm + row * H + kc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (row < n) {
+    *reinterpret_cast<float4*>(rm + row * H + kc * 4) = *f;
+  }
+}
+
 // row-major [n][K] fp32 -> SB (A operand, 128-row panels).  Rows >= n of the last panel are zero-filled.
 template <int KIND>
 __global__ void __launch_bounds__(256)
@@ -682,7 +729,14 @@ static size_t act_sb_bytes(const kbs_handle* h, int64_t n) { return kbs_sb_bytes
 // scratch (floats) of the per-step TC trunk: x_sb ping/pong + h_sb in/out per layer + x row-major + hbuf row-major
 size_t kbs_tc_scratch_floats(const kbs_handle* h, int64_t n) {
   const size_t H = size_t(h->p.hidden_size);
-  return act_sb_bytes(h, n) / 4 * (2 + 2 * size_t(h->p.depth)) + 2 * size_t(n) * H + 256;
+  return act_sb_bytes(h, n) / 4 * (2 + 2 * size_t(h->p.depth)) + 2 * size_t(h->p.depth) * size_t(pad_rows(n)) * H +
+         2 * size_t(n) * H + 256;
+}
+
+static int fb_convert(kbs_handle* h, float* rm, float* fb, int64_t n, int64_t np, int H, int to_fb, cudaStream_t st) {
+  const int64_t tot = np * (H / 4);
+  KBS_LAUNCH(h, KBS_K_PACK, st, (fb_convert_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(rm, fb, n, np, H, to_fb)));
+  return KBS_OK;
 }
 
 static void fill_lstm_args(const kbs_handle* h, int net, int l, LayerArgs& a) {
@@ -705,7 +759,11 @@ int kbs_tc_lstm_stack(kbs_handle* h, int net, const float* x_rm, float* carry, c
   char* x_sb[2] = {wsb, wsb + sbb};
   char* h_sb = wsb + 2 * sbb;   // [depth][2 (in, out)]: the column-tile CTAs of a panel all read h_{t-1} while their
                                 // epilogues write h_t, so in and out must be distinct buffers
+  float* fb = reinterpret_cast<float*>(h_sb + sbb * 2 * depth);   // [depth][c, h] x np*H: state in the kernel's FB layout
+  const size_t fbf = size_t(np) * H;
   pack_rows(h, x_rm, H, x_sb[0], n, np, H, st);
+  for (int l = 0; l < depth; ++l)
+    fb_convert(h, carry + (size_t(l) * 2 + 1) * size_t(n) * H, fb + fbf * (2 * l), n, np, H, 1, st);
   if (!carry_sb_valid) {
     for (int l = 0; l < depth; ++l)
       pack_rows(h, carry + (size_t(l) * 2 + 0) * size_t(n) * H, H, h_sb + sbb * (2 * l), n, np, H, st);
@@ -717,14 +775,18 @@ int kbs_tc_lstm_stack(kbs_handle* h, int net, const float* x_rm, float* carry, c
     a.x_sb = x_sb[l & 1];
     a.h_sb_in = h_sb + sbb * (2 * l);
     a.h_sb_out = h_sb + sbb * (2 * l + 1);
-    a.c = carry + (size_t(l) * 2 + 1) * size_t(n) * H;
-    a.h_carry = carry + (size_t(l) * 2 + 0) * size_t(n) * H;
+    a.c = fb + fbf * (2 * l);
+    a.h_carry = fb + fbf * (2 * l + 1);
     a.x_next_sb = (l + 1 < depth) ? x_sb[(l + 1) & 1] : nullptr;
     a.h_next_rm = (l + 1 < depth) ? nullptr : out_h_rm;
     a.done = done;
     a.n = n;
     dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile));
     KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(tc_kind(h), a2, grid, st)));
+  }
+  for (int l = 0; l < depth; ++l) {   // FB state -> ABI carry
+    fb_convert(h, carry + (size_t(l) * 2 + 1) * size_t(n) * H, fb + fbf * (2 * l), n, np, H, 0, st);
+    fb_convert(h, carry + (size_t(l) * 2 + 0) * size_t(n) * H, fb + fbf * (2 * l + 1), n, np, H, 0, st);
   }
   KBS_LAUNCH_CHECK();
   return KBS_OK;
@@ -758,7 +820,8 @@ int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, con
 // ---- fused rollout: tensor-core input projection of all T steps + the recurrent phase --------------------------------
 // Workspace per net: h_sb [depth][2 parity] | x_mid_sb [2] | h2_rm [n][H] (floats)
 static size_t rollout_ws_per_net_bytes(const kbs_handle* h, int64_t n) {
-  return act_sb_bytes(h, n) * (2 * size_t(h->p.depth) + 2) + size_t(n) * h->p.hidden_size * 4 + 256;
+  return act_sb_bytes(h, n) * (2 * size_t(h->p.depth) + 2) + size_t(n) * h->p.hidden_size * 4 +
+         2 * size_t(h->p.depth) * size_t(pad_rows(n)) * h->p.hidden_size * 4 + 256;
 }
 size_t kbs_tc_rollout_ws_floats(const kbs_handle* h, int64_t n) { return 2 * rollout_ws_per_net_bytes(h, n) / 4; }
 int64_t kbs_tc_sb_floats(const kbs_handle* h, int64_t n) { return int64_t(act_sb_bytes(h, n) / 4); }
@@ -812,14 +875,18 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
   }
   const int64_t n = r.n, ld = r.ld, np = pad_rows(n);
   const size_t sbb = act_sb_bytes(h, n), per_net = rollout_ws_per_net_bytes(h, n);
-  char* hsb[2]; char* xmid[2]; float* h2rm[2];
+  char* hsb[2]; char* xmid[2]; float* h2rm[2]; float* fb[2];
+  const size_t fbf = size_t(np) * H;
   for (int k = 0; k < nets; ++k) {
     char* base = reinterpret_cast<char*>(r.ws) + per_net * k;
     hsb[k] = base;                                   // [depth][2] x sbb
     xmid[k] = base + sbb * 2 * depth;                // [2] x sbb
     h2rm[k] = reinterpret_cast<float*>(xmid[k] + 2 * sbb);
-    for (int l = 0; l < depth; ++l)                  // ABI carry h -> SB, parity 0
+    fb[k] = h2rm[k] + size_t(n) * H;                 // [depth][c, h] x np*H, FB layout
+    for (int l = 0; l < depth; ++l) {                // ABI carry: h -> SB (parity 0), c -> FB
       pack_rows(h, r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H, H, hsb[k] + sbb * (2 * l), n, np, H, st);
+      fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 1, st);
+    }
   }
   dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile), unsigned(nets));
   for (int64_t t = 0; t < r.T; ++t) {
@@ -833,12 +900,13 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
         a.x_sb = (l == 0) ? reinterpret_cast<const char*>(r.x_sb_all[k]) + size_t(t) * sbb : xmid[k] + sbb * ((l - 1) & 1);
         a.h_sb_in = hsb[k] + sbb * (2 * l + pin);
         a.h_sb_out = hsb[k] + sbb * (2 * l + pout);
-        a.c = r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H;
-        a.h_carry = r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H;
+        a.c = fb[k] + fbf * (2 * l);
+        a.h_carry = fb[k] + fbf * (2 * l + 1);
         a.x_next_sb = (l + 1 < depth) ? xmid[k] + sbb * (l & 1) : nullptr;
         a.h_next_rm = (l + 1 < depth) ? nullptr : h2rm[k];
         a.done = done_t;
         a.n = n;
+        if (h->trace_buf && t == h->trace_step && l == h->trace_layer) a.trace = h->trace_buf;
       }
       KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(kind, a2, grid, st)));
     }
@@ -860,6 +928,37 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
                (rollout_head_kernel<<<dim3(unsigned((n + kHeadEnvs - 1) / kHeadEnvs), unsigned(nets)), 128, head_smem, st>>>(
                    h->p, ha)));
   }
+  for (int k = 0; k < nets; ++k)
+    for (int l = 0; l < depth; ++l) {                // FB state -> ABI carry
+      fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 0, st);
+      fb_convert(h, r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H, fb[k] + fbf * (2 * l + 1), n, np, H, 0, st);
+    }
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+// Debug: one LSTM-mode layer launch for both nets on scratch data with per-CTA clock64 stamps.
+// trace_out (device) [2 * tiles * panels][8]: start, setup done, first stage landed, MMAs issued, accumulators ready,
+// epilogue done, smid, unused.
+int kbs_tc_debug_trace(kbs_handle* h, long long* trace_out, float* ws, int64_t n, cudaStream_t st) {
+  const int H = h->p.hidden_size;
+  for (int k = 0; k < 2; ++k)
+    if (!h->net[k].packed || !h->net[k].tc_image) return KBS_E_STATE;
+  const int64_t np = pad_rows(n);
+  const size_t sbb = act_sb_bytes(h, n);
+  char* wsb = reinterpret_cast<char*>(ws);
+  KBS_CUDA_TRY(cudaMemsetAsync(wsb, 0, sbb * 4 + size_t(np) * H * 4 * 3, st));
+  float* rm = reinterpret_cast<float*>(wsb + sbb * 4);
+  LayerArgs2 a2{};
+  for (int k = 0; k < 2; ++k) {
+    LayerArgs& a = a2.net[k];
+    fill_lstm_args(h, k, 0, a);
+    a.x_sb = wsb; a.h_sb_in = wsb + sbb; a.h_sb_out = wsb + 2 * sbb; a.x_next_sb = wsb + 3 * sbb;
+    a.c = rm; a.h_carry = rm + size_t(np) * H; a.h_next_rm = nullptr; a.done = nullptr; a.n = n;
+    a.trace = trace_out;
+  }
+  dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile), 2);
+  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(tc_kind(h), a2, grid, st)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
