@@ -16,7 +16,7 @@ $(SRC)/%.o: $(SRC)/%.cu $(SRC)/kbs_common.cuh include/kbotstep.h
 	$(NVCC) $(COMMON) -c $< -o $@
 
 $(OUT): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -lcuda
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 clean:
 	rm -f $(OBJS) $(OUT)

@@ -255,6 +255,29 @@ typedef struct kbs_rollout_io {
 
 int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n_envs, void* stream);
 
+/* Replaces: get_ppo_variables -> xax.scan(_ppo_scan_fn) (train.py:1435-1524): on a STORED trajectory, re-run actor and
+ * critic step by step from `*_carry`, carries reset to initial where done[t] (train.py:1502-1506), and return what
+ * ksim.PPOVariables holds.  The observations are the stored ones (Trajectory.obs): actor_obs [T][65][ld] is the
+ * run_actor concat of the noisy observations, critic_obs [T][475][ld] the run_critic concat (both are outputs of
+ * kbs_observations / kbs_rollout).  The mirror passes (aux_losses, scaled by 0.0 in the launch config
+ * train.py:1771-1772) are evaluated by calling this function again on mirrored observations. */
+typedef struct kbs_ppo_io {
+  const float* actor_obs;   /* [T][65][ld] */
+  const float* critic_obs;  /* [T][475][ld] or NULL (then values is not written) */
+  const float* action;      /* [T][20][ld]  Trajectory.action */
+  const uint8_t* done;      /* [T][ld] */
+  float* actor_carry;       /* AoS [depth][2][n][H] in/out */
+  float* critic_carry;      /* AoS [depth][2][n][H] in/out (if critic_obs) */
+  float* lpf;               /* [20][ld] in/out */
+  float* log_probs;         /* [T][ld]      PPOVariables.log_probs  train.py:1484 */
+  float* values;            /* [T][ld]      PPOVariables.values     train.py:1485 */
+  float* entropy;           /* [T][ld]      PPOVariables.entropy    train.py:1486 */
+  float* action_std;        /* [T][20][ld]  PPOVariables.action_std train.py:1487, or NULL */
+  float* mean;              /* [T][20][ld]  dist.mean() (for the mirror loss), or NULL */
+  int64_t T, ld;
+} kbs_ppo_io;
+int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n_envs, void* stream);
+
 /* Number of kernel launches this library has enqueued since the handle was created (bench bookkeeping). */
 int64_t kbs_launch_count(const kbs_handle* h);
 

@@ -82,11 +82,16 @@ class KbsRolloutIO(C.Structure):
                            "term_codes", "done", "success", "value")] + [("T", _i64)]
 
 
+class KbsPpoIO(C.Structure):
+    _fields_ = [(k, _vp) for k in ("actor_obs", "critic_obs", "action", "done", "actor_carry", "critic_carry", "lpf",
+                                   "log_probs", "values", "entropy", "action_std", "mean")] + [("T", _i64), ("ld", _i64)]
+
+
 # every symbol include/kbotstep.h declares (tests check the .so exports all of them)
 EXPORTS = (
     "kbs_version", "kbs_error_string", "kbs_default_params", "kbs_create", "kbs_destroy", "kbs_get_params",
     "kbs_weights_pack", "kbs_observations", "kbs_command_update", "kbs_actor_step", "kbs_critic_step",
-    "kbs_torque", "kbs_terminate", "kbs_rewards", "kbs_gae", "kbs_policy_step", "kbs_rollout",
+    "kbs_torque", "kbs_terminate", "kbs_rewards", "kbs_gae", "kbs_policy_step", "kbs_rollout", "kbs_ppo_variables",
     "kbs_launch_count", "kbs_profile_enable", "kbs_profile_read", "kbs_kernel_name", "kbs_debug_tc_gates", "kbs_debug_tc_trace", "kbs_debug_tc_trace_attach",
 )
 NUM_KERNEL_IDS = 17
@@ -124,6 +129,7 @@ def load() -> C.CDLL:
     lib.kbs_gae.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]
     lib.kbs_policy_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
     lib.kbs_rollout.argtypes = [_vp, P(KbsRolloutIO), _i64, _vp]
+    lib.kbs_ppo_variables.argtypes = [_vp, P(KbsPpoIO), _i64, _vp]
     lib.kbs_launch_count.argtypes = [_vp]
     lib.kbs_launch_count.restype = _i64
     lib.kbs_profile_enable.argtypes = [_vp, C.c_int]

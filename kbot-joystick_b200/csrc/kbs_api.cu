@@ -450,6 +450,73 @@ int kbs_policy_step(kbs_handle* h, const float* joint_angles, const float* joint
   return kbs_launch_policy_unpack(h, carry, lpf, mean, carry_out, action_out, ld, n, st);
 }
 
+int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n, void* stream) {
+  REQ(h); REQ(io);
+  REQ(io->actor_obs); REQ(io->action); REQ(io->done); REQ(io->actor_carry); REQ(io->lpf); REQ(io->log_probs);
+  REQ(io->entropy);
+  if (io->T <= 0) return KBS_E_SHAPE;
+  int rc = check_ld(io->ld, n);
+  if (rc) return rc;
+  const bool critic = io->critic_obs != nullptr;
+  if (critic) { REQ(io->critic_carry); REQ(io->values); }
+  AL(io->actor_obs); AL(io->critic_obs); AL(io->action); AL(io->lpf); AL(io->log_probs); AL(io->values); AL(io->entropy);
+  AL(io->action_std); AL(io->mean);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ld = io->ld, T = io->T;
+  if (h->p.gemm_path == KBS_GEMM_SIMT_FP32 || io->mean) {
+    // stage-by-stage form (exact-fp32 datapath, or when dist.mean() is wanted): T x (actor step, critic step)
+    const size_t ts = trunk_scratch_floats(h, n);
+    if ((rc = kbs_scratch_reserve(h, ts + size_t(n) * kOutLd))) return rc;
+    float* out_rm = h->scratch + ts;
+    for (int64_t t = 0; t < T; ++t) {
+      const uint8_t* done_t = io->done + t * ld;
+      if ((rc = trunk(h, KBS_NET_ACTOR, io->actor_obs + t * KBS_ACTOR_OBS * ld, ld, io->actor_carry, done_t, out_rm, n, st)))
+        return rc;
+      kbs_actor_out o{};
+      o.log_prob = io->log_probs + t * ld;
+      o.entropy = io->entropy + t * ld;
+      o.std = io->action_std ? io->action_std + t * KBS_NUM_JOINTS * ld : nullptr;
+      o.mean = io->mean ? io->mean + t * KBS_NUM_JOINTS * ld : nullptr;
+      if ((rc = kbs_launch_actor_head(h, out_rm, kOutLd, io->actor_obs + t * KBS_ACTOR_OBS * ld, ld, io->lpf, nullptr,
+                                      io->action + t * KBS_NUM_JOINTS * ld, done_t, o, n, st)))
+        return rc;
+      if (critic) {
+        if ((rc = trunk(h, KBS_NET_CRITIC, io->critic_obs + t * KBS_CRITIC_OBS * ld, ld, io->critic_carry, done_t, out_rm,
+                        n, st)))
+          return rc;
+        if ((rc = kbs_launch_critic_head(h, out_rm, kOutLd, io->values + t * ld, n, st))) return rc;
+      }
+    }
+    return KBS_OK;
+  }
+  // tensor-core form: input projections of all T steps in one launch, then 3 launches per step
+  const size_t sbf = size_t(kbs_tc_sb_floats(h, n));
+  const size_t ws_f = kbs_tc_rollout_ws_floats(h, n), xsb_f = size_t(T) * sbf;
+  const size_t osb_a_f = size_t(kbs_tc_obs_sb_floats(h, KBS_NET_ACTOR, n, T));
+  const size_t osb_c_f = critic ? size_t(kbs_tc_obs_sb_floats(h, KBS_NET_CRITIC, n, T)) : 0;
+  if ((rc = kbs_scratch_reserve(h, ws_f + xsb_f * (critic ? 2 : 1) + osb_a_f + osb_c_f + 64))) return rc;
+  float* ws = h->scratch;
+  float* xsb_a = ws + ws_f;
+  float* xsb_c = critic ? xsb_a + xsb_f : nullptr;
+  float* osb_a = xsb_a + xsb_f * (critic ? 2 : 1);
+  float* osb_c = critic ? osb_a + osb_a_f : nullptr;
+  {
+    const float* obs_soa[2] = {io->actor_obs, io->critic_obs};
+    float* obs_sb[2] = {osb_a, osb_c};
+    float* xsb[2] = {xsb_a, xsb_c};
+    if ((rc = kbs_tc_input_proj_all(h, critic ? 2 : 1, obs_soa, obs_sb, xsb, ld, n, T, st))) return rc;
+  }
+  KbsTcRolloutArgs r{};
+  r.n = n; r.ld = ld; r.T = T; r.with_critic = critic;
+  r.x_sb_all[0] = xsb_a; r.x_sb_all[1] = xsb_c;
+  r.carry[0] = io->actor_carry; r.carry[1] = io->critic_carry;
+  r.done = io->done; r.actor_obs = io->actor_obs; r.lpf = io->lpf;
+  r.action_in = io->action; r.log_prob = io->log_probs; r.entropy = io->entropy; r.action_std = io->action_std;
+  r.value = io->values;
+  r.ws = ws;
+  return kbs_tc_rollout_recurrent(h, r, st);
+}
+
 int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n, void* stream) {
   REQ(h); REQ(io);
   if (io->T <= 0) return KBS_E_SHAPE;

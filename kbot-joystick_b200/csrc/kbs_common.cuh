@@ -141,7 +141,10 @@ struct KbsTcRolloutArgs {
   const float* qpos;          // [T][27][ld]
   const float* qvel;          // [T][26][ld]
   kbs_episode_view ep;
-  float* action; float* log_prob; float* ctrl; float* value;
+  float* action; float* log_prob; float* ctrl; float* value;   // action / ctrl may be nullptr (PPO-variable pass)
+  const float* action_in;     // [T][20][ld] stored actions whose log-prob is wanted, or nullptr (log-prob of own sample)
+  float* entropy;             // [T][ld] or nullptr
+  float* action_std;          // [T][20][ld] or nullptr
   float* ws;                  // kbs_tc_rollout_ws_floats
 };
 size_t kbs_tc_rollout_ws_floats(const kbs_handle* h, int64_t n);

@@ -401,7 +401,11 @@ struct HeadArgs {
   const float* q;            // qpos rows 7.. [20][ld]
   const float* qd;           // qvel rows 6.. [20][ld]
   kbs_episode_view ep;
-  float* action; float* log_prob; float* ctrl; float* value;   // [20][ld], [ld], [20][ld], [ld]
+  float* action; float* log_prob; float* ctrl; float* value;   // [20][ld], [ld], [20][ld] or nullptr, [ld]
+  // stored-transition mode of _ppo_scan_fn (train.py:1443-1452, 1486-1487): log-prob of action_in, entropy, stddev
+  const float* action_in;    // [20][ld] or nullptr
+  float* entropy;            // [ld] or nullptr
+  float* std;                // [20][ld] or nullptr
   int64_t n, ld;
   int H;
 };
@@ -489,10 +493,13 @@ rollout_head_kernel(const __grid_constant__ kbs_params P, const __grid_constant_
       a.lpf[j * ld + e] = rst ? 0.0f : yn;
       float act = yn;
       if (a.eps) act = yn + sd * a.eps[j * ld + e];
-      const float z = (act - yn) / sd;
+      const float a_eval = a.action_in ? a.action_in[j * ld + e] : act;
+      const float z = (a_eval - yn) / sd;
       s_z = s_z + (-0.5f * z * z - kHalfLog2Pi);
       s_log = s_log + logf(sd);
-      a.action[j * ld + e] = act;
+      if (a.action) a.action[j * ld + e] = act;
+      if (a.std) a.std[j * ld + e] = sd;
+      if (!a.ctrl) continue;
       // PositionActuators.get_ctrl
       const float kp = a.ep.kp ? a.ep.kp[j * ld + e] : P.kp[j];
       const float kd = a.ep.kd ? a.ep.kd[j * ld + e] : P.kd[j];
@@ -506,11 +513,12 @@ rollout_head_kernel(const __grid_constant__ kbs_params P, const __grid_constant_
   part[(g * 32 + lane) * 2] = s_z;
   part[(g * 32 + lane) * 2 + 1] = s_log;
   __syncthreads();
-  if (g == 0 && live && a.log_prob) {
+  if (g == 0 && live) {
     float z = 0.0f, l = 0.0f;
 #pragma unroll
     for (int w = 0; w < 4; ++w) { z = z + part[(w * 32 + lane) * 2]; l = l + part[(w * 32 + lane) * 2 + 1]; }
-    a.log_prob[e] = z - l;
+    if (a.log_prob) a.log_prob[e] = z - l;
+    if (a.entropy) a.entropy[e] = l + float(KBS_NUM_JOINTS) * (0.5f + kHalfLog2Pi);
   }
 }
 
@@ -916,13 +924,16 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     ha.lpf = r.lpf;
     ha.eps = r.eps_action ? r.eps_action + size_t(t) * KBS_NUM_JOINTS * ld : nullptr;
     ha.done = done_t;
-    ha.q = r.qpos + (size_t(t) * KBS_NQ + 7) * ld;
-    ha.qd = r.qvel + (size_t(t) * KBS_NV + 6) * ld;
+    ha.q = r.qpos ? r.qpos + (size_t(t) * KBS_NQ + 7) * ld : nullptr;
+    ha.qd = r.qvel ? r.qvel + (size_t(t) * KBS_NV + 6) * ld : nullptr;
     ha.ep = r.ep;
-    ha.action = r.action + size_t(t) * KBS_NUM_JOINTS * ld;
+    ha.action = r.action ? r.action + size_t(t) * KBS_NUM_JOINTS * ld : nullptr;
     ha.log_prob = r.log_prob ? r.log_prob + size_t(t) * ld : nullptr;
-    ha.ctrl = r.ctrl + size_t(t) * KBS_NUM_JOINTS * ld;
+    ha.ctrl = r.ctrl ? r.ctrl + size_t(t) * KBS_NUM_JOINTS * ld : nullptr;
     ha.value = r.value ? r.value + size_t(t) * ld : nullptr;
+    ha.action_in = r.action_in ? r.action_in + size_t(t) * KBS_NUM_JOINTS * ld : nullptr;
+    ha.entropy = r.entropy ? r.entropy + size_t(t) * ld : nullptr;
+    ha.std = r.action_std ? r.action_std + size_t(t) * KBS_NUM_JOINTS * ld : nullptr;
     ha.n = n; ha.ld = ld; ha.H = H;
     KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
                (rollout_head_kernel<<<dim3(unsigned((n + kHeadEnvs - 1) / kHeadEnvs), unsigned(nets)), 128, head_smem, st>>>(

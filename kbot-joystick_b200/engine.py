@@ -203,6 +203,24 @@ class KbotStep:
                                          n, _stream()), "kbs_policy_step")
         return action, carry_out
 
+    def ppo_variables(self, actor_obs, action, done, actor_carry, lpf, critic_obs=None, critic_carry=None,
+                      want_std: bool = True, want_mean: bool = False, n_envs: int | None = None) -> dict:
+        """get_ppo_variables on a stored trajectory (train.py:1510-1524): returns log_probs/values/entropy/action_std."""
+        T, _, ld = actor_obs.shape
+        dev = actor_obs.device
+        out = {"log_probs": torch.empty((T, ld), device=dev), "entropy": torch.empty((T, ld), device=dev),
+               "values": torch.empty((T, ld), device=dev) if critic_obs is not None else None,
+               "action_std": torch.empty((T, 20, ld), device=dev) if want_std else None,
+               "mean": torch.empty((T, 20, ld), device=dev) if want_mean else None}
+        io = L.KbsPpoIO()
+        io.actor_obs, io.critic_obs, io.action, io.done = L.ptr(actor_obs), L.ptr(critic_obs), L.ptr(action), L.ptr(done)
+        io.actor_carry, io.critic_carry, io.lpf = L.ptr(actor_carry), L.ptr(critic_carry), L.ptr(lpf)
+        io.log_probs, io.values, io.entropy = L.ptr(out["log_probs"]), L.ptr(out["values"]), L.ptr(out["entropy"])
+        io.action_std, io.mean = L.ptr(out["action_std"]), L.ptr(out["mean"])
+        io.T, io.ld = T, ld
+        L.check(self.lib.kbs_ppo_variables(self._h, C.byref(io), n_envs or ld, _stream()), "kbs_ppo_variables")
+        return out
+
     def rollout(self, io: dict, n_envs: int) -> None:
         """io: tensors named as the fields of kbs_rollout_io (state/noise/episode are nested dicts)."""
         r = L.KbsRolloutIO()

@@ -385,3 +385,89 @@ def test_error_codes(eng, dev):
     with pytest.raises(RuntimeError, match="not ready"):
         e2.actor_step(out, torch.zeros((2, 2, 8, 256), device=dev), torch.zeros((20, 8), device=dev))
     e2.close()
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("T,N,hidden", [(8, 50, 256), (5, 130, 128)])
+def test_ppo_variables(dev, path, T, N, hidden):
+    """get_ppo_variables (train.py:1435-1524) on a stored trajectory: log_probs / values / entropy / action_std and the
+    final carries, incl. the done-resets; the mirror pass is the same call on mirrored observations."""
+    e, wa, wc = Hn.make_engine(hidden=hidden, gemm_path=path, device=dev)
+    p = O.OracleParams(hidden_size=hidden)
+    b = Batch(1000 + N, T, N, dev)
+    rng = np.random.default_rng(4)
+    obs_list = [O.get_observations(b.np_state_at(t), b.np_noise_at(t), b.np["episode"], None, P)[0] for t in range(T)]
+    cmd = np.stack([b.cmd0_np] * T)
+    done = rng.random((T, N)) < 0.15
+    act = np.stack([o["joint_position"] for o in obs_list]) + (0.2 * rng.standard_normal((T, N, 20))).astype(np.float32)
+    carry0 = O.initial_model_carry((N,), p)
+    ref, c_end = O.get_ppo_variables(wa, wc, obs_list, cmd, act.astype(np.float32), done, carry0, p, mirror=True)
+
+    def run(olist, cmds, want_mean):
+        a_obs = np.stack([O.actor_obs_from_dict(o, c) for o, c in zip(olist, cmds)])
+        c_obs = np.stack([O.critic_obs_from_dict(o, c) for o, c in zip(olist, cmds)])
+        ac = torch.zeros((2, 2, N, hidden), device=dev)
+        cc = torch.zeros((2, 2, N, hidden), device=dev)
+        lpf = torch.zeros((20, b.ld), device=dev)
+        out = e.ppo_variables(synth.to_soa(a_obs, 1, dev), synth.to_soa(act.astype(np.float32), 1, dev),
+                              synth.to_soa(done.astype(np.uint8), 1, dev), ac, lpf, synth.to_soa(c_obs, 1, dev), cc,
+                              want_mean=want_mean, n_envs=N)
+        return out, ac, cc, lpf
+
+    out, ac, cc, lpf = run(obs_list, cmd, False)
+    close(S(out["log_probs"], N), ref["log_probs"][..., 0], "log_probs", atol=1e-4)     # |log_prob| up to ~1e3 here
+    close(S(out["entropy"], N), ref["entropy"][..., 0], "entropy", atol=1e-5)
+    close(S(out["values"], N), ref["values"], "values", atol=1e-5)
+    close(S(out["action_std"], N, (20,)), ref["action_std"], "action_std")
+    close(Hn.carry_to_np(ac, N), c_end["actor"], "actor carry")
+    close(Hn.carry_to_np(cc, N), c_end["critic"], "critic carry", atol=1e-5)
+    close(S(lpf, N, (20,)), c_end["lpf_params"], "lpf")
+    # mirror pass (train.py:1463-1481): same entry point on mirror_obs / mirror_cmd
+    m_list = [O.mirror_obs(o) for o in obs_list]
+    m_cmd = np.stack([O.mirror_cmd(c) for c in cmd])
+    mout, _, _, _ = run(m_list, m_cmd, True)
+    close(S(mout["mean"], N, (20,)), ref["mirror_mean"], "mirrored dist.mean()")
+    close(S(mout["values"], N), ref["mirror_value"], "mirrored value", atol=1e-5)
+    e.close()
+
+
+def test_task_plugin_surface_end_to_end(dev):
+    """The reference-shaped host API (kbot-joystick_b200/task.py): observations -> sample_action -> actuators ->
+    terminations through HumanoidWalkingTask, against the oracle's single-env functions."""
+    from kbot_joystick_b200.task import HumanoidWalkingTask, HumanoidWalkingTaskConfig
+
+    N = 96
+    b = Batch(1100, 2, N, dev)
+    task = HumanoidWalkingTask(HumanoidWalkingTaskConfig(num_envs=N))
+    wa = synth.make_weights(77, 65, 40, 256, 2)
+    wc = synth.make_weights(78, 475, 1, 256, 2)
+    task.get_model(synth.weights_to_device(wa, dev), synth.weights_to_device(wc, dev))
+    carry = task.get_initial_model_carry(N, dev)
+    assert set(carry) == {"actor", "actor_mirror", "critic", "critic_mirror", "lpf_params", "lpf_params_mirror"}
+    cmd = task.get_commands(torch.zeros((16, b.ld), device=dev),
+                            {k: synth.to_soa(v, 0, dev) for k, v in b.np["cmd0_rand"].items()}, initial=True, n_envs=N)
+    exact(S(cmd["unified_command"], N, (16,)), b.cmd0_np, "initial command")
+    obs = task.get_observations(b.state_at(0), cmd, b.noise_at(0), b.episode, n_envs=N)
+    o_np, _ = O.get_observations(b.np_state_at(0), b.np_noise_at(0), b.np["episode"], None, P)
+    for name in ("joint_position", "noisy_biased_joint_position", "noisy_joint_velocity", "noisy_imu_gyro", "feet_position",
+                 "projected_gravity", "noisy_imu_projected_gravity", "base_orientation", "center_of_mass_velocity",
+                 "left_foot_touch", "base_height", "imu_gyro"):
+        ref = o_np[name]
+        close(S(obs[name], N, (ref.shape[-1],)), ref, name, atol=1e-5 if "gravity" in name else 1e-6)
+    act = task.sample_action(carry, obs, eps=b.noise["eps_action"][0], argmax=False, n_envs=N)
+    p = O.OracleParams()
+    a_np, mean, std, _, _ = O.sample_action(wa, O.actor_obs_from_dict(o_np, b.cmd0_np), np.zeros((N, 2, 2, 256), np.float32),
+                                            np.zeros((N, 20), np.float32), b.np["noise"]["eps_action"][0], False, p)
+    close(S(act["action"], N, (20,)), a_np, "sample_action")
+    val = task.run_critic(obs, carry["critic"], n_envs=N)
+    v_np, _ = O.critic_forward(wc, O.critic_obs_from_dict(o_np, b.cmd0_np), np.zeros((N, 2, 2, 256), np.float32))
+    close(S(val, N), v_np[:, 0], "run_critic", atol=1e-5)
+    ctrl = task.get_actuators(act["action"], b.state_at(0), b.episode, n_envs=N)
+    ep = b.np["episode"]
+    st = b.np_state_at(0)
+    close(S(ctrl, N, (20,)), O.position_actuator_torque(a_np, st["qpos"][:, 7:], st["qvel"][:, 6:], ep["kp"], ep["kd"],
+                                                       ep["tau_limit"], ep["action_bias"], ep["torque_bias"]), "ctrl", atol=1e-4)
+    term = task.get_terminations(b.state_at(0), n_envs=N)
+    codes, done, succ = O.terminations(st["xpos"], st["qpos"][:, 3:7], st["time"], P)
+    exact(S(term["codes"], N, (3,)), codes, "termination codes")
+    task.close()

@@ -1,0 +1,188 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/kbotstep.h declares, the
+ctypes structs match the C structs, constants agree between spec.py / the oracle / kbs_default_params, the Task mirror
+exposes the reference's plugin surface, and the env sharding covers N > 1 (world_size-2 gloo)."""
+
+import ctypes as C
+import inspect
+import os
+import re
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import kbot_oracle as O
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    from kbot_joystick_b200 import _lib as L
+
+    hdr = (ROOT / "include" / "kbotstep.h").read_text()
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(kbs_\w+)\s*\(", hdr, flags=re.M))
+    assert len(declared) >= 20
+    lib = L.load()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"declared in kbotstep.h but not exported: {missing}"
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    assert lib.kbs_version() == 100
+    assert b"aligned" in lib.kbs_error_string(-3)
+    nm = subprocess.run(["nm", "-D", "--defined-only", os.fspath(L.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (kbs_\w+)", nm))
+    assert declared <= exported
+
+
+def test_default_params_match_spec_and_oracle(lib_built):
+    from kbot_joystick_b200 import _lib as L
+    from kbot_joystick_b200 import spec
+
+    p = L.default_params()               # pure host function: no GPU needed
+    op = O.OracleParams()
+    assert (p.hidden_size, p.depth) == (256, 2)
+    np.testing.assert_array_equal(np.array(p.joint_bias[:], np.float32), O.joint_biases())
+    np.testing.assert_array_equal(np.array(p.joint_range[:], np.float32), O.max_joint_range())
+    np.testing.assert_array_equal(np.array(p.joint_bias[:], np.float32), np.array(spec.JOINT_BIASES, np.float32))
+    np.testing.assert_array_equal(np.array(p.kp[:]), np.array(spec.KP, np.float32))
+    np.testing.assert_array_equal(np.array(p.kd[:], np.float32), np.array(spec.KD, np.float32))
+    np.testing.assert_array_equal(np.array(p.ctrl_limit[:]), np.array(spec.CTRL_LIMIT, np.float32))
+    np.testing.assert_array_equal(np.array(p.reward_scale[:], np.float32), np.array(O.REWARD_SCALES, np.float32))
+    np.testing.assert_array_equal(np.array(p.arm_lo[:], np.float32), O.JOINT_LIMITS64[10:, 0].astype(np.float32))
+    np.testing.assert_array_equal(np.array(p.arm_hi[:], np.float32), O.JOINT_LIMITS64[10:, 1].astype(np.float32))
+    for k in ("ctrl_dt", "min_std", "max_std", "var_scale", "gamma", "lam", "gravity", "eps_quat", "unhealthy_z",
+              "max_tilt", "max_length_sec", "switch_prob", "lpf_alpha", "jpos_noise_mag", "jvel_noise_mag",
+              "gyro_noise_std", "pg_noise_std", "linvel_es", "angvel_es", "rp_es", "rp_es_zero", "bh_es", "bh_standard",
+              "bh_foot_origin", "arm_es", "grace_period", "touchdown_penalty", "feet_es", "com_es", "acc_es", "torque_es"):
+        assert np.float32(getattr(p, k)) == np.float32(getattr(op, k)), k
+    assert (p.body_base, p.body_lfoot, p.body_rfoot) == (spec.BODY_BASE, spec.BODY_LFOOT, spec.BODY_RFOOT)
+    assert (p.sd_gyro, p.sd_imu_quat, p.sd_touch_l, p.sd_touch_r) == (19, 28, 47, 48)
+    assert spec.net_flops(65, 40) == 2150912 and spec.net_flops(475, 1) == 2340864
+
+
+def test_ctypes_structs_match_header(lib_built):
+    """Field order of the ctypes mirrors == field order of the C structs (same names, same count)."""
+    from kbot_joystick_b200 import _lib as L
+
+    hdr = (ROOT / "include" / "kbotstep.h").read_text()
+
+    def c_fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = re.sub(r"^(const\s+)?(kbs_\w+|float|int32_t|int64_t|uint8_t)\s*\*?\s*", "", decl)
+            for nm in names.split(","):
+                out.append(re.sub(r"[\*\s]|\[.*?\]", "", nm))
+        return out
+
+    for cname, cls in (("kbs_params", L.KbsParams), ("kbs_state_view", L.KbsStateView), ("kbs_noise_view", L.KbsNoiseView),
+                       ("kbs_episode_view", L.KbsEpisodeView), ("kbs_net_weights", L.KbsNetWeights),
+                       ("kbs_actor_out", L.KbsActorOut), ("kbs_traj_view", L.KbsTrajView),
+                       ("kbs_reward_carry", L.KbsRewardCarry), ("kbs_rollout_io", L.KbsRolloutIO),
+                       ("kbs_ppo_io", L.KbsPpoIO)):
+        assert c_fields(cname) == [f[0] for f in cls._fields_], cname
+    assert C.sizeof(L.KbsStateView) == 11 * 8 and C.sizeof(L.KbsPpoIO) == 14 * 8
+
+
+def test_product_fails_loudly_without_gpu_or_library(lib_built, monkeypatch):
+    import torch
+
+    from kbot_joystick_b200 import _lib as L
+    from kbot_joystick_b200.engine import KbotStep
+
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            KbotStep()
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", ROOT / "kbot-joystick_b200" / "does_not_exist.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        L.load()
+
+
+def test_product_never_imports_the_oracle():
+    for f in (ROOT / "kbot-joystick_b200").rglob("*.py"):
+        src = f.read_text()
+        assert "kbot_oracle" not in src and "import oracle" not in src, f
+
+
+def test_task_mirror_exposes_reference_plugin_surface():
+    from kbot_joystick_b200.task import HumanoidWalkingTask, HumanoidWalkingTaskConfig
+
+    for name in ("get_model", "get_initial_model_carry", "get_observations", "get_commands", "get_rewards",
+                 "get_terminations", "get_actuators", "run_actor", "run_critic", "sample_action", "get_ppo_variables",
+                 "mirror_joints"):                                    # train.py:1091-1582
+        assert callable(getattr(HumanoidWalkingTask, name)), name
+    assert "argmax" in inspect.signature(HumanoidWalkingTask.sample_action).parameters      # train.py:1555
+    c = HumanoidWalkingTaskConfig()
+    assert (c.hidden_size, c.num_envs, c.rollout_steps, c.gamma, c.lam) == (256, 4096, 100, 0.94, 0.94)   # train.py:1761-1776
+    import torch
+
+    j = torch.arange(20.0).reshape(20, 1)
+    np.testing.assert_array_equal(HumanoidWalkingTask.mirror_joints(j)[:, 0].numpy(),
+                                  O.mirror_joints(np.arange(20, dtype=np.float32)))
+
+
+def test_env_shard_partition():
+    from kbot_joystick_b200.sharding import env_shard
+
+    for n, w in ((4096, 8), (16384, 3), (7, 8), (65536, 8), (1, 1)):
+        spans = [env_shard(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+        for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+            assert s0 + c0 == s1
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        env_shard(8, 8, 8)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import kbot_oracle as O
+from kbot_joystick_b200 import synth
+from kbot_joystick_b200.sharding import env_shard, max_over_ranks, sum_over_ranks
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+N, T = 37, 6
+b = synth.make_batch(3, T, N)                       # every rank draws the same global batch ...
+start, cnt = env_shard(N, rank, world)               # ... and owns a contiguous block of envs
+rng = np.random.default_rng(0)
+v = rng.standard_normal((T, N)).astype(np.float32); r = rng.random((T, N)).astype(np.float32)
+done = rng.random((T, N)) < 0.1; succ = done & (rng.random((T, N)) < 0.5)
+p = O.OracleParams()
+adv_full, _ = O.compute_ppo_inputs(v, r, done, succ, p)
+sl = slice(start, start + cnt)
+adv_loc, _ = O.compute_ppo_inputs(v[:, sl], r[:, sl], done[:, sl], succ[:, sl], p)
+assert np.array_equal(adv_loc, adv_full[:, sl])      # envs are independent: sharding needs no data-path collective
+tot = sum_over_ranks(float(cnt))
+assert tot == N, tot
+t = max_over_ranks(1.0 + rank)
+assert t == float(world), t
+chk = sum_over_ranks(float(adv_loc.astype(np.float64).sum()))
+assert abs(chk - float(adv_full.astype(np.float64).sum())) < 1e-6
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_env_sharding_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % (str(ROOT), str(ROOT / "oracle")))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o}"
+        assert f"rank {r} ok" in o
