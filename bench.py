@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--gemm", default="f16", choices=["f16", "tf32", "simt"],
                     help="LSTM/MLP datapath: tcgen05 2xFP16-split (default), tcgen05 3xTF32, or fp32 FFMA")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the step as one CUDA graph instead of launching eagerly (measured slower: 10.9 vs 10.0 ms)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -103,9 +105,22 @@ def oracle_step(n, T, hidden, seed=4321):
     return run
 
 
+def blas_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core, so lift the BLAS pool limit."""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=n)
+        used = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return used
+    except Exception:  # noqa: BLE001
+        return 1
+
+
 def time_oracle(a, seconds, steps=None, warmup=1):
     n, T = 512, 10
     run = oracle_step(n, T, a.hidden)
+    threads = blas_threads(cpu_cores())
     for _ in range(warmup):
         run()
     t0 = time.perf_counter()
@@ -116,7 +131,7 @@ def time_oracle(a, seconds, steps=None, warmup=1):
         el = time.perf_counter() - t0
         if (steps is not None and k >= steps) or (steps is None and el >= seconds):
             break
-    return {"value": n * T * k / el, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+    return {"value": n * T * k / el, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{k} x ({n} envs x {T} control steps + rewards + GAE), NumPy oracle restatement of train.py "
                       f"(JAX/ksim not installable), BLAS threads = host cores", "seconds": el, "n": n, "T": T, "k": k}
 
@@ -262,21 +277,37 @@ def run_b200(a):
         io_["command"][0].copy_(io_["command"][T])       # next rollout continues from the last command
 
     # ---- device-resident timing ------------------------------------------------------------------------------------
+    # The step is ~330 kernel launches on two streams (the library forks its side stream from / joins it into the
+    # caller's stream with events; nothing allocates after warm-up), so it can be captured into a CUDA graph (--graph);
+    # eager launches are the default because the GPU-side step is long enough to hide the CPU launch cost.
+    l_before = eng.launches
+    step()
+    launches_per_step = eng.launches - l_before
+    run_step, launch_mode = step, "eager"
+    if a.graph:
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            run_step, launch_mode = graph.replay, "cuda-graph replay"
+        except Exception as ex:  # noqa: BLE001
+            print(f"[bench] CUDA graph capture failed ({ex!r}); timing eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
     for _ in range(max(a.warmup, 3)):
-        step()
+        run_step()
     barrier()
     clocks = Clocks(local)
     clocks.start()
-    l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        step()
+        run_step()
     e1.record()
     barrier()
     ck = clocks.finish()
     ms_total = max_ranks(e0.elapsed_time(e1))
-    launches = int(sum_ranks(eng.launches - l0))
+    launches = int(sum_ranks(launches_per_step * a.steps))
     ms_step = ms_total / a.steps
     value = world * N * T / (ms_step * 1e-3)
     assert torch.isfinite(adv).all() and torch.isfinite(total).all(), "non-finite outputs"
@@ -340,7 +371,7 @@ def run_b200(a):
                           "tf32": "f32 (tcgen05 3xTF32 GEMMs, fp32 accumulate)", "simt": "f32"}[a.gemm],
                 "data": "synthetic", "config": config_dict(a, world), "clocks": ck, "gpu_launches": launches,
                 "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernel_breakdown_ms": breakdown,
-                "profile_overflow": overflow, "gemm_path": a.gemm}
+                "profile_overflow": overflow, "gemm_path": a.gemm, "launch_mode": launch_mode}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -140,6 +140,16 @@ int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStr
 
 }  // namespace
 
+int kbs_side_stream_init(kbs_handle* h) {
+  if (h->side_stream) return 0;
+  KBS_CUDA_TRY(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    KBS_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_lstm[i], cudaEventDisableTiming));
+    KBS_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_head[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
 int kbs_scratch_reserve(kbs_handle* h, size_t floats) {
   if (floats <= h->scratch_floats) return KBS_OK;
   if (h->scratch) { KBS_CUDA_TRY(cudaFree(h->scratch)); h->scratch = nullptr; h->scratch_floats = 0; }
@@ -242,6 +252,10 @@ int kbs_destroy(kbs_handle* h) {
     for (int l = 0; l < KBS_MAX_DEPTH; ++l) { cudaFree(N.w_ih[l]); cudaFree(N.w_hh[l]); cudaFree(N.b[l]); }
   }
   cudaFree(h->scratch);
+  if (h->side_stream) {
+    cudaStreamDestroy(h->side_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_lstm[i]); cudaEventDestroy(h->ev_head[i]); }
+  }
   if (h->prof_ev) {
     for (int i = 0; i < 2 * kKbsProfMaxPairs; ++i) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev; delete[] h->prof_id;

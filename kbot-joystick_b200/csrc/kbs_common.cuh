@@ -63,6 +63,9 @@ struct kbs_handle {
   cudaEvent_t* prof_ev = nullptr;   // 2 * kKbsProfMaxPairs events, created on first enable
   int8_t* prof_id = nullptr;        // kernel id of each pair
   // debug: per-CTA phase stamps of one LSTM launch inside kbs_rollout (kbs_debug_tc_trace_attach)
+  // side stream of the fused rollout (heads overlap the next step's LSTM launches); forked/joined with events
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_lstm[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr};
   long long* trace_buf = nullptr;
   int64_t trace_step = -1;
   int trace_layer = 0;
@@ -83,6 +86,7 @@ struct KbsLaunchScope {
 };
 #define KBS_LAUNCH(h, id, st, ...) do { KbsLaunchScope _ls((h), (id), (st)); __VA_ARGS__; } while (0)
 
+int kbs_side_stream_init(kbs_handle* h);   // kbs_api.cu: lazily creates side_stream + events (returns cudaError_t)
 // scratch management (kbs_api.cu)
 int kbs_scratch_reserve(kbs_handle* h, size_t floats);
 

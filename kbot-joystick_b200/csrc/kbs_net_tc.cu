@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
     const char* wb = a.w_sb + size_t(tile) * kb_total * kBBlockBytes;
     for (int b = warp - 1; b < kb_total; b += kProducers) {
       const int s = b % kStages;
+      // (staggering the four opening stages brings the first MMA forward by ~1.7 K cycles but starves stages 1-3:
+      //  measured net loss, so all producers start at once)
       mbar_wait(&empty[s], ((b / kStages) & 1) ^ 1);
       uint8_t* sa = smem + size_t(s) * kStageBytes;
       uint8_t* sb = sa + kABlockBytes;
@@ -423,8 +425,34 @@ rollout_head_kernel(const __grid_constant__ kbs_params P, const __grid_constant_
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int64_t e0 = int64_t(blockIdx.x) * kHeadEnvs;
   const int nout = net == 0 ? KBS_ACTOR_OUT : 1;
-  // stage h2 tile and W_out with cp.async: all ~36 16-byte requests of a thread are in flight at once (a plain
-  // load/store loop exposed one L2 round trip per iteration: 26 us per launch, measured)
+  // The per-joint inputs of the head / torque math do not depend on the GEMM: fetch them first so their L2/HBM latency
+  // hides under the staging and the out-projection (ncu: the kernel was long-scoreboard bound, FMA pipe 10 % active).
+  const int64_t e = e0 + lane;
+  const bool live = e < a.n;
+  const int64_t ld = a.ld;
+  float in_lpf[5], in_eps[5], in_arm[5], in_ain[5], in_q[5], in_qd[5], in_kp[5], in_kd[5], in_lim[5], in_ab[5], in_tb[5];
+  bool rst = false;
+  if (net == 0 && live) {
+    rst = a.done && a.done[e];
+#pragma unroll
+    for (int jj = 0; jj < 5; ++jj) {
+      const int j = 5 * g + jj;
+      const int64_t o = j * ld + e;
+      in_lpf[jj] = a.lpf[o];
+      in_eps[jj] = a.eps ? a.eps[o] : 0.0f;
+      in_arm[jj] = (j >= 10) ? a.arm_cmd[(j - 10) * ld + e] : 0.0f;
+      in_ain[jj] = a.action_in ? a.action_in[o] : 0.0f;
+      if (a.ctrl) {
+        in_q[jj] = a.q[o]; in_qd[jj] = a.qd[o];
+        in_kp[jj] = a.ep.kp ? a.ep.kp[o] : P.kp[j];
+        in_kd[jj] = a.ep.kd ? a.ep.kd[o] : P.kd[j];
+        in_lim[jj] = a.ep.tau_limit ? a.ep.tau_limit[o] : P.ctrl_limit[j];
+        in_ab[jj] = a.ep.action_bias ? a.ep.action_bias[o] : 0.0f;
+        in_tb[jj] = a.ep.torque_bias ? a.ep.torque_bias[o] : 0.0f;
+      }
+    }
+  }
+  // stage h2 tile and W_out with cp.async: all ~36 16-byte requests of a thread are in flight at once
   for (int i = threadIdx.x; i < kHeadEnvs * (H / 4); i += 128) {
     const int r = i / (H / 4), c4 = i % (H / 4);
     float* dst = h_s + r * hs + c4 * 4;
@@ -439,7 +467,6 @@ rollout_head_kernel(const __grid_constant__ kbs_params P, const __grid_constant_
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(w_s + i * 4)), "l"(a.w_out[net] + i * 4) : "memory");
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  const int64_t e = e0 + lane;
   if (net == 1) {
     // critic: 4 warps split K, fixed-order combine
     float s = 0.0f;
@@ -451,7 +478,7 @@ rollout_head_kernel(const __grid_constant__ kbs_params P, const __grid_constant_
     }
     part[g * 32 + lane] = s;
     __syncthreads();
-    if (g == 0 && e < a.n) a.value[e] = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + a.b_out[1][0];
+    if (g == 0 && live) a.value[e] = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + a.b_out[1][0];
     return;
   }
   // actor: thread (env = lane, outputs 10g .. 10g+9)
@@ -474,40 +501,35 @@ rollout_head_kernel(const __grid_constant__ kbs_params P, const __grid_constant_
   }
   __syncthreads();
   // head: thread (env = lane, joints 5g .. 5g+4); all global accesses are env-contiguous rows
-  const bool live = e < a.n;
-  const int64_t ld = a.ld;
-  const bool rst = live && a.done && a.done[e];
   float s_z = 0.0f, s_log = 0.0f;
   constexpr float kHalfLog2Pi = 0.918938533204672742f;
   if (live) {
 #pragma unroll
     for (int jj = 0; jj < 5; ++jj) {
       const int j = 5 * g + jj;
+      const int64_t o = j * ld + e;
       const float sraw = out_s[lane * 41 + KBS_NUM_JOINTS + j];
       const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
       const float sd = fminf((sp + P.min_std) * P.var_scale, P.max_std);
       float m = out_s[lane * 41 + j] + P.joint_bias[j];
-      m = m + ((j >= 10) ? a.arm_cmd[(j - 10) * ld + e] : 0.0f);
-      const float y = a.lpf[j * ld + e];
+      m = m + in_arm[jj];
+      const float y = in_lpf[jj];
       const float yn = y + P.lpf_alpha * (m - y);
-      a.lpf[j * ld + e] = rst ? 0.0f : yn;
+      a.lpf[o] = rst ? 0.0f : yn;
       float act = yn;
-      if (a.eps) act = yn + sd * a.eps[j * ld + e];
-      const float a_eval = a.action_in ? a.action_in[j * ld + e] : act;
+      if (a.eps) act = yn + sd * in_eps[jj];
+      const float a_eval = a.action_in ? in_ain[jj] : act;
       const float z = (a_eval - yn) / sd;
       s_z = s_z + (-0.5f * z * z - kHalfLog2Pi);
       s_log = s_log + logf(sd);
-      if (a.action) a.action[j * ld + e] = act;
-      if (a.std) a.std[j * ld + e] = sd;
+      if (a.action) a.action[o] = act;
+      if (a.std) a.std[o] = sd;
       if (!a.ctrl) continue;
       // PositionActuators.get_ctrl
-      const float kp = a.ep.kp ? a.ep.kp[j * ld + e] : P.kp[j];
-      const float kd = a.ep.kd ? a.ep.kd[j * ld + e] : P.kd[j];
-      const float lim = a.ep.tau_limit ? a.ep.tau_limit[j * ld + e] : P.ctrl_limit[j];
-      const float target = a.ep.action_bias ? __fadd_rn(act, a.ep.action_bias[j * ld + e]) : act;
-      float tau = __fsub_rn(__fmul_rn(kp, __fsub_rn(target, a.q[j * ld + e])), __fmul_rn(kd, a.qd[j * ld + e]));
-      if (a.ep.torque_bias) tau = __fadd_rn(tau, a.ep.torque_bias[j * ld + e]);
-      a.ctrl[j * ld + e] = fminf(fmaxf(tau, -lim), lim);
+      const float target = a.ep.action_bias ? __fadd_rn(act, in_ab[jj]) : act;
+      float tau = __fsub_rn(__fmul_rn(in_kp[jj], __fsub_rn(target, in_q[jj])), __fmul_rn(in_kd[jj], in_qd[jj]));
+      if (a.ep.torque_bias) tau = __fadd_rn(tau, in_tb[jj]);
+      a.ctrl[o] = fminf(fmaxf(tau, -in_lim[jj]), in_lim[jj]);
     }
   }
   part[(g * 32 + lane) * 2] = s_z;
@@ -828,7 +850,7 @@ int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, con
 // ---- fused rollout: tensor-core input projection of all T steps + the recurrent phase --------------------------------
 // Workspace per net: h_sb [depth][2 parity] | x_mid_sb [2] | h2_rm [n][H] (floats)
 static size_t rollout_ws_per_net_bytes(const kbs_handle* h, int64_t n) {
-  return act_sb_bytes(h, n) * (2 * size_t(h->p.depth) + 2) + size_t(n) * h->p.hidden_size * 4 +
+  return act_sb_bytes(h, n) * (2 * size_t(h->p.depth) + 2) + 2 * size_t(n) * h->p.hidden_size * 4 +
          2 * size_t(h->p.depth) * size_t(pad_rows(n)) * h->p.hidden_size * 4 + 256;
 }
 size_t kbs_tc_rollout_ws_floats(const kbs_handle* h, int64_t n) { return 2 * rollout_ws_per_net_bytes(h, n) / 4; }
@@ -889,17 +911,24 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     char* base = reinterpret_cast<char*>(r.ws) + per_net * k;
     hsb[k] = base;                                   // [depth][2] x sbb
     xmid[k] = base + sbb * 2 * depth;                // [2] x sbb
-    h2rm[k] = reinterpret_cast<float*>(xmid[k] + 2 * sbb);
-    fb[k] = h2rm[k] + size_t(n) * H;                 // [depth][c, h] x np*H, FB layout
+    h2rm[k] = reinterpret_cast<float*>(xmid[k] + 2 * sbb);   // [2 parity] x n*H: top-layer output, read by the head
+    fb[k] = h2rm[k] + 2 * size_t(n) * H;             // [depth][c, h] x np*H, FB layout
     for (int l = 0; l < depth; ++l) {                // ABI carry: h -> SB (parity 0), c -> FB
       pack_rows(h, r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H, H, hsb[k] + sbb * (2 * l), n, np, H, st);
       fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 1, st);
     }
   }
   dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile), unsigned(nets));
+  // The head of step t (out-projection, sampling, log-prob, torque, value) feeds nothing back into the recurrence, so
+  // it runs on the handle's side stream, forked from and joined back into the caller's stream with events, while the
+  // LSTM launches of step t+1 proceed: it lands on the SMs the 256-CTA LSTM grid leaves idle in its second wave.
+  { const int rc0 = kbs_side_stream_init(h); if (rc0) return rc0; }
+  cudaStream_t side = h->side_stream;
   for (int64_t t = 0; t < r.T; ++t) {
     const int pin = int(t & 1), pout = pin ^ 1;
     const uint8_t* done_t = r.done ? r.done + t * ld : nullptr;
+    // top layer of step t overwrites h2rm[pin], last read by the head of step t-2
+    if (t >= 2) KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[pin], 0));
     for (int l = 0; l < depth; ++l) {
       LayerArgs2 a2{};
       for (int k = 0; k < nets; ++k) {
@@ -911,15 +940,19 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
         a.c = fb[k] + fbf * (2 * l);
         a.h_carry = fb[k] + fbf * (2 * l + 1);
         a.x_next_sb = (l + 1 < depth) ? xmid[k] + sbb * (l & 1) : nullptr;
-        a.h_next_rm = (l + 1 < depth) ? nullptr : h2rm[k];
+        a.h_next_rm = (l + 1 < depth) ? nullptr : h2rm[k] + size_t(pin) * n * H;
         a.done = done_t;
         a.n = n;
         if (h->trace_buf && t == h->trace_step && l == h->trace_layer) a.trace = h->trace_buf;
       }
       KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(kind, a2, grid, st)));
     }
+    KBS_CUDA_TRY(cudaEventRecord(h->ev_lstm[pin], st));
+    KBS_CUDA_TRY(cudaStreamWaitEvent(side, h->ev_lstm[pin], 0));
     HeadArgs ha{};
-    for (int k = 0; k < nets; ++k) { ha.h2[k] = h2rm[k]; ha.w_out[k] = h->net[k].w_out; ha.b_out[k] = h->net[k].b_out; }
+    for (int k = 0; k < nets; ++k) {
+      ha.h2[k] = h2rm[k] + size_t(pin) * n * H; ha.w_out[k] = h->net[k].w_out; ha.b_out[k] = h->net[k].b_out;
+    }
     ha.arm_cmd = r.actor_obs + (size_t(t) * KBS_ACTOR_OBS + 55) * ld;
     ha.lpf = r.lpf;
     ha.eps = r.eps_action ? r.eps_action + size_t(t) * KBS_NUM_JOINTS * ld : nullptr;
@@ -935,10 +968,14 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     ha.entropy = r.entropy ? r.entropy + size_t(t) * ld : nullptr;
     ha.std = r.action_std ? r.action_std + size_t(t) * KBS_NUM_JOINTS * ld : nullptr;
     ha.n = n; ha.ld = ld; ha.H = H;
-    KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
-               (rollout_head_kernel<<<dim3(unsigned((n + kHeadEnvs - 1) / kHeadEnvs), unsigned(nets)), 128, head_smem, st>>>(
+    KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, side,
+               (rollout_head_kernel<<<dim3(unsigned((n + kHeadEnvs - 1) / kHeadEnvs), unsigned(nets)), 128, head_smem, side>>>(
                    h->p, ha)));
+    KBS_CUDA_TRY(cudaEventRecord(h->ev_head[pin], side));
   }
+  // join: everything the heads wrote (and the lpf state) is visible to the caller's stream
+  KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[0], 0));
+  if (r.T > 1) KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[1], 0));
   for (int k = 0; k < nets; ++k)
     for (int l = 0; l < depth; ++l) {                // FB state -> ABI carry
       fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 0, st);
