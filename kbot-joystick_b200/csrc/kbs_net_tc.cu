@@ -24,24 +24,32 @@
 namespace {
 
 constexpr int kPanelRows = 128;          // UMMA M
-constexpr int kTileCols = 256;           // UMMA N: 64 hidden units x 4 gates (gate-interleaved)
-constexpr int kUnitsPerTile = 64;
+constexpr int kTileCols = 128;           // UMMA N: 32 hidden units x 4 gates (gate-interleaved), or 128 plain columns (proj)
+constexpr int kUnitsPerTile = 32;
 // One pipeline stage = one SB block of each operand = 4 chunks of 16 B along K (2 MMA k-steps): K = 16 for TF32
 // operands, 32 for F16 operands -- the BYTES (and therefore all shared-memory offsets / descriptors) are identical.
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 constexpr int kABlockBytes = 2 * 4 * kPanelRows * 16;   // [hi|lo][4 chunks][128 rows][16 B] = 16 KB
-constexpr int kBBlockBytes = 2 * 4 * kTileCols * 16;    // 32 KB
-constexpr int kStageBytes = kABlockBytes + kBBlockBytes;   // 48 KB
-constexpr int kEpiWarps = 8;             // kEpiWarps/4 per TMEM lane quarter; a thread owns kEpiChunks x 16 of the tile's 64 units
-constexpr int kEpiChunks = 16 / kEpiWarps;   // (measured: 16 warps = same epilogue time as 8, but spills at the 96-register cap)
-// warp 0 = MMA issuer (+ TMEM allocation); warps 1..8 = epilogue.  Lane 0 of warps 1..4 doubles as a bulk-copy
-// producer during the K loop (the epilogue warps are idle then).  MEASURED (tools/bulk_copy_bench2.cu,
-// profiles/r01_bulk_copy_microbench.md): one thread can start a new stage only every ~735 cycles whatever its size,
-// so a single producer caps the fill rate at 48 KB / 735 clk = 65 B/clk/SM and, with two requests per stage, at ~32;
-// four producers reach the ~80 B/clk/SM port limit, above the 62.5 B/clk the MMA loop consumes.
-constexpr int kProducers = 4;
-constexpr int kThreadsTC = 32 + 32 * kEpiWarps;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int kBBlockBytes = 2 * 4 * kTileCols * 16;    // 16 KB
+constexpr int kStageBytes = kABlockBytes + kBBlockBytes;   // 32 KB
+static_assert(kABlockBytes == kBBlockBytes, "the two producer lanes copy equal-sized blocks");
+// Persistent CTA (one per SM) walking a list of (net, panel, tile) items.  TMEM holds TWO accumulator sets
+// {hi.hi sum | correction sum} x 128 columns, so the epilogue of item j (TMEM -> cell math -> state stores) overlaps the
+// MMAs of item j+1 -- with 256-column tiles both accumulators filled TMEM and the epilogue (as long as the FP16 K loop,
+// profiles/r01_tc_kernel_phases.md) ran serially after it.
+// warp 0 = MMA issuer (+ TMEM allocation); warps 1..3 = bulk-copy producers (lane 0; one thread can start a stage only
+// every ~735 cycles, profiles/r01_bulk_copy_microbench.md); warps 4..11 = epilogue (2 per TMEM lane quarter).
+// MEASURED (tools/tc_trace.py per-stage stamps): one thread issues a tcgen05.mma only every ~108 cycles, which hides
+// behind a 128-cycle N = 256 instruction but not behind a 64-cycle N = 128 one -- so THREE threads issue, two MMAs per
+// stage each: warp 0 the hi.hi MMAs (main set), warps 1 / 2 the lo.hi + hi.lo MMAs of k-step 0 / 1 (correction set).
+// All three commit to the stage's empty barrier; warp 2's first MMA of an item is ordered after warp 1's (which
+// zero-initialises the correction set) with tcgen05.fence + an mbarrier.
+constexpr int kIssuers = 3;
+constexpr int kProducers = 2;
+constexpr int kEpiWarps = 8;
+constexpr int kThreadsTC = 32 * (kIssuers + kProducers + kEpiWarps);
+constexpr int kMaxBias = 1024;           // 4H floats per net (H <= 256)
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kMaxBias * 4 + 256 /*barriers*/ + 1024 /*align*/;
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,18 +75,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// multicast variant: the slice lands at the same CTA-relative offset in every CTA of `mask`, and completes `bytes` on
-// the mbarrier at the same offset in each of them
-__device__ __forceinline__ void bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+// one lane of a converged warp; the surrounding code stays warp-uniform, so the compiler keeps descriptors / addresses
+// in uniform registers instead of moving them there (R2UR) for every tcgen05 instruction
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -118,19 +120,21 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -163,7 +167,7 @@ struct LayerArgs {
   const char* x_sb;       // A blocks, first K segment: [panels][kb_x] blocks (layer input / observation rows)
   const char* h_sb_in;    // A blocks, second K segment: [panels][kb_h] blocks (h_{t-1}, reset where done_{t-1}); kb_h may be 0
   const char* w_sb;       // B blocks: [tiles][kb_x + kb_h]
-  const float* bias_t;    // [tiles][256] bias in tile-column order
+  const float* bias_t;    // [tiles][128] bias in tile-column order
   float* c;               // LSTM: cell carry in/out (reset where done), fp32 "FB" blocked layout (fb_offset)
   float* h_carry;         // LSTM: hidden carry out (reset where done), FB layout
   char* h_sb_out;         // LSTM: SB recurrent state out (reset where done); must NOT alias h_sb_in
@@ -174,217 +178,263 @@ struct LayerArgs {
   long long* trace;       // debug: per-CTA clock64 stamps [ctas][8] or nullptr
   int64_t n;              // valid rows (LSTM/RAW: envs; PROJ: T * padded envs, all rows valid)
   int H, kb_x, kb_h, mode;
+  int panels, tiles;      // work items of this net = panels x tiles (panels = 0: net unused)
+  int dbg;                // profiling only (KBS_TC_EPI_DEBUG): 1 = linear instead of sigmoid/tanh, 2 = no state stores
 };
-struct LayerArgs2 { LayerArgs net[2]; };   // blockIdx.z selects the network (actor / critic share one launch)
+struct LayerArgs2 { LayerArgs net[2]; };   // actor / critic share one launch
+
+struct WorkItem { int net, panel, tile; };
+__device__ __forceinline__ WorkItem decode_item(const LayerArgs2& args, int item) {
+  const int n0 = args.net[0].panels * args.net[0].tiles;
+  WorkItem w;
+  w.net = item >= n0 ? 1 : 0;
+  const int r = item - (w.net ? n0 : 0);
+  const int tiles = args.net[w.net].tiles;
+  w.panel = r / tiles;          // consecutive items share the activation panel (L2 reuse of A across its tiles)
+  w.tile = r - w.panel * tiles;
+  return w;
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __grid_constant__ LayerArgs2 args) {
-  const LayerArgs& a = args.net[blockIdx.z];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + 1024);
-  uint64_t* full = bars;                 // [kStages]
-  uint64_t* empty = bars + kStages;      // [kStages]
-  uint64_t* acc_full = bars + 2 * kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);                 // [2 nets][kMaxBias]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + 2 * kMaxBias * 4);
+  uint64_t* full = bars;                      // [kStages]  bulk copies landed
+  uint64_t* empty = bars + kStages;           // [kStages]  MMAs have read the stage
+  uint64_t* acc_full = bars + 2 * kStages;    // [2]        accumulator set complete
+  uint64_t* acc_empty = acc_full + 2;         // [2]        epilogue has pulled the set into registers
+  uint64_t* corr_init = acc_empty + 2;        // [2]        warp 1 has issued the zero-initialising correction MMA of the set
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_init + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int panel = blockIdx.x, tile = blockIdx.y;
-  const int H = a.H;
-  long long* tr = a.trace ? a.trace + ((size_t(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  const int n_items = args.net[0].panels * args.net[0].tiles + args.net[1].panels * args.net[1].tiles;
+  long long* tr = args.net[0].trace ? args.net[0].trace + size_t(blockIdx.x) * 8 : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = clock64();
-  const int kb_x = a.kb_x, kb_total = a.kb_x + a.kb_h;
-  constexpr int kBlk = kbs_block_k(KIND);        // K elements per block
-  const int kb_out = H / kBlk;                   // K blocks of an [.][H] SB activation buffer
-  // Thread-block cluster along the panel axis: the csz CTAs of a cluster share one weight tile, so every CTA fetches
-  // 1/csz of each weight block and multicasts it to all of them (optional, see launch_layer).
-  const uint32_t csz = cluster_nctarank(), crank = cluster_ctarank();
-  const uint16_t cmask = uint16_t((1u << csz) - 1u);
+  // CTA 0 only: per-stage stamps of the first 64 stages: [0] producer saw empty, [1] producer issued, [2] MMA saw full,
+  // [3] MMA issued + committed
+  long long* tr2 = (args.net[0].trace && blockIdx.x == 0) ? args.net[0].trace + size_t(gridDim.x) * 8 : nullptr;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], csz); }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kIssuers); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], kIssuers); mbar_init(&acc_empty[b], kEpiWarps); mbar_init(&corr_init[b], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {   // TMEM: 2 x 256 fp32 accumulator columns x 128 lanes (hi.hi sum | correction sum)
+  if (warp == 0) {   // TMEM: 2 accumulator sets x {hi.hi | correction} x 128 fp32 columns = all 512 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(uint32_t(2 * kTileCols)));
+                 "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (warp >= 1) {
-    for (int i = threadIdx.x - 32; i < kTileCols; i += 32 * kEpiWarps) bias_s[i] = a.bias_t[size_t(tile) * kTileCols + i];
   }
   tc_fence_before();
   __syncthreads();
-  if (csz > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts / commits into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tr && threadIdx.x == 0) tr[1] = clock64();    // setup done
 
-  if (warp >= 1 && warp <= kProducers && lane == 0) {
-    // ===== producers: stage b belongs to producer b % kProducers; one bulk copy per operand per stage =====
-    const char* xa = a.x_sb + size_t(panel) * kb_x * kABlockBytes;
-    const char* ha = a.h_sb_in + size_t(panel) * a.kb_h * kABlockBytes;
-    const char* wb = a.w_sb + size_t(tile) * kb_total * kBBlockBytes;
-    for (int b = warp - 1; b < kb_total; b += kProducers) {
-      const int s = b % kStages;
-      // (staggering the four opening stages brings the first MMA forward by ~1.7 K cycles but starves stages 1-3:
-      //  measured net loss, so all producers start at once)
-      mbar_wait(&empty[s], ((b / kStages) & 1) ^ 1);
-      uint8_t* sa = smem + size_t(s) * kStageBytes;
-      uint8_t* sb = sa + kABlockBytes;
-      mbar_expect_tx(&full[s], kStageBytes);
-      const char* asrc = (b < kb_x) ? xa + size_t(b) * kABlockBytes : ha + size_t(b - kb_x) * kABlockBytes;
-      bulk_g2s(sa, asrc, kABlockBytes, &full[s]);
-      if (csz == 1) {
-        bulk_g2s(sb, wb + size_t(b) * kBBlockBytes, kBBlockBytes, &full[s]);
-      } else {
-        const uint32_t slice = kBBlockBytes / csz;
-        bulk_g2s_mcast(sb + crank * slice, wb + size_t(b) * kBBlockBytes + crank * slice, slice, &full[s], cmask);
-      }
-    }
-  }
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== MMA issuer: 2 k-steps x (lo.hi + hi.lo -> correction accumulator, hi.hi -> main accumulator) per stage =====
-      for (int b = 0; b < kb_total; ++b) {
-        const int s = b % kStages;
-        mbar_wait(&full[s], (b / kStages) & 1);
-        tc_fence_after();
-        if (tr && b == 0) tr[2] = clock64();        // first stage landed
-        const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
-        const uint32_t sb = sa + kABlockBytes;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          // A: [part][chunk][128 rows][16 B]: part stride 8 KB, chunk stride 2 KB.   B: part 16 KB, chunk 4 KB.
-          const uint64_t a_hi = umma_desc(sa + ks * 4096, 2048, 128);
-          const uint64_t a_lo = umma_desc(sa + 8192 + ks * 4096, 2048, 128);
-          const uint64_t b_hi = umma_desc(sb + ks * 8192, 4096, 128);
-          const uint64_t b_lo = umma_desc(sb + 16384 + ks * 8192, 4096, 128);
-          umma<KIND>(tmem_base + kTileCols, a_lo, b_hi, (b | ks) != 0);
-          umma<KIND>(tmem_base + kTileCols, a_hi, b_lo, 1);
-          umma<KIND>(tmem_base, a_hi, b_hi, (b | ks) != 0);
-        }
-        // frees the stage (in every CTA that multicasts into it) when these MMAs have read it
-        if (csz == 1) umma_commit(&empty[s]); else umma_commit_mcast(&empty[s], cmask);
-      }
-      umma_commit(acc_full);             // accumulators complete
-      if (tr) tr[3] = clock64();                    // all MMAs issued
-    }
-    __syncwarp();                        // lanes 1..31 must not reach the CTA barrier before lane 0 (bar.sync is warp-aligned)
-  } else {
-    // ===== epilogue: warp%4 selects the TMEM lane quarter, (warp-1)/4 the group of kEpiChunks x 16 units =====
-    __syncwarp();
-    const int q4 = warp & 3, cg = (warp - 1) >> 2;
-    const int r = q4 * 32 + lane;
-    const int64_t R = int64_t(panel) * kPanelRows + r;
-    const bool live = R < a.n;
-    constexpr float kCorr = (KIND == KBS_KIND_F16) ? (1.0f / kKbsF16LoScale) : 1.0f;   // lo planes are scaled by 2^11
-    float4 cpre[4 * kEpiChunks];         // c_{t-1} of this thread's units, fetched under the MMA loop
-    if (a.mode == MODE_LSTM && live) {
-#pragma unroll
-      for (int j = 0; j < 4 * kEpiChunks; ++j)
-        cpre[j] = *reinterpret_cast<const float4*>(a.c + fb_offset(R, tile * kUnitsPerTile + cg * 16 * kEpiChunks + j * 4, H));
-    }
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    if (tr && threadIdx.x == 160) tr[4] = clock64();  // accumulators ready: epilogue starts (warp 5: pure epilogue warp)
-    const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16);
-    if (a.mode == MODE_PROJ) {
-      // x = acc + bias for 128 plain columns of this thread's row -> SB planes of the LSTM input
-#pragma unroll 1
-      for (int cc = 0; cc < 4 * kEpiChunks; ++cc) {
-        const int col = cg * 64 * kEpiChunks + cc * 16;
-        float v[16], cr[16];
-        tmem_ld16(tq + col, v);
-        tmem_ld16(tq + kTileCols + col, cr);
-        tmem_ld_wait();
-        if (!live || col >= H) continue;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float o[4] = {v[i] + kCorr * cr[i] + bias_s[col + i], v[i + 1] + kCorr * cr[i + 1] + bias_s[col + i + 1],
-                              v[i + 2] + kCorr * cr[i + 2] + bias_s[col + i + 2], v[i + 3] + kCorr * cr[i + 3] + bias_s[col + i + 3]};
-          sb_store4<kPanelRows, KIND>(a.x_next_sb, R, col + i, kb_out, o);
-        }
-      }
-    } else {
-      const bool rst = live && a.done && a.done[R];
-      // the previous cell state of this thread's units was prefetched while the MMAs ran (cpre)
-#pragma unroll
-      for (int cj = 0; cj < kEpiChunks; ++cj) {
-        const int uo = (cg * kEpiChunks + cj) * 16;          // unit offset inside the tile
-        const uint32_t t0 = tq + uint32_t(uo);
-        float gi[16], gf[16], gg[16], go[16];
-        tmem_ld16(t0, gi);
-        tmem_ld16(t0 + 64, gf);
-        tmem_ld16(t0 + 128, gg);
-        tmem_ld16(t0 + 192, go);
-        tmem_ld_wait();
-        {  // + correction accumulator (hi.lo + lo.hi), round-to-nearest
-          float cr[16];
-          tmem_ld16(t0 + kTileCols, cr); tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) gi[i] += kCorr * cr[i];
-          tmem_ld16(t0 + kTileCols + 64, cr); tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) gf[i] += kCorr * cr[i];
-          tmem_ld16(t0 + kTileCols + 128, cr); tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) gg[i] += kCorr * cr[i];
-          tmem_ld16(t0 + kTileCols + 192, cr); tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) go[i] += kCorr * cr[i];
-        }
-        const int u0 = tile * kUnitsPerTile + uo;            // first hidden unit of this chunk
-        if (live) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          gi[i] += bias_s[uo + i]; gf[i] += bias_s[64 + uo + i]; gg[i] += bias_s[128 + uo + i]; go[i] += bias_s[192 + uo + i];
-        }
-        if (a.mode == MODE_RAW) {
-          float* g = a.raw + R * 4 * H + u0;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            *reinterpret_cast<float4*>(g + i) = make_float4(gi[i], gi[i + 1], gi[i + 2], gi[i + 3]);
-            *reinterpret_cast<float4*>(g + H + i) = make_float4(gf[i], gf[i + 1], gf[i + 2], gf[i + 3]);
-            *reinterpret_cast<float4*>(g + 2 * H + i) = make_float4(gg[i], gg[i + 1], gg[i + 2], gg[i + 3]);
-            *reinterpret_cast<float4*>(g + 3 * H + i) = make_float4(go[i], go[i + 1], go[i + 2], go[i + 3]);
+  if (warp >= kIssuers && warp < kIssuers + kProducers) {
+    if (lane < 2) {
+      // ===== producers: global stage g belongs to producer warp g % kProducers.  MEASURED (tools/bulk_copy_bench3.cu): a
+      // cp.async.bulk blocks its issuing thread ~530 cycles (16 KB), so the two operand copies of a stage are issued by
+      // TWO lanes in one instruction (lane 0: activation block, lane 1: weight block) instead of back to back.
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const WorkItem w = decode_item(args, item);
+        const LayerArgs& a = args.net[w.net];
+        const int kb_x = a.kb_x, kb_total = a.kb_x + a.kb_h;
+        const char* xa = a.x_sb + size_t(w.panel) * kb_x * kABlockBytes;
+        const char* ha = a.h_sb_in + size_t(w.panel) * a.kb_h * kABlockBytes;
+        const char* wb = a.w_sb + size_t(w.tile) * kb_total * kBBlockBytes;
+        for (int b = 0; b < kb_total; ++b, ++g) {
+          if (int(g % kProducers) != warp - kIssuers) continue;
+          const int s = g % kStages;
+          const uint32_t cp_bytes = (a.dbg & 16) ? 16u : uint32_t(kABlockBytes);   // dbg 16: token copies (MMA-rate probe)
+          if (lane == 0) {
+            mbar_wait(&empty[s], ((g / kStages) & 1) ^ 1);
+            if (tr2 && g < 64) tr2[g] = clock64();
+            mbar_expect_tx(&full[s], 2 * cp_bytes);
           }
-        } else {
+          __syncwarp(0x3);
+          uint8_t* sa = smem + size_t(s) * kStageBytes;
+          const char* src = lane == 0 ? ((b < kb_x) ? xa + size_t(b) * kABlockBytes : ha + size_t(b - kb_x) * kABlockBytes)
+                                      : wb + size_t(b) * kBBlockBytes;
+          bulk_g2s(sa + lane * kABlockBytes, src, cp_bytes, &full[s]);    // kABlockBytes == kBBlockBytes
+          if (tr2 && g < 64 && lane == 0) tr2[64 + g] = clock64();
+        }
+      }
+    }
+    __syncwarp();                        // reconverge before the CTA barrier (bar.sync is warp-aligned)
+  } else if (warp < kIssuers) {
+    {
+      // ===== MMA issuers (whole warp runs the loop; one elected lane issues): per stage, warp 0: hi.hi of both k-steps ->
+      // main set; warp 1 / 2: lo.hi + hi.lo of k-step 0 / 1 -> correction set =====
+      uint32_t g = 0;
+      int j = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+        const WorkItem w = decode_item(args, item);
+        const LayerArgs& a = args.net[w.net];
+        const int kb_total = a.kb_x + a.kb_h;
+        const int buf = j & 1;
+        mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);     // the epilogue of item j-2 has drained this set
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + buf * (2 * kTileCols), d_corr = d_main + kTileCols;
+        for (int b = 0; b < kb_total; ++b, ++g) {
+          const int s = g % kStages;
+          mbar_wait(&full[s], (g / kStages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
+          const uint32_t sb = sa + kABlockBytes;
+          // [part][chunk][128 rows][16 B]: part stride 8 KB, chunk stride 2 KB (A and B alike); k-step stride 4 KB
+          if (warp == 0) {
+            const uint64_t a0 = umma_desc(sa, 2048, 128), b0 = umma_desc(sb, 2048, 128);
+            const uint64_t a1 = umma_desc(sa + 4096, 2048, 128), b1 = umma_desc(sb + 4096, 2048, 128);
+            if (elect_one()) {
+              if (tr && g == 0) tr[2] = clock64();        // first stage landed
+              if (tr2 && g < 64) tr2[128 + g] = clock64();
+              umma<KIND>(d_main, a0, b0, b != 0);
+              umma<KIND>(d_main, a1, b1, 1);
+              umma_commit(&empty[s]);          // frees the stage when these MMAs have read it
+              if (tr2 && g < 64) tr2[192 + g] = clock64();
+            }
+          } else {
+            const int ks = warp - 1;
+            const uint64_t a_hi = umma_desc(sa + ks * 4096, 2048, 128);
+            const uint64_t a_lo = umma_desc(sa + 8192 + ks * 4096, 2048, 128);
+            const uint64_t b_hi = umma_desc(sb + ks * 4096, 2048, 128);
+            const uint64_t b_lo = umma_desc(sb + 8192 + ks * 4096, 2048, 128);
+            if (b == 0 && warp == 2) {            // warp 1's accumulate = 0 MMA must be queued first
+              mbar_wait(&corr_init[buf], (j >> 1) & 1);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              umma<KIND>(d_corr, a_lo, b_hi, (b | ks) != 0);
+              if (b == 0 && warp == 1) { tc_fence_before(); mbar_arrive(&corr_init[buf]); }
+              umma<KIND>(d_corr, a_hi, b_lo, 1);
+              umma_commit(&empty[s]);
+            }
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          umma_commit(&acc_full[buf]);       // accumulator set complete (this warp's share)
+          if (tr && j == 0 && warp == 0) tr[3] = clock64();
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue: warp%4 selects the TMEM lane quarter, (warp-4)/4 the half of the tile's 128 columns =====
+    // the whole bias vector of each net (<= 4 KB) goes to shared memory; only the epilogue warps wait for it (named
+    // barrier 1), the issuers and producers are already running
+    {
+      const int et = threadIdx.x - 32 * (kIssuers + kProducers);
+      for (int k = 0; k < 2; ++k) {
+        const int nb = args.net[k].panels ? args.net[k].tiles * kTileCols : 0;
+        for (int i = et * 4; i < nb; i += 32 * kEpiWarps * 4)
+          *reinterpret_cast<float4*>(bias_s + k * kMaxBias + i) = *reinterpret_cast<const float4*>(args.net[k].bias_t + i);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    }
+    const int q4 = warp & 3, c2 = (warp - kIssuers - kProducers) >> 2;
+    const int r = q4 * 32 + lane;
+    constexpr float kCorr = (KIND == KBS_KIND_F16) ? (1.0f / kKbsF16LoScale) : 1.0f;   // lo planes are scaled by 2^11
+    constexpr int kBlk = kbs_block_k(KIND);
+    int j = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+      const WorkItem w = decode_item(args, item);
+      const LayerArgs& a = args.net[w.net];
+      const int H = a.H, kb_out = H / kBlk;
+      const int buf = j & 1;
+      const int64_t R = int64_t(w.panel) * kPanelRows + r;
+      const bool live = R < a.n;
+      // tile column layout (LSTM): [half c2][gate i,f,g,o][16 units]; this thread: 16 units x 4 gates = 64 columns
+      const int u0 = w.tile * kUnitsPerTile + c2 * 16;          // first hidden unit of this thread
+      float4 cpre[4];                                           // c_{t-1}, fetched while the MMAs of this item run
+      if (a.mode == MODE_LSTM && live) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cpre[q] = *reinterpret_cast<const float4*>(a.c + fb_offset(R, u0 + q * 4, H));
+      }
+      const bool rst = a.mode == MODE_LSTM && live && a.done && a.done[R];
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      if (tr && j == 0 && threadIdx.x == 32 * (kIssuers + kProducers)) tr[4] = clock64();
+      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * kTileCols) + c2 * 64);
+      float v[64];
+      {
+        float cr[32];
+        tmem_ld32(tq, v);
+        tmem_ld32(tq + 32, v + 32);
+        tmem_ld32(tq + kTileCols, cr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += kCorr * cr[i];
+        tmem_ld32(tq + kTileCols + 32, cr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[32 + i] += kCorr * cr[i];
+      }
+      // the accumulator set is in registers: hand it back to the MMA issuer before doing the math
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      const float* bs = bias_s + w.net * kMaxBias + w.tile * kTileCols + c2 * 64;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] += bs[i];
+      if (!live) continue;
+      if (a.mode == MODE_PROJ) {
+        const int col0 = w.tile * kTileCols + c2 * 64;
+        if (col0 < H) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            const float o[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
+            sb_store4<kPanelRows, KIND>(a.x_next_sb, R, col0 + i, kb_out, o);
+          }
+        }
+      } else if (a.mode == MODE_RAW) {
+        float* g = a.raw + R * 4 * H + u0;
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(g + gate * H + i) =
+                make_float4(v[gate * 16 + i], v[gate * 16 + i + 1], v[gate * 16 + i + 2], v[gate * 16 + i + 3]);
+      } else {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 c4 = cpre[cj * 4 + (i >> 2)];
+          const float4 c4 = cpre[i >> 2];
           const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
-          float hn[4], cn[4], hr[4], cr[4];
+          float hn[4], cn[4], cr[4];
 #pragma unroll
           for (int l = 0; l < 4; ++l) {
+            const float gi = v[i + l], gf = v[16 + i + l], gg = v[32 + i + l], go = v[48 + i + l];
             // c' = s(f) c + s(i) tanh(g);  h' = s(o) tanh(c')   (eqx LSTMCell)
-            cn[l] = sigmoidf_(gf[i + l]) * cv[l] + sig_mul_tanh(gi[i + l], gg[i + l]);
-            hn[l] = sig_mul_tanh(go[i + l], cn[l]);
-            hr[l] = rst ? 0.0f : hn[l];
+            if (a.dbg & 1) { cn[l] = gf * cv[l] + gi * gg; hn[l] = go * cn[l]; }
+            else {
+              cn[l] = sigmoidf_(gf) * cv[l] + sig_mul_tanh(gi, gg);
+              hn[l] = sig_mul_tanh(go, cn[l]);
+            }
             cr[l] = rst ? 0.0f : cn[l];
           }
-          *reinterpret_cast<float4*>(a.c + fb_offset(R, u0 + i, H)) = make_float4(cr[0], cr[1], cr[2], cr[3]);
-          *reinterpret_cast<float4*>(a.h_carry + fb_offset(R, u0 + i, H)) = make_float4(hr[0], hr[1], hr[2], hr[3]);
+          if ((a.dbg & 2) && hn[0] != 12345.0f) continue;
           KbsSplit4 sp = sb_split4<KIND>(hn);               // one split serves the next layer (un-reset) ...
           if (a.x_next_sb) sb_store_split<kPanelRows, KIND>(a.x_next_sb, R, u0 + i, kb_out, sp);
-          if (rst) { sp.hi = make_uint4(0u, 0u, 0u, 0u); sp.lo = sp.hi; }
-          sb_store_split<kPanelRows, KIND>(a.h_sb_out, R, u0 + i, kb_out, sp);   // ... and the recurrent input (reset)
           if (a.h_next_rm) *reinterpret_cast<float4*>(a.h_next_rm + R * H + u0 + i) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-        }
-        }
+          if (rst) { sp.hi = make_uint4(0u, 0u, 0u, 0u); sp.lo = sp.hi; hn[0] = hn[1] = hn[2] = hn[3] = 0.0f; }
+          sb_store_split<kPanelRows, KIND>(a.h_sb_out, R, u0 + i, kb_out, sp);   // ... and the recurrent input (reset)
+          *reinterpret_cast<float4*>(a.c + fb_offset(R, u0 + i, H)) = make_float4(cr[0], cr[1], cr[2], cr[3]);
+          *reinterpret_cast<float4*>(a.h_carry + fb_offset(R, u0 + i, H)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
         }
       }
+      if (tr && j == 0 && threadIdx.x == 32 * (kIssuers + kProducers)) tr[7] = clock64();
     }
   }
-  if (tr && threadIdx.x == 160) tr[7] = clock64();   // this warp's epilogue done
   tc_fence_before();
   __syncthreads();
   if (tr && threadIdx.x == 0) { tr[5] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); tr[6] = sm; }
-  if (csz > 1) cluster_sync_all();     // no CTA leaves while peers may still signal its barriers
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(2 * kTileCols)));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
 }
 
@@ -546,7 +596,8 @@ rollout_head_kernel(const __grid_constant__ kbs_params P, const __grid_constant_
 
 // ---- packing kernels ------------------------------------------------------------------------------------------------
 // eqx LSTMCell weights [4H][H] x2 + bias [4H]  ->  gate-interleaved SB tiles (hi/lo) + interleaved bias.
-// tile j, column c: gate = c / 64, unit = 64 j + c % 64  (so one 256-column tile holds i,f,g,o of 64 units)
+// tile j (128 columns = 32 hidden units), column c = half * 64 + gate * 16 + uu  ->  unit = 32 j + 16 half + uu:
+// an epilogue thread that owns 16 units finds their i, f, g, o pre-activations in 64 CONSECUTIVE TMEM columns.
 template <int KIND>
 __global__ void __launch_bounds__(256)
 pack_lstm_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b,
@@ -554,10 +605,11 @@ pack_lstm_weights_kernel(const float* __restrict__ w_ih, const float* __restrict
   const int kq = 2 * H / 4;
   const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (idx >= int64_t(4 * H) * kq) return;
-  const int col_g = int(idx / kq);                        // global packed column: tile * 256 + c
+  const int col_g = int(idx / kq);                        // global packed column: tile * 128 + c
   const int k = int(idx % kq) * 4;
   const int tile = col_g / kTileCols, c = col_g % kTileCols;
-  const int gate = c / kUnitsPerTile, u = tile * kUnitsPerTile + c % kUnitsPerTile;
+  const int half = c / 64, gate = (c % 64) / 16, uu = c % 16;
+  const int u = tile * kUnitsPerTile + half * 16 + uu;
   const int row = gate * H + u;                           // eqx row (i,f,g,o blocks of H)
   const float* src = (k < H) ? w_ih + size_t(row) * H + k : w_hh + size_t(row) * H + (k - H);
   const float x[4] = {src[0], src[1], src[2], src[3]};
@@ -565,14 +617,14 @@ pack_lstm_weights_kernel(const float* __restrict__ w_ih, const float* __restrict
   if (k == 0) bias_t[col_g] = b[row];
 }
 
-// eqx Linear weight [H][ldw] (K zero-padded to ldw) -> one 256-column SB tile (rows >= H zero) with K padded to Kp.
+// eqx Linear weight [H][ldw] (K zero-padded to ldw) -> ceil(H/128) SB tiles of 128 plain columns (rows >= H zero), K padded to Kp.
 template <int KIND>
 __global__ void __launch_bounds__(256)
 pack_proj_weights_kernel(const float* __restrict__ w, int ldw, const float* __restrict__ b, char* __restrict__ w_sb,
-                         float* __restrict__ bias_t, int H, int Kp) {
+                         float* __restrict__ bias_t, int H, int Kp, int cols) {
   const int kq = Kp / 4;
   const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  if (idx >= int64_t(kTileCols) * kq) return;
+  if (idx >= int64_t(cols) * kq) return;
   const int col = int(idx / kq), k = int(idx % kq) * 4;
   float x[4] = {0.f, 0.f, 0.f, 0.f};
   if (col < H) {
@@ -648,33 +700,16 @@ pack_soa_sb_kernel(const float* __restrict__ soa, int F, int64_t ld, char* __res
 inline int64_t pad_rows(int64_t n) { return (n + kPanelRows - 1) / kPanelRows * kPanelRows; }
 inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 
-// launch the layer kernel with the largest allowed cluster size dividing the number of panels
+// persistent launch: one CTA per SM (or per item if there are fewer items)
 template <int KIND>
-cudaError_t launch_layer_k(const LayerArgs2& a2, dim3 grid, cudaStream_t st) {
-  static int max_csz = 0;
-  if (!max_csz) {   // KBS_TC_CLUSTER = 1 | 2 | 4 | 8 caps the cluster size (tuning / A-B profiling)
-    const char* e = getenv("KBS_TC_CLUSTER");
-    // default 1: the fill rate is bound by the per-SM inbound port, which multicast does not relieve (measured:
-    // cluster 2/4 = no gain, 8 = slower because 8 CTAs advance in lock-step); kept as an option for larger grids
-    max_csz = e ? atoi(e) : 1;
-    if (max_csz != 1 && max_csz != 2 && max_csz != 4 && max_csz != 8) max_csz = 1;
-  }
-  int csz = max_csz;
-  while (grid.x % csz) csz >>= 1;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(kThreadsTC);
-  cfg.dynamicSmemBytes = kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, lstm_layer_tc_kernel<KIND>, a2);
+cudaError_t launch_layer_k(const LayerArgs2& a2, int num_sms, cudaStream_t st) {
+  const int items = a2.net[0].panels * a2.net[0].tiles + a2.net[1].panels * a2.net[1].tiles;
+  const int grid = items < num_sms ? items : num_sms;
+  lstm_layer_tc_kernel<KIND><<<grid, kThreadsTC, kSmemBytes, st>>>(a2);
+  return cudaPeekAtLastError();
 }
-inline cudaError_t launch_layer(int kind, const LayerArgs2& a2, dim3 grid, cudaStream_t st) {
-  return kind == KBS_KIND_TF32 ? launch_layer_k<KBS_KIND_TF32>(a2, grid, st) : launch_layer_k<KBS_KIND_F16>(a2, grid, st);
+inline cudaError_t launch_layer(const kbs_handle* h, int kind, const LayerArgs2& a2, cudaStream_t st) {
+  return kind == KBS_KIND_TF32 ? launch_layer_k<KBS_KIND_TF32>(a2, h->num_sms, st) : launch_layer_k<KBS_KIND_F16>(a2, h->num_sms, st);
 }
 
 }  // namespace
@@ -689,8 +724,9 @@ static size_t layer_image_bytes(const kbs_handle* h) {
   const int H = h->p.hidden_size;
   return kbs_sb_bytes_kind(tc_kind(h), 4 * H, 2 * H) + size_t(4 * H) * 4;
 }
+static inline int proj_cols(const kbs_handle* h) { return round_up_i(h->p.hidden_size, kTileCols); }
 static size_t proj_image_bytes(const kbs_handle* h, int net) {
-  return kbs_sb_bytes_kind(tc_kind(h), kTileCols, proj_kp(h, net)) + size_t(kTileCols) * 4;
+  return kbs_sb_bytes_kind(tc_kind(h), proj_cols(h), proj_kp(h, net)) + size_t(proj_cols(h)) * 4;
 }
 static inline char* layer_w(const kbs_handle* h, int net, int l) {
   return reinterpret_cast<char*>(h->net[net].tc_image) + layer_image_bytes(h) * l;
@@ -701,7 +737,7 @@ static inline float* layer_bias(const kbs_handle* h, int net, int l) {
 }
 static inline char* proj_w(const kbs_handle* h, int net) { return layer_w(h, net, h->p.depth); }
 static inline float* proj_bias(const kbs_handle* h, int net) {
-  return reinterpret_cast<float*>(proj_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), kTileCols, proj_kp(h, net)));
+  return reinterpret_cast<float*>(proj_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), proj_cols(h), proj_kp(h, net)));
 }
 
 int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
@@ -730,14 +766,15 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
   }
   {
     const int Kp = proj_kp(h, net);
-    const int64_t total = int64_t(kTileCols) * (Kp / 4);
+    const int cols = proj_cols(h);
+    const int64_t total = int64_t(cols) * (Kp / 4);
     const unsigned gb = unsigned((total + 255) / 256);
     if (kind == KBS_KIND_TF32)
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(
-                                        N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp)));
+                                        N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp, cols)));
     else
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
-                                        N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp)));
+                                        N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp, cols)));
   }
   KBS_LAUNCH_CHECK();
   return KBS_OK;
@@ -769,11 +806,18 @@ static int fb_convert(kbs_handle* h, float* rm, float* fb, int64_t n, int64_t np
   return KBS_OK;
 }
 
+static int epi_debug() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KBS_TC_EPI_DEBUG"); v = e ? atoi(e) : 0; }
+  return v;
+}
 static void fill_lstm_args(const kbs_handle* h, int net, int l, LayerArgs& a) {
+  a.dbg = epi_debug();
   const int H = h->p.hidden_size, kb = H / kbs_block_k(tc_kind(h));
   a.w_sb = layer_w(h, net, l);
   a.bias_t = layer_bias(h, net, l);
   a.H = H; a.kb_x = kb; a.kb_h = kb; a.mode = MODE_LSTM;
+  a.tiles = H / kUnitsPerTile;
 }
 
 // Runs depth LSTM layers on the tensor cores.  x_rm: [n][H] row-major layer-0 input (input_proj output);
@@ -811,8 +855,8 @@ int kbs_tc_lstm_stack(kbs_handle* h, int net, const float* x_rm, float* carry, c
     a.h_next_rm = (l + 1 < depth) ? nullptr : out_h_rm;
     a.done = done;
     a.n = n;
-    dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile));
-    KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(tc_kind(h), a2, grid, st)));
+    a.panels = int(np / kPanelRows);
+    KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(h, tc_kind(h), a2, st)));
   }
   for (int l = 0; l < depth; ++l) {   // FB state -> ABI carry
     fb_convert(h, carry + (size_t(l) * 2 + 1) * size_t(n) * H, fb + fbf * (2 * l), n, np, H, 0, st);
@@ -841,8 +885,8 @@ int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, con
   a.raw = gates_out;
   a.mode = MODE_RAW;
   a.n = n;
-  dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile));
-  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(tc_kind(h), a2, grid, st)));
+  a.panels = int(np / kPanelRows);
+  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(h, tc_kind(h), a2, st)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -885,9 +929,9 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
     a.x_next_sb = reinterpret_cast<char*>(x_sb_all[k]);
     a.n = T * np;                    // every staged row is written (pad rows carry the bias: harmless, never read back)
     a.H = H; a.kb_x = Kp / kbs_block_k(kind); a.kb_h = 0; a.mode = MODE_PROJ;
+    a.panels = int(T * np / kPanelRows); a.tiles = proj_cols(h) / kTileCols;
   }
-  dim3 grid(unsigned(T * np / kPanelRows), 1, unsigned(nets));
-  KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (launch_layer(kind, a2, grid, st)));
+  KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (launch_layer(h, kind, a2, st)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -918,7 +962,6 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
       fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 1, st);
     }
   }
-  dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile), unsigned(nets));
   // The head of step t (out-projection, sampling, log-prob, torque, value) feeds nothing back into the recurrence, so
   // it runs on the handle's side stream, forked from and joined back into the caller's stream with events, while the
   // LSTM launches of step t+1 proceed: it lands on the SMs the 256-CTA LSTM grid leaves idle in its second wave.
@@ -943,9 +986,10 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
         a.h_next_rm = (l + 1 < depth) ? nullptr : h2rm[k] + size_t(pin) * n * H;
         a.done = done_t;
         a.n = n;
+        a.panels = int(np / kPanelRows);
         if (h->trace_buf && t == h->trace_step && l == h->trace_layer) a.trace = h->trace_buf;
       }
-      KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(kind, a2, grid, st)));
+      KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(h, kind, a2, st)));
     }
     KBS_CUDA_TRY(cudaEventRecord(h->ev_lstm[pin], st));
     KBS_CUDA_TRY(cudaStreamWaitEvent(side, h->ev_lstm[pin], 0));
@@ -1004,9 +1048,9 @@ int kbs_tc_debug_trace(kbs_handle* h, long long* trace_out, float* ws, int64_t n
     a.x_sb = wsb; a.h_sb_in = wsb + sbb; a.h_sb_out = wsb + 2 * sbb; a.x_next_sb = wsb + 3 * sbb;
     a.c = rm; a.h_carry = rm + size_t(np) * H; a.h_next_rm = nullptr; a.done = nullptr; a.n = n;
     a.trace = trace_out;
+    a.panels = int(np / kPanelRows);
   }
-  dim3 grid(unsigned(np / kPanelRows), unsigned(H / kUnitsPerTile), 2);
-  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(tc_kind(h), a2, grid, st)));
+  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(h, tc_kind(h), a2, st)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

@@ -23,21 +23,26 @@ for name, path in (("tf32", L.GEMM_TC_3XTF32), ("f16", L.GEMM_TC_2XF16)):
           "log_prob": torch.zeros((T, N), **f32), "ctrl": torch.zeros((T, 20, N), **f32), "term_codes": None,
           "done": torch.zeros((T, N), device=dev, dtype=torch.uint8), "success": torch.zeros((T, N), device=dev, dtype=torch.uint8),
           "value": torch.zeros((T, N), **f32), "T": T}
-    ctas = (N // 128) * 4 * 2
+    ctas = 148
     for layer in (0, 1):
-        tr = torch.zeros((ctas, 8), dtype=torch.int64, device=dev)
+        tr = torch.zeros((ctas * 8 + 256,), dtype=torch.int64, device=dev)
         e.lib.kbs_debug_tc_trace_attach(e._h, tr.data_ptr(), 10, layer)
         for rep in range(3):
             e.rollout(io, N)
         torch.cuda.synchronize()
-        t = tr.cpu().numpy().astype(np.float64)
+        full_t = tr.cpu().numpy().astype(np.float64); t = full_t[:ctas * 8].reshape(ctas, 8); t2 = full_t[ctas * 8:].reshape(4, 64)
         dd = {"setup": t[:, 1] - t[:, 0], "first stage wait": t[:, 2] - t[:, 1], "K loop (issue)": t[:, 3] - t[:, 2],
               "MMA drain->epi start": t[:, 4] - t[:, 3], "epilogue (warp 5)": t[:, 7] - t[:, 4], "total": t[:, 5] - t[:, 0]}
         print(f"--- {name} layer {layer} in rollout: n={N} ctas={ctas} (cycles, median / p90 / max)")
         for k, v in dd.items():
             print(f"   {k:22s} {np.median(v):9.0f} {np.percentile(v, 90):9.0f} {v.max():9.0f}")
+        if layer == 1:
+            base = t2[2, 0]
+            print("   CTA 0 per-stage stamps relative to first full (prod_empty_ok, prod_issued, mma_full_ok, mma_issued):")
+            for g in range(0, 40):
+                print(f"     g={g:2d}  {t2[0,g]-base:8.0f} {t2[1,g]-base:8.0f} {t2[2,g]-base:8.0f} {t2[3,g]-base:8.0f}")
         sm = t[:, 6].astype(int)
         span = (t[:, 5].max() - t[:, 0].min())
-        print(f"   CTAs/SM max {np.bincount(sm).max()}, SMs used {len(np.unique(sm))}; first start -> last end on one SM clock domain ~ {span:.0f} cycles (clocks differ per SM)")
+        print(f"   persistent CTAs: {len(np.unique(sm))} SMs; stamps 2-4,7 are for each CTA's FIRST item; total = whole CTA lifetime")
     e.lib.kbs_debug_tc_trace_attach(e._h, None, -1, 0)
     e.close()
