@@ -301,8 +301,10 @@ def run_b200(a):
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_cpu0 = time.perf_counter()
     for _ in range(a.steps):
         run_step()
+    cpu_enqueue_ms = 1e3 * (time.perf_counter() - t_cpu0) / a.steps      # host time to enqueue one step (no sync inside)
     e1.record()
     barrier()
     ck = clocks.finish()
@@ -371,7 +373,8 @@ def run_b200(a):
                           "tf32": "f32 (tcgen05 3xTF32 GEMMs, fp32 accumulate)", "simt": "f32"}[a.gemm],
                 "data": "synthetic", "config": config_dict(a, world), "clocks": ck, "gpu_launches": launches,
                 "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernel_breakdown_ms": breakdown,
-                "profile_overflow": overflow, "gemm_path": a.gemm, "launch_mode": launch_mode}
+                "profile_overflow": overflow, "gemm_path": a.gemm, "launch_mode": launch_mode,
+                "cpu_enqueue_ms_per_step": cpu_enqueue_ms}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -2,6 +2,7 @@
 // management and stage orchestration.  No CPU fallback: every entry point enqueues sm_100a kernels or fails.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -91,14 +92,25 @@ constexpr int kOutLd = 64;  // row stride of the trunk output buffer
 int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStream_t st) {
   const int64_t ld = io->state.ld, T = io->T;
   const bool critic = io->value != nullptr;
+  // Observation assembly + input projections can run in chunks of CT steps on the handle's aux stream while the
+  // recurrence of the previous chunk runs on the caller's stream (KBS_ROLLOUT_CHUNKS = 2..8).  MEASURED: slower
+  // (9.97 vs 8.89 ms per 100-step rollout): the persistent recurrence kernel wants every SM to itself, so the
+  // concurrent kernels delay its CTAs more than they hide.  Default = 1 chunk: phase A first, then the recurrence.
+  static int chunks_cfg = 0;
+  if (!chunks_cfg) {
+    const char* e = getenv("KBS_ROLLOUT_CHUNKS");
+    chunks_cfg = e ? atoi(e) : 1;
+    if (chunks_cfg < 1 || chunks_cfg > kKbsMaxChunks) chunks_cfg = 1;
+  }
+  const int64_t CT = (T + chunks_cfg - 1) / chunks_cfg;
   const size_t sbf = size_t(kbs_tc_sb_floats(h, n));
   const size_t ws_f = kbs_tc_rollout_ws_floats(h, n);
   const size_t lag_f = io->pg_carry ? size_t(T) * 3 * ld : 0;
   const size_t aobs_f = io->actor_obs ? 0 : size_t(T) * KBS_ACTOR_OBS * ld;
-  const size_t cobs_f = critic ? size_t(T) * KBS_CRITIC_OBS * ld : 0;
+  const size_t cobs_f = critic ? size_t(CT) * KBS_CRITIC_OBS * ld : 0;
   const size_t xsb_f = size_t(T) * sbf;
-  const size_t osb_a_f = size_t(kbs_tc_obs_sb_floats(h, KBS_NET_ACTOR, n, T));
-  const size_t osb_c_f = critic ? size_t(kbs_tc_obs_sb_floats(h, KBS_NET_CRITIC, n, T)) : 0;
+  const size_t osb_a_f = size_t(kbs_tc_obs_sb_floats(h, KBS_NET_ACTOR, n, CT));
+  const size_t osb_c_f = critic ? size_t(kbs_tc_obs_sb_floats(h, KBS_NET_CRITIC, n, CT)) : 0;
   int rc = kbs_scratch_reserve(h, ws_f + lag_f + aobs_f + cobs_f + xsb_f * (critic ? 2 : 1) + osb_a_f + osb_c_f + 64);
   if (rc) return rc;
   float* ws = h->scratch;
@@ -117,17 +129,31 @@ int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStr
   if (lagged &&
       (rc = kbs_launch_pg_scan(h, io->state.sensordata, io->episode.pg_lag, io->done, io->pg_carry, lagged, T, ld, n, st)))
     return rc;
-  if ((rc = kbs_launch_observations(h, io->state, &io->noise, &io->episode, io->command, nullptr, nullptr, nullptr, aobs,
-                                    cobs, n, st, T, lagged)))
-    return rc;
-  {
-    const float* obs_soa[2] = {aobs, cobs};
+  if ((rc = kbs_side_stream_init(h))) return rc;
+  const bool overlap = chunks_cfg > 1;
+  cudaStream_t aux = overlap ? h->aux_stream : st;
+  if (overlap) {
+    KBS_CUDA_TRY(cudaEventRecord(h->ev_pre, st));           // scans done; previous call's readers of the staging buffers too
+    KBS_CUDA_TRY(cudaStreamWaitEvent(aux, h->ev_pre, 0));
+  }
+  int n_chunks = 0;
+  for (int64_t t0 = 0; t0 < T; t0 += CT, ++n_chunks) {
+    const int64_t tc = (T - t0 < CT) ? T - t0 : CT;
+    const kbs_state_view s = state_at(io->state, t0);
+    const kbs_noise_view nz = noise_at(io->noise, t0, ld);
+    float* aobs_c = aobs + t0 * KBS_ACTOR_OBS * ld;
+    if ((rc = kbs_launch_observations(h, s, &nz, &io->episode, io->command + t0 * KBS_NUM_COMMANDS * ld, nullptr, nullptr,
+                                      nullptr, aobs_c, cobs, n, aux, tc, lagged ? lagged + t0 * 3 * ld : nullptr)))
+      return rc;
+    const float* obs_soa[2] = {aobs_c, cobs};
     float* obs_sb[2] = {osb_a, osb_c};
-    float* xsb[2] = {xsb_a, xsb_c};
-    if ((rc = kbs_tc_input_proj_all(h, critic ? 2 : 1, obs_soa, obs_sb, xsb, ld, n, T, st))) return rc;
+    float* xsb[2] = {xsb_a + size_t(t0) * sbf, critic ? xsb_c + size_t(t0) * sbf : nullptr};
+    if ((rc = kbs_tc_input_proj_all(h, critic ? 2 : 1, obs_soa, obs_sb, xsb, ld, n, tc, aux))) return rc;
+    if (overlap) KBS_CUDA_TRY(cudaEventRecord(h->ev_chunk[n_chunks], aux));
   }
 
   KbsTcRolloutArgs r{};
+  r.chunk_len = overlap ? CT : 0; r.chunk_events = h->ev_chunk;
   r.n = n; r.ld = ld; r.T = T; r.with_critic = critic;
   r.x_sb_all[0] = xsb_a; r.x_sb_all[1] = xsb_c;
   r.carry[0] = io->actor_carry; r.carry[1] = io->critic_carry;
@@ -143,6 +169,9 @@ int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStr
 int kbs_side_stream_init(kbs_handle* h) {
   if (h->side_stream) return 0;
   KBS_CUDA_TRY(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+  KBS_CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+  KBS_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+  for (int i = 0; i < kKbsMaxChunks; ++i) KBS_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     KBS_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_lstm[i], cudaEventDisableTiming));
     KBS_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_head[i], cudaEventDisableTiming));
@@ -254,6 +283,9 @@ int kbs_destroy(kbs_handle* h) {
   cudaFree(h->scratch);
   if (h->side_stream) {
     cudaStreamDestroy(h->side_stream);
+    cudaStreamDestroy(h->aux_stream);
+    cudaEventDestroy(h->ev_pre);
+    for (int i = 0; i < kKbsMaxChunks; ++i) cudaEventDestroy(h->ev_chunk[i]);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_lstm[i]); cudaEventDestroy(h->ev_head[i]); }
   }
   if (h->prof_ev) {

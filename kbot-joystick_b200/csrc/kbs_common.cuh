@@ -47,6 +47,7 @@ enum KbsKernelId {
   KBS_K_PACK, KBS_K_LSTM_TC, KBS_K_PROJ_TC, KBS_K_COUNT
 };
 constexpr int kKbsProfMaxPairs = 8192;
+constexpr int kKbsMaxChunks = 8;
 
 struct kbs_handle {
   kbs_params p;
@@ -65,6 +66,8 @@ struct kbs_handle {
   // debug: per-CTA phase stamps of one LSTM launch inside kbs_rollout (kbs_debug_tc_trace_attach)
   // side stream of the fused rollout (heads overlap the next step's LSTM launches); forked/joined with events
   cudaStream_t side_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;          // chunked observation / input-projection phase of the fused rollout
+  cudaEvent_t ev_pre = nullptr, ev_chunk[8] = {};
   cudaEvent_t ev_lstm[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr};
   long long* trace_buf = nullptr;
   int64_t trace_step = -1;
@@ -150,6 +153,8 @@ struct KbsTcRolloutArgs {
   float* entropy;             // [T][ld] or nullptr
   float* action_std;          // [T][20][ld] or nullptr
   float* ws;                  // kbs_tc_rollout_ws_floats
+  int64_t chunk_len;          // > 0: before step t with t % chunk_len == 0, wait for chunk_events[t / chunk_len]
+  cudaEvent_t* chunk_events;  //      (the input projections of that chunk of steps, produced on another stream)
 };
 size_t kbs_tc_rollout_ws_floats(const kbs_handle* h, int64_t n);
 int64_t kbs_tc_sb_floats(const kbs_handle* h, int64_t n);

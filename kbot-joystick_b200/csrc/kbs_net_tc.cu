@@ -215,6 +215,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
   // CTA 0 only: per-stage stamps of the first 64 stages: [0] producer saw empty, [1] producer issued, [2] MMA saw full,
   // [3] MMA issued + committed
   long long* tr2 = (args.net[0].trace && blockIdx.x == 0) ? args.net[0].trace + size_t(gridDim.x) * 8 : nullptr;
+  long long* tr3 = args.net[0].trace ? args.net[0].trace + size_t(gridDim.x) * 8 + 256 + 2 * blockIdx.x : nullptr;   // globaltimer ns
+  if (tr3 && threadIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); tr3[0] = (long long)gt; }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kIssuers); }
@@ -433,6 +435,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   if (tr && threadIdx.x == 0) { tr[5] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); tr[6] = sm; }
+  if (tr3 && threadIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); tr3[1] = (long long)gt; }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
@@ -970,6 +973,7 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
   for (int64_t t = 0; t < r.T; ++t) {
     const int pin = int(t & 1), pout = pin ^ 1;
     const uint8_t* done_t = r.done ? r.done + t * ld : nullptr;
+    if (r.chunk_len > 0 && t % r.chunk_len == 0) KBS_CUDA_TRY(cudaStreamWaitEvent(st, r.chunk_events[t / r.chunk_len], 0));
     // top layer of step t overwrites h2rm[pin], last read by the head of step t-2
     if (t >= 2) KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[pin], 0));
     for (int l = 0; l < depth; ++l) {
@@ -1012,6 +1016,9 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     ha.entropy = r.entropy ? r.entropy + size_t(t) * ld : nullptr;
     ha.std = r.action_std ? r.action_std + size_t(t) * KBS_NUM_JOINTS * ld : nullptr;
     ha.n = n; ha.ld = ld; ha.H = H;
+    static int skip_head = -1;
+    if (skip_head < 0) { const char* e = getenv("KBS_SKIP_HEAD"); skip_head = e ? atoi(e) : 0; }   // profiling only
+    if (!skip_head)
     KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, side,
                (rollout_head_kernel<<<dim3(unsigned((n + kHeadEnvs - 1) / kHeadEnvs), unsigned(nets)), 128, head_smem, side>>>(
                    h->p, ha)));

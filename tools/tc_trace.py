@@ -25,18 +25,21 @@ for name, path in (("tf32", L.GEMM_TC_3XTF32), ("f16", L.GEMM_TC_2XF16)):
           "value": torch.zeros((T, N), **f32), "T": T}
     ctas = 148
     for layer in (0, 1):
-        tr = torch.zeros((ctas * 8 + 256,), dtype=torch.int64, device=dev)
+        tr = torch.zeros((ctas * 8 + 256 + 2 * ctas,), dtype=torch.int64, device=dev)
         e.lib.kbs_debug_tc_trace_attach(e._h, tr.data_ptr(), 10, layer)
         for rep in range(3):
             e.rollout(io, N)
         torch.cuda.synchronize()
-        full_t = tr.cpu().numpy().astype(np.float64); t = full_t[:ctas * 8].reshape(ctas, 8); t2 = full_t[ctas * 8:].reshape(4, 64)
+        full_t = tr.cpu().numpy().astype(np.float64); t = full_t[:ctas * 8].reshape(ctas, 8); t2 = full_t[ctas * 8:ctas * 8 + 256].reshape(4, 64); t3 = full_t[ctas * 8 + 256:].reshape(ctas, 2)
         dd = {"setup": t[:, 1] - t[:, 0], "first stage wait": t[:, 2] - t[:, 1], "K loop (issue)": t[:, 3] - t[:, 2],
               "MMA drain->epi start": t[:, 4] - t[:, 3], "epilogue (warp 5)": t[:, 7] - t[:, 4], "total": t[:, 5] - t[:, 0]}
         print(f"--- {name} layer {layer} in rollout: n={N} ctas={ctas} (cycles, median / p90 / max)")
         for k, v in dd.items():
             print(f"   {k:22s} {np.median(v):9.0f} {np.percentile(v, 90):9.0f} {v.max():9.0f}")
-        if layer == 1:
+        g0 = t3[:, 0].min()
+        print(f"   globaltimer (ns from first CTA start): CTA start median {np.median(t3[:,0]-g0):.0f} max {np.max(t3[:,0]-g0):.0f}; "
+              f"CTA end median {np.median(t3[:,1]-g0):.0f} max {np.max(t3[:,1]-g0):.0f}")
+        if False:
             base = t2[2, 0]
             print("   CTA 0 per-stage stamps relative to first full (prod_empty_ok, prod_issued, mma_full_ok, mma_issued):")
             for g in range(0, 40):
