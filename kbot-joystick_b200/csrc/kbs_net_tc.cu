@@ -235,6 +235,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tr && threadIdx.x == 0) tr[1] = clock64();    // setup done
+  // Programmatic dependent launch: the next launch in the stream may start its prologue on SMs this grid has left;
+  // every thread that touches memory written by the previous grid executes griddepcontrol.wait first (pdl_wait).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp >= kIssuers && warp < kIssuers + kProducers) {
     if (lane < 2) {
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
           const int s = g % kStages;
           const uint32_t cp_bytes = (a.dbg & 16) ? 16u : uint32_t(kABlockBytes);   // dbg 16: token copies (MMA-rate probe)
           if (lane == 0) {
+            if (g < kProducers) asm volatile("griddepcontrol.wait;" ::: "memory");   // activations come from the previous grid
             mbar_wait(&empty[s], ((g / kStages) & 1) ^ 1);
             if (tr2 && g < 64) tr2[g] = clock64();
             mbar_expect_tx(&full[s], 2 * cp_bytes);
@@ -338,6 +342,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
           *reinterpret_cast<float4*>(bias_s + k * kMaxBias + i) = *reinterpret_cast<const float4*>(args.net[k].bias_t + i);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      asm volatile("griddepcontrol.wait;" ::: "memory");    // state / done / outputs belong to the previous grid until here
     }
     const int q4 = warp & 3, c2 = (warp - kIssuers - kProducers) >> 2;
     const int r = q4 * 32 + lane;
@@ -708,8 +713,17 @@ template <int KIND>
 cudaError_t launch_layer_k(const LayerArgs2& a2, int num_sms, cudaStream_t st) {
   const int items = a2.net[0].panels * a2.net[0].tiles + a2.net[1].panels * a2.net[1].tiles;
   const int grid = items < num_sms ? items : num_sms;
-  lstm_layer_tc_kernel<KIND><<<grid, kThreadsTC, kSmemBytes, st>>>(a2);
-  return cudaPeekAtLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreadsTC);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol.* in the kernel
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, lstm_layer_tc_kernel<KIND>, a2);
 }
 inline cudaError_t launch_layer(const kbs_handle* h, int kind, const LayerArgs2& a2, cudaStream_t st) {
   return kind == KBS_KIND_TF32 ? launch_layer_k<KBS_KIND_TF32>(a2, h->num_sms, st) : launch_layer_k<KBS_KIND_F16>(a2, h->num_sms, st);
