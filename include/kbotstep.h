@@ -281,6 +281,11 @@ int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n_envs, void*
 /* Number of kernel launches this library has enqueued since the handle was created (bench bookkeeping). */
 int64_t kbs_launch_count(const kbs_handle* h);
 
+/* Device-side health word of the fused rollout (kbs_rollout / kbs_ppo_variables on the tensor-core paths run all T
+ * steps as one persistent kernel whose CTAs wait on each other's progress counters; a wait that times out is recorded
+ * here instead of hanging).  Synchronises with the device.  *status_out == 0: healthy. */
+int kbs_device_status(kbs_handle* h, int* status_out);
+
 /* Per-kernel device timing for bench.py's roofline line: while enabled, every kernel launch of this handle is
  * bracketed by CUDA events on its launch stream (up to 8192 launches; do not enable during stream capture).
  * kbs_profile_read sums elapsed ms and launch counts per kernel id (ids 0..KBS_NUM_KERNEL_IDS-1, names from

@@ -92,9 +92,9 @@ EXPORTS = (
     "kbs_version", "kbs_error_string", "kbs_default_params", "kbs_create", "kbs_destroy", "kbs_get_params",
     "kbs_weights_pack", "kbs_observations", "kbs_command_update", "kbs_actor_step", "kbs_critic_step",
     "kbs_torque", "kbs_terminate", "kbs_rewards", "kbs_gae", "kbs_policy_step", "kbs_rollout", "kbs_ppo_variables",
-    "kbs_launch_count", "kbs_profile_enable", "kbs_profile_read", "kbs_kernel_name", "kbs_debug_tc_gates", "kbs_debug_tc_trace", "kbs_debug_tc_trace_attach",
+    "kbs_launch_count", "kbs_device_status", "kbs_profile_enable", "kbs_profile_read", "kbs_kernel_name", "kbs_debug_tc_gates", "kbs_debug_tc_trace", "kbs_debug_tc_trace_attach",
 )
-NUM_KERNEL_IDS = 17
+NUM_KERNEL_IDS = 18
 
 _lib = None
 
@@ -132,6 +132,7 @@ def load() -> C.CDLL:
     lib.kbs_ppo_variables.argtypes = [_vp, P(KbsPpoIO), _i64, _vp]
     lib.kbs_launch_count.argtypes = [_vp]
     lib.kbs_launch_count.restype = _i64
+    lib.kbs_device_status.argtypes = [_vp, P(C.c_int)]
     lib.kbs_profile_enable.argtypes = [_vp, C.c_int]
     lib.kbs_profile_read.argtypes = [_vp, C.c_int, P(C.c_double), P(_i64)]
     lib.kbs_debug_tc_gates.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _i64, _vp]

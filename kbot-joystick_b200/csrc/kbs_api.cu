@@ -281,6 +281,7 @@ int kbs_destroy(kbs_handle* h) {
     for (int l = 0; l < KBS_MAX_DEPTH; ++l) { cudaFree(N.w_ih[l]); cudaFree(N.w_hh[l]); cudaFree(N.b[l]); }
   }
   cudaFree(h->scratch);
+  cudaFree(h->persist_status);
   if (h->side_stream) {
     cudaStreamDestroy(h->side_stream);
     cudaStreamDestroy(h->aux_stream);
@@ -303,6 +304,16 @@ int kbs_get_params(const kbs_handle* h, kbs_params* out) {
 }
 
 int64_t kbs_launch_count(const kbs_handle* h) { return h ? h->launches : -1; }
+
+int kbs_device_status(kbs_handle* h, int* status_out) {
+  REQ(h); REQ(status_out);
+  *status_out = 0;
+  if (!h->persist_status) return KBS_OK;
+  unsigned int v = 0;
+  KBS_CUDA_TRY(cudaMemcpy(&v, h->persist_status, 4, cudaMemcpyDeviceToHost));   // synchronises with the device
+  *status_out = int(v);
+  return KBS_OK;
+}
 
 int kbs_debug_tc_trace_attach(kbs_handle* h, long long* trace_out, int64_t step, int layer) {
   REQ(h);
@@ -358,7 +369,7 @@ const char* kbs_kernel_name(int id) {
       "obs_kernel", "command_kernel", "torque_kernel", "terminate_kernel", "reward_rot_kernel", "reward_terms_kernel",
       "reward_scan_kernel", "gae_kernel", "adv_norm_kernel", "policy_io_kernels", "gemm_nt_kernel(simt)",
       "lstm_cell_kernel", "actor_head_kernel", "critic_head_kernel", "pack_kernels", "lstm_layer_tc_kernel",
-      "proj_tc_kernel"};
+      "proj_tc_kernel", "rollout_persist_kernel"};
   return (id >= 0 && id < KBS_K_COUNT) ? names[id] : "?";
 }
 

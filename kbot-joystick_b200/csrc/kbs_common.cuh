@@ -44,7 +44,7 @@ struct KbsNet {
 enum KbsKernelId {
   KBS_K_OBS = 0, KBS_K_COMMAND, KBS_K_TORQUE, KBS_K_TERMINATE, KBS_K_REWARD_ROT, KBS_K_REWARD_TERMS, KBS_K_REWARD_SCAN,
   KBS_K_GAE, KBS_K_ADV_NORM, KBS_K_POLICY_IO, KBS_K_GEMM_SIMT, KBS_K_LSTM_CELL, KBS_K_ACTOR_HEAD, KBS_K_CRITIC_HEAD,
-  KBS_K_PACK, KBS_K_LSTM_TC, KBS_K_PROJ_TC, KBS_K_COUNT
+  KBS_K_PACK, KBS_K_LSTM_TC, KBS_K_PROJ_TC, KBS_K_ROLLOUT_TC, KBS_K_COUNT
 };
 constexpr int kKbsProfMaxPairs = 8192;
 constexpr int kKbsMaxChunks = 8;
@@ -69,6 +69,7 @@ struct kbs_handle {
   cudaStream_t aux_stream = nullptr;          // chunked observation / input-projection phase of the fused rollout
   cudaEvent_t ev_pre = nullptr, ev_chunk[8] = {};
   cudaEvent_t ev_lstm[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr};
+  unsigned int* persist_status = nullptr;     // device word set by rollout_persist_kernel when a dependency wait times out
   long long* trace_buf = nullptr;
   int64_t trace_step = -1;
   int trace_layer = 0;

@@ -133,6 +133,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -602,6 +610,487 @@ rollout_head_kernel(const __grid_constant__ kbs_params P, const __grid_constant_
   }
 }
 
+// ---- persistent recurrence kernel: ALL T control steps of the rollout in ONE launch --------------------------------------
+// One CTA per SM walks a static, globally ordered list of work items; there is no kernel boundary between steps or
+// layers.  Item kinds: LSTM (net, layer l, step t, 128-env panel, 128-column gate tile) -- the same datapath as
+// lstm_layer_tc_kernel -- and HEAD (net, step t, panel): out = W_out h_top on the tensor core (W_out zero-padded to one
+// 128-column tile), then in the epilogue the whole actor head for the row's env (std / mean / low-pass / sample /
+// log-prob / entropy / PD torque, train.py:922-939, 1091-1105, 1564) or the critic value (train.py:1002).
+// Order: "slot" s holds layer l at step s - l and the head at step s - depth (a wavefront: everything in a slot depends
+// only on earlier slots), items of a slot are panel-major so the ~17 CTAs that share a panel's activations run together.
+// Dependencies between CTAs travel through monotone completion counters in global memory, one per (net, layer | head,
+// panel): every epilogue warp adds 1 after its stores (fence + red), so "layer l of step t is complete for panel p" is
+// counter >= (t + 1) * tiles * kEpiWarps.  The producer lane polls the (at most three) counters an item needs before
+// its first bulk copy, then publishes the item's sequence number in shared memory for the epilogue warps (which read
+// the cell state with L2-coherent loads).  All CTAs are co-resident (cooperative launch, grid <= SM count) and every
+// CTA takes its items in the global order, so the earliest unfinished item can always run: no deadlock.  Polling is
+// bounded: after ~2^22 polls a CTA records an error in `status` and stops waiting.
+constexpr int kPMaxDepth = 2;            // bias table in shared memory: [2 nets][kPMaxDepth][4H] + head [2][128]
+constexpr int kPBiasFloats = 2 * kPMaxDepth * kMaxBias + 2 * kTileCols;
+constexpr int kEpiWarpsP = 16;
+constexpr int kThreadsP = 32 * (kIssuers + kProducers + kEpiWarpsP + 2);   // + dependency poller warp + publisher warp
+constexpr int kPHeadPartFloats = 4 * kPanelRows * 2;
+constexpr int kPSmemBytes = kStages * kStageBytes + (kPBiasFloats + kPHeadPartFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
+
+struct PNet {
+  const char* x_sb_all;            // [T] x sbb: layer-0 inputs (input projection of every step)
+  char* hsb;                       // [depth][2] x sbb: recurrent SB state (reset where done); step t reads parity t & 1
+  char* xmid;                      // [depth][2] x sbb: un-reset SB output of layer l at step t (parity t & 1)
+  float* fb;                       // [depth][c, h] x np*H: fp32 FB state
+  const char* w_sb[kPMaxDepth];
+  const float* bias_t[kPMaxDepth];
+  const char* w_head;              // [128][H] SB, rows >= num_out zero
+  const float* bias_head;          // [128]
+  unsigned int* flags;             // [depth + 1][panels] completion counters (zeroed before the launch)
+};
+struct PArgs {
+  PNet net[2];
+  int nets, depth, H, panels, tiles;
+  int64_t n, ld, T;
+  size_t sbb;
+  const uint8_t* done;             // [T][ld] or nullptr
+  // head I/O (time-major SoA, env contiguous); see HeadArgs
+  const float* arm_cmd;            // actor_obs + 55 * ld, stride KBS_ACTOR_OBS * ld per step
+  float* lpf;
+  const float* eps;                // stride 20 * ld
+  const float* q; const float* qd; // qpos + 7 * ld (stride KBS_NQ * ld), qvel + 6 * ld (stride KBS_NV * ld)
+  kbs_episode_view ep;
+  float* action; float* log_prob; float* ctrl; float* value;
+  const float* action_in; float* entropy; float* std;
+  int dbg;                         // profiling only (KBS_PERSIST_DBG): 1 = ignore dependencies (wrong results, timing probe)
+  unsigned int* status;            // != 0: a dependency wait timed out (bug / lost CTA)
+  long long* trace;                // per CTA [8]: total cycles, poller wait cycles, items, issuer wait-for-stage cycles,
+                                   // epilogue cycles in LSTM / head items, epilogue wait-for-accumulator, issuer wait-for-TMEM
+};
+
+struct PItem { int kind, net, layer, panel, tile; int t; bool valid; };
+__device__ __forceinline__ PItem p_decode(const PArgs& a, int g) {
+  const int lt = a.depth * a.tiles, per_panel = lt + 1, per_net = a.panels * per_panel, C = a.nets * per_net;
+  const int s = g / C;
+  int i = g - s * C;
+  PItem it;
+  it.net = i / per_net; i -= it.net * per_net;
+  it.panel = i / per_panel;
+  const int q = i - it.panel * per_panel;
+  if (q < lt) { it.kind = 0; it.layer = q / a.tiles; it.tile = q - it.layer * a.tiles; it.t = s - it.layer; }
+  else { it.kind = 1; it.layer = a.depth; it.tile = 0; it.t = s - a.depth; }
+  it.valid = it.t >= 0 && it.t < int(a.T);
+  return it;
+}
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Blocks until the counters item `it` depends on have reached their targets; returns cycles spent.
+__device__ __forceinline__ long long p_wait_deps(const PArgs& a, const PItem& it) {
+  const PNet& N = a.net[it.net];
+  const unsigned int full_l = unsigned(a.tiles * kEpiWarpsP), full_h = unsigned(kEpiWarpsP);
+  const unsigned int* fp[3]; unsigned int tg[3]; int nd = 0;
+  const unsigned int t = unsigned(it.t);
+  if (it.kind == 0) {
+    const int l = it.layer;
+    if (t >= 1) { fp[nd] = N.flags + l * a.panels + it.panel; tg[nd++] = t * full_l; }              // h_{t-1}, c_{t-1}
+    if (l >= 1) { fp[nd] = N.flags + (l - 1) * a.panels + it.panel; tg[nd++] = (t + 1) * full_l; }  // x_t from layer l-1
+    if (t >= 2) {   // xmid[l][t & 1] was last read by the consumer of this layer's output at step t - 2
+      fp[nd] = N.flags + (l + 1) * a.panels + it.panel;
+      tg[nd++] = (t - 1) * (l + 1 == a.depth ? full_h : full_l);
+    }
+  } else {
+    fp[nd] = N.flags + (a.depth - 1) * a.panels + it.panel; tg[nd++] = (t + 1) * full_l;            // h_top of step t
+    if (t >= 1) { fp[nd] = N.flags + a.depth * a.panels + it.panel; tg[nd++] = t * full_h; }       // lpf of step t-1
+  }
+  if (nd == 0) return 0;
+  for (int i = nd; i < 3; ++i) { fp[i] = fp[0]; tg[i] = 0u; }   // fixed three independent loads per poll
+  const long long c0 = clock64();
+  unsigned int polls = 0;
+  while (true) {
+    const unsigned int v0 = ld_volatile_u32(fp[0]), v1 = ld_volatile_u32(fp[1]), v2 = ld_volatile_u32(fp[2]);
+    if (v0 >= tg[0] && v1 >= tg[1] && v2 >= tg[2]) break;
+    if (++polls > (1u << 22)) { atomicExch(a.status, 1u + unsigned(it.kind)); break; }
+  }
+  __threadfence();                                            // acquire: the counted stores are visible
+  return clock64() - c0;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreadsP, 1)
+rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_constant__ PArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);   // [net][layer][kMaxBias] then head [net][128]
+  float* bias_head_s = bias_s + 2 * kPMaxDepth * kMaxBias;
+  float* head_part = bias_s + kPBiasFloats;                                 // [4 joint groups][128 rows][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + (kPBiasFloats + kPHeadPartFloats) * 4);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* acc_full = bars + 2 * kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* corr_init = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_init + 2);
+  volatile int* dep_seq = reinterpret_cast<volatile int*>(tmem_slot + 1);   // items whose dependencies are satisfied
+  unsigned int* epi_done = reinterpret_cast<unsigned int*>(tmem_slot + 2);  // epilogue warps that have stored their share (monotone)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_slot = args.nets * args.panels * (args.depth * args.tiles + 1);
+  const int n_g = (int(args.T) + args.depth) * per_slot;
+  const int H = args.H;
+  constexpr int kBlk = kbs_block_k(KIND);
+  const int kb = H / kBlk;
+  long long* tr = args.trace ? args.trace + size_t(blockIdx.x) * 12 : nullptr;
+  const long long t_start = clock64();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kIssuers); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], kIssuers); mbar_init(&acc_empty[b], kEpiWarpsP); mbar_init(&corr_init[b], 1);
+    }
+    *dep_seq = 0;
+    *epi_done = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kIssuers + kProducers + kEpiWarpsP + 1) {
+    if (lane == 0) {
+      // ===== publisher: the gpu-scope fence that makes an item's stores visible costs ~2 K cycles of store-ack latency.
+      // The epilogue warps therefore only signal "stored" in shared memory (release.cta) and move on; this thread
+      // observes all 16 signals (acquire.cta), fences at gpu scope -- cumulative over everything it has observed, the
+      // same pattern as bar.sync + one thread's __threadfence() in a grid barrier -- and bumps the item's counter =====
+      int j = 0;
+      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+        const PItem it = p_decode(args, gi);
+        if (!it.valid) continue;
+        ++j;
+        const unsigned int want = unsigned(j) * kEpiWarpsP;
+        unsigned int seen;
+        do {
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(epi_done)) : "memory");
+        } while (seen < want);
+        __threadfence();
+        atomicAdd(args.net[it.net].flags + it.layer * args.panels + it.panel, unsigned(kEpiWarpsP));
+      }
+    }
+    __syncwarp();
+  } else if (warp == kIssuers + kProducers + kEpiWarpsP) {
+    if (lane == 0) {
+      // ===== dependency poller: runs ahead of the producers through the item list, so the L2 round trips of the
+      // counter polls and the fence stay off the load pipeline's critical path; publishes "items 0..j-1 may start" =====
+      int j = 0;
+      long long waited = 0;
+      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+        const PItem it = p_decode(args, gi);
+        if (!it.valid) continue;
+        if (!(args.dbg & 1)) waited += p_wait_deps(args, it);
+        *dep_seq = ++j;
+      }
+      if (tr) { tr[1] = waited; tr[2] = j; }
+    }
+    __syncwarp();
+  } else if (warp >= kIssuers && warp < kIssuers + kProducers) {
+    if (lane < 2) {
+      // ===== producers (see lstm_layer_tc_kernel): lane 0 = activation block, lane 1 = weight block of the stage =====
+      uint32_t g = 0;
+      int j = 0;
+      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+        const PItem it = p_decode(args, gi);
+        if (!it.valid) continue;
+        const PNet& N = args.net[it.net];
+        const int kb_x = kb, kb_total = it.kind == 0 ? 2 * kb : kb;
+        const size_t poff = size_t(it.panel) * kb * kABlockBytes;
+        const char* xa; const char* ha; const char* wb;
+        if (it.kind == 0) {
+          xa = (it.layer == 0 ? N.x_sb_all + size_t(it.t) * args.sbb
+                              : N.xmid + size_t((it.layer - 1) * 2 + (it.t & 1)) * args.sbb) + poff;
+          ha = N.hsb + size_t(it.layer * 2 + (it.t & 1)) * args.sbb + poff;
+          wb = N.w_sb[it.layer] + size_t(it.tile) * kb_total * kBBlockBytes;
+        } else {
+          xa = N.xmid + size_t((args.depth - 1) * 2 + (it.t & 1)) * args.sbb + poff;
+          ha = xa;
+          wb = N.w_head;
+        }
+        ++j;
+        if (lane == 0) {
+          while (*dep_seq < j) { }
+          __threadfence_block();
+          asm volatile("fence.proxy.async;" ::: "memory");    // the activation blocks were written with generic stores
+        }
+        for (int b = 0; b < kb_total; ++b, ++g) {
+          if (int(g % kProducers) != warp - kIssuers) continue;
+          const int s = g % kStages;
+          if (lane == 0) {
+            mbar_wait(&empty[s], ((g / kStages) & 1) ^ 1);
+            mbar_expect_tx(&full[s], 2 * kABlockBytes);
+          }
+          __syncwarp(0x3);
+          uint8_t* sa = smem + size_t(s) * kStageBytes;
+          const char* src = lane == 0 ? ((b < kb_x) ? xa + size_t(b) * kABlockBytes : ha + size_t(b - kb_x) * kABlockBytes)
+                                      : wb + size_t(b) * kBBlockBytes;
+          bulk_g2s(sa + lane * kABlockBytes, src, kABlockBytes, &full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < kIssuers) {
+    // ===== MMA issuers (see lstm_layer_tc_kernel) =====
+    uint32_t g = 0;
+    int j = 0;
+    long long waited = 0, waited_acc = 0;
+    for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+      const PItem it = p_decode(args, gi);
+      if (!it.valid) continue;
+      const int kb_total = it.kind == 0 ? 2 * kb : kb;
+      const int buf = j & 1;
+      const long long e0 = tr ? clock64() : 0;
+      mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
+      if (tr) waited_acc += clock64() - e0;
+      tc_fence_after();
+      const uint32_t d_main = tmem_base + buf * (2 * kTileCols), d_corr = d_main + kTileCols;
+      for (int b = 0; b < kb_total; ++b, ++g) {
+        const int s = g % kStages;
+        const long long w0 = tr ? clock64() : 0;
+        mbar_wait(&full[s], (g / kStages) & 1);
+        if (tr) waited += clock64() - w0;
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
+        const uint32_t sb = sa + kABlockBytes;
+        if (warp == 0) {
+          const uint64_t a0 = umma_desc(sa, 2048, 128), b0 = umma_desc(sb, 2048, 128);
+          const uint64_t a1 = umma_desc(sa + 4096, 2048, 128), b1 = umma_desc(sb + 4096, 2048, 128);
+          if (elect_one()) {
+            umma<KIND>(d_main, a0, b0, b != 0);
+            umma<KIND>(d_main, a1, b1, 1);
+            umma_commit(&empty[s]);
+          }
+        } else {
+          const int ks = warp - 1;
+          const uint64_t a_hi = umma_desc(sa + ks * 4096, 2048, 128);
+          const uint64_t a_lo = umma_desc(sa + 8192 + ks * 4096, 2048, 128);
+          const uint64_t b_hi = umma_desc(sb + ks * 4096, 2048, 128);
+          const uint64_t b_lo = umma_desc(sb + 8192 + ks * 4096, 2048, 128);
+          if (b == 0 && warp == 2) {
+            mbar_wait(&corr_init[buf], (j >> 1) & 1);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            umma<KIND>(d_corr, a_lo, b_hi, (b | ks) != 0);
+            if (b == 0 && warp == 1) { tc_fence_before(); mbar_arrive(&corr_init[buf]); }
+            umma<KIND>(d_corr, a_hi, b_lo, 1);
+            umma_commit(&empty[s]);
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
+      ++j;
+    }
+    if (tr && warp == 0 && lane == 0) { tr[3] = waited; tr[7] = waited_acc; }
+  } else {
+    // ===== epilogue: 16 warps; warp % 4 = TMEM lane quarter (rows), the other two bits = which 8 of the tile's 32 hidden
+    // units (LSTM items) or which 5 of the 20 joints (actor head items).  The cell math is latency-bound (MUFU chains),
+    // so four warps per scheduler instead of two is what shortens it (measured: 8.2 K cycles per item with 8 warps).
+    const int ew = warp - kIssuers - kProducers;
+    {
+      const int et = threadIdx.x - 32 * (kIssuers + kProducers);
+      for (int k = 0; k < args.nets; ++k) {
+        for (int l = 0; l < args.depth; ++l)
+          for (int i = et * 4; i < 4 * H; i += 32 * kEpiWarpsP * 4)
+            *reinterpret_cast<float4*>(bias_s + (k * kPMaxDepth + l) * kMaxBias + i) =
+                *reinterpret_cast<const float4*>(args.net[k].bias_t[l] + i);
+        if (et < kTileCols) bias_head_s[k * kTileCols + et] = args.net[k].bias_head[et];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarpsP) : "memory");
+    }
+    const int q4 = warp & 3, grp = ew >> 2, c2 = grp >> 1, sub = grp & 1;
+    const int r = q4 * 32 + lane;
+    constexpr float kCorr = (KIND == KBS_KIND_F16) ? (1.0f / kKbsF16LoScale) : 1.0f;
+    const int64_t ld = args.ld;
+    const int colq = c2 * 64 + sub * 8;          // this thread's 8 columns of gate g start at colq + 16 g
+    int j = 0;
+    long long epi_cyc[2] = {0, 0}, epi_wait = 0, ph[4] = {0, 0, 0, 0};
+    for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+      const PItem it = p_decode(args, gi);
+      if (!it.valid) continue;
+      const PNet& N = args.net[it.net];
+      const int buf = j & 1;
+      const int64_t R = int64_t(it.panel) * kPanelRows + r;
+      const bool live = R < args.n;
+      const int u0 = it.tile * kUnitsPerTile + c2 * 16 + sub * 8;
+      // dependencies of this item are satisfied once the poller says so (acquire through shared memory)
+      while (*dep_seq < j + 1) { }
+      __threadfence_block();
+      float* cst = N.fb + size_t(it.layer) * 2 * size_t(args.panels) * kPanelRows * H;      // c of this layer (kind 0 only)
+      float4 cpre[2];
+      if (it.kind == 0 && live) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) cpre[q] = __ldcg(reinterpret_cast<const float4*>(cst + fb_offset(R, u0 + q * 4, H)));
+      }
+      const uint8_t* done_t = args.done ? args.done + size_t(it.t) * ld : nullptr;
+      const bool rst = live && done_t && done_t[R];
+      const long long ew0 = tr ? clock64() : 0;
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      const long long ew1 = tr ? clock64() : 0;
+      tc_fence_after();
+      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * kTileCols) + colq);
+      if (it.kind == 0) {
+        float v[32];
+        {
+          float cr[32];
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) { tmem_ld8(tq + 16 * g4, v + 8 * g4); tmem_ld8(tq + kTileCols + 16 * g4, cr + 8 * g4); }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += kCorr * cr[i];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (tr) ph[0] += clock64() - ew1;
+        const float* bs = bias_s + (it.net * kPMaxDepth + it.layer) * kMaxBias + it.tile * kTileCols + colq;
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[8 * g4 + i] += bs[16 * g4 + i];
+        if (live) {
+          char* x_out = N.xmid + size_t(it.layer * 2 + (it.t & 1)) * args.sbb;
+          char* h_out = N.hsb + size_t(it.layer * 2 + ((it.t + 1) & 1)) * args.sbb;
+          float* h_carry = (it.t == int(args.T) - 1) ? cst + size_t(args.panels) * kPanelRows * H : nullptr;
+#pragma unroll
+          for (int i = 0; i < 8; i += 4) {
+            const float4 c4 = cpre[i >> 2];
+            const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+            float hn[4], cn[4];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+              const float gi_ = v[i + l], gf = v[8 + i + l], gg = v[16 + i + l], go = v[24 + i + l];
+              // c' = s(f) c + s(i) tanh(g);  h' = s(o) tanh(c')   (eqx LSTMCell)
+              cn[l] = sigmoidf_(gf) * cv[l] + sig_mul_tanh(gi_, gg);
+              hn[l] = sig_mul_tanh(go, cn[l]);
+              if (rst) cn[l] = 0.0f;
+            }
+            KbsSplit4 sp = sb_split4<KIND>(hn);               // one split serves the consumer of this layer (un-reset) ...
+            sb_store_split<kPanelRows, KIND>(x_out, R, u0 + i, kb, sp);
+            if (rst) { sp.hi = make_uint4(0u, 0u, 0u, 0u); sp.lo = sp.hi; hn[0] = hn[1] = hn[2] = hn[3] = 0.0f; }
+            sb_store_split<kPanelRows, KIND>(h_out, R, u0 + i, kb, sp);   // ... and the recurrent input (reset)
+            *reinterpret_cast<float4*>(cst + fb_offset(R, u0 + i, H)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            if (h_carry) *reinterpret_cast<float4*>(h_carry + fb_offset(R, u0 + i, H)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          }
+        }
+      } else {
+        // head item: "gate" 0 columns = mean rows, "gate" 1 columns = std rows of joints 5 grp .. 5 grp + 4 (pack_head_weights_kernel)
+        float v[16];
+        {
+          float cr[16];
+          tmem_ld8(tq, v); tmem_ld8(tq + 16, v + 8);
+          tmem_ld8(tq + kTileCols, cr); tmem_ld8(tq + kTileCols + 16, cr + 8);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += kCorr * cr[i];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        const float* bs = bias_head_s + it.net * kTileCols + colq;
+        const int64_t e = R;
+        const size_t t = size_t(it.t);
+        float s_z = 0.0f, s_log = 0.0f;
+        if (it.net == 1) {
+          if (live && grp == 0) args.value[t * ld + e] = v[0] + bs[0];
+        } else {
+          constexpr float kHalfLog2Pi = 0.918938533204672742f;
+          if (live) {
+            const int j0 = 5 * grp;
+            float in_lpf[5], in_eps[5], in_arm[5], in_ain[5], in_q[5], in_qd[5], in_kp[5], in_kd[5], in_lim[5], in_ab[5], in_tb[5];
+#pragma unroll
+            for (int jj = 0; jj < 5; ++jj) {            // every input of the 5 joints first: one L2 round trip, not five
+              const int jn = j0 + jj;
+              const int64_t o = jn * ld + e;
+              in_lpf[jj] = __ldcg(args.lpf + o);
+              in_eps[jj] = args.eps ? __ldg(args.eps + t * KBS_NUM_JOINTS * ld + o) : 0.0f;
+              in_arm[jj] = (jn >= 10) ? __ldg(args.arm_cmd + t * KBS_ACTOR_OBS * ld + (jn - 10) * ld + e) : 0.0f;
+              in_ain[jj] = args.action_in ? __ldg(args.action_in + t * KBS_NUM_JOINTS * ld + o) : 0.0f;
+              if (args.ctrl) {
+                in_q[jj] = __ldg(args.q + t * KBS_NQ * ld + o);
+                in_qd[jj] = __ldg(args.qd + t * KBS_NV * ld + o);
+                in_kp[jj] = args.ep.kp ? __ldg(args.ep.kp + o) : P.kp[jn];
+                in_kd[jj] = args.ep.kd ? __ldg(args.ep.kd + o) : P.kd[jn];
+                in_lim[jj] = args.ep.tau_limit ? __ldg(args.ep.tau_limit + o) : P.ctrl_limit[jn];
+                in_ab[jj] = args.ep.action_bias ? __ldg(args.ep.action_bias + o) : 0.0f;
+                in_tb[jj] = args.ep.torque_bias ? __ldg(args.ep.torque_bias + o) : 0.0f;
+              }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 5; ++jj) {
+              const int jn = j0 + jj;
+              const int64_t o = jn * ld + e;
+              const float sraw = v[8 + jj] + bs[16 + jj];
+              const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
+              const float sd = fminf((sp + P.min_std) * P.var_scale, P.max_std);
+              float m = (v[jj] + bs[jj]) + P.joint_bias[jn];
+              m = m + in_arm[jj];
+              const float y = in_lpf[jj];
+              const float yn = y + P.lpf_alpha * (m - y);
+              args.lpf[o] = rst ? 0.0f : yn;
+              float act = yn;
+              if (args.eps) act = yn + sd * in_eps[jj];
+              const float a_eval = args.action_in ? in_ain[jj] : act;
+              const float z = (a_eval - yn) / sd;
+              s_z = s_z + (-0.5f * z * z - kHalfLog2Pi);
+              s_log = s_log + logf(sd);
+              if (args.action) args.action[t * KBS_NUM_JOINTS * ld + o] = act;
+              if (args.std) args.std[t * KBS_NUM_JOINTS * ld + o] = sd;
+              if (args.ctrl) {                         // PositionActuators.get_ctrl (train.py:1091-1105)
+                const float target = args.ep.action_bias ? __fadd_rn(act, in_ab[jj]) : act;
+                float tau = __fsub_rn(__fmul_rn(in_kp[jj], __fsub_rn(target, in_q[jj])), __fmul_rn(in_kd[jj], in_qd[jj]));
+                if (args.ep.torque_bias) tau = __fadd_rn(tau, in_tb[jj]);
+                args.ctrl[t * KBS_NUM_JOINTS * ld + o] = fminf(fmaxf(tau, -in_lim[jj]), in_lim[jj]);
+              }
+            }
+          }
+          // log-prob / entropy: the four joint groups of a row meet in shared memory (fixed order: deterministic)
+          head_part[(grp * kPanelRows + r) * 2] = s_z;
+          head_part[(grp * kPanelRows + r) * 2 + 1] = s_log;
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + q4) : "memory");
+          if (grp == 0 && live) {
+            float z = 0.0f, l = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { z = z + head_part[(w * kPanelRows + r) * 2]; l = l + head_part[(w * kPanelRows + r) * 2 + 1]; }
+            if (args.log_prob) args.log_prob[t * ld + e] = z - l;
+            if (args.entropy) args.entropy[t * ld + e] = l + float(KBS_NUM_JOINTS) * (0.5f + kHalfLog2Pi);
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + q4) : "memory");   // head_part may be rewritten by the next head item
+        }
+      }
+      // publish: this warp's share of the item is in global memory
+      const long long ew2 = tr ? clock64() : 0;
+      __syncwarp();
+      long long ewf = 0;
+      if (lane == 0) {
+        asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(epi_done)) : "memory");
+        if (tr) ewf = clock64();
+      }
+      if (tr) { const long long ew3 = clock64(); epi_cyc[it.kind] += ew3 - ew1; epi_wait += ew1 - ew0; if (it.kind == 0) { ph[1] += ew2 - ew1; ph[2] += ew3 - ew2; ph[3] += ewf - ew2; } }
+      ++j;
+    }
+    if (tr && threadIdx.x == 32 * (kIssuers + kProducers)) { tr[4] = epi_cyc[0]; tr[5] = epi_cyc[1]; tr[6] = epi_wait; tr[8] = ph[0]; tr[9] = ph[1]; tr[10] = ph[2]; tr[11] = ph[3]; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tr && threadIdx.x == 0) tr[0] = clock64() - t_start;
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
 // ---- packing kernels ------------------------------------------------------------------------------------------------
 // eqx LSTMCell weights [4H][H] x2 + bias [4H]  ->  gate-interleaved SB tiles (hi/lo) + interleaved bias.
 // tile j (128 columns = 32 hidden units), column c = half * 64 + gate * 16 + uu  ->  unit = 32 j + 16 half + uu:
@@ -641,6 +1130,31 @@ pack_proj_weights_kernel(const float* __restrict__ w, int ldw, const float* __re
   }
   sb_store4<kTileCols, KIND>(w_sb, col, k, Kp / kbs_block_k(KIND), x);
   if (k == 0) bias_t[col] = col < H ? b[col] : 0.0f;
+}
+
+// Output head of the persistent rollout kernel: eqx Linear weight [num_out][H] -> ONE 128-column SB tile whose columns
+// follow the epilogue's thread map: column c = half * 64 + gate * 16 + sub * 8 + uu; joint group grp = 2 half + sub holds
+// joints 5 grp .. 5 grp + 4 in uu = 0..4: gate 0 = mean row (joint), gate 1 = std row (20 + joint); all else zero.
+// The critic (num_out = 1) lands in column 0.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+pack_head_weights_kernel(const float* __restrict__ w, const float* __restrict__ b, char* __restrict__ w_sb,
+                         float* __restrict__ bias_t, int H, int num_out) {
+  const int kq = H / 4;
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= int64_t(kTileCols) * kq) return;
+  const int col = int(idx / kq), k = int(idx % kq) * 4;
+  const int half = col / 64, gate = (col % 64) / 16, sub = (col % 16) / 8, uu = col % 8;
+  int row = -1;
+  if (gate < 2 && uu < 5) row = gate * KBS_NUM_JOINTS + (2 * half + sub) * 5 + uu;
+  if (row >= num_out) row = -1;
+  float x[4] = {0.f, 0.f, 0.f, 0.f};
+  if (row >= 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = w[size_t(row) * H + k + i];
+  }
+  sb_store4<kTileCols, KIND>(w_sb, col, k, H / kbs_block_k(KIND), x);
+  if (k == 0) bias_t[col] = row >= 0 ? b[row] : 0.0f;
 }
 
 // ABI row-major [n][H] <-> FB blocked state.  to_fb: rows >= n of the last panel are zero-filled.
@@ -756,6 +1270,14 @@ static inline char* proj_w(const kbs_handle* h, int net) { return layer_w(h, net
 static inline float* proj_bias(const kbs_handle* h, int net) {
   return reinterpret_cast<float*>(proj_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), proj_cols(h), proj_kp(h, net)));
 }
+// output head: W_out zero-padded to one 128-column tile [128][H] SB + bias [128]
+static size_t head_image_bytes(const kbs_handle* h) {
+  return kbs_sb_bytes_kind(tc_kind(h), kTileCols, h->p.hidden_size) + size_t(kTileCols) * 4;
+}
+static inline char* head_w(const kbs_handle* h, int net) { return proj_w(h, net) + proj_image_bytes(h, net); }
+static inline float* head_bias(const kbs_handle* h, int net) {
+  return reinterpret_cast<float*>(head_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), kTileCols, h->p.hidden_size));
+}
 
 int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
   KbsNet& N = h->net[net];
@@ -765,10 +1287,12 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
   if (!attr_set) {
     KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_tc_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_tc_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
+    KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
     attr_set = true;
   }
   if (N.tc_image) { KBS_CUDA_TRY(cudaFree(N.tc_image)); N.tc_image = nullptr; }
-  const size_t bytes = layer_image_bytes(h) * h->p.depth + proj_image_bytes(h, net);
+  const size_t bytes = layer_image_bytes(h) * h->p.depth + proj_image_bytes(h, net) + head_image_bytes(h);
   N.tc_image_floats = (bytes + 3) / 4;
   KBS_CUDA_TRY(cudaMalloc(&N.tc_image, bytes));
   for (int l = 0; l < h->p.depth; ++l) {
@@ -792,6 +1316,16 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
     else
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
                                         N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp, cols)));
+  }
+  if (N.num_out <= kTileCols && H % kbs_block_k(kind) == 0) {   // output head tile (persistent rollout kernel)
+    const int64_t total = int64_t(kTileCols) * (H / 4);
+    const unsigned gb = unsigned((total + 255) / 256);
+    if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_head_weights_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(
+                                        N.w_out, N.b_out, head_w(h, net), head_bias(h, net), H, N.num_out)));
+    else
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_head_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
+                                        N.w_out, N.b_out, head_w(h, net), head_bias(h, net), H, N.num_out)));
   }
   KBS_LAUNCH_CHECK();
   return KBS_OK;
@@ -910,9 +1444,12 @@ int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, con
 
 // ---- fused rollout: tensor-core input projection of all T steps + the recurrent phase --------------------------------
 // Workspace per net: h_sb [depth][2 parity] | x_mid_sb [2] | h2_rm [n][H] (floats)
+static size_t rollout_flag_bytes(const kbs_handle* h, int64_t n) {
+  return (size_t(h->p.depth + 1) * size_t(pad_rows(n) / kPanelRows) * 4 + 255) / 256 * 256;
+}
 static size_t rollout_ws_per_net_bytes(const kbs_handle* h, int64_t n) {
-  return act_sb_bytes(h, n) * (2 * size_t(h->p.depth) + 2) + 2 * size_t(n) * h->p.hidden_size * 4 +
-         2 * size_t(h->p.depth) * size_t(pad_rows(n)) * h->p.hidden_size * 4 + 256;
+  return act_sb_bytes(h, n) * (4 * size_t(h->p.depth)) + 2 * size_t(n) * h->p.hidden_size * 4 +
+         2 * size_t(h->p.depth) * size_t(pad_rows(n)) * h->p.hidden_size * 4 + rollout_flag_bytes(h, n) + 256;
 }
 size_t kbs_tc_rollout_ws_floats(const kbs_handle* h, int64_t n) { return 2 * rollout_ws_per_net_bytes(h, n) / 4; }
 int64_t kbs_tc_sb_floats(const kbs_handle* h, int64_t n) { return int64_t(act_sb_bytes(h, n) / 4); }
@@ -966,18 +1503,75 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
   }
   const int64_t n = r.n, ld = r.ld, np = pad_rows(n);
   const size_t sbb = act_sb_bytes(h, n), per_net = rollout_ws_per_net_bytes(h, n);
-  char* hsb[2]; char* xmid[2]; float* h2rm[2]; float* fb[2];
+  char* hsb[2]; char* xmid[2]; float* h2rm[2]; float* fb[2]; unsigned int* flags[2];
   const size_t fbf = size_t(np) * H;
   for (int k = 0; k < nets; ++k) {
     char* base = reinterpret_cast<char*>(r.ws) + per_net * k;
     hsb[k] = base;                                   // [depth][2] x sbb
-    xmid[k] = base + sbb * 2 * depth;                // [2] x sbb
-    h2rm[k] = reinterpret_cast<float*>(xmid[k] + 2 * sbb);   // [2 parity] x n*H: top-layer output, read by the head
+    xmid[k] = base + sbb * 2 * depth;                // [depth][2] x sbb (the per-step launch path uses the first two)
+    h2rm[k] = reinterpret_cast<float*>(xmid[k] + 2 * depth * sbb);   // [2 parity] x n*H: top-layer output (per-step path)
     fb[k] = h2rm[k] + 2 * size_t(n) * H;             // [depth][c, h] x np*H, FB layout
+    flags[k] = reinterpret_cast<unsigned int*>(fb[k] + 2 * size_t(depth) * fbf);
     for (int l = 0; l < depth; ++l) {                // ABI carry: h -> SB (parity 0), c -> FB
       pack_rows(h, r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H, H, hsb[k] + sbb * (2 * l), n, np, H, st);
       fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 1, st);
     }
+  }
+  const char* legacy_env = getenv("KBS_TC_PER_STEP");          // A/B and cross-check against the per-step launches
+  const int legacy = legacy_env ? atoi(legacy_env) : 0;
+  const int panels = int(np / kPanelRows), tiles = H / kUnitsPerTile;
+  const int64_t n_items = (r.T + depth) * int64_t(nets) * panels * (depth * tiles + 1);
+  if (!legacy && depth <= kPMaxDepth && H <= kMaxBias / 4 && n_items < (int64_t(1) << 31) &&
+      h->net[0].num_out <= kTileCols && (nets < 2 || h->net[1].num_out <= kTileCols)) {
+    // ---- persistent recurrence: one cooperative launch for all T steps (rollout_persist_kernel) ----
+    if (!h->persist_status) KBS_CUDA_TRY(cudaMalloc(&h->persist_status, 256));
+    PArgs a{};
+    for (int k = 0; k < nets; ++k) {
+      PNet& N = a.net[k];
+      N.x_sb_all = reinterpret_cast<const char*>(r.x_sb_all[k]);
+      N.hsb = hsb[k]; N.xmid = xmid[k]; N.fb = fb[k]; N.flags = flags[k];
+      for (int l = 0; l < depth; ++l) { N.w_sb[l] = layer_w(h, k, l); N.bias_t[l] = layer_bias(h, k, l); }
+      N.w_head = head_w(h, k); N.bias_head = head_bias(h, k);
+      KBS_CUDA_TRY(cudaMemsetAsync(flags[k], 0, rollout_flag_bytes(h, n), st));
+    }
+    KBS_CUDA_TRY(cudaMemsetAsync(h->persist_status, 0, 4, st));
+    a.nets = nets; a.depth = depth; a.H = H; a.panels = panels; a.tiles = tiles;
+    a.n = n; a.ld = ld; a.T = r.T; a.sbb = sbb;
+    a.done = r.done;
+    a.arm_cmd = r.actor_obs + size_t(55) * ld;
+    a.lpf = r.lpf; a.eps = r.eps_action;
+    a.q = r.qpos ? r.qpos + size_t(7) * ld : nullptr;
+    a.qd = r.qvel ? r.qvel + size_t(6) * ld : nullptr;
+    a.ep = r.ep;
+    a.action = r.action; a.log_prob = r.log_prob; a.ctrl = (r.ctrl && r.qpos && r.qvel) ? r.ctrl : nullptr; a.value = r.value;
+    a.action_in = r.action_in; a.entropy = r.entropy; a.std = r.action_std;
+    a.status = h->persist_status;
+    { const char* e = getenv("KBS_PERSIST_DBG"); a.dbg = e ? atoi(e) : 0; }
+    a.trace = h->trace_buf;
+    cudaLaunchConfig_t cfg{};
+    const int64_t per_slot = int64_t(nets) * panels * (depth * tiles + 1);
+    cfg.gridDim = dim3(unsigned(per_slot < h->num_sms ? per_slot : h->num_sms));
+    cfg.blockDim = dim3(kThreadsP);
+    cfg.dynamicSmemBytes = kPSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;      // every CTA must be resident: they wait on each other's counters
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaSuccess;
+    if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<KBS_KIND_TF32>, h->p, a)));
+    else
+      KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<KBS_KIND_F16>, h->p, a)));
+    KBS_CUDA_TRY(le);
+    for (int k = 0; k < nets; ++k)
+      for (int l = 0; l < depth; ++l) {                // FB state -> ABI carry
+        fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 0, st);
+        fb_convert(h, r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H, fb[k] + fbf * (2 * l + 1), n, np, H, 0, st);
+      }
+    KBS_LAUNCH_CHECK();
+    return KBS_OK;
   }
   // The head of step t (out-projection, sampling, log-prob, torque, value) feeds nothing back into the recurrence, so
   // it runs on the handle's side stream, forked from and joined back into the caller's stream with events, while the

@@ -83,6 +83,12 @@ class KbotStep:
     def launches(self) -> int:
         return int(self.lib.kbs_launch_count(self._h))
 
+    def device_status(self) -> int:
+        """0 = healthy; != 0 = a dependency wait of the persistent rollout kernel timed out (synchronises)."""
+        v = C.c_int(0)
+        L.check(self.lib.kbs_device_status(self._h, C.byref(v)), "kbs_device_status")
+        return int(v.value)
+
     def profile(self, on: bool) -> None:
         L.check(self.lib.kbs_profile_enable(self._h, 1 if on else 0), "kbs_profile_enable")
 

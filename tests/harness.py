@@ -168,6 +168,7 @@ def run_rollout_case(seed: int, T: int, N: int, hidden: int, device, gemm_path=L
     l0 = eng.launches
     eng.rollout(io, N)
     torch.cuda.synchronize()
+    assert eng.device_status() == 0, "persistent rollout kernel: a dependency wait timed out"
     ref = oracle_rollout(b, wa, wc, hidden, depth, with_critic)
     errs = compare_rollout(io, ref, N, with_critic)
     out = {"errors": errs, "launches": eng.launches - l0, "done_count": ref["done"].sum()}

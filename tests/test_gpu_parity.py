@@ -323,13 +323,43 @@ def test_policy_step(dev, path, N):
 
 
 @pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("T,N,hidden", [(16, 32, 256), (6, 130, 256), (5, 50, 128)])
+@pytest.mark.parametrize("T,N,hidden", [(16, 32, 256), (6, 130, 256), (5, 50, 128), (7, 1100, 256), (1, 300, 256)])
 def test_rollout_fused(dev, path, T, N, hidden):
     """BASELINE config 1 shape (num_envs = 32, short rollout): the fused control step over T recorded steps."""
     res = Hn.run_rollout_case(seed=800 + N, T=T, N=N, hidden=hidden, device=dev, gemm_path=path)
     bad = {k: v for k, v in res["errors"].items() if not v <= 1.0}
     assert not bad, f"scaled errors > 1: {bad} (all: {res['errors']})"
     assert res["launches"] > 0
+
+
+@pytest.mark.parametrize("T,N", [(12, 2048), (40, 4096)])
+def test_rollout_persistent_vs_per_step_launches(dev, T, N, monkeypatch):
+    """Size-independent property at BASELINE configs[1] scale: the persistent recurrence kernel (one launch, CTAs
+    synchronised through progress counters) and the per-step launch sequence (kernel boundaries as the only
+    synchronisation) run the same tcgen05 datapath; they agree to rounding level (the three MMA-issuing warps of a
+    CTA interleave differently from run to run, so the truncating accumulation is reproducible to ~1 ulp, not bitwise;
+    a missed dependency would show as an O(0.1) error).  The heads differ in summation order (tensor-core vs FFMA)."""
+    b = Batch(4242, T, N, dev)
+    outs = []
+    for per_step in ("0", "1"):
+        monkeypatch.setenv("KBS_TC_PER_STEP", per_step)
+        e, _, _ = Hn.make_engine(gemm_path=L.GEMM_TC_2XF16, device=dev)
+        io = Hn.rollout_buffers(b, 256, 2)
+        l0 = e.launches
+        e.rollout(io, N)
+        torch.cuda.synchronize()
+        assert e.device_status() == 0
+        outs.append((io, e.launches - l0))
+        e.close()
+    (a, la), (c, lc) = outs
+    assert la < lc and lc - la >= 3 * T - 10, (la, lc)          # one launch instead of 3 per step
+    close(a["actor_carry"].cpu().numpy(), c["actor_carry"].cpu().numpy(), "actor carry", atol=2e-6)
+    close(a["critic_carry"].cpu().numpy(), c["critic_carry"].cpu().numpy(), "critic carry", atol=2e-6)
+    close(S(a["action"], N, (20,)), S(c["action"], N, (20,)), "action")
+    close(S(a["log_prob"], N), S(c["log_prob"], N), "log_prob", atol=1e-5)
+    close(S(a["value"], N), S(c["value"], N), "value", atol=1e-5)
+    close(S(a["ctrl"], N, (20,)), S(c["ctrl"], N, (20,)), "ctrl", atol=1e-4)
+    close(S(a["lpf"], N, (20,)), S(c["lpf"], N, (20,)), "lpf")
 
 
 def test_rollout_then_rewards_gae_chain(dev):
@@ -415,6 +445,7 @@ def test_ppo_variables(dev, path, T, N, hidden):
         return out, ac, cc, lpf
 
     out, ac, cc, lpf = run(obs_list, cmd, False)
+    assert e.device_status() == 0
     close(S(out["log_probs"], N), ref["log_probs"][..., 0], "log_probs", atol=1e-4)     # |log_prob| up to ~1e3 here
     close(S(out["entropy"], N), ref["entropy"][..., 0], "entropy", atol=1e-5)
     close(S(out["values"], N), ref["values"], "values", atol=1e-5)
