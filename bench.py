@@ -333,9 +333,13 @@ def run_b200(a):
     flops_actor, flops_critic = spec.net_flops(65, 40, H, 2), spec.net_flops(475, 1, H, 2)
     lstm_layer_flops = 2 * (2 * H) * (4 * H)                      # one layer-step per env: [x|h] (2H) x 4H gates
     roof = None
-    if dom_name in ("lstm_layer_tc_kernel", "gemm_nt_kernel(simt)"):
-        if dom_name == "lstm_layer_tc_kernel":
-            flops_per_launch = lstm_layer_flops * N * 2          # one launch = one layer-step of BOTH nets
+    if dom_name in ("lstm_layer_tc_kernel", "gemm_nt_kernel(simt)", "rollout_persist_kernel"):
+        if dom_name in ("lstm_layer_tc_kernel", "rollout_persist_kernel"):
+            if dom_name == "rollout_persist_kernel":
+                # one launch = the whole recurrence: T steps x (2 nets x depth LSTM layers + actor/critic output heads)
+                flops_per_launch = N * T * (2 * 2 * lstm_layer_flops + 2 * H * (40 + 1))
+            else:
+                flops_per_launch = lstm_layer_flops * N * 2      # one launch = one layer-step of BOTH nets
             if a.gemm == "tf32":
                 peak = bf16_sus / 6.0                             # 3xTF32: TF32 = bf16 / 2, three MMAs per product
                 note = "fp32-accurate 3xTF32: peak = sustained bf16 / 6"
@@ -347,8 +351,11 @@ def run_b200(a):
             peak = 72.0                                           # fp32 FFMA: 148 SMs x 128 lanes x 2 x ~1.9 GHz
             note = "fp32 FFMA path: peak = nominal FFMA rate (interim SIMT datapath)"
         ach = flops_per_launch / (dom_ms / dom_n * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_persist_kernel.md);
+        # only valid for the configuration that capture was taken on
+        traffic = 8.56e9 if (dom_name == "rollout_persist_kernel" and (N, T, H, a.gemm) == (4096, 100, 256, "f16")) else None
         roof = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "launches": dom_n, "avg_launch_us": 1e3 * dom_ms / dom_n,
+                "frac": ach / peak, "traffic": traffic, "launches": dom_n, "avg_launch_us": 1e3 * dom_ms / dom_n,
                 "share_of_step": dom_ms / tot_prof, "peak_source": which, "note": note}
     else:
         roof = {"kernel": dom_name, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 _PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = _PKG_DIR / "libkbotstep.so"
+LIB_PATH = Path(os.environ["KBS_LIB_PATH"]) if os.environ.get("KBS_LIB_PATH") else _PKG_DIR / "libkbotstep.so"   # override: A/B builds
 
 NUM_JOINTS = 20
 NUM_COMMANDS = 16

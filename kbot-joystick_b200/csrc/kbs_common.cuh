@@ -260,6 +260,24 @@ __device__ __forceinline__ void sb_store_split(void* __restrict__ sb, int64_t ro
     *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1) + sub) = make_uint2(s.lo.x, s.lo.y);
   }
 }
+// 8 consecutive K values (k % 8 == 0) from two splits: FP16 kind = ONE 16-byte chunk per plane; zero = store zeros
+template <int R, int KIND>
+__device__ __forceinline__ void sb_store_split8(void* __restrict__ sb, int64_t row, int k, int kblocks, const KbsSplit4& a,
+                                                const KbsSplit4& b, bool zero) {
+  char* base = reinterpret_cast<char*>(sb);
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  if (KIND == KBS_KIND_TF32) {
+    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 0)) = zero ? z4 : a.hi;
+    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1)) = zero ? z4 : a.lo;
+    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k + 4, kblocks, 0)) = zero ? z4 : b.hi;
+    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k + 4, kblocks, 1)) = zero ? z4 : b.lo;
+  } else {
+    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 0)) =
+        zero ? z4 : make_uint4(a.hi.x, a.hi.y, b.hi.x, b.hi.y);
+    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1)) =
+        zero ? z4 : make_uint4(a.lo.x, a.lo.y, b.lo.x, b.lo.y);
+  }
+}
 // store 4 consecutive K values (k % 4 == 0)
 template <int R, int KIND>
 __device__ __forceinline__ void sb_store4(void* __restrict__ sb, int64_t row, int k, int kblocks, const float (&x)[4]) {

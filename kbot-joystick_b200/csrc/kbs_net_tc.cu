@@ -28,7 +28,10 @@ constexpr int kTileCols = 128;           // UMMA N: 32 hidden units x 4 gates (g
 constexpr int kUnitsPerTile = 32;
 // One pipeline stage = one SB block of each operand = 4 chunks of 16 B along K (2 MMA k-steps): K = 16 for TF32
 // operands, 32 for F16 operands -- the BYTES (and therefore all shared-memory offsets / descriptors) are identical.
-constexpr int kStages = 6;
+#ifndef KBS_STAGES
+#define KBS_STAGES 6
+#endif
+constexpr int kStages = KBS_STAGES;
 constexpr int kABlockBytes = 2 * 4 * kPanelRows * 16;   // [hi|lo][4 chunks][128 rows][16 B] = 16 KB
 constexpr int kBBlockBytes = 2 * 4 * kTileCols * 16;    // 16 KB
 constexpr int kStageBytes = kABlockBytes + kBBlockBytes;   // 32 KB
@@ -805,13 +808,14 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
         if (!it.valid) continue;
         const PNet& N = args.net[it.net];
         const int kb_x = kb, kb_total = it.kind == 0 ? 2 * kb : kb;
-        const size_t poff = size_t(it.panel) * kb * kABlockBytes;
+        size_t poff = size_t(it.panel) * kb * kABlockBytes;
+        if (args.dbg & 8) poff = size_t(blockIdx.x % args.panels) * kb * kABlockBytes;   // probe: no two CTAs share a panel at a time
         const char* xa; const char* ha; const char* wb;
         if (it.kind == 0) {
           xa = (it.layer == 0 ? N.x_sb_all + size_t(it.t) * args.sbb
                               : N.xmid + size_t((it.layer - 1) * 2 + (it.t & 1)) * args.sbb) + poff;
           ha = N.hsb + size_t(it.layer * 2 + (it.t & 1)) * args.sbb + poff;
-          wb = N.w_sb[it.layer] + size_t(it.tile) * kb_total * kBBlockBytes;
+          wb = N.w_sb[it.layer] + size_t((args.dbg & 16) ? (blockIdx.x + it.t) % args.tiles : it.tile) * kb_total * kBBlockBytes;
         } else {
           xa = N.xmid + size_t((args.depth - 1) * 2 + (it.t & 1)) * args.sbb + poff;
           ha = xa;
@@ -960,29 +964,35 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
         for (int g4 = 0; g4 < 4; ++g4)
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[8 * g4 + i] += bs[16 * g4 + i];
-        if (live) {
+        if (live && !(args.dbg & 2)) {
           char* x_out = N.xmid + size_t(it.layer * 2 + (it.t & 1)) * args.sbb;
           char* h_out = N.hsb + size_t(it.layer * 2 + ((it.t + 1) & 1)) * args.sbb;
           float* h_carry = (it.t == int(args.T) - 1) ? cst + size_t(args.panels) * kPanelRows * H : nullptr;
+          // 8 hidden units per thread = exactly one 16-byte SB chunk per plane (FP16 kind): every store below is a full
+          // 16 B per lane, 512 contiguous bytes per warp (the 8-byte half-chunk stores of the 4-unit version cost the
+          // bulk-copy pipeline 2.5 K cycles per item in L2 write contention)
+          float hn[8], cn[8];
 #pragma unroll
-          for (int i = 0; i < 8; i += 4) {
-            const float4 c4 = cpre[i >> 2];
-            const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
-            float hn[4], cn[4];
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-              const float gi_ = v[i + l], gf = v[8 + i + l], gg = v[16 + i + l], go = v[24 + i + l];
-              // c' = s(f) c + s(i) tanh(g);  h' = s(o) tanh(c')   (eqx LSTMCell)
-              cn[l] = sigmoidf_(gf) * cv[l] + sig_mul_tanh(gi_, gg);
-              hn[l] = sig_mul_tanh(go, cn[l]);
-              if (rst) cn[l] = 0.0f;
+          for (int i = 0; i < 8; ++i) {
+            const float cprev = i < 4 ? (&cpre[0].x)[i] : (&cpre[1].x)[i - 4];
+            const float gi_ = v[i], gf = v[8 + i], gg = v[16 + i], go = v[24 + i];
+            // c' = s(f) c + s(i) tanh(g);  h' = s(o) tanh(c')   (eqx LSTMCell)
+            cn[i] = sigmoidf_(gf) * cprev + sig_mul_tanh(gi_, gg);
+            hn[i] = sig_mul_tanh(go, cn[i]);
+            if (rst) cn[i] = 0.0f;
+          }
+          if (!((args.dbg & 4) && hn[0] != 12345.0f)) {
+            const float h0[4] = {hn[0], hn[1], hn[2], hn[3]}, h1[4] = {hn[4], hn[5], hn[6], hn[7]};
+            const KbsSplit4 s0 = sb_split4<KIND>(h0), s1 = sb_split4<KIND>(h1);   // one split serves both consumers
+            sb_store_split8<kPanelRows, KIND>(x_out, R, u0, kb, s0, s1, false);   // next layer / head input (un-reset)
+            sb_store_split8<kPanelRows, KIND>(h_out, R, u0, kb, s0, s1, rst);     // recurrent input (reset where done)
+            *reinterpret_cast<float4*>(cst + fb_offset(R, u0, H)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            *reinterpret_cast<float4*>(cst + fb_offset(R, u0 + 4, H)) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+            if (h_carry) {
+              const float z = rst ? 0.0f : 1.0f;
+              *reinterpret_cast<float4*>(h_carry + fb_offset(R, u0, H)) = make_float4(z * hn[0], z * hn[1], z * hn[2], z * hn[3]);
+              *reinterpret_cast<float4*>(h_carry + fb_offset(R, u0 + 4, H)) = make_float4(z * hn[4], z * hn[5], z * hn[6], z * hn[7]);
             }
-            KbsSplit4 sp = sb_split4<KIND>(hn);               // one split serves the consumer of this layer (un-reset) ...
-            sb_store_split<kPanelRows, KIND>(x_out, R, u0 + i, kb, sp);
-            if (rst) { sp.hi = make_uint4(0u, 0u, 0u, 0u); sp.lo = sp.hi; hn[0] = hn[1] = hn[2] = hn[3] = 0.0f; }
-            sb_store_split<kPanelRows, KIND>(h_out, R, u0 + i, kb, sp);   // ... and the recurrent input (reset)
-            *reinterpret_cast<float4*>(cst + fb_offset(R, u0 + i, H)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            if (h_carry) *reinterpret_cast<float4*>(h_carry + fb_offset(R, u0 + i, H)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
           }
         }
       } else {
@@ -1551,6 +1561,7 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     cudaLaunchConfig_t cfg{};
     const int64_t per_slot = int64_t(nets) * panels * (depth * tiles + 1);
     cfg.gridDim = dim3(unsigned(per_slot < h->num_sms ? per_slot : h->num_sms));
+    { const char* e = getenv("KBS_PERSIST_GRID"); if (e && atoi(e) > 0 && atoi(e) < int(cfg.gridDim.x)) cfg.gridDim.x = unsigned(atoi(e)); }   // profiling only
     cfg.blockDim = dim3(kThreadsP);
     cfg.dynamicSmemBytes = kPSmemBytes;
     cfg.stream = st;

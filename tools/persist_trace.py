@@ -22,7 +22,8 @@ io = {"state": d["state"], "noise": d["noise"], "episode": d["episode"], "eps_ac
       "log_prob": torch.zeros((T, N), **f32), "ctrl": torch.zeros((T, 20, N), **f32), "term_codes": None,
       "done": torch.zeros((T, N), device=dev, dtype=torch.uint8), "success": torch.zeros((T, N), device=dev, dtype=torch.uint8),
       "value": torch.zeros((T, N), **f32), "T": T}
-ctas = 148
+import os
+ctas = int(os.environ.get("KBS_PERSIST_GRID", "148"))
 tr = torch.zeros((ctas * 12 + 1024,), dtype=torch.int64, device=dev)
 e.lib.kbs_debug_tc_trace_attach(e._h, tr.data_ptr(), 0, 0)
 for rep in range(3):
