@@ -161,6 +161,18 @@ int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_vie
                      const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs,
                      int64_t n_envs, void* stream);
 
+/* Replaces: mirror_obs + mirror_cmd (train.py:1584-1756) followed by the run_actor / run_critic concatenations on the
+ * mirrored observations (train.py:1463-1481), for T stored steps.  The mirror acts on the RAW named observations, so it
+ * is built from what the rollout stored: `computed` [T][78][ld] (kbs_observations), the recorded state (time-major
+ * [T][rows][ld] arrays in *s) and `command` [T][16][ld].
+ *   actor_obs [T][65][ld] / critic_obs [T][475][ld] / command_out [T][16][ld]: any may be NULL (not all). */
+int kbs_mirror_observations(kbs_handle* h, const kbs_state_view* s, const float* computed, const float* command,
+                            float* actor_obs, float* critic_obs, float* command_out, int64_t T, int64_t n_envs,
+                            void* stream);
+/* Replaces: mirror_joints (train.py:1574-1582): out = -[in[5:10], in[0:5], in[10:15], in[15:20]] on [T][20][ld]
+ * (legs swapped, arm halves NOT exchanged -- as the reference writes it).  in != out. */
+int kbs_mirror_joints(kbs_handle* h, const float* in, float* out, int64_t T, int64_t ld, int64_t n_envs, void* stream);
+
 /* Replaces: UnifiedCommand.__call__/initial_command (train.py:724-785).  Randomness explicit:
  *   u_switch [ld] U[0,1); mode int32 [ld] in 0..5; u6 [6][ld]; u_arms [10][ld].  u_switch NULL = always
  *   resample (initial_command).  command [16][ld] in/out. */

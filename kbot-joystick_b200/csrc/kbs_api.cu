@@ -143,12 +143,15 @@ int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStr
     const kbs_noise_view nz = noise_at(io->noise, t0, ld);
     float* aobs_c = aobs + t0 * KBS_ACTOR_OBS * ld;
     if ((rc = kbs_launch_observations(h, s, &nz, &io->episode, io->command + t0 * KBS_NUM_COMMANDS * ld, nullptr, nullptr,
-                                      nullptr, aobs_c, cobs, n, aux, tc, lagged ? lagged + t0 * 3 * ld : nullptr)))
+                                      nullptr, aobs_c, cobs, n, aux, tc, lagged ? lagged + t0 * 3 * ld : nullptr,
+                                      /*skip_dump=*/true)))
       return rc;
     const float* obs_soa[2] = {aobs_c, cobs};
     float* obs_sb[2] = {osb_a, osb_c};
     float* xsb[2] = {xsb_a + size_t(t0) * sbf, critic ? xsb_c + size_t(t0) * sbf : nullptr};
-    if ((rc = kbs_tc_input_proj_all(h, critic ? 2 : 1, obs_soa, obs_sb, xsb, ld, n, tc, aux))) return rc;
+    if ((rc = kbs_tc_input_proj_all(h, critic ? 2 : 1, obs_soa, obs_sb, xsb, ld, n, tc, aux,
+                                    critic ? s.cinert : nullptr, critic ? s.cvel : nullptr)))
+      return rc;
     if (overlap) KBS_CUDA_TRY(cudaEventRecord(h->ev_chunk[n_chunks], aux));
   }
 
@@ -399,6 +402,27 @@ int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_vie
   if (reinterpret_cast<uintptr_t>(pg_reset) & 3u) return KBS_E_ALIGN;
   return kbs_launch_observations(h, *s, noise, ep, command, pg_carry, pg_reset, computed, actor_obs, critic_obs, n,
                                  (cudaStream_t)stream);
+}
+
+int kbs_mirror_observations(kbs_handle* h, const kbs_state_view* s, const float* computed, const float* command,
+                            float* actor_obs, float* critic_obs, float* command_out, int64_t T, int64_t n, void* stream) {
+  REQ(h); REQ(computed); REQ(command);
+  if (T <= 0 || T > 65535) return KBS_E_SHAPE;
+  int rc = check_state(s, n, true);
+  if (rc) return rc;
+  if (critic_obs) { REQ(s->cinert); REQ(s->cvel); REQ(s->actuator_force); REQ(s->xpos); }
+  if (!actor_obs && !critic_obs && !command_out) return KBS_E_NULL;
+  AL(computed); AL(command); AL(actor_obs); AL(critic_obs); AL(command_out);
+  return kbs_launch_mirror_obs(h, *s, computed, command, actor_obs, critic_obs, command_out, n, T, (cudaStream_t)stream);
+}
+
+int kbs_mirror_joints(kbs_handle* h, const float* in, float* out, int64_t T, int64_t ld, int64_t n, void* stream) {
+  REQ(h); REQ(in); REQ(out);
+  if (T <= 0 || T > 65535 || in == out) return KBS_E_SHAPE;
+  int rc = check_ld(ld, n);
+  if (rc) return rc;
+  AL(in); AL(out);
+  return kbs_launch_mirror_joints(h, in, out, ld, n, T, (cudaStream_t)stream);
 }
 
 int kbs_command_update(kbs_handle* h, float* command, const float* u_switch, const int32_t* mode, const float* u6,

@@ -99,7 +99,10 @@ int kbs_scratch_reserve(kbs_handle* h, size_t floats);
 int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_noise_view* nz,
                             const kbs_episode_view* ep, const float* command, float* pg_carry,
                             const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n,
-                            cudaStream_t st, int64_t T = 1, const float* pg_lagged = nullptr);
+                            cudaStream_t st, int64_t T = 1, const float* pg_lagged = nullptr, bool skip_dump = false);
+int kbs_launch_mirror_obs(kbs_handle* h, const kbs_state_view& s, const float* computed, const float* command,
+                          float* actor_obs, float* critic_obs, float* command_out, int64_t n, int64_t T, cudaStream_t st);
+int kbs_launch_mirror_joints(kbs_handle* h, const float* in, float* out, int64_t ld, int64_t n, int64_t T, cudaStream_t st);
 int kbs_launch_command(kbs_handle* h, const float* cmd_in, float* cmd_out, const float* u_switch,
                        const int32_t* mode, const float* u6, const float* u_arms, const uint8_t* done, int64_t ld,
                        int64_t n, cudaStream_t st);
@@ -160,8 +163,11 @@ struct KbsTcRolloutArgs {
 size_t kbs_tc_rollout_ws_floats(const kbs_handle* h, int64_t n);
 int64_t kbs_tc_sb_floats(const kbs_handle* h, int64_t n);
 int64_t kbs_tc_obs_sb_floats(const kbs_handle* h, int net, int64_t n, int64_t T);
+// cinert / cvel != nullptr: the critic's privileged dump (features 80..447) is read from the recorded state
+// ([T][240][ld] / [T][144][ld]) instead of obs_soa[critic]
 int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, float* const* obs_sb, float* const* x_sb_all,
-                          int64_t ld, int64_t n, int64_t T, cudaStream_t st);
+                          int64_t ld, int64_t n, int64_t T, cudaStream_t st, const float* cinert = nullptr,
+                          const float* cvel = nullptr);
 int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStream_t st);
 int kbs_tc_debug_trace(kbs_handle* h, long long* trace_out, float* ws, int64_t n, cudaStream_t st);
 int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,

@@ -258,6 +258,191 @@ obs_kernel(const __grid_constant__ kbs_params P, kbs_state_view s, kbs_noise_vie
 }
 
 // =====================================================================================================
+// X1: mirror_obs / mirror_cmd / mirror_joints (train.py:1574-1756) followed by the run_actor / run_critic
+// concatenations on the MIRRORED observations -- what _ppo_scan_fn feeds the *_mirror carries (train.py:1463-1481).
+// The mirror acts on the raw named observations (before normalisation), so it is built from the stored raw
+// observations (`computed`, the noisy twins the rollout recorded) and the state slices, not from actor_obs.
+//   mirror_joints(j) = -[j[5:10], j[0:5], j[10:15], j[15:20]]  (legs swapped, arms NOT: as written)
+// grid = (env groups, 1 + copy sections, T)
+// =====================================================================================================
+__device__ __forceinline__ int mirror_src_joint(int j) { return j < 5 ? j + 5 : (j < 10 ? j - 5 : j); }
+
+__global__ void __launch_bounds__(kThreads)
+mirror_obs_kernel(const __grid_constant__ kbs_params P, kbs_state_view s, const float* __restrict__ computed,
+                  const float* __restrict__ command, float* __restrict__ actor_obs, float* __restrict__ critic_obs,
+                  float* __restrict__ command_out, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  const int64_t ld = s.ld;
+  {
+    const int64_t t = blockIdx.z;
+    s.qpos += t * KBS_NQ * ld; s.qvel += t * KBS_NV * ld; s.sensordata += t * KBS_NSENSORDATA * ld;
+    s.xpos += t * 3 * KBS_NBODY * ld;
+    if (s.cinert) s.cinert += t * 10 * KBS_NBODY * ld;
+    if (s.cvel) s.cvel += t * 6 * KBS_NBODY * ld;
+    if (s.actuator_force) s.actuator_force += t * KBS_NUM_JOINTS * ld;
+    computed += t * KBS_NUM_COMPUTED_OBS * ld;
+    command += t * KBS_NUM_COMMANDS * ld;
+    if (actor_obs) actor_obs += t * KBS_ACTOR_OBS * ld;
+    if (critic_obs) critic_obs += t * KBS_CRITIC_OBS * ld;
+    if (command_out) command_out += t * KBS_NUM_COMMANDS * ld;
+  }
+  if (blockIdx.y > 0) {
+    // center_of_mass_inertia (.,10) * (1,1,-1,1,1,1,1,-1,1,-1); center_of_mass_velocity (.,6) * (1,-1,1,-1,1,-1)
+    const int i0 = (blockIdx.y - 1) * kCopyRowsPerSection;
+    for (int i = i0; i < i0 + kCopyRowsPerSection; ++i) {
+      float v[4];
+      if (i < 230) {
+        const int c = i % 10;
+        const float sg = (c == 2 || c == 7 || c == 9) ? -1.0f : 1.0f;
+        kbs_ld4(s.cinert, 10 + i, ld, n0, v);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) v[l] = v[l] * sg;
+        kbs_st4(critic_obs, 80 + i, ld, n0, v);
+      } else if (i < 368) {
+        const int c = (i - 230) % 6;
+        const float sg = (c & 1) ? -1.0f : 1.0f;
+        kbs_ld4(s.cvel, 6 + (i - 230), ld, n0, v);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) v[l] = v[l] * sg;
+        kbs_st4(critic_obs, 310 + (i - 230), ld, n0, v);
+      }
+    }
+    return;
+  }
+  // mirror_cmd: (vx, -vy, -wz, bh, -rx, ry, -arms)
+  float c[16][4], zc[4];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    kbs_ld4(command, k, ld, n0, c[k]);
+    const bool neg = (k == 1 || k == 2 || k == 4 || k >= 6);
+    if (neg) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l) c[k][l] = -c[k][l];
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < 4; ++l) zc[l] = zero_cmd(c[0][l], c[1][l], c[2][l]) ? 1.0f : 0.0f;
+  if (command_out) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) kbs_st4(command_out, k, ld, n0, c[k]);
+  }
+#pragma unroll 4
+  for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+    const int sj = mirror_src_joint(j);
+    float nbj[4], nv[4], q[4], qd[4], a0[4], a1[4], c0[4], c1[4];
+    kbs_ld4(computed, 20 + sj, ld, n0, nbj);
+    kbs_ld4(computed, 40 + sj, ld, n0, nv);
+    kbs_ld4(s.qpos, 7 + sj, ld, n0, q);
+    kbs_ld4(s.qvel, 6 + sj, ld, n0, qd);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      a0[l] = (-nbj[l] - P.joint_bias[j]) / P.joint_range[j];
+      a1[l] = -nv[l] / 10.0f;
+      c0[l] = (-q[l] - P.joint_bias[j]) / P.joint_range[j];
+      c1[l] = -qd[l] / 10.0f;
+    }
+    if (actor_obs) { kbs_st4(actor_obs, j, ld, n0, a0); kbs_st4(actor_obs, 20 + j, ld, n0, a1); }
+    if (critic_obs) { kbs_st4(critic_obs, j, ld, n0, c0); kbs_st4(critic_obs, 20 + j, ld, n0, c1); }
+  }
+  {
+    // projected gravity * (1,-1,1) -> encode; gyro * (-1,1,-1)
+    float npg[3][4], pg[3][4], ngy[3][4], gy[3][4], ea[5][4], ec[5][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      kbs_ld4(computed, 75 + k, ld, n0, npg[k]);
+      kbs_ld4(computed, 69 + k, ld, n0, pg[k]);
+      kbs_ld4(computed, 60 + k, ld, n0, ngy[k]);
+      kbs_ld4(s.sensordata, P.sd_gyro + k, ld, n0, gy[k]);
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float ga[3] = {npg[0][l], -npg[1][l], npg[2][l]}, gc[3] = {pg[0][l], -pg[1][l], pg[2][l]};
+      float oa[5], oc[5];
+      encode_pg(ga, oa);
+      encode_pg(gc, oc);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) { ea[k][l] = oa[k]; ec[k][l] = oc[k]; }
+      ngy[0][l] = -ngy[0][l]; ngy[2][l] = -ngy[2][l];
+      gy[0][l] = -gy[0][l]; gy[2][l] = -gy[2][l];
+    }
+    if (actor_obs) {
+      for (int k = 0; k < 5; ++k) kbs_st4(actor_obs, 40 + k, ld, n0, ea[k]);
+      for (int k = 0; k < 3; ++k) kbs_st4(actor_obs, 45 + k, ld, n0, ngy[k]);
+    }
+    if (critic_obs) {
+      for (int k = 0; k < 5; ++k) kbs_st4(critic_obs, 40 + k, ld, n0, ec[k]);
+      for (int k = 0; k < 3; ++k) kbs_st4(critic_obs, 45 + k, ld, n0, gy[k]);
+    }
+  }
+  if (actor_obs) {
+    kbs_st4(actor_obs, 48, ld, n0, zc);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) kbs_st4(actor_obs, 49 + k, ld, n0, c[k]);
+  }
+  if (critic_obs) {
+    kbs_st4(critic_obs, 48, ld, n0, zc);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) kbs_st4(critic_obs, 49 + k, ld, n0, c[k]);
+    kbs_copy4(s.sensordata, P.sd_touch_r, critic_obs, 65, ld, n0);       // left <- right
+    kbs_copy4(s.sensordata, P.sd_touch_l, critic_obs, 66, ld, n0);
+    // feet_position: [fp[3:6], fp[0:3]] * (1,-1,1,1,-1,1)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      float v[4];
+      kbs_ld4(computed, 63 + (k < 3 ? k + 3 : k - 3), ld, n0, v);
+      if (k % 3 == 1) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) v[l] = -v[l];
+      }
+      kbs_st4(critic_obs, 67 + k, ld, n0, v);
+    }
+    for (int k = 0; k < 3; ++k) kbs_copy4(s.qpos, k, critic_obs, 73 + k, ld, n0);      // base_position unchanged
+    for (int k = 0; k < 4; ++k) {                                                       // base_orientation * (1,-1,-1,1)
+      float v[4];
+      kbs_ld4(s.qpos, 3 + k, ld, n0, v);
+      if (k == 1 || k == 2) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) v[l] = -v[l];
+      }
+      kbs_st4(critic_obs, 76 + k, ld, n0, v);
+    }
+    for (int k = 0; k < 6; ++k) {                 // base lin vel * (1,-1,1), ang vel * (-1,1,-1)
+      float v[4];
+      kbs_ld4(s.qvel, k, ld, n0, v);
+      if (k == 1 || k == 3 || k == 5) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) v[l] = -v[l];
+      }
+      kbs_st4(critic_obs, 448 + k, ld, n0, v);
+    }
+#pragma unroll 4
+    for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+      float f[4];
+      kbs_ld4(s.actuator_force, mirror_src_joint(j), ld, n0, f);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) f[l] = -f[l] / 4.0f;
+      kbs_st4(critic_obs, 454 + j, ld, n0, f);
+    }
+    kbs_copy4(s.xpos, 3 * P.body_base + 2, critic_obs, 474, ld, n0);
+  }
+}
+
+// mirror_joints on a [T][20][ld] array (e.g. dist.mean() of the mirrored pass, train.py:1468)
+__global__ void __launch_bounds__(kThreads)
+mirror_joints_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t ld, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  const int64_t t = blockIdx.z;
+  const int j = blockIdx.y;
+  float v[4];
+  kbs_ld4(in + t * KBS_NUM_JOINTS * ld, mirror_src_joint(j), ld, n0, v);
+#pragma unroll
+  for (int l = 0; l < 4; ++l) v[l] = -v[l];
+  kbs_st4(out + t * KBS_NUM_JOINTS * ld, j, ld, n0, v);
+}
+
+// =====================================================================================================
 // UnifiedCommand train.py:724-785
 // =====================================================================================================
 __global__ void __launch_bounds__(kThreads)
@@ -839,14 +1024,31 @@ inline unsigned groups4(int64_t n) { return unsigned((((n + 3) / 4) + kThreads -
 int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_noise_view* nz,
                             const kbs_episode_view* ep, const float* command, float* pg_carry,
                             const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n,
-                            cudaStream_t st, int64_t T, const float* pg_lagged) {
+                            cudaStream_t st, int64_t T, const float* pg_lagged, bool skip_dump) {
   kbs_noise_view z{};
   kbs_episode_view e{};
   if (nz) z = *nz;
   if (ep) e = *ep;
-  dim3 grid(groups4(n), critic_obs ? 1 + 368 / kCopyRowsPerSection : 1, unsigned(T));
+  // skip_dump: the caller reads cinert / cvel straight from the state (critic rows 80..447 stay unwritten)
+  dim3 grid(groups4(n), (critic_obs && !skip_dump) ? 1 + 368 / kCopyRowsPerSection : 1, unsigned(T));
   KBS_LAUNCH(h, KBS_K_OBS, st, (obs_kernel<<<grid, kThreads, 0, st>>>(h->p, s, z, e, command, pg_carry, pg_reset, pg_lagged,
                                                                       computed, actor_obs, critic_obs, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_mirror_obs(kbs_handle* h, const kbs_state_view& s, const float* computed, const float* command,
+                          float* actor_obs, float* critic_obs, float* command_out, int64_t n, int64_t T, cudaStream_t st) {
+  dim3 grid(groups4(n), critic_obs ? 1 + 368 / kCopyRowsPerSection : 1, unsigned(T));
+  KBS_LAUNCH(h, KBS_K_OBS, st, (mirror_obs_kernel<<<grid, kThreads, 0, st>>>(h->p, s, computed, command, actor_obs, critic_obs,
+                                                                             command_out, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_mirror_joints(kbs_handle* h, const float* in, float* out, int64_t ld, int64_t n, int64_t T, cudaStream_t st) {
+  dim3 grid(groups4(n), KBS_NUM_JOINTS, unsigned(T));
+  KBS_LAUNCH(h, KBS_K_OBS, st, (mirror_joints_kernel<<<grid, kThreads, 0, st>>>(in, out, ld, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

@@ -1206,12 +1206,16 @@ pack_rows_sb_kernel(const float* __restrict__ src, int64_t ld, char* __restrict_
 }
 
 // env-major SoA observations [T][F][ld] -> SB rows [T * n_pad][Kp] (features beyond F and envs beyond n zero-filled).
-// thread = (t, panel, 4-feature group, row): reads 4 SoA rows at one env (coalesced over envs), writes 16 B / 8 B.
+// thread = (t, panel, 8-feature group, row): reads 8 SoA rows at one env (coalesced over envs) and writes one full
+// 16-byte chunk per plane (FP16 kind; two per plane for TF32): 512 contiguous bytes per warp and store instruction.
+// Critic shortcut (cinert != nullptr): features 80..447 are the privileged dump cinert[1:] (230) | cvel[1:] (138)
+// (train.py:1405-1413) -- they are read straight from the recorded state, so the observation kernel never writes them
+// to the SoA buffer and this kernel never reads them back (saves 2 x 1.5 KB of HBM traffic per env-step).
 template <int KIND>
 __global__ void __launch_bounds__(256)
 pack_soa_sb_kernel(const float* __restrict__ soa, int F, int64_t ld, char* __restrict__ sb, int64_t n, int64_t n_pad,
-                   int Kp, int64_t T) {
-  const int kq = Kp / 4;
+                   int Kp, int64_t T, const float* __restrict__ cinert, const float* __restrict__ cvel) {
+  const int kq = Kp / 8;
   const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
   const int64_t rows = T * n_pad;
   if (idx >= rows * kq) return;
@@ -1220,13 +1224,24 @@ pack_soa_sb_kernel(const float* __restrict__ soa, int F, int64_t ld, char* __res
   const int kc = rem / kPanelRows, r = rem % kPanelRows;
   const int64_t row = panel * kPanelRows + r;
   const int64_t t = row / n_pad, e = row - t * n_pad;
-  float x[4] = {0.f, 0.f, 0.f, 0.f};
-  if (e < n) {
-    const float* p = soa + (t * F + kc * 4) * ld + e;
+  float x[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = (kc * 4 + i < F) ? __ldcs(p + i * ld) : 0.0f;
+  for (int i = 0; i < 8; ++i) {
+    const int f = kc * 8 + i;
+    x[i] = 0.0f;
+    if (e < n && f < F) {
+      const float* p;
+      if (cinert && f >= 80 && f < 448) {
+        const int c = f - 80;
+        p = c < 230 ? cinert + (t * (10 * KBS_NBODY) + 10 + c) * ld : cvel + (t * (6 * KBS_NBODY) + 6 + (c - 230)) * ld;
+      } else {
+        p = soa + (t * F + f) * ld;
+      }
+      x[i] = __ldcs(p + e);
+    }
   }
-  sb_store4<kPanelRows, KIND>(sb, row, kc * 4, Kp / kbs_block_k(KIND), x);
+  const float x0[4] = {x[0], x[1], x[2], x[3]}, x1[4] = {x[4], x[5], x[6], x[7]};
+  sb_store_split8<kPanelRows, KIND>(sb, row, kc * 8, Kp / kbs_block_k(KIND), sb_split4<KIND>(x0), sb_split4<KIND>(x1), false);
 }
 
 inline int64_t pad_rows(int64_t n) { return (n + kPanelRows - 1) / kPanelRows * kPanelRows; }
@@ -1470,7 +1485,7 @@ int64_t kbs_tc_obs_sb_floats(const kbs_handle* h, int net, int64_t n, int64_t T)
 
 // obs_soa[k]: [T][num_in][ld] observations of net k; obs_sb[k]: staging (kbs_tc_obs_sb_floats); x_sb_all[k]: [T] x act SB.
 int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, float* const* obs_sb, float* const* x_sb_all,
-                          int64_t ld, int64_t n, int64_t T, cudaStream_t st) {
+                          int64_t ld, int64_t n, int64_t T, cudaStream_t st, const float* cinert, const float* cvel) {
   const int H = h->p.hidden_size, kind = tc_kind(h);
   const int64_t np = pad_rows(n);
   LayerArgs2 a2{};
@@ -1478,13 +1493,15 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
     const KbsNet& N = h->net[k];
     if (!N.packed || !N.tc_image) return KBS_E_STATE;
     const int Kp = proj_kp(h, k);
-    const int64_t total = T * np * (Kp / 4);
+    const int64_t total = T * np * (Kp / 8);
     const unsigned gb = unsigned((total + 255) / 256);
     char* osb = reinterpret_cast<char*>(obs_sb[k]);
+    const float* ci = (k == KBS_NET_CRITIC) ? cinert : nullptr;
+    const float* cv = (k == KBS_NET_CRITIC) ? cvel : nullptr;
     if (kind == KBS_KIND_TF32)
-      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T)));
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv)));
     else
-      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T)));
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv)));
     LayerArgs& a = a2.net[k];
     a.x_sb = osb;
     a.h_sb_in = osb;

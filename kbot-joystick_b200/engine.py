@@ -127,6 +127,25 @@ class KbotStep:
                                           L.ptr(critic_obs), n,
                                           _stream()), "kbs_observations")
 
+    def mirror_observations(self, state: dict, computed, command, actor_obs=None, critic_obs=None, command_out=None,
+                            n_envs: int | None = None) -> None:
+        """mirror_obs / mirror_cmd + the actor / critic concatenations (train.py:1463-1481, 1584-1756) for T stored steps:
+        every array is time-major [T][rows][ld]."""
+        T, ld = computed.shape[0], computed.shape[-1]
+        sv = _view(L.KbsStateView, STATE_ROWS, state, ld)
+        L.check(self.lib.kbs_mirror_observations(self._h, C.byref(sv), L.ptr(computed), L.ptr(command), L.ptr(actor_obs),
+                                                 L.ptr(critic_obs), L.ptr(command_out), T, n_envs or ld, _stream()),
+                "kbs_mirror_observations")
+
+    def mirror_joints(self, x, out=None, n_envs: int | None = None):
+        """mirror_joints (train.py:1574-1582) on [T][20][ld] (or [20][ld])."""
+        ld = x.shape[-1]
+        T = x.shape[0] if x.dim() == 3 else 1
+        if out is None:
+            out = torch.empty_like(x)
+        L.check(self.lib.kbs_mirror_joints(self._h, L.ptr(x), L.ptr(out), T, ld, n_envs or ld, _stream()), "kbs_mirror_joints")
+        return out
+
     def command_update(self, command, mode, u6, u_arms, u_switch=None, n_envs: int | None = None) -> None:
         ld = command.shape[-1]
         L.check(self.lib.kbs_command_update(self._h, L.ptr(command), L.ptr(u_switch), L.ptr(mode), L.ptr(u6),

@@ -48,3 +48,6 @@ NOISY_OBSERVATION_NAMES = ("noisy_biased_joint_position", "noisy_joint_velocity"
 # per-network FLOPs per env-step at hidden size H: 2*(in*H + depth*8*H*H + H*out)
 def net_flops(num_in: int, num_out: int, hidden: int = 256, depth: int = 2) -> int:
     return 2 * (num_in * hidden + depth * 8 * hidden * hidden + hidden * num_out)
+
+# mirror_joints (train.py:1574-1582): out[j] = -in[MIRROR_JOINT_SRC[j]] -- legs swapped, arm halves NOT (as written)
+MIRROR_JOINT_SRC = (5, 6, 7, 8, 9, 0, 1, 2, 3, 4, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19)

@@ -144,15 +144,25 @@ class HumanoidWalkingTask:
             m = e.ppo_variables(mirror["actor_obs"], trajectory["action"], trajectory["done"], model_carry["actor_mirror"],
                                 model_carry["lpf_params_mirror"], mirror.get("critic_obs"), model_carry.get("critic_mirror"),
                                 want_std=False, want_mean=True, n_envs=n_envs)
-            dm = self.mirror_joints(m["mean"])
+            dm = e.mirror_joints(m["mean"].contiguous(), n_envs=n_envs)
             ppo["aux_losses"] = {"action_mirror_loss": ((out["mean"] - dm) ** 2).mean(dim=1),
                                  "value_mirror_loss": (out["values"] - m["values"]) ** 2}
         return ppo, model_carry
 
-    @staticmethod
-    def mirror_joints(j):
-        """train.py:1574-1582 on `[..., 20, ld]`: negate all, swap the LEG halves only (as written)."""
-        return -torch.cat([j[..., 5:10, :], j[..., 0:5, :], j[..., 10:15, :], j[..., 15:20, :]], dim=-2)
+    def mirror_joints(self, j, n_envs: int | None = None):
+        """train.py:1574-1582 on `[T, 20, ld]`: negate all, swap the LEG halves only (as written)."""
+        return self.engine.mirror_joints(j.contiguous(), n_envs=n_envs)
+
+    def mirror_obs(self, trajectory_state: dict, computed, command, n_envs: int | None = None) -> dict:
+        """mirror_obs + mirror_cmd (train.py:1584-1756) -> the `mirror` argument of get_ppo_variables.
+        computed: [T, 78, ld] raw observations stored at rollout time (kbs_observations `computed`)."""
+        T, ld = computed.shape[0], computed.shape[-1]
+        out = {"actor_obs": torch.empty((T, spec.ACTOR_OBS, ld), device=computed.device),
+               "critic_obs": torch.empty((T, spec.CRITIC_OBS, ld), device=computed.device),
+               "command": torch.empty((T, spec.NUM_COMMANDS, ld), device=computed.device)}
+        self.engine.mirror_observations(trajectory_state, computed, command, out["actor_obs"], out["critic_obs"],
+                                        out["command"], n_envs=n_envs)
+        return out
 
     # ---- actuators / terminations / rewards / GAE -----------------------------------------------------------------------
     def get_actuators(self, action, state: dict, episode: dict | None = None, n_envs: int | None = None):

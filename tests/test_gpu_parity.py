@@ -62,6 +62,38 @@ def test_observations(eng, dev, N):
     exact(S(aobs[48], N), O.zero_cmd_mask(b.cmd0_np).astype(np.float32), "zero_cmd flag")
 
 
+@pytest.mark.parametrize("T,N", [(3, 50), (2, 1001)])
+def test_mirror_observations(eng, dev, T, N):
+    """X1: mirror_obs / mirror_cmd / mirror_joints (train.py:1574-1756) + the concatenations on the mirrored
+    observations, from what a rollout stores (raw observations incl. the noisy twins, state, commands)."""
+    b = Batch(150 + N, T, N, dev)
+    ld = b.ld
+    comp = torch.zeros((T, 78, ld), device=dev)
+    cmd_np = np.stack([b.cmd0_np * (1.0 + 0.25 * t) for t in range(T)]).astype(np.float32)
+    cmd = synth.to_soa(cmd_np, 1, dev)
+    ref_a, ref_c, ref_cmd = [], [], []
+    for t in range(T):
+        eng.observations(b.state_at(t), cmd[t], b.noise_at(t), b.episode, None, comp[t], None, None, N)
+        o, _ = O.get_observations(b.np_state_at(t), b.np_noise_at(t), b.np["episode"], None, P)
+        mo, mc = O.mirror_obs(o), O.mirror_cmd(cmd_np[t])
+        ref_a.append(O.actor_obs_from_dict(mo, mc))
+        ref_c.append(O.critic_obs_from_dict(mo, mc))
+        ref_cmd.append(mc)
+    aobs = torch.full((T, 65, ld), float("nan"), device=dev)
+    cobs = torch.full((T, 475, ld), float("nan"), device=dev)
+    cout = torch.full((T, 16, ld), float("nan"), device=dev)
+    eng.mirror_observations(b.state, comp, cmd, aobs, cobs, cout, n_envs=N)
+    close(S(aobs, N, (65,)), np.stack(ref_a), "mirrored actor_obs", atol=1e-5)
+    close(S(cobs, N, (475,)), np.stack(ref_c), "mirrored critic_obs", atol=1e-5)
+    exact(S(cout, N, (16,)), np.stack(ref_cmd), "mirror_cmd")
+    # pure sign/permutation rows are bit-exact
+    exact(S(cobs[:, 80:448], N, (368,)), np.stack(ref_c)[..., 80:448], "mirrored cinert/cvel dump")
+    j = torch.randn((T, 20, ld), device=dev)
+    exact(S(eng.mirror_joints(j, n_envs=N), N, (20,)), O.mirror_joints(S(j, N, (20,))), "mirror_joints")
+    # involution: mirroring twice is the identity (size-independent property)
+    exact(S(eng.mirror_joints(eng.mirror_joints(j, n_envs=N), n_envs=N), N, (20,)), S(j, N, (20,)), "mirror_joints twice")
+
+
 def test_observations_without_noise_twins_equal_clean(eng, dev):
     b = Batch(7, 1, 64, dev)
     aobs = torch.zeros((65, b.ld), device=dev)

@@ -116,16 +116,15 @@ def test_task_mirror_exposes_reference_plugin_surface():
 
     for name in ("get_model", "get_initial_model_carry", "get_observations", "get_commands", "get_rewards",
                  "get_terminations", "get_actuators", "run_actor", "run_critic", "sample_action", "get_ppo_variables",
-                 "mirror_joints"):                                    # train.py:1091-1582
+                 "mirror_joints", "mirror_obs"):                                    # train.py:1091-1582
         assert callable(getattr(HumanoidWalkingTask, name)), name
     assert "argmax" in inspect.signature(HumanoidWalkingTask.sample_action).parameters      # train.py:1555
     c = HumanoidWalkingTaskConfig()
     assert (c.hidden_size, c.num_envs, c.rollout_steps, c.gamma, c.lam) == (256, 4096, 100, 0.94, 0.94)   # train.py:1761-1776
-    import torch
+    from kbot_joystick_b200 import spec
 
-    j = torch.arange(20.0).reshape(20, 1)
-    np.testing.assert_array_equal(HumanoidWalkingTask.mirror_joints(j)[:, 0].numpy(),
-                                  O.mirror_joints(np.arange(20, dtype=np.float32)))
+    j = np.arange(20, dtype=np.float32)
+    np.testing.assert_array_equal(-j[list(spec.MIRROR_JOINT_SRC)], O.mirror_joints(j))   # the kernel's index table
 
 
 def test_env_shard_partition():
