@@ -218,12 +218,16 @@ __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float(r);
 }
 // byte offset of the 16-byte chunk holding (row, k) in plane `part`
-template <int R, int KIND>
+// WB = weight-block variant: [k-block][chunk][hi|lo][row][16 B], i.e. the hi and lo rows of one k-chunk are adjacent, so
+// ONE N = 2R descriptor (LBO = 2R*16 B) presents [W_hi | W_lo] to the tensor core and x_hi . [W_hi | W_lo]^T comes out of a
+// single instruction (A is streamed from shared memory once instead of twice).
+template <int R, int KIND, bool WB = false>
 __device__ __forceinline__ size_t sb_chunk_offset(int64_t row, int k, int kblocks, int part) {
   constexpr int E = kbs_chunk_elems(KIND);
   const int64_t panel = row / R;
   const int r = int(row - panel * R);
   const int b = k / (4 * E), kc = (k / E) & 3;
+  if (WB) return ((((size_t(panel) * kblocks + b) * 4 + kc) * 2 + part) * size_t(R) + size_t(r)) * 16;
   return ((((size_t(panel) * kblocks + b) * 2 + part) * 4 + kc) * size_t(R) + size_t(r)) * 16;
 }
 // split 4 consecutive K values into the (hi, lo) planes: 16 B each for TF32, 8 B each for F16
@@ -254,16 +258,16 @@ __device__ __forceinline__ KbsSplit4 sb_split4(const float (&x)[4]) {
   }
   return s;
 }
-template <int R, int KIND>
+template <int R, int KIND, bool WB = false>
 __device__ __forceinline__ void sb_store_split(void* __restrict__ sb, int64_t row, int k, int kblocks, const KbsSplit4& s) {
   char* base = reinterpret_cast<char*>(sb);
   if (KIND == KBS_KIND_TF32) {
-    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 0)) = s.hi;
-    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1)) = s.lo;
+    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND, WB>(row, k, kblocks, 0)) = s.hi;
+    *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND, WB>(row, k, kblocks, 1)) = s.lo;
   } else {
     const int sub = (k & 4) * 2;   // byte offset of the half-chunk inside the 16-byte chunk
-    *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 0) + sub) = make_uint2(s.hi.x, s.hi.y);
-    *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1) + sub) = make_uint2(s.lo.x, s.lo.y);
+    *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND, WB>(row, k, kblocks, 0) + sub) = make_uint2(s.hi.x, s.hi.y);
+    *reinterpret_cast<uint2*>(base + sb_chunk_offset<R, KIND, WB>(row, k, kblocks, 1) + sub) = make_uint2(s.lo.x, s.lo.y);
   }
 }
 // 8 consecutive K values (k % 8 == 0) from two splits: FP16 kind = ONE 16-byte chunk per plane; zero = store zeros
@@ -285,9 +289,9 @@ __device__ __forceinline__ void sb_store_split8(void* __restrict__ sb, int64_t r
   }
 }
 // store 4 consecutive K values (k % 4 == 0)
-template <int R, int KIND>
+template <int R, int KIND, bool WB = false>
 __device__ __forceinline__ void sb_store4(void* __restrict__ sb, int64_t row, int k, int kblocks, const float (&x)[4]) {
-  sb_store_split<R, KIND>(sb, row, k, kblocks, sb_split4<KIND>(x));
+  sb_store_split<R, KIND, WB>(sb, row, k, kblocks, sb_split4<KIND>(x));
 }
 #endif  // __CUDACC__
 

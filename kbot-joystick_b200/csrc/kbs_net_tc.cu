@@ -96,12 +96,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor: D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 // (F16 operands: format code 0, kind::f16, K = 16 per instruction)
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kTileCols >> 3) << 17) |
-                                (uint32_t(kPanelRows >> 4) << 24);
-constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | (uint32_t(kTileCols >> 3) << 17) |
-                               (uint32_t(kPanelRows >> 4) << 24);
+template <int N>
+__host__ __device__ constexpr uint32_t idesc_tf32() { return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(kPanelRows >> 4) << 24); }
+template <int N>
+__host__ __device__ constexpr uint32_t idesc_f16() { return (1u << 4) | (0u << 7) | (0u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(kPanelRows >> 4) << 24); }
 
-template <int KIND>
+template <int KIND, int N>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   if (KIND == KBS_KIND_TF32) {
     asm volatile(
@@ -109,14 +109,14 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdescTf32), "r"(accumulate) : "memory");
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc_tf32<N>()), "r"(accumulate) : "memory");
   } else {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdescF16), "r"(accumulate) : "memory");
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc_f16<N>()), "r"(accumulate) : "memory");
   }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -143,6 +143,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                : "r"(taddr));
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -304,31 +314,31 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
           const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
           const uint32_t sb = sa + kABlockBytes;
           // [part][chunk][128 rows][16 B]: part stride 8 KB, chunk stride 2 KB (A and B alike); k-step stride 4 KB
+          // A block [part][chunk][128 rows][16 B]: part stride 8 KB, chunk stride 2 KB, k-step (2 chunks) 4 KB.
+          // B block [chunk][hi|lo][128 rows][16 B]: chunk stride 4 KB (LBO), k-step 8 KB; hi rows then lo rows = one
+          // 256-row operand, so x_hi . [W_hi | W_lo]^T is ONE N = 256 instruction into [main | correction] columns.
           if (warp == 0) {
-            const uint64_t a0 = umma_desc(sa, 2048, 128), b0 = umma_desc(sb, 2048, 128);
-            const uint64_t a1 = umma_desc(sa + 4096, 2048, 128), b1 = umma_desc(sb + 4096, 2048, 128);
+            const uint64_t a0 = umma_desc(sa, 2048, 128), b0 = umma_desc(sb, 4096, 128);
+            const uint64_t a1 = umma_desc(sa + 4096, 2048, 128), b1 = umma_desc(sb + 8192, 4096, 128);
             if (elect_one()) {
               if (tr && g == 0) tr[2] = clock64();        // first stage landed
               if (tr2 && g < 64) tr2[128 + g] = clock64();
-              umma<KIND>(d_main, a0, b0, b != 0);
-              umma<KIND>(d_main, a1, b1, 1);
+              umma<KIND, 2 * kTileCols>(d_main, a0, b0, b != 0);
+              if (b == 0) { tc_fence_before(); mbar_arrive(&corr_init[buf]); }   // the correction columns are initialised
+              umma<KIND, 2 * kTileCols>(d_main, a1, b1, 1);
               umma_commit(&empty[s]);          // frees the stage when these MMAs have read it
               if (tr2 && g < 64) tr2[192 + g] = clock64();
             }
           } else {
             const int ks = warp - 1;
-            const uint64_t a_hi = umma_desc(sa + ks * 4096, 2048, 128);
             const uint64_t a_lo = umma_desc(sa + 8192 + ks * 4096, 2048, 128);
-            const uint64_t b_hi = umma_desc(sb + ks * 4096, 2048, 128);
-            const uint64_t b_lo = umma_desc(sb + 8192 + ks * 4096, 2048, 128);
-            if (b == 0 && warp == 2) {            // warp 1's accumulate = 0 MMA must be queued first
+            const uint64_t b_hi = umma_desc(sb + ks * 8192, 4096, 128);
+            if (b == 0) {                         // warp 0's accumulate = 0 MMA must be queued first
               mbar_wait(&corr_init[buf], (j >> 1) & 1);
               tc_fence_after();
             }
             if (elect_one()) {
-              umma<KIND>(d_corr, a_lo, b_hi, (b | ks) != 0);
-              if (b == 0 && warp == 1) { tc_fence_before(); mbar_arrive(&corr_init[buf]); }
-              umma<KIND>(d_corr, a_hi, b_lo, 1);
+              umma<KIND, kTileCols>(d_corr, a_lo, b_hi, 1);
               umma_commit(&empty[s]);
             }
           }
@@ -629,11 +639,24 @@ rollout_head_kernel(const __grid_constant__ kbs_params P, const __grid_constant_
 // CTA takes its items in the global order, so the earliest unfinished item can always run: no deadlock.  Polling is
 // bounded: after ~2^22 polls a CTA records an error in `status` and stops waiting.
 constexpr int kPMaxDepth = 2;            // bias table in shared memory: [2 nets][kPMaxDepth][4H] + head [2][128]
-constexpr int kPBiasFloats = 2 * kPMaxDepth * kMaxBias + 2 * kTileCols;
+constexpr int kPBiasFloats = 2 * kPMaxDepth * kMaxBias + 2 * 256;
 constexpr int kEpiWarpsP = 16;
-constexpr int kThreadsP = 32 * (kIssuers + kProducers + kEpiWarpsP + 2);   // + dependency poller warp + publisher warp
+constexpr int kIssuersP = 1;
+constexpr int kProducersP = 1;           // one 16 KB + one 32 KB request per 878-cycle stage: one warp keeps up
+constexpr int kThreadsP = 32 * (kIssuersP + kProducersP + kEpiWarpsP + 2);   // + dependency poller warp + publisher warp = 640
 constexpr int kPHeadPartFloats = 4 * kPanelRows * 2;
-constexpr int kPSmemBytes = kStages * kStageBytes + (kPBiasFloats + kPHeadPartFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
+// Tile of the persistent kernel: 128 envs x 256 gate columns (64 hidden units).  MEASURED (tools/stage_pipe_bench.cu): one
+// thread issues a tcgen05.mma only every ~110-128 cycles whatever its size, and a tcgen05.commit costs about as much, so
+// only N = 256 instructions (128 tensor cycles each) keep the tensor pipe busy: 3 x N = 256 per k-step (hi.hi -> main,
+// lo.hi + hi.lo -> correction) = 878 cycles per stage against 768 of tensor work, where the N = 128 tile ran at 643-720
+// cycles for 384.  Main + correction of one tile fill the 512 TMEM columns: single-buffered, the epilogue pulls the
+// accumulators into registers and hands TMEM back before doing the cell math.
+constexpr int kTileColsP = 256;
+constexpr int kUnitsPerTileP = kTileColsP / 4;
+constexpr int kBBlockBytesP = 2 * 4 * kTileColsP * 16;          // [chunk][hi|lo][256 rows][16 B] = 32 KB
+constexpr int kStageBytesP = kABlockBytes + kBBlockBytesP;      // 48 KB
+constexpr int kStagesP = 4;              // power of two that divides every item's stage count (8 or 16 at H = 256)
+constexpr int kPSmemBytes = kStagesP * kStageBytesP + (kPBiasFloats + kPHeadPartFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
 
 struct PNet {
   const char* x_sb_all;            // [T] x sbb: layer-0 inputs (input projection of every step)
@@ -721,13 +744,13 @@ __global__ void __launch_bounds__(kThreadsP, 1)
 rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_constant__ PArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);   // [net][layer][kMaxBias] then head [net][128]
+  float* bias_s = reinterpret_cast<float*>(smem + kStagesP * kStageBytesP);   // [net][layer][kMaxBias] then head [net][256]
   float* bias_head_s = bias_s + 2 * kPMaxDepth * kMaxBias;
   float* head_part = bias_s + kPBiasFloats;                                 // [4 joint groups][128 rows][2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + (kPBiasFloats + kPHeadPartFloats) * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesP * kStageBytesP + (kPBiasFloats + kPHeadPartFloats) * 4);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kStages;
-  uint64_t* acc_full = bars + 2 * kStages;
+  uint64_t* empty = bars + kStagesP;
+  uint64_t* acc_full = bars + 2 * kStagesP;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* corr_init = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_init + 2);
@@ -740,13 +763,15 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
   const int H = args.H;
   constexpr int kBlk = kbs_block_k(KIND);
   const int kb = H / kBlk;
-  long long* tr = args.trace ? args.trace + size_t(blockIdx.x) * 12 : nullptr;
+  long long* tr = args.trace ? args.trace + size_t(blockIdx.x) * 16 : nullptr;
   const long long t_start = clock64();
+  unsigned long long gt_start = 0;
+  if (tr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kIssuers); }
+    for (int s = 0; s < kStagesP; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], kIssuers); mbar_init(&acc_empty[b], kEpiWarpsP); mbar_init(&corr_init[b], 1);
+      mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarpsP);
     }
     *dep_seq = 0;
     *epi_done = 0u;
@@ -762,7 +787,7 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kIssuers + kProducers + kEpiWarpsP + 1) {
+  if (warp == kIssuersP + kProducersP + kEpiWarpsP + 1) {
     if (lane == 0) {
       // ===== publisher: the gpu-scope fence that makes an item's stores visible costs ~2 K cycles of store-ack latency.
       // The epilogue warps therefore only signal "stored" in shared memory (release.cta) and move on; this thread
@@ -783,7 +808,7 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
       }
     }
     __syncwarp();
-  } else if (warp == kIssuers + kProducers + kEpiWarpsP) {
+  } else if (warp == kIssuersP + kProducersP + kEpiWarpsP) {
     if (lane == 0) {
       // ===== dependency poller: runs ahead of the producers through the item list, so the L2 round trips of the
       // counter polls and the fence stay off the load pipeline's critical path; publishes "items 0..j-1 may start" =====
@@ -798,11 +823,12 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
       if (tr) { tr[1] = waited; tr[2] = j; }
     }
     __syncwarp();
-  } else if (warp >= kIssuers && warp < kIssuers + kProducers) {
+  } else if (warp >= kIssuersP && warp < kIssuersP + kProducersP) {
     if (lane < 2) {
       // ===== producers (see lstm_layer_tc_kernel): lane 0 = activation block, lane 1 = weight block of the stage =====
       uint32_t g = 0;
       int j = 0;
+      long long pw[3] = {0, 0, 0};
       for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
         const PItem it = p_decode(args, gi);
         if (!it.valid) continue;
@@ -815,7 +841,7 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
           xa = (it.layer == 0 ? N.x_sb_all + size_t(it.t) * args.sbb
                               : N.xmid + size_t((it.layer - 1) * 2 + (it.t & 1)) * args.sbb) + poff;
           ha = N.hsb + size_t(it.layer * 2 + (it.t & 1)) * args.sbb + poff;
-          wb = N.w_sb[it.layer] + size_t((args.dbg & 16) ? (blockIdx.x + it.t) % args.tiles : it.tile) * kb_total * kBBlockBytes;
+          wb = N.w_sb[it.layer] + size_t((args.dbg & 16) ? (blockIdx.x + it.t) % args.tiles : it.tile) * kb_total * kBBlockBytesP;
         } else {
           xa = N.xmid + size_t((args.depth - 1) * 2 + (it.t & 1)) * args.sbb + poff;
           ha = xa;
@@ -823,175 +849,189 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
         }
         ++j;
         if (lane == 0) {
+          const long long d0 = tr ? clock64() : 0;
           while (*dep_seq < j) { }
           __threadfence_block();
           asm volatile("fence.proxy.async;" ::: "memory");    // the activation blocks were written with generic stores
+          if (tr) pw[2] += clock64() - d0;
         }
         for (int b = 0; b < kb_total; ++b, ++g) {
-          if (int(g % kProducers) != warp - kIssuers) continue;
-          const int s = g % kStages;
+          const int s = g % kStagesP;
+          // probes: 32 = token weight copies, 128 = no weight request at all, 256 = half-size activation request
+          const uint32_t wbytes = (args.dbg & 128) ? 0u : (args.dbg & 32) ? 16u : uint32_t(kBBlockBytesP);
+          const uint32_t abytes = (args.dbg & 256) ? uint32_t(kABlockBytes / 2) : uint32_t(kABlockBytes);
+          long long p0 = 0, p1 = 0;
           if (lane == 0) {
-            mbar_wait(&empty[s], ((g / kStages) & 1) ^ 1);
-            mbar_expect_tx(&full[s], 2 * kABlockBytes);
+            if (tr) p0 = clock64();
+            mbar_wait(&empty[s], ((g / kStagesP) & 1) ^ 1);
+            if (tr) p1 = clock64();
+            mbar_expect_tx(&full[s], abytes + wbytes);
           }
           __syncwarp(0x3);
-          uint8_t* sa = smem + size_t(s) * kStageBytes;
+          uint8_t* sa = smem + size_t(s) * kStageBytesP;
           const char* src = lane == 0 ? ((b < kb_x) ? xa + size_t(b) * kABlockBytes : ha + size_t(b - kb_x) * kABlockBytes)
-                                      : wb + size_t(b) * kBBlockBytes;
-          bulk_g2s(sa + lane * kABlockBytes, src, kABlockBytes, &full[s]);
+                                      : wb + size_t(b) * kBBlockBytesP;
+          if (lane == 0 || wbytes) bulk_g2s(sa + lane * kABlockBytes, src, lane == 0 ? abytes : wbytes, &full[s]);
+          if (tr && lane == 0) { pw[0] += p1 - p0; pw[1] += clock64() - p1; }
         }
       }
+      if (tr && lane == 0 && warp == kIssuersP) { tr[12] = pw[0]; tr[13] = pw[1]; tr[14] = pw[2]; }
     }
     __syncwarp();
-  } else if (warp < kIssuers) {
-    // ===== MMA issuers (see lstm_layer_tc_kernel) =====
-    uint32_t g = 0;
+  } else if (warp < kIssuersP) {
+    // ===== MMA issuer (warp 0; warps 1, 2 idle here).  A power-of-two ring with the stage loop unrolled over it (stage index,
+    // barrier addresses and parities are compile-time / one register) and descriptors = one 64-bit add from a base keep
+    // the issuing thread's own instruction stream short. =====
+    // One thread issues everything, in order: per stage 2 k-steps x (x_hi.W_hi -> main, x_lo.W_hi -> correction,
+    // x_hi.W_lo -> correction), all N = 256, and ONE tcgen05.commit (three issuing warps = three commits per stage were
+    // slower: every tcgen05 instruction costs the issue path ~110 cycles).  In-order issue from one thread also fixes
+    // the accumulation order: results are bitwise reproducible run to run.
     int j = 0;
+    uint32_t ph = 0;                              // parity of the full[] barriers: flips after every pass over the ring
     long long waited = 0, waited_acc = 0;
-    for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
-      const PItem it = p_decode(args, gi);
-      if (!it.valid) continue;
-      const int kb_total = it.kind == 0 ? 2 * kb : kb;
-      const int buf = j & 1;
-      const long long e0 = tr ? clock64() : 0;
-      mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
-      if (tr) waited_acc += clock64() - e0;
-      tc_fence_after();
-      const uint32_t d_main = tmem_base + buf * (2 * kTileCols), d_corr = d_main + kTileCols;
-      for (int b = 0; b < kb_total; ++b, ++g) {
-        const int s = g % kStages;
-        const long long w0 = tr ? clock64() : 0;
-        mbar_wait(&full[s], (g / kStages) & 1);
-        if (tr) waited += clock64() - w0;
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
-        const uint32_t sb = sa + kABlockBytes;
-        if (warp == 0) {
-          const uint64_t a0 = umma_desc(sa, 2048, 128), b0 = umma_desc(sb, 2048, 128);
-          const uint64_t a1 = umma_desc(sa + 4096, 2048, 128), b1 = umma_desc(sb + 4096, 2048, 128);
-          if (elect_one()) {
-            umma<KIND>(d_main, a0, b0, b != 0);
-            umma<KIND>(d_main, a1, b1, 1);
-            umma_commit(&empty[s]);
-          }
-        } else {
-          const int ks = warp - 1;
-          const uint64_t a_hi = umma_desc(sa + ks * 4096, 2048, 128);
-          const uint64_t a_lo = umma_desc(sa + 8192 + ks * 4096, 2048, 128);
-          const uint64_t b_hi = umma_desc(sb + ks * 4096, 2048, 128);
-          const uint64_t b_lo = umma_desc(sb + 8192 + ks * 4096, 2048, 128);
-          if (b == 0 && warp == 2) {
-            mbar_wait(&corr_init[buf], (j >> 1) & 1);
-            tc_fence_after();
-          }
-          if (elect_one()) {
-            umma<KIND>(d_corr, a_lo, b_hi, (b | ks) != 0);
-            if (b == 0 && warp == 1) { tc_fence_before(); mbar_arrive(&corr_init[buf]); }
-            umma<KIND>(d_corr, a_hi, b_lo, 1);
-            umma_commit(&empty[s]);
-          }
-        }
-        __syncwarp();
-      }
-      if (elect_one()) umma_commit(&acc_full[buf]);
-      __syncwarp();
-      ++j;
-    }
-    if (tr && warp == 0 && lane == 0) { tr[3] = waited; tr[7] = waited_acc; }
-  } else {
-    // ===== epilogue: 16 warps; warp % 4 = TMEM lane quarter (rows), the other two bits = which 8 of the tile's 32 hidden
-    // units (LSTM items) or which 5 of the 20 joints (actor head items).  The cell math is latency-bound (MUFU chains),
-    // so four warps per scheduler instead of two is what shortens it (measured: 8.2 K cycles per item with 8 warps).
-    const int ew = warp - kIssuers - kProducers;
     {
-      const int et = threadIdx.x - 32 * (kIssuers + kProducers);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t a_hi = umma_desc(smem_base, 2048, 128);                      // A block [part][chunk][128 rows][16 B]
+      const uint64_t a_lo = a_hi + (8192 >> 4);
+      const uint64_t b_hi = umma_desc(smem_base + kABlockBytes, 8192, 128);       // B block [chunk][hi|lo][256 rows][16 B]
+      const uint64_t b_lo = b_hi + (4096 >> 4);
+      constexpr uint64_t kStageDesc = uint64_t(kStageBytesP) >> 4;                // descriptor address units are 16 B
+      constexpr uint64_t kAStep = 4096 >> 4, kBStep = 16384 >> 4;                 // k-step (2 chunks) strides
+      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+        const PItem it = p_decode(args, gi);
+        if (!it.valid) continue;
+        const int kb_total = it.kind == 0 ? 2 * kb : kb;
+        const long long e0 = tr ? clock64() : 0;
+        mbar_wait(&acc_empty[0], (j & 1) ^ 1);    // the epilogue of the previous item has pulled the accumulators
+        if (tr) waited_acc += clock64() - e0;
+        tc_fence_after();
+        const uint32_t d_main = tmem_base, d_corr = tmem_base + kTileColsP;
+        for (int b0 = 0; b0 < kb_total; b0 += kStagesP) {
+#pragma unroll
+          for (int st = 0; st < kStagesP; ++st) {
+            const long long w0 = tr ? clock64() : 0;
+            mbar_wait(&full[st], ph);
+            if (tr) waited += clock64() - w0;
+            tc_fence_after();
+            const uint64_t so = st * kStageDesc;
+            if (elect_one()) {
+              if (!(args.dbg & 64)) {
+                const uint32_t acc = (b0 | st) != 0;
+                umma<KIND, kTileColsP>(d_main, a_hi + so, b_hi + so, acc);
+                umma<KIND, kTileColsP>(d_corr, a_lo + so, b_hi + so, acc);
+                umma<KIND, kTileColsP>(d_corr, a_hi + so, b_lo + so, 1);
+                umma<KIND, kTileColsP>(d_main, a_hi + so + kAStep, b_hi + so + kBStep, 1);
+                umma<KIND, kTileColsP>(d_corr, a_lo + so + kAStep, b_hi + so + kBStep, 1);
+                umma<KIND, kTileColsP>(d_corr, a_hi + so + kAStep, b_lo + so + kBStep, 1);
+              }
+              umma_commit(&empty[st]);            // frees the stage when the MMAs issued so far have read it
+            }
+            __syncwarp();
+          }
+          ph ^= 1;
+        }
+        if (elect_one()) umma_commit(&acc_full[0]);
+        __syncwarp();
+        ++j;
+      }
+      if (tr && lane == 0) { tr[3] = waited; tr[7] = waited_acc; }
+    }
+  } else {
+    // ===== epilogue: 16 warps; warp % 4 = TMEM lane quarter (rows), grp = the other two bits = which 16 of the tile's 64
+    // hidden units (LSTM items: columns [grp][gate i,f,g,o][16 units]) or which 5 of the 20 joints (actor head items).
+    const int ew = warp - kIssuersP - kProducersP;
+    {
+      const int et = threadIdx.x - 32 * (kIssuersP + kProducersP);
       for (int k = 0; k < args.nets; ++k) {
         for (int l = 0; l < args.depth; ++l)
           for (int i = et * 4; i < 4 * H; i += 32 * kEpiWarpsP * 4)
             *reinterpret_cast<float4*>(bias_s + (k * kPMaxDepth + l) * kMaxBias + i) =
                 *reinterpret_cast<const float4*>(args.net[k].bias_t[l] + i);
-        if (et < kTileCols) bias_head_s[k * kTileCols + et] = args.net[k].bias_head[et];
+        if (et < kTileColsP) bias_head_s[k * kTileColsP + et] = args.net[k].bias_head[et];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarpsP) : "memory");
     }
-    const int q4 = warp & 3, grp = ew >> 2, c2 = grp >> 1, sub = grp & 1;
+    const int q4 = warp & 3, grp = ew >> 2;
     const int r = q4 * 32 + lane;
     constexpr float kCorr = (KIND == KBS_KIND_F16) ? (1.0f / kKbsF16LoScale) : 1.0f;
     const int64_t ld = args.ld;
-    const int colq = c2 * 64 + sub * 8;          // this thread's 8 columns of gate g start at colq + 16 g
+    const int colq = grp * 64;                   // this thread's 16 columns of gate g start at colq + 16 g
     int j = 0;
     long long epi_cyc[2] = {0, 0}, epi_wait = 0, ph[4] = {0, 0, 0, 0};
     for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
       const PItem it = p_decode(args, gi);
       if (!it.valid) continue;
       const PNet& N = args.net[it.net];
-      const int buf = j & 1;
       const int64_t R = int64_t(it.panel) * kPanelRows + r;
       const bool live = R < args.n;
-      const int u0 = it.tile * kUnitsPerTile + c2 * 16 + sub * 8;
+      const int u0 = it.tile * kUnitsPerTileP + grp * 16;
       // dependencies of this item are satisfied once the poller says so (acquire through shared memory)
       while (*dep_seq < j + 1) { }
       __threadfence_block();
       float* cst = N.fb + size_t(it.layer) * 2 * size_t(args.panels) * kPanelRows * H;      // c of this layer (kind 0 only)
-      float4 cpre[2];
+      float4 cpre[4];
       if (it.kind == 0 && live) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) cpre[q] = __ldcg(reinterpret_cast<const float4*>(cst + fb_offset(R, u0 + q * 4, H)));
+        for (int q = 0; q < 4; ++q) cpre[q] = __ldcg(reinterpret_cast<const float4*>(cst + fb_offset(R, u0 + q * 4, H)));
       }
       const uint8_t* done_t = args.done ? args.done + size_t(it.t) * ld : nullptr;
       const bool rst = live && done_t && done_t[R];
       const long long ew0 = tr ? clock64() : 0;
-      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      mbar_wait(&acc_full[0], j & 1);
       const long long ew1 = tr ? clock64() : 0;
       tc_fence_after();
-      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * kTileCols) + colq);
+      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(colq);
       if (it.kind == 0) {
-        float v[32];
-        {
-          float cr[32];
+        float v[64];
 #pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) { tmem_ld8(tq + 16 * g4, v + 8 * g4); tmem_ld8(tq + kTileCols + 16 * g4, cr + 8 * g4); }
+        for (int g4 = 0; g4 < 4; ++g4) {
+          float cr[16];
+          tmem_ld16(tq + 16 * g4, v + 16 * g4);
+          tmem_ld16(tq + kTileColsP + 16 * g4, cr);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += kCorr * cr[i];
+          for (int i = 0; i < 16; ++i) v[16 * g4 + i] += kCorr * cr[i];
         }
+        // the accumulators are in registers: hand TMEM back to the MMA issuer before doing the math
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) mbar_arrive(&acc_empty[0]);
         if (tr) ph[0] += clock64() - ew1;
-        const float* bs = bias_s + (it.net * kPMaxDepth + it.layer) * kMaxBias + it.tile * kTileCols + colq;
+        const float* bs = bias_s + (it.net * kPMaxDepth + it.layer) * kMaxBias + it.tile * kTileColsP + colq;
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[8 * g4 + i] += bs[16 * g4 + i];
+        for (int i = 0; i < 64; ++i) v[i] += bs[i];
         if (live && !(args.dbg & 2)) {
           char* x_out = N.xmid + size_t(it.layer * 2 + (it.t & 1)) * args.sbb;
           char* h_out = N.hsb + size_t(it.layer * 2 + ((it.t + 1) & 1)) * args.sbb;
           float* h_carry = (it.t == int(args.T) - 1) ? cst + size_t(args.panels) * kPanelRows * H : nullptr;
-          // 8 hidden units per thread = exactly one 16-byte SB chunk per plane (FP16 kind): every store below is a full
-          // 16 B per lane, 512 contiguous bytes per warp (the 8-byte half-chunk stores of the 4-unit version cost the
-          // bulk-copy pipeline 2.5 K cycles per item in L2 write contention)
-          float hn[8], cn[8];
+          // 8 hidden units = exactly one 16-byte SB chunk per plane (FP16 kind): every store below is a full 16 B per
+          // lane, 512 contiguous bytes per warp (8-byte half-chunk stores cost the operand pipeline 2.5 K cycles per item)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float cprev = i < 4 ? (&cpre[0].x)[i] : (&cpre[1].x)[i - 4];
-            const float gi_ = v[i], gf = v[8 + i], gg = v[16 + i], go = v[24 + i];
-            // c' = s(f) c + s(i) tanh(g);  h' = s(o) tanh(c')   (eqx LSTMCell)
-            cn[i] = sigmoidf_(gf) * cprev + sig_mul_tanh(gi_, gg);
-            hn[i] = sig_mul_tanh(go, cn[i]);
-            if (rst) cn[i] = 0.0f;
-          }
-          if (!((args.dbg & 4) && hn[0] != 12345.0f)) {
-            const float h0[4] = {hn[0], hn[1], hn[2], hn[3]}, h1[4] = {hn[4], hn[5], hn[6], hn[7]};
-            const KbsSplit4 s0 = sb_split4<KIND>(h0), s1 = sb_split4<KIND>(h1);   // one split serves both consumers
-            sb_store_split8<kPanelRows, KIND>(x_out, R, u0, kb, s0, s1, false);   // next layer / head input (un-reset)
-            sb_store_split8<kPanelRows, KIND>(h_out, R, u0, kb, s0, s1, rst);     // recurrent input (reset where done)
-            *reinterpret_cast<float4*>(cst + fb_offset(R, u0, H)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            *reinterpret_cast<float4*>(cst + fb_offset(R, u0 + 4, H)) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-            if (h_carry) {
-              const float z = rst ? 0.0f : 1.0f;
-              *reinterpret_cast<float4*>(h_carry + fb_offset(R, u0, H)) = make_float4(z * hn[0], z * hn[1], z * hn[2], z * hn[3]);
-              *reinterpret_cast<float4*>(h_carry + fb_offset(R, u0 + 4, H)) = make_float4(z * hn[4], z * hn[5], z * hn[6], z * hn[7]);
+          for (int hf = 0; hf < 2; ++hf) {
+            float hn[8], cn[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int u = hf * 8 + i;
+              const float cprev = (&cpre[u >> 2].x)[u & 3];
+              const float gi_ = v[u], gf = v[16 + u], gg = v[32 + u], go = v[48 + u];
+              // c' = s(f) c + s(i) tanh(g);  h' = s(o) tanh(c')   (eqx LSTMCell)
+              cn[i] = sigmoidf_(gf) * cprev + sig_mul_tanh(gi_, gg);
+              hn[i] = sig_mul_tanh(go, cn[i]);
+              if (rst) cn[i] = 0.0f;
+            }
+            if (!((args.dbg & 4) && hn[0] != 12345.0f)) {
+              const int uu = u0 + hf * 8;
+              const float h0[4] = {hn[0], hn[1], hn[2], hn[3]}, h1[4] = {hn[4], hn[5], hn[6], hn[7]};
+              const KbsSplit4 s0 = sb_split4<KIND>(h0), s1 = sb_split4<KIND>(h1);   // one split serves both consumers
+              sb_store_split8<kPanelRows, KIND>(x_out, R, uu, kb, s0, s1, false);   // next layer / head input (un-reset)
+              sb_store_split8<kPanelRows, KIND>(h_out, R, uu, kb, s0, s1, rst);     // recurrent input (reset where done)
+              *reinterpret_cast<float4*>(cst + fb_offset(R, uu, H)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+              *reinterpret_cast<float4*>(cst + fb_offset(R, uu + 4, H)) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+              if (h_carry) {
+                const float z = rst ? 0.0f : 1.0f;
+                *reinterpret_cast<float4*>(h_carry + fb_offset(R, uu, H)) = make_float4(z * hn[0], z * hn[1], z * hn[2], z * hn[3]);
+                *reinterpret_cast<float4*>(h_carry + fb_offset(R, uu + 4, H)) = make_float4(z * hn[4], z * hn[5], z * hn[6], z * hn[7]);
+              }
             }
           }
         }
@@ -1001,15 +1041,15 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
         {
           float cr[16];
           tmem_ld8(tq, v); tmem_ld8(tq + 16, v + 8);
-          tmem_ld8(tq + kTileCols, cr); tmem_ld8(tq + kTileCols + 16, cr + 8);
+          tmem_ld8(tq + kTileColsP, cr); tmem_ld8(tq + kTileColsP + 16, cr + 8);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += kCorr * cr[i];
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        const float* bs = bias_head_s + it.net * kTileCols + colq;
+        if (lane == 0) mbar_arrive(&acc_empty[0]);
+        const float* bs = bias_head_s + it.net * kTileColsP + colq;
         const int64_t e = R;
         const size_t t = size_t(it.t);
         float s_z = 0.0f, s_log = 0.0f;
@@ -1091,11 +1131,16 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
       if (tr) { const long long ew3 = clock64(); epi_cyc[it.kind] += ew3 - ew1; epi_wait += ew1 - ew0; if (it.kind == 0) { ph[1] += ew2 - ew1; ph[2] += ew3 - ew2; ph[3] += ewf - ew2; } }
       ++j;
     }
-    if (tr && threadIdx.x == 32 * (kIssuers + kProducers)) { tr[4] = epi_cyc[0]; tr[5] = epi_cyc[1]; tr[6] = epi_wait; tr[8] = ph[0]; tr[9] = ph[1]; tr[10] = ph[2]; tr[11] = ph[3]; }
+    if (tr && threadIdx.x == 32 * (kIssuersP + kProducersP)) { tr[4] = epi_cyc[0]; tr[5] = epi_cyc[1]; tr[6] = epi_wait; tr[8] = ph[0]; tr[9] = ph[1]; tr[10] = ph[2]; tr[11] = ph[3]; }
   }
   tc_fence_before();
   __syncthreads();
-  if (tr && threadIdx.x == 0) tr[0] = clock64() - t_start;
+  if (tr && threadIdx.x == 0) {
+    unsigned long long gt_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
+    tr[0] = clock64() - t_start;
+    tr[15] = (long long)(gt_end - gt_start);      // ns: SM clock under load = tr[0] / tr[15] GHz
+  }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
@@ -1105,22 +1150,22 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
 // eqx LSTMCell weights [4H][H] x2 + bias [4H]  ->  gate-interleaved SB tiles (hi/lo) + interleaved bias.
 // tile j (128 columns = 32 hidden units), column c = half * 64 + gate * 16 + uu  ->  unit = 32 j + 16 half + uu:
 // an epilogue thread that owns 16 units finds their i, f, g, o pre-activations in 64 CONSECUTIVE TMEM columns.
-template <int KIND>
+template <int KIND, int TILE>
 __global__ void __launch_bounds__(256)
 pack_lstm_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b,
                          char* __restrict__ w_sb, float* __restrict__ bias_t, int H) {
   const int kq = 2 * H / 4;
   const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (idx >= int64_t(4 * H) * kq) return;
-  const int col_g = int(idx / kq);                        // global packed column: tile * 128 + c
+  const int col_g = int(idx / kq);                        // global packed column: tile * TILE + c
   const int k = int(idx % kq) * 4;
-  const int tile = col_g / kTileCols, c = col_g % kTileCols;
-  const int half = c / 64, gate = (c % 64) / 16, uu = c % 16;
-  const int u = tile * kUnitsPerTile + half * 16 + uu;
+  const int tile = col_g / TILE, c = col_g % TILE;
+  const int grp = c / 64, gate = (c % 64) / 16, uu = c % 16;      // [16-unit group][gate i,f,g,o][unit]
+  const int u = tile * (TILE / 4) + grp * 16 + uu;
   const int row = gate * H + u;                           // eqx row (i,f,g,o blocks of H)
   const float* src = (k < H) ? w_ih + size_t(row) * H + k : w_hh + size_t(row) * H + (k - H);
   const float x[4] = {src[0], src[1], src[2], src[3]};
-  sb_store4<kTileCols, KIND>(w_sb, col_g, k, 2 * H / kbs_block_k(KIND), x);
+  sb_store4<TILE, KIND, true>(w_sb, col_g, k, 2 * H / kbs_block_k(KIND), x);
   if (k == 0) bias_t[col_g] = b[row];
 }
 
@@ -1138,32 +1183,32 @@ pack_proj_weights_kernel(const float* __restrict__ w, int ldw, const float* __re
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = (k + i < ldw) ? w[size_t(col) * ldw + k + i] : 0.0f;
   }
-  sb_store4<kTileCols, KIND>(w_sb, col, k, Kp / kbs_block_k(KIND), x);
+  sb_store4<kTileCols, KIND, true>(w_sb, col, k, Kp / kbs_block_k(KIND), x);
   if (k == 0) bias_t[col] = col < H ? b[col] : 0.0f;
 }
 
-// Output head of the persistent rollout kernel: eqx Linear weight [num_out][H] -> ONE 128-column SB tile whose columns
-// follow the epilogue's thread map: column c = half * 64 + gate * 16 + sub * 8 + uu; joint group grp = 2 half + sub holds
-// joints 5 grp .. 5 grp + 4 in uu = 0..4: gate 0 = mean row (joint), gate 1 = std row (20 + joint); all else zero.
-// The critic (num_out = 1) lands in column 0.
+// Output head of the persistent rollout kernel: eqx Linear weight [num_out][H] -> ONE 256-column SB tile whose columns
+// follow the epilogue's thread map: column c = grp * 64 + gate * 16 + uu; joint group grp holds joints 5 grp .. 5 grp + 4
+// in uu = 0..4: gate 0 = mean row (joint), gate 1 = std row (20 + joint); all else zero.  The critic (num_out = 1)
+// lands in column 0.
 template <int KIND>
 __global__ void __launch_bounds__(256)
 pack_head_weights_kernel(const float* __restrict__ w, const float* __restrict__ b, char* __restrict__ w_sb,
                          float* __restrict__ bias_t, int H, int num_out) {
   const int kq = H / 4;
   const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  if (idx >= int64_t(kTileCols) * kq) return;
+  if (idx >= int64_t(kTileColsP) * kq) return;
   const int col = int(idx / kq), k = int(idx % kq) * 4;
-  const int half = col / 64, gate = (col % 64) / 16, sub = (col % 16) / 8, uu = col % 8;
+  const int grp = col / 64, gate = (col % 64) / 16, uu = col % 16;
   int row = -1;
-  if (gate < 2 && uu < 5) row = gate * KBS_NUM_JOINTS + (2 * half + sub) * 5 + uu;
+  if (gate < 2 && uu < 5) row = gate * KBS_NUM_JOINTS + grp * 5 + uu;
   if (row >= num_out) row = -1;
   float x[4] = {0.f, 0.f, 0.f, 0.f};
   if (row >= 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = w[size_t(row) * H + k + i];
   }
-  sb_store4<kTileCols, KIND>(w_sb, col, k, H / kbs_block_k(KIND), x);
+  sb_store4<kTileColsP, KIND, true>(w_sb, col, k, H / kbs_block_k(KIND), x);
   if (k == 0) bias_t[col] = row >= 0 ? b[row] : 0.0f;
 }
 
@@ -1295,13 +1340,26 @@ static inline char* proj_w(const kbs_handle* h, int net) { return layer_w(h, net
 static inline float* proj_bias(const kbs_handle* h, int net) {
   return reinterpret_cast<float*>(proj_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), proj_cols(h), proj_kp(h, net)));
 }
-// output head: W_out zero-padded to one 128-column tile [128][H] SB + bias [128]
-static size_t head_image_bytes(const kbs_handle* h) {
-  return kbs_sb_bytes_kind(tc_kind(h), kTileCols, h->p.hidden_size) + size_t(kTileCols) * 4;
+// persistent rollout kernel: the same LSTM weights in 256-column tiles (image P), then the output head: W_out zero-padded
+// to one 256-column tile [256][H] SB + bias [256]
+static inline char* layer_w_p(const kbs_handle* h, int net, int l) {
+  return proj_w(h, net) + proj_image_bytes(h, net) + layer_image_bytes(h) * l;
 }
-static inline char* head_w(const kbs_handle* h, int net) { return proj_w(h, net) + proj_image_bytes(h, net); }
+static inline float* layer_bias_p(const kbs_handle* h, int net, int l) {
+  const int H = h->p.hidden_size;
+  return reinterpret_cast<float*>(layer_w_p(h, net, l) + kbs_sb_bytes_kind(tc_kind(h), 4 * H, 2 * H));
+}
+static size_t head_image_bytes(const kbs_handle* h) {
+  return kbs_sb_bytes_kind(tc_kind(h), kTileColsP, h->p.hidden_size) + size_t(kTileColsP) * 4;
+}
+static inline char* head_w(const kbs_handle* h, int net) { return layer_w_p(h, net, h->p.depth); }
 static inline float* head_bias(const kbs_handle* h, int net) {
-  return reinterpret_cast<float*>(head_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), kTileCols, h->p.hidden_size));
+  return reinterpret_cast<float*>(head_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), kTileColsP, h->p.hidden_size));
+}
+static inline bool persist_shape_ok(const kbs_handle* h) {
+  const int H = h->p.hidden_size;
+  return H % kUnitsPerTileP == 0 && h->p.depth <= kPMaxDepth && H <= kMaxBias / 4 &&
+         (H / kbs_block_k(tc_kind(h))) % kStagesP == 0;
 }
 
 int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
@@ -1317,18 +1375,25 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
     attr_set = true;
   }
   if (N.tc_image) { KBS_CUDA_TRY(cudaFree(N.tc_image)); N.tc_image = nullptr; }
-  const size_t bytes = layer_image_bytes(h) * h->p.depth + proj_image_bytes(h, net) + head_image_bytes(h);
+  const size_t bytes = 2 * layer_image_bytes(h) * h->p.depth + proj_image_bytes(h, net) + head_image_bytes(h);
   N.tc_image_floats = (bytes + 3) / 4;
   KBS_CUDA_TRY(cudaMalloc(&N.tc_image, bytes));
   for (int l = 0; l < h->p.depth; ++l) {
     const int64_t total = int64_t(4 * H) * (2 * H / 4);
     const unsigned gb = unsigned((total + 255) / 256);
     if (kind == KBS_KIND_TF32)
-      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_TF32, kTileCols><<<gb, 256, 0, st>>>(
                                         N.w_ih[l], N.w_hh[l], N.b[l], layer_w(h, net, l), layer_bias(h, net, l), H)));
     else
-      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_F16, kTileCols><<<gb, 256, 0, st>>>(
                                         N.w_ih[l], N.w_hh[l], N.b[l], layer_w(h, net, l), layer_bias(h, net, l), H)));
+    if (!persist_shape_ok(h)) continue;
+    if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_TF32, kTileColsP><<<gb, 256, 0, st>>>(
+                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w_p(h, net, l), layer_bias_p(h, net, l), H)));
+    else
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_F16, kTileColsP><<<gb, 256, 0, st>>>(
+                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w_p(h, net, l), layer_bias_p(h, net, l), H)));
   }
   {
     const int Kp = proj_kp(h, net);
@@ -1342,8 +1407,8 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
                                         N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp, cols)));
   }
-  if (N.num_out <= kTileCols && H % kbs_block_k(kind) == 0) {   // output head tile (persistent rollout kernel)
-    const int64_t total = int64_t(kTileCols) * (H / 4);
+  if (persist_shape_ok(h)) {   // output head tile (persistent rollout kernel)
+    const int64_t total = int64_t(kTileColsP) * (H / 4);
     const unsigned gb = unsigned((total + 255) / 256);
     if (kind == KBS_KIND_TF32)
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_head_weights_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(
@@ -1546,10 +1611,9 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
   }
   const char* legacy_env = getenv("KBS_TC_PER_STEP");          // A/B and cross-check against the per-step launches
   const int legacy = legacy_env ? atoi(legacy_env) : 0;
-  const int panels = int(np / kPanelRows), tiles = H / kUnitsPerTile;
+  const int panels = int(np / kPanelRows), tiles = H / kUnitsPerTileP;
   const int64_t n_items = (r.T + depth) * int64_t(nets) * panels * (depth * tiles + 1);
-  if (!legacy && depth <= kPMaxDepth && H <= kMaxBias / 4 && n_items < (int64_t(1) << 31) &&
-      h->net[0].num_out <= kTileCols && (nets < 2 || h->net[1].num_out <= kTileCols)) {
+  if (!legacy && persist_shape_ok(h) && n_items < (int64_t(1) << 31)) {
     // ---- persistent recurrence: one cooperative launch for all T steps (rollout_persist_kernel) ----
     if (!h->persist_status) KBS_CUDA_TRY(cudaMalloc(&h->persist_status, 256));
     PArgs a{};
@@ -1557,7 +1621,7 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
       PNet& N = a.net[k];
       N.x_sb_all = reinterpret_cast<const char*>(r.x_sb_all[k]);
       N.hsb = hsb[k]; N.xmid = xmid[k]; N.fb = fb[k]; N.flags = flags[k];
-      for (int l = 0; l < depth; ++l) { N.w_sb[l] = layer_w(h, k, l); N.bias_t[l] = layer_bias(h, k, l); }
+      for (int l = 0; l < depth; ++l) { N.w_sb[l] = layer_w_p(h, k, l); N.bias_t[l] = layer_bias_p(h, k, l); }
       N.w_head = head_w(h, k); N.bias_head = head_bias(h, k);
       KBS_CUDA_TRY(cudaMemsetAsync(flags[k], 0, rollout_flag_bytes(h, n), st));
     }

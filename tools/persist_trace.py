@@ -24,19 +24,20 @@ io = {"state": d["state"], "noise": d["noise"], "episode": d["episode"], "eps_ac
       "value": torch.zeros((T, N), **f32), "T": T}
 import os
 ctas = int(os.environ.get("KBS_PERSIST_GRID", "148"))
-tr = torch.zeros((ctas * 12 + 1024,), dtype=torch.int64, device=dev)
+tr = torch.zeros((ctas * 16 + 1024,), dtype=torch.int64, device=dev)
 e.lib.kbs_debug_tc_trace_attach(e._h, tr.data_ptr(), 0, 0)
 for rep in range(3):
     e.rollout(io, N)
 torch.cuda.synchronize()
 print("status", e.device_status())
-t = tr.cpu().numpy()[:ctas * 12].reshape(ctas, 12).astype(np.float64)
+t = tr.cpu().numpy()[:ctas * 16].reshape(ctas, 16).astype(np.float64)
 names = ("total cycles", "poller wait cycles", "items", "issuer wait-for-stage", "epilogue cycles (LSTM items)",
          "epilogue cycles (head items)", "epilogue wait-for-accumulator", "issuer wait-for-TMEM", "LSTM epi: TMEM pull", "LSTM epi: pull+math+stores",
-         "LSTM epi: publish (fence+red)", "LSTM epi: syncwarp+threadfence only")
+         "LSTM epi: publish (fence+red)", "LSTM epi: syncwarp+threadfence only", "producer: wait for a free stage", "producer: expect_tx + bulk issue", "producer: wait deps + proxy fence", "-")
 for i, name in enumerate(names):
     v = t[:, i]
     print(f"{name:32s} median {np.median(v):12.0f}  min {v.min():12.0f}  max {v.max():12.0f}   per item {np.median(v / t[:, 2]):9.0f}")
+print("SM clock during the kernel: %.3f GHz (clock64 / globaltimer)" % np.median(t[:, 0] / t[:, 15]))
 slots = T + 2
 print("cycles per slot: %.0f (items per CTA per slot %.2f)" % (np.median(t[:, 0]) / slots, np.median(t[:, 2]) / slots))
 e.lib.kbs_debug_tc_trace_attach(e._h, None, -1, 0)
