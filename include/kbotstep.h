@@ -161,6 +161,14 @@ int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_vie
                      const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs,
                      int64_t n_envs, void* stream);
 
+/* Host -> device upload of T recorded steps of MuJoCo-shaped state ([T][rows][ld] per array, pinned host memory for
+ * asynchronous copies): only the rows the path reads cross PCIe -- qpos, qvel, actuator_force, com_distance, time in
+ * full; sensordata rows imu_gyro / imu_site_quat / foot touch; xpos / xquat of base and both feet; cinert[1:], cvel[1:]
+ * (473 of the 676 rows, row indices from kbs_params).  One cudaMemcpy2DAsync per row range on `stream`; arrays whose
+ * pointer is NULL in either view are skipped.  *bytes_out (optional) = bytes enqueued. */
+int kbs_upload_state(kbs_handle* h, const kbs_state_view* host, const kbs_state_view* dev, int64_t T, int64_t* bytes_out,
+                     void* stream);
+
 /* Replaces: mirror_obs + mirror_cmd (train.py:1584-1756) followed by the run_actor / run_critic concatenations on the
  * mirrored observations (train.py:1463-1481), for T stored steps.  The mirror acts on the RAW named observations, so it
  * is built from what the rollout stored: `computed` [T][78][ld] (kbs_observations), the recorded state (time-major

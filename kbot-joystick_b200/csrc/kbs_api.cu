@@ -404,6 +404,45 @@ int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_vie
                                  (cudaStream_t)stream);
 }
 
+int kbs_upload_state(kbs_handle* h, const kbs_state_view* host, const kbs_state_view* dev, int64_t T, int64_t* bytes_out,
+                     void* stream) {
+  REQ(h); REQ(host); REQ(dev);
+  if (T <= 0 || host->ld != dev->ld || host->ld <= 0) return KBS_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ldb = size_t(host->ld) * sizeof(float);
+  const int bb = h->p.body_base, bl = h->p.body_lfoot, br = h->p.body_rfoot;
+  struct Range { const float* src; const float* dst; int rows, r0, r1; };
+  const Range rs[] = {
+      {host->qpos, dev->qpos, KBS_NQ, 0, KBS_NQ},
+      {host->qvel, dev->qvel, KBS_NV, 0, KBS_NV},
+      {host->sensordata, dev->sensordata, KBS_NSENSORDATA, h->p.sd_gyro, h->p.sd_gyro + 3},
+      {host->sensordata, dev->sensordata, KBS_NSENSORDATA, h->p.sd_imu_quat, h->p.sd_imu_quat + 4},
+      {host->sensordata, dev->sensordata, KBS_NSENSORDATA, h->p.sd_touch_l, h->p.sd_touch_l + 1},
+      {host->sensordata, dev->sensordata, KBS_NSENSORDATA, h->p.sd_touch_r, h->p.sd_touch_r + 1},
+      {host->xpos, dev->xpos, 3 * KBS_NBODY, 3 * bb, 3 * bb + 3},
+      {host->xpos, dev->xpos, 3 * KBS_NBODY, 3 * bl, 3 * bl + 3},
+      {host->xpos, dev->xpos, 3 * KBS_NBODY, 3 * br, 3 * br + 3},
+      {host->xquat, dev->xquat, 4 * KBS_NBODY, 4 * bb, 4 * bb + 4},
+      {host->xquat, dev->xquat, 4 * KBS_NBODY, 4 * bl, 4 * bl + 4},
+      {host->xquat, dev->xquat, 4 * KBS_NBODY, 4 * br, 4 * br + 4},
+      {host->cinert, dev->cinert, 10 * KBS_NBODY, 10, 10 * KBS_NBODY},       // cinert[1:]
+      {host->cvel, dev->cvel, 6 * KBS_NBODY, 6, 6 * KBS_NBODY},              // cvel[1:]
+      {host->actuator_force, dev->actuator_force, KBS_NUM_JOINTS, 0, KBS_NUM_JOINTS},
+      {host->com_distance, dev->com_distance, 1, 0, 1},
+      {host->time, dev->time, 1, 0, 1},
+  };
+  int64_t bytes = 0;
+  for (const Range& r : rs) {
+    if (!r.src || !r.dst) continue;
+    const size_t pitch = size_t(r.rows) * ldb, width = size_t(r.r1 - r.r0) * ldb;
+    KBS_CUDA_TRY(cudaMemcpy2DAsync(const_cast<float*>(r.dst) + size_t(r.r0) * host->ld, pitch, r.src + size_t(r.r0) * host->ld,
+                                   pitch, width, size_t(T), cudaMemcpyHostToDevice, st));
+    bytes += int64_t(width) * T;
+  }
+  if (bytes_out) *bytes_out = bytes;
+  return KBS_OK;
+}
+
 int kbs_mirror_observations(kbs_handle* h, const kbs_state_view* s, const float* computed, const float* command,
                             float* actor_obs, float* critic_obs, float* command_out, int64_t T, int64_t n, void* stream) {
   REQ(h); REQ(computed); REQ(command);

@@ -240,9 +240,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
   if (tr3 && threadIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); tr3[0] = (long long)gt; }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kIssuers); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], kIssuers); mbar_init(&acc_empty[b], kEpiWarps); mbar_init(&corr_init[b], 1);
+      mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); mbar_init(&corr_init[b], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -294,9 +294,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
     }
     __syncwarp();                        // reconverge before the CTA barrier (bar.sync is warp-aligned)
   } else if (warp < kIssuers) {
-    {
-      // ===== MMA issuers (whole warp runs the loop; one elected lane issues): per stage, warp 0: hi.hi of both k-steps ->
-      // main set; warp 1 / 2: lo.hi + hi.lo of k-step 0 / 1 -> correction set =====
+    if (warp == 0) {
+      // ===== MMA issuer (whole warp runs the loop; one elected lane issues; warps 1, 2 idle).  Per k-step two instructions:
+      // x_hi . [W_hi | W_lo]^T as ONE N = 256 MMA into [main | correction] columns, x_lo . W_hi^T as an N = 128 MMA into
+      // the correction columns; one commit per stage.  MEASURED (tools/stage_pipe_bench.cu): every tcgen05 instruction
+      // costs the issue path ~110-128 cycles whoever issues it, so three warps with three commits per stage were no
+      // faster than one thread with one -- and one thread fixes the accumulation order (bitwise reproducible). =====
       uint32_t g = 0;
       int j = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
@@ -313,40 +316,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
           const uint32_t sb = sa + kABlockBytes;
-          // [part][chunk][128 rows][16 B]: part stride 8 KB, chunk stride 2 KB (A and B alike); k-step stride 4 KB
           // A block [part][chunk][128 rows][16 B]: part stride 8 KB, chunk stride 2 KB, k-step (2 chunks) 4 KB.
           // B block [chunk][hi|lo][128 rows][16 B]: chunk stride 4 KB (LBO), k-step 8 KB; hi rows then lo rows = one
-          // 256-row operand, so x_hi . [W_hi | W_lo]^T is ONE N = 256 instruction into [main | correction] columns.
-          if (warp == 0) {
-            const uint64_t a0 = umma_desc(sa, 2048, 128), b0 = umma_desc(sb, 4096, 128);
-            const uint64_t a1 = umma_desc(sa + 4096, 2048, 128), b1 = umma_desc(sb + 8192, 4096, 128);
-            if (elect_one()) {
-              if (tr && g == 0) tr[2] = clock64();        // first stage landed
-              if (tr2 && g < 64) tr2[128 + g] = clock64();
-              umma<KIND, 2 * kTileCols>(d_main, a0, b0, b != 0);
-              if (b == 0) { tc_fence_before(); mbar_arrive(&corr_init[buf]); }   // the correction columns are initialised
-              umma<KIND, 2 * kTileCols>(d_main, a1, b1, 1);
-              umma_commit(&empty[s]);          // frees the stage when these MMAs have read it
-              if (tr2 && g < 64) tr2[192 + g] = clock64();
-            }
-          } else {
-            const int ks = warp - 1;
-            const uint64_t a_lo = umma_desc(sa + 8192 + ks * 4096, 2048, 128);
-            const uint64_t b_hi = umma_desc(sb + ks * 8192, 4096, 128);
-            if (b == 0) {                         // warp 0's accumulate = 0 MMA must be queued first
-              mbar_wait(&corr_init[buf], (j >> 1) & 1);
-              tc_fence_after();
-            }
-            if (elect_one()) {
-              umma<KIND, kTileCols>(d_corr, a_lo, b_hi, 1);
-              umma_commit(&empty[s]);
-            }
+          // 256-row operand.
+          const uint64_t a_hi = umma_desc(sa, 2048, 128), a_lo = umma_desc(sa + 8192, 2048, 128);
+          const uint64_t b_all = umma_desc(sb, 4096, 128);
+          if (elect_one()) {
+            if (tr && g == 0) tr[2] = clock64();        // first stage landed
+            if (tr2 && g < 64) tr2[128 + g] = clock64();
+            umma<KIND, 2 * kTileCols>(d_main, a_hi, b_all, b != 0);
+            umma<KIND, kTileCols>(d_corr, a_lo, b_all, 1);
+            umma<KIND, 2 * kTileCols>(d_main, a_hi + (4096 >> 4), b_all + (8192 >> 4), 1);
+            umma<KIND, kTileCols>(d_corr, a_lo + (4096 >> 4), b_all + (8192 >> 4), 1);
+            umma_commit(&empty[s]);          // frees the stage when these MMAs have read it
+            if (tr2 && g < 64) tr2[192 + g] = clock64();
           }
           __syncwarp();
         }
         if (elect_one()) {
-          umma_commit(&acc_full[buf]);       // accumulator set complete (this warp's share)
-          if (tr && j == 0 && warp == 0) tr[3] = clock64();
+          umma_commit(&acc_full[buf]);       // accumulator set complete
+          if (tr && j == 0) tr[3] = clock64();
         }
         __syncwarp();
       }

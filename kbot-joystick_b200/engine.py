@@ -33,13 +33,13 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def _view(cls, rows: dict, tensors: dict | None, ld: int | None = None):
+def _view(cls, rows: dict, tensors: dict | None, ld: int | None = None, host: bool = False):
     v = cls()
     if tensors:
         for k in rows:
             t = tensors.get(k)
             if t is not None:
-                setattr(v, k, L.ptr(t))
+                setattr(v, k, L.host_ptr(t) if host else L.ptr(t))
     if ld is not None:
         v.ld = ld
     return v
@@ -126,6 +126,17 @@ class KbotStep:
                                           L.ptr(pg_carry), L.ptr(pg_reset), L.ptr(computed), L.ptr(actor_obs),
                                           L.ptr(critic_obs), n,
                                           _stream()), "kbs_observations")
+
+    def upload_state(self, host_state: dict, dev_state: dict, stream: int | None = None) -> int:
+        """Enqueue the H2D copy of T recorded steps ([T][rows][ld] per array; host tensors pinned): only the rows the path
+        reads (kbs_upload_state).  Returns the bytes enqueued."""
+        T, ld = dev_state["qpos"].shape[0], dev_state["qpos"].shape[-1]
+        hv = _view(L.KbsStateView, STATE_ROWS, host_state, ld, host=True)
+        dv = _view(L.KbsStateView, STATE_ROWS, dev_state, ld)
+        n = C.c_int64(0)
+        L.check(self.lib.kbs_upload_state(self._h, C.byref(hv), C.byref(dv), T, C.byref(n),
+                                          _stream() if stream is None else stream), "kbs_upload_state")
+        return int(n.value)
 
     def mirror_observations(self, state: dict, computed, command, actor_obs=None, critic_obs=None, command_out=None,
                             n_envs: int | None = None) -> None:

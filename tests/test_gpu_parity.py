@@ -368,9 +368,10 @@ def test_rollout_fused(dev, path, T, N, hidden):
 def test_rollout_persistent_vs_per_step_launches(dev, T, N, monkeypatch):
     """Size-independent property at BASELINE configs[1] scale: the persistent recurrence kernel (one launch, CTAs
     synchronised through progress counters) and the per-step launch sequence (kernel boundaries as the only
-    synchronisation) run the same tcgen05 datapath; they agree to rounding level (the three MMA-issuing warps of a
-    CTA interleave differently from run to run, so the truncating accumulation is reproducible to ~1 ulp, not bitwise;
-    a missed dependency would show as an O(0.1) error).  The heads differ in summation order (tensor-core vs FFMA)."""
+    synchronisation) run the same split-precision tcgen05 datapath with different tile shapes (128 x 256 vs 128 x 128
+    tiles, so the truncating accumulation order differs): they agree to rounding level, a missed dependency would show
+    as an O(0.1) error.  The heads differ in summation order (tensor-core vs FFMA).  Each path on its own is bitwise
+    reproducible run to run (one MMA-issuing thread per CTA): checked by running the persistent kernel twice."""
     b = Batch(4242, T, N, dev)
     outs = []
     for per_step in ("0", "1"):
@@ -385,6 +386,14 @@ def test_rollout_persistent_vs_per_step_launches(dev, T, N, monkeypatch):
         e.close()
     (a, la), (c, lc) = outs
     assert la < lc and lc - la >= 3 * T - 10, (la, lc)          # one launch instead of 3 per step
+    monkeypatch.setenv("KBS_TC_PER_STEP", "0")
+    e, _, _ = Hn.make_engine(gemm_path=L.GEMM_TC_2XF16, device=dev)
+    again = Hn.rollout_buffers(b, 256, 2)
+    e.rollout(again, N)
+    torch.cuda.synchronize()
+    e.close()
+    for k in ("actor_carry", "critic_carry", "action", "log_prob", "value", "ctrl", "lpf"):
+        assert torch.equal(a[k], again[k]), f"{k}: the persistent kernel is not bitwise reproducible"
     close(a["actor_carry"].cpu().numpy(), c["actor_carry"].cpu().numpy(), "actor carry", atol=2e-6)
     close(a["critic_carry"].cpu().numpy(), c["critic_carry"].cpu().numpy(), "critic carry", atol=2e-6)
     close(S(a["action"], N, (20,)), S(c["action"], N, (20,)), "action")
@@ -392,6 +401,38 @@ def test_rollout_persistent_vs_per_step_launches(dev, T, N, monkeypatch):
     close(S(a["value"], N), S(c["value"], N), "value", atol=1e-5)
     close(S(a["ctrl"], N, (20,)), S(c["ctrl"], N, (20,)), "ctrl", atol=1e-4)
     close(S(a["lpf"], N, (20,)), S(c["lpf"], N, (20,)), "lpf")
+
+
+def test_upload_state_moves_every_row_the_path_reads(dev):
+    """kbs_upload_state copies 473 of the 676 MuJoCo rows.  Device arrays pre-filled with NaN + that upload must give
+    the same rollout, rewards and GAE, bit for bit, as the fully populated state (any row the path reads but the
+    upload skips would poison the outputs)."""
+    T, N = 5, 260
+    b = Batch(4343, T, N, dev)
+    e, _, _ = Hn.make_engine(gemm_path=L.GEMM_TC_2XF16, device=dev)
+
+    def run(state):
+        io = Hn.rollout_buffers(b, 256, 2)
+        io["state"] = state
+        e.rollout(io, N)
+        carry = {"t_single": torch.zeros(b.ld, device=dev), "airtime": torch.zeros((2, b.ld), device=dev),
+                 "prev_contact": torch.ones((2, b.ld), device=dev, dtype=torch.uint8)}
+        total = e.rewards(state, io["command"][:T].contiguous(), io["ctrl"], io["done"], carry, n_envs=N)
+        adv, tgt = e.gae(io["value"], total, io["done"], io["success"], n_envs=N)
+        torch.cuda.synchronize()
+        return {"action": io["action"], "value": io["value"], "done": io["done"], "total": total, "adv": adv, "tgt": tgt,
+                "ctrl": io["ctrl"], "log_prob": io["log_prob"], "term": io["term_codes"]}
+
+    ref = run(b.state)
+    host = {k: v.cpu().pin_memory() for k, v in b.state.items()}
+    poisoned = {k: torch.full_like(v, float("nan")) for k, v in b.state.items()}
+    nbytes = e.upload_state(host, poisoned)
+    torch.cuda.synchronize()
+    assert nbytes == 473 * 4 * b.ld * T
+    out = run(poisoned)
+    for k in ref:
+        assert torch.equal(ref[k][..., :N], out[k][..., :N]), k
+    e.close()
 
 
 def test_rollout_then_rewards_gae_chain(dev):
