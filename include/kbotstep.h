@@ -161,6 +161,17 @@ int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_vie
                      const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs,
                      int64_t n_envs, void* stream);
 
+/* Replaces: COMDistanceObservation.observe (train.py:509-659): distance between subtree_com[2].xy and the centroid of the
+ * convex hull (Andrew's monotone chain) of the floor-contact points, -1 when fewer than 3 distinct contact.geom2 values.
+ *   contact_geom1 / contact_geom2  int32 [T][ncon][ld]   (MJX contact.geom1 / geom2, padding included)
+ *   contact_pos                    [T][3 ncon][ld]       row 3 c + k = contact.pos[c][k]
+ *   subtree_com_base               [T][3][ld]            data.subtree_com[2]
+ *   com_distance                   [T][ld] out           (what kbs_state_view.com_distance / the COM reward consume)
+ * 3 <= ncon <= 32. */
+int kbs_com_distance(kbs_handle* h, const int32_t* contact_geom1, const int32_t* contact_geom2, const float* contact_pos,
+                     const float* subtree_com_base, float* com_distance, int ncon, int64_t T, int64_t ld, int64_t n_envs,
+                     void* stream);
+
 /* Host -> device upload of T recorded steps of MuJoCo-shaped state ([T][rows][ld] per array, pinned host memory for
  * asynchronous copies): only the rows the path reads cross PCIe -- qpos, qvel, actuator_force, com_distance, time in
  * full; sensordata rows imu_gyro / imu_site_quat / foot touch; xpos / xquat of base and both feet; cinert[1:], cvel[1:]

@@ -404,6 +404,17 @@ int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_vie
                                  (cudaStream_t)stream);
 }
 
+int kbs_com_distance(kbs_handle* h, const int32_t* contact_geom1, const int32_t* contact_geom2, const float* contact_pos,
+                     const float* subtree_com_base, float* com_distance, int ncon, int64_t T, int64_t ld, int64_t n,
+                     void* stream) {
+  REQ(h); REQ(contact_geom1); REQ(contact_geom2); REQ(contact_pos); REQ(subtree_com_base); REQ(com_distance);
+  if (T <= 0 || T > 65535) return KBS_E_SHAPE;
+  int rc = check_ld(ld, n);
+  if (rc) return rc;
+  return kbs_launch_com_distance(h, contact_geom1, contact_geom2, contact_pos, subtree_com_base, com_distance, ncon, T, ld, n,
+                                 (cudaStream_t)stream);
+}
+
 int kbs_upload_state(kbs_handle* h, const kbs_state_view* host, const kbs_state_view* dev, int64_t T, int64_t* bytes_out,
                      void* stream) {
   REQ(h); REQ(host); REQ(dev);

@@ -100,6 +100,8 @@ int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_no
                             const kbs_episode_view* ep, const float* command, float* pg_carry,
                             const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n,
                             cudaStream_t st, int64_t T = 1, const float* pg_lagged = nullptr, bool skip_dump = false);
+int kbs_launch_com_distance(kbs_handle* h, const int32_t* geom1, const int32_t* geom2, const float* pos, const float* com,
+                            float* out, int ncon, int64_t T, int64_t ld, int64_t n, cudaStream_t st);
 int kbs_launch_mirror_obs(kbs_handle* h, const kbs_state_view& s, const float* computed, const float* command,
                           float* actor_obs, float* critic_obs, float* command_out, int64_t n, int64_t T, cudaStream_t st);
 int kbs_launch_mirror_joints(kbs_handle* h, const float* in, float* out, int64_t ld, int64_t n, int64_t T, cudaStream_t st);

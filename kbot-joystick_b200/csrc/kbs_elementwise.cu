@@ -443,6 +443,85 @@ mirror_joints_kernel(const float* __restrict__ in, float* __restrict__ out, int6
 }
 
 // =====================================================================================================
+// O12: COMDistanceObservation (train.py:509-659): >= 3 distinct contact.geom2 values -> distance between the centroid of the
+// convex hull of the floor-contact points (xy; non-floor rows become the origin and stay in the set, as written) and
+// subtree_com[2].xy, else -1.  Andrew's monotone chain exactly as the reference runs it (lexicographic stable sort, pop
+// while cross <= 0, lower chain on the sorted order, upper chain on the reversed order, last vertex of each dropped),
+// then the shoelace centroid with the mean-of-vertices fallback for |area| < 1e-12.  One thread per (env, step): the
+// data-dependent loops XLA runs as while_loop inside scan live in registers / local memory here.
+// grid = (env blocks, T)
+// =====================================================================================================
+constexpr int kMaxContacts = 32;
+
+__global__ void __launch_bounds__(kThreads)
+com_distance_kernel(const int32_t* __restrict__ geom1, const int32_t* __restrict__ geom2, const float* __restrict__ pos,
+                    const float* __restrict__ com, float* __restrict__ out, int ncon, int64_t ld, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  if (e >= n) return;
+  const int64_t t = blockIdx.y;
+  geom1 += t * ncon * ld + e; geom2 += t * ncon * ld + e; pos += t * 3 * ncon * ld + e; com += t * 3 * ld + e;
+  // num_unique(contact.geom2): sort + count the changes (padding entries count like any other value: as written)
+  int g[kMaxContacts];
+  for (int i = 0; i < ncon; ++i) {
+    const int v = geom2[i * ld];
+    int j = i - 1;
+    while (j >= 0 && g[j] > v) { g[j + 1] = g[j]; --j; }
+    g[j + 1] = v;
+  }
+  int unique = ncon > 0 ? 1 : 0;
+  for (int i = 1; i < ncon; ++i) unique += (g[i] != g[i - 1]) ? 1 : 0;
+  if (unique < 3) { out[t * ld + e] = -1.0f; return; }
+  // points, lexicographically sorted by (x, y), stable (jnp.lexsort)
+  float sx[kMaxContacts], sy[kMaxContacts];
+  for (int i = 0; i < ncon; ++i) {
+    const bool floor = geom1[i * ld] == 0;
+    const float x = floor ? pos[(3 * i) * ld] : 0.0f, y = floor ? pos[(3 * i + 1) * ld] : 0.0f;
+    int j = i - 1;
+    while (j >= 0 && (sx[j] > x || (sx[j] == x && sy[j] > y))) { sx[j + 1] = sx[j]; sy[j + 1] = sy[j]; --j; }
+    sx[j + 1] = x; sy[j + 1] = y;
+  }
+  // the two chains (indices into the sorted points)
+  int chain[2][kMaxContacts];
+  int len[2];
+  for (int c = 0; c < 2; ++c) {
+    int ptr = 0;
+    for (int k = 0; k < ncon; ++k) {
+      const int idx = c == 0 ? k : ncon - 1 - k;
+      while (ptr >= 2) {
+        const int a = chain[c][ptr - 2], b = chain[c][ptr - 1];
+        const float cr = (sx[b] - sx[a]) * (sy[idx] - sy[a]) - (sy[b] - sy[a]) * (sx[idx] - sx[a]);
+        if (!(cr <= 0.0f)) break;
+        --ptr;
+      }
+      chain[c][ptr++] = idx;
+    }
+    len[c] = ptr - 1 > 0 ? ptr - 1 : 0;          // Andrew: drop the last vertex of each chain
+  }
+  const int count = len[0] + len[1];
+  // polygon_centroid_masked on the packed hull [lower | upper]
+  float s_cross = 0.0f, s_cx = 0.0f, s_cy = 0.0f, s_mx = 0.0f, s_my = 0.0f;
+  for (int i = 0; i < count; ++i) {
+    const int i1 = (i + 1 < count) ? i + 1 : 0;
+    const int v0 = i < len[0] ? chain[0][i] : chain[1][i - len[0]];
+    const int v1 = i1 < len[0] ? chain[0][i1] : chain[1][i1 - len[0]];
+    const float x = sx[v0], y = sy[v0], x1 = sx[v1], y1 = sy[v1];
+    const float cr = x * y1 - x1 * y;
+    s_cross = s_cross + cr;
+    s_cx = s_cx + (x + x1) * cr;
+    s_cy = s_cy + (y + y1) * cr;
+    s_mx = s_mx + x;
+    s_my = s_my + y;
+  }
+  const float area = 0.5f * s_cross;
+  const float cnt = count > 0 ? float(count) : 1.0f;
+  float cx, cy;
+  if (fabsf(area) < 1e-12f) { cx = s_mx / cnt; cy = s_my / cnt; }
+  else { cx = s_cx / (6.0f * area); cy = s_cy / (6.0f * area); }
+  const float dx = cx - com[0], dy = cy - com[ld];
+  out[t * ld + e] = sqrtf(dx * dx + dy * dy);
+}
+
+// =====================================================================================================
 // UnifiedCommand train.py:724-785
 // =====================================================================================================
 __global__ void __launch_bounds__(kThreads)
@@ -1033,6 +1112,15 @@ int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_no
   dim3 grid(groups4(n), (critic_obs && !skip_dump) ? 1 + 368 / kCopyRowsPerSection : 1, unsigned(T));
   KBS_LAUNCH(h, KBS_K_OBS, st, (obs_kernel<<<grid, kThreads, 0, st>>>(h->p, s, z, e, command, pg_carry, pg_reset, pg_lagged,
                                                                       computed, actor_obs, critic_obs, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_com_distance(kbs_handle* h, const int32_t* geom1, const int32_t* geom2, const float* pos, const float* com,
+                            float* out, int ncon, int64_t T, int64_t ld, int64_t n, cudaStream_t st) {
+  if (ncon < 3 || ncon > kMaxContacts) return KBS_E_SHAPE;
+  dim3 grid(unsigned((n + kThreads - 1) / kThreads), unsigned(T));
+  KBS_LAUNCH(h, KBS_K_OBS, st, (com_distance_kernel<<<grid, kThreads, 0, st>>>(geom1, geom2, pos, com, out, ncon, ld, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

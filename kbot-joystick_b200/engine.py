@@ -127,6 +127,16 @@ class KbotStep:
                                           L.ptr(critic_obs), n,
                                           _stream()), "kbs_observations")
 
+    def com_distance(self, geom1, geom2, pos, subtree_com_base, out=None, n_envs: int | None = None):
+        """COMDistanceObservation (train.py:509-659) for T steps: geom1/geom2 int32 [T, ncon, ld], pos [T, 3 ncon, ld],
+        subtree_com_base [T, 3, ld] -> [T, ld]."""
+        T, ncon, ld = geom1.shape
+        if out is None:
+            out = torch.empty((T, ld), device=pos.device)
+        L.check(self.lib.kbs_com_distance(self._h, L.ptr(geom1), L.ptr(geom2), L.ptr(pos), L.ptr(subtree_com_base), L.ptr(out),
+                                          ncon, T, ld, n_envs or ld, _stream()), "kbs_com_distance")
+        return out
+
     def upload_state(self, host_state: dict, dev_state: dict, stream: int | None = None) -> int:
         """Enqueue the H2D copy of T recorded steps ([T][rows][ld] per array; host tensors pinned): only the rows the path
         reads (kbs_upload_state).  Returns the bytes enqueued."""

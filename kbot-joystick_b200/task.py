@@ -149,6 +149,11 @@ class HumanoidWalkingTask:
                                  "value_mirror_loss": (out["values"] - m["values"]) ** 2}
         return ppo, model_carry
 
+    def com_distance(self, contact: dict, subtree_com_base, n_envs: int | None = None):
+        """COMDistanceObservation.observe (train.py:509-659) for T steps.  contact: geom1 / geom2 int32 [T, ncon, ld],
+        pos [T, 3 ncon, ld]; subtree_com_base [T, 3, ld] = data.subtree_com[2].  -> [T, ld] (the `com_distance` state row)."""
+        return self.engine.com_distance(contact["geom1"], contact["geom2"], contact["pos"], subtree_com_base, n_envs=n_envs)
+
     def mirror_joints(self, j, n_envs: int | None = None):
         """train.py:1574-1582 on `[T, 20, ld]`: negate all, swap the LEG halves only (as written)."""
         return self.engine.mirror_joints(j.contiguous(), n_envs=n_envs)

@@ -358,6 +358,87 @@ def critic_obs_from_dict(o: dict, cmd: np.ndarray) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------
+# O12 COMDistanceObservation  train.py:509-659  [R]
+# --------------------------------------------------------------------------------------
+
+
+def _com_distance_single(geom1, geom2, pos, com, dt):
+    """One env.  geom1/geom2 int [ncon], pos [ncon,3], com [3] (subtree_com[2]).  Loops follow the jnp code line by line:
+    observe (train.py:635-659), monotone_chain_hull (561-633), polygon_centroid_masked (519-559)."""
+    n = geom1.shape[0]
+    f = dt.type
+    # num_unique (train.py:642-647): distinct values of contact.geom2, padding entries included -- as written
+    sx = np.sort(geom2.ravel())
+    unique = 0 if n == 0 else int(np.sum(sx[1:] != sx[:-1])) + 1
+    if unique < 3:
+        return f(-1.0)
+    # feet_to_floor_contacts (train.py:637-638): non-floor rows become the origin and STAY in the point set
+    pts = np.where((geom1 == 0)[:, None], pos, np.zeros_like(pos))[:, :2].astype(dt)
+    order = np.lexsort((pts[:, 1], pts[:, 0])).astype(np.int32)              # by x then y, stable
+    spts = pts[order]
+
+    def cross(a, b, c):
+        return (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0])
+
+    def build(indices):
+        stack = -np.ones((n,), np.int32)
+        ptr = 0
+        for idx in indices:
+            while ptr >= 2 and cross(spts[stack[ptr - 2]], spts[stack[ptr - 1]], spts[idx]) <= 0:
+                stack[ptr - 1] = -1
+                ptr -= 1
+            stack[ptr] = idx
+            ptr += 1
+        return stack, ptr
+
+    sorted_idxs = np.arange(n, dtype=np.int32)
+    stack_l, ptr_l = build(sorted_idxs)
+    stack_u, ptr_u = build(sorted_idxs[::-1])
+    idxs = np.arange(n, dtype=np.int32)
+    lower_mask = idxs < max(ptr_l - 1, 0)
+    upper_mask = idxs < max(ptr_u - 1, 0)
+    hull_pos = np.concatenate([np.where(lower_mask, stack_l, -1), np.where(upper_mask, stack_u, -1)])
+    hull_mask = np.concatenate([lower_mask, upper_mask])
+    hull_pts = pts[order[np.where(hull_mask, hull_pos, 0)]]
+    # polygon_centroid_masked
+    L = hull_pts.shape[0]
+    ii = np.arange(L, dtype=np.int32)
+    count = int(hull_mask.sum())
+    valid = np.zeros((L,), np.int64)
+    nz = np.nonzero(hull_mask)[0]
+    valid[:nz.shape[0]] = nz                                                  # jnp.nonzero(size=L) pads with 0
+    packed = hull_pts[valid]
+    nxt = packed[np.where(ii + 1 < count, ii + 1, 0)]
+    edge = ((ii < max(count - 1, 0)) | ((ii == max(count - 1, 0)) & (count > 0))).astype(dt)
+    x, y, x1, y1 = packed[:, 0], packed[:, 1], nxt[:, 0], nxt[:, 1]
+    cr = (x * y1 - x1 * y) * edge
+    area = f(0.5) * np.sum(cr, dtype=dt)
+    first = (ii < max(count, 0)).astype(dt)
+    count_f = max(first.sum(dtype=dt), f(1.0))
+    mean_pt = np.sum(packed * first[:, None], axis=0, dtype=dt) / count_f
+    if abs(area) < 1e-12:
+        cx, cy = mean_pt[0], mean_pt[1]
+    else:
+        cx = np.sum((x + x1) * cr, dtype=dt) / (f(6.0) * area)
+        cy = np.sum((y + y1) * cr, dtype=dt) / (f(6.0) * area)
+    d = np.array([cx - com[0], cy - com[1]], dt)
+    return np.sqrt(np.sum(d * d, dtype=dt))
+
+
+def com_distance_observation(geom1, geom2, pos, subtree_com_base):
+    """[R] COMDistanceObservation.observe, train.py:635-659, batched over leading axes.
+    geom1, geom2 int [..., ncon]; pos [..., ncon, 3]; subtree_com_base [..., 3] (= data.subtree_com[2]) -> [...]."""
+    dt = pos.dtype
+    lead = geom1.shape[:-1]
+    g1 = geom1.reshape(-1, geom1.shape[-1]); g2 = geom2.reshape(-1, geom2.shape[-1])
+    ps = pos.reshape(-1, pos.shape[-2], 3); cm = subtree_com_base.reshape(-1, 3)
+    out = np.empty((g1.shape[0],), dt)
+    for i in range(g1.shape[0]):
+        out[i] = _com_distance_single(g1[i], g2[i], ps[i], cm[i], np.dtype(dt))
+    return out.reshape(lead)
+
+
+# --------------------------------------------------------------------------------------
 # Commands C1, C2   train.py:710-785, ranges 1206-1222
 # --------------------------------------------------------------------------------------
 

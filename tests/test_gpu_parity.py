@@ -94,6 +94,53 @@ def test_mirror_observations(eng, dev, T, N):
     exact(S(eng.mirror_joints(eng.mirror_joints(j, n_envs=N), n_envs=N), N, (20,)), S(j, N, (20,)), "mirror_joints twice")
 
 
+@pytest.mark.parametrize("ncon", [4, 8, 16])
+def test_com_distance_observation(eng, dev, ncon):
+    """O12 COMDistanceObservation (train.py:509-659): convex hull of the floor contacts (monotone chain) -> centroid ->
+    distance to subtree_com[2]; the < 3 distinct geoms branch (-1) and the selection are exact, the distance fp32."""
+    T, N = 3, 700
+    rng = np.random.default_rng(50 + ncon)
+    geom1 = rng.choice([0, 0, 0, 5], size=(T, N, ncon)).astype(np.int32)             # 0 = floor
+    geom2 = rng.choice([-1, 30, 31, 32, 33, 34, 35], size=(T, N, ncon)).astype(np.int32)
+    geom2[:, ::7] = 30                                                                # a block with < 3 distinct geoms
+    geom2[:, ::7, 0] = 31
+    pos = np.concatenate([rng.uniform(-0.3, 0.3, (T, N, ncon, 2)), rng.uniform(0, 0.02, (T, N, ncon, 1))], -1).astype(np.float32)
+    pos[:, 1::11, :, 1] = pos[:, 1::11, :, 0] * 0.5                                   # collinear: degenerate hull, fallback mean
+    pos[:, 2::13, 1:] = pos[:, 2::13, :1]                                             # all contacts at one point
+    com = np.concatenate([rng.uniform(-0.2, 0.2, (T, N, 2)), np.full((T, N, 1), 0.8)], -1).astype(np.float32)
+    ref = O.com_distance_observation(geom1, geom2, pos, com)
+    ref64 = O.com_distance_observation(geom1, geom2, pos.astype(np.float64), com.astype(np.float64))
+    out = eng.com_distance(synth.to_soa(geom1, 1, dev), synth.to_soa(geom2, 1, dev),
+                           synth.to_soa(pos.reshape(T, N, 3 * ncon), 1, dev), synth.to_soa(com, 1, dev), n_envs=N)
+    got = S(out, N)
+    exact(got < 0, ref < 0, "fewer than 3 distinct contact geoms -> -1")
+    assert (ref < 0).sum() > 0 and (ref >= 0).sum() > N
+    # the centroid divides by the hull area: conditioning ~ |coords|^3 / area; bound the fp32 oracle by the fp64 one too
+    tol = np.maximum(2e-5, 4 * np.abs(ref - ref64))
+    err = np.abs(got - ref)
+    assert (err <= tol + 1e-5 * np.abs(ref)).all(), (err.max(), np.argmax(err - tol))
+    # size-independent property: with all-floor contacts, translating every contact and the COM together leaves the
+    # distance unchanged (up to the conditioning of the centroid, bounded per env by the fp32-vs-fp64 oracle gap)
+    g1 = np.zeros_like(geom1)
+    shift = np.array([0.25, -0.5, 0.0], np.float32)
+    pos_s, com_s = pos + shift, com + shift
+
+    def gpu(p_, c_):
+        return S(eng.com_distance(synth.to_soa(g1, 1, dev), synth.to_soa(geom2, 1, dev),
+                                  synth.to_soa(p_.reshape(T, N, 3 * ncon), 1, dev), synth.to_soa(c_, 1, dev), n_envs=N), N)
+
+    a, bsh = gpu(pos, com), gpu(pos_s, com_s)
+    gap = (np.abs(O.com_distance_observation(g1, geom2, pos, com) -
+                  O.com_distance_observation(g1, geom2, pos.astype(np.float64), com.astype(np.float64))) +
+           np.abs(O.com_distance_observation(g1, geom2, pos_s, com_s) -
+                  O.com_distance_observation(g1, geom2, pos_s.astype(np.float64), com_s.astype(np.float64))))
+    regular = np.ones((T, N), bool)
+    regular[:, 1::11] = False          # the collinear / coincident constructions switch between the area formula and the
+    regular[:, 2::13] = False          # mean fallback under translation (|area| < 1e-12 is not translation invariant)
+    ok = (a >= 0) & regular
+    assert ok.sum() > N and (np.abs(a - bsh)[ok] <= 4 * gap[ok] + 5e-5).all()
+
+
 def test_observations_without_noise_twins_equal_clean(eng, dev):
     b = Batch(7, 1, 64, dev)
     aobs = torch.zeros((65, b.ld), device=dev)

@@ -246,3 +246,34 @@ def test_fp32_oracle_tracks_fp64():
             np.testing.assert_allclose(c32[k], c64[k], rtol=2e-3, atol=1e-6, err_msg=k)
         else:
             np.testing.assert_allclose(c32[k], c64[k], rtol=2e-4, atol=1e-6, err_msg=k)
+
+
+def test_com_distance_known_answers():
+    """O12 (train.py:509-659) on hand-checkable polygons: unit square -> centroid (0.5, 0.5); a triangle -> mean of its
+    vertices; interior points do not move the hull; < 3 distinct geom2 values -> -1; coincident points -> fallback mean."""
+    f = np.float32
+    sq = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 0.5, 0], [0.25, 0.75, 0]], f)
+    g1 = np.zeros((6,), np.int32)
+    g2 = np.array([7, 7, 12, 12, 3, 3], np.int32)
+    d = O.com_distance_observation(g1[None], g2[None], sq[None], np.array([[0.5, 0.5, 0.8]], f))
+    assert abs(float(d[0])) < 1e-6
+    d = O.com_distance_observation(g1[None], g2[None], sq[None], np.array([[3.5, 4.5, 0.8]], f))
+    np.testing.assert_allclose(d, [5.0], rtol=1e-6)                     # 3-4-5 triangle from the centroid
+    tri = np.array([[0, 0, 0], [3, 0, 0], [0, 3, 0], [1, 1, 0]], f)
+    d = O.com_distance_observation(np.zeros((1, 4), np.int32), np.array([[1, 2, 3, 3]], np.int32), tri[None],
+                                   np.array([[1, 1, 0]], f))
+    assert abs(float(d[0])) < 1e-6                                       # centroid of the triangle = (1, 1)
+    d = O.com_distance_observation(np.zeros((1, 4), np.int32), np.array([[1, 1, 2, 2]], np.int32), tri[None],
+                                   np.array([[1, 1, 0]], f))
+    assert float(d[0]) == -1.0                                           # 2 distinct geoms: not enough support
+    same = np.tile(np.array([[0.2, -0.1, 0]], f), (5, 1))
+    d = O.com_distance_observation(np.zeros((1, 5), np.int32), np.array([[1, 2, 3, 4, 5]], np.int32), same[None],
+                                   np.array([[0.2, -0.1, 0]], f))
+    assert abs(float(d[0])) < 1e-6                                       # degenerate hull -> mean of the vertices
+    # non-floor rows collapse to the origin and stay in the point set (as written, train.py:637-638)
+    g1b = np.array([0, 0, 0, 5], np.int32)
+    pts = np.array([[2, 2, 0], [3, 2, 0], [2, 3, 0], [9, 9, 9]], f)
+    d_with_origin = O.com_distance_observation(g1b[None], np.array([[1, 2, 3, 4]], np.int32), pts[None], np.zeros((1, 3), f))
+    d_tri_only = O.com_distance_observation(np.zeros((1, 3), np.int32), np.array([[1, 2, 3]], np.int32), pts[None, :3],
+                                            np.zeros((1, 3), f))
+    assert float(d_with_origin[0]) < float(d_tri_only[0])               # the origin pulls the hull centroid towards it
