@@ -183,7 +183,8 @@ __device__ __forceinline__ size_t fb_offset(int64_t row, int k, int H) {
 }
 
 // ---- the layer kernel -----------------------------------------------------------------------------------------------
-enum { MODE_LSTM = 0, MODE_PROJ = 1, MODE_RAW = 2 };
+enum { MODE_LSTM = 0, MODE_PROJ = 1, MODE_RAW = 2, MODE_PROJ_SOA = 3 };
+constexpr int kSoaWarps = 4;             // MODE_PROJ_SOA: warps 1..4 build the activation stage in shared memory, one row per thread
 struct LayerArgs {
   const char* x_sb;       // A blocks, first K segment: [panels][kb_x] blocks (layer input / observation rows)
   const char* h_sb_in;    // A blocks, second K segment: [panels][kb_h] blocks (h_{t-1}, reset where done_{t-1}); kb_h may be 0
@@ -201,6 +202,11 @@ struct LayerArgs {
   int H, kb_x, kb_h, mode;
   int panels, tiles;      // work items of this net = panels x tiles (panels = 0: net unused)
   int dbg;                // profiling only (KBS_TC_EPI_DEBUG): 1 = linear instead of sigmoid/tanh, 2 = no state stores
+  // MODE_PROJ_SOA: the A operand is built from env-major SoA observations [T][F][ld] by software producers (no packed
+  // staging buffer): rows = T x n_pad, row -> (t, env); features >= F and envs >= n_env are zero.  cinert / cvel != nullptr:
+  // features 80..447 come straight from the recorded state (critic's privileged dump, train.py:1405-1413).
+  const float* soa; const float* cinert; const float* cvel;
+  int F; int64_t soa_ld, n_env, n_pad;
 };
 struct LayerArgs2 { LayerArgs net[2]; };   // actor / critic share one launch
 
@@ -240,7 +246,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
   if (tr3 && threadIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); tr3[0] = (long long)gt; }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    const bool soa_mode = args.net[0].mode == MODE_PROJ_SOA;    // full[s]: the weight copy's expect_tx arrive + one arrive per row warp
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], soa_mode ? 1 + kSoaWarps : 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); mbar_init(&corr_init[b], 1);
     }
@@ -260,7 +267,70 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
   // every thread that touches memory written by the previous grid executes griddepcontrol.wait first (pdl_wait).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp >= kIssuers && warp < kIssuers + kProducers) {
+  if (args.net[0].mode == MODE_PROJ_SOA && warp >= 1 && warp <= kSoaWarps) {
+    // ===== software producers of the fused input projection: thread = one row (t, env) of the 128-row panel.  Per stage
+    // (K = 32 features) it reads 32 SoA rows at its env (a warp reads 32 consecutive envs: coalesced), splits them into
+    // the hi / lo planes and writes four 16-byte chunks per plane into the stage in UMMA layout; generic-proxy stores
+    // are made visible to the tensor core with fence.proxy.async before the warp arrives on full[s].  Warp 1's lane 0
+    // also issues the stage's weight block as a bulk copy.  Saves the packed staging buffer's write + read. =====
+    const int pw = warp - 1, r = pw * 32 + lane;
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // the observations come from the previous grid
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const WorkItem w = decode_item(args, item);
+      const LayerArgs& a = args.net[w.net];
+      const int64_t row = int64_t(w.panel) * kPanelRows + r;
+      const int64_t t = row / a.n_pad, e = row - t * a.n_pad;
+      const bool valid = e < a.n_env;
+      const char* wb = a.w_sb + size_t(w.tile) * a.kb_x * kBBlockBytes;
+      constexpr int kE = kbs_chunk_elems(KIND);             // features per 16-byte chunk: 8 (FP16) / 4 (TF32)
+      for (int b = 0; b < a.kb_x; ++b, ++g) {
+        const int s = g % kStages;
+        float x[4 * kE];
+#pragma unroll
+        for (int i = 0; i < 4 * kE; ++i) {
+          const int f = b * (4 * kE) + i;
+          x[i] = 0.0f;
+          if (valid && f < a.F) {
+            const float* p;
+            if (a.cinert && f >= 80 && f < 448) {
+              const int c = f - 80;
+              p = c < 230 ? a.cinert + (t * (10 * KBS_NBODY) + 10 + c) * a.soa_ld : a.cvel + (t * (6 * KBS_NBODY) + 6 + (c - 230)) * a.soa_ld;
+            } else {
+              p = a.soa + (t * a.F + f) * a.soa_ld;
+            }
+            x[i] = __ldcs(p + e);
+          }
+        }
+        mbar_wait(&empty[s], ((g / kStages) & 1) ^ 1);
+        uint8_t* sa = smem + size_t(s) * kStageBytes;
+        if (pw == 0 && lane == 0) {
+          mbar_expect_tx(&full[s], kBBlockBytes);
+          bulk_g2s(sa + kABlockBytes, wb + size_t(b) * kBBlockBytes, kBBlockBytes, &full[s]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                        // chunk c of the block: [part][chunk][row][16 B]
+          uint4 hi, lo;
+          if (KIND == KBS_KIND_F16) {
+            const float x0[4] = {x[8 * c], x[8 * c + 1], x[8 * c + 2], x[8 * c + 3]};
+            const float x1[4] = {x[8 * c + 4], x[8 * c + 5], x[8 * c + 6], x[8 * c + 7]};
+            const KbsSplit4 s0 = sb_split4<KIND>(x0), s1 = sb_split4<KIND>(x1);
+            hi = make_uint4(s0.hi.x, s0.hi.y, s1.hi.x, s1.hi.y);
+            lo = make_uint4(s0.lo.x, s0.lo.y, s1.lo.x, s1.lo.y);
+          } else {
+            const float x0[4] = {x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]};
+            const KbsSplit4 s0 = sb_split4<KIND>(x0);
+            hi = s0.hi; lo = s0.lo;
+          }
+          *reinterpret_cast<uint4*>(sa + c * 2048 + r * 16) = hi;
+          *reinterpret_cast<uint4*>(sa + 8192 + c * 2048 + r * 16) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+    }
+  } else if (args.net[0].mode != MODE_PROJ_SOA && warp >= kIssuers && warp < kIssuers + kProducers) {
     if (lane < 2) {
       // ===== producers: global stage g belongs to producer warp g % kProducers.  MEASURED (tools/bulk_copy_bench3.cu): a
       // cp.async.bulk blocks its issuing thread ~530 cycles (16 KB), so the two operand copies of a stage are issued by
@@ -400,7 +470,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
 #pragma unroll
       for (int i = 0; i < 64; ++i) v[i] += bs[i];
       if (!live) continue;
-      if (a.mode == MODE_PROJ) {
+      if (a.mode == MODE_PROJ || a.mode == MODE_PROJ_SOA) {
         const int col0 = w.tile * kTileCols + c2 * 64;
         if (col0 < H) {
 #pragma unroll
@@ -1542,30 +1612,45 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
                           int64_t ld, int64_t n, int64_t T, cudaStream_t st, const float* cinert, const float* cvel) {
   const int H = h->p.hidden_size, kind = tc_kind(h);
   const int64_t np = pad_rows(n);
+  // Default: pack kernel -> SB staging buffer -> bulk copies.  KBS_PROJ_FUSED=1: the projection kernel's producer warps
+  // read the SoA observations themselves (MODE_PROJ_SOA).  MEASURED: 3.87 ms instead of 0.45 + 0.49 ms per 100-step
+  // rollout -- 128 threads x 32 register-staged loads are ~16 KB in flight per SM where HBM latency needs ~90 KB; the
+  // fused form needs an asynchronous (bulk-copy) first stage, which is round-2 work.
+  static int staged = -1;
+  if (staged < 0) { const char* e = getenv("KBS_PROJ_FUSED"); staged = (e && atoi(e)) ? 0 : 1; }
   LayerArgs2 a2{};
   for (int k = 0; k < nets; ++k) {
     const KbsNet& N = h->net[k];
     if (!N.packed || !N.tc_image) return KBS_E_STATE;
     const int Kp = proj_kp(h, k);
-    const int64_t total = T * np * (Kp / 8);
-    const unsigned gb = unsigned((total + 255) / 256);
-    char* osb = reinterpret_cast<char*>(obs_sb[k]);
     const float* ci = (k == KBS_NET_CRITIC) ? cinert : nullptr;
     const float* cv = (k == KBS_NET_CRITIC) ? cvel : nullptr;
-    if (kind == KBS_KIND_TF32)
-      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv)));
-    else
-      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv)));
+    char* osb = reinterpret_cast<char*>(obs_sb[k]);
     LayerArgs& a = a2.net[k];
+    if (staged) {
+      const int64_t total = T * np * (Kp / 8);
+      const unsigned gb = unsigned((total + 255) / 256);
+      if (kind == KBS_KIND_TF32)
+        KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv)));
+      else
+        KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv)));
+      a.mode = MODE_PROJ;
+    } else {
+      // fused: the projection kernel's producer warps read the SoA observations (and the critic's cinert / cvel dump from the
+      // recorded state) themselves and build the MMA operand in shared memory
+      a.mode = MODE_PROJ_SOA;
+      a.soa = obs_soa[k]; a.cinert = ci; a.cvel = cv; a.F = N.num_in; a.soa_ld = ld; a.n_env = n; a.n_pad = np;
+    }
     a.x_sb = osb;
     a.h_sb_in = osb;
     a.w_sb = proj_w(h, k);
     a.bias_t = proj_bias(h, k);
     a.x_next_sb = reinterpret_cast<char*>(x_sb_all[k]);
     a.n = T * np;                    // every staged row is written (pad rows carry the bias: harmless, never read back)
-    a.H = H; a.kb_x = Kp / kbs_block_k(kind); a.kb_h = 0; a.mode = MODE_PROJ;
+    a.H = H; a.kb_x = Kp / kbs_block_k(kind); a.kb_h = 0;
     a.panels = int(T * np / kPanelRows); a.tiles = proj_cols(h) / kTileCols;
   }
+  if (nets == 1) a2.net[1].mode = a2.net[0].mode;
   KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (launch_layer(h, kind, a2, st)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
