@@ -1038,33 +1038,41 @@ command_scan_kernel(const __grid_constant__ kbs_params P, float* __restrict__ co
                     const float* __restrict__ u_arms, const uint8_t* __restrict__ done, int64_t T, int64_t ld, int64_t n) {
   const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
   if (e >= n) return;
-  float c[16];
+  // thread = (env, command row k = blockIdx.y): 16x the threads of a one-thread-per-env walk (4 096 envs alone fill only
+  // 32 SMs and the kernel is pure latency); the switch decisions are re-derived per row (two loads per step) and fetched
+  // 10 steps at a time, the row's new value is computed only on a switch.
+  const int k = blockIdx.y;
+  float c = command[k * ld + e];
+  constexpr int kB = 10;
+  for (int64_t t0 = 0; t0 < T; t0 += kB) {
+    bool swv[kB];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) c[k] = command[k * ld + e];
-  for (int64_t t = 0; t < T; ++t) {
-    const bool sw = (done[t * ld + e] != 0) || (u_switch[t * ld + e] < P.switch_prob);
-    if (sw) {
-      const int m = mode[t * ld + e];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const float v = P.cmd_lo[k] + u6[(t * 6 + k) * ld + e] * (P.cmd_hi[k] - P.cmd_lo[k]);
-        bool on;
-        if (k == 0) on = (m == 0) || (m == 3);
-        else if (k == 1) on = (m == 1) || (m == 3);
-        else if (k == 2) on = (m == 2) || (m == 3);
-        else on = (m == 4);
-        c[k] = on ? v : 0.0f;
-      }
-#pragma unroll
-      for (int k = 0; k < 10; ++k) {
-        const float u = u_arms[(t * 10 + k) * ld + e];
-        const float arm = (P.arm_lo[k] + u * (P.arm_hi[k] - P.arm_lo[k])) * ((u < 0.5f) ? 1.0f : 0.0f);
-        c[6 + k] = (m == 3 || m == 4) ? arm : 0.0f;
-      }
+    for (int i = 0; i < kB; ++i) {
+      const int64_t t = t0 + i;
+      swv[i] = t < T && ((done[t * ld + e] != 0) || (u_switch[t * ld + e] < P.switch_prob));
     }
-    float* out = command + (t + 1) * KBS_NUM_COMMANDS * ld + e;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) out[k * ld] = c[k];
+    for (int i = 0; i < kB; ++i) {
+      const int64_t t = t0 + i;
+      if (t >= T) break;
+      if (swv[i]) {
+        const int m = mode[t * ld + e];
+        if (k < 6) {
+          const float v = P.cmd_lo[k] + u6[(t * 6 + k) * ld + e] * (P.cmd_hi[k] - P.cmd_lo[k]);
+          bool on;
+          if (k == 0) on = (m == 0) || (m == 3);
+          else if (k == 1) on = (m == 1) || (m == 3);
+          else if (k == 2) on = (m == 2) || (m == 3);
+          else on = (m == 4);
+          c = on ? v : 0.0f;
+        } else {
+          const float u = u_arms[(t * 10 + (k - 6)) * ld + e];
+          const float arm = (P.arm_lo[k - 6] + u * (P.arm_hi[k - 6] - P.arm_lo[k - 6])) * ((u < 0.5f) ? 1.0f : 0.0f);
+          c = (m == 3 || m == 4) ? arm : 0.0f;
+        }
+      }
+      command[((t + 1) * KBS_NUM_COMMANDS + k) * ld + e] = c;
+    }
   }
 }
 
@@ -1078,18 +1086,32 @@ pg_scan_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ s
   if (e >= n) return;
   const float lag = lag_p ? lag_p[e] : 0.0f;
   float x[3] = {pg_carry[e], pg_carry[ld + e], pg_carry[2 * ld + e]};
-  for (int64_t t = 0; t < T; ++t) {
-    const float* sd = sensordata + (t * KBS_NSENSORDATA + P.sd_imu_quat) * ld + e;
-    const float q[4] = {sd[0], sd[ld], sd[2 * ld], sd[3 * ld]};
-    const float g[3] = {0.0f, 0.0f, -P.gravity};
-    float gb[3];
-    rotate_vec(g, q, true, P.eps_quat, gb);
-    const bool rs = (t > 0) && (done[(t - 1) * ld + e] != 0);
+  // the inputs of step t do not depend on the recurrence: fetch 8 steps at a time so the load latencies overlap
+  constexpr int kB = 8;
+  for (int64_t t0 = 0; t0 < T; t0 += kB) {
+    float qv[kB][4];
+    bool rsv[kB];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float pv = rs ? gb[k] : x[k];
-      x[k] = lag * pv + (1.0f - lag) * gb[k];
-      lagged[(t * 3 + k) * ld + e] = x[k];
+    for (int i = 0; i < kB; ++i) {
+      const int64_t t = t0 + i < T ? t0 + i : T - 1;
+      const float* sd = sensordata + (t * KBS_NSENSORDATA + P.sd_imu_quat) * ld + e;
+      qv[i][0] = sd[0]; qv[i][1] = sd[ld]; qv[i][2] = sd[2 * ld]; qv[i][3] = sd[3 * ld];
+      rsv[i] = (t > 0) && (done[(t - 1) * ld + e] != 0);
+    }
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+      const int64_t t = t0 + i;
+      if (t >= T) break;
+      const float q[4] = {qv[i][0], qv[i][1], qv[i][2], qv[i][3]};
+      const float g[3] = {0.0f, 0.0f, -P.gravity};
+      float gb[3];
+      rotate_vec(g, q, true, P.eps_quat, gb);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float pv = rsv[i] ? gb[k] : x[k];
+        x[k] = lag * pv + (1.0f - lag) * gb[k];
+        lagged[(t * 3 + k) * ld + e] = x[k];
+      }
     }
   }
   pg_carry[e] = x[0]; pg_carry[ld + e] = x[1]; pg_carry[2 * ld + e] = x[2];
@@ -1153,7 +1175,7 @@ int kbs_launch_command(kbs_handle* h, const float* cmd_in, float* cmd_out, const
 int kbs_launch_command_scan(kbs_handle* h, float* command, const float* u_switch, const int32_t* mode, const float* u6,
                             const float* u_arms, const uint8_t* done, int64_t T, int64_t ld, int64_t n, cudaStream_t st) {
   KBS_LAUNCH(h, KBS_K_COMMAND, st,
-             (command_scan_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(h->p, command, u_switch, mode,
+             (command_scan_kernel<<<dim3(unsigned((n + kThreads - 1) / kThreads), KBS_NUM_COMMANDS), kThreads, 0, st>>>(h->p, command, u_switch, mode,
                                                                                               u6, u_arms, done, T, ld, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
