@@ -161,6 +161,28 @@ int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_vie
                      const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs,
                      int64_t n_envs, void* stream);
 
+/* Replaces: ksim.compute_ppo_loss inside PPOTask (hyper-parameters: entropy_coef train.py:1767; the rest are ksim defaults,
+ * unverified): clipped surrogate + (clipped) value loss + entropy bonus over a stored trajectory, reduced to means.
+ *   ratio = exp(clip(log_probs - old_log_probs, +-log_clip_value)); policy = min(ratio A, clip(ratio, 1 +- eps) A)
+ *   value = 0.5 max((tgt - v)^2, (tgt - (v_old + clip(v - v_old, +-eps)))^2)  (0.5 (tgt - v)^2 when not clipped)
+ *   objective = policy - value_loss_coef value + entropy_coef entropy
+ * All inputs [T][ld] (log-probs / entropy summed over the action dimensions, as kbs_ppo_variables returns them).
+ * out (device, 4 floats): loss = -mean(objective), mean policy, mean value, mean entropy; the reduction order is fixed
+ * (bitwise reproducible).  per_step [T][ld] optional: the objective per transition. */
+typedef struct kbs_ppo_loss_params {
+  float clip_param, value_loss_coef, entropy_coef, log_clip_value;
+  int32_t use_clipped_value_loss;
+} kbs_ppo_loss_params;
+typedef struct kbs_ppo_loss_io {
+  const float* log_probs; const float* old_log_probs; const float* advantages;
+  const float* values; const float* old_values; const float* value_targets; const float* entropy;
+  float* per_step;
+  float* out;
+  int64_t T, ld;
+} kbs_ppo_loss_io;
+int kbs_ppo_loss_default_params(kbs_ppo_loss_params* p);
+int kbs_ppo_loss(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo_loss_io* io, int64_t n_envs, void* stream);
+
 /* Replaces: COMDistanceObservation.observe (train.py:509-659): distance between subtree_com[2].xy and the centroid of the
  * convex hull (Andrew's monotone chain) of the floor-contact points, -1 when fewer than 3 distinct contact.geom2 values.
  *   contact_geom1 / contact_geom2  int32 [T][ncon][ld]   (MJX contact.geom1 / geom2, padding included)

@@ -285,6 +285,7 @@ int kbs_destroy(kbs_handle* h) {
   }
   cudaFree(h->scratch);
   cudaFree(h->persist_status);
+  cudaFree(h->loss_ticket);
   if (h->side_stream) {
     cudaStreamDestroy(h->side_stream);
     cudaStreamDestroy(h->aux_stream);
@@ -402,6 +403,23 @@ int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_vie
   if (reinterpret_cast<uintptr_t>(pg_reset) & 3u) return KBS_E_ALIGN;
   return kbs_launch_observations(h, *s, noise, ep, command, pg_carry, pg_reset, computed, actor_obs, critic_obs, n,
                                  (cudaStream_t)stream);
+}
+
+int kbs_ppo_loss_default_params(kbs_ppo_loss_params* p) {
+  REQ(p);
+  p->clip_param = 0.2f; p->value_loss_coef = 0.5f; p->entropy_coef = 0.004f /* train.py:1767 */; p->log_clip_value = 10.0f;
+  p->use_clipped_value_loss = 1;
+  return KBS_OK;
+}
+
+int kbs_ppo_loss(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo_loss_io* io, int64_t n, void* stream) {
+  REQ(h); REQ(params); REQ(io);
+  REQ(io->log_probs); REQ(io->old_log_probs); REQ(io->advantages); REQ(io->values); REQ(io->value_targets); REQ(io->entropy);
+  REQ(io->out);
+  if (params->use_clipped_value_loss) REQ(io->old_values);
+  if (io->T <= 0) return KBS_E_SHAPE;
+  if (n <= 0 || io->ld < n) return KBS_E_SHAPE;
+  return kbs_launch_ppo_loss(h, *params, *io, n, (cudaStream_t)stream);
 }
 
 int kbs_com_distance(kbs_handle* h, const int32_t* contact_geom1, const int32_t* contact_geom2, const float* contact_pos,

@@ -69,6 +69,7 @@ struct kbs_handle {
   cudaStream_t aux_stream = nullptr;          // chunked observation / input-projection phase of the fused rollout
   cudaEvent_t ev_pre = nullptr, ev_chunk[8] = {};
   cudaEvent_t ev_lstm[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr};
+  unsigned int* loss_ticket = nullptr;        // "last block" counter of ppo_loss_kernel
   unsigned int* persist_status = nullptr;     // device word set by rollout_persist_kernel when a dependency wait times out
   long long* trace_buf = nullptr;
   int64_t trace_step = -1;
@@ -100,6 +101,7 @@ int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_no
                             const kbs_episode_view* ep, const float* command, float* pg_carry,
                             const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n,
                             cudaStream_t st, int64_t T = 1, const float* pg_lagged = nullptr, bool skip_dump = false);
+int kbs_launch_ppo_loss(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_ppo_loss_io& io, int64_t n, cudaStream_t st);
 int kbs_launch_com_distance(kbs_handle* h, const int32_t* geom1, const int32_t* geom2, const float* pos, const float* com,
                             float* out, int ncon, int64_t T, int64_t ld, int64_t n, cudaStream_t st);
 int kbs_launch_mirror_obs(kbs_handle* h, const kbs_state_view& s, const float* computed, const float* command,

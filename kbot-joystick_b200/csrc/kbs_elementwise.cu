@@ -522,6 +522,70 @@ com_distance_kernel(const int32_t* __restrict__ geom1, const int32_t* __restrict
 }
 
 // =====================================================================================================
+// PPO loss (ksim.compute_ppo_loss [U], entropy_coef train.py:1767): clipped surrogate + (clipped) value loss + entropy
+// bonus, reduced to four means.  Deterministic: fixed per-thread strides, warp-shuffle + shared-memory tree per block,
+// and the last block to finish (ticket counter) adds the per-block partials in block order.
+// =====================================================================================================
+constexpr int kLossThreads = 256;
+
+__global__ void __launch_bounds__(kLossThreads)
+ppo_loss_kernel(kbs_ppo_loss_params L, kbs_ppo_loss_io io, int64_t n, double* __restrict__ partials,
+                unsigned int* __restrict__ ticket) {
+  const int64_t ld = io.ld, total = io.T * ld;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};                 // objective, policy, value, entropy
+  for (int64_t i = int64_t(blockIdx.x) * kLossThreads + threadIdx.x; i < total; i += int64_t(gridDim.x) * kLossThreads) {
+    const int64_t e = i % ld;
+    if (e >= n) continue;
+    const float lp = io.log_probs[i], lpo = io.old_log_probs[i], adv = io.advantages[i], v = io.values[i];
+    const float tgt = io.value_targets[i], ent = io.entropy[i];
+    const float lr = fminf(fmaxf(lp - lpo, -L.log_clip_value), L.log_clip_value);
+    const float ratio = expf(lr);
+    const float pol = fminf(ratio * adv, fminf(fmaxf(ratio, 1.0f - L.clip_param), 1.0f + L.clip_param) * adv);
+    const float err = tgt - v;
+    float val = 0.5f * (err * err);
+    if (L.use_clipped_value_loss) {
+      const float vo = io.old_values[i];
+      const float vc = vo + fminf(fmaxf(v - vo, -L.clip_param), L.clip_param);
+      const float errc = tgt - vc;
+      val = 0.5f * fmaxf(err * err, errc * errc);
+    }
+    const float obj = (pol - L.value_loss_coef * val) + L.entropy_coef * ent;
+    if (io.per_step) io.per_step[i] = obj;
+    s[0] += obj; s[1] += pol; s[2] += val; s[3] += ent;
+  }
+  __shared__ double red[kLossThreads / 32][4];
+  __shared__ bool last;
+  double d[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    d[k] = double(s[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d[k] += __shfl_down_sync(0xffffffffu, d[k], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { for (int k = 0; k < 4; ++k) red[warp][k] = d[k]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) {
+      double a = 0.0;
+      for (int w = 0; w < kLossThreads / 32; ++w) a += red[w][k];
+      partials[size_t(blockIdx.x) * 4 + k] = a;
+    }
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 4) {
+    __threadfence();
+    double a = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) a += partials[size_t(b) * 4 + threadIdx.x];   // block order: deterministic
+    const double mean = a / (double(io.T) * double(n));
+    io.out[threadIdx.x] = float(threadIdx.x == 0 ? -mean : mean);
+    if (threadIdx.x == 0) *ticket = 0u;              // re-arm for the next call on this stream
+  }
+}
+
+// =====================================================================================================
 // UnifiedCommand train.py:724-785
 // =====================================================================================================
 __global__ void __launch_bounds__(kThreads)
@@ -1134,6 +1198,23 @@ int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_no
   dim3 grid(groups4(n), (critic_obs && !skip_dump) ? 1 + 368 / kCopyRowsPerSection : 1, unsigned(T));
   KBS_LAUNCH(h, KBS_K_OBS, st, (obs_kernel<<<grid, kThreads, 0, st>>>(h->p, s, z, e, command, pg_carry, pg_reset, pg_lagged,
                                                                       computed, actor_obs, critic_obs, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_ppo_loss(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_ppo_loss_io& io, int64_t n, cudaStream_t st) {
+  const int64_t total = io.T * io.ld;
+  int blocks = int((total + kLossThreads * 8 - 1) / (kLossThreads * 8));
+  if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
+  if (blocks < 1) blocks = 1;
+  int rc = kbs_scratch_reserve(h, size_t(blocks) * 8 + 16);
+  if (rc) return rc;
+  double* partials = reinterpret_cast<double*>(h->scratch);
+  if (!h->loss_ticket) {
+    KBS_CUDA_TRY(cudaMalloc(&h->loss_ticket, 256));
+    KBS_CUDA_TRY(cudaMemsetAsync(h->loss_ticket, 0, 256, st));
+  }
+  KBS_LAUNCH(h, KBS_K_GAE, st, (ppo_loss_kernel<<<blocks, kLossThreads, 0, st>>>(L, io, n, partials, h->loss_ticket)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

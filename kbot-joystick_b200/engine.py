@@ -127,6 +127,24 @@ class KbotStep:
                                           L.ptr(critic_obs), n,
                                           _stream()), "kbs_observations")
 
+    def ppo_loss(self, log_probs, old_log_probs, advantages, values, old_values, value_targets, entropy,
+                 per_step=None, n_envs: int | None = None, **hyper) -> torch.Tensor:
+        """ksim.compute_ppo_loss on [T, ld] arrays -> device tensor [loss, mean policy, mean value, mean entropy].
+        hyper: clip_param, value_loss_coef, entropy_coef, log_clip_value, use_clipped_value_loss (kbs_ppo_loss_params)."""
+        T, ld = log_probs.shape
+        lp = L.KbsPpoLossParams()
+        L.check(self.lib.kbs_ppo_loss_default_params(C.byref(lp)), "kbs_ppo_loss_default_params")
+        for k, v in hyper.items():
+            setattr(lp, k, v)
+        out = torch.empty((4,), device=log_probs.device)
+        io = L.KbsPpoLossIO()
+        io.log_probs, io.old_log_probs, io.advantages = L.ptr(log_probs), L.ptr(old_log_probs), L.ptr(advantages)
+        io.values, io.old_values, io.value_targets = L.ptr(values), L.ptr(old_values), L.ptr(value_targets)
+        io.entropy, io.per_step, io.out = L.ptr(entropy), L.ptr(per_step), L.ptr(out)
+        io.T, io.ld = T, ld
+        L.check(self.lib.kbs_ppo_loss(self._h, C.byref(lp), C.byref(io), n_envs or ld, _stream()), "kbs_ppo_loss")
+        return out
+
     def com_distance(self, geom1, geom2, pos, subtree_com_base, out=None, n_envs: int | None = None):
         """COMDistanceObservation (train.py:509-659) for T steps: geom1/geom2 int32 [T, ncon, ld], pos [T, 3 ncon, ld],
         subtree_com_base [T, 3, ld] -> [T, ld]."""

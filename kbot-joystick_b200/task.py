@@ -187,6 +187,16 @@ class HumanoidWalkingTask:
         """ksim.compute_ppo_inputs (GAE), gamma / lam from the config (train.py:1769-1770)."""
         return self.engine.gae(values, rewards, done, success, n_envs=n_envs)
 
+    def compute_ppo_loss(self, ppo_variables: dict, old_ppo_variables: dict, advantages, value_targets,
+                         n_envs: int | None = None, **hyper):
+        """ksim.compute_ppo_loss (forward): clipped surrogate + value loss + entropy bonus, entropy_coef = 0.004
+        (train.py:1767).  *_variables: the dicts get_ppo_variables returns ([T, 1, ld] log_probs / entropy, [T, ld] values).
+        -> device tensor [loss, mean policy objective, mean value objective, mean entropy]."""
+        sq = lambda x: x.squeeze(1).contiguous() if x.dim() == 3 else x
+        return self.engine.ppo_loss(sq(ppo_variables["log_probs"]), sq(old_ppo_variables["log_probs"]), advantages,
+                                    ppo_variables["values"], old_ppo_variables["values"], value_targets,
+                                    sq(ppo_variables["entropy"]), n_envs=n_envs, **hyper)
+
     def rollout(self, io: dict, n_envs: int) -> None:
         """The fused control step over T recorded steps (ksim step_engine around mjx.step)."""
         self.engine.rollout(io, n_envs)

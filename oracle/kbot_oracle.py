@@ -678,6 +678,36 @@ def get_ppo_variables(w_actor, w_critic, traj_obs: list, traj_cmd, traj_action, 
 
 
 # --------------------------------------------------------------------------------------
+# PPO loss [U: ksim.compute_ppo_loss; entropy_coef train.py:1767]
+# --------------------------------------------------------------------------------------
+
+
+def ppo_loss(log_probs, old_log_probs, advantages, values, old_values, value_targets, entropy, clip_param=0.2,
+             value_loss_coef=0.5, entropy_coef=0.004, log_clip_value=10.0, use_clipped_value_loss=True):
+    """[U] ksim.compute_ppo_loss restated from its published form (oracle-defined, reference-unverified):
+      ratio     = exp(clip(log_probs - old_log_probs, +-log_clip_value))
+      policy    = min(ratio A, clip(ratio, 1 - eps, 1 + eps) A)
+      value     = 0.5 max((target - v)^2, (target - (v_old + clip(v - v_old, +-eps)))^2)   (unclipped: 0.5 (target - v)^2)
+      objective = policy - value_loss_coef value + entropy_coef entropy;    loss = -mean(objective)
+    All arrays [T, N] (log-probs / entropy already summed over the 20 action dimensions).
+    Returns (loss, mean policy, mean value, mean entropy, per-step objective [T, N])."""
+    dt = log_probs.dtype
+    c = lambda v: np.asarray(v, dt)
+    log_ratio = np.clip(log_probs - old_log_probs, -c(log_clip_value), c(log_clip_value))
+    ratio = np.exp(log_ratio)
+    pol = np.minimum(ratio * advantages, np.clip(ratio, c(1.0) - c(clip_param), c(1.0) + c(clip_param)) * advantages)
+    err = value_targets - values
+    val = c(0.5) * err * err
+    if use_clipped_value_loss:
+        vc = old_values + np.clip(values - old_values, -c(clip_param), c(clip_param))
+        errc = value_targets - vc
+        val = c(0.5) * np.maximum(err * err, errc * errc)
+    obj = pol - c(value_loss_coef) * val + c(entropy_coef) * entropy
+    f64 = np.float64
+    return (-obj.astype(f64).mean(), pol.astype(f64).mean(), val.astype(f64).mean(), entropy.astype(f64).mean(), obj)
+
+
+# --------------------------------------------------------------------------------------
 # Actuators A1 [U fork]  train.py:1091-1105
 # --------------------------------------------------------------------------------------
 

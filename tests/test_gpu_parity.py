@@ -507,6 +507,31 @@ def test_rollout_then_rewards_gae_chain(dev):
     e.close()
 
 
+@pytest.mark.parametrize("T,N,clipped", [(7, 33, True), (100, 4096, True), (20, 1001, False)])
+def test_ppo_loss(eng, dev, T, N, clipped):
+    """ksim.compute_ppo_loss (clipped surrogate + value loss + entropy bonus) as one deterministic reduction."""
+    rng = np.random.default_rng(77 + N)
+    f = np.float32
+    old_lp = rng.normal(-20, 5, (T, N)).astype(f)
+    lp = (old_lp + rng.normal(0, 0.3, (T, N))).astype(f)
+    lp[0, 0] = old_lp[0, 0] + 30.0                                    # beyond log_clip_value
+    adv = rng.normal(0, 1, (T, N)).astype(f)
+    v_old = rng.normal(0, 1, (T, N)).astype(f)
+    v = (v_old + rng.normal(0, 0.3, (T, N))).astype(f)
+    tgt = (v_old + rng.normal(0, 0.5, (T, N))).astype(f)
+    ent = rng.normal(25, 3, (T, N)).astype(f)
+    ref = O.ppo_loss(lp, old_lp, adv, v, v_old, tgt, ent, use_clipped_value_loss=clipped)
+    d = lambda a: synth.to_soa(a, 1, dev)
+    per = torch.full((T, (N + 3) // 4 * 4), float("nan"), device=dev)
+    args = (d(lp), d(old_lp), d(adv), d(v), d(v_old), d(tgt), d(ent))
+    out = eng.ppo_loss(*args, per_step=per, n_envs=N, use_clipped_value_loss=int(clipped))
+    got = out.cpu().numpy()
+    close(got, np.array(ref[:4], np.float32), "loss, mean policy / value / entropy", atol=1e-6)
+    close(S(per, N), ref[4], "per-step objective", atol=1e-5)
+    again = eng.ppo_loss(*args, n_envs=N, use_clipped_value_loss=int(clipped))
+    assert torch.equal(out, again), "the reduction order is fixed: bitwise reproducible"
+
+
 def test_error_codes(eng, dev):
     lib = L.load()
     assert lib.kbs_version() == 100

@@ -277,3 +277,22 @@ def test_com_distance_known_answers():
     d_tri_only = O.com_distance_observation(np.zeros((1, 3), np.int32), np.array([[1, 2, 3]], np.int32), pts[None, :3],
                                             np.zeros((1, 3), f))
     assert float(d_with_origin[0]) < float(d_tri_only[0])               # the origin pulls the hull centroid towards it
+
+
+def test_ppo_loss_known_answers():
+    """PPO loss restatement: on-policy data (ratio = 1) gives policy = A; a ratio outside the clip range with a positive
+    advantage is capped at (1 + eps) A; the clipped value loss takes the larger of the two squared errors."""
+    f = np.float32
+    one = np.ones((2, 3), f)
+    lp = np.zeros((2, 3), f)
+    loss, pol, val, ent, obj = O.ppo_loss(lp, lp, 2 * one, one, one, one, 3 * one, entropy_coef=0.5)
+    assert pol == 2.0 and val == 0.0 and ent == 3.0 and loss == -(2.0 + 0.5 * 3.0)
+    _, pol, _, _, _ = O.ppo_loss(lp + f(np.log(2.0)), lp, one, one, one, one, one)          # ratio 2, A = 1 -> 1.2
+    np.testing.assert_allclose(pol, 1.2, rtol=1e-6)
+    _, pol, _, _, _ = O.ppo_loss(lp + f(np.log(2.0)), lp, -one, one, one, one, one)         # ratio 2, A = -1 -> -2
+    np.testing.assert_allclose(pol, -2.0, rtol=1e-6)
+    # v moved 1.0 away from v_old = 0 towards the target 1: unclipped error 0, clipped value = 0.2 -> error 0.8
+    _, _, val, _, _ = O.ppo_loss(lp, lp, one, one, 0 * one, one, one)
+    np.testing.assert_allclose(val, 0.5 * 0.8 ** 2, rtol=1e-6)
+    _, _, val, _, _ = O.ppo_loss(lp, lp, one, one, 0 * one, one, one, use_clipped_value_loss=False)
+    assert val == 0.0
