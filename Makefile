@@ -5,7 +5,7 @@ PKG := kbot-joystick_b200
 SRC := $(PKG)/csrc
 OUT := $(PKG)/libkbotstep.so
 COMMON := -O3 -std=c++17 -lineinfo $(ARCH) -Iinclude -I$(SRC) -Xcompiler -fPIC -Xptxas -v
-OBJS := $(SRC)/kbs_api.o $(SRC)/kbs_elementwise.o $(SRC)/kbs_net_simt.o $(SRC)/kbs_net_tc.o
+OBJS := $(SRC)/kbs_api.o $(SRC)/kbs_elementwise.o $(SRC)/kbs_net_simt.o $(SRC)/kbs_net_tc.o $(SRC)/kbs_ppo_update.o
 
 all: $(OUT)
 

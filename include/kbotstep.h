@@ -183,6 +183,44 @@ typedef struct kbs_ppo_loss_io {
 int kbs_ppo_loss_default_params(kbs_ppo_loss_params* p);
 int kbs_ppo_loss(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo_loss_io* io, int64_t n_envs, void* stream);
 
+/* Replaces: jax.grad of the PPO minibatch loss through get_ppo_variables (train.py:1435-1524) -- back-propagation through
+ * time through both LSTM stacks, the projections, the actor head (softplus std, clamp, one-pole low-pass of the mean) and
+ * ksim.compute_ppo_loss [U] (kbs_ppo_loss_params) -- for one minibatch of n stored trajectories of T steps (BASELINE
+ * configs[3]; the per-rank gradients are then all-reduced over NCCL by the caller).
+ *   batch: env-major SoA arrays as kbs_ppo_variables takes them; *_carry0 [depth][2][n][H] / lpf0 [20][ld] = the carries
+ *          at the first step (NULL = zeros, get_initial_model_carry)
+ *   actor / critic: gradient buffers in the eqx layout of kbs_net_weights (written): w_in [H][num_in], b_in [H],
+ *          w_ih / w_hh [4H][H], b [4H] per layer, w_out [num_out][H], b_out [num_out]
+ *   log_probs / values / entropy [T][ld]: the forward outputs (written); stats_out: device, 4 floats as kbs_ppo_loss.
+ * First version: fp32 FFMA GEMMs, deterministic (no atomics). */
+typedef struct kbs_ppo_batch {
+  const float* actor_obs;      /* [T][65][ld] */
+  const float* critic_obs;     /* [T][475][ld] */
+  const float* action;         /* [T][20][ld] */
+  const uint8_t* done;         /* [T][ld] */
+  const float* old_log_probs;  /* [T][ld] */
+  const float* advantages;     /* [T][ld] */
+  const float* value_targets;  /* [T][ld] */
+  const float* old_values;     /* [T][ld] */
+  const float* actor_carry0;   /* [depth][2][n][H] or NULL */
+  const float* critic_carry0;  /* [depth][2][n][H] or NULL */
+  const float* lpf0;           /* [20][ld] or NULL */
+  int64_t T, ld;
+} kbs_ppo_batch;
+typedef struct kbs_net_grads {
+  float* w_in;  float* b_in;
+  float* w_ih[KBS_MAX_DEPTH]; float* w_hh[KBS_MAX_DEPTH]; float* b[KBS_MAX_DEPTH];
+  float* w_out; float* b_out;
+} kbs_net_grads;
+int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo_batch* batch, const kbs_net_grads* actor,
+                 const kbs_net_grads* critic, float* log_probs, float* values, float* entropy, float* stats_out,
+                 int64_t n_envs, void* stream);
+/* Replaces: optax.adam (train.py:1057-1063: scale_by_adam, eps_root = 0, then -learning_rate) on one flat parameter
+ * array: g = grad * grad_scale (1 / world_size after a sum all-reduce, or a global-norm clip factor);
+ * m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2; p -= lr (m / (1 - b1^step)) / (sqrt(v / (1 - b2^step)) + eps).  step >= 1. */
+int kbs_adam_step(kbs_handle* h, float* param, const float* grad, float* m, float* v, int64_t count, float lr, float b1,
+                  float b2, float eps, float grad_scale, int64_t step, void* stream);
+
 /* Replaces: COMDistanceObservation.observe (train.py:509-659): distance between subtree_com[2].xy and the centroid of the
  * convex hull (Andrew's monotone chain) of the floor-contact points, -1 when fewer than 3 distinct contact.geom2 values.
  *   contact_geom1 / contact_geom2  int32 [T][ncon][ld]   (MJX contact.geom1 / geom2, padding included)

@@ -102,6 +102,8 @@ int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_no
                             const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs, int64_t n,
                             cudaStream_t st, int64_t T = 1, const float* pg_lagged = nullptr, bool skip_dump = false);
 int kbs_launch_ppo_loss(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_ppo_loss_io& io, int64_t n, cudaStream_t st);
+int kbs_launch_ppo_loss_at(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_ppo_loss_io& io, int64_t n, double* partials,
+                           cudaStream_t st);
 int kbs_launch_com_distance(kbs_handle* h, const int32_t* geom1, const int32_t* geom2, const float* pos, const float* com,
                             float* out, int ncon, int64_t T, int64_t ld, int64_t n, cudaStream_t st);
 int kbs_launch_mirror_obs(kbs_handle* h, const kbs_state_view& s, const float* computed, const float* command,
@@ -135,6 +137,10 @@ int kbs_simt_trunk(kbs_handle* h, int net, const float* obs_soa, int64_t ld, flo
                    float* out_rowmajor /*[n][nout_pad]*/, int64_t n, cudaStream_t st);
 size_t kbs_simt_scratch_floats(const kbs_handle* h, int64_t n);
 
+int kbs_simt_gemm_nt(kbs_handle* h, const float* A, int64_t lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                     int64_t M, int Npad, int K, int accumulate, cudaStream_t st, int batch = 1, int64_t a_ts = 0, int64_t c_ts = 0);
+int kbs_simt_gemm_tn(kbs_handle* h, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int64_t K,
+                     float* partials, int splits, cudaStream_t st);
 int kbs_simt_in_proj(kbs_handle* h, int net, const float* obs_soa, int64_t ld, float* x_rm, int64_t n, cudaStream_t st);
 int kbs_simt_out_proj(kbs_handle* h, int net, const float* h_rm, float* out_rm, int64_t n, cudaStream_t st);
 

@@ -1202,14 +1202,24 @@ int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_no
   return KBS_OK;
 }
 
-int kbs_launch_ppo_loss(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_ppo_loss_io& io, int64_t n, cudaStream_t st) {
+static int ppo_loss_blocks(const kbs_handle* h, const kbs_ppo_loss_io& io) {
   const int64_t total = io.T * io.ld;
   int blocks = int((total + kLossThreads * 8 - 1) / (kLossThreads * 8));
   if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
-  if (blocks < 1) blocks = 1;
+  return blocks < 1 ? 1 : blocks;
+}
+
+int kbs_launch_ppo_loss(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_ppo_loss_io& io, int64_t n, cudaStream_t st) {
+  const int blocks = ppo_loss_blocks(h, io);
   int rc = kbs_scratch_reserve(h, size_t(blocks) * 8 + 16);
   if (rc) return rc;
-  double* partials = reinterpret_cast<double*>(h->scratch);
+  return kbs_launch_ppo_loss_at(h, L, io, n, reinterpret_cast<double*>(h->scratch), st);
+}
+
+// partials: >= 4 * 4 * num_sms doubles of caller-provided device scratch
+int kbs_launch_ppo_loss_at(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_ppo_loss_io& io, int64_t n, double* partials,
+                           cudaStream_t st) {
+  const int blocks = ppo_loss_blocks(h, io);
   if (!h->loss_ticket) {
     KBS_CUDA_TRY(cudaMalloc(&h->loss_ticket, 256));
     KBS_CUDA_TRY(cudaMemsetAsync(h->loss_ticket, 0, 256, st));

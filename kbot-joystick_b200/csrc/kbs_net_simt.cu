@@ -70,6 +70,59 @@ gemm_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
   }
 }
 
+// C[m][n] = sum_k A[k][m] B[k][n] over k in [k0, k1) of this split (gridDim.z splits; partial z goes to C + z * M * ldc).
+// A: [K][lda] (M columns), B: [K][ldb] (N columns), both read along their contiguous axis.  M % 64 == 0, N % 64 == 0.
+// Used by the PPO update for the weight gradients dW = dG^T X summed over (t, env).
+__global__ void __launch_bounds__(256)
+gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+               int M, int64_t K) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int64_t per = (K + gridDim.z - 1) / gridDim.z;
+  const int64_t kb = int64_t(blockIdx.z) * per, ke = (kb + per < K) ? kb + per : K;
+  C += size_t(blockIdx.z) * size_t(M) * ldc;
+  float acc[4][4] = {};
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+    const int k = tid >> 4, c4 = (tid & 15) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (k0 + k < ke) {
+      a = *reinterpret_cast<const float4*>(A + (k0 + k) * lda + m0 + c4);
+      b = *reinterpret_cast<const float4*>(B + (k0 + k) * ldb + n0 + c4);
+    }
+    *reinterpret_cast<float4*>(&As[k][c4]) = a;
+    *reinterpret_cast<float4*>(&Bs[k][c4]) = b;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 av4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bv4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {av4.x, av4.y, av4.z, av4.w}, bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(C + size_t(m0 + ty * 4 + i) * ldc + n0 + tx * 4) =
+        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+}
+
+// out[i] = sum_s partial[s][i]  (fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+reduce_splits_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_t count, int splits) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= count) return;
+  float a = 0.0f;
+  for (int s = 0; s < splits; ++s) a += partial[size_t(s) * count + i];
+  out[i] = a;
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // eqx LSTMCell: i,f,g,o = split(lin, 4); c' = s(f) c + s(i) tanh(g); h' = s(o) tanh(c').
@@ -197,6 +250,33 @@ int kbs_simt_pack(kbs_handle* h, int net, const kbs_net_weights* w, cudaStream_t
   if ((rc = pad_copy(h, w->w_out, &N.w_out, N.num_out, H, N.nout_pad, H, st))) return rc;
   if ((rc = pad_copy(h, w->b_out, &N.b_out, 1, N.num_out, 1, N.nout_pad, st))) return rc;
   N.packed = true;
+  return KBS_OK;
+}
+
+// ---- plain fp32 GEMM launchers for the PPO update (kbs_ppo_update.cu) ----
+// C[M][ldc] (+)= A[M][lda] . W[Npad][ldw]^T + bias; batch > 1 walks gridDim.z with the given strides (floats)
+int kbs_simt_gemm_nt(kbs_handle* h, const float* A, int64_t lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                     int64_t M, int Npad, int K, int accumulate, cudaStream_t st, int batch, int64_t a_ts, int64_t c_ts) {
+  if (Npad % BN || K % BK) return KBS_E_SHAPE;
+  const unsigned mb = unsigned((M + BM - 1) / BM);
+  KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+             (gemm_nt_kernel<false><<<dim3(mb, Npad / BN, batch), 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, K, K, accumulate,
+                                                                                a_ts, c_ts)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+// C[M][ldc] = sum_k A[k][0..M) x B[k][0..N): split-K over `splits` partial buffers (partials: splits x M x ldc floats),
+// reduced in a fixed order
+int kbs_simt_gemm_tn(kbs_handle* h, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int64_t K,
+                     float* partials, int splits, cudaStream_t st) {
+  if (M % BM || N % BN || ldc < N) return KBS_E_SHAPE;
+  KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+             (gemm_tn_kernel<<<dim3(M / BM, N / BN, splits), 256, 0, st>>>(A, lda, B, ldb, partials, ldc, M, K)));
+  const int64_t count = int64_t(M) * ldc;
+  KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+             (reduce_splits_kernel<<<unsigned((count + 255) / 256), 256, 0, st>>>(partials, C, count, splits)));
+  KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
 

@@ -1,0 +1,444 @@
+// kbs_ppo_update.cu -- gradients of the PPO minibatch loss (BASELINE configs[3]) and the Adam step.
+//
+// Replaces, for one minibatch of stored trajectories: jax.grad of ksim's PPO loss through get_ppo_variables
+// (train.py:1435-1524: actor log-prob / entropy of the stored action + critic value per step, carries reset where
+// done) -- i.e. back-propagation through time through both 2-layer LSTMs, the input / output projections, the actor
+// head (softplus std, clamp, one-pole low-pass on the mean: a second recurrence in time) and the loss
+// (ksim.compute_ppo_loss [U], kbs_ppo_loss).  Optimiser: optax.adam (train.py:1057-1063).
+//
+// First correct version: fp32 FFMA GEMMs (gemm_nt / split-K gemm_tn of kbs_net_simt.cu), one launch per (step, layer)
+// for the recurrent part, everything that is not recurrent batched over all T x n rows.  The forward pass stores what
+// the backward pass needs (activated gates, cell states, layer inputs).  Deterministic: no atomics.
+#include <math.h>
+
+#include "kbs_common.cuh"
+
+namespace {
+
+constexpr int kT = 256;
+inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+
+// env-major SoA observations [T][F][ld] -> row-major [T*n][kp] (features >= F zero)
+__global__ void __launch_bounds__(kT)
+soa_to_rows_kernel(const float* __restrict__ soa, int F, int64_t ld, float* __restrict__ rm, int kp, int64_t n, int64_t T) {
+  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (idx >= T * n * kp) return;
+  const int f = int(idx % kp);
+  const int64_t row = idx / kp;
+  const int64_t t = row / n, e = row - t * n;
+  rm[idx] = f < F ? soa[(t * F + f) * ld + e] : 0.0f;
+}
+
+__global__ void __launch_bounds__(kT)
+transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {   // out[c][r] = in[r][c]
+  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (idx >= int64_t(rows) * cols) return;
+  const int r = int(idx / cols), c = int(idx % cols);
+  out[size_t(c) * rows + r] = in[idx];
+}
+
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// eqx LSTMCell forward with everything the backward pass needs.  gates_pre [n][4H] (bias added).
+//   ga [n][4H] = (s(i), s(f), tanh(g), s(o)); cs [n][H] = c_t; hs [n][H] = h_t (un-reset: next layer's input);
+//   h_next_in / c_next_in [n][H] = the carries step t+1 reads (reset where done, train.py:1502-1506), or nullptr at t = T-1.
+__global__ void __launch_bounds__(kT)
+cell_fwd_save_kernel(const float* __restrict__ gates_pre, const float* __restrict__ c_in, float* __restrict__ ga,
+                     float* __restrict__ cs, float* __restrict__ hs, float* __restrict__ h_next_in,
+                     float* __restrict__ c_next_in, const uint8_t* __restrict__ done, int H, int64_t n) {
+  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (idx >= n * H) return;
+  const int64_t e = idx / H;
+  const int k = int(idx - e * H);
+  const float* g = gates_pre + e * 4 * H;
+  const float i = sigm(g[k]), f = sigm(g[H + k]), gg = tanhf(g[2 * H + k]), o = sigm(g[3 * H + k]);
+  const float c = f * c_in[idx] + i * gg;
+  const float h = o * tanhf(c);
+  float* a = ga + e * 4 * H;
+  a[k] = i; a[H + k] = f; a[2 * H + k] = gg; a[3 * H + k] = o;
+  cs[idx] = c;
+  hs[idx] = h;
+  if (h_next_in) {
+    const bool rst = done && done[e];
+    h_next_in[idx] = rst ? 0.0f : h;
+    c_next_in[idx] = rst ? 0.0f : c;
+  }
+}
+
+// LSTMCell backward at step t.  dh_in: gradient wrt h_t from above (next layer's dx or the head); dh_rec / dc_rec:
+// gradients wrt the carries step t+1 read (they see keep_t h_t, keep_t c_t).  Writes dG [n][4H] (pre-activation
+// gradients, eqx order) and overwrites dc_rec with the gradient wrt c_in of this step.
+__global__ void __launch_bounds__(kT)
+cell_bwd_kernel(const float* __restrict__ dh_in, const float* __restrict__ dh_rec, float* __restrict__ dc_rec,
+                const float* __restrict__ ga, const float* __restrict__ cs, const float* __restrict__ c_in,
+                const uint8_t* __restrict__ done, float* __restrict__ dG, int H, int64_t n) {
+  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (idx >= n * H) return;
+  const int64_t e = idx / H;
+  const int k = int(idx - e * H);
+  const float keep = (done && done[e]) ? 0.0f : 1.0f;
+  const float* a = ga + e * 4 * H;
+  const float i = a[k], f = a[H + k], g = a[2 * H + k], o = a[3 * H + k];
+  const float tc = tanhf(cs[idx]);
+  const float dh = dh_in[idx] + keep * dh_rec[idx];
+  const float dc = keep * dc_rec[idx] + dh * o * (1.0f - tc * tc);
+  float* d = dG + e * 4 * H;
+  d[k] = dc * g * i * (1.0f - i);
+  d[H + k] = dc * c_in[idx] * f * (1.0f - f);
+  d[2 * H + k] = dc * i * (1.0f - g * g);
+  d[3 * H + k] = dh * tc * o * (1.0f - o);
+  dc_rec[idx] = dc * f;
+}
+
+// out[c] partial column sums over a chunk of rows: partial[chunk][c]
+__global__ void __launch_bounds__(kT)
+colsum_partial_kernel(const float* __restrict__ X, int ld, int64_t rows, int cols, int64_t rows_per_chunk, float* __restrict__ partial) {
+  const int c = blockIdx.x * kT + threadIdx.x;
+  if (c >= cols) return;
+  const int64_t r0 = int64_t(blockIdx.y) * rows_per_chunk, r1 = (r0 + rows_per_chunk < rows) ? r0 + rows_per_chunk : rows;
+  float a = 0.0f;
+  for (int64_t r = r0; r < r1; ++r) a += X[r * ld + c];
+  partial[size_t(blockIdx.y) * cols + c] = a;
+}
+__global__ void __launch_bounds__(kT)
+reduce_rows_kernel(const float* __restrict__ partial, int chunks, int cols, float* __restrict__ out) {
+  const int c = blockIdx.x * kT + threadIdx.x;
+  if (c >= cols) return;
+  float a = 0.0f;
+  for (int s = 0; s < chunks; ++s) a += partial[size_t(s) * cols + c];
+  out[c] = a;
+}
+
+// copy the leading [rows][cols] block of a [.][ld] matrix into a dense [rows][cols] one
+__global__ void __launch_bounds__(kT)
+copy_block_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int rows, int cols) {
+  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (idx >= int64_t(rows) * cols) return;
+  const int r = int(idx / cols), c = int(idx % cols);
+  dst[idx] = src[size_t(r) * ld + c];
+}
+
+// Actor head: forward over t (std, mean, low-pass, log-prob / entropy of the stored action, train.py:924-939, 1452,
+// 1486), then the loss gradient and the backward pass of the head including the reverse scan of the low-pass filter.
+// One thread per env (the filter is a recurrence in time; 20 joints per thread).
+//   out [T*n][64] row-major (mean rows 0..19, std rows 20..39); dout same shape (written; columns >= 40 zero)
+//   y_s, sd_s [T][20][ld] scratch (filtered mean, std); log_prob, entropy [T][ld] out
+__global__ void __launch_bounds__(128)
+actor_head_fwd_bwd_kernel(const __grid_constant__ kbs_params P, kbs_ppo_loss_params L, const float* __restrict__ out,
+                          const float* __restrict__ actor_obs, const float* __restrict__ action, const uint8_t* __restrict__ done,
+                          const float* __restrict__ lpf0, const float* __restrict__ old_lp, const float* __restrict__ adv,
+                          float* __restrict__ y_s, float* __restrict__ sd_s, float* __restrict__ log_prob,
+                          float* __restrict__ entropy, float* __restrict__ dout, int64_t T, int64_t ld, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (e >= n) return;
+  constexpr float kHalfLog2Pi = 0.918938533204672742f;
+  float y[KBS_NUM_JOINTS];
+#pragma unroll
+  for (int j = 0; j < KBS_NUM_JOINTS; ++j) y[j] = lpf0 ? lpf0[j * ld + e] : 0.0f;
+  for (int64_t t = 0; t < T; ++t) {
+    const float* o = out + (t * n + e) * 64;
+    float s_z = 0.0f, s_log = 0.0f;
+#pragma unroll
+    for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+      const float sraw = o[KBS_NUM_JOINTS + j];
+      const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
+      const float sd = fminf((sp + P.min_std) * P.var_scale, P.max_std);
+      float m = o[j] + P.joint_bias[j];
+      if (j >= 10) m = m + actor_obs[(t * KBS_ACTOR_OBS + 55 + (j - 10)) * ld + e];
+      y[j] = y[j] + P.lpf_alpha * (m - y[j]);
+      const int64_t so = (t * KBS_NUM_JOINTS + j) * ld + e;
+      y_s[so] = y[j];
+      sd_s[so] = sd;
+      const float z = (action[so] - y[j]) / sd;
+      s_z = s_z + (-0.5f * z * z - kHalfLog2Pi);
+      s_log = s_log + logf(sd);
+    }
+    log_prob[t * ld + e] = s_z - s_log;
+    entropy[t * ld + e] = s_log + float(KBS_NUM_JOINTS) * (0.5f + kHalfLog2Pi);
+    if (done[t * ld + e]) {
+#pragma unroll
+      for (int j = 0; j < KBS_NUM_JOINTS; ++j) y[j] = 0.0f;
+    }
+  }
+  // backward
+  const float inv = 1.0f / (float(T) * float(n));
+  float gy[KBS_NUM_JOINTS];
+#pragma unroll
+  for (int j = 0; j < KBS_NUM_JOINTS; ++j) gy[j] = 0.0f;
+  for (int64_t t = T - 1; t >= 0; --t) {
+    const float lr = log_prob[t * ld + e] - old_lp[t * ld + e];
+    const float lrc = fminf(fmaxf(lr, -L.log_clip_value), L.log_clip_value);
+    const float r = expf(lrc);
+    const float a = adv[t * ld + e];
+    const float dr = (fabsf(lr) <= L.log_clip_value) ? r : 0.0f;                        // d r / d log_prob
+    const bool inside = r >= 1.0f - L.clip_param && r <= 1.0f + L.clip_param;
+    const float rc = fminf(fmaxf(r, 1.0f - L.clip_param), 1.0f + L.clip_param);
+    const float dpol = (inside || r * a < rc * a) ? a * dr : 0.0f;                      // d policy / d log_prob
+    const float glp = -inv * dpol, gent = -inv * L.entropy_coef;                        // d loss / d log_prob, d entropy
+    const float keep = done[t * ld + e] ? 0.0f : 1.0f;
+    const float* o = out + (t * n + e) * 64;
+    float* d = dout + (t * n + e) * 64;
+#pragma unroll
+    for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+      const int64_t so = (t * KBS_NUM_JOINTS + j) * ld + e;
+      const float sd = sd_s[so], yy = y_s[so];
+      const float z = (action[so] - yy) / sd;
+      const float dmu = glp * z / sd;
+      const float dsd = (glp * (z * z - 1.0f) + gent) / sd;
+      const float sraw = o[KBS_NUM_JOINTS + j];
+      const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
+      const bool clamped = (sp + P.min_std) * P.var_scale > P.max_std;
+      d[KBS_NUM_JOINTS + j] = clamped ? 0.0f : dsd * P.var_scale * sigm(sraw);
+      gy[j] = dmu + (1.0f - P.lpf_alpha) * keep * gy[j];      // y_{t+1} = (1 - alpha) keep_t y_t + alpha m_{t+1}
+      d[j] = P.lpf_alpha * gy[j];
+    }
+#pragma unroll
+    for (int j = 2 * KBS_NUM_JOINTS; j < 64; ++j) d[j] = 0.0f;
+  }
+}
+
+// Critic head: value_t = out[t][e][0]; dout[.][0] = d loss / d value (clipped value loss), other columns zero.
+__global__ void __launch_bounds__(kT)
+critic_head_fwd_bwd_kernel(kbs_ppo_loss_params L, const float* __restrict__ out, const float* __restrict__ old_values,
+                           const float* __restrict__ targets, float* __restrict__ values, float* __restrict__ dout, int64_t T,
+                           int64_t ld, int64_t n) {
+  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (idx >= T * n) return;
+  const int64_t t = idx / n, e = idx - t * n;
+  const float v = out[idx * 64];
+  values[t * ld + e] = v;
+  const float tgt = targets[t * ld + e];
+  const float err = tgt - v;
+  float dval = -err;                                        // d (0.5 err^2) / d v
+  if (L.use_clipped_value_loss) {
+    const float vo = old_values[t * ld + e];
+    const float dv = v - vo;
+    const float errc = tgt - (vo + fminf(fmaxf(dv, -L.clip_param), L.clip_param));
+    if (fabsf(dv) > L.clip_param) dval = (err * err > errc * errc) ? -err : 0.0f;   // the clipped branch has no gradient
+  }
+  float* d = dout + idx * 64;
+  d[0] = L.value_loss_coef * dval / (float(T) * float(n));
+#pragma unroll
+  for (int j = 1; j < 64; ++j) d[j] = 0.0f;
+}
+
+__global__ void __launch_bounds__(kT)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t count,
+            float lr, float b1, float b2, float eps, float grad_scale, float bc1, float bc2) {
+  const int64_t i = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (i >= count) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  p[i] = p[i] - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);       // optax.scale_by_adam (eps_root = 0) then -lr
+}
+
+unsigned blocks(int64_t n) { return unsigned((n + kT - 1) / kT); }
+
+struct NetWork {      // per-net workspace (floats), carved from the handle's scratch
+  float* obs_rm; float* x0; float* out; float* dout; float* dh_top; float* dx0;
+  float* ga[KBS_MAX_DEPTH]; float* cs[KBS_MAX_DEPTH]; float* hs[KBS_MAX_DEPTH]; float* h_in[KBS_MAX_DEPTH]; float* c_in[KBS_MAX_DEPTH];
+  float* dG[KBS_MAX_DEPTH];
+  float* w_ihT[KBS_MAX_DEPTH]; float* w_hhT[KBS_MAX_DEPTH]; float* w_outT;
+};
+
+size_t net_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n) {
+  const size_t H = size_t(h->p.hidden_size), rows = size_t(T) * size_t(n);
+  const size_t kp = size_t(round_up_i(h->net[net].num_in, 64));
+  size_t f = rows * kp + rows * H * 3 /*x0, dh_top, dx0*/ + rows * 64 * 2;
+  f += size_t(h->p.depth) * (rows * 4 * H * 2 + rows * H * 4 + 2 * 4 * H * H);
+  f += 64 * H;
+  return f + 1024;
+}
+
+float* carve(float*& p, size_t floats) { float* r = p; p += (floats + 63) / 64 * 64; return r; }
+
+int run_net(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0, NetWork& w, float* gates_pre, float* dx_up,
+            float* dh_rec, float* dc_rec, float* part, int splits, int64_t n, cudaStream_t st, bool backward,
+            const kbs_net_grads* g) {
+  const KbsNet& N = h->net[net];
+  const int H = h->p.hidden_size, depth = h->p.depth;
+  const int64_t T = b.T, ld = b.ld, rows = T * n;
+  const int kp = round_up_i(N.num_in, 64);
+  const size_t sH = size_t(n) * H;
+  int rc;
+  if (!backward) {
+    const float* obs = net == KBS_NET_ACTOR ? b.actor_obs : b.critic_obs;
+    KBS_LAUNCH(h, KBS_K_PACK, st, (soa_to_rows_kernel<<<blocks(rows * kp), kT, 0, st>>>(obs, N.num_in, ld, w.obs_rm, kp, n, T)));
+    if ((rc = kbs_simt_gemm_nt(h, w.obs_rm, kp, N.w_in, N.kin_pad, N.b_in, w.x0, H, rows, H, N.kin_pad, 0, st))) return rc;
+    for (int l = 0; l < depth; ++l) {       // carries the first step reads: ABI layout [depth][2][n][H] or zeros
+      if (carry0) {
+        KBS_CUDA_TRY(cudaMemcpyAsync(w.h_in[l], carry0 + (size_t(l) * 2 + 0) * sH, sH * 4, cudaMemcpyDeviceToDevice, st));
+        KBS_CUDA_TRY(cudaMemcpyAsync(w.c_in[l], carry0 + (size_t(l) * 2 + 1) * sH, sH * 4, cudaMemcpyDeviceToDevice, st));
+      } else {
+        KBS_CUDA_TRY(cudaMemsetAsync(w.h_in[l], 0, sH * 4, st));
+        KBS_CUDA_TRY(cudaMemsetAsync(w.c_in[l], 0, sH * 4, st));
+      }
+    }
+    for (int64_t t = 0; t < T; ++t) {
+      for (int l = 0; l < depth; ++l) {
+        const float* x_in = (l == 0 ? w.x0 : w.hs[l - 1]) + size_t(t) * sH;
+        if ((rc = kbs_simt_gemm_nt(h, x_in, H, N.w_ih[l], H, N.b[l], gates_pre, 4 * H, n, 4 * H, H, 0, st))) return rc;
+        if ((rc = kbs_simt_gemm_nt(h, w.h_in[l] + size_t(t) * sH, H, N.w_hh[l], H, nullptr, gates_pre, 4 * H, n, 4 * H, H, 1, st)))
+          return rc;
+        const bool last = t + 1 == T;
+        KBS_LAUNCH(h, KBS_K_LSTM_CELL, st,
+                   (cell_fwd_save_kernel<<<blocks(n * H), kT, 0, st>>>(
+                       gates_pre, w.c_in[l] + size_t(t) * sH, w.ga[l] + size_t(t) * sH * 4, w.cs[l] + size_t(t) * sH,
+                       w.hs[l] + size_t(t) * sH, last ? nullptr : w.h_in[l] + size_t(t + 1) * sH,
+                       last ? nullptr : w.c_in[l] + size_t(t + 1) * sH, b.done + t * ld, H, n)));
+      }
+    }
+    if ((rc = kbs_simt_gemm_nt(h, w.hs[depth - 1], H, N.w_out, H, N.b_out, w.out, 64, rows, 64, H, 0, st))) return rc;
+    KBS_LAUNCH_CHECK();
+    return KBS_OK;
+  }
+  // ---- backward: w.dout [rows][64] holds d loss / d out ----
+  for (int l = 0; l < depth; ++l) {
+    KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(4) * H * H), kT, 0, st>>>(N.w_ih[l], 4 * H, H, w.w_ihT[l])));
+    KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(4) * H * H), kT, 0, st>>>(N.w_hh[l], 4 * H, H, w.w_hhT[l])));
+  }
+  KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(64) * H), kT, 0, st>>>(N.w_out, 64, H, w.w_outT)));
+  if ((rc = kbs_simt_gemm_nt(h, w.dout, 64, w.w_outT, 64, nullptr, w.dh_top, H, rows, H, 64, 0, st))) return rc;
+  for (int l = 0; l < depth; ++l) {
+    KBS_CUDA_TRY(cudaMemsetAsync(dh_rec + size_t(l) * sH, 0, sH * 4, st));
+    KBS_CUDA_TRY(cudaMemsetAsync(dc_rec + size_t(l) * sH, 0, sH * 4, st));
+  }
+  for (int64_t t = T - 1; t >= 0; --t) {
+    for (int l = depth - 1; l >= 0; --l) {
+      const float* dh_in = (l == depth - 1) ? w.dh_top + size_t(t) * sH : dx_up;
+      float* dG = w.dG[l] + size_t(t) * sH * 4;
+      KBS_LAUNCH(h, KBS_K_LSTM_CELL, st,
+                 (cell_bwd_kernel<<<blocks(n * H), kT, 0, st>>>(dh_in, dh_rec + size_t(l) * sH, dc_rec + size_t(l) * sH,
+                                                                w.ga[l] + size_t(t) * sH * 4, w.cs[l] + size_t(t) * sH,
+                                                                w.c_in[l] + size_t(t) * sH, b.done + t * ld, dG, H, n)));
+      float* dx = (l == 0) ? w.dx0 + size_t(t) * sH : dx_up;
+      if ((rc = kbs_simt_gemm_nt(h, dG, 4 * H, w.w_ihT[l], 4 * H, nullptr, dx, H, n, H, 4 * H, 0, st))) return rc;
+      if (t > 0 && (rc = kbs_simt_gemm_nt(h, dG, 4 * H, w.w_hhT[l], 4 * H, nullptr, dh_rec + size_t(l) * sH, H, n, H, 4 * H, 0, st)))
+        return rc;
+    }
+  }
+  // weight gradients: sums over all (t, env) rows
+  const int chunks = int((rows + 511) / 512);
+  auto colsum = [&](const float* X, int ldx, int cols, float* out) {
+    KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st, (colsum_partial_kernel<<<dim3(blocks(cols), chunks), kT, 0, st>>>(X, ldx, rows, cols, 512, part)));
+    KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st, (reduce_rows_kernel<<<blocks(cols), kT, 0, st>>>(part, chunks, cols, out)));
+  };
+  float* part2 = part + size_t(chunks) * 4 * H;          // split-K partials of gemm_tn behind the column-sum partials
+  for (int l = 0; l < depth; ++l) {
+    const float* x_l = l == 0 ? w.x0 : w.hs[l - 1];
+    if ((rc = kbs_simt_gemm_tn(h, w.dG[l], 4 * H, x_l, H, g->w_ih[l], H, 4 * H, H, rows, part2, splits, st))) return rc;
+    if ((rc = kbs_simt_gemm_tn(h, w.dG[l], 4 * H, w.h_in[l], H, g->w_hh[l], H, 4 * H, H, rows, part2, splits, st))) return rc;
+    colsum(w.dG[l], 4 * H, 4 * H, g->b[l]);
+  }
+  {
+    // dW_in [H][kp] -> caller's dense [H][num_in]; dW_out [64][H] -> first num_out rows
+    float* tmp = part2 + size_t(splits) * size_t(4 * H) * size_t(kp > H ? kp : H);
+    if ((rc = kbs_simt_gemm_tn(h, w.dx0, H, w.obs_rm, kp, tmp, kp, H, kp, rows, part2, splits, st))) return rc;
+    KBS_LAUNCH(h, KBS_K_PACK, st, (copy_block_kernel<<<blocks(int64_t(H) * N.num_in), kT, 0, st>>>(tmp, kp, g->w_in, H, N.num_in)));
+    colsum(w.dx0, H, H, g->b_in);
+    if ((rc = kbs_simt_gemm_tn(h, w.dout, 64, w.hs[depth - 1], H, tmp, H, 64, H, rows, part2, splits, st))) return rc;
+    KBS_LAUNCH(h, KBS_K_PACK, st, (copy_block_kernel<<<blocks(int64_t(N.num_out) * H), kT, 0, st>>>(tmp, H, g->w_out, N.num_out, H)));
+    float* bsum = tmp + size_t(64) * H;
+    colsum(w.dout, 64, 64, bsum);
+    KBS_CUDA_TRY(cudaMemcpyAsync(g->b_out, bsum, size_t(N.num_out) * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo_batch* b, const kbs_net_grads* actor,
+                 const kbs_net_grads* critic, float* log_probs, float* values, float* entropy, float* stats_out, int64_t n,
+                 void* stream) {
+  if (!h || !params || !b || !actor || !critic || !log_probs || !values || !entropy || !stats_out) return KBS_E_NULL;
+  if (!b->actor_obs || !b->critic_obs || !b->action || !b->done || !b->old_log_probs || !b->advantages || !b->value_targets ||
+      !b->old_values)
+    return KBS_E_NULL;
+  if (b->T <= 0 || n <= 0 || b->ld < n || (b->ld & 3)) return KBS_E_SHAPE;
+  for (int k = 0; k < 2; ++k)
+    if (!h->net[k].packed) return KBS_E_STATE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = h->p.hidden_size, depth = h->p.depth;
+  const int64_t T = b->T, ld = b->ld, rows = T * n;
+  const size_t sH = size_t(n) * H;
+  const int splits = 8;
+  const int chunks = int((rows + 511) / 512);
+  const int kp_max = round_up_i(KBS_CRITIC_OBS, 64);
+  const size_t shared_f = sH * 4 /*gates_pre*/ + sH /*dx_up*/ + 2 * size_t(depth) * sH /*dh_rec, dc_rec*/ +
+                          size_t(chunks) * 4 * H + size_t(splits) * size_t(4 * H) * size_t(kp_max) + size_t(H) * kp_max + 64 * H + 4096 +
+                          2 * size_t(T) * KBS_NUM_JOINTS * ld /*y_s, sd_s*/;
+  const size_t total_f = shared_f + net_work_floats(h, 0, T, n) + net_work_floats(h, 1, T, n) + 8192;
+  int rc = kbs_scratch_reserve(h, total_f);
+  if (rc) return rc;
+  float* p = h->scratch;
+  float* gates_pre = carve(p, sH * 4);
+  float* dx_up = carve(p, sH);
+  float* dh_rec = carve(p, size_t(depth) * sH);
+  float* dc_rec = carve(p, size_t(depth) * sH);
+  float* part = carve(p, size_t(chunks) * 4 * H + size_t(splits) * size_t(4 * H) * size_t(kp_max) + size_t(H) * kp_max + 64 * H + 4096);
+  float* y_s = carve(p, size_t(T) * KBS_NUM_JOINTS * ld);
+  float* sd_s = carve(p, size_t(T) * KBS_NUM_JOINTS * ld);
+  NetWork w[2];
+  for (int k = 0; k < 2; ++k) {
+    const size_t kp = size_t(round_up_i(h->net[k].num_in, 64));
+    w[k].obs_rm = carve(p, size_t(rows) * kp);
+    w[k].x0 = carve(p, size_t(rows) * H);
+    w[k].dh_top = carve(p, size_t(rows) * H);
+    w[k].dx0 = carve(p, size_t(rows) * H);
+    w[k].out = carve(p, size_t(rows) * 64);
+    w[k].dout = carve(p, size_t(rows) * 64);
+    for (int l = 0; l < depth; ++l) {
+      w[k].ga[l] = carve(p, size_t(rows) * 4 * H);
+      w[k].dG[l] = carve(p, size_t(rows) * 4 * H);
+      w[k].cs[l] = carve(p, size_t(rows) * H);
+      w[k].hs[l] = carve(p, size_t(rows) * H);
+      w[k].h_in[l] = carve(p, size_t(rows) * H);
+      w[k].c_in[l] = carve(p, size_t(rows) * H);
+      w[k].w_ihT[l] = carve(p, size_t(4) * H * H);
+      w[k].w_hhT[l] = carve(p, size_t(4) * H * H);
+    }
+    w[k].w_outT = carve(p, size_t(64) * H);
+  }
+  // forward with saved activations
+  if ((rc = run_net(h, KBS_NET_ACTOR, *b, b->actor_carry0, w[0], gates_pre, dx_up, dh_rec, dc_rec, part, splits, n, st, false, nullptr)))
+    return rc;
+  if ((rc = run_net(h, KBS_NET_CRITIC, *b, b->critic_carry0, w[1], gates_pre, dx_up, dh_rec, dc_rec, part, splits, n, st, false, nullptr)))
+    return rc;
+  // heads: outputs, loss gradient wrt the head outputs
+  KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
+             (actor_head_fwd_bwd_kernel<<<unsigned((n + 127) / 128), 128, 0, st>>>(
+                 h->p, *params, w[0].out, b->actor_obs, b->action, b->done, b->lpf0, b->old_log_probs, b->advantages, y_s, sd_s,
+                 log_probs, entropy, w[0].dout, T, ld, n)));
+  KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
+             (critic_head_fwd_bwd_kernel<<<blocks(rows), kT, 0, st>>>(*params, w[1].out, b->old_values, b->value_targets, values,
+                                                                      w[1].dout, T, ld, n)));
+  // loss statistics (same kernel as kbs_ppo_loss; its partials live at the start of `part`, consumed before the backward pass)
+  {
+    kbs_ppo_loss_io io{};
+    io.log_probs = log_probs; io.old_log_probs = b->old_log_probs; io.advantages = b->advantages; io.values = values;
+    io.old_values = b->old_values; io.value_targets = b->value_targets; io.entropy = entropy; io.out = stats_out;
+    io.T = T; io.ld = ld;
+    if ((rc = kbs_launch_ppo_loss_at(h, *params, io, n, reinterpret_cast<double*>(part), st))) return rc;
+  }
+  if ((rc = run_net(h, KBS_NET_ACTOR, *b, nullptr, w[0], gates_pre, dx_up, dh_rec, dc_rec, part, splits, n, st, true, actor))) return rc;
+  if ((rc = run_net(h, KBS_NET_CRITIC, *b, nullptr, w[1], gates_pre, dx_up, dh_rec, dc_rec, part, splits, n, st, true, critic))) return rc;
+  return KBS_OK;
+}
+
+int kbs_adam_step(kbs_handle* h, float* param, const float* grad, float* m, float* v, int64_t count, float lr, float b1, float b2,
+                  float eps, float grad_scale, int64_t step, void* stream) {
+  if (!h || !param || !grad || !m || !v) return KBS_E_NULL;
+  if (count <= 0 || step <= 0) return KBS_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float bc1 = 1.0f - powf(b1, float(step)), bc2 = 1.0f - powf(b2, float(step));
+  KBS_LAUNCH(h, KBS_K_ADV_NORM, st, (adam_kernel<<<blocks(count), kT, 0, st>>>(param, grad, m, v, count, lr, b1, b2, eps, grad_scale, bc1, bc2)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+}  // extern "C"

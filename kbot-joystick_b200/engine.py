@@ -145,6 +145,43 @@ class KbotStep:
         L.check(self.lib.kbs_ppo_loss(self._h, C.byref(lp), C.byref(io), n_envs or ld, _stream()), "kbs_ppo_loss")
         return out
 
+    def ppo_grad(self, batch: dict, grads_actor: dict, grads_critic: dict, n_envs: int | None = None, **hyper) -> dict:
+        """Gradients of the PPO minibatch loss (kbs_ppo_grad).  batch: actor_obs [T,65,ld], critic_obs [T,475,ld],
+        action [T,20,ld], done u8 [T,ld], old_log_probs / advantages / value_targets / old_values [T,ld], optional
+        actor_carry0 / critic_carry0 [depth,2,n,H], lpf0 [20,ld].  grads_*: eqx-layout dicts of CUDA tensors (written).
+        Returns {"stats": [loss, policy, value, entropy] (device), "log_probs", "values", "entropy": [T, ld]}."""
+        T, _, ld = batch["actor_obs"].shape
+        dev = batch["actor_obs"].device
+        lp = L.KbsPpoLossParams()
+        L.check(self.lib.kbs_ppo_loss_default_params(C.byref(lp)), "kbs_ppo_loss_default_params")
+        for k, v in hyper.items():
+            setattr(lp, k, v)
+        b = L.KbsPpoBatch()
+        for k in ("actor_obs", "critic_obs", "action", "done", "old_log_probs", "advantages", "value_targets", "old_values",
+                  "actor_carry0", "critic_carry0", "lpf0"):
+            setattr(b, k, L.ptr(batch.get(k)))
+        b.T, b.ld = T, ld
+
+        def gview(g):
+            s = L.KbsNetGrads()
+            s.w_in, s.b_in, s.w_out, s.b_out = (L.ptr(g[k]) for k in ("w_in", "b_in", "w_out", "b_out"))
+            for i, lw in enumerate(g["layers"]):
+                s.w_ih[i], s.w_hh[i], s.b[i] = L.ptr(lw["w_ih"]), L.ptr(lw["w_hh"]), L.ptr(lw["b"])
+            return s
+
+        ga, gc = gview(grads_actor), gview(grads_critic)
+        out = {"stats": torch.empty((4,), device=dev), "log_probs": torch.empty((T, ld), device=dev),
+               "values": torch.empty((T, ld), device=dev), "entropy": torch.empty((T, ld), device=dev)}
+        L.check(self.lib.kbs_ppo_grad(self._h, C.byref(lp), C.byref(b), C.byref(ga), C.byref(gc), L.ptr(out["log_probs"]),
+                                      L.ptr(out["values"]), L.ptr(out["entropy"]), L.ptr(out["stats"]), n_envs or ld, _stream()),
+                "kbs_ppo_grad")
+        return out
+
+    def adam_step(self, param, grad, m, v, step: int, lr=5e-4, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0) -> None:
+        """optax.adam on one flat parameter tensor (train.py:1057-1063)."""
+        L.check(self.lib.kbs_adam_step(self._h, L.ptr(param), L.ptr(grad), L.ptr(m), L.ptr(v), param.numel(), lr, b1, b2, eps,
+                                       grad_scale, step, _stream()), "kbs_adam_step")
+
     def com_distance(self, geom1, geom2, pos, subtree_com_base, out=None, n_envs: int | None = None):
         """COMDistanceObservation (train.py:509-659) for T steps: geom1/geom2 int32 [T, ncon, ld], pos [T, 3 ncon, ld],
         subtree_com_base [T, 3, ld] -> [T, ld]."""

@@ -1,0 +1,84 @@
+"""PPO minibatch update on top of the C-ABI (BASELINE configs[3]): kbs_ppo_grad -> gradient all-reduce over
+NCCL (the only collective of the path: environments are sharded, weights replicated) -> kbs_adam_step -> re-pack.
+
+Mirrors ksim's PPOTask.update_model for this Task (train.py:1057-1063 optimiser, 1763-1770 hyper-parameters): torch is
+allocation, streams and torch.distributed only."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+class NetParams:
+    """One network's parameters as ONE flat fp32 tensor (what Adam and the all-reduce see) with eqx-layout views."""
+
+    ORDER = ("w_in", "b_in", "layers", "w_out", "b_out")
+
+    def __init__(self, w: dict, device=None):
+        parts = [w["w_in"], w["b_in"]] + [lw[k] for lw in w["layers"] for k in ("w_ih", "w_hh", "b")] + [w["w_out"], w["b_out"]]
+        parts = [torch.as_tensor(p, dtype=torch.float32, device=device) for p in parts]
+        self.flat = torch.cat([p.reshape(-1) for p in parts]).contiguous()
+        self.shapes = [tuple(p.shape) for p in parts]
+        self.depth = len(w["layers"])
+
+    def _views(self, flat):
+        out, off = [], 0
+        for s in self.shapes:
+            n = 1
+            for d in s:
+                n *= d
+            out.append(flat[off:off + n].view(s))
+            off += n
+        return out
+
+    def as_dict(self, flat=None) -> dict:
+        v = self._views(self.flat if flat is None else flat)
+        layers = [{"w_ih": v[2 + 3 * i], "w_hh": v[3 + 3 * i], "b": v[4 + 3 * i]} for i in range(self.depth)]
+        return {"w_in": v[0], "b_in": v[1], "layers": layers, "w_out": v[-2], "b_out": v[-1]}
+
+
+def allreduce_sum_(flat: torch.Tensor) -> int:
+    """Sum the flat gradient over the ranks (NCCL on GPUs; gloo in the CPU test).  Returns the world size."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 1
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return dist.get_world_size()
+
+
+class PpoUpdater:
+    """grad -> all-reduce -> Adam -> re-pack, for the actor and the critic."""
+
+    def __init__(self, engine, w_actor: dict, w_critic: dict, lr: float = 5e-4, b1: float = 0.9, b2: float = 0.999,
+                 eps: float = 1e-8, **loss_hyper):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.eng = engine
+        self.pa, self.pc = NetParams(w_actor, dev), NetParams(w_critic, dev)
+        n = self.pa.flat.numel() + self.pc.flat.numel()
+        self.grad = torch.zeros(n, device=dev)            # [actor | critic]: one all-reduce for both nets
+        self.m, self.v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        self.param = torch.cat([self.pa.flat, self.pc.flat])
+        self.pa.flat, self.pc.flat = self.param[:self.pa.flat.numel()], self.param[self.pa.flat.numel():]
+        self.step_count = 0
+        self.opt = dict(lr=lr, b1=b1, b2=b2, eps=eps)
+        self.loss_hyper = loss_hyper
+        self._repack()
+
+    def _repack(self):
+        self.eng.pack_weights(L.NET_ACTOR, self.pa.as_dict())
+        self.eng.pack_weights(L.NET_CRITIC, self.pc.as_dict())
+
+    def grads(self, batch: dict, n_envs: int) -> dict:
+        na = self.pa.flat.numel()
+        return self.eng.ppo_grad(batch, self.pa.as_dict(self.grad[:na]), self.pc.as_dict(self.grad[na:]), n_envs=n_envs,
+                                 **self.loss_hyper)
+
+    def update(self, batch: dict, n_envs: int) -> dict:
+        out = self.grads(batch, n_envs)
+        world = allreduce_sum_(self.grad)                   # the PPO gradient all-reduce (NVLink / NVSwitch via NCCL)
+        self.step_count += 1
+        self.eng.adam_step(self.param, self.grad, self.m, self.v, self.step_count, grad_scale=1.0 / world, **self.opt)
+        self._repack()
+        return out

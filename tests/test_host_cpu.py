@@ -86,7 +86,8 @@ def test_ctypes_structs_match_header(lib_built):
                        ("kbs_actor_out", L.KbsActorOut), ("kbs_traj_view", L.KbsTrajView),
                        ("kbs_reward_carry", L.KbsRewardCarry), ("kbs_rollout_io", L.KbsRolloutIO),
                        ("kbs_ppo_io", L.KbsPpoIO), ("kbs_ppo_loss_params", L.KbsPpoLossParams),
-                       ("kbs_ppo_loss_io", L.KbsPpoLossIO)):
+                       ("kbs_ppo_loss_io", L.KbsPpoLossIO), ("kbs_ppo_batch", L.KbsPpoBatch),
+                       ("kbs_net_grads", L.KbsNetGrads)):
         assert c_fields(cname) == [f[0] for f in cls._fields_], cname
     assert C.sizeof(L.KbsStateView) == 11 * 8 and C.sizeof(L.KbsPpoIO) == 14 * 8
 
