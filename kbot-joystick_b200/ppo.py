@@ -75,8 +75,21 @@ class PpoUpdater:
         return self.eng.ppo_grad(batch, self.pa.as_dict(self.grad[:na]), self.pc.as_dict(self.grad[na:]), n_envs=n_envs,
                                  **self.loss_hyper)
 
+    def capture(self, batch: dict, n_envs: int) -> None:
+        """Record kbs_ppo_grad on `batch` (~3 000 kernel launches for T = 100) as ONE CUDA graph; later update() calls with the
+        same batch object replay it (refill the batch tensors in place between updates).  Call after one eager update."""
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_out = self.grads(batch, n_envs)
+        self._graph_batch = batch
+
     def update(self, batch: dict, n_envs: int) -> dict:
-        out = self.grads(batch, n_envs)
+        if getattr(self, "_graph", None) is not None and batch is self._graph_batch:
+            self._graph.replay()
+            out = self._graph_out
+        else:
+            out = self.grads(batch, n_envs)
         world = allreduce_sum_(self.grad)                   # the PPO gradient all-reduce (NVLink / NVSwitch via NCCL)
         self.step_count += 1
         self.eng.adam_step(self.param, self.grad, self.m, self.v, self.step_count, grad_scale=1.0 / world, **self.opt)

@@ -187,3 +187,56 @@ def test_env_sharding_world_size_2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o}"
         assert f"rank {r} ok" in o
+
+
+_PPO_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import kbot_oracle as O
+import ppo_grad_torch as G
+from kbot_joystick_b200 import synth
+from kbot_joystick_b200.ppo import NetParams, allreduce_sum_
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+T, N, H = 3, 8, 128
+p = O.OracleParams(hidden_size=H)
+wa, wc = synth.make_weights(1, 65, 40, H, 2), synth.make_weights(2, 475, 1, H, 2)
+rng = np.random.default_rng(0)
+f = np.float32
+b = {"actor_obs": rng.normal(0, .7, (T, N, 65)).astype(f), "critic_obs": rng.normal(0, .7, (T, N, 475)).astype(f),
+     "action": (.3 * rng.normal(size=(T, N, 20))).astype(f), "done": rng.random((T, N)) < .2,
+     "advantages": rng.normal(size=(T, N)).astype(f), "value_targets": rng.normal(size=(T, N)).astype(f),
+     "old_log_probs": rng.normal(-18, 1, (T, N)).astype(f), "old_values": rng.normal(size=(T, N)).astype(f)}
+full = G.ppo_minibatch_grads(wa, wc, b, p)
+sl = slice(rank * N // world, (rank + 1) * N // world)               # environments shard across ranks, weights replicated
+loc = G.ppo_minibatch_grads(wa, wc, {k: v[:, sl] for k, v in b.items()}, p)
+flat = torch.cat([NetParams(loc[2]).flat.double(), NetParams(loc[3]).flat.double()])
+assert allreduce_sum_(flat) == world                                 # the PPO gradient all-reduce
+flat /= world
+ref = torch.cat([NetParams(full[2]).flat.double(), NetParams(full[3]).flat.double()])
+assert flat.numel() == ref.numel() == sum(int(np.prod(s)) for s in NetParams(wa).shapes + NetParams(wc).shapes)
+assert torch.allclose(flat, ref, rtol=1e-5, atol=2e-6 * float(ref.abs().max())), float((flat - ref).abs().max())   # NetParams is fp32
+v = NetParams(wa).as_dict()                                           # flat <-> eqx-layout views round trip
+assert np.array_equal(v["layers"][1]["w_hh"].numpy(), wa["layers"][1]["w_hh"]) and np.array_equal(v["b_out"].numpy(), wa["b_out"])
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_ppo_gradient_allreduce_world_size_2_gloo(tmp_path):
+    """Data-parallel PPO update: per-rank gradients on an env shard, summed over ranks and divided by the world size,
+    equal the gradients of the whole minibatch (equal shards); NetParams' flat layout round-trips."""
+    script = tmp_path / "worker.py"
+    script.write_text(_PPO_WORKER % (str(ROOT), str(ROOT / "oracle")))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o}"
+        assert f"rank {r} ok" in o
