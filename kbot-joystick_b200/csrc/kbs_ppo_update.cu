@@ -369,18 +369,23 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
   const int splits = 8;
   const int chunks = int((rows + 511) / 512);
   const int kp_max = round_up_i(KBS_CRITIC_OBS, 64);
-  const size_t shared_f = sH * 4 /*gates_pre*/ + sH /*dx_up*/ + 2 * size_t(depth) * sH /*dh_rec, dc_rec*/ +
-                          size_t(chunks) * 4 * H + size_t(splits) * size_t(4 * H) * size_t(kp_max) + size_t(H) * kp_max + 64 * H + 4096 +
+  const size_t shared_f = 2 * (sH * 4 /*gates_pre*/ + sH /*dx_up*/ + 2 * size_t(depth) * sH /*dh_rec, dc_rec*/ +
+                               size_t(chunks) * 4 * H + size_t(splits) * size_t(4 * H) * size_t(kp_max) + size_t(H) * kp_max + 64 * H +
+                               4096 + 1024) +
                           2 * size_t(T) * KBS_NUM_JOINTS * ld /*y_s, sd_s*/;
   const size_t total_f = shared_f + net_work_floats(h, 0, T, n) + net_work_floats(h, 1, T, n) + 8192;
   int rc = kbs_scratch_reserve(h, total_f);
   if (rc) return rc;
   float* p = h->scratch;
-  float* gates_pre = carve(p, sH * 4);
-  float* dx_up = carve(p, sH);
-  float* dh_rec = carve(p, size_t(depth) * sH);
-  float* dc_rec = carve(p, size_t(depth) * sH);
-  float* part = carve(p, size_t(chunks) * 4 * H + size_t(splits) * size_t(4 * H) * size_t(kp_max) + size_t(H) * kp_max + 64 * H + 4096);
+  const size_t part_f = size_t(chunks) * 4 * H + size_t(splits) * size_t(4 * H) * size_t(kp_max) + size_t(H) * kp_max + 64 * H + 4096;
+  float* gates_pre[2]; float* dx_up[2]; float* dh_rec[2]; float* dc_rec[2]; float* part[2];
+  for (int k = 0; k < 2; ++k) {            // per net: actor and critic run concurrently on two streams
+    gates_pre[k] = carve(p, sH * 4);
+    dx_up[k] = carve(p, sH);
+    dh_rec[k] = carve(p, size_t(depth) * sH);
+    dc_rec[k] = carve(p, size_t(depth) * sH);
+    part[k] = carve(p, part_f);
+  }
   float* y_s = carve(p, size_t(T) * KBS_NUM_JOINTS * ld);
   float* sd_s = carve(p, size_t(T) * KBS_NUM_JOINTS * ld);
   NetWork w[2];
@@ -404,29 +409,42 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
     }
     w[k].w_outT = carve(p, size_t(64) * H);
   }
+  // The two networks share nothing until the loss statistics: the critic runs on the handle's side stream, forked from
+  // and joined into the caller's stream with events (capturable: the whole call can be replayed as one CUDA graph).
+  { const int rc0 = kbs_side_stream_init(h); if (rc0) return rc0; }
+  cudaStream_t sc = h->side_stream;
+  KBS_CUDA_TRY(cudaEventRecord(h->ev_pre, st));
+  KBS_CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_pre, 0));
   // forward with saved activations
-  if ((rc = run_net(h, KBS_NET_ACTOR, *b, b->actor_carry0, w[0], gates_pre, dx_up, dh_rec, dc_rec, part, splits, n, st, false, nullptr)))
+  if ((rc = run_net(h, KBS_NET_ACTOR, *b, b->actor_carry0, w[0], gates_pre[0], dx_up[0], dh_rec[0], dc_rec[0], part[0], splits, n, st,
+                    false, nullptr)))
     return rc;
-  if ((rc = run_net(h, KBS_NET_CRITIC, *b, b->critic_carry0, w[1], gates_pre, dx_up, dh_rec, dc_rec, part, splits, n, st, false, nullptr)))
+  if ((rc = run_net(h, KBS_NET_CRITIC, *b, b->critic_carry0, w[1], gates_pre[1], dx_up[1], dh_rec[1], dc_rec[1], part[1], splits, n, sc,
+                    false, nullptr)))
     return rc;
   // heads: outputs, loss gradient wrt the head outputs
   KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
              (actor_head_fwd_bwd_kernel<<<unsigned((n + 127) / 128), 128, 0, st>>>(
                  h->p, *params, w[0].out, b->actor_obs, b->action, b->done, b->lpf0, b->old_log_probs, b->advantages, y_s, sd_s,
                  log_probs, entropy, w[0].dout, T, ld, n)));
-  KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
-             (critic_head_fwd_bwd_kernel<<<blocks(rows), kT, 0, st>>>(*params, w[1].out, b->old_values, b->value_targets, values,
+  KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, sc,
+             (critic_head_fwd_bwd_kernel<<<blocks(rows), kT, 0, sc>>>(*params, w[1].out, b->old_values, b->value_targets, values,
                                                                       w[1].dout, T, ld, n)));
-  // loss statistics (same kernel as kbs_ppo_loss; its partials live at the start of `part`, consumed before the backward pass)
+  // critic backward on the side stream
+  if ((rc = run_net(h, KBS_NET_CRITIC, *b, nullptr, w[1], gates_pre[1], dx_up[1], dh_rec[1], dc_rec[1], part[1], splits, n, sc, true, critic)))
+    return rc;
+  KBS_CUDA_TRY(cudaEventRecord(h->ev_head[0], sc));
+  if ((rc = run_net(h, KBS_NET_ACTOR, *b, nullptr, w[0], gates_pre[0], dx_up[0], dh_rec[0], dc_rec[0], part[0], splits, n, st, true, actor)))
+    return rc;
+  KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[0], 0));       // join: values + critic gradients are complete
+  // loss statistics (same kernel as kbs_ppo_loss; partials in the actor's reduction scratch, free again by now)
   {
     kbs_ppo_loss_io io{};
     io.log_probs = log_probs; io.old_log_probs = b->old_log_probs; io.advantages = b->advantages; io.values = values;
     io.old_values = b->old_values; io.value_targets = b->value_targets; io.entropy = entropy; io.out = stats_out;
     io.T = T; io.ld = ld;
-    if ((rc = kbs_launch_ppo_loss_at(h, *params, io, n, reinterpret_cast<double*>(part), st))) return rc;
+    if ((rc = kbs_launch_ppo_loss_at(h, *params, io, n, reinterpret_cast<double*>(part[0]), st))) return rc;
   }
-  if ((rc = run_net(h, KBS_NET_ACTOR, *b, nullptr, w[0], gates_pre, dx_up, dh_rec, dc_rec, part, splits, n, st, true, actor))) return rc;
-  if ((rc = run_net(h, KBS_NET_CRITIC, *b, nullptr, w[1], gates_pre, dx_up, dh_rec, dc_rec, part, splits, n, st, true, critic))) return rc;
   return KBS_OK;
 }
 
