@@ -184,7 +184,7 @@ class Clocks:
                         self.reasons.add(nm)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv:
