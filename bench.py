@@ -420,42 +420,59 @@ def run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world)
     d2h = sum(v.numel() * v.element_size() for v in outs.values())
     copy_s = torch.cuda.Stream(device=dev)
     comp_s = torch.cuda.current_stream()
+    # Two sets of device input buffers: the upload of step k + 1 runs while step k's last chunks, rewards, GAE and the
+    # result read-back are still in flight (it only waits for step k - 1, the previous user of its buffer set).
+    INPUTS = ("eps_action", "u_switch", "cmd_mode", "cmd_u6", "cmd_u_arms")
+    io_b = dict(io)
+    for grp in ("state", "noise", "episode"):
+        io_b[grp] = {k: torch.empty_like(v) for k, v in io[grp].items()}
+    for k in INPUTS:
+        io_b[k] = torch.empty_like(io[k])
+    sets = [io, io_b]
+    done_ev = [None, None]                                  # compute of the last step that used buffer set i
+    count = [0]
 
-    def sub_io(t0, t1):
-        s = dict(io)
-        s["state"] = {k: v[t0:t1] for k, v in io["state"].items()}
-        s["noise"] = {k: v[t0:t1] for k, v in io["noise"].items()}
-        for k in ("eps_action", "u_switch", "cmd_mode", "cmd_u6", "cmd_u_arms", "action", "log_prob", "ctrl", "done",
-                  "success", "value"):
-            s[k] = io[k][t0:t1]
-        s["command"] = io["command"][t0:t1 + 1]
+    def sub_io(cur, t0, t1):
+        s = dict(cur)
+        s["state"] = {k: v[t0:t1] for k, v in cur["state"].items()}
+        s["noise"] = {k: v[t0:t1] for k, v in cur["noise"].items()}
+        for k in INPUTS + ("action", "log_prob", "ctrl", "done", "success", "value"):
+            s[k] = cur[k][t0:t1]
+        s["command"] = cur["command"][t0:t1 + 1]
         s["T"] = t1 - t0
         return s
 
     def step():
+        which = count[0] & 1
+        count[0] += 1
+        cur = sets[which]
         evs = []
         with torch.cuda.stream(copy_s):
-            copy_s.wait_stream(comp_s)                      # previous step's readers are done with the buffers
+            if done_ev[which] is not None:
+                copy_s.wait_event(done_ev[which])           # the readers of this buffer set (two steps ago) are done
             for k, v in host["episode"].items():
-                io["episode"][k].copy_(v, non_blocking=True)
+                cur["episode"][k].copy_(v, non_blocking=True)
             for t0 in range(0, T, chunk):
                 t1 = t0 + chunk
                 # recorded state: only the 473 of 676 MuJoCo rows the path reads cross PCIe (kbs_upload_state)
                 eng.upload_state({k: v[t0:t1] for k, v in host["state"].items()},
-                                 {k: v[t0:t1] for k, v in io["state"].items()}, stream=copy_s.cuda_stream)
+                                 {k: v[t0:t1] for k, v in cur["state"].items()}, stream=copy_s.cuda_stream)
                 for k, v in host["noise"].items():
-                    io["noise"][k][t0:t1].copy_(v[t0:t1], non_blocking=True)
-                for k in ("eps_action", "u_switch", "cmd_mode", "cmd_u6", "cmd_u_arms"):
-                    io[k][t0:t1].copy_(host[k][t0:t1], non_blocking=True)
+                    cur["noise"][k][t0:t1].copy_(v[t0:t1], non_blocking=True)
+                for k in INPUTS:
+                    cur[k][t0:t1].copy_(host[k][t0:t1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_s)
                 evs.append(ev)
         for i, t0 in enumerate(range(0, T, chunk)):
             comp_s.wait_event(evs[i])
-            eng.rollout(sub_io(t0, t0 + chunk), N)
-        eng.rewards(io["state"], io["command"][:T], io["ctrl"], io["done"], rcarry, total=total, n_envs=N)
+            eng.rollout(sub_io(cur, t0, t0 + chunk), N)
+        eng.rewards(cur["state"], io["command"][:T], io["ctrl"], io["done"], rcarry, total=total, n_envs=N)
         eng.gae(io["value"], total, io["done"], io["success"], adv=adv, targets=tgt, n_envs=N)
         io["command"][0].copy_(io["command"][T])
+        ev = torch.cuda.Event()
+        ev.record(comp_s)
+        done_ev[which] = ev
         for k, v in outs.items():
             host_out[k].copy_(v, non_blocking=True)
 
@@ -472,8 +489,8 @@ def run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world)
     ms = max_ranks(e0.elapsed_time(e1)) / k
     assert torch.isfinite(host_out["adv"]).all()
     return {"value": world * N * T / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": ms, "steps": k, "pipeline": f"H2D in {chunk}-step chunks on a copy stream (state: only the 473 of 676 rows the path reads), "
-                        f"overlapped with kbs_rollout on the chunks already resident"}
+            "ms_per_step": ms, "steps": k, "pipeline": f"H2D in {chunk}-step chunks on a copy stream (state: only the 473 of 676 rows the path reads) into "
+                        f"double-buffered device inputs, overlapped with kbs_rollout on the chunks already resident"}
 
 
 if __name__ == "__main__":
