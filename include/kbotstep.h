@@ -161,6 +161,16 @@ int kbs_observations(kbs_handle* h, const kbs_state_view* s, const kbs_noise_vie
                      const uint8_t* pg_reset, float* computed, float* actor_obs, float* critic_obs,
                      int64_t n_envs, void* stream);
 
+/* Replaces: the per-physics-sub-step actuator path of ksim's engine (train.py:1775-1781: dt 0.004,
+ * ctrl_dt 0.02 => 5 sub-steps, action_latency_range (0.003, 0.01) s, drop_action_prob 0.05; engine semantics unverified):
+ * a dropped command (u_drop < drop_prob) repeats the last applied action; sub-step k sees the new action once
+ * k * sub_dt >= latency, the previous one before; ctrl_k = PositionActuators.get_ctrl on the sub-step's joint state.
+ *   action [20][ld]; prev_action [20][ld] in/out (last applied action); u_drop, latency [ld];
+ *   q_sub, qd_sub [S][20][ld] joint positions / velocities at each sub-step; ctrl_out [S][20][ld]. */
+int kbs_torque_substeps(kbs_handle* h, const float* action, float* prev_action, const float* u_drop, const float* latency,
+                        const float* q_sub, const float* qd_sub, const kbs_episode_view* ep, float* ctrl_out, int32_t n_substeps,
+                        float sub_dt, float drop_prob, int64_t ld, int64_t n_envs, void* stream);
+
 /* Replaces: ksim.compute_ppo_loss inside PPOTask (hyper-parameters: entropy_coef train.py:1767; the rest are ksim defaults,
  * unverified): clipped surrogate + (clipped) value loss + entropy bonus over a stored trajectory, reduced to means.
  *   ratio = exp(clip(log_probs - old_log_probs, +-log_clip_value)); policy = min(ratio A, clip(ratio, 1 +- eps) A)

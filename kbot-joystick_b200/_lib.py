@@ -112,7 +112,7 @@ EXPORTS = (
     "kbs_version", "kbs_error_string", "kbs_default_params", "kbs_create", "kbs_destroy", "kbs_get_params",
     "kbs_weights_pack", "kbs_observations", "kbs_command_update", "kbs_actor_step", "kbs_critic_step",
     "kbs_torque", "kbs_terminate", "kbs_rewards", "kbs_gae", "kbs_policy_step", "kbs_rollout", "kbs_ppo_variables",
-    "kbs_launch_count", "kbs_device_status", "kbs_mirror_observations", "kbs_mirror_joints", "kbs_upload_state", "kbs_com_distance", "kbs_ppo_loss_default_params", "kbs_ppo_loss", "kbs_ppo_grad", "kbs_adam_step", "kbs_profile_enable", "kbs_profile_read", "kbs_kernel_name", "kbs_debug_tc_gates", "kbs_debug_tc_trace", "kbs_debug_tc_trace_attach",
+    "kbs_launch_count", "kbs_device_status", "kbs_mirror_observations", "kbs_mirror_joints", "kbs_upload_state", "kbs_com_distance", "kbs_ppo_loss_default_params", "kbs_ppo_loss", "kbs_ppo_grad", "kbs_adam_step", "kbs_torque_substeps", "kbs_profile_enable", "kbs_profile_read", "kbs_kernel_name", "kbs_debug_tc_gates", "kbs_debug_tc_trace", "kbs_debug_tc_trace_attach",
 )
 NUM_KERNEL_IDS = 18
 
@@ -146,6 +146,8 @@ def load() -> C.CDLL:
     lib.kbs_ppo_grad.argtypes = [_vp, P(KbsPpoLossParams), P(KbsPpoBatch), P(KbsNetGrads), P(KbsNetGrads), _vp, _vp, _vp, _vp,
                                  _i64, _vp]
     lib.kbs_adam_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i64, _vp]
+    lib.kbs_torque_substeps.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, P(KbsEpisodeView), _vp, C.c_int32, C.c_float, C.c_float,
+                                        _i64, _i64, _vp]
     lib.kbs_com_distance.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _i64, _i64, _vp]
     lib.kbs_upload_state.argtypes = [_vp, P(KbsStateView), P(KbsStateView), _i64, P(_i64), _vp]
     lib.kbs_mirror_joints.argtypes = [_vp, _vp, _vp, _i64, _i64, _i64, _vp]

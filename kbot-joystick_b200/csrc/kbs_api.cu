@@ -539,6 +539,18 @@ int kbs_torque(kbs_handle* h, const float* action, const kbs_state_view* s, cons
   return kbs_launch_torque(h, action, *s, ep, ctrl_out, n, (cudaStream_t)stream);
 }
 
+int kbs_torque_substeps(kbs_handle* h, const float* action, float* prev_action, const float* u_drop, const float* latency,
+                        const float* q_sub, const float* qd_sub, const kbs_episode_view* ep, float* ctrl_out, int32_t n_substeps,
+                        float sub_dt, float drop_prob, int64_t ld, int64_t n, void* stream) {
+  REQ(h); REQ(action); REQ(prev_action); REQ(u_drop); REQ(latency); REQ(q_sub); REQ(qd_sub); REQ(ctrl_out);
+  if (n_substeps <= 0 || n_substeps > 64) return KBS_E_SHAPE;
+  int rc = check_ld(ld, n);
+  if (rc) return rc;
+  AL(action); AL(prev_action); AL(u_drop); AL(latency); AL(q_sub); AL(qd_sub); AL(ctrl_out);
+  return kbs_launch_torque_substeps(h, action, prev_action, u_drop, latency, q_sub, qd_sub, ep, ctrl_out, n_substeps, sub_dt,
+                                    drop_prob, ld, n, (cudaStream_t)stream);
+}
+
 int kbs_terminate(kbs_handle* h, const kbs_state_view* s, int32_t* codes, uint8_t* done, uint8_t* success, float* pre,
                   int64_t n, void* stream) {
   REQ(h);

@@ -118,6 +118,9 @@ int kbs_launch_pg_scan(kbs_handle* h, const float* sensordata, const float* lag,
                        float* lagged, int64_t T, int64_t ld, int64_t n, cudaStream_t st);
 int kbs_launch_torque(kbs_handle* h, const float* action, const kbs_state_view& s, const kbs_episode_view* ep,
                       float* ctrl, int64_t n, cudaStream_t st);
+int kbs_launch_torque_substeps(kbs_handle* h, const float* action, float* prev_action, const float* u_drop, const float* latency,
+                               const float* q_sub, const float* qd_sub, const kbs_episode_view* ep, float* ctrl, int S, float sub_dt,
+                               float drop_prob, int64_t ld, int64_t n, cudaStream_t st);
 int kbs_launch_terminate(kbs_handle* h, const kbs_state_view& s, int32_t* codes, uint8_t* done, uint8_t* success,
                          float* pre, int64_t n, cudaStream_t st, int64_t T = 1);
 int kbs_launch_rewards(kbs_handle* h, const kbs_traj_view& tr, const kbs_reward_carry& carry, float* total,

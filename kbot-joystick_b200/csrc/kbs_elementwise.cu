@@ -681,6 +681,54 @@ torque_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ ac
   }
 }
 
+// Per-physics-sub-step actuator path (train.py:1775-1781: dt 0.004, ctrl_dt 0.02, action latency 3-10 ms,
+// 5 % dropped commands; ksim engine semantics [U], see oracle position_actuator_substeps): a dropped command repeats
+// the last applied action; sub-step k sees the new action once k sub_dt >= latency; PD torque on the sub-step's joint state.
+//   q_sub / qd_sub / ctrl [S][20][ld]; prev_action [20][ld] in/out
+__global__ void __launch_bounds__(kThreads)
+torque_substeps_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ action, float* __restrict__ prev_action,
+                       const float* __restrict__ u_drop, const float* __restrict__ latency, const float* __restrict__ q_sub,
+                       const float* __restrict__ qd_sub, const kbs_episode_view ep, float* __restrict__ ctrl, int S, float sub_dt,
+                       float drop_prob, int64_t ld, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  float ud[4], lat[4];
+  kbs_ld4(u_drop, 0, ld, n0, ud);
+  kbs_ld4(latency, 0, ld, n0, lat);
+#pragma unroll 2
+  for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+    float a[4], pa[4], ap[4];
+    float kp[4] = {P.kp[j], P.kp[j], P.kp[j], P.kp[j]}, kd[4] = {P.kd[j], P.kd[j], P.kd[j], P.kd[j]};
+    float lim[4] = {P.ctrl_limit[j], P.ctrl_limit[j], P.ctrl_limit[j], P.ctrl_limit[j]};
+    float ab[4] = {0, 0, 0, 0}, tb[4] = {0, 0, 0, 0};
+    kbs_ld4(action, j, ld, n0, a);
+    kbs_ld4(prev_action, j, ld, n0, pa);
+    if (ep.kp) kbs_ld4(ep.kp, j, ld, n0, kp);
+    if (ep.kd) kbs_ld4(ep.kd, j, ld, n0, kd);
+    if (ep.tau_limit) kbs_ld4(ep.tau_limit, j, ld, n0, lim);
+    if (ep.action_bias) kbs_ld4(ep.action_bias, j, ld, n0, ab);
+    if (ep.torque_bias) kbs_ld4(ep.torque_bias, j, ld, n0, tb);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) ap[l] = (ud[l] < drop_prob) ? pa[l] : a[l];
+    for (int k = 0; k < S; ++k) {
+      float q[4], qd[4], o[4];
+      kbs_ld4(q_sub + int64_t(k) * KBS_NUM_JOINTS * ld, j, ld, n0, q);
+      kbs_ld4(qd_sub + int64_t(k) * KBS_NUM_JOINTS * ld, j, ld, n0, qd);
+      const float tk = float(k) * sub_dt;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const float act = (tk >= lat[l]) ? ap[l] : pa[l];
+        const float target = ep.action_bias ? act + ab[l] : act;
+        float tau = kp[l] * (target - q[l]) - kd[l] * qd[l];
+        if (ep.torque_bias) tau = tau + tb[l];
+        o[l] = fminf(fmaxf(tau, -lim[l]), lim[l]);
+      }
+      kbs_st4(ctrl + int64_t(k) * KBS_NUM_JOINTS * ld, j, ld, n0, o);
+    }
+    kbs_st4(prev_action, j, ld, n0, ap);
+  }
+}
+
 // =====================================================================================================
 // Terminations train.py:1258-1269, 817-823 (+ ksim NotUpright / EpisodeLength / done-success reduce)
 // =====================================================================================================
@@ -1286,6 +1334,18 @@ int kbs_launch_torque(kbs_handle* h, const float* action, const kbs_state_view& 
   kbs_episode_view e{};
   if (ep) e = *ep;
   KBS_LAUNCH(h, KBS_K_TORQUE, st, (torque_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, action, s, e, ctrl, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_torque_substeps(kbs_handle* h, const float* action, float* prev_action, const float* u_drop, const float* latency,
+                               const float* q_sub, const float* qd_sub, const kbs_episode_view* ep, float* ctrl, int S, float sub_dt,
+                               float drop_prob, int64_t ld, int64_t n, cudaStream_t st) {
+  kbs_episode_view e{};
+  if (ep) e = *ep;
+  KBS_LAUNCH(h, KBS_K_TORQUE, st,
+             (torque_substeps_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, action, prev_action, u_drop, latency, q_sub, qd_sub, e,
+                                                                      ctrl, S, sub_dt, drop_prob, ld, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

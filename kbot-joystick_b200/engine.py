@@ -260,6 +260,19 @@ class KbotStep:
                                     _stream()), "kbs_torque")
         return ctrl
 
+    def torque_substeps(self, action, prev_action, u_drop, latency, q_sub, qd_sub, episode: dict | None = None, ctrl=None,
+                        sub_dt: float = 0.004, drop_prob: float = 0.05, n_envs: int | None = None):
+        """Per-physics-sub-step actuator path (latency / dropped commands, train.py:1775-1781): q_sub / qd_sub [S, 20, ld]
+        -> ctrl [S, 20, ld]; prev_action [20, ld] is updated in place to the action that was applied."""
+        S, _, ld = q_sub.shape
+        if ctrl is None:
+            ctrl = torch.empty_like(q_sub)
+        ev = _view(L.KbsEpisodeView, EPISODE_ROWS, episode)
+        L.check(self.lib.kbs_torque_substeps(self._h, L.ptr(action), L.ptr(prev_action), L.ptr(u_drop), L.ptr(latency),
+                                             L.ptr(q_sub), L.ptr(qd_sub), C.byref(ev), L.ptr(ctrl), S, sub_dt, drop_prob, ld,
+                                             n_envs or ld, _stream()), "kbs_torque_substeps")
+        return ctrl
+
     def terminate(self, state: dict, n_envs: int | None = None, want_pre: bool = False) -> dict:
         ld = state["qpos"].shape[-1]
         dev = state["qpos"].device

@@ -725,6 +725,24 @@ def position_actuator_torque(action, q, qd, kp=None, kd=None, tau_limit=None, ac
     return np.minimum(np.maximum(tau, -lim), lim)
 
 
+def position_actuator_substeps(action, prev_action, u_drop, latency, q_sub, qd_sub, sub_dt=0.004, drop_prob=0.05,
+                               **gains):
+    """[U] the per-physics-sub-step actuator path of ksim's engine (train.py:1775-1781: dt = 0.004,
+    ctrl_dt = 0.02, action_latency_range = (0.003, 0.01), drop_action_prob = 0.05) -- oracle-defined, reference-unverified:
+      applied = prev_action if u_drop < drop_prob else action              (a dropped command repeats the last applied one)
+      sub-step k (time k sub_dt since the control tick) sees `applied` once k sub_dt >= latency, else prev_action
+      ctrl_k = PositionActuators.get_ctrl(that action, q_k, qd_k)          (position_actuator_torque)
+    action / prev_action [..., 20], u_drop / latency [...], q_sub / qd_sub [S, ..., 20].
+    Returns (ctrl [S, ..., 20], new prev_action = applied)."""
+    dt = action.dtype
+    applied = np.where((u_drop < np.asarray(drop_prob, dt))[..., None], prev_action, action)
+    out = []
+    for k in range(q_sub.shape[0]):
+        seen = (np.asarray(k, dt) * np.asarray(sub_dt, dt) >= latency)[..., None]
+        out.append(position_actuator_torque(np.where(seen, applied, prev_action), q_sub[k], qd_sub[k], **gains))
+    return np.stack(out), applied
+
+
 # --------------------------------------------------------------------------------------
 # Terminations Z1  train.py:1258-1269, 817-823
 # --------------------------------------------------------------------------------------

@@ -229,6 +229,31 @@ def test_torque(eng, dev, N):
     close(S(ctrl, N, (20,)), O.position_actuator_torque(act_np, q, qd), "ctrl (nominal gains)", atol=1e-4)
 
 
+@pytest.mark.parametrize("N", [5, 640])
+def test_torque_substeps_latency_and_drop(eng, dev, N):
+    """8f-2: five PD evaluations per control step on the latency / drop-selected action (train.py:1775-1781)."""
+    S_ = 5
+    rng = np.random.default_rng(300 + N)
+    f = np.float32
+    b = Batch(310 + N, 1, N, dev)
+    ep = b.np["episode"]
+    act = (0.5 * rng.normal(size=(N, 20))).astype(f)
+    prev = (0.5 * rng.normal(size=(N, 20))).astype(f)
+    u_drop = rng.random(N).astype(f)
+    lat = rng.uniform(0.003, 0.01, N).astype(f)
+    lat[:: 7] = 0.004                                                  # exactly on a sub-step boundary: k dt >= latency
+    q = rng.normal(0, 0.5, (S_, N, 20)).astype(f)
+    qd = rng.normal(0, 2.0, (S_, N, 20)).astype(f)
+    ref, applied = O.position_actuator_substeps(act, prev, u_drop, lat, q, qd, kp=ep["kp"], kd=ep["kd"], tau_limit=ep["tau_limit"],
+                                                action_bias=ep["action_bias"], torque_bias=ep["torque_bias"])
+    prev_d = synth.to_soa(prev, 0, dev)
+    ctrl = eng.torque_substeps(synth.to_soa(act, 0, dev), prev_d, synth.to_soa(u_drop, 0, dev), synth.to_soa(lat, 0, dev),
+                               synth.to_soa(q, 1, dev), synth.to_soa(qd, 1, dev), b.episode, n_envs=N)
+    close(S(ctrl, N, (20,)), ref, "sub-step torques", atol=1e-4)
+    exact(S(prev_d, N, (20,)), applied, "applied action (drop = repeat the previous one)")
+    assert (u_drop < 0.05).sum() >= 0 and ((np.arange(S_)[:, None] * f(0.004) >= lat[None]).sum(0) >= 2).all()
+
+
 @pytest.mark.parametrize("N", [1, 32, 4099])
 def test_terminations_bit_exact(eng, dev, N):
     b = Batch(500 + N, 1, N, dev)

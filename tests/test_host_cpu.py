@@ -240,3 +240,23 @@ def test_ppo_gradient_allreduce_world_size_2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o}"
         assert f"rank {r} ok" in o
+
+
+def test_checkpoint_leaf_stream_round_trip(tmp_path):
+    """8f-4: the eqx `tree_serialise_leaves` stream of Model(actor, critic) <-> the weight dicts kbs_weights_pack takes."""
+    from kbot_joystick_b200 import checkpoint as ck
+    from kbot_joystick_b200 import synth
+
+    wa, wc = synth.make_weights(5, 65, 40, 128, 2), synth.make_weights(6, 475, 1, 128, 2)
+    static = (65, 20, 0.01, 1.0, 0.5, 10.0, 0.02)          # Actor's scalar fields (train.py:853-860) ride along as 0-d leaves
+    path = tmp_path / "model.eqx"
+    ck.write_leaves(ck.weights_to_leaves(wa, wc, static_actor=static, static_critic=(475,)), path)
+    a, c = ck.load_policy(path, hidden=128, depth=2)
+    for got, ref in ((a, wa), (c, wc)):
+        for k in ("w_in", "b_in", "w_out", "b_out"):
+            np.testing.assert_array_equal(got[k], ref[k])
+        for l in range(2):
+            for k in ("w_ih", "w_hh", "b"):
+                np.testing.assert_array_equal(got["layers"][l][k], ref["layers"][l][k])
+    with pytest.raises(AssertionError):
+        ck.load_policy(path, hidden=256, depth=2)            # wrong architecture is refused, not silently reshaped
