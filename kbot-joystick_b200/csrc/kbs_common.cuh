@@ -38,6 +38,7 @@ struct KbsNet {
   // tcgen05 path: one contiguous image of UMMA-ready operand tiles (see kbs_net_tc.cu)
   float* tc_image = nullptr;
   size_t tc_image_floats = 0;
+  float* tc_bwd_image = nullptr;   // PPO update: [W_ih | W_hh] transposed per layer as MMA operand (kbs_tc_pack_bwd)
 };
 
 // kernel ids of the per-kernel CUDA-event profiler (kbs_profile_*): one id per __global__ of the library
@@ -183,6 +184,13 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
                           const float* cvel = nullptr);
 int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStream_t st);
 int kbs_tc_debug_trace(kbs_handle* h, long long* trace_out, float* ws, int64_t n, cudaStream_t st);
+// tensor-core GEMMs of the PPO update
+int kbs_tc_gates_fwd(kbs_handle* h, int net, int layer, const void* x_sb, const void* h_sb, float* gates_out, int64_t n,
+                     cudaStream_t st);
+int kbs_tc_pack_bwd(kbs_handle* h, int net, cudaStream_t st);
+int kbs_tc_bwd_gemm(kbs_handle* h, int net, int layer, const void* dG_sb, float* out, int64_t n, float out_scale, cudaStream_t st);
+size_t kbs_tc_rows_sb_bytes(const kbs_handle* h, int64_t n, int K);
+int kbs_tc_kind_of(const kbs_handle* h);
 int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,
                        float* ws, int64_t n, cudaStream_t st);
 

@@ -113,6 +113,78 @@ gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
         make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
 }
 
+// Large-tile variant of gemm_tn for the weight-gradient GEMMs of the PPO update (K = T x n ~ 5e4): 128 x 128 x 16 tiles,
+// 8 x 8 outputs per thread (two 4-wide strips per axis), global loads of slab k+1 issued before the FMAs of slab k
+// (register staging + double-buffered shared memory: one barrier per slab).  M % 128 == 0, N % 128 == 0.
+constexpr int LBM = 128, LBN = 128;
+__global__ void __launch_bounds__(256)
+gemm_tn_large_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                     int M, int64_t K) {
+  __shared__ __align__(16) float As[2][BK][LBM];
+  __shared__ __align__(16) float Bs[2][BK][LBN];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;                    // 16 x 16 threads; thread owns rows ty*4 + {0..3, 64..67}, cols likewise
+  const int m0 = blockIdx.x * LBM, n0 = blockIdx.y * LBN;
+  const int64_t per = ((K + gridDim.z - 1) / gridDim.z + BK - 1) / BK * BK;
+  const int64_t kb = int64_t(blockIdx.z) * per, ke = (kb + per < K) ? kb + per : K;
+  C += size_t(blockIdx.z) * size_t(M) * ldc;
+  // loader mapping: 16 k-rows x 128 columns = 512 float4 per operand, 2 per thread
+  const int lk = tid >> 5, lc = (tid & 31) * 4;              // k rows lk and lk + 8
+  float acc[8][8] = {};
+  float4 ra[2], rb[2];
+  auto gload = [&](int64_t k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t k = k0 + lk + 8 * h;
+      ra[h] = rb[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < ke) {
+        ra[h] = *reinterpret_cast<const float4*>(A + k * lda + m0 + lc);
+        rb[h] = *reinterpret_cast<const float4*>(B + k * ldb + n0 + lc);
+      }
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<float4*>(&As[buf][lk + 8 * h][lc]) = ra[h];
+      *reinterpret_cast<float4*>(&Bs[buf][lk + 8 * h][lc]) = rb[h];
+    }
+  };
+  if (kb < ke) {
+    gload(kb);
+    sstore(0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+    const bool more = k0 + BK < ke;
+    if (more) gload(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) sstore(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    float* row = C + size_t(m) * ldc + n0;
+    *reinterpret_cast<float4*>(row + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    *reinterpret_cast<float4*>(row + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  }
+}
+
 // out[i] = sum_s partial[s][i]  (fixed order: deterministic)
 __global__ void __launch_bounds__(256)
 reduce_splits_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_t count, int splits) {
@@ -219,8 +291,9 @@ __global__ void pad_copy_kernel(const float* __restrict__ src, float* __restrict
 
 int pad_copy(kbs_handle* h, const float* src, float** dst, int rows, int cols, int rows_pad, int cols_pad,
              cudaStream_t st) {
-  if (*dst) { KBS_CUDA_TRY(cudaFree(*dst)); *dst = nullptr; }
-  KBS_CUDA_TRY(cudaMalloc(dst, sizeof(float) * size_t(rows_pad) * cols_pad));
+  // shapes are fixed per handle (hidden size, depth, net): a re-pack after a weight update reuses the allocation, so the
+  // device pointers stay stable (CUDA graphs captured over them stay valid)
+  if (!*dst) KBS_CUDA_TRY(cudaMalloc(dst, sizeof(float) * size_t(rows_pad) * cols_pad));
   const int64_t tot = int64_t(rows_pad) * cols_pad;
   KBS_LAUNCH(h, KBS_K_PACK, st,
              (pad_copy_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(src, *dst, rows, cols, rows_pad, cols_pad)));
@@ -271,8 +344,12 @@ int kbs_simt_gemm_nt(kbs_handle* h, const float* A, int64_t lda, const float* W,
 int kbs_simt_gemm_tn(kbs_handle* h, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int64_t K,
                      float* partials, int splits, cudaStream_t st) {
   if (M % BM || N % BN || ldc < N) return KBS_E_SHAPE;
-  KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
-             (gemm_tn_kernel<<<dim3(M / BM, N / BN, splits), 256, 0, st>>>(A, lda, B, ldb, partials, ldc, M, K)));
+  if (M % LBM == 0 && N % LBN == 0)
+    KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+               (gemm_tn_large_kernel<<<dim3(M / LBM, N / LBN, splits), 256, 0, st>>>(A, lda, B, ldb, partials, ldc, M, K)));
+  else
+    KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
+               (gemm_tn_kernel<<<dim3(M / BM, N / BN, splits), 256, 0, st>>>(A, lda, B, ldb, partials, ldc, M, K)));
   const int64_t count = int64_t(M) * ldc;
   KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st,
              (reduce_splits_kernel<<<unsigned((count + 255) / 256), 256, 0, st>>>(partials, C, count, splits)));

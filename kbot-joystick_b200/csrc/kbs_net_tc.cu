@@ -183,7 +183,7 @@ __device__ __forceinline__ size_t fb_offset(int64_t row, int k, int H) {
 }
 
 // ---- the layer kernel -----------------------------------------------------------------------------------------------
-enum { MODE_LSTM = 0, MODE_PROJ = 1, MODE_RAW = 2, MODE_PROJ_SOA = 3 };
+enum { MODE_LSTM = 0, MODE_PROJ = 1, MODE_RAW = 2, MODE_PROJ_SOA = 3, MODE_PLAIN = 4 };   // PLAIN: fp32 row-major [n][ldo] output
 constexpr int kSoaWarps = 4;             // MODE_PROJ_SOA: warps 1..4 build the activation stage in shared memory, one row per thread
 struct LayerArgs {
   const char* x_sb;       // A blocks, first K segment: [panels][kb_x] blocks (layer input / observation rows)
@@ -207,6 +207,8 @@ struct LayerArgs {
   // features 80..447 come straight from the recorded state (critic's privileged dump, train.py:1405-1413).
   const float* soa; const float* cinert; const float* cvel;
   int F; int64_t soa_ld, n_env, n_pad;
+  int ldo;                // MODE_PLAIN: row stride of `raw` (floats)
+  float oscale;           // MODE_PLAIN: output multiplier (power of two: undoes the operand pre-scaling of small gradients)
 };
 struct LayerArgs2 { LayerArgs net[2]; };   // actor / critic share one launch
 
@@ -479,6 +481,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
             sb_store4<kPanelRows, KIND>(a.x_next_sb, R, col0 + i, kb_out, o);
           }
         }
+      } else if (a.mode == MODE_PLAIN) {
+        float* o = a.raw + R * a.ldo + w.tile * kTileCols + c2 * 64;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4)
+          *reinterpret_cast<float4*>(o + i) = make_float4(a.oscale * v[i], a.oscale * v[i + 1], a.oscale * v[i + 2], a.oscale * v[i + 3]);
       } else if (a.mode == MODE_RAW) {
         float* g = a.raw + R * 4 * H + u0;
 #pragma unroll
@@ -1433,10 +1440,9 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
     KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
     attr_set = true;
   }
-  if (N.tc_image) { KBS_CUDA_TRY(cudaFree(N.tc_image)); N.tc_image = nullptr; }
   const size_t bytes = 2 * layer_image_bytes(h) * h->p.depth + proj_image_bytes(h, net) + head_image_bytes(h);
   N.tc_image_floats = (bytes + 3) / 4;
-  KBS_CUDA_TRY(cudaMalloc(&N.tc_image, bytes));
+  if (!N.tc_image) KBS_CUDA_TRY(cudaMalloc(&N.tc_image, bytes));      // fixed size per handle: re-packs keep the pointer
   for (int l = 0; l < h->p.depth; ++l) {
     const int64_t total = int64_t(4 * H) * (2 * H / 4);
     const unsigned gb = unsigned((total + 255) / 256);
@@ -1590,6 +1596,97 @@ int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, con
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
+
+// ---- tensor-core GEMMs of the PPO update (kbs_ppo_update.cu): split-precision, fp32-accurate ---------------------------
+// gates_out [n][4H] (eqx order, bias added) = [x | h] . Wcat^T from SB operands the caller already holds
+int kbs_tc_gates_fwd(kbs_handle* h, int net, int layer, const void* x_sb, const void* h_sb, float* gates_out, int64_t n,
+                     cudaStream_t st) {
+  const KbsNet& N = h->net[net];
+  if (!N.packed || !N.tc_image) return KBS_E_STATE;
+  LayerArgs2 a2{};
+  LayerArgs& a = a2.net[0];
+  fill_lstm_args(h, net, layer, a);
+  a.x_sb = reinterpret_cast<const char*>(x_sb);
+  a.h_sb_in = reinterpret_cast<const char*>(h_sb);
+  a.raw = gates_out;
+  a.mode = MODE_RAW;
+  a.n = n;
+  a.panels = int(pad_rows(n) / kPanelRows);
+  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(h, tc_kind(h), a2, st)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+// backward weights of one layer: Wb [2H][4H], Wb[c][k] = W_ih[k][c] (c < H) | W_hh[k][c - H]: [dx | dh] = dG . Wb^T
+template <int KIND>
+__global__ void __launch_bounds__(256)
+pack_bwd_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, char* __restrict__ w_sb,
+                        float* __restrict__ bias_t, int H) {
+  const int kq = 4 * H / 4;
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= int64_t(2 * H) * kq) return;
+  const int col = int(idx / kq), k = int(idx % kq) * 4;
+  const float* w = col < H ? w_ih : w_hh;
+  const int c = col < H ? col : col - H;
+  const float x[4] = {w[size_t(k) * H + c], w[size_t(k + 1) * H + c], w[size_t(k + 2) * H + c], w[size_t(k + 3) * H + c]};
+  sb_store4<kTileCols, KIND, true>(w_sb, col, k, 4 * H / kbs_block_k(KIND), x);
+  if (k == 0) bias_t[col] = 0.0f;
+}
+
+static size_t bwd_layer_bytes(const kbs_handle* h) {
+  const int H = h->p.hidden_size;
+  return kbs_sb_bytes_kind(tc_kind(h), 2 * H, 4 * H) + size_t(2 * H) * 4;
+}
+
+// (re)builds the backward operand image of `net` from its current fp32 weights (call after every weight update)
+int kbs_tc_pack_bwd(kbs_handle* h, int net, cudaStream_t st) {
+  KbsNet& N = h->net[net];
+  if (!N.packed) return KBS_E_STATE;
+  const int H = h->p.hidden_size, kind = tc_kind(h);
+  if ((2 * H) % kTileCols || (4 * H) % kbs_block_k(kind)) return KBS_E_SHAPE;
+  const size_t bytes = bwd_layer_bytes(h) * h->p.depth;
+  if (!N.tc_bwd_image) KBS_CUDA_TRY(cudaMalloc(&N.tc_bwd_image, bytes));
+  for (int l = 0; l < h->p.depth; ++l) {
+    char* w = reinterpret_cast<char*>(N.tc_bwd_image) + bwd_layer_bytes(h) * l;
+    float* bias = reinterpret_cast<float*>(w + kbs_sb_bytes_kind(kind, 2 * H, 4 * H));
+    const int64_t total = int64_t(2 * H) * (4 * H / 4);
+    const unsigned gb = unsigned((total + 255) / 256);
+    if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_bwd_weights_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(N.w_ih[l], N.w_hh[l], w, bias, H)));
+    else
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_bwd_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(N.w_ih[l], N.w_hh[l], w, bias, H)));
+  }
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+// out [n][2H] row-major = out_scale * dG [n][4H] (SB) . [W_ih | W_hh]: columns 0..H-1 = gradient wrt the layer input,
+// H..2H-1 wrt h_in.  Gradients are ~1 / (T n) small: the caller scales dG by a power of two before splitting it into FP16
+// planes (whose range ends at 6e-5 / 6e-8) and passes the inverse here.
+int kbs_tc_bwd_gemm(kbs_handle* h, int net, int layer, const void* dG_sb, float* out, int64_t n, float out_scale, cudaStream_t st) {
+  const KbsNet& N = h->net[net];
+  if (!N.packed || !N.tc_bwd_image) return KBS_E_STATE;
+  const int H = h->p.hidden_size, kind = tc_kind(h);
+  char* w = reinterpret_cast<char*>(N.tc_bwd_image) + bwd_layer_bytes(h) * layer;
+  LayerArgs2 a2{};
+  LayerArgs& a = a2.net[0];
+  a.dbg = 0;
+  a.x_sb = reinterpret_cast<const char*>(dG_sb);
+  a.h_sb_in = a.x_sb;
+  a.w_sb = w;
+  a.bias_t = reinterpret_cast<const float*>(w + kbs_sb_bytes_kind(kind, 2 * H, 4 * H));
+  a.raw = out; a.ldo = 2 * H; a.oscale = out_scale;
+  a.mode = MODE_PLAIN;
+  a.n = n;
+  a.H = H; a.kb_x = 4 * H / kbs_block_k(kind); a.kb_h = 0;
+  a.panels = int(pad_rows(n) / kPanelRows); a.tiles = 2 * H / kTileCols;
+  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(h, kind, a2, st)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+size_t kbs_tc_rows_sb_bytes(const kbs_handle* h, int64_t n, int K) { return kbs_sb_bytes_kind(tc_kind(h), pad_rows(n), K); }
+int kbs_tc_kind_of(const kbs_handle* h) { return tc_kind(h); }
 
 // ---- fused rollout: tensor-core input projection of all T steps + the recurrent phase --------------------------------
 // Workspace per net: h_sb [depth][2 parity] | x_mid_sb [2] | h2_rm [n][H] (floats)

@@ -90,6 +90,117 @@ cell_bwd_kernel(const float* __restrict__ dh_in, const float* __restrict__ dh_re
   dc_rec[idx] = dc * f;
 }
 
+// ---- tensor-core variant of the recurrent part: the same cell math, 8 hidden units per thread, and the operands of the
+// next GEMM written in the split-blocked MMA layout by the producing kernel (kbs_common.cuh) ----
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <int KIND>
+__device__ __forceinline__ void st8_sb(void* sb, int64_t row, int k, int K, const float (&v)[8], bool zero) {
+  const float a[4] = {v[0], v[1], v[2], v[3]}, b[4] = {v[4], v[5], v[6], v[7]};
+  sb_store_split8<kKbsPanelRows, KIND>(sb, row, k, K / kbs_block_k(KIND), sb_split4<KIND>(a), sb_split4<KIND>(b), zero);
+}
+
+// row-major [T][n][K] -> SB [T][np][K] (per-step panels; rows >= n of a step's last panel are left untouched)
+template <int KIND>
+__global__ void __launch_bounds__(kT)
+rows_to_sb_kernel(const float* __restrict__ rm, char* __restrict__ sb, size_t sb_step_bytes, int K, int64_t n, int64_t T) {
+  const int kq = K / 8;
+  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (idx >= T * n * kq) return;
+  const int g8 = int(idx % kq);
+  const int64_t row = idx / kq;
+  const int64_t t = row / n, e = row - t * n;
+  float v[8];
+  ld8(rm + row * K + g8 * 8, v);
+  st8_sb<KIND>(sb + size_t(t) * sb_step_bytes, e, g8 * 8, K, v, false);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kT)
+cell_fwd_save8_kernel(const float* __restrict__ gates_pre, const float* __restrict__ c_in, float* __restrict__ ga,
+                      float* __restrict__ cs, float* __restrict__ hs, float* __restrict__ h_next_in,
+                      float* __restrict__ c_next_in, char* __restrict__ hs_sb, char* __restrict__ h_next_in_sb,
+                      const uint8_t* __restrict__ done, int H, int64_t n) {
+  const int hq = H / 8;
+  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (idx >= n * hq) return;
+  const int64_t e = idx / hq;
+  const int k = int(idx - e * hq) * 8;
+  const float* g = gates_pre + e * 4 * H + k;
+  float gi[8], gf[8], gg[8], go[8], ci[8], c[8], hh[8];
+  ld8(g, gi); ld8(g + H, gf); ld8(g + 2 * H, gg); ld8(g + 3 * H, go); ld8(c_in + e * H + k, ci);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gi[j] = sigm(gi[j]); gf[j] = sigm(gf[j]); gg[j] = tanhf(gg[j]); go[j] = sigm(go[j]);
+    c[j] = gf[j] * ci[j] + gi[j] * gg[j];
+    hh[j] = go[j] * tanhf(c[j]);
+  }
+  float* a = ga + e * 4 * H + k;
+  st8(a, gi); st8(a + H, gf); st8(a + 2 * H, gg); st8(a + 3 * H, go);
+  st8(cs + e * H + k, c);
+  st8(hs + e * H + k, hh);
+  st8_sb<KIND>(hs_sb, e, k, H, hh, false);
+  if (h_next_in) {
+    const bool rst = done && done[e];
+    if (rst) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { hh[j] = 0.0f; c[j] = 0.0f; }
+    }
+    st8(h_next_in + e * H + k, hh);
+    st8(c_next_in + e * H + k, c);
+    st8_sb<KIND>(h_next_in_sb, e, k, H, hh, false);
+  }
+}
+
+// dh_in / dh_rec are read with their own row strides (they live in [n][2H] GEMM outputs); dG also in SB form [np][4H]
+template <int KIND>
+__global__ void __launch_bounds__(kT)
+cell_bwd8_kernel(const float* __restrict__ dh_in, int ld_in, const float* __restrict__ dh_rec, int ld_rec, float* __restrict__ dc_rec,
+                 const float* __restrict__ ga, const float* __restrict__ cs, const float* __restrict__ c_in,
+                 const uint8_t* __restrict__ done, float* __restrict__ dG, char* __restrict__ dG_sb, float gscale, int H, int64_t n) {
+  const int hq = H / 8;
+  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (idx >= n * hq) return;
+  const int64_t e = idx / hq;
+  const int k = int(idx - e * hq) * 8;
+  const float keep = (done && done[e]) ? 0.0f : 1.0f;
+  const float* a = ga + e * 4 * H + k;
+  float i[8], f[8], g[8], o[8], c[8], ci[8], dhi[8], dhr[8], dcr[8], di[8], df[8], dg[8], dob[8];
+  ld8(a, i); ld8(a + H, f); ld8(a + 2 * H, g); ld8(a + 3 * H, o);
+  ld8(cs + e * H + k, c); ld8(c_in + e * H + k, ci);
+  ld8(dh_in + e * ld_in + k, dhi);
+  if (dh_rec) ld8(dh_rec + e * ld_rec + k, dhr);
+  ld8(dc_rec + e * H + k, dcr);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float tc = tanhf(c[j]);
+    const float dh = dhi[j] + (dh_rec ? keep * dhr[j] : 0.0f);
+    const float dc = keep * dcr[j] + dh * o[j] * (1.0f - tc * tc);
+    di[j] = dc * g[j] * i[j] * (1.0f - i[j]);
+    df[j] = dc * ci[j] * f[j] * (1.0f - f[j]);
+    dg[j] = dc * i[j] * (1.0f - g[j] * g[j]);
+    dob[j] = dh * tc * o[j] * (1.0f - o[j]);
+    dcr[j] = dc * f[j];
+  }
+  float* d = dG + e * 4 * H + k;
+  st8(d, di); st8(d + H, df); st8(d + 2 * H, dg); st8(d + 3 * H, dob);
+  st8(dc_rec + e * H + k, dcr);
+  if (dG_sb) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { di[j] *= gscale; df[j] *= gscale; dg[j] *= gscale; dob[j] *= gscale; }   // into the FP16 planes' range
+    st8_sb<KIND>(dG_sb, e, k, 4 * H, di, false);
+    st8_sb<KIND>(dG_sb, e, H + k, 4 * H, df, false);
+    st8_sb<KIND>(dG_sb, e, 2 * H + k, 4 * H, dg, false);
+    st8_sb<KIND>(dG_sb, e, 3 * H + k, 4 * H, dob, false);
+  }
+}
+
 // out[c] partial column sums over a chunk of rows: partial[chunk][c]
 __global__ void __launch_bounds__(kT)
 colsum_partial_kernel(const float* __restrict__ X, int ld, int64_t rows, int cols, int64_t rows_per_chunk, float* __restrict__ partial) {
@@ -197,6 +308,80 @@ actor_head_fwd_bwd_kernel(const __grid_constant__ kbs_params P, kbs_ppo_loss_par
   }
 }
 
+// The same head with one WARP per env (lane j = joint j, log-prob / entropy by warp shuffles): the one-thread-per-env form
+// above was 3.5 ms of an 18 ms update (512 threads walking 2 x T steps x 20 joints of libm math and strided loads).
+__global__ void __launch_bounds__(128)
+actor_head_fwd_bwd_warp_kernel(const __grid_constant__ kbs_params P, kbs_ppo_loss_params L, const float* __restrict__ out,
+                               const float* __restrict__ actor_obs, const float* __restrict__ action,
+                               const uint8_t* __restrict__ done, const float* __restrict__ lpf0, const float* __restrict__ old_lp,
+                               const float* __restrict__ adv, float* __restrict__ y_s, float* __restrict__ sd_s,
+                               float* __restrict__ log_prob, float* __restrict__ entropy, float* __restrict__ dout, int64_t T,
+                               int64_t ld, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (e >= n) return;                                   // whole warps leave together
+  const int j = threadIdx.x & 31;
+  const bool act = j < KBS_NUM_JOINTS;
+  const int jj = act ? j : 0;
+  constexpr float kHalfLog2Pi = 0.918938533204672742f;
+  float y = (act && lpf0) ? lpf0[jj * ld + e] : 0.0f;
+  for (int64_t t = 0; t < T; ++t) {
+    const float* o = out + (t * n + e) * 64;
+    float tz = 0.0f, tl = 0.0f;
+    if (act) {
+      const float sraw = o[KBS_NUM_JOINTS + j];
+      const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
+      const float sd = fminf((sp + P.min_std) * P.var_scale, P.max_std);
+      float m = o[j] + P.joint_bias[j];
+      if (j >= 10) m = m + actor_obs[(t * KBS_ACTOR_OBS + 55 + (j - 10)) * ld + e];
+      y = y + P.lpf_alpha * (m - y);
+      const int64_t so = (t * KBS_NUM_JOINTS + j) * ld + e;
+      y_s[so] = y;
+      sd_s[so] = sd;
+      const float z = (action[so] - y) / sd;
+      tz = -0.5f * z * z - kHalfLog2Pi;
+      tl = logf(sd);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { tz += __shfl_xor_sync(0xffffffffu, tz, s); tl += __shfl_xor_sync(0xffffffffu, tl, s); }
+    if (j == 0) {
+      log_prob[t * ld + e] = tz - tl;
+      entropy[t * ld + e] = tl + float(KBS_NUM_JOINTS) * (0.5f + kHalfLog2Pi);
+    }
+    if (done[t * ld + e]) y = 0.0f;
+  }
+  __syncwarp();
+  const float inv = 1.0f / (float(T) * float(n));
+  float gy = 0.0f;
+  for (int64_t t = T - 1; t >= 0; --t) {
+    const float lr = log_prob[t * ld + e] - old_lp[t * ld + e];
+    const float lrc = fminf(fmaxf(lr, -L.log_clip_value), L.log_clip_value);
+    const float r = expf(lrc);
+    const float a = adv[t * ld + e];
+    const float dr = (fabsf(lr) <= L.log_clip_value) ? r : 0.0f;
+    const bool inside = r >= 1.0f - L.clip_param && r <= 1.0f + L.clip_param;
+    const float rc = fminf(fmaxf(r, 1.0f - L.clip_param), 1.0f + L.clip_param);
+    const float dpol = (inside || r * a < rc * a) ? a * dr : 0.0f;
+    const float glp = -inv * dpol, gent = -inv * L.entropy_coef;
+    const float keep = done[t * ld + e] ? 0.0f : 1.0f;
+    const float* o = out + (t * n + e) * 64;
+    float* d = dout + (t * n + e) * 64;
+    if (act) {
+      const int64_t so = (t * KBS_NUM_JOINTS + j) * ld + e;
+      const float sd = sd_s[so], yy = y_s[so];
+      const float z = (action[so] - yy) / sd;
+      const float dmu = glp * z / sd;
+      const float dsd = (glp * (z * z - 1.0f) + gent) / sd;
+      const float sraw = o[KBS_NUM_JOINTS + j];
+      const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
+      const bool clamped = (sp + P.min_std) * P.var_scale > P.max_std;
+      d[KBS_NUM_JOINTS + j] = clamped ? 0.0f : dsd * P.var_scale * sigm(sraw);
+      gy = dmu + (1.0f - P.lpf_alpha) * keep * gy;
+      d[j] = P.lpf_alpha * gy;
+    }
+    if (j < 24) d[2 * KBS_NUM_JOINTS + j] = 0.0f;
+  }
+}
+
 // Critic head: value_t = out[t][e][0]; dout[.][0] = d loss / d value (clipped value loss), other columns zero.
 __global__ void __launch_bounds__(kT)
 critic_head_fwd_bwd_kernel(kbs_ppo_loss_params L, const float* __restrict__ out, const float* __restrict__ old_values,
@@ -237,36 +422,48 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 unsigned blocks(int64_t n) { return unsigned((n + kT - 1) / kT); }
 
 struct NetWork {      // per-net workspace (floats), carved from the handle's scratch
-  float* obs_rm; float* x0; float* out; float* dout; float* dh_top; float* dx0;
+  float* obs_rm; float* x0; float* out; float* dout; float* dh_top;
+  float* dxh0;                           // [T*n][2H]: layer 0's (dx | dh_rec) of every step (dx feeds dW_in)
+  float* dxh[KBS_MAX_DEPTH];             // [n][2H] per layer >= 1: (dx for the layer below | dh_rec for step t - 1)
   float* ga[KBS_MAX_DEPTH]; float* cs[KBS_MAX_DEPTH]; float* hs[KBS_MAX_DEPTH]; float* h_in[KBS_MAX_DEPTH]; float* c_in[KBS_MAX_DEPTH];
   float* dG[KBS_MAX_DEPTH];
   float* w_ihT[KBS_MAX_DEPTH]; float* w_hhT[KBS_MAX_DEPTH]; float* w_outT;
+  // tensor-core path: the same activations as split-blocked MMA operands ([T] x per-step buffers)
+  char* x0_sb; char* hs_sb[KBS_MAX_DEPTH]; char* h_in_sb[KBS_MAX_DEPTH]; char* dG_sb;
 };
 
-size_t net_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n) {
+size_t net_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n, bool tc) {
   const size_t H = size_t(h->p.hidden_size), rows = size_t(T) * size_t(n);
   const size_t kp = size_t(round_up_i(h->net[net].num_in, 64));
-  size_t f = rows * kp + rows * H * 3 /*x0, dh_top, dx0*/ + rows * 64 * 2;
-  f += size_t(h->p.depth) * (rows * 4 * H * 2 + rows * H * 4 + 2 * 4 * H * H);
+  const size_t depth = size_t(h->p.depth);
+  size_t f = rows * kp + rows * H * 2 /*x0, dh_top*/ + rows * 2 * H /*dxh0*/ + rows * 64 * 2 + depth * size_t(n) * 2 * H;
+  f += depth * (rows * 4 * H * 2 + rows * H * 4 + 2 * 4 * H * H + 256);
   f += 64 * H;
-  return f + 1024;
+  if (tc) {
+    const size_t sbH = kbs_tc_rows_sb_bytes(h, n, int(H)) / 4, sb4H = kbs_tc_rows_sb_bytes(h, n, int(4 * H)) / 4;
+    f += size_t(T) * sbH * (1 + 2 * depth) + sb4H + 1024;
+  }
+  return f + 4096;
 }
 
 float* carve(float*& p, size_t floats) { float* r = p; p += (floats + 63) / 64 * 64; return r; }
 
-int run_net(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0, NetWork& w, float* gates_pre, float* dx_up,
-            float* dh_rec, float* dc_rec, float* part, int splits, int64_t n, cudaStream_t st, bool backward,
-            const kbs_net_grads* g) {
+template <int KIND>
+int run_net_k(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0, NetWork& w, float* gates_pre, float* dc_rec,
+              float* part, int splits, int64_t n, cudaStream_t st, bool backward, const kbs_net_grads* g, bool tc) {
   const KbsNet& N = h->net[net];
   const int H = h->p.hidden_size, depth = h->p.depth;
   const int64_t T = b.T, ld = b.ld, rows = T * n;
   const int kp = round_up_i(N.num_in, 64);
   const size_t sH = size_t(n) * H;
+  const size_t sbH = tc ? kbs_tc_rows_sb_bytes(h, n, H) : 0;
   int rc;
   if (!backward) {
     const float* obs = net == KBS_NET_ACTOR ? b.actor_obs : b.critic_obs;
     KBS_LAUNCH(h, KBS_K_PACK, st, (soa_to_rows_kernel<<<blocks(rows * kp), kT, 0, st>>>(obs, N.num_in, ld, w.obs_rm, kp, n, T)));
     if ((rc = kbs_simt_gemm_nt(h, w.obs_rm, kp, N.w_in, N.kin_pad, N.b_in, w.x0, H, rows, H, N.kin_pad, 0, st))) return rc;
+    if (tc)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (rows_to_sb_kernel<KIND><<<blocks(rows * (H / 8)), kT, 0, st>>>(w.x0, w.x0_sb, sbH, H, n, T)));
     for (int l = 0; l < depth; ++l) {       // carries the first step reads: ABI layout [depth][2][n][H] or zeros
       if (carry0) {
         KBS_CUDA_TRY(cudaMemcpyAsync(w.h_in[l], carry0 + (size_t(l) * 2 + 0) * sH, sH * 4, cudaMemcpyDeviceToDevice, st));
@@ -275,19 +472,32 @@ int run_net(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0,
         KBS_CUDA_TRY(cudaMemsetAsync(w.h_in[l], 0, sH * 4, st));
         KBS_CUDA_TRY(cudaMemsetAsync(w.c_in[l], 0, sH * 4, st));
       }
+      if (tc)
+        KBS_LAUNCH(h, KBS_K_PACK, st, (rows_to_sb_kernel<KIND><<<blocks(n * (H / 8)), kT, 0, st>>>(w.h_in[l], w.h_in_sb[l], sbH, H, n, 1)));
     }
     for (int64_t t = 0; t < T; ++t) {
       for (int l = 0; l < depth; ++l) {
-        const float* x_in = (l == 0 ? w.x0 : w.hs[l - 1]) + size_t(t) * sH;
-        if ((rc = kbs_simt_gemm_nt(h, x_in, H, N.w_ih[l], H, N.b[l], gates_pre, 4 * H, n, 4 * H, H, 0, st))) return rc;
-        if ((rc = kbs_simt_gemm_nt(h, w.h_in[l] + size_t(t) * sH, H, N.w_hh[l], H, nullptr, gates_pre, 4 * H, n, 4 * H, H, 1, st)))
-          return rc;
         const bool last = t + 1 == T;
-        KBS_LAUNCH(h, KBS_K_LSTM_CELL, st,
-                   (cell_fwd_save_kernel<<<blocks(n * H), kT, 0, st>>>(
-                       gates_pre, w.c_in[l] + size_t(t) * sH, w.ga[l] + size_t(t) * sH * 4, w.cs[l] + size_t(t) * sH,
-                       w.hs[l] + size_t(t) * sH, last ? nullptr : w.h_in[l] + size_t(t + 1) * sH,
-                       last ? nullptr : w.c_in[l] + size_t(t + 1) * sH, b.done + t * ld, H, n)));
+        float* hn = last ? nullptr : w.h_in[l] + size_t(t + 1) * sH;
+        float* cn = last ? nullptr : w.c_in[l] + size_t(t + 1) * sH;
+        if (tc) {
+          const char* x_sb = (l == 0 ? w.x0_sb : w.hs_sb[l - 1]) + size_t(t) * sbH;
+          if ((rc = kbs_tc_gates_fwd(h, net, l, x_sb, w.h_in_sb[l] + size_t(t) * sbH, gates_pre, n, st))) return rc;
+          KBS_LAUNCH(h, KBS_K_LSTM_CELL, st,
+                     (cell_fwd_save8_kernel<KIND><<<blocks(n * (H / 8)), kT, 0, st>>>(
+                         gates_pre, w.c_in[l] + size_t(t) * sH, w.ga[l] + size_t(t) * sH * 4, w.cs[l] + size_t(t) * sH,
+                         w.hs[l] + size_t(t) * sH, hn, cn, w.hs_sb[l] + size_t(t) * sbH,
+                         last ? nullptr : w.h_in_sb[l] + size_t(t + 1) * sbH, b.done + t * ld, H, n)));
+        } else {
+          const float* x_in = (l == 0 ? w.x0 : w.hs[l - 1]) + size_t(t) * sH;
+          if ((rc = kbs_simt_gemm_nt(h, x_in, H, N.w_ih[l], H, N.b[l], gates_pre, 4 * H, n, 4 * H, H, 0, st))) return rc;
+          if ((rc = kbs_simt_gemm_nt(h, w.h_in[l] + size_t(t) * sH, H, N.w_hh[l], H, nullptr, gates_pre, 4 * H, n, 4 * H, H, 1, st)))
+            return rc;
+          KBS_LAUNCH(h, KBS_K_LSTM_CELL, st,
+                     (cell_fwd_save_kernel<<<blocks(n * H), kT, 0, st>>>(
+                         gates_pre, w.c_in[l] + size_t(t) * sH, w.ga[l] + size_t(t) * sH * 4, w.cs[l] + size_t(t) * sH,
+                         w.hs[l] + size_t(t) * sH, hn, cn, b.done + t * ld, H, n)));
+        }
       }
     }
     if ((rc = kbs_simt_gemm_nt(h, w.hs[depth - 1], H, N.w_out, H, N.b_out, w.out, 64, rows, 64, H, 0, st))) return rc;
@@ -295,28 +505,48 @@ int run_net(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0,
     return KBS_OK;
   }
   // ---- backward: w.dout [rows][64] holds d loss / d out ----
-  for (int l = 0; l < depth; ++l) {
-    KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(4) * H * H), kT, 0, st>>>(N.w_ih[l], 4 * H, H, w.w_ihT[l])));
-    KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(4) * H * H), kT, 0, st>>>(N.w_hh[l], 4 * H, H, w.w_hhT[l])));
+  if (tc) {
+    if ((rc = kbs_tc_pack_bwd(h, net, st))) return rc;
+  } else {
+    for (int l = 0; l < depth; ++l) {
+      KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(4) * H * H), kT, 0, st>>>(N.w_ih[l], 4 * H, H, w.w_ihT[l])));
+      KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(4) * H * H), kT, 0, st>>>(N.w_hh[l], 4 * H, H, w.w_hhT[l])));
+    }
   }
   KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(64) * H), kT, 0, st>>>(N.w_out, 64, H, w.w_outT)));
   if ((rc = kbs_simt_gemm_nt(h, w.dout, 64, w.w_outT, 64, nullptr, w.dh_top, H, rows, H, 64, 0, st))) return rc;
-  for (int l = 0; l < depth; ++l) {
-    KBS_CUDA_TRY(cudaMemsetAsync(dh_rec + size_t(l) * sH, 0, sH * 4, st));
-    KBS_CUDA_TRY(cudaMemsetAsync(dc_rec + size_t(l) * sH, 0, sH * 4, st));
-  }
+  for (int l = 0; l < depth; ++l) KBS_CUDA_TRY(cudaMemsetAsync(dc_rec + size_t(l) * sH, 0, sH * 4, st));
+  // the loss is a mean over T n transitions: per-sample gradients are O(1e-2..1), dG = that / (T n).  Scale dG back up by
+  // the next power of two of T n (x 16) before the FP16 split; exact, undone by the GEMM's output scale.
+  float gscale = 16.0f;
+  while (gscale < 16.0f * float(rows)) gscale *= 2.0f;
   for (int64_t t = T - 1; t >= 0; --t) {
     for (int l = depth - 1; l >= 0; --l) {
-      const float* dh_in = (l == depth - 1) ? w.dh_top + size_t(t) * sH : dx_up;
+      // gradient wrt h_t from above: the head (top layer) or the dx half of the layer above at this step
+      const float* dh_in = (l == depth - 1) ? w.dh_top + size_t(t) * sH : w.dxh[l + 1];
+      const int ld_in = (l == depth - 1) ? H : 2 * H;
+      // gradient wrt the carry h that step t + 1 read: the dh half of this layer's own GEMM at step t + 1
+      float* dxh_next = (l == 0) ? w.dxh0 + size_t(t + 1) * sH * 2 : w.dxh[l];
+      const float* dh_rec = (t + 1 < T) ? dxh_next + H : nullptr;
       float* dG = w.dG[l] + size_t(t) * sH * 4;
-      KBS_LAUNCH(h, KBS_K_LSTM_CELL, st,
-                 (cell_bwd_kernel<<<blocks(n * H), kT, 0, st>>>(dh_in, dh_rec + size_t(l) * sH, dc_rec + size_t(l) * sH,
-                                                                w.ga[l] + size_t(t) * sH * 4, w.cs[l] + size_t(t) * sH,
-                                                                w.c_in[l] + size_t(t) * sH, b.done + t * ld, dG, H, n)));
-      float* dx = (l == 0) ? w.dx0 + size_t(t) * sH : dx_up;
-      if ((rc = kbs_simt_gemm_nt(h, dG, 4 * H, w.w_ihT[l], 4 * H, nullptr, dx, H, n, H, 4 * H, 0, st))) return rc;
-      if (t > 0 && (rc = kbs_simt_gemm_nt(h, dG, 4 * H, w.w_hhT[l], 4 * H, nullptr, dh_rec + size_t(l) * sH, H, n, H, 4 * H, 0, st)))
-        return rc;
+      float* dxh_out = (l == 0) ? w.dxh0 + size_t(t) * sH * 2 : w.dxh[l];
+      if (tc) {
+        KBS_LAUNCH(h, KBS_K_LSTM_CELL, st,
+                   (cell_bwd8_kernel<KIND><<<blocks(n * (H / 8)), kT, 0, st>>>(dh_in, ld_in, dh_rec, 2 * H, dc_rec + size_t(l) * sH,
+                                                                              w.ga[l] + size_t(t) * sH * 4, w.cs[l] + size_t(t) * sH,
+                                                                              w.c_in[l] + size_t(t) * sH, b.done + t * ld, dG,
+                                                                              w.dG_sb, gscale, H, n)));
+        if ((rc = kbs_tc_bwd_gemm(h, net, l, w.dG_sb, dxh_out, n, 1.0f / gscale, st))) return rc;
+      } else {
+        KBS_LAUNCH(h, KBS_K_LSTM_CELL, st,
+                   (cell_bwd8_kernel<KIND><<<blocks(n * (H / 8)), kT, 0, st>>>(dh_in, ld_in, dh_rec, 2 * H, dc_rec + size_t(l) * sH,
+                                                                              w.ga[l] + size_t(t) * sH * 4, w.cs[l] + size_t(t) * sH,
+                                                                              w.c_in[l] + size_t(t) * sH, b.done + t * ld, dG,
+                                                                              nullptr, 1.0f, H, n)));
+        if ((rc = kbs_simt_gemm_nt(h, dG, 4 * H, w.w_ihT[l], 4 * H, nullptr, dxh_out, 2 * H, n, H, 4 * H, 0, st))) return rc;
+        if (t > 0 && (rc = kbs_simt_gemm_nt(h, dG, 4 * H, w.w_hhT[l], 4 * H, nullptr, dxh_out + H, 2 * H, n, H, 4 * H, 0, st)))
+          return rc;
+      }
     }
   }
   // weight gradients: sums over all (t, env) rows
@@ -335,9 +565,9 @@ int run_net(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0,
   {
     // dW_in [H][kp] -> caller's dense [H][num_in]; dW_out [64][H] -> first num_out rows
     float* tmp = part2 + size_t(splits) * size_t(4 * H) * size_t(kp > H ? kp : H);
-    if ((rc = kbs_simt_gemm_tn(h, w.dx0, H, w.obs_rm, kp, tmp, kp, H, kp, rows, part2, splits, st))) return rc;
+    if ((rc = kbs_simt_gemm_tn(h, w.dxh0, 2 * H, w.obs_rm, kp, tmp, kp, H, kp, rows, part2, splits, st))) return rc;
     KBS_LAUNCH(h, KBS_K_PACK, st, (copy_block_kernel<<<blocks(int64_t(H) * N.num_in), kT, 0, st>>>(tmp, kp, g->w_in, H, N.num_in)));
-    colsum(w.dx0, H, H, g->b_in);
+    colsum(w.dxh0, 2 * H, H, g->b_in);
     if ((rc = kbs_simt_gemm_tn(h, w.dout, 64, w.hs[depth - 1], H, tmp, H, 64, H, rows, part2, splits, st))) return rc;
     KBS_LAUNCH(h, KBS_K_PACK, st, (copy_block_kernel<<<blocks(int64_t(N.num_out) * H), kT, 0, st>>>(tmp, H, g->w_out, N.num_out, H)));
     float* bsum = tmp + size_t(64) * H;
@@ -346,6 +576,14 @@ int run_net(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0,
   }
   KBS_LAUNCH_CHECK();
   return KBS_OK;
+}
+
+int run_net(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0, NetWork& w, float* gates_pre, float* dc_rec,
+            float* part, int splits, int64_t n, cudaStream_t st, bool backward, const kbs_net_grads* g) {
+  const bool tc = h->p.gemm_path != KBS_GEMM_SIMT_FP32 && h->net[net].tc_image != nullptr && (h->p.hidden_size % 64) == 0;
+  if (tc && kbs_tc_kind_of(h) == KBS_KIND_TF32)
+    return run_net_k<KBS_KIND_TF32>(h, net, b, carry0, w, gates_pre, dc_rec, part, splits, n, st, backward, g, true);
+  return run_net_k<KBS_KIND_F16>(h, net, b, carry0, w, gates_pre, dc_rec, part, splits, n, st, backward, g, tc);
 }
 
 }  // namespace
@@ -369,20 +607,17 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
   const int splits = 8;
   const int chunks = int((rows + 511) / 512);
   const int kp_max = round_up_i(KBS_CRITIC_OBS, 64);
-  const size_t shared_f = 2 * (sH * 4 /*gates_pre*/ + sH /*dx_up*/ + 2 * size_t(depth) * sH /*dh_rec, dc_rec*/ +
-                               size_t(chunks) * 4 * H + size_t(splits) * size_t(4 * H) * size_t(kp_max) + size_t(H) * kp_max + 64 * H +
-                               4096 + 1024) +
+  const bool tc = h->p.gemm_path != KBS_GEMM_SIMT_FP32;
+  const size_t part_f = size_t(chunks) * 4 * H + size_t(splits) * size_t(4 * H) * size_t(kp_max) + size_t(H) * kp_max + 64 * H + 4096;
+  const size_t shared_f = 2 * (sH * 4 /*gates_pre*/ + size_t(depth) * sH /*dc_rec*/ + part_f + 1024) +
                           2 * size_t(T) * KBS_NUM_JOINTS * ld /*y_s, sd_s*/;
-  const size_t total_f = shared_f + net_work_floats(h, 0, T, n) + net_work_floats(h, 1, T, n) + 8192;
+  const size_t total_f = shared_f + net_work_floats(h, 0, T, n, tc) + net_work_floats(h, 1, T, n, tc) + 8192;
   int rc = kbs_scratch_reserve(h, total_f);
   if (rc) return rc;
   float* p = h->scratch;
-  const size_t part_f = size_t(chunks) * 4 * H + size_t(splits) * size_t(4 * H) * size_t(kp_max) + size_t(H) * kp_max + 64 * H + 4096;
-  float* gates_pre[2]; float* dx_up[2]; float* dh_rec[2]; float* dc_rec[2]; float* part[2];
+  float* gates_pre[2]; float* dc_rec[2]; float* part[2];
   for (int k = 0; k < 2; ++k) {            // per net: actor and critic run concurrently on two streams
     gates_pre[k] = carve(p, sH * 4);
-    dx_up[k] = carve(p, sH);
-    dh_rec[k] = carve(p, size_t(depth) * sH);
     dc_rec[k] = carve(p, size_t(depth) * sH);
     part[k] = carve(p, part_f);
   }
@@ -394,10 +629,11 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
     w[k].obs_rm = carve(p, size_t(rows) * kp);
     w[k].x0 = carve(p, size_t(rows) * H);
     w[k].dh_top = carve(p, size_t(rows) * H);
-    w[k].dx0 = carve(p, size_t(rows) * H);
+    w[k].dxh0 = carve(p, size_t(rows) * 2 * H);
     w[k].out = carve(p, size_t(rows) * 64);
     w[k].dout = carve(p, size_t(rows) * 64);
     for (int l = 0; l < depth; ++l) {
+      w[k].dxh[l] = carve(p, sH * 2);
       w[k].ga[l] = carve(p, size_t(rows) * 4 * H);
       w[k].dG[l] = carve(p, size_t(rows) * 4 * H);
       w[k].cs[l] = carve(p, size_t(rows) * H);
@@ -408,6 +644,15 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
       w[k].w_hhT[l] = carve(p, size_t(4) * H * H);
     }
     w[k].w_outT = carve(p, size_t(64) * H);
+    if (tc) {
+      const size_t sbH = kbs_tc_rows_sb_bytes(h, n, H) / 4, sb4H = kbs_tc_rows_sb_bytes(h, n, 4 * H) / 4;
+      w[k].x0_sb = reinterpret_cast<char*>(carve(p, size_t(T) * sbH));
+      for (int l = 0; l < depth; ++l) {
+        w[k].hs_sb[l] = reinterpret_cast<char*>(carve(p, size_t(T) * sbH));
+        w[k].h_in_sb[l] = reinterpret_cast<char*>(carve(p, size_t(T) * sbH));
+      }
+      w[k].dG_sb = reinterpret_cast<char*>(carve(p, sb4H));
+    }
   }
   // The two networks share nothing until the loss statistics: the critic runs on the handle's side stream, forked from
   // and joined into the caller's stream with events (capturable: the whole call can be replayed as one CUDA graph).
@@ -416,25 +661,25 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
   KBS_CUDA_TRY(cudaEventRecord(h->ev_pre, st));
   KBS_CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_pre, 0));
   // forward with saved activations
-  if ((rc = run_net(h, KBS_NET_ACTOR, *b, b->actor_carry0, w[0], gates_pre[0], dx_up[0], dh_rec[0], dc_rec[0], part[0], splits, n, st,
+  if ((rc = run_net(h, KBS_NET_ACTOR, *b, b->actor_carry0, w[0], gates_pre[0], dc_rec[0], part[0], splits, n, st,
                     false, nullptr)))
     return rc;
-  if ((rc = run_net(h, KBS_NET_CRITIC, *b, b->critic_carry0, w[1], gates_pre[1], dx_up[1], dh_rec[1], dc_rec[1], part[1], splits, n, sc,
+  if ((rc = run_net(h, KBS_NET_CRITIC, *b, b->critic_carry0, w[1], gates_pre[1], dc_rec[1], part[1], splits, n, sc,
                     false, nullptr)))
     return rc;
   // heads: outputs, loss gradient wrt the head outputs
   KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
-             (actor_head_fwd_bwd_kernel<<<unsigned((n + 127) / 128), 128, 0, st>>>(
+             (actor_head_fwd_bwd_warp_kernel<<<unsigned((n + 3) / 4), 128, 0, st>>>(
                  h->p, *params, w[0].out, b->actor_obs, b->action, b->done, b->lpf0, b->old_log_probs, b->advantages, y_s, sd_s,
                  log_probs, entropy, w[0].dout, T, ld, n)));
   KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, sc,
              (critic_head_fwd_bwd_kernel<<<blocks(rows), kT, 0, sc>>>(*params, w[1].out, b->old_values, b->value_targets, values,
                                                                       w[1].dout, T, ld, n)));
   // critic backward on the side stream
-  if ((rc = run_net(h, KBS_NET_CRITIC, *b, nullptr, w[1], gates_pre[1], dx_up[1], dh_rec[1], dc_rec[1], part[1], splits, n, sc, true, critic)))
+  if ((rc = run_net(h, KBS_NET_CRITIC, *b, nullptr, w[1], gates_pre[1], dc_rec[1], part[1], splits, n, sc, true, critic)))
     return rc;
   KBS_CUDA_TRY(cudaEventRecord(h->ev_head[0], sc));
-  if ((rc = run_net(h, KBS_NET_ACTOR, *b, nullptr, w[0], gates_pre[0], dx_up[0], dh_rec[0], dc_rec[0], part[0], splits, n, st, true, actor)))
+  if ((rc = run_net(h, KBS_NET_ACTOR, *b, nullptr, w[0], gates_pre[0], dc_rec[0], part[0], splits, n, st, true, actor)))
     return rc;
   KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[0], 0));       // join: values + critic gradients are complete
   // loss statistics (same kernel as kbs_ppo_loss; partials in the actor's reduction scratch, free again by now)

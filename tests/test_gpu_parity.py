@@ -572,13 +572,15 @@ def _ppo_batch(rng, T, N, H, p, wa, wc):
     return b
 
 
-@pytest.mark.parametrize("T,N,hidden", [(5, 24, 128), (7, 70, 256)])
-def test_ppo_grad_against_autograd(dev, T, N, hidden):
+@pytest.mark.parametrize("path", [pytest.param(L.GEMM_SIMT_FP32, id="simt"), pytest.param(L.GEMM_TC_2XF16, id="tc2xf16"),
+                                  pytest.param(L.GEMM_TC_3XTF32, id="tc3xtf32")])
+@pytest.mark.parametrize("T,N,hidden", [(5, 24, 128), (7, 70, 256), (4, 300, 256)])
+def test_ppo_grad_against_autograd(dev, T, N, hidden, path):
     """8f-1: back-propagation through time through both LSTMs, the projections, the actor head (incl. the low-pass filter's
     recurrence and the done-resets) and the PPO loss, against torch.autograd (float64) on the same minibatch."""
     import ppo_grad_torch as G
 
-    e, wa, wc = Hn.make_engine(hidden=hidden, device=dev)
+    e, wa, wc = Hn.make_engine(hidden=hidden, gemm_path=path, device=dev)
     p = O.OracleParams(hidden_size=hidden)
     rng = np.random.default_rng(90 + N)
     b = _ppo_batch(rng, T, N, hidden, p, wa, wc)
@@ -621,7 +623,7 @@ def test_ppo_update_adam_step_decreases_loss(dev):
     from kbot_joystick_b200.ppo import PpoUpdater
 
     T, N, H = 6, 48, 128
-    e, wa, wc = Hn.make_engine(hidden=H, device=dev)
+    e, wa, wc = Hn.make_engine(hidden=H, gemm_path=L.GEMM_TC_2XF16, device=dev)
     p = O.OracleParams(hidden_size=H)
     rng = np.random.default_rng(5)
     b = _ppo_batch(rng, T, N, H, p, wa, wc)

@@ -71,7 +71,7 @@ if rank == 0:
     msf = float(ms.item())
     print(json.dumps({"config": "configs[3] PPO minibatch update (kbs_ppo_grad + NCCL all-reduce + kbs_adam_step)", "n_gpus": world,
                       "trajectories_per_gpu": N, "T": T, "ms_per_update": msf, "env_steps_per_s": world * N * T / (msf * 1e-3),
-                      "grad_floats": int(up.grad.numel()), "loss": float(st["stats"][0]), "datapath": "fp32 FFMA GEMMs (first version)", "launch": "cuda-graph replay" if a.graph else "eager"}),
+                      "grad_floats": int(up.grad.numel()), "loss": float(st["stats"][0]), "datapath": "tcgen05 2xFP16-split recurrent GEMMs + fp32 FFMA batched GEMMs", "launch": "cuda-graph replay" if a.graph else "eager"}),
           flush=True)
 eng.close()
 if world > 1:
