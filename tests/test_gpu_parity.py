@@ -507,6 +507,17 @@ def test_upload_state_moves_every_row_the_path_reads(dev):
     e.close()
 
 
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("depth,with_critic,N", [(1, True, 140), (2, False, 200), (1, False, 33)])
+def test_rollout_fused_other_shapes(dev, path, depth, with_critic, N):
+    """Shapes off the launch configuration: one LSTM layer, actor only (the persistent kernel's item list and counter
+    protocol depend on both)."""
+    res = Hn.run_rollout_case(seed=860 + N, T=5, N=N, hidden=256, device=dev, gemm_path=path, depth=depth,
+                              with_critic=with_critic)
+    bad = {k: v for k, v in res["errors"].items() if not v <= 1.0}
+    assert not bad, f"scaled errors > 1: {bad} (all: {res['errors']})"
+
+
 def test_rollout_then_rewards_gae_chain(dev):
     """Whole path once: rollout -> rewards -> GAE on its outputs, against the same chain in the oracle."""
     T, N = 12, 64
