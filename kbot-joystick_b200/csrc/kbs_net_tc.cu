@@ -721,7 +721,9 @@ constexpr int kTileColsP = 256;
 constexpr int kUnitsPerTileP = kTileColsP / 4;
 constexpr int kBBlockBytesP = 2 * 4 * kTileColsP * 16;          // [chunk][hi|lo][256 rows][16 B] = 32 KB
 constexpr int kStageBytesP = kABlockBytes + kBBlockBytesP;      // 48 KB
-constexpr int kStagesP = 4;              // power of two that divides every item's stage count (8 or 16 at H = 256)
+constexpr int kStagesP = 4;              // power of two that divides every item's stage count (8 or 16 at H = 256).  A ring of
+                                         // 8 half-stages (24 KB, one k-step, 3 MMAs + commit each) measured the same 20.6 K
+                                         // cycles per item: the extra commits eat what the finer ring gives.
 constexpr int kPSmemBytes = kStagesP * kStageBytesP + (kPBiasFloats + kPHeadPartFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
 
 struct PNet {
@@ -914,13 +916,7 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
           wb = N.w_head;
         }
         ++j;
-        if (lane == 0) {
-          const long long d0 = tr ? clock64() : 0;
-          while (*dep_seq < j) { }
-          __threadfence_block();
-          asm volatile("fence.proxy.async;" ::: "memory");    // the activation blocks were written with generic stores
-          if (tr) pw[2] += clock64() - d0;
-        }
+        bool need_dep = true;        // lane 0: the item's dependency wait + proxy fence, taken just before its first activation copy
         for (int b = 0; b < kb_total; ++b, ++g) {
           const int s = g % kStagesP;
           // probes: 32 = token weight copies, 128 = no weight request at all, 256 = half-size activation request
@@ -937,6 +933,16 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
           uint8_t* sa = smem + size_t(s) * kStageBytesP;
           const char* src = lane == 0 ? ((b < kb_x) ? xa + size_t(b) * kABlockBytes : ha + size_t(b - kb_x) * kABlockBytes)
                                       : wb + size_t(b) * kBBlockBytesP;
+          // the weight block needs no dependency: lane 1 issues it at once, while lane 0 (first stage of the item only) waits
+          // for the poller's go-ahead and orders the other CTAs' generic stores before its bulk copy
+          if (lane == 0 && need_dep) {
+            const long long d0 = tr ? clock64() : 0;
+            while (*dep_seq < j) { }
+            __threadfence_block();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            if (tr) pw[2] += clock64() - d0;
+            need_dep = false;
+          }
           if (lane == 0 || wbytes) bulk_g2s(sa + lane * kABlockBytes, src, lane == 0 ? abytes : wbytes, &full[s]);
           if (tr && lane == 0) { pw[0] += p1 - p0; pw[1] += clock64() - p1; }
         }
@@ -1425,7 +1431,7 @@ static inline float* head_bias(const kbs_handle* h, int net) {
 static inline bool persist_shape_ok(const kbs_handle* h) {
   const int H = h->p.hidden_size;
   return H % kUnitsPerTileP == 0 && h->p.depth <= kPMaxDepth && H <= kMaxBias / 4 &&
-         (H / kbs_block_k(tc_kind(h))) % kStagesP == 0;
+         (H / kbs_block_k(tc_kind(h))) % 4 == 0;
 }
 
 int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
