@@ -592,6 +592,43 @@ int kbs_policy_step(kbs_handle* h, const float* joint_angles, const float* joint
   cudaStream_t st = (cudaStream_t)stream;
   const int H = h->p.hidden_size, d2 = 2 * h->p.depth;
   const int64_t ld = round_up4(n);
+  {
+    const char* legacy_env = getenv("KBS_TC_PER_STEP");
+    if (h->p.gemm_path != KBS_GEMM_SIMT_FP32 && !(legacy_env && atoi(legacy_env)) && d2 <= 8 &&
+        kbs_tc_persistent_available(h, n, 1, 1)) {
+      // Tensor-core form: input projection on tcgen05, then the persistent recurrence kernel with T = 1 (128 x 256 tiles,
+      // output head fused into its epilogue; action = dist.mode() because no sampling noise is passed).  The flat carry
+      // records [n][d2 * H + 20] are converted straight to / from the kernel's operand layouts: one pass each way
+      // instead of flat -> [d2][n][H] -> SB / FB (and back), which was 2/3 of the step's HBM traffic at large n.
+      const int carry_w = d2 * H + 20;
+      const size_t ws_f = kbs_tc_rollout_ws_floats(h, n);
+      const size_t xsb_f = size_t(kbs_tc_sb_floats(h, n));
+      const size_t osb_f = size_t(kbs_tc_obs_sb_floats(h, KBS_NET_ACTOR, n, 1));
+      int rc = kbs_scratch_reserve(h, ws_f + xsb_f + osb_f + size_t(KBS_ACTOR_OBS + 20 + 20) * ld + 64);
+      if (rc) return rc;
+      float* ws = h->scratch;
+      float* xsb = ws + ws_f;
+      float* osb = xsb + xsb_f;
+      float* obs = osb + osb_f;
+      float* lpf = obs + size_t(KBS_ACTOR_OBS) * ld;
+      float* act = lpf + 20 * ld;
+      if ((rc = kbs_launch_policy_pack(h, joint_angles, joint_vel, projected_gravity, gyro, command, carry_in, obs, nullptr,
+                                       lpf, ld, n, st)))
+        return rc;
+      const float* obs_soa[2] = {obs, nullptr};
+      float* obs_sb[2] = {osb, nullptr};
+      float* x_all[2] = {xsb, nullptr};
+      if ((rc = kbs_tc_input_proj_all(h, 1, obs_soa, obs_sb, x_all, ld, n, 1, st))) return rc;
+      KbsTcRolloutArgs r{};
+      r.n = n; r.ld = ld; r.T = 1; r.with_critic = false;
+      r.x_sb_all[0] = xsb;
+      r.carry[0] = const_cast<float*>(carry_in); r.carry_out[0] = carry_out; r.carry_ld = carry_w;
+      r.actor_obs = obs; r.lpf = lpf; r.action = act;
+      r.ws = ws;
+      if ((rc = kbs_tc_rollout_recurrent(h, r, st))) return rc;
+      return kbs_launch_policy_unpack(h, nullptr, lpf, act, carry_out, action_out, ld, n, st);
+    }
+  }
   const size_t ts = trunk_scratch_floats(h, n);
   const size_t need = ts + size_t(n) * kOutLd + size_t(KBS_ACTOR_OBS + 20 + 20) * ld + size_t(d2) * n * H + 64;
   int rc = kbs_scratch_reserve(h, need);

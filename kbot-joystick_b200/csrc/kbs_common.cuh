@@ -159,6 +159,11 @@ struct KbsTcRolloutArgs {
   bool with_critic;
   const float* x_sb_all[2];   // [T] x kbs_tc_sb_floats SB input-projection outputs per net (actor, critic)
   float* carry[2];            // ABI carries [depth][2][n][H]
+  // carry_ld != 0 (persistent kernel only): the carries are rows of a flat per-env record instead (convert.py carry
+  // [n][depth*2*H + 20]): element (slot = 2 * layer + {h, c}, env e, unit k) at carry[net][e * carry_ld + slot * H + k],
+  // read from carry[] and written to carry_out[] (nullptr = in place).
+  int64_t carry_ld;
+  float* carry_out[2];
   const uint8_t* done;        // [T][ld]
   const float* actor_obs;     // [T][65][ld]
   float* lpf;                 // [20][ld]
@@ -183,6 +188,8 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
                           int64_t ld, int64_t n, int64_t T, cudaStream_t st, const float* cinert = nullptr,
                           const float* cvel = nullptr);
 int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStream_t st);
+// true when kbs_tc_rollout_recurrent will take the persistent kernel for this shape (all T steps in one launch)
+bool kbs_tc_persistent_available(const kbs_handle* h, int64_t n, int64_t T, int nets);
 int kbs_tc_debug_trace(kbs_handle* h, long long* trace_out, float* ws, int64_t n, cudaStream_t st);
 // tensor-core GEMMs of the PPO update
 int kbs_tc_gates_fwd(kbs_handle* h, int net, int layer, const void* x_sb, const void* h_sb, float* gates_out, int64_t n,

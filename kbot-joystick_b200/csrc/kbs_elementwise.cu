@@ -69,6 +69,7 @@ __device__ __forceinline__ void encode_pg(const float (&g)[3], float (&o)[5]) {
 // train.py:1155-1204, 682-707, 1329-1431.  grid = (env groups, 1 + copy sections).
 // =====================================================================================================
 constexpr int kCopyRowsPerSection = 46;  // 368 pure-copy rows (cinert 230 + cvel 138) in 8 sections
+constexpr int kObsSections = 4;          // computed rows of one env-step in 4 sections (see obs_kernel)
 
 __global__ void __launch_bounds__(kThreads)
 obs_kernel(const __grid_constant__ kbs_params P, kbs_state_view s, kbs_noise_view nz,
@@ -93,9 +94,13 @@ obs_kernel(const __grid_constant__ kbs_params P, kbs_state_view s, kbs_noise_vie
     if (critic_obs) critic_obs += t * KBS_CRITIC_OBS * ld;
   }
 
-  if (blockIdx.y > 0) {
+  // blockIdx.y = section: the rows of one env-step are independent, so they are spread over kObsSections x as many
+  // threads (one thread doing all ~250 rows of its 4 envs left 21 warps per SM and 2.4 TB/s).
+  //   0 / 1: joints 0-9 / 10-19   2: IMU + command slots   3: feet positions + the critic's small copies   4..: dump
+  const int sec = blockIdx.y;
+  if (sec >= kObsSections) {
     // critic privileged dump: center_of_mass_inertia = cinert[1:], center_of_mass_velocity = cvel[1:]
-    const int i0 = (blockIdx.y - 1) * kCopyRowsPerSection;
+    const int i0 = (sec - kObsSections) * kCopyRowsPerSection;
 #pragma unroll 8
     for (int i = i0; i < i0 + kCopyRowsPerSection; ++i) {
       if (i < 230) kbs_copy4(s.cinert, 10 + i, critic_obs, 80 + i, ld, n0);
@@ -105,16 +110,11 @@ obs_kernel(const __grid_constant__ kbs_params P, kbs_state_view s, kbs_noise_vie
   }
 
   const bool has_noise = nz.eps_jpos != nullptr;
-  float c[16][4];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) kbs_ld4(command, k, ld, n0, c[k]);
-  float zc[4];
-#pragma unroll
-  for (int l = 0; l < 4; ++l) zc[l] = zero_cmd(c[0][l], c[1][l], c[2][l]) ? 1.0f : 0.0f;
 
   // joints: slots 0-19 / 20-39
-#pragma unroll 4
-  for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+  if (sec < 2) {
+#pragma unroll 5
+  for (int j = sec * 10; j < sec * 10 + 10; ++j) {
     float q[4], qd[4], jb[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0}, e2[4] = {0, 0, 0, 0};
     kbs_ld4(s.qpos, 7 + j, ld, n0, q);
     kbs_ld4(s.qvel, 6 + j, ld, n0, qd);
@@ -135,9 +135,11 @@ obs_kernel(const __grid_constant__ kbs_params P, kbs_state_view s, kbs_noise_vie
     if (actor_obs) { kbs_st4(actor_obs, j, ld, n0, a0); kbs_st4(actor_obs, 20 + j, ld, n0, a1); }
     if (critic_obs) { kbs_st4(critic_obs, j, ld, n0, c0); kbs_st4(critic_obs, 20 + j, ld, n0, c1); }
   }
+  return;
+  }
 
   // IMU: projected gravity (clean + lagged/biased/noisy twin) and gyro
-  {
+  if (sec == 2) {
     float iq[4][4], gy[3][4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) kbs_ld4(s.sensordata, P.sd_imu_quat + k, ld, n0, iq[k]);
@@ -202,6 +204,13 @@ obs_kernel(const __grid_constant__ kbs_params P, kbs_state_view s, kbs_noise_vie
   }
 
   // zero_cmd flag + command: slots 48, 49-64
+  if (sec == 2) {
+  float c[16][4];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) kbs_ld4(command, k, ld, n0, c[k]);
+  float zc[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) zc[l] = zero_cmd(c[0][l], c[1][l], c[2][l]) ? 1.0f : 0.0f;
   if (actor_obs) {
     kbs_st4(actor_obs, 48, ld, n0, zc);
 #pragma unroll
@@ -211,6 +220,8 @@ obs_kernel(const __grid_constant__ kbs_params P, kbs_state_view s, kbs_noise_vie
     kbs_st4(critic_obs, 48, ld, n0, zc);
 #pragma unroll
     for (int k = 0; k < 16; ++k) kbs_st4(critic_obs, 49 + k, ld, n0, c[k]);
+  }
+  return;
   }
 
   if (computed || critic_obs) {
@@ -808,11 +819,18 @@ __device__ __forceinline__ float quat_dot(const float (&a)[4], const float (&b)[
   return ((a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]) + a[3] * b[3];
 }
 
-__global__ void __launch_bounds__(kThreads)
+// One env-step per thread: the ~10 quaternion <-> euler conversions per env-step (IEEE atan2f / asinf / sincosf, no
+// fast-math) make this kernel issue-bound, so it wants every warp slot of the SM filled (4 envs per thread left 21 warps
+// per SM resident and 217 us per 4 096 x 100 launch; rows are still read as full 128-byte lines per warp).
+__device__ __forceinline__ float ld1(const float* __restrict__ base, int64_t row, int64_t ld, int64_t e) {
+  return __ldcs(base + row * ld + e);
+}
+
+__global__ void __launch_bounds__(kThreads, 6)
 reward_terms_kernel(const __grid_constant__ kbs_params P, const kbs_traj_view tr, const uint8_t* __restrict__ is_rot,
                     float* __restrict__ total, float* __restrict__ comp, uint8_t* __restrict__ flags, int64_t n) {
-  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
-  if (n0 >= n) return;
+  const int64_t e0 = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  if (e0 >= n) return;
   const int64_t t = blockIdx.y;
   const int64_t ld = tr.state.ld;
   const float* xquat = tr.state.xquat + t * 4 * KBS_NBODY * ld;
@@ -822,161 +840,135 @@ reward_terms_kernel(const __grid_constant__ kbs_params P, const kbs_traj_view tr
   const float* sd = tr.state.sensordata + t * KBS_NSENSORDATA * ld;
   const float* cmdp = tr.command + t * KBS_NUM_COMMANDS * ld;
   const float* ctrl = tr.ctrl + t * KBS_NUM_JOINTS * ld;
-  float* comp_t = comp ? comp + t * KBS_NUM_REWARDS * ld : nullptr;
 
-  float c[16][4];
+  // every load of the thread is issued before the first trig call: ~70 independent 4-byte loads in flight
+  float c[16], bq[4], fq[2][4], v[6], pv[6], u[KBS_NUM_JOINTS], qa[10];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) kbs_ld4(cmdp, k, ld, n0, c[k]);
-  float bq[4][4], lq[4][4], rq[4][4];
+  for (int k = 0; k < 16; ++k) c[k] = ld1(cmdp, k, ld, e0);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    kbs_ld4(xquat, 4 * P.body_base + k, ld, n0, bq[k]);
-    kbs_ld4(xquat, 4 * P.body_lfoot + k, ld, n0, lq[k]);
-    kbs_ld4(xquat, 4 * P.body_rfoot + k, ld, n0, rq[k]);
+    bq[k] = ld1(xquat, 4 * P.body_base + k, ld, e0);
+    fq[0][k] = ld1(xquat, 4 * P.body_lfoot + k, ld, e0);
+    fq[1][k] = ld1(xquat, 4 * P.body_rfoot + k, ld, e0);
   }
-  float v[6][4], bz[4], lz[4], rz[4], tl[4], trr[4], cd[4];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) kbs_ld4(qvel, k, ld, n0, v[k]);
-  kbs_ld4(xpos, 3 * P.body_base + 2, ld, n0, bz);
-  kbs_ld4(xpos, 3 * P.body_lfoot + 2, ld, n0, lz);
-  kbs_ld4(xpos, 3 * P.body_rfoot + 2, ld, n0, rz);
-  kbs_ld4(sd, P.sd_touch_l, ld, n0, tl);
-  kbs_ld4(sd, P.sd_touch_r, ld, n0, trr);
-  kbs_ld4(tr.state.com_distance + t * ld, 0, ld, n0, cd);
-  const uchar4 rot4 = *reinterpret_cast<const uchar4*>(is_rot + n0);
-  const unsigned char rot[4] = {rot4.x, rot4.y, rot4.z, rot4.w};
-
-  float r[KBS_NUM_REWARDS][4];
-  bool zc[4];
-  uchar4 fl;
-  unsigned char* flp = reinterpret_cast<unsigned char*>(&fl);
-
+  for (int k = 0; k < 6; ++k) v[k] = ld1(qvel, k, ld, e0);
+  const float bz = ld1(xpos, 3 * P.body_base + 2, ld, e0);
+  const float lz = ld1(xpos, 3 * P.body_lfoot + 2, ld, e0);
+  const float rz = ld1(xpos, 3 * P.body_rfoot + 2, ld, e0);
+  const float tl = ld1(sd, P.sd_touch_l, ld, e0);
+  const float trr = ld1(sd, P.sd_touch_r, ld, e0);
+  const float cd = __ldcs(tr.state.com_distance + t * ld + e0);
+  const bool rot = is_rot[e0] != 0;
+  bool prev_done = true;  // t = 0: edge pad, zero difference (train.py:487-494)
+  if (t > 0) {
+    prev_done = tr.done[(t - 1) * ld + e0] != 0;
 #pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    zc[l] = zero_cmd(c[0][l], c[1][l], c[2][l]);
-    const float q[4] = {bq[0][l], bq[1][l], bq[2][l], bq[3][l]};
-    float e[3];
-    quat_to_euler(q, P.eps_quat, e);
-    // R1 linvel train.py:274-292
-    {
-      float qz[4], g[3];
-      euler_to_quat(0.0f, 0.0f, e[2], qz);
-      const float vc[3] = {c[0][l], c[1][l], 0.0f};
-      rotate_vec(vc, qz, false, P.eps_quat, g);
-      const float dx = v[0][l] - g[0], dy = v[1][l] - g[1];
-      const float verr = sqrtf(dx * dx + dy * dy);
-      const float err = zc[l] ? verr : verr * verr;
-      r[0][l] = expf(-err / P.linvel_es);
-    }
-    // R2 angvel train.py:301-306
-    r[1][l] = expf(-fabsf(v[5][l] - c[2][l]) / P.angvel_es);
-    // R3 roll_pitch train.py:316-334
-    {
-      float qxy[4], qc[4];
-      euler_to_quat(e[0], e[1], 0.0f, qxy);
-      euler_to_quat(c[4][l], c[5][l], 0.0f, qc);
-      const float d = quat_dot(qc, qxy);
-      const float qerr = 1.0f - d * d;
-      r[2][l] = expf(-qerr / (zc[l] ? P.rp_es_zero : P.rp_es));
-    }
-    // R4 base_height train.py:377-388
-    {
-      const float h = bz[l] - fminf(lz[l] - P.bh_foot_origin, rz[l] - P.bh_foot_origin);
-      r[3][l] = expf(-fabsf(h - (c[3][l] + P.bh_standard)) / P.bh_es);
-    }
-    // contacts train.py:139-140
-    const bool cl = tl[l] > 0.1f, cr = trr[l] > 0.1f;
-    flp[l] = (cl ? 1 : 0) | (cr ? 2 : 0) | (zc[l] ? 4 : 0);
-    // R7 no_contact_p train.py:161-165
-    r[6][l] = zc[l] ? 0.0f : ((cl || cr) ? 0.0f : 1.0f);
-    // R9 feet_orient train.py:418-457
-    {
-      const float yaw = e[2];
-      float tq[2][4], tq0[2][4];
-      euler_to_quat(-kHalfPi, 0.0f, yaw - kPi, tq[0]);
-      euler_to_quat(kHalfPi, 0.0f, yaw - kPi, tq[1]);
-      euler_to_quat(-kHalfPi, 0.0f, 0.0f, tq0[0]);
-      euler_to_quat(kHalfPi, 0.0f, 0.0f, tq0[1]);
-      const float fq[2][4] = {{lq[0][l], lq[1][l], lq[2][l], lq[3][l]}, {rq[0][l], rq[1][l], rq[2][l], rq[3][l]}};
-      float rpy = 0.0f, rp = 0.0f;
+    for (int k = 0; k < 6; ++k) pv[k] = ld1(qvel - KBS_NV * ld, k, ld, e0);
+  } else {
 #pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const float d = quat_dot(tq[f], fq[f]);
-        rpy = rpy + (1.0f - d * d);
-        float fe[3], fq0[4];
-        quat_to_euler(fq[f], P.eps_quat, fe);
-        euler_to_quat(fe[0], fe[1], 0.0f, fq0);
-        const float d0 = quat_dot(tq0[f], fq0);
-        rp = rp + (1.0f - d0 * d0);
-      }
-      r[8][l] = expf(-(rot[l] ? rp : rpy) / P.feet_es);
-    }
-    // R10 com_distance train.py:466-478
-    r[9][l] = (cd[l] >= 0.0f) ? (zc[l] ? expf(-cd[l] / P.com_es) : 0.0f) : 0.0f;
-    r[5][l] = 0.0f;  // single_contact: scan kernel
-    r[7][l] = 0.0f;  // feet_airtime: scan kernel
+    for (int k = 0; k < 6; ++k) pv[k] = 0.0f;
   }
+#pragma unroll
+  for (int j = 0; j < KBS_NUM_JOINTS; ++j) u[j] = ld1(ctrl, j, ld, e0);
+#pragma unroll
+  for (int k = 0; k < 10; ++k) qa[k] = ld1(qpos, 17 + k, ld, e0);
 
+  float r[KBS_NUM_REWARDS];
+  const bool zc = zero_cmd(c[0], c[1], c[2]);
+  // the sums over joints first: their 36 loaded values die before the trig-heavy terms need registers
   // R5 arm_pos train.py:261-265
   {
-    float err[4] = {0, 0, 0, 0};
+    float err = 0.0f;
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
-      float q[4];
-      kbs_ld4(qpos, 17 + k, ld, n0, q);
-#pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        const float d = q[l] - (c[6 + k][l] + P.joint_bias[10 + k]);
-        err[l] = err[l] + d * d;
-      }
+      const float d = qa[k] - (c[6 + k] + P.joint_bias[10 + k]);
+      err = err + d * d;
     }
-#pragma unroll
-    for (int l = 0; l < 4; ++l) r[4][l] = expf(-err[l] / P.arm_es);
+    r[4] = expf(-err / P.arm_es);
   }
-  // R11 base_accel train.py:487-494 (edge pad: t = 0 has zero difference)
+  // R11 base_accel train.py:487-494
   {
-    float err[4] = {0, 0, 0, 0};
-    if (t > 0) {
-      const uchar4 pd4 = *reinterpret_cast<const uchar4*>(tr.done + (t - 1) * ld + n0);
-      const unsigned char pd[4] = {pd4.x, pd4.y, pd4.z, pd4.w};
+    float err = 0.0f;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        float pv[4];
-        kbs_ld4(qvel - KBS_NV * ld, k, ld, n0, pv);
-#pragma unroll
-        for (int l = 0; l < 4; ++l) err[l] = err[l] + fabsf(pd[l] ? 0.0f : (v[k][l] - pv[l]));
-      }
-    }
-#pragma unroll
-    for (int l = 0; l < 4; ++l) r[10][l] = expf(-err[l] / P.acc_es);
+    for (int k = 0; k < 6; ++k) err = err + fabsf(prev_done ? 0.0f : (v[k] - pv[k]));
+    r[10] = expf(-err / P.acc_es);
   }
   // R12 torque train.py:503-506
   {
-    float acc[4] = {0, 0, 0, 0};
-#pragma unroll 5
-    for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
-      float u[4];
-      kbs_ld4(ctrl, j, ld, n0, u);
+    float acc = 0.0f;
 #pragma unroll
-      for (int l = 0; l < 4; ++l) acc[l] = acc[l] + expf(-fabsf(u[l]) / P.torque_es);
-    }
-#pragma unroll
-    for (int l = 0; l < 4; ++l) r[11][l] = zc[l] ? acc[l] / 20.0f : 1.0f;
+    for (int j = 0; j < KBS_NUM_JOINTS; ++j) acc = acc + expf(-fabsf(u[j]) / P.torque_es);
+    r[11] = zc ? acc / 20.0f : 1.0f;
   }
 
-  float tot[4];
-#pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    float s = 0.0f;
-#pragma unroll
-    for (int k = 0; k < KBS_NUM_REWARDS; ++k) s = s + P.reward_scale[k] * r[k][l];
-    tot[l] = s;
+  float e[3];
+  quat_to_euler(bq, P.eps_quat, e);
+  // R1 linvel train.py:274-292
+  {
+    float qz[4], g[3];
+    euler_to_quat(0.0f, 0.0f, e[2], qz);
+    const float vc[3] = {c[0], c[1], 0.0f};
+    rotate_vec(vc, qz, false, P.eps_quat, g);
+    const float dx = v[0] - g[0], dy = v[1] - g[1];
+    const float verr = sqrtf(dx * dx + dy * dy);
+    const float err = zc ? verr : verr * verr;
+    r[0] = expf(-err / P.linvel_es);
   }
-  kbs_st4(total + t * ld, 0, ld, n0, tot);
-  *reinterpret_cast<uchar4*>(flags + t * ld + n0) = fl;
-  if (comp_t) {
+  // R2 angvel train.py:301-306
+  r[1] = expf(-fabsf(v[5] - c[2]) / P.angvel_es);
+  // R3 roll_pitch train.py:316-334
+  {
+    float qxy[4], qc[4];
+    euler_to_quat(e[0], e[1], 0.0f, qxy);
+    euler_to_quat(c[4], c[5], 0.0f, qc);
+    const float d = quat_dot(qc, qxy);
+    const float qerr = 1.0f - d * d;
+    r[2] = expf(-qerr / (zc ? P.rp_es_zero : P.rp_es));
+  }
+  // R4 base_height train.py:377-388
+  {
+    const float h = bz - fminf(lz - P.bh_foot_origin, rz - P.bh_foot_origin);
+    r[3] = expf(-fabsf(h - (c[3] + P.bh_standard)) / P.bh_es);
+  }
+  // contacts train.py:139-140
+  const bool cl = tl > 0.1f, cr = trr > 0.1f;
+  flags[t * ld + e0] = (cl ? 1 : 0) | (cr ? 2 : 0) | (zc ? 4 : 0);
+  // R7 no_contact_p train.py:161-165
+  r[6] = zc ? 0.0f : ((cl || cr) ? 0.0f : 1.0f);
+  // R9 feet_orient train.py:418-457
+  {
+    const float yaw = e[2];
+    float tq[2][4], tq0[2][4];
+    euler_to_quat(-kHalfPi, 0.0f, yaw - kPi, tq[0]);
+    euler_to_quat(kHalfPi, 0.0f, yaw - kPi, tq[1]);
+    euler_to_quat(-kHalfPi, 0.0f, 0.0f, tq0[0]);
+    euler_to_quat(kHalfPi, 0.0f, 0.0f, tq0[1]);
+    float rpy = 0.0f, rp = 0.0f;
 #pragma unroll
-    for (int k = 0; k < KBS_NUM_REWARDS; ++k) kbs_st4(comp_t, k, ld, n0, r[k]);
+    for (int f = 0; f < 2; ++f) {
+      const float d = quat_dot(tq[f], fq[f]);
+      rpy = rpy + (1.0f - d * d);
+      float fe[3], fq0[4];
+      quat_to_euler(fq[f], P.eps_quat, fe);
+      euler_to_quat(fe[0], fe[1], 0.0f, fq0);
+      const float d0 = quat_dot(tq0[f], fq0);
+      rp = rp + (1.0f - d0 * d0);
+    }
+    r[8] = expf(-(rot ? rp : rpy) / P.feet_es);
+  }
+  // R10 com_distance train.py:466-478
+  r[9] = (cd >= 0.0f) ? (zc ? expf(-cd / P.com_es) : 0.0f) : 0.0f;
+  r[5] = 0.0f;  // single_contact: scan kernel
+  r[7] = 0.0f;  // feet_airtime: scan kernel
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < KBS_NUM_REWARDS; ++k) s = s + P.reward_scale[k] * r[k];
+  __stcs(total + t * ld + e0, s);
+  if (comp) {
+    float* comp_t = comp + t * KBS_NUM_REWARDS * ld;
+#pragma unroll
+    for (int k = 0; k < KBS_NUM_REWARDS; ++k) __stcs(comp_t + k * ld + e0, r[k]);
   }
 }
 
@@ -1151,39 +1143,44 @@ command_scan_kernel(const __grid_constant__ kbs_params P, float* __restrict__ co
   const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
   if (e >= n) return;
   // thread = (env, command row k = blockIdx.y): 16x the threads of a one-thread-per-env walk (4 096 envs alone fill only
-  // 32 SMs and the kernel is pure latency); the switch decisions are re-derived per row (two loads per step) and fetched
-  // 10 steps at a time, the row's new value is computed only on a switch.
+  // 32 SMs and the kernel is pure latency).  The command after step t is new(t*) at the LAST switch t* <= t (the new value
+  // does not depend on the previous one, train.py:768-785), so a 32-step chunk is: 64 independent loads -> a switch bit
+  // mask -> the (rare: p ~ 0.014 per step) switch values, loaded only at the set bits -> 32 coalesced stores.
   const int k = blockIdx.y;
   float c = command[k * ld + e];
-  constexpr int kB = 10;
-  for (int64_t t0 = 0; t0 < T; t0 += kB) {
-    bool swv[kB];
+  for (int64_t t0 = 0; t0 < T; t0 += 32) {
+    unsigned mask = 0;
 #pragma unroll
-    for (int i = 0; i < kB; ++i) {
-      const int64_t t = t0 + i;
-      swv[i] = t < T && ((done[t * ld + e] != 0) || (u_switch[t * ld + e] < P.switch_prob));
+    for (int i = 0; i < 32; ++i) {
+      const int64_t t = t0 + i < T ? t0 + i : T - 1;
+      const bool sw = (done[t * ld + e] != 0) || (u_switch[t * ld + e] < P.switch_prob);
+      mask |= (sw && t0 + i < T) ? (1u << i) : 0u;
     }
-#pragma unroll
-    for (int i = 0; i < kB; ++i) {
-      const int64_t t = t0 + i;
-      if (t >= T) break;
-      if (swv[i]) {
-        const int m = mode[t * ld + e];
-        if (k < 6) {
-          const float v = P.cmd_lo[k] + u6[(t * 6 + k) * ld + e] * (P.cmd_hi[k] - P.cmd_lo[k]);
-          bool on;
-          if (k == 0) on = (m == 0) || (m == 3);
-          else if (k == 1) on = (m == 1) || (m == 3);
-          else if (k == 2) on = (m == 2) || (m == 3);
-          else on = (m == 4);
-          c = on ? v : 0.0f;
-        } else {
-          const float u = u_arms[(t * 10 + (k - 6)) * ld + e];
-          const float arm = (P.arm_lo[k - 6] + u * (P.arm_hi[k - 6] - P.arm_lo[k - 6])) * ((u < 0.5f) ? 1.0f : 0.0f);
-          c = (m == 3 || m == 4) ? arm : 0.0f;
-        }
+    int i = 0;
+    while (true) {
+      // steps before the next switch keep c
+      const int nxt = mask ? __ffs(mask) - 1 : 32;
+      for (; i < nxt; ++i) {
+        if (t0 + i >= T) break;
+        command[((t0 + i + 1) * KBS_NUM_COMMANDS + k) * ld + e] = c;
       }
-      command[((t + 1) * KBS_NUM_COMMANDS + k) * ld + e] = c;
+      if (nxt == 32 || t0 + nxt >= T) break;
+      mask &= mask - 1;
+      const int64_t t = t0 + nxt;
+      const int m = mode[t * ld + e];
+      if (k < 6) {
+        const float v = P.cmd_lo[k] + u6[(t * 6 + k) * ld + e] * (P.cmd_hi[k] - P.cmd_lo[k]);
+        bool on;
+        if (k == 0) on = (m == 0) || (m == 3);
+        else if (k == 1) on = (m == 1) || (m == 3);
+        else if (k == 2) on = (m == 2) || (m == 3);
+        else on = (m == 4);
+        c = on ? v : 0.0f;
+      } else {
+        const float u = u_arms[(t * 10 + (k - 6)) * ld + e];
+        const float arm = (P.arm_lo[k - 6] + u * (P.arm_hi[k - 6] - P.arm_lo[k - 6])) * ((u < 0.5f) ? 1.0f : 0.0f);
+        c = (m == 3 || m == 4) ? arm : 0.0f;
+      }
     }
   }
 }
@@ -1243,7 +1240,7 @@ int kbs_launch_observations(kbs_handle* h, const kbs_state_view& s, const kbs_no
   if (nz) z = *nz;
   if (ep) e = *ep;
   // skip_dump: the caller reads cinert / cvel straight from the state (critic rows 80..447 stay unwritten)
-  dim3 grid(groups4(n), (critic_obs && !skip_dump) ? 1 + 368 / kCopyRowsPerSection : 1, unsigned(T));
+  dim3 grid(groups4(n), (critic_obs && !skip_dump) ? kObsSections + 368 / kCopyRowsPerSection : kObsSections, unsigned(T));
   KBS_LAUNCH(h, KBS_K_OBS, st, (obs_kernel<<<grid, kThreads, 0, st>>>(h->p, s, z, e, command, pg_carry, pg_reset, pg_lagged,
                                                                       computed, actor_obs, critic_obs, n)));
   KBS_LAUNCH_CHECK();
@@ -1368,7 +1365,7 @@ int kbs_launch_rewards(kbs_handle* h, const kbs_traj_view& tr, const kbs_reward_
   uint8_t* is_rot = reinterpret_cast<uint8_t*>(h->scratch);
   uint8_t* flags = is_rot + ld;
   KBS_LAUNCH(h, KBS_K_REWARD_ROT, st, (reward_rot_kernel<<<groups4(n), kThreads, 0, st>>>(tr.command, is_rot, T, ld, n)));
-  dim3 grid(groups4(n), unsigned(T));
+  dim3 grid(unsigned((n + kThreads - 1) / kThreads), unsigned(T));
   KBS_LAUNCH(h, KBS_K_REWARD_TERMS, st,
              (reward_terms_kernel<<<grid, kThreads, 0, st>>>(h->p, tr, is_rot, total, components, flags, n)));
   KBS_LAUNCH(h, KBS_K_REWARD_SCAN, st,
@@ -1400,8 +1397,9 @@ int kbs_launch_policy_pack(kbs_handle* h, const float* ja, const float* jv, cons
              (policy_pack_obs_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(
                  h->p, ja, jv, pg, gyro, cmd, carry_in, cw, obs_soa, lpf_soa, ld, n)));
   const int64_t tot = n * int64_t(d2) * H;
-  KBS_LAUNCH(h, KBS_K_POLICY_IO, st,
-             (policy_carry_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(carry_in, carry_aos, d2, H, cw, n, true)));
+  if (carry_aos)   // nullptr: the caller converts the flat carry records itself (tensor-core path)
+    KBS_LAUNCH(h, KBS_K_POLICY_IO, st,
+               (policy_carry_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(carry_in, carry_aos, d2, H, cw, n, true)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -1410,8 +1408,9 @@ int kbs_launch_policy_unpack(kbs_handle* h, const float* carry_aos, const float*
                              float* carry_out, float* action_out, int64_t ld, int64_t n, cudaStream_t st) {
   const int H = h->p.hidden_size, d2 = 2 * h->p.depth, cw = d2 * H + 20;
   const int64_t tot = n * int64_t(d2) * H;
-  KBS_LAUNCH(h, KBS_K_POLICY_IO, st,
-             (policy_carry_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(carry_aos, carry_out, d2, H, cw, n, false)));
+  if (carry_aos)
+    KBS_LAUNCH(h, KBS_K_POLICY_IO, st,
+               (policy_carry_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(carry_aos, carry_out, d2, H, cw, n, false)));
   KBS_LAUNCH(h, KBS_K_POLICY_IO, st,
              (policy_unpack_kernel<<<unsigned((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(
                  lpf_soa, mean_soa, carry_out, cw, action_out, ld, n)));

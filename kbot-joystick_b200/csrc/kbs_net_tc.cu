@@ -1322,6 +1322,45 @@ pack_rows_sb_kernel(const float* __restrict__ src, int64_t ld, char* __restrict_
   sb_store4<kPanelRows, KIND>(sb, row, kc * 4, K / kbs_block_k(KIND), x);
 }
 
+// All ABI carry <-> kernel layout conversions of one rollout call as ONE launch (blockIdx.y = job): the 8 + 8 separate
+// fb_convert / pack_rows launches around the persistent kernel were pure launch latency (~6 us each, 4 MB moved).
+//   mode 0: row-major [n][H] -> SB (h, A operand);  mode 1: row-major -> FB (c);  mode 2: FB -> row-major.
+struct CarryJobs {
+  float* rm[8];
+  void* blk[8];
+  int mode[8];
+  int64_t ld_rm;     // row stride of the row-major side (H for the ABI carries, the record width for flat carries)
+};
+template <int KIND>
+__global__ void __launch_bounds__(256)
+carry_convert_kernel(const __grid_constant__ CarryJobs J, int64_t n, int64_t n_pad, int H) {
+  const int64_t ldr = J.ld_rm;
+  const int j = blockIdx.y;
+  const int hq = H / 4;
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= n_pad * hq) return;
+  const int64_t panel = idx / (int64_t(kPanelRows) * hq);
+  const int rem = int(idx - panel * int64_t(kPanelRows) * hq);
+  const int kc = rem / kPanelRows, r = rem % kPanelRows;
+  const int64_t row = panel * kPanelRows + r;
+  float* rm = J.rm[j];
+  const int mode = J.mode[j];
+  if (mode == 2) {
+    if (row < n)
+      *reinterpret_cast<float4*>(rm + row * ldr + kc * 4) =
+          *reinterpret_cast<const float4*>(static_cast<const float*>(J.blk[j]) + fb_offset(row, kc * 4, H));
+    return;
+  }
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < n) v = *reinterpret_cast<const float4*>(rm + row * ldr + kc * 4);
+  if (mode == 1) {
+    *reinterpret_cast<float4*>(static_cast<float*>(J.blk[j]) + fb_offset(row, kc * 4, H)) = v;
+  } else {
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    sb_store4<kPanelRows, KIND>(static_cast<char*>(J.blk[j]), row, kc * 4, H / kbs_block_k(KIND), x);
+  }
+}
+
 // env-major SoA observations [T][F][ld] -> SB rows [T * n_pad][Kp] (features beyond F and envs beyond n zero-filled).
 // thread = (t, panel, 8-feature group, row): reads 8 SoA rows at one env (coalesced over envs) and writes one full
 // 16-byte chunk per plane (FP16 kind; two per plane for TF32): 512 contiguous bytes per warp and store instruction.
@@ -1515,6 +1554,16 @@ size_t kbs_tc_scratch_floats(const kbs_handle* h, int64_t n) {
 static int fb_convert(kbs_handle* h, float* rm, float* fb, int64_t n, int64_t np, int H, int to_fb, cudaStream_t st) {
   const int64_t tot = np * (H / 4);
   KBS_LAUNCH(h, KBS_K_PACK, st, (fb_convert_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(rm, fb, n, np, H, to_fb)));
+  return KBS_OK;
+}
+
+static int carry_convert(kbs_handle* h, const CarryJobs& J, int jobs, int64_t n, int64_t np, int H, cudaStream_t st) {
+  const int64_t tot = np * (H / 4);
+  const dim3 grid(unsigned((tot + 255) / 256), unsigned(jobs));
+  if (tc_kind(h) == KBS_KIND_TF32)
+    KBS_LAUNCH(h, KBS_K_PACK, st, (carry_convert_kernel<KBS_KIND_TF32><<<grid, 256, 0, st>>>(J, n, np, H)));
+  else
+    KBS_LAUNCH(h, KBS_K_PACK, st, (carry_convert_kernel<KBS_KIND_F16><<<grid, 256, 0, st>>>(J, n, np, H)));
   return KBS_OK;
 }
 
@@ -1759,6 +1808,13 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
   return KBS_OK;
 }
 
+bool kbs_tc_persistent_available(const kbs_handle* h, int64_t n, int64_t T, int nets) {
+  const int H = h->p.hidden_size, depth = h->p.depth;
+  if (!persist_shape_ok(h)) return false;
+  const int64_t panels = pad_rows(n) / kPanelRows, tiles = H / kUnitsPerTileP;
+  return (T + depth) * int64_t(nets) * panels * (depth * tiles + 1) < (int64_t(1) << 31);
+}
+
 int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStream_t st) {
   const int H = h->p.hidden_size, depth = h->p.depth, kind = tc_kind(h);
   const int nets = r.with_critic ? 2 : 1;
@@ -1781,16 +1837,31 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     h2rm[k] = reinterpret_cast<float*>(xmid[k] + 2 * depth * sbb);   // [2 parity] x n*H: top-layer output (per-step path)
     fb[k] = h2rm[k] + 2 * size_t(n) * H;             // [depth][c, h] x np*H, FB layout
     flags[k] = reinterpret_cast<unsigned int*>(fb[k] + 2 * size_t(depth) * fbf);
-    for (int l = 0; l < depth; ++l) {                // ABI carry: h -> SB (parity 0), c -> FB
-      pack_rows(h, r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H, H, hsb[k] + sbb * (2 * l), n, np, H, st);
-      fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 1, st);
-    }
   }
   const char* legacy_env = getenv("KBS_TC_PER_STEP");          // A/B and cross-check against the per-step launches
   const int legacy = legacy_env ? atoi(legacy_env) : 0;
+  const bool persistent = !legacy && kbs_tc_persistent_available(h, n, r.T, nets);
+  if (r.carry_ld && (!persistent || nets * depth * 2 > 8)) return KBS_E_STATE;   // flat carries: persistent kernel only
+  const size_t slot_f = r.carry_ld ? size_t(H) : size_t(n) * H;                  // floats between carry slots
+  if (nets * depth * 2 <= 8) {                       // ABI carry: h -> SB (parity 0), c -> FB; one launch
+    CarryJobs J{};
+    J.ld_rm = r.carry_ld ? r.carry_ld : H;
+    int j = 0;
+    for (int k = 0; k < nets; ++k)
+      for (int l = 0; l < depth; ++l) {
+        J.rm[j] = r.carry[k] + (size_t(l) * 2 + 0) * slot_f; J.blk[j] = hsb[k] + sbb * (2 * l); J.mode[j++] = 0;
+        J.rm[j] = r.carry[k] + (size_t(l) * 2 + 1) * slot_f; J.blk[j] = fb[k] + fbf * (2 * l); J.mode[j++] = 1;
+      }
+    carry_convert(h, J, j, n, np, H, st);
+  } else {
+    for (int k = 0; k < nets; ++k)
+      for (int l = 0; l < depth; ++l) {
+        pack_rows(h, r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H, H, hsb[k] + sbb * (2 * l), n, np, H, st);
+        fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 1, st);
+      }
+  }
   const int panels = int(np / kPanelRows), tiles = H / kUnitsPerTileP;
-  const int64_t n_items = (r.T + depth) * int64_t(nets) * panels * (depth * tiles + 1);
-  if (!legacy && persist_shape_ok(h) && n_items < (int64_t(1) << 31)) {
+  if (persistent) {
     // ---- persistent recurrence: one cooperative launch for all T steps (rollout_persist_kernel) ----
     if (!h->persist_status) KBS_CUDA_TRY(cudaMalloc(&h->persist_status, 256));
     PArgs a{};
@@ -1834,11 +1905,25 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     else
       KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<KBS_KIND_F16>, h->p, a)));
     KBS_CUDA_TRY(le);
-    for (int k = 0; k < nets; ++k)
-      for (int l = 0; l < depth; ++l) {                // FB state -> ABI carry
-        fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 0, st);
-        fb_convert(h, r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H, fb[k] + fbf * (2 * l + 1), n, np, H, 0, st);
+    if (nets * depth * 2 <= 8) {                       // FB state -> ABI carry; one launch
+      CarryJobs J{};
+      J.ld_rm = r.carry_ld ? r.carry_ld : H;
+      int j = 0;
+      for (int k = 0; k < nets; ++k) {
+        float* dst = (r.carry_ld && r.carry_out[k]) ? r.carry_out[k] : r.carry[k];
+        for (int l = 0; l < depth; ++l) {
+          J.rm[j] = dst + (size_t(l) * 2 + 1) * slot_f; J.blk[j] = fb[k] + fbf * (2 * l); J.mode[j++] = 2;
+          J.rm[j] = dst + (size_t(l) * 2 + 0) * slot_f; J.blk[j] = fb[k] + fbf * (2 * l + 1); J.mode[j++] = 2;
+        }
       }
+      carry_convert(h, J, j, n, np, H, st);
+    } else {
+      for (int k = 0; k < nets; ++k)
+        for (int l = 0; l < depth; ++l) {
+          fb_convert(h, r.carry[k] + (size_t(l) * 2 + 1) * size_t(n) * H, fb[k] + fbf * (2 * l), n, np, H, 0, st);
+          fb_convert(h, r.carry[k] + (size_t(l) * 2 + 0) * size_t(n) * H, fb[k] + fbf * (2 * l + 1), n, np, H, 0, st);
+        }
+    }
     KBS_LAUNCH_CHECK();
     return KBS_OK;
   }

@@ -407,7 +407,7 @@ def test_gae_linearity_full_size(eng, dev):
 
 
 @pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("N", [1, 33, 1024])
+@pytest.mark.parametrize("N", [1, 33, 1024, 4100])
 def test_policy_step(dev, path, N):
     """convert.py step_fn: AoS inputs + flat carry -> (mode, carry)."""
     e, wa, _ = Hn.make_engine(gemm_path=path, device=dev)
