@@ -1331,33 +1331,66 @@ struct CarryJobs {
   int mode[8];
   int64_t ld_rm;     // row stride of the row-major side (H for the ABI carries, the record width for flat carries)
 };
+// Both sides coalesced: a block moves a 32-row x 32-group tile (group = 8 consecutive units = 32 B) through shared
+// memory -- on the row-major side a warp touches 1 KB of ONE row (flat carry records are 4 KB apart: one row per lane
+// fetched half-used sectors at 3.1 TB/s), on the blocked side 512 B of one 16-byte chunk column (lane = row).
 template <int KIND>
 __global__ void __launch_bounds__(256)
 carry_convert_kernel(const __grid_constant__ CarryJobs J, int64_t n, int64_t n_pad, int H) {
-  const int64_t ldr = J.ld_rm;
+  __shared__ float4 tile[2][32][33];
   const int j = blockIdx.y;
-  const int hq = H / 4;
-  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  if (idx >= n_pad * hq) return;
-  const int64_t panel = idx / (int64_t(kPanelRows) * hq);
-  const int rem = int(idx - panel * int64_t(kPanelRows) * hq);
-  const int kc = rem / kPanelRows, r = rem % kPanelRows;
-  const int64_t row = panel * kPanelRows + r;
+  const int kgs = H / 8, kt = (kgs + 31) / 32;
+  const int64_t rb = blockIdx.x / kt;
+  const int kg0 = int(blockIdx.x - rb * kt) * 32;
+  const int64_t row0 = rb * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* rm = J.rm[j];
   const int mode = J.mode[j];
-  if (mode == 2) {
-    if (row < n)
-      *reinterpret_cast<float4*>(rm + row * ldr + kc * 4) =
-          *reinterpret_cast<const float4*>(static_cast<const float*>(J.blk[j]) + fb_offset(row, kc * 4, H));
-    return;
-  }
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row < n) v = *reinterpret_cast<const float4*>(rm + row * ldr + kc * 4);
-  if (mode == 1) {
-    *reinterpret_cast<float4*>(static_cast<float*>(J.blk[j]) + fb_offset(row, kc * 4, H)) = v;
+  const int64_t ldr = J.ld_rm;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mode != 2) {
+    for (int rr = warp; rr < 32; rr += 8) {
+      const int64_t row = row0 + rr;
+      const int kg = kg0 + lane;
+      float4 a = z, b = z;
+      if (row < n && kg < kgs) {
+        const float4* p = reinterpret_cast<const float4*>(rm + row * ldr + kg * 8);
+        a = __ldcs(p); b = __ldcs(p + 1);
+      }
+      tile[0][rr][lane] = a; tile[1][rr][lane] = b;
+    }
+    __syncthreads();
+    const int64_t row = row0 + lane;                  // < n_pad: rows >= n carry zeros
+    for (int kk = warp; kk < 32 && kg0 + kk < kgs; kk += 8) {
+      const int kg = kg0 + kk;
+      const float4 a = tile[0][lane][kk], b = tile[1][lane][kk];
+      if (mode == 1) {
+        float* fb = static_cast<float*>(J.blk[j]);
+        *reinterpret_cast<float4*>(fb + fb_offset(row, kg * 8, H)) = a;
+        *reinterpret_cast<float4*>(fb + fb_offset(row, kg * 8 + 4, H)) = b;
+      } else {
+        const float x0[4] = {a.x, a.y, a.z, a.w}, x1[4] = {b.x, b.y, b.z, b.w};
+        sb_store_split8<kPanelRows, KIND>(J.blk[j], row, kg * 8, H / kbs_block_k(KIND), sb_split4<KIND>(x0), sb_split4<KIND>(x1),
+                                          false);
+      }
+    }
   } else {
-    const float x[4] = {v.x, v.y, v.z, v.w};
-    sb_store4<kPanelRows, KIND>(static_cast<char*>(J.blk[j]), row, kc * 4, H / kbs_block_k(KIND), x);
+    const float* fb = static_cast<const float*>(J.blk[j]);
+    const int64_t row = row0 + lane;
+    for (int kk = warp; kk < 32 && kg0 + kk < kgs; kk += 8) {
+      const int kg = kg0 + kk;
+      tile[0][lane][kk] = *reinterpret_cast<const float4*>(fb + fb_offset(row, kg * 8, H));
+      tile[1][lane][kk] = *reinterpret_cast<const float4*>(fb + fb_offset(row, kg * 8 + 4, H));
+    }
+    __syncthreads();
+    for (int rr = warp; rr < 32; rr += 8) {
+      const int64_t r2 = row0 + rr;
+      const int kg = kg0 + lane;
+      if (r2 < n && kg < kgs) {
+        float4* p = reinterpret_cast<float4*>(rm + r2 * ldr + kg * 8);
+        __stcs(p, tile[0][rr][lane]); __stcs(p + 1, tile[1][rr][lane]);
+      }
+    }
   }
 }
 
@@ -1558,8 +1591,8 @@ static int fb_convert(kbs_handle* h, float* rm, float* fb, int64_t n, int64_t np
 }
 
 static int carry_convert(kbs_handle* h, const CarryJobs& J, int jobs, int64_t n, int64_t np, int H, cudaStream_t st) {
-  const int64_t tot = np * (H / 4);
-  const dim3 grid(unsigned((tot + 255) / 256), unsigned(jobs));
+  const int kt = (H / 8 + 31) / 32;
+  const dim3 grid(unsigned((np / 32) * kt), unsigned(jobs));
   if (tc_kind(h) == KBS_KIND_TF32)
     KBS_LAUNCH(h, KBS_K_PACK, st, (carry_convert_kernel<KBS_KIND_TF32><<<grid, 256, 0, st>>>(J, n, np, H)));
   else
@@ -1841,9 +1874,9 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
   const char* legacy_env = getenv("KBS_TC_PER_STEP");          // A/B and cross-check against the per-step launches
   const int legacy = legacy_env ? atoi(legacy_env) : 0;
   const bool persistent = !legacy && kbs_tc_persistent_available(h, n, r.T, nets);
-  if (r.carry_ld && (!persistent || nets * depth * 2 > 8)) return KBS_E_STATE;   // flat carries: persistent kernel only
+  if (r.carry_ld && (!persistent || nets * depth * 2 > 8 || H % 8)) return KBS_E_STATE;   // flat carries: persistent kernel only
   const size_t slot_f = r.carry_ld ? size_t(H) : size_t(n) * H;                  // floats between carry slots
-  if (nets * depth * 2 <= 8) {                       // ABI carry: h -> SB (parity 0), c -> FB; one launch
+  if (nets * depth * 2 <= 8 && H % 8 == 0) {                       // ABI carry: h -> SB (parity 0), c -> FB; one launch
     CarryJobs J{};
     J.ld_rm = r.carry_ld ? r.carry_ld : H;
     int j = 0;
@@ -1905,7 +1938,7 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     else
       KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<KBS_KIND_F16>, h->p, a)));
     KBS_CUDA_TRY(le);
-    if (nets * depth * 2 <= 8) {                       // FB state -> ABI carry; one launch
+    if (nets * depth * 2 <= 8 && H % 8 == 0) {                       // FB state -> ABI carry; one launch
       CarryJobs J{};
       J.ld_rm = r.carry_ld ? r.carry_ld : H;
       int j = 0;

@@ -76,8 +76,16 @@ def policy_sweep():
             _, carry[0] = eng.policy_step(ja, jv, pg, gy, cmd, carry[0])
 
         ms = timed(step)
-        print(json.dumps({"config": "configs[4] actor-only policy step (convert.py step_fn)", "n_envs": N, "ms_per_step": ms,
-                          "env_steps_per_s": N / (ms * 1e-3), "n_gpus": 1}), flush=True)
+        rec = {"config": "configs[4] actor-only policy step (convert.py step_fn)", "n_envs": N, "ms_per_step": ms,
+               "env_steps_per_s": N / (ms * 1e-3), "n_gpus": 1}
+        if p in (12, 20):   # per-kernel CUDA-event pass (events around every launch of one step)
+            eng.profile(True)
+            step()
+            torch.cuda.synchronize()
+            prof = eng.profile_read()
+            eng.profile(False)
+            rec["kernel_breakdown_ms"] = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in prof.items() if k != "_overflow"}
+        print(json.dumps(rec), flush=True)
 
 
 if __name__ == "__main__":
