@@ -123,12 +123,14 @@ int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStr
   float* osb_c = critic ? osb_a + osb_a_f : nullptr;
 
   if ((rc = kbs_launch_terminate(h, io->state, io->term_codes, io->done, io->success, nullptr, n, st, T))) return rc;
-  if ((rc = kbs_launch_command_scan(h, io->command, io->u_switch, io->cmd_mode, io->cmd_u6, io->cmd_u_arms, io->done, T,
-                                    ld, n, st)))
+  if (lagged) {
+    if ((rc = kbs_launch_phase_a_scans(h, io->command, io->u_switch, io->cmd_mode, io->cmd_u6, io->cmd_u_arms, io->done,
+                                       io->state.sensordata, io->episode.pg_lag, io->pg_carry, lagged, T, ld, n, st)))
+      return rc;
+  } else if ((rc = kbs_launch_command_scan(h, io->command, io->u_switch, io->cmd_mode, io->cmd_u6, io->cmd_u_arms, io->done,
+                                           T, ld, n, st))) {
     return rc;
-  if (lagged &&
-      (rc = kbs_launch_pg_scan(h, io->state.sensordata, io->episode.pg_lag, io->done, io->pg_carry, lagged, T, ld, n, st)))
-    return rc;
+  }
   if ((rc = kbs_side_stream_init(h))) return rc;
   const bool overlap = chunks_cfg > 1;
   cudaStream_t aux = overlap ? h->aux_stream : st;

@@ -804,11 +804,18 @@ reward_rot_kernel(const float* __restrict__ command, uint8_t* __restrict__ is_ro
   const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
   if (n0 >= n) return;
   float acc[4] = {0, 0, 0, 0};
-  for (int64_t t = 0; t < T; ++t) {
-    float wz[4];
-    kbs_ld4(command + t * KBS_NUM_COMMANDS * ld, 2, ld, n0, wz);
+  constexpr int kB = 16;   // 16 independent row loads in flight, summed in time order (the reference's reduction order)
+  for (int64_t t0 = 0; t0 < T; t0 += kB) {
+    float wz[kB][4];
 #pragma unroll
-    for (int l = 0; l < 4; ++l) acc[l] = acc[l] + wz[l] * wz[l];
+    for (int i = 0; i < kB; ++i) kbs_ld4(command + (t0 + i < T ? t0 + i : T - 1) * KBS_NUM_COMMANDS * ld, 2, ld, n0, wz[i]);
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+      if (t0 + i < T) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) acc[l] = acc[l] + wz[i][l] * wz[i][l];
+      }
+    }
   }
   uchar4 o;
   o.x = sqrtf(acc[0]) > 1e-3f; o.y = sqrtf(acc[1]) > 1e-3f; o.z = sqrtf(acc[2]) > 1e-3f; o.w = sqrtf(acc[3]) > 1e-3f;
@@ -983,9 +990,20 @@ reward_scan_kernel(const __grid_constant__ kbs_params P, const uint8_t* __restri
   float t_sc = carry.t_single[e];
   float air0 = carry.airtime[e], air1 = carry.airtime[ld + e];
   bool pc0 = carry.prev_contact[e] != 0, pc1 = carry.prev_contact[ld + e] != 0;
-  for (int64_t t = 0; t < T; ++t) {
-    const unsigned f = flags[t * ld + e];
-    const bool dn = done[t * ld + e] != 0;
+  constexpr int kB = 16;   // the inputs of step t do not depend on the recurrence: 16 steps of loads in flight
+  for (int64_t t0 = 0; t0 < T; t0 += kB) {
+  unsigned fv[kB]; bool dv[kB]; float tv[kB];
+#pragma unroll
+  for (int i = 0; i < kB; ++i) {
+    const int64_t tt = t0 + i < T ? t0 + i : T - 1;
+    fv[i] = flags[tt * ld + e]; dv[i] = done[tt * ld + e] != 0; tv[i] = total[tt * ld + e];
+  }
+#pragma unroll
+  for (int i = 0; i < kB; ++i) {
+    const int64_t t = t0 + i;
+    if (t >= T) break;
+    const unsigned f = fv[i];
+    const bool dn = dv[i];
     const bool cl = f & 1, cr = (f & 2) != 0, zc = (f & 4) != 0;
     const bool single = cl != cr;
     t_sc = single ? 0.0f : t_sc + P.ctrl_dt;
@@ -997,11 +1015,12 @@ reward_scan_kernel(const __grid_constant__ kbs_params P, const uint8_t* __restri
     air0 = (cl || dn) ? 0.0f : air0 + P.ctrl_dt;
     air1 = (cr || dn) ? 0.0f : air1 + P.ctrl_dt;
     pc0 = cl; pc1 = cr;
-    total[t * ld + e] = total[t * ld + e] + (P.reward_scale[5] * r6 + P.reward_scale[7] * r8);
+    total[t * ld + e] = tv[i] + (P.reward_scale[5] * r6 + P.reward_scale[7] * r8);
     if (comp) {
       comp[(t * KBS_NUM_REWARDS + 5) * ld + e] = r6;
       comp[(t * KBS_NUM_REWARDS + 7) * ld + e] = r8;
     }
+  }
   }
   carry.t_single[e] = t_sc;
   carry.airtime[e] = air0; carry.airtime[ld + e] = air1;
@@ -1136,8 +1155,8 @@ policy_unpack_kernel(const float* __restrict__ lpf, const float* __restrict__ me
 // evaluated for all T steps up front).  One thread per env, time walked sequentially; loads are env-coalesced.
 // =====================================================================================================
 // UnifiedCommand over T steps: command[t+1] = (done[t] or u_switch[t] < p) ? initial_command(rand[t]) : command[t]
-__global__ void __launch_bounds__(kThreads)
-command_scan_kernel(const __grid_constant__ kbs_params P, float* __restrict__ command /*[T+1][16][ld]*/,
+__device__ __forceinline__ void
+command_scan_body(const kbs_params& P, int k, float* __restrict__ command /*[T+1][16][ld]*/,
                     const float* __restrict__ u_switch, const int32_t* __restrict__ mode, const float* __restrict__ u6,
                     const float* __restrict__ u_arms, const uint8_t* __restrict__ done, int64_t T, int64_t ld, int64_t n) {
   const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
@@ -1146,7 +1165,6 @@ command_scan_kernel(const __grid_constant__ kbs_params P, float* __restrict__ co
   // 32 SMs and the kernel is pure latency).  The command after step t is new(t*) at the LAST switch t* <= t (the new value
   // does not depend on the previous one, train.py:768-785), so a 32-step chunk is: 64 independent loads -> a switch bit
   // mask -> the (rare: p ~ 0.014 per step) switch values, loaded only at the set bits -> 32 coalesced stores.
-  const int k = blockIdx.y;
   float c = command[k * ld + e];
   for (int64_t t0 = 0; t0 < T; t0 += 32) {
     unsigned mask = 0;
@@ -1187,8 +1205,8 @@ command_scan_kernel(const __grid_constant__ kbs_params P, float* __restrict__ co
 
 // Lagged projected gravity (ProjectedGravityObservation min_lag/max_lag): x_t = lag x_{t-1} + (1-lag) g_b(t), restarted at
 // g_b(t) on the first step of a new episode (done[t-1]).  pg_carry in/out; lagged[T][3][ld] out.
-__global__ void __launch_bounds__(kThreads)
-pg_scan_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ sensordata, const float* __restrict__ lag_p,
+__device__ __forceinline__ void
+pg_scan_body(const kbs_params& P, const float* __restrict__ sensordata, const float* __restrict__ lag_p,
                const uint8_t* __restrict__ done, float* __restrict__ pg_carry, float* __restrict__ lagged, int64_t T,
                int64_t ld, int64_t n) {
   const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
@@ -1224,6 +1242,29 @@ pg_scan_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ s
     }
   }
   pg_carry[e] = x[0]; pg_carry[ld + e] = x[1]; pg_carry[2 * ld + e] = x[2];
+}
+
+__global__ void __launch_bounds__(kThreads)
+command_scan_kernel(const __grid_constant__ kbs_params P, float* __restrict__ command, const float* __restrict__ u_switch,
+                    const int32_t* __restrict__ mode, const float* __restrict__ u6, const float* __restrict__ u_arms,
+                    const uint8_t* __restrict__ done, int64_t T, int64_t ld, int64_t n) {
+  command_scan_body(P, blockIdx.y, command, u_switch, mode, u6, u_arms, done, T, ld, n);
+}
+__global__ void __launch_bounds__(kThreads)
+pg_scan_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ sensordata, const float* __restrict__ lag_p,
+               const uint8_t* __restrict__ done, float* __restrict__ pg_carry, float* __restrict__ lagged, int64_t T,
+               int64_t ld, int64_t n) {
+  pg_scan_body(P, sensordata, lag_p, done, pg_carry, lagged, T, ld, n);
+}
+// Both scans of the fused rollout's phase A in one launch (they only depend on `done`): blockIdx.y = 0..15 command rows,
+// 16 = the lagged-gravity scan -- two latency-bound kernels side by side instead of back to back.
+__global__ void __launch_bounds__(kThreads)
+phase_a_scans_kernel(const __grid_constant__ kbs_params P, float* __restrict__ command, const float* __restrict__ u_switch,
+                     const int32_t* __restrict__ mode, const float* __restrict__ u6, const float* __restrict__ u_arms,
+                     const uint8_t* __restrict__ done, const float* __restrict__ sensordata, const float* __restrict__ lag_p,
+                     float* __restrict__ pg_carry, float* __restrict__ lagged, int64_t T, int64_t ld, int64_t n) {
+  if (blockIdx.y < KBS_NUM_COMMANDS) command_scan_body(P, blockIdx.y, command, u_switch, mode, u6, u_arms, done, T, ld, n);
+  else pg_scan_body(P, sensordata, lag_p, done, pg_carry, lagged, T, ld, n);
 }
 
 inline unsigned groups4(int64_t n) { return unsigned((((n + 3) / 4) + kThreads - 1) / kThreads); }
@@ -1313,6 +1354,16 @@ int kbs_launch_command_scan(kbs_handle* h, float* command, const float* u_switch
   KBS_LAUNCH(h, KBS_K_COMMAND, st,
              (command_scan_kernel<<<dim3(unsigned((n + kThreads - 1) / kThreads), KBS_NUM_COMMANDS), kThreads, 0, st>>>(h->p, command, u_switch, mode,
                                                                                               u6, u_arms, done, T, ld, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_phase_a_scans(kbs_handle* h, float* command, const float* u_switch, const int32_t* mode, const float* u6,
+                             const float* u_arms, const uint8_t* done, const float* sensordata, const float* lag,
+                             float* pg_carry, float* lagged, int64_t T, int64_t ld, int64_t n, cudaStream_t st) {
+  KBS_LAUNCH(h, KBS_K_COMMAND, st,
+             (phase_a_scans_kernel<<<dim3(unsigned((n + kThreads - 1) / kThreads), KBS_NUM_COMMANDS + 1), kThreads, 0, st>>>(
+                 h->p, command, u_switch, mode, u6, u_arms, done, sensordata, lag, pg_carry, lagged, T, ld, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

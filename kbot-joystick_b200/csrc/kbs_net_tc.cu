@@ -727,7 +727,11 @@ constexpr int kStagesP = 4;              // power of two that divides every item
 constexpr int kPSmemBytes = kStagesP * kStageBytesP + (kPBiasFloats + kPHeadPartFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
 
 struct PNet {
-  const char* x_sb_all;            // [T] x sbb: layer-0 inputs (input projection of every step)
+  const char* x_sb_all;            // [T] x x0_stride: layer-0 inputs -- the input projection of every step (kb_x0 = H / block
+                                   // K), or, for a net whose input projection is folded into layer 0 (kbs_tc_fused_input),
+                                   // the packed observations themselves (kb_x0 = padded input width / block K)
+  size_t x0_stride;                // bytes per step of x_sb_all
+  int kb_x0;                       // K blocks of the layer-0 input operand
   char* hsb;                       // [depth][2] x sbb: recurrent SB state (reset where done); step t reads parity t & 1
   char* xmid;                      // [depth][2] x sbb: un-reset SB output of layer l at step t (parity t & 1)
   float* fb;                       // [depth][c, h] x np*H: fp32 FB state
@@ -901,13 +905,14 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
         const PItem it = p_decode(args, gi);
         if (!it.valid) continue;
         const PNet& N = args.net[it.net];
-        const int kb_x = kb, kb_total = it.kind == 0 ? 2 * kb : kb;
+        const int kb_x = (it.kind == 0 && it.layer == 0) ? N.kb_x0 : kb;
+        const int kb_total = it.kind == 0 ? kb_x + kb : kb;
         size_t poff = size_t(it.panel) * kb * kABlockBytes;
         if (args.dbg & 8) poff = size_t(blockIdx.x % args.panels) * kb * kABlockBytes;   // probe: no two CTAs share a panel at a time
         const char* xa; const char* ha; const char* wb;
         if (it.kind == 0) {
-          xa = (it.layer == 0 ? N.x_sb_all + size_t(it.t) * args.sbb
-                              : N.xmid + size_t((it.layer - 1) * 2 + (it.t & 1)) * args.sbb) + poff;
+          xa = it.layer == 0 ? N.x_sb_all + size_t(it.t) * N.x0_stride + poff / kb * kb_x
+                             : N.xmid + size_t((it.layer - 1) * 2 + (it.t & 1)) * args.sbb + poff;
           ha = N.hsb + size_t(it.layer * 2 + (it.t & 1)) * args.sbb + poff;
           wb = N.w_sb[it.layer] + size_t((args.dbg & 16) ? (blockIdx.x + it.t) % args.tiles : it.tile) * kb_total * kBBlockBytesP;
         } else {
@@ -972,7 +977,7 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
       for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
         const PItem it = p_decode(args, gi);
         if (!it.valid) continue;
-        const int kb_total = it.kind == 0 ? 2 * kb : kb;
+        const int kb_total = it.kind == 0 ? ((it.layer == 0 ? args.net[it.net].kb_x0 : kb) + kb) : kb;
         const long long e0 = tr ? clock64() : 0;
         mbar_wait(&acc_empty[0], (j & 1) ^ 1);    // the epilogue of the previous item has pulled the accumulators
         if (tr) waited_acc += clock64() - e0;
