@@ -138,6 +138,8 @@ int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStr
     KBS_CUDA_TRY(cudaEventRecord(h->ev_pre, st));           // scans done; previous call's readers of the staging buffers too
     KBS_CUDA_TRY(cudaStreamWaitEvent(aux, h->ev_pre, 0));
   }
+  KbsTcRolloutArgs r{};
+  r.x_sb_all[0] = xsb_a; r.x_sb_all[1] = xsb_c;
   int n_chunks = 0;
   for (int64_t t0 = 0; t0 < T; t0 += CT, ++n_chunks) {
     const int64_t tc = (T - t0 < CT) ? T - t0 : CT;
@@ -151,16 +153,15 @@ int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStr
     const float* obs_soa[2] = {aobs_c, cobs};
     float* obs_sb[2] = {osb_a, osb_c};
     float* xsb[2] = {xsb_a + size_t(t0) * sbf, critic ? xsb_c + size_t(t0) * sbf : nullptr};
+    // one chunk (default): the actor's input projection is folded into layer 0 of the persistent kernel (r.x_is_obs)
     if ((rc = kbs_tc_input_proj_all(h, critic ? 2 : 1, obs_soa, obs_sb, xsb, ld, n, tc, aux,
-                                    critic ? s.cinert : nullptr, critic ? s.cvel : nullptr)))
+                                    critic ? s.cinert : nullptr, critic ? s.cvel : nullptr, chunks_cfg == 1 ? &r : nullptr)))
       return rc;
     if (overlap) KBS_CUDA_TRY(cudaEventRecord(h->ev_chunk[n_chunks], aux));
   }
 
-  KbsTcRolloutArgs r{};
   r.chunk_len = overlap ? CT : 0; r.chunk_events = h->ev_chunk;
   r.n = n; r.ld = ld; r.T = T; r.with_critic = critic;
-  r.x_sb_all[0] = xsb_a; r.x_sb_all[1] = xsb_c;
   r.carry[0] = io->actor_carry; r.carry[1] = io->critic_carry;
   r.done = io->done; r.actor_obs = aobs; r.lpf = io->lpf; r.eps_action = io->eps_action;
   r.qpos = io->state.qpos; r.qvel = io->state.qvel; r.ep = io->episode;
@@ -620,10 +621,9 @@ int kbs_policy_step(kbs_handle* h, const float* joint_angles, const float* joint
       const float* obs_soa[2] = {obs, nullptr};
       float* obs_sb[2] = {osb, nullptr};
       float* x_all[2] = {xsb, nullptr};
-      if ((rc = kbs_tc_input_proj_all(h, 1, obs_soa, obs_sb, x_all, ld, n, 1, st))) return rc;
       KbsTcRolloutArgs r{};
+      if ((rc = kbs_tc_input_proj_all(h, 1, obs_soa, obs_sb, x_all, ld, n, 1, st, nullptr, nullptr, &r))) return rc;
       r.n = n; r.ld = ld; r.T = 1; r.with_critic = false;
-      r.x_sb_all[0] = xsb;
       r.carry[0] = const_cast<float*>(carry_in); r.carry_out[0] = carry_out; r.carry_ld = carry_w;
       r.actor_obs = obs; r.lpf = lpf; r.action = act;
       r.ws = ws;
@@ -700,15 +700,14 @@ int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n, void* stre
   float* xsb_c = critic ? xsb_a + xsb_f : nullptr;
   float* osb_a = xsb_a + xsb_f * (critic ? 2 : 1);
   float* osb_c = critic ? osb_a + osb_a_f : nullptr;
+  KbsTcRolloutArgs r{};
   {
     const float* obs_soa[2] = {io->actor_obs, io->critic_obs};
     float* obs_sb[2] = {osb_a, osb_c};
     float* xsb[2] = {xsb_a, xsb_c};
-    if ((rc = kbs_tc_input_proj_all(h, critic ? 2 : 1, obs_soa, obs_sb, xsb, ld, n, T, st))) return rc;
+    if ((rc = kbs_tc_input_proj_all(h, critic ? 2 : 1, obs_soa, obs_sb, xsb, ld, n, T, st, nullptr, nullptr, &r))) return rc;
   }
-  KbsTcRolloutArgs r{};
   r.n = n; r.ld = ld; r.T = T; r.with_critic = critic;
-  r.x_sb_all[0] = xsb_a; r.x_sb_all[1] = xsb_c;
   r.carry[0] = io->actor_carry; r.carry[1] = io->critic_carry;
   r.done = io->done; r.actor_obs = io->actor_obs; r.lpf = io->lpf;
   r.action_in = io->action; r.log_prob = io->log_probs; r.entropy = io->entropy; r.action_std = io->action_std;

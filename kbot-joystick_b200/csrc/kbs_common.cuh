@@ -161,6 +161,8 @@ struct KbsTcRolloutArgs {
   int64_t n, ld, T;
   bool with_critic;
   const float* x_sb_all[2];   // [T] x kbs_tc_sb_floats SB input-projection outputs per net (actor, critic)
+  bool x_is_obs[2];           // x_sb_all[k] holds the packed observations: the projection is folded into layer 0
+                              // (set by kbs_tc_input_proj_all(.., r_out); persistent kernel only)
   float* carry[2];            // ABI carries [depth][2][n][H]
   // carry_ld != 0 (persistent kernel only): the carries are rows of a flat per-env record instead (convert.py carry
   // [n][depth*2*H + 20]): element (slot = 2 * layer + {h, c}, env e, unit k) at carry[net][e * carry_ld + slot * H + k],
@@ -189,7 +191,8 @@ int64_t kbs_tc_obs_sb_floats(const kbs_handle* h, int net, int64_t n, int64_t T)
 // ([T][240][ld] / [T][144][ld]) instead of obs_soa[critic]
 int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, float* const* obs_sb, float* const* x_sb_all,
                           int64_t ld, int64_t n, int64_t T, cudaStream_t st, const float* cinert = nullptr,
-                          const float* cvel = nullptr);
+                          const float* cvel = nullptr, struct KbsTcRolloutArgs* r_out = nullptr);
+bool kbs_tc_fused_input(const kbs_handle* h, int net, int64_t n, int64_t T, int nets);
 int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStream_t st);
 // true when kbs_tc_rollout_recurrent will take the persistent kernel for this shape (all T steps in one launch)
 bool kbs_tc_persistent_available(const kbs_handle* h, int64_t n, int64_t T, int nets);

@@ -1230,8 +1230,10 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
 template <int KIND, int TILE>
 __global__ void __launch_bounds__(256)
 pack_lstm_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b,
-                         char* __restrict__ w_sb, float* __restrict__ bias_t, int H) {
-  const int kq = 2 * H / 4;
+                         char* __restrict__ w_sb, float* __restrict__ bias_t, int H, int Kx, int ldx) {
+  // w_ih: [4H][ldx] with Kx (<= ldx) columns used -- eqx weight_ih (Kx = ldx = H), or the layer-0 weight with the input
+  // projection folded in (fuse_input_weights_kernel: Kx = padded observation width)
+  const int kq = (Kx + H) / 4;
   const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (idx >= int64_t(4 * H) * kq) return;
   const int col_g = int(idx / kq);                        // global packed column: tile * TILE + c
@@ -1240,10 +1242,33 @@ pack_lstm_weights_kernel(const float* __restrict__ w_ih, const float* __restrict
   const int grp = c / 64, gate = (c % 64) / 16, uu = c % 16;      // [16-unit group][gate i,f,g,o][unit]
   const int u = tile * (TILE / 4) + grp * 16 + uu;
   const int row = gate * H + u;                           // eqx row (i,f,g,o blocks of H)
-  const float* src = (k < H) ? w_ih + size_t(row) * H + k : w_hh + size_t(row) * H + (k - H);
+  const float* src = (k < Kx) ? w_ih + size_t(row) * ldx + k : w_hh + size_t(row) * H + (k - Kx);
   const float x[4] = {src[0], src[1], src[2], src[3]};
-  sb_store4<TILE, KIND, true>(w_sb, col_g, k, 2 * H / kbs_block_k(KIND), x);
+  sb_store4<TILE, KIND, true>(w_sb, col_g, k, (Kx + H) / kbs_block_k(KIND), x);
   if (k == 0) bias_t[col_g] = b[row];
+}
+
+// Input projection folded into LSTM layer 0 (persistent kernel): gates = W_ih (W_in o + b_in) + W_hh h + b
+//   = (W_ih W_in) o + W_hh h + (W_ih b_in + b).  wf [4H][Kf] = W_ih W_in (columns >= num_in zero), bf [4H]; sums in
+// double, rounded once to fp32 (the reference rounds x = W_in o + b_in to fp32 first: the two forms differ at the 1e-7
+// level, inside the 1e-5 tolerance; the oracle keeps the reference's two-step form).
+__global__ void __launch_bounds__(256)
+fuse_input_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_in, int ld_in, int num_in,
+                          const float* __restrict__ b_in, const float* __restrict__ b, float* __restrict__ wf,
+                          float* __restrict__ bf, int H, int Kf) {
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= int64_t(4 * H) * (Kf + 1)) return;
+  const int row = int(idx / (Kf + 1)), k = int(idx % (Kf + 1));
+  const float* wr = w_ih + size_t(row) * H;
+  double acc = 0.0;
+  if (k == Kf) {
+    for (int j = 0; j < H; ++j) acc += double(wr[j]) * double(b_in[j]);
+    bf[row] = float(acc + double(b[row]));
+  } else {
+    if (k < num_in)
+      for (int j = 0; j < H; ++j) acc += double(wr[j]) * double(w_in[size_t(j) * ld_in + k]);
+    wf[size_t(row) * Kf + k] = float(acc);
+  }
 }
 
 // eqx Linear weight [H][ldw] (K zero-padded to ldw) -> ceil(H/128) SB tiles of 128 plain columns (rows >= H zero), K padded to Kp.
@@ -1505,6 +1530,24 @@ static inline char* head_w(const kbs_handle* h, int net) { return layer_w_p(h, n
 static inline float* head_bias(const kbs_handle* h, int net) {
   return reinterpret_cast<float*>(head_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), kTileColsP, h->p.hidden_size));
 }
+// Layer 0 with the input projection folded in (persistent kernel, see fuse_input_weights_kernel): the observation operand
+// is padded to a multiple of 4 K blocks (the kernel's stage ring); worth it when that is narrower than H (actor: 65 ->
+// 128 < 256; critic: 475 -> 512 > 256, keeps its projection launch).  Image F: [wf fp32 | bf | w_sb | bias_t].
+static inline int fused_kp(const kbs_handle* h, int net) { return round_up_i(h->net[net].num_in, 4 * kbs_block_k(tc_kind(h))); }
+static inline bool fused_shape(const kbs_handle* h, int net) { return fused_kp(h, net) < h->p.hidden_size; }
+static size_t fused_image_bytes(const kbs_handle* h, int net) {
+  if (!fused_shape(h, net)) return 0;
+  const int H = h->p.hidden_size, Kf = fused_kp(h, net);
+  return size_t(4 * H) * Kf * 4 + size_t(4 * H) * 4 + kbs_sb_bytes_kind(tc_kind(h), 4 * H, Kf + H) + size_t(4 * H) * 4;
+}
+static inline float* fused_wf(const kbs_handle* h, int net) {
+  return reinterpret_cast<float*>(head_w(h, net) + head_image_bytes(h));
+}
+static inline float* fused_bf(const kbs_handle* h, int net) { return fused_wf(h, net) + size_t(4 * h->p.hidden_size) * fused_kp(h, net); }
+static inline char* fused_w(const kbs_handle* h, int net) { return reinterpret_cast<char*>(fused_bf(h, net) + 4 * h->p.hidden_size); }
+static inline float* fused_bias(const kbs_handle* h, int net) {
+  return reinterpret_cast<float*>(fused_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), 4 * h->p.hidden_size, fused_kp(h, net) + h->p.hidden_size));
+}
 static inline bool persist_shape_ok(const kbs_handle* h) {
   const int H = h->p.hidden_size;
   return H % kUnitsPerTileP == 0 && h->p.depth <= kPMaxDepth && H <= kMaxBias / 4 &&
@@ -1523,7 +1566,8 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
     KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
     attr_set = true;
   }
-  const size_t bytes = 2 * layer_image_bytes(h) * h->p.depth + proj_image_bytes(h, net) + head_image_bytes(h);
+  const size_t bytes = 2 * layer_image_bytes(h) * h->p.depth + proj_image_bytes(h, net) + head_image_bytes(h) +
+                       fused_image_bytes(h, net);
   N.tc_image_floats = (bytes + 3) / 4;
   if (!N.tc_image) KBS_CUDA_TRY(cudaMalloc(&N.tc_image, bytes));      // fixed size per handle: re-packs keep the pointer
   for (int l = 0; l < h->p.depth; ++l) {
@@ -1531,17 +1575,17 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
     const unsigned gb = unsigned((total + 255) / 256);
     if (kind == KBS_KIND_TF32)
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_TF32, kTileCols><<<gb, 256, 0, st>>>(
-                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w(h, net, l), layer_bias(h, net, l), H)));
+                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w(h, net, l), layer_bias(h, net, l), H, H, H)));
     else
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_F16, kTileCols><<<gb, 256, 0, st>>>(
-                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w(h, net, l), layer_bias(h, net, l), H)));
+                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w(h, net, l), layer_bias(h, net, l), H, H, H)));
     if (!persist_shape_ok(h)) continue;
     if (kind == KBS_KIND_TF32)
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_TF32, kTileColsP><<<gb, 256, 0, st>>>(
-                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w_p(h, net, l), layer_bias_p(h, net, l), H)));
+                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w_p(h, net, l), layer_bias_p(h, net, l), H, H, H)));
     else
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_F16, kTileColsP><<<gb, 256, 0, st>>>(
-                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w_p(h, net, l), layer_bias_p(h, net, l), H)));
+                                        N.w_ih[l], N.w_hh[l], N.b[l], layer_w_p(h, net, l), layer_bias_p(h, net, l), H, H, H)));
   }
   {
     const int Kp = proj_kp(h, net);
@@ -1554,6 +1598,20 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
     else
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
                                         N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp, cols)));
+  }
+  if (persist_shape_ok(h) && fused_shape(h, net)) {   // layer 0 with the input projection folded in
+    const int Kf = fused_kp(h, net);
+    const int64_t tot_f = int64_t(4 * H) * (Kf + 1);
+    KBS_LAUNCH(h, KBS_K_PACK, st, (fuse_input_weights_kernel<<<unsigned((tot_f + 255) / 256), 256, 0, st>>>(
+                                      N.w_ih[0], N.w_in, N.kin_pad, N.num_in, N.b_in, N.b[0], fused_wf(h, net), fused_bf(h, net), H, Kf)));
+    const int64_t total = int64_t(4 * H) * ((Kf + H) / 4);
+    const unsigned gb = unsigned((total + 255) / 256);
+    if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_TF32, kTileColsP><<<gb, 256, 0, st>>>(
+                                        fused_wf(h, net), N.w_hh[0], fused_bf(h, net), fused_w(h, net), fused_bias(h, net), H, Kf, Kf)));
+    else
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_F16, kTileColsP><<<gb, 256, 0, st>>>(
+                                        fused_wf(h, net), N.w_hh[0], fused_bf(h, net), fused_w(h, net), fused_bias(h, net), H, Kf, Kf)));
   }
   if (persist_shape_ok(h)) {   // output head tile (persistent rollout kernel)
     const int64_t total = int64_t(kTileColsP) * (H / 4);
@@ -1794,13 +1852,25 @@ size_t kbs_tc_rollout_ws_floats(const kbs_handle* h, int64_t n) { return 2 * rol
 int64_t kbs_tc_sb_floats(const kbs_handle* h, int64_t n) { return int64_t(act_sb_bytes(h, n) / 4); }
 // floats of the SB observation staging buffer of `net` for T steps
 int64_t kbs_tc_obs_sb_floats(const kbs_handle* h, int net, int64_t n, int64_t T) {
-  return int64_t(kbs_sb_bytes_kind(tc_kind(h), T * pad_rows(n), proj_kp(h, net)) / 4);
+  const int kp = proj_kp(h, net), kf = fused_shape(h, net) ? fused_kp(h, net) : 0;
+  return int64_t(kbs_sb_bytes_kind(tc_kind(h), T * pad_rows(n), kp > kf ? kp : kf) / 4);
+}
+
+// true: kbs_tc_input_proj_all(.., r_out) will fold net's input projection into layer 0 of the persistent kernel
+bool kbs_tc_fused_input(const kbs_handle* h, int net, int64_t n, int64_t T, int nets) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("KBS_NO_FUSED_INPUT"); off = (e && atoi(e)) ? 1 : 0; }
+  const char* legacy_env = getenv("KBS_TC_PER_STEP");
+  if (off || (legacy_env && atoi(legacy_env))) return false;
+  return fused_shape(h, net) && kbs_tc_persistent_available(h, n, T, nets);
 }
 
 // obs_soa[k]: [T][num_in][ld] observations of net k; obs_sb[k]: staging (kbs_tc_obs_sb_floats); x_sb_all[k]: [T] x act SB.
 int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, float* const* obs_sb, float* const* x_sb_all,
-                          int64_t ld, int64_t n, int64_t T, cudaStream_t st, const float* cinert, const float* cvel) {
+                          int64_t ld, int64_t n, int64_t T, cudaStream_t st, const float* cinert, const float* cvel,
+                          KbsTcRolloutArgs* r_out) {
   const int H = h->p.hidden_size, kind = tc_kind(h);
+  int proj_nets = 0;
   const int64_t np = pad_rows(n);
   // Default: pack kernel -> SB staging buffer -> bulk copies.  KBS_PROJ_FUSED=1: the projection kernel's producer warps
   // read the SoA observations themselves (MODE_PROJ_SOA).  MEASURED: 3.87 ms instead of 0.45 + 0.49 ms per 100-step
@@ -1812,12 +1882,14 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
   for (int k = 0; k < nets; ++k) {
     const KbsNet& N = h->net[k];
     if (!N.packed || !N.tc_image) return KBS_E_STATE;
-    const int Kp = proj_kp(h, k);
+    const bool fuse = r_out && kbs_tc_fused_input(h, k, n, T, nets);
+    const int Kp = fuse ? fused_kp(h, k) : proj_kp(h, k);
     const float* ci = (k == KBS_NET_CRITIC) ? cinert : nullptr;
     const float* cv = (k == KBS_NET_CRITIC) ? cvel : nullptr;
     char* osb = reinterpret_cast<char*>(obs_sb[k]);
     LayerArgs& a = a2.net[k];
-    if (staged) {
+    if (r_out) { r_out->x_sb_all[k] = fuse ? obs_sb[k] : x_sb_all[k]; r_out->x_is_obs[k] = fuse; }
+    if (staged || fuse) {
       const int64_t total = T * np * (Kp / 8);
       const unsigned gb = unsigned((total + 255) / 256);
       if (kind == KBS_KIND_TF32)
@@ -1825,6 +1897,7 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
       else
         KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv)));
       a.mode = MODE_PROJ;
+      if (fuse) continue;            // the packed observations ARE layer 0's input operand: no projection items (panels = 0)
     } else {
       // fused: the projection kernel's producer warps read the SoA observations (and the critic's cinert / cvel dump from the
       // recorded state) themselves and build the MMA operand in shared memory
@@ -1839,8 +1912,11 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
     a.n = T * np;                    // every staged row is written (pad rows carry the bias: harmless, never read back)
     a.H = H; a.kb_x = Kp / kbs_block_k(kind); a.kb_h = 0;
     a.panels = int(T * np / kPanelRows); a.tiles = proj_cols(h) / kTileCols;
+    ++proj_nets;
   }
-  if (nets == 1) a2.net[1].mode = a2.net[0].mode;
+  if (!proj_nets) { KBS_LAUNCH_CHECK(); return KBS_OK; }
+  for (int k = 0; k < 2; ++k)
+    if (!a2.net[k].panels) a2.net[k].mode = a2.net[k ^ 1].mode;
   KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (launch_layer(h, kind, a2, st)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
@@ -1879,6 +1955,7 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
   const char* legacy_env = getenv("KBS_TC_PER_STEP");          // A/B and cross-check against the per-step launches
   const int legacy = legacy_env ? atoi(legacy_env) : 0;
   const bool persistent = !legacy && kbs_tc_persistent_available(h, n, r.T, nets);
+  if ((r.x_is_obs[0] || r.x_is_obs[1]) && !persistent) return KBS_E_STATE;         // folded input projection: persistent only
   if (r.carry_ld && (!persistent || nets * depth * 2 > 8 || H % 8)) return KBS_E_STATE;   // flat carries: persistent kernel only
   const size_t slot_f = r.carry_ld ? size_t(H) : size_t(n) * H;                  // floats between carry slots
   if (nets * depth * 2 <= 8 && H % 8 == 0) {                       // ABI carry: h -> SB (parity 0), c -> FB; one launch
@@ -1906,8 +1983,11 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     for (int k = 0; k < nets; ++k) {
       PNet& N = a.net[k];
       N.x_sb_all = reinterpret_cast<const char*>(r.x_sb_all[k]);
+      N.kb_x0 = r.x_is_obs[k] ? fused_kp(h, k) / kbs_block_k(kind) : H / kbs_block_k(kind);
+      N.x0_stride = r.x_is_obs[k] ? kbs_sb_bytes_kind(kind, np, fused_kp(h, k)) : sbb;
       N.hsb = hsb[k]; N.xmid = xmid[k]; N.fb = fb[k]; N.flags = flags[k];
       for (int l = 0; l < depth; ++l) { N.w_sb[l] = layer_w_p(h, k, l); N.bias_t[l] = layer_bias_p(h, k, l); }
+      if (r.x_is_obs[k]) { N.w_sb[0] = fused_w(h, k); N.bias_t[0] = fused_bias(h, k); }
       N.w_head = head_w(h, k); N.bias_head = head_bias(h, k);
       KBS_CUDA_TRY(cudaMemsetAsync(flags[k], 0, rollout_flag_bytes(h, n), st));
     }
