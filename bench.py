@@ -337,7 +337,9 @@ def run_b200(a):
         if dom_name in ("lstm_layer_tc_kernel", "rollout_persist_kernel"):
             if dom_name == "rollout_persist_kernel":
                 # one launch = the whole recurrence: T steps x (2 nets x depth LSTM layers + actor/critic output heads)
-                flops_per_launch = N * T * (2 * 2 * lstm_layer_flops + 2 * H * (40 + 1))
+                # (+ the actor's input projection 2 x 65 x H, folded into its layer 0 since r01 session 4).  ALGORITHMIC
+                # FLOPs = the reference's arithmetic for this work, not the MMAs the kernel happens to issue.
+                flops_per_launch = N * T * (2 * 2 * lstm_layer_flops + 2 * H * (40 + 1) + 2 * 65 * H)
             else:
                 flops_per_launch = lstm_layer_flops * N * 2      # one launch = one layer-step of BOTH nets
             if a.gemm == "tf32":
@@ -351,9 +353,9 @@ def run_b200(a):
             peak = 72.0                                           # fp32 FFMA: 148 SMs x 128 lanes x 2 x ~1.9 GHz
             note = "fp32 FFMA path: peak = nominal FFMA rate (interim SIMT datapath)"
         ach = flops_per_launch / (dom_ms / dom_n * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_persist_kernel.md);
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_s4_phase_a_and_persist.md);
         # only valid for the configuration that capture was taken on
-        traffic = 8.56e9 if (dom_name == "rollout_persist_kernel" and (N, T, H, a.gemm) == (4096, 100, 256, "f16")) else None
+        traffic = 9.01e9 if (dom_name == "rollout_persist_kernel" and (N, T, H, a.gemm) == (4096, 100, 256, "f16")) else None
         roof = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic, "launches": dom_n, "avg_launch_us": 1e3 * dom_ms / dom_n,
                 "share_of_step": dom_ms / tot_prof, "peak_source": which, "note": note}
@@ -362,6 +364,14 @@ def run_b200(a):
                 "traffic": None, "launches": dom_n, "avg_launch_us": 1e3 * dom_ms / dom_n,
                 "share_of_step": dom_ms / tot_prof, "peak_source": which}
     breakdown = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    # HBM-bound stages: algorithmic bytes per env-step (DESIGN.md section 4 / SURVEY 8d) x N x T / event time / HBM peak
+    hbm_bytes = {"obs_kernel": 808 + 1300, "pack_kernels": 3788 + 650, "proj_tc_kernel": 480 * 4 + H * 4,
+                 "reward_terms_kernel": 340, "command_kernel": 244 + 28, "terminate_kernel": 46, "gae_kernel": 18}
+    for k, b in hbm_bytes.items():
+        if k in breakdown and breakdown[k]["ms"] > 0:
+            gbs = b * N * T / (breakdown[k]["ms"] * 1e-3) / 1e9
+            breakdown[k]["hbm_gbs"] = round(gbs, 1)
+            breakdown[k]["hbm_frac"] = round(gbs / hbm_peak, 3)
 
     # ---- end-to-end: host (pinned) inputs -> H2D -> step -> D2H of the results -------------------------------------
     e2e = None

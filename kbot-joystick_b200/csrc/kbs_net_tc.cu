@@ -1858,10 +1858,9 @@ int64_t kbs_tc_obs_sb_floats(const kbs_handle* h, int net, int64_t n, int64_t T)
 
 // true: kbs_tc_input_proj_all(.., r_out) will fold net's input projection into layer 0 of the persistent kernel
 bool kbs_tc_fused_input(const kbs_handle* h, int net, int64_t n, int64_t T, int nets) {
-  static int off = -1;
-  if (off < 0) { const char* e = getenv("KBS_NO_FUSED_INPUT"); off = (e && atoi(e)) ? 1 : 0; }
+  const char* off_env = getenv("KBS_NO_FUSED_INPUT");          // A/B + cross-check (tests): keep the projection launch
   const char* legacy_env = getenv("KBS_TC_PER_STEP");
-  if (off || (legacy_env && atoi(legacy_env))) return false;
+  if ((off_env && atoi(off_env)) || (legacy_env && atoi(legacy_env))) return false;
   return fused_shape(h, net) && kbs_tc_persistent_available(h, n, T, nets);
 }
 

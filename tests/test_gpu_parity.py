@@ -427,7 +427,8 @@ def test_policy_step(dev, path, N):
 
 
 @pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("T,N,hidden", [(16, 32, 256), (6, 130, 256), (5, 50, 128), (7, 1100, 256), (1, 300, 256)])
+@pytest.mark.parametrize("T,N,hidden", [(16, 32, 256), (6, 130, 256), (5, 50, 128), (7, 1100, 256), (1, 300, 256),
+                                        (70, 40, 256)])   # 70 steps: three 32-step chunks of the command / reward scans
 def test_rollout_fused(dev, path, T, N, hidden):
     """BASELINE config 1 shape (num_envs = 32, short rollout): the fused control step over T recorded steps."""
     res = Hn.run_rollout_case(seed=800 + N, T=T, N=N, hidden=hidden, device=dev, gemm_path=path)
@@ -471,6 +472,35 @@ def test_rollout_persistent_vs_per_step_launches(dev, T, N, monkeypatch):
     close(S(a["action"], N, (20,)), S(c["action"], N, (20,)), "action")
     close(S(a["log_prob"], N), S(c["log_prob"], N), "log_prob", atol=1e-5)
     close(S(a["value"], N), S(c["value"], N), "value", atol=1e-5)
+    close(S(a["ctrl"], N, (20,)), S(c["ctrl"], N, (20,)), "ctrl", atol=1e-4)
+    close(S(a["lpf"], N, (20,)), S(c["lpf"], N, (20,)), "lpf")
+
+
+@pytest.mark.parametrize("T,N", [(30, 4096)])
+def test_rollout_folded_input_projection_vs_projection_launch(dev, T, N, monkeypatch):
+    """The actor's input projection folded into LSTM layer 0 of the persistent kernel ((W_ih W_in) o, packed once) against
+    the reference's two-step form (x = W_in o + b_in as its own tensor-core launch, then W_ih x) at BASELINE configs[1]
+    width: same mathematics, different rounding points -- they must agree far inside the 1e-5 tolerance."""
+    b = Batch(777, T, N, dev)
+    outs = []
+    for off in ("0", "1"):
+        monkeypatch.setenv("KBS_NO_FUSED_INPUT", off)
+        e, _, _ = Hn.make_engine(gemm_path=L.GEMM_TC_2XF16, device=dev)
+        io = Hn.rollout_buffers(b, 256, 2)
+        e.profile(True)
+        e.rollout(io, N)
+        torch.cuda.synchronize()
+        prof = e.profile_read()
+        e.profile(False)
+        assert e.device_status() == 0
+        outs.append((io, prof))
+        e.close()
+    (a, pa), (c, pc) = outs
+    assert pa["proj_tc_kernel"][1] == pc["proj_tc_kernel"][1] == 1      # critic projection stays a launch in both
+    close(a["actor_carry"].cpu().numpy(), c["actor_carry"].cpu().numpy(), "actor carry", atol=2e-6)
+    assert torch.equal(a["critic_carry"], c["critic_carry"])            # the critic's datapath is untouched
+    close(S(a["action"], N, (20,)), S(c["action"], N, (20,)), "action")
+    close(S(a["log_prob"], N), S(c["log_prob"], N), "log_prob", atol=1e-5)
     close(S(a["ctrl"], N, (20,)), S(c["ctrl"], N, (20,)), "ctrl", atol=1e-4)
     close(S(a["lpf"], N, (20,)), S(c["lpf"], N, (20,)), "lpf")
 

@@ -32,7 +32,7 @@ def timed(fn, warm=3, it=5):
     return e0.elapsed_time(e1) / it
 
 
-def rollout_case(N, T):
+def rollout_case(N, T, label="configs[2] full rollout + rewards + GAE", it=5):
     ld = (N + 3) // 4 * 4
     d = synth.make_batch_device(1234 + 3, T, N, dev)
     command = torch.zeros((T + 1, 16, ld), **f32)
@@ -55,9 +55,9 @@ def rollout_case(N, T):
         eng.gae(io["value"], total, io["done"], io["success"], adv=adv, targets=tgt, n_envs=N)
         io["command"][0].copy_(io["command"][T])
 
-    ms = timed(step)
+    ms = timed(step, it=it)
     assert eng.device_status() == 0 and torch.isfinite(adv).all()
-    print(json.dumps({"config": "configs[2] full rollout + rewards + GAE", "n_envs": N, "T": T, "ms_per_rollout": ms,
+    print(json.dumps({"config": label, "n_envs": N, "T": T, "ms_per_rollout": ms,
                       "env_steps_per_s": N * T / (ms * 1e-3), "n_gpus": 1}), flush=True)
 
 
@@ -92,6 +92,9 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "rollout"):
         rollout_case(16384, 256)
+    if which in ("all", "online"):
+        # the call ksim's engine loop makes with MJX between control steps: one kbs_rollout per control step (T = 1)
+        rollout_case(4096, 1, "configs[1] online form: one kbs_rollout + rewards + GAE call per control step (T = 1)", it=200)
     if which in ("all", "policy"):
         policy_sweep()
     eng.close()
