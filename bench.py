@@ -365,8 +365,12 @@ def run_b200(a):
                 "share_of_step": dom_ms / tot_prof, "peak_source": which}
     breakdown = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     # HBM-bound stages: algorithmic bytes per env-step (DESIGN.md section 4 / SURVEY 8d) x N x T / event time / HBM peak
-    hbm_bytes = {"obs_kernel": 808 + 1300, "pack_kernels": 3788 + 650, "proj_tc_kernel": 480 * 4 + H * 4,
-                 "reward_terms_kernel": 340, "command_kernel": 244 + 28, "terminate_kernel": 46, "gae_kernel": 18}
+    # obs: unique rows read (~160 floats: joints, noise, IMU, command, feet, base) + 65 actor / 107 critic rows written
+    # (the 368-row cinert / cvel dump goes straight from the state into pack); command + lagged-gravity scans: the switch
+    # draw, done, IMU quaternion in, 16 command rows + 3 gravity rows out (the new-command uniforms are read only at a
+    # switch).  All within 5 % of ncu's dram__bytes per launch (profiles/r01_s4_phase_a_and_persist.md).
+    hbm_bytes = {"obs_kernel": 1210, "pack_kernels": 3788 + 650, "proj_tc_kernel": 480 * 4 + H * 4,
+                 "reward_terms_kernel": 340, "command_kernel": 100, "terminate_kernel": 46, "gae_kernel": 18}
     for k, b in hbm_bytes.items():
         if k in breakdown and breakdown[k]["ms"] > 0:
             gbs = b * N * T / (breakdown[k]["ms"] * 1e-3) / 1e9

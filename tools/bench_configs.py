@@ -2,7 +2,7 @@
   configs[2]  full rollout + rewards + GAE, 16 384 envs x 256 steps (env-sharded across GPUs = the same per-GPU work)
   configs[4]  actor-only inference batch sweep 2^10 .. 2^20 envs: the deployed policy step of convert.py:84-119
 Prints one JSON line per measurement (CUDA events, 3 warm-up + 5 timed iterations, inputs larger than L2 or rotated)."""
-import json, sys
+import json, os, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -11,7 +11,16 @@ import kbot_joystick_b200  # noqa: F401
 from kbot_joystick_b200 import _lib as L, synth
 from kbot_joystick_b200.engine import KbotStep
 
-dev = torch.device("cuda:0")
+from kbot_joystick_b200.sharding import max_over_ranks
+# one process per GPU under torch.distributed.run: every rank runs the same per-GPU work on its own envs (environments are
+# independent: no data-path collective); times are the MAX over ranks, throughput = per-GPU units x world / that time
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
 H = 256
 eng = KbotStep(hidden_size=H, depth=2, gemm_path=L.GEMM_TC_2XF16)
 eng.pack_weights(L.NET_ACTOR, synth.weights_to_device(synth.make_weights(77, 65, 40, H, 2), dev))
@@ -29,10 +38,21 @@ def timed(fn, warm=3, it=5):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / it
+    return max_over_ranks(e0.elapsed_time(e1) / it, dev)
 
 
-def rollout_case(N, T, label="configs[2] full rollout + rewards + GAE", it=5):
+def emit(rec):
+    rec["n_gpus"] = world
+    for k in list(rec):
+        if k.startswith("env_steps_per_s"):
+            rec[k] *= world
+    if world > 1:
+        rec["n_envs_per_gpu"] = rec.pop("n_envs")
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
+
+
+def rollout_case(N, T, label="configs[2] full rollout + rewards + GAE", it=5, graph=False):
     ld = (N + 3) // 4 * 4
     d = synth.make_batch_device(1234 + 3, T, N, dev)
     command = torch.zeros((T + 1, 16, ld), **f32)
@@ -57,8 +77,23 @@ def rollout_case(N, T, label="configs[2] full rollout + rewards + GAE", it=5):
 
     ms = timed(step, it=it)
     assert eng.device_status() == 0 and torch.isfinite(adv).all()
-    print(json.dumps({"config": label, "n_envs": N, "T": T, "ms_per_rollout": ms,
-                      "env_steps_per_s": N * T / (ms * 1e-3), "n_gpus": 1}), flush=True)
+    rec = {"config": label, "n_envs": N, "T": T, "ms_per_rollout": ms, "env_steps_per_s": N * T / (ms * 1e-3), "n_gpus": 1}
+    if graph:   # the same step replayed as one CUDA graph (the library launches only on the caller's stream)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            msg = timed(g.replay, it=it)
+            rec["ms_per_rollout_cuda_graph"] = msg
+            rec["env_steps_per_s_cuda_graph"] = N * T / (msg * 1e-3)
+        except Exception as ex:  # noqa: BLE001
+            rec["cuda_graph_error"] = repr(ex)[:200]
+    emit(rec)
 
 
 def policy_sweep():
@@ -85,7 +120,7 @@ def policy_sweep():
             prof = eng.profile_read()
             eng.profile(False)
             rec["kernel_breakdown_ms"] = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in prof.items() if k != "_overflow"}
-        print(json.dumps(rec), flush=True)
+        emit(rec)
 
 
 if __name__ == "__main__":
@@ -94,7 +129,7 @@ if __name__ == "__main__":
         rollout_case(16384, 256)
     if which in ("all", "online"):
         # the call ksim's engine loop makes with MJX between control steps: one kbs_rollout per control step (T = 1)
-        rollout_case(4096, 1, "configs[1] online form: one kbs_rollout + rewards + GAE call per control step (T = 1)", it=200)
+        rollout_case(4096, 1, "configs[1] online form: one kbs_rollout + rewards + GAE call per control step (T = 1)", it=200, graph=True)
     if which in ("all", "policy"):
         policy_sweep()
     eng.close()
