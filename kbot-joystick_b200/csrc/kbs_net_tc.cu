@@ -1223,6 +1223,308 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
   }
 }
 
+// ---- input projection straight from the env-major SoA observations ("async" form of MODE_PROJ_SOA) -------------------------
+// x = W_in o + b_in for all T x n rows, written as the SB operand of LSTM layer 0, WITHOUT the packed staging buffer:
+// pack_soa_sb_kernel (read 1.9 KB + write 1.9 KB per critic row) followed by the MODE_PROJ launch (read it again, 128-column
+// tiles: two items per panel) cost 0.33 + 0.33 ms per 4 096 x 100 rollout for ~0.2 ms of HBM traffic.  Here one CTA per SM
+// walks the 128-row panels; per K block (32 features; 16 for TF32):
+//   warps 1, 3  raw producers: cp.async (16 B per thread, a warp instruction = the 512 bytes of one feature row of the panel's
+//             128 envs; features 80..447 of the critic come straight from the recorded cinert / cvel arrays,
+//             train.py:1405-1413), 4-deep ring: ~48 KB of HBM reads in flight per SM (the register-staged MODE_PROJ_SOA
+//             had ~16 KB: 4x slower);
+//   warp 2    weight producer: the 32 KB W_in block (one 256-column tile = all H outputs, L2-resident) into the operand ring;
+//   warps 12-19  converters: thread = (env row, half of the K block); 16 floats from the raw stage (conflict-free column
+//             reads) -> hi / lo split -> two chunks of the A block in UMMA layout -> fence.proxy.async -> arrive;
+//   warp 0    MMA issuer: the persistent kernel's scheme (3 x N = 256 MMAs per k-step, main + correction accumulators);
+//   warps 4-11   epilogue: TMEM -> + bias -> split -> SB stores (16-byte chunks, 512 B per warp).
+// Requires H == 256 (one tile).  KBS_PROJ_STAGED=1 restores pack + MODE_PROJ.
+constexpr int kFStagesRaw = 4, kFStagesOp = 3;
+constexpr int kFRawBytes = 32 * kPanelRows * 4;                  // 32 feature rows x 128 envs x 4 B = 16 KB
+constexpr int kFOpBytes = kABlockBytes + 2 * 4 * 256 * 16;       // A block 16 KB + B block [chunk][hi|lo][256 rows][16 B] 32 KB
+constexpr int kFThreads = 640;
+constexpr int kFConvWarp0 = 12, kFConvWarps = 8, kFEpiWarp0 = 4, kFEpiWarps = 8;
+constexpr int kFSmemBytes = kFStagesRaw * kFRawBytes + kFStagesOp * kFOpBytes + 256 * 4 + 256 /*barriers*/ + 1024 /*align*/;
+
+struct FProjArgs {
+  const float* soa;        // [T][F][ld]
+  const float* cinert;     // [T][240][ld] or nullptr
+  const float* cvel;       // [T][144][ld]
+  int F, kb, H;
+  int64_t ld, n, n_pad, T;
+  const char* w_sb;        // [kb] x 32 KB blocks, WB layout, 256 columns
+  const float* bias;       // [256]
+  char* x_sb;              // out [T] x sbb
+  size_t sbb;
+  int items;               // T * n_pad / 128
+  int dbg;                 // profiling only (KBS_FPROJ_DBG): 1 converters skip load + split, 2 no MMAs, 4 no raw copies,
+                           // 8 no epilogue stores, 16 raw rows by cp.async (64 threads x 16 B) instead of cp.async.bulk
+  long long* trace;        // per CTA [16] at trace + (148 + blockIdx.x) * 16: total cycles, items, then wait cycles of
+                           // raw producer (raw_empty), weight producer (empty), converter warp 12 (raw_full, empty),
+                           // issuer (full, acc_empty), epilogue warp 4 (acc_full)
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __grid_constant__ FProjArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* raw = smem;
+  uint8_t* op = smem + kFStagesRaw * kFRawBytes;
+  float* bias_s = reinterpret_cast<float*>(op + kFStagesOp * kFOpBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 256);
+  uint64_t* raw_full = bars;                       // [kFStagesRaw] feature rows landed
+  uint64_t* raw_empty = raw_full + kFStagesRaw;    // [kFStagesRaw] converters have the values in registers
+  uint64_t* full = raw_empty + kFStagesRaw;        // [kFStagesOp]  A block written + W block landed
+  uint64_t* empty = full + kFStagesOp;             // [kFStagesOp]  MMAs have read the stage
+  uint64_t* acc_full = empty + kFStagesOp;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  constexpr int kE = kbs_chunk_elems(KIND), kFeat = 4 * kE;      // features per 16-byte chunk / per K block
+  constexpr int kBlk = kbs_block_k(KIND);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ppt = int(a.n_pad / kPanelRows);                     // panels per step
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFStagesRaw; ++s) { mbar_init(&raw_full[s], (a.dbg & 16) ? 64 : 3); mbar_init(&raw_empty[s], kFConvWarps); }
+    for (int s = 0; s < kFStagesOp; ++s) { mbar_init(&full[s], 1 + kFConvWarps); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, kFEpiWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long* tr = a.trace ? a.trace + size_t(148 + blockIdx.x) * 16 : nullptr;
+  const long long t_start = clock64();
+#define FTR_WAIT(slot, stmt) do { if (tr) { const long long w0_ = clock64(); stmt; tw[slot] += clock64() - w0_; } else { stmt; } } while (0)
+  long long tw[2] = {0, 0};
+
+  if (!(a.dbg & 16) && warp >= 1 && warp <= 3) {
+    // ===== raw producers (default): the 32 feature rows of a K block as 512-byte cp.async.bulk copies, spread over THREE
+    // warps (copy ci -> warp 1 + ci % 3, lane ci / 3).  MEASURED (tools/fproj_probe.py): the 32 copies issued by the lanes
+    // of ONE warp serialise at ~78 cycles each = 2.5 K cycles per stage, three times the stage's MMA time.  Each warp
+    // posts its own expect_tx arrival (raw_full counts 3).  Warp 3's lane 31 also issues the stage's 32 KB weight block
+    // (after the raw copies: it may block on the operand ring, which only happens when the MMAs are behind). =====
+    const int pw = warp - 1;
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
+      const int64_t t = item / ppt, e0 = int64_t(item % ppt) * kPanelRows;
+      const int64_t left = a.ld - e0;
+      const uint32_t vb = uint32_t(left < kPanelRows ? left : kPanelRows) * 4u;      // bytes of one feature row in this panel
+      for (int b = 0; b < a.kb; ++b, ++g) {
+        const int sr = g % kFStagesRaw;
+        const int nvalid = (a.F - b * kFeat) < kFeat ? (a.F - b * kFeat) : kFeat;    // feature rows of this block
+        const int mine = nvalid > pw ? (nvalid - pw + 2) / 3 : 0;                    // copies ci = pw, pw + 3, ... < nvalid
+        if (lane == 0) {
+          FTR_WAIT(0, mbar_wait(&raw_empty[sr], ((g / kFStagesRaw) & 1) ^ 1));
+          mbar_expect_tx(&raw_full[sr], (a.dbg & 4) ? 0u : uint32_t(mine) * vb);
+        }
+        __syncwarp();
+        const int ci = pw + 3 * lane, f = b * kFeat + ci;
+        if (lane < mine && !(a.dbg & 4)) {
+          const float* src;
+          if (a.cinert && f >= 80 && f < 448) {
+            const int c = f - 80;
+            src = c < 230 ? a.cinert + (t * (10 * KBS_NBODY) + 10 + c) * a.ld : a.cvel + (t * (6 * KBS_NBODY) + 6 + (c - 230)) * a.ld;
+          } else {
+            src = a.soa + (t * a.F + f) * a.ld;
+          }
+          bulk_g2s(raw + size_t(sr) * kFRawBytes + size_t(ci) * (kPanelRows * 4), src + e0, vb, &raw_full[sr]);
+        }
+        if (warp == 3 && lane == 31) {
+          const int s = g % kFStagesOp;
+          FTR_WAIT(1, mbar_wait(&empty[s], ((g / kFStagesOp) & 1) ^ 1));
+          mbar_expect_tx(&full[s], uint32_t(kFOpBytes - kABlockBytes));
+          bulk_g2s(op + size_t(s) * kFOpBytes + kABlockBytes, a.w_sb + size_t(b) * (kFOpBytes - kABlockBytes),
+                   uint32_t(kFOpBytes - kABlockBytes), &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    if (tr && warp == 1 && lane == 0) tr[2] = tw[0];
+    if (tr && warp == 3 && lane == 31) tr[3] = tw[1];
+  } else if (warp == 1 || warp == 3) {
+    // ===== raw producers, cp.async variant (dbg 16; MEASURED slower: 686 vs 556 us per launch): 64 threads x 16 cp.async
+    // (LDGSTS, 16 B) per stage; a warp instruction = the 512 bytes of one feature row of the panel; completion is tracked
+    // by the stage's mbarrier (cp.async.mbarrier.arrive.noinc: one arrival per producer thread). =====
+    const int pw = warp >> 1;                                     // 0, 1
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
+      const int64_t t = item / ppt, e0 = int64_t(item % ppt) * kPanelRows;
+      const bool in_row = e0 + lane * 4 < a.ld;                   // ld % 4 == 0: a 16-byte piece is inside the row or not at all
+      for (int b = 0; b < a.kb; ++b, ++g) {
+        const int sr = g % kFStagesRaw;
+        if (lane == 0) mbar_wait(&raw_empty[sr], ((g / kFStagesRaw) & 1) ^ 1);
+        __syncwarp();
+        const uint32_t dst0 = smem_u32(raw + size_t(sr) * kFRawBytes) + uint32_t(lane) * 16u;
+#pragma unroll 4
+        for (int i = 0; i < kFeat / 2; ++i) {
+          const int fl = pw + 2 * i, f = b * kFeat + fl;
+          const float* src = a.soa;
+          uint32_t nbytes = 0;
+          if (f < a.F && in_row) {
+            if (a.cinert && f >= 80 && f < 448) {
+              const int c = f - 80;
+              src = c < 230 ? a.cinert + (t * (10 * KBS_NBODY) + 10 + c) * a.ld : a.cvel + (t * (6 * KBS_NBODY) + 6 + (c - 230)) * a.ld;
+            } else {
+              src = a.soa + (t * a.F + f) * a.ld;
+            }
+            src += e0 + lane * 4;
+            nbytes = 16;
+          }
+          if (!(a.dbg & 4))
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + uint32_t(fl) * (kPanelRows * 4)), "l"(src),
+                       "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[sr])) : "memory");
+      }
+    }
+  } else if (warp == 2) {
+    // ===== weight producer (cp.async variant only; by default warp 3's lane 31 does it) =====
+    if (lane == 0 && (a.dbg & 16)) {
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
+        for (int b = 0; b < a.kb; ++b, ++g) {
+          const int s = g % kFStagesOp;
+          FTR_WAIT(0, mbar_wait(&empty[s], ((g / kFStagesOp) & 1) ^ 1));
+          mbar_expect_tx(&full[s], uint32_t(kFOpBytes - kABlockBytes));
+          bulk_g2s(op + size_t(s) * kFOpBytes + kABlockBytes, a.w_sb + size_t(b) * (kFOpBytes - kABlockBytes),
+                   uint32_t(kFOpBytes - kABlockBytes), &full[s]);
+        }
+      }
+      if (tr) tr[3] = tw[0];
+    }
+    __syncwarp();
+  } else if (warp >= kFConvWarp0 && warp < kFConvWarp0 + kFConvWarps) {
+    // ===== converters: 8 warps; thread = (env row of the panel, half of the block's 4 chunks).  MEASURED: with 4 warps doing
+    // whole rows the converters were busy 81 % of the kernel (~1.4 K cycles per stage against 880 of MMA work). =====
+    const int cw = warp - kFConvWarp0;
+    const int r = (cw & 3) * 32 + lane, ch0 = (cw >> 2) * 2;         // chunks ch0, ch0 + 1
+    constexpr int kHalf = kFeat / 2;
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
+      const int64_t e0 = int64_t(item % ppt) * kPanelRows;
+      const bool valid = e0 + r < a.n;
+      for (int b = 0; b < a.kb; ++b, ++g) {
+        const int sr = g % kFStagesRaw, s = g % kFStagesOp;
+        FTR_WAIT(0, mbar_wait(&raw_full[sr], (g / kFStagesRaw) & 1));
+        const float* rf = reinterpret_cast<const float*>(raw + size_t(sr) * kFRawBytes) + (ch0 * kE) * kPanelRows + r;
+        const int f0 = b * kFeat + ch0 * kE;
+        float x[kHalf];
+#pragma unroll
+        for (int i = 0; i < kHalf; ++i) x[i] = (valid && f0 + i < a.F && !(a.dbg & 1)) ? rf[i * kPanelRows] : 0.0f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[sr]);
+        FTR_WAIT(1, mbar_wait(&empty[s], ((g / kFStagesOp) & 1) ^ 1));
+        uint8_t* sa = op + size_t(s) * kFOpBytes;
+        if (!(a.dbg & 1))
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {                        // chunk ch0 + c of the block: [part][chunk][row][16 B]
+          uint4 hi, lo;
+          if (KIND == KBS_KIND_F16) {
+            const float x0[4] = {x[(8 * c) % kHalf], x[(8 * c + 1) % kHalf], x[(8 * c + 2) % kHalf], x[(8 * c + 3) % kHalf]};
+            const float x1[4] = {x[(8 * c + 4) % kHalf], x[(8 * c + 5) % kHalf], x[(8 * c + 6) % kHalf], x[(8 * c + 7) % kHalf]};
+            const KbsSplit4 s0 = sb_split4<KIND>(x0), s1 = sb_split4<KIND>(x1);
+            hi = make_uint4(s0.hi.x, s0.hi.y, s1.hi.x, s1.hi.y);
+            lo = make_uint4(s0.lo.x, s0.lo.y, s1.lo.x, s1.lo.y);
+          } else {
+            const float x0[4] = {x[(4 * c) % kHalf], x[(4 * c + 1) % kHalf], x[(4 * c + 2) % kHalf], x[(4 * c + 3) % kHalf]};
+            const KbsSplit4 s0 = sb_split4<KIND>(x0);
+            hi = s0.hi; lo = s0.lo;
+          }
+          *reinterpret_cast<uint4*>(sa + (ch0 + c) * 2048 + r * 16) = hi;
+          *reinterpret_cast<uint4*>(sa + 8192 + (ch0 + c) * 2048 + r * 16) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+    }
+    if (tr && warp == kFConvWarp0 && lane == 0) { tr[4] = tw[0]; tr[5] = tw[1]; }
+  } else if (warp == 0) {
+    // ===== MMA issuer =====
+    uint32_t g = 0;
+    int j = 0;
+    for (int item = blockIdx.x; item < a.items; item += gridDim.x, ++j) {
+      FTR_WAIT(1, mbar_wait(acc_empty, (j & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t d_main = tmem_base, d_corr = tmem_base + 256;
+      for (int b = 0; b < a.kb; ++b, ++g) {
+        const int s = g % kFStagesOp;
+        FTR_WAIT(0, mbar_wait(&full[s], (g / kFStagesOp) & 1));
+        tc_fence_after();
+        const uint32_t sa = smem_u32(op + size_t(s) * kFOpBytes);
+        const uint64_t a_hi = umma_desc(sa, 2048, 128), a_lo = a_hi + (8192 >> 4);
+        const uint64_t b_hi = umma_desc(sa + kABlockBytes, 8192, 128), b_lo = b_hi + (4096 >> 4);
+        constexpr uint64_t kAStep = 4096 >> 4, kBStep = 16384 >> 4;
+        if (elect_one()) {
+          const uint32_t acc = b != 0;
+          if (!(a.dbg & 2)) {
+          umma<KIND, 256>(d_main, a_hi, b_hi, acc);
+          umma<KIND, 256>(d_corr, a_lo, b_hi, acc);
+          umma<KIND, 256>(d_corr, a_hi, b_lo, 1);
+          umma<KIND, 256>(d_main, a_hi + kAStep, b_hi + kBStep, 1);
+          umma<KIND, 256>(d_corr, a_lo + kAStep, b_hi + kBStep, 1);
+          umma<KIND, 256>(d_corr, a_hi + kAStep, b_lo + kBStep, 1);
+          }
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
+    }
+    if (tr && lane == 0) { tr[6] = tw[0]; tr[7] = tw[1]; tr[1] = j; }
+  } else if (warp >= kFEpiWarp0 && warp < kFEpiWarp0 + kFEpiWarps) {
+    // ===== epilogue: warp % 4 = TMEM lane quarter, (warp - 4) / 4 = which 128 of the 256 output columns =====
+    const int et = threadIdx.x - 32 * kFEpiWarp0;
+    bias_s[et] = a.bias[et];
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kFEpiWarps) : "memory");
+    const int q4 = warp & 3, half = (warp - kFEpiWarp0) >> 2;
+    const int r = q4 * 32 + lane;
+    constexpr float kCorr = (KIND == KBS_KIND_F16) ? (1.0f / kKbsF16LoScale) : 1.0f;
+    int j = 0;
+    for (int item = blockIdx.x; item < a.items; item += gridDim.x, ++j) {
+      const int64_t t = item / ppt, R = int64_t(item % ppt) * kPanelRows + r;
+      char* xo = a.x_sb + size_t(t) * a.sbb;
+      FTR_WAIT(0, mbar_wait(acc_full, j & 1));
+      tc_fence_after();
+      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(half * 128);
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        float v[16], cr[16];
+        tmem_ld16(tq + cc * 16, v);
+        tmem_ld16(tq + 256 + cc * 16, cr);
+        tmem_ld_wait();
+        const float* bs = bias_s + half * 128 + cc * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (v[i] + kCorr * cr[i]) + bs[i];
+#pragma unroll
+        for (int c8 = 0; c8 < 2; ++c8) {
+          const float x0[4] = {v[8 * c8], v[8 * c8 + 1], v[8 * c8 + 2], v[8 * c8 + 3]};
+          const float x1[4] = {v[8 * c8 + 4], v[8 * c8 + 5], v[8 * c8 + 6], v[8 * c8 + 7]};
+          if (!(a.dbg & 8))
+          sb_store_split8<kPanelRows, KIND>(xo, R, half * 128 + cc * 16 + c8 * 8, a.H / kBlk, sb_split4<KIND>(x0), sb_split4<KIND>(x1),
+                                            false);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+    if (tr && warp == kFEpiWarp0 && lane == 0) tr[8] = tw[0];
+  }
+#undef FTR_WAIT
+  tc_fence_before();
+  __syncthreads();
+  if (tr && threadIdx.x == 0) tr[0] = clock64() - t_start;
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
 // ---- packing kernels ------------------------------------------------------------------------------------------------
 // eqx LSTMCell weights [4H][H] x2 + bias [4H]  ->  gate-interleaved SB tiles (hi/lo) + interleaved bias.
 // tile j (128 columns = 32 hidden units), column c = half * 64 + gate * 16 + uu  ->  unit = 32 j + 16 half + uu:
@@ -1272,7 +1574,7 @@ fuse_input_weights_kernel(const float* __restrict__ w_ih, const float* __restric
 }
 
 // eqx Linear weight [H][ldw] (K zero-padded to ldw) -> ceil(H/128) SB tiles of 128 plain columns (rows >= H zero), K padded to Kp.
-template <int KIND>
+template <int KIND, int TILE = kTileCols>
 __global__ void __launch_bounds__(256)
 pack_proj_weights_kernel(const float* __restrict__ w, int ldw, const float* __restrict__ b, char* __restrict__ w_sb,
                          float* __restrict__ bias_t, int H, int Kp, int cols) {
@@ -1285,7 +1587,7 @@ pack_proj_weights_kernel(const float* __restrict__ w, int ldw, const float* __re
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = (k + i < ldw) ? w[size_t(col) * ldw + k + i] : 0.0f;
   }
-  sb_store4<kTileCols, KIND, true>(w_sb, col, k, Kp / kbs_block_k(KIND), x);
+  sb_store4<TILE, KIND, true>(w_sb, col, k, Kp / kbs_block_k(KIND), x);
   if (k == 0) bias_t[col] = col < H ? b[col] : 0.0f;
 }
 
@@ -1548,6 +1850,17 @@ static inline char* fused_w(const kbs_handle* h, int net) { return reinterpret_c
 static inline float* fused_bias(const kbs_handle* h, int net) {
   return reinterpret_cast<float*>(fused_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), 4 * h->p.hidden_size, fused_kp(h, net) + h->p.hidden_size));
 }
+// Image Q: W_in as ONE 256-column tile for input_proj_fused_kernel (H == 256 only): [w_sb (256 x Kp SB, WB layout) | bias (256)]
+static inline bool projq_shape(const kbs_handle* h) { return h->p.hidden_size == 256; }
+static size_t projq_image_bytes(const kbs_handle* h, int net) {
+  return projq_shape(h) ? kbs_sb_bytes_kind(tc_kind(h), 256, proj_kp(h, net)) + size_t(256) * 4 : 0;
+}
+static inline char* projq_w(const kbs_handle* h, int net) {
+  return reinterpret_cast<char*>(fused_wf(h, net)) + fused_image_bytes(h, net);
+}
+static inline float* projq_bias(const kbs_handle* h, int net) {
+  return reinterpret_cast<float*>(projq_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), 256, proj_kp(h, net)));
+}
 static inline bool persist_shape_ok(const kbs_handle* h) {
   const int H = h->p.hidden_size;
   return H % kUnitsPerTileP == 0 && h->p.depth <= kPMaxDepth && H <= kMaxBias / 4 &&
@@ -1564,10 +1877,12 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
     KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_tc_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
     KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
+    KBS_CUDA_TRY(cudaFuncSetAttribute(input_proj_fused_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
+    KBS_CUDA_TRY(cudaFuncSetAttribute(input_proj_fused_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
     attr_set = true;
   }
   const size_t bytes = 2 * layer_image_bytes(h) * h->p.depth + proj_image_bytes(h, net) + head_image_bytes(h) +
-                       fused_image_bytes(h, net);
+                       fused_image_bytes(h, net) + projq_image_bytes(h, net);
   N.tc_image_floats = (bytes + 3) / 4;
   if (!N.tc_image) KBS_CUDA_TRY(cudaMalloc(&N.tc_image, bytes));      // fixed size per handle: re-packs keep the pointer
   for (int l = 0; l < h->p.depth; ++l) {
@@ -1598,6 +1913,17 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
     else
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
                                         N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp, cols)));
+  }
+  if (projq_shape(h)) {   // W_in as one 256-column tile (input_proj_fused_kernel)
+    const int Kp = proj_kp(h, net);
+    const int64_t total = int64_t(256) * (Kp / 4);
+    const unsigned gb = unsigned((total + 255) / 256);
+    if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_TF32, 256><<<gb, 256, 0, st>>>(
+                                        N.w_in, N.kin_pad, N.b_in, projq_w(h, net), projq_bias(h, net), H, Kp, 256)));
+    else
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_F16, 256><<<gb, 256, 0, st>>>(
+                                        N.w_in, N.kin_pad, N.b_in, projq_w(h, net), projq_bias(h, net), H, Kp, 256)));
   }
   if (persist_shape_ok(h) && fused_shape(h, net)) {   // layer 0 with the input projection folded in
     const int Kf = fused_kp(h, net);
@@ -1888,6 +2214,25 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
     char* osb = reinterpret_cast<char*>(obs_sb[k]);
     LayerArgs& a = a2.net[k];
     if (r_out) { r_out->x_sb_all[k] = fuse ? obs_sb[k] : x_sb_all[k]; r_out->x_is_obs[k] = fuse; }
+    const char* staged_env = getenv("KBS_PROJ_STAGED");            // A/B + cross-check: pack kernel + MODE_PROJ launch
+    if (!fuse && staged && projq_shape(h) && !(staged_env && atoi(staged_env))) {
+      // straight from the SoA observations (input_proj_fused_kernel): no staging buffer, one launch per net
+      FProjArgs fa{};
+      fa.soa = obs_soa[k]; fa.cinert = ci; fa.cvel = cv;
+      fa.F = N.num_in; fa.kb = Kp / kbs_block_k(kind); fa.H = H;
+      fa.ld = ld; fa.n = n; fa.n_pad = np; fa.T = T;
+      fa.w_sb = projq_w(h, k); fa.bias = projq_bias(h, k);
+      fa.x_sb = reinterpret_cast<char*>(x_sb_all[k]); fa.sbb = act_sb_bytes(h, n);
+      fa.items = int(T * np / kPanelRows);
+      { const char* e = getenv("KBS_FPROJ_DBG"); fa.dbg = e ? atoi(e) : 0; }
+      fa.trace = h->trace_buf;
+      const unsigned grid = unsigned(fa.items < h->num_sms ? fa.items : h->num_sms);
+      if (kind == KBS_KIND_TF32)
+        KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (input_proj_fused_kernel<KBS_KIND_TF32><<<grid, kFThreads, kFSmemBytes, st>>>(fa)));
+      else
+        KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (input_proj_fused_kernel<KBS_KIND_F16><<<grid, kFThreads, kFSmemBytes, st>>>(fa)));
+      continue;                       // no MODE_PROJ items for this net (panels = 0)
+    }
     if (staged || fuse) {
       const int64_t total = T * np * (Kp / 8);
       const unsigned gb = unsigned((total + 255) / 256);

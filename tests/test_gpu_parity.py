@@ -496,13 +496,37 @@ def test_rollout_folded_input_projection_vs_projection_launch(dev, T, N, monkeyp
         outs.append((io, prof))
         e.close()
     (a, pa), (c, pc) = outs
-    assert pa["proj_tc_kernel"][1] == pc["proj_tc_kernel"][1] == 1      # critic projection stays a launch in both
+    assert pa["proj_tc_kernel"][1] == 1 and pc["proj_tc_kernel"][1] == 2   # critic: a launch in both; actor: only unfolded
     close(a["actor_carry"].cpu().numpy(), c["actor_carry"].cpu().numpy(), "actor carry", atol=2e-6)
     assert torch.equal(a["critic_carry"], c["critic_carry"])            # the critic's datapath is untouched
     close(S(a["action"], N, (20,)), S(c["action"], N, (20,)), "action")
     close(S(a["log_prob"], N), S(c["log_prob"], N), "log_prob", atol=1e-5)
     close(S(a["ctrl"], N, (20,)), S(c["ctrl"], N, (20,)), "ctrl", atol=1e-4)
     close(S(a["lpf"], N, (20,)), S(c["lpf"], N, (20,)), "lpf")
+
+
+@pytest.mark.parametrize("T,N", [(20, 4096), (3, 200)])
+def test_rollout_input_projection_from_soa_vs_staged(dev, T, N, monkeypatch):
+    """input_proj_fused_kernel (feature rows bulk-copied straight from the env-major observations / the recorded cinert /
+    cvel arrays, converted to the MMA operand in shared memory, 256-column tile) against the staged form (pack kernel ->
+    SB buffer -> 128-column MODE_PROJ launch): same products, different accumulator tiling -> rounding-level agreement."""
+    b = Batch(778, T, N, dev)
+    outs = []
+    for staged in ("0", "1"):
+        monkeypatch.setenv("KBS_PROJ_STAGED", staged)
+        e, _, _ = Hn.make_engine(gemm_path=L.GEMM_TC_2XF16, device=dev)
+        io = Hn.rollout_buffers(b, 256, 2)
+        l0 = e.launches
+        e.rollout(io, N)
+        torch.cuda.synchronize()
+        assert e.device_status() == 0
+        outs.append((io, e.launches - l0))
+        e.close()
+    (a, la), (c, lc) = outs
+    assert lc == la + 1, (la, lc)                                       # the critic's pack launch is gone
+    assert torch.equal(a["actor_carry"], c["actor_carry"])              # the actor's datapath is untouched
+    close(a["critic_carry"].cpu().numpy(), c["critic_carry"].cpu().numpy(), "critic carry", atol=2e-6)
+    close(S(a["value"], N), S(c["value"], N), "value", atol=1e-5)
 
 
 def test_upload_state_moves_every_row_the_path_reads(dev):
