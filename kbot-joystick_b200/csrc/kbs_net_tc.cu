@@ -17,6 +17,7 @@
 // cp.async.bulk per operand per stage lands it in shared memory ready for the tensor core, no tensor map needed.
 // Weights are packed once (kbs_weights_pack); activations are written in SB form by the producing epilogue.
 #include <math.h>
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "kbs_common.cuh"
@@ -1228,10 +1229,9 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
 // pack_soa_sb_kernel (read 1.9 KB + write 1.9 KB per critic row) followed by the MODE_PROJ launch (read it again, 128-column
 // tiles: two items per panel) cost 0.33 + 0.33 ms per 4 096 x 100 rollout for ~0.2 ms of HBM traffic.  Here one CTA per SM
 // walks the 128-row panels; per K block (32 features; 16 for TF32):
-//   warps 1, 3  raw producers: cp.async (16 B per thread, a warp instruction = the 512 bytes of one feature row of the panel's
-//             128 envs; features 80..447 of the critic come straight from the recorded cinert / cvel arrays,
-//             train.py:1405-1413), 4-deep ring: ~48 KB of HBM reads in flight per SM (the register-staged MODE_PROJ_SOA
-//             had ~16 KB: 4x slower);
+//   warp 1    raw producer: one 2-D TMA tensor request per stage = 32 feature rows x 128 envs (features 80..447 of the
+//             critic come straight from the recorded cinert / cvel arrays, train.py:1405-1413), 4-deep ring: ~48 KB of HBM
+//             reads in flight per SM (the register-staged MODE_PROJ_SOA had ~16 KB: 4x slower);
 //   warp 2    weight producer: the 32 KB W_in block (one 256-column tile = all H outputs, L2-resident) into the operand ring;
 //   warps 12-19  converters: thread = (env row, half of the K block); 16 floats from the raw stage (conflict-free column
 //             reads) -> hi / lo split -> two chunks of the A block in UMMA layout -> fence.proxy.async -> arrive;
@@ -1245,19 +1245,28 @@ constexpr int kFThreads = 640;
 constexpr int kFConvWarp0 = 12, kFConvWarps = 8, kFEpiWarp0 = 4, kFEpiWarps = 8;
 constexpr int kFSmemBytes = kFStagesRaw * kFRawBytes + kFStagesOp * kFOpBytes + 256 * 4 + 256 /*barriers*/ + 1024 /*align*/;
 
+constexpr int kFMaxBlocks = 32;
 struct FProjArgs {
-  const float* soa;        // [T][F][ld]
-  const float* cinert;     // [T][240][ld] or nullptr
-  const float* cvel;       // [T][144][ld]
-  int F, kb, H;
-  int64_t ld, n, n_pad, T;
+  // K blocks of the projection in the order the kernel walks them: block b = kFeat consecutive feature ROWS of one source
+  // array starting at blk_row0[b] (within a step), the first blk_nvalid[b] of them real (the rest -- the unwritten dump
+  // slots of the critic's SoA buffer, rows of the next step, rows past the array -- are masked to zero by the converters
+  // and meet zero weights).  Sources: 0 = observations [T][F][ld], 1 = cinert [T][240][ld], 2 = cvel [T][144][ld]
+  // (features 80..447 of the critic are cinert[1:] | cvel[1:], train.py:1405-1413).  The weight tile is packed in the same
+  // K order (pack_proj_weights_kmap_kernel).
+  CUtensorMap tmap[3];     // 2-D {ld envs, T * rows per step} fp32, box {128 envs, kFeat rows}
+  int rows_per_step[3];
+  signed char blk_src[kFMaxBlocks];
+  short blk_row0[kFMaxBlocks];
+  short blk_nvalid[kFMaxBlocks];
+  int kb, H;
+  int64_t n, n_pad;
   const char* w_sb;        // [kb] x 32 KB blocks, WB layout, 256 columns
   const float* bias;       // [256]
   char* x_sb;              // out [T] x sbb
   size_t sbb;
   int items;               // T * n_pad / 128
   int dbg;                 // profiling only (KBS_FPROJ_DBG): 1 converters skip load + split, 2 no MMAs, 4 no raw copies,
-                           // 8 no epilogue stores, 16 raw rows by cp.async (64 threads x 16 B) instead of cp.async.bulk
+                           // 8 no epilogue stores
   long long* trace;        // per CTA [16] at trace + (148 + blockIdx.x) * 16: total cycles, items, then wait cycles of
                            // raw producer (raw_empty), weight producer (empty), converter warp 12 (raw_full, empty),
                            // issuer (full, acc_empty), epilogue warp 4 (acc_full)
@@ -1285,7 +1294,7 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
   const int ppt = int(a.n_pad / kPanelRows);                     // panels per step
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFStagesRaw; ++s) { mbar_init(&raw_full[s], (a.dbg & 16) ? 64 : 3); mbar_init(&raw_empty[s], kFConvWarps); }
+    for (int s = 0; s < kFStagesRaw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kFConvWarps); }
     for (int s = 0; s < kFStagesOp; ++s) { mbar_init(&full[s], 1 + kFConvWarps); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1); mbar_init(acc_empty, kFEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1303,89 +1312,37 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
 #define FTR_WAIT(slot, stmt) do { if (tr) { const long long w0_ = clock64(); stmt; tw[slot] += clock64() - w0_; } else { stmt; } } while (0)
   long long tw[2] = {0, 0};
 
-  if (!(a.dbg & 16) && warp >= 1 && warp <= 3) {
-    // ===== raw producers (default): the 32 feature rows of a K block as 512-byte cp.async.bulk copies, spread over THREE
-    // warps (copy ci -> warp 1 + ci % 3, lane ci / 3).  MEASURED (tools/fproj_probe.py): the 32 copies issued by the lanes
-    // of ONE warp serialise at ~78 cycles each = 2.5 K cycles per stage, three times the stage's MMA time.  Each warp
-    // posts its own expect_tx arrival (raw_full counts 3).  Warp 3's lane 31 also issues the stage's 32 KB weight block
-    // (after the raw copies: it may block on the operand ring, which only happens when the MMAs are behind). =====
-    const int pw = warp - 1;
-    uint32_t g = 0;
-    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-      const int64_t t = item / ppt, e0 = int64_t(item % ppt) * kPanelRows;
-      const int64_t left = a.ld - e0;
-      const uint32_t vb = uint32_t(left < kPanelRows ? left : kPanelRows) * 4u;      // bytes of one feature row in this panel
-      for (int b = 0; b < a.kb; ++b, ++g) {
-        const int sr = g % kFStagesRaw;
-        const int nvalid = (a.F - b * kFeat) < kFeat ? (a.F - b * kFeat) : kFeat;    // feature rows of this block
-        const int mine = nvalid > pw ? (nvalid - pw + 2) / 3 : 0;                    // copies ci = pw, pw + 3, ... < nvalid
-        if (lane == 0) {
+  if (warp == 1) {
+    // ===== raw producer: ONE 2-D TMA request per stage = the block's kFeat feature rows x the panel's 128 envs (16 KB,
+    // box rows land as [feature][env] fp32).  MEASURED (tools/fproj_probe.py): the same rows as 32 separate 512-byte
+    // cp.async.bulk requests cost the SM ~48 cycles each whichever warps issue them = 1.5 K cycles per stage (the MMAs
+    // need 880), and as cp.async (LDGSTS) 16-byte pieces the kernel was slower still.  Out-of-range envs / rows are
+    // zero-filled by the TMA unit, so every stage expects the full box. =====
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
+        const int t = item / ppt, e0 = (item % ppt) * kPanelRows;
+        for (int b = 0; b < a.kb; ++b, ++g) {
+          const int sr = g % kFStagesRaw;
+          const int src = a.blk_src[b];
           FTR_WAIT(0, mbar_wait(&raw_empty[sr], ((g / kFStagesRaw) & 1) ^ 1));
-          mbar_expect_tx(&raw_full[sr], (a.dbg & 4) ? 0u : uint32_t(mine) * vb);
-        }
-        __syncwarp();
-        const int ci = pw + 3 * lane, f = b * kFeat + ci;
-        if (lane < mine && !(a.dbg & 4)) {
-          const float* src;
-          if (a.cinert && f >= 80 && f < 448) {
-            const int c = f - 80;
-            src = c < 230 ? a.cinert + (t * (10 * KBS_NBODY) + 10 + c) * a.ld : a.cvel + (t * (6 * KBS_NBODY) + 6 + (c - 230)) * a.ld;
-          } else {
-            src = a.soa + (t * a.F + f) * a.ld;
+          mbar_expect_tx(&raw_full[sr], (a.dbg & 4) ? 0u : uint32_t(kFeat * kPanelRows * 4));
+          if (!(a.dbg & 4)) {
+            const int c1 = t * a.rows_per_step[src] + a.blk_row0[b];
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                    smem_u32(raw + size_t(sr) * kFRawBytes)),
+                "l"(reinterpret_cast<uint64_t>(&a.tmap[src])), "r"(e0), "r"(c1), "r"(smem_u32(&raw_full[sr]))
+                : "memory");
           }
-          bulk_g2s(raw + size_t(sr) * kFRawBytes + size_t(ci) * (kPanelRows * 4), src + e0, vb, &raw_full[sr]);
         }
-        if (warp == 3 && lane == 31) {
-          const int s = g % kFStagesOp;
-          FTR_WAIT(1, mbar_wait(&empty[s], ((g / kFStagesOp) & 1) ^ 1));
-          mbar_expect_tx(&full[s], uint32_t(kFOpBytes - kABlockBytes));
-          bulk_g2s(op + size_t(s) * kFOpBytes + kABlockBytes, a.w_sb + size_t(b) * (kFOpBytes - kABlockBytes),
-                   uint32_t(kFOpBytes - kABlockBytes), &full[s]);
-        }
-        __syncwarp();
       }
+      if (tr) tr[2] = tw[0];
     }
-    if (tr && warp == 1 && lane == 0) tr[2] = tw[0];
-    if (tr && warp == 3 && lane == 31) tr[3] = tw[1];
-  } else if (warp == 1 || warp == 3) {
-    // ===== raw producers, cp.async variant (dbg 16; MEASURED slower: 686 vs 556 us per launch): 64 threads x 16 cp.async
-    // (LDGSTS, 16 B) per stage; a warp instruction = the 512 bytes of one feature row of the panel; completion is tracked
-    // by the stage's mbarrier (cp.async.mbarrier.arrive.noinc: one arrival per producer thread). =====
-    const int pw = warp >> 1;                                     // 0, 1
-    uint32_t g = 0;
-    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-      const int64_t t = item / ppt, e0 = int64_t(item % ppt) * kPanelRows;
-      const bool in_row = e0 + lane * 4 < a.ld;                   // ld % 4 == 0: a 16-byte piece is inside the row or not at all
-      for (int b = 0; b < a.kb; ++b, ++g) {
-        const int sr = g % kFStagesRaw;
-        if (lane == 0) mbar_wait(&raw_empty[sr], ((g / kFStagesRaw) & 1) ^ 1);
-        __syncwarp();
-        const uint32_t dst0 = smem_u32(raw + size_t(sr) * kFRawBytes) + uint32_t(lane) * 16u;
-#pragma unroll 4
-        for (int i = 0; i < kFeat / 2; ++i) {
-          const int fl = pw + 2 * i, f = b * kFeat + fl;
-          const float* src = a.soa;
-          uint32_t nbytes = 0;
-          if (f < a.F && in_row) {
-            if (a.cinert && f >= 80 && f < 448) {
-              const int c = f - 80;
-              src = c < 230 ? a.cinert + (t * (10 * KBS_NBODY) + 10 + c) * a.ld : a.cvel + (t * (6 * KBS_NBODY) + 6 + (c - 230)) * a.ld;
-            } else {
-              src = a.soa + (t * a.F + f) * a.ld;
-            }
-            src += e0 + lane * 4;
-            nbytes = 16;
-          }
-          if (!(a.dbg & 4))
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + uint32_t(fl) * (kPanelRows * 4)), "l"(src),
-                       "r"(nbytes) : "memory");
-        }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[sr])) : "memory");
-      }
-    }
+    __syncwarp();
   } else if (warp == 2) {
-    // ===== weight producer (cp.async variant only; by default warp 3's lane 31 does it) =====
-    if (lane == 0 && (a.dbg & 16)) {
+    // ===== weight producer =====
+    if (lane == 0) {
       uint32_t g = 0;
       for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
         for (int b = 0; b < a.kb; ++b, ++g) {
@@ -1413,10 +1370,10 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
         const int sr = g % kFStagesRaw, s = g % kFStagesOp;
         FTR_WAIT(0, mbar_wait(&raw_full[sr], (g / kFStagesRaw) & 1));
         const float* rf = reinterpret_cast<const float*>(raw + size_t(sr) * kFRawBytes) + (ch0 * kE) * kPanelRows + r;
-        const int f0 = b * kFeat + ch0 * kE;
+        const int nv = int(a.blk_nvalid[b]) - ch0 * kE;         // real rows among this thread's kHalf
         float x[kHalf];
 #pragma unroll
-        for (int i = 0; i < kHalf; ++i) x[i] = (valid && f0 + i < a.F && !(a.dbg & 1)) ? rf[i * kPanelRows] : 0.0f;
+        for (int i = 0; i < kHalf; ++i) x[i] = (valid && i < nv && !(a.dbg & 1)) ? rf[i * kPanelRows] : 0.0f;
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[sr]);
         FTR_WAIT(1, mbar_wait(&empty[s], ((g / kFStagesOp) & 1) ^ 1));
@@ -1588,6 +1545,34 @@ pack_proj_weights_kernel(const float* __restrict__ w, int ldw, const float* __re
     for (int i = 0; i < 4; ++i) x[i] = (k + i < ldw) ? w[size_t(col) * ldw + k + i] : 0.0f;
   }
   sb_store4<TILE, KIND, true>(w_sb, col, k, Kp / kbs_block_k(KIND), x);
+  if (k == 0) bias_t[col] = col < H ? b[col] : 0.0f;
+}
+
+// W_in as ONE 256-column tile in the K order input_proj_fused_kernel walks: K index kk = block kk / kf, row j = kk % kf of
+// the block -> eqx input column fbase[block] + j, or a zero weight for a masked row (j >= nvalid[block]).
+struct FPackLayout {
+  int kb;
+  int fbase[kFMaxBlocks];
+  short nvalid[kFMaxBlocks];
+};
+template <int KIND>
+__global__ void __launch_bounds__(256)
+pack_proj_weights_kmap_kernel(const float* __restrict__ w, int ldw, const float* __restrict__ b, const __grid_constant__ FPackLayout L,
+                              char* __restrict__ w_sb, float* __restrict__ bias_t, int H, int Kq) {
+  constexpr int kf = kbs_block_k(KIND);
+  const int kq = Kq / 4;
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= int64_t(256) * kq) return;
+  const int col = int(idx / kq), k = int(idx % kq) * 4;
+  float x[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col < H) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int blk = (k + i) / kf, j = (k + i) % kf;
+      x[i] = j < L.nvalid[blk] ? w[size_t(col) * ldw + L.fbase[blk] + j] : 0.0f;
+    }
+  }
+  sb_store4<256, KIND, true>(w_sb, col, k, Kq / kf, x);
   if (k == 0) bias_t[col] = col < H ? b[col] : 0.0f;
 }
 
@@ -1850,16 +1835,80 @@ static inline char* fused_w(const kbs_handle* h, int net) { return reinterpret_c
 static inline float* fused_bias(const kbs_handle* h, int net) {
   return reinterpret_cast<float*>(fused_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), 4 * h->p.hidden_size, fused_kp(h, net) + h->p.hidden_size));
 }
-// Image Q: W_in as ONE 256-column tile for input_proj_fused_kernel (H == 256 only): [w_sb (256 x Kp SB, WB layout) | bias (256)]
+// Images Q0 / Q1: W_in as ONE 256-column tile for input_proj_fused_kernel (H == 256 only), in the kernel's K-block order.
+//   layout 0 (plain): the net's SoA observation rows 0 .. Kp-1 in order;
+//   layout 1 (critic with the privileged dump read from the recorded state): obs rows 0..79 | cinert rows 10..239 |
+//            cvel rows 6..143 | obs rows 448..474, each region padded to whole K blocks (masked rows, zero weights).
+// Per image: [w_sb (256 x Kq SB, WB layout) | bias (256)].
+struct FLayout {
+  int kb = 0;
+  signed char src[kFMaxBlocks];
+  short row0[kFMaxBlocks], nvalid[kFMaxBlocks];
+  int fbase[kFMaxBlocks];      // eqx input column of the block's first row
+};
 static inline bool projq_shape(const kbs_handle* h) { return h->p.hidden_size == 256; }
+static FLayout projq_layout(const kbs_handle* h, int net, int which) {
+  FLayout L;
+  const int kf = kbs_block_k(tc_kind(h)), F = h->net[net].num_in;
+  auto region = [&](int src, int start, int count, int f_base) {
+    for (int i = 0; i * kf < count; ++i) {
+      const int b = L.kb++;
+      L.src[b] = (signed char)src; L.row0[b] = short(start + i * kf);
+      L.nvalid[b] = short(count - i * kf < kf ? count - i * kf : kf);
+      L.fbase[b] = f_base + i * kf;
+    }
+  };
+  if (which == 1) { region(0, 0, 80, 0); region(1, 10, 230, 80); region(2, 6, 138, 310); region(0, 448, F - 448, 448); }
+  else region(0, 0, F, 0);
+  return L;
+}
+static inline bool projq_has_dump_layout(const kbs_handle* h, int net) { return h->net[net].num_in == KBS_CRITIC_OBS; }
+static inline int projq_kq(const kbs_handle* h, int net, int which) {
+  const int kf = kbs_block_k(tc_kind(h)), F = h->net[net].num_in;
+  auto up = [&](int c) { return (c + kf - 1) / kf * kf; };
+  return which == 1 ? up(80) + up(230) + up(138) + up(F - 448) : up(F);
+}
+static size_t projq_image_bytes1(const kbs_handle* h, int net, int which) {
+  const int Kq = projq_kq(h, net, which);
+  return kbs_sb_bytes_kind(tc_kind(h), 256, Kq) + size_t(256) * 4;
+}
 static size_t projq_image_bytes(const kbs_handle* h, int net) {
-  return projq_shape(h) ? kbs_sb_bytes_kind(tc_kind(h), 256, proj_kp(h, net)) + size_t(256) * 4 : 0;
+  if (!projq_shape(h)) return 0;
+  return projq_image_bytes1(h, net, 0) + (projq_has_dump_layout(h, net) ? projq_image_bytes1(h, net, 1) : 0);
 }
-static inline char* projq_w(const kbs_handle* h, int net) {
-  return reinterpret_cast<char*>(fused_wf(h, net)) + fused_image_bytes(h, net);
+static inline char* projq_w(const kbs_handle* h, int net, int which) {
+  char* base = reinterpret_cast<char*>(fused_wf(h, net)) + fused_image_bytes(h, net);
+  return which ? base + projq_image_bytes1(h, net, 0) : base;
 }
-static inline float* projq_bias(const kbs_handle* h, int net) {
-  return reinterpret_cast<float*>(projq_w(h, net) + kbs_sb_bytes_kind(tc_kind(h), 256, proj_kp(h, net)));
+static inline float* projq_bias(const kbs_handle* h, int net, int which) {
+  return reinterpret_cast<float*>(projq_w(h, net, which) + kbs_sb_bytes_kind(tc_kind(h), 256, projq_kq(h, net, which)));
+}
+
+typedef CUresult (*KbsTensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static KbsTensorMapEncodeFn tensor_map_encode_fn() {
+  static KbsTensorMapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<KbsTensorMapEncodeFn>(p);
+  }
+  return fn;
+}
+// 2-D fp32 tensor {ld envs (inner), rows}, box {128 envs, box_rows}; out-of-range elements read as zero
+static bool encode_rows_map(CUtensorMap* m, const float* base, int64_t ld, int64_t rows, int box_rows) {
+  KbsTensorMapEncodeFn fn = tensor_map_encode_fn();
+  if (!fn || !base) return false;
+  const cuuint64_t gdim[2] = {cuuint64_t(ld), cuuint64_t(rows)};
+  const cuuint64_t gstride[1] = {cuuint64_t(ld) * 4};
+  const cuuint32_t box[2] = {cuuint32_t(kPanelRows), cuuint32_t(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 static inline bool persist_shape_ok(const kbs_handle* h) {
   const int H = h->p.hidden_size;
@@ -1914,16 +1963,22 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
                                         N.w_in, N.kin_pad, N.b_in, proj_w(h, net), proj_bias(h, net), H, Kp, cols)));
   }
-  if (projq_shape(h)) {   // W_in as one 256-column tile (input_proj_fused_kernel)
-    const int Kp = proj_kp(h, net);
-    const int64_t total = int64_t(256) * (Kp / 4);
-    const unsigned gb = unsigned((total + 255) / 256);
-    if (kind == KBS_KIND_TF32)
-      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_TF32, 256><<<gb, 256, 0, st>>>(
-                                        N.w_in, N.kin_pad, N.b_in, projq_w(h, net), projq_bias(h, net), H, Kp, 256)));
-    else
-      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kernel<KBS_KIND_F16, 256><<<gb, 256, 0, st>>>(
-                                        N.w_in, N.kin_pad, N.b_in, projq_w(h, net), projq_bias(h, net), H, Kp, 256)));
+  if (projq_shape(h)) {   // W_in as one 256-column tile in input_proj_fused_kernel's K order (plain and, for the critic, dump layout)
+    for (int which = 0; which < (projq_has_dump_layout(h, net) ? 2 : 1); ++which) {
+      const FLayout L = projq_layout(h, net, which);
+      const int Kq = projq_kq(h, net, which);
+      FPackLayout P{};
+      P.kb = L.kb;
+      for (int b = 0; b < L.kb; ++b) { P.fbase[b] = L.fbase[b]; P.nvalid[b] = L.nvalid[b]; }
+      const int64_t total = int64_t(256) * (Kq / 4);
+      const unsigned gb = unsigned((total + 255) / 256);
+      if (kind == KBS_KIND_TF32)
+        KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kmap_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(
+                                          N.w_in, N.kin_pad, N.b_in, P, projq_w(h, net, which), projq_bias(h, net, which), H, Kq)));
+      else
+        KBS_LAUNCH(h, KBS_K_PACK, st, (pack_proj_weights_kmap_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(
+                                          N.w_in, N.kin_pad, N.b_in, P, projq_w(h, net, which), projq_bias(h, net, which), H, Kq)));
+    }
   }
   if (persist_shape_ok(h) && fused_shape(h, net)) {   // layer 0 with the input projection folded in
     const int Kf = fused_kp(h, net);
@@ -2215,23 +2270,40 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
     LayerArgs& a = a2.net[k];
     if (r_out) { r_out->x_sb_all[k] = fuse ? obs_sb[k] : x_sb_all[k]; r_out->x_is_obs[k] = fuse; }
     const char* staged_env = getenv("KBS_PROJ_STAGED");            // A/B + cross-check: pack kernel + MODE_PROJ launch
-    if (!fuse && staged && projq_shape(h) && !(staged_env && atoi(staged_env))) {
+    // FP16-split datapath only: with 3xTF32 operands (16-row boxes, 31 K blocks) a second engine in the same process gave
+    // run-to-run differences of ~1e-4 in 16 rows of one panel (tools/_dbg_tf32.py) -- not understood yet, so that
+    // datapath keeps the staged form (KBS_FPROJ_TF32=1 enables the kernel for debugging).
+    const char* tf32_env = getenv("KBS_FPROJ_TF32");
+    const bool kind_ok = kind == KBS_KIND_F16 || (tf32_env && atoi(tf32_env));
+    if (!fuse && staged && kind_ok && projq_shape(h) && !(staged_env && atoi(staged_env)) && tensor_map_encode_fn()) {
       // straight from the SoA observations (input_proj_fused_kernel): no staging buffer, one launch per net
+      const int which = (ci && cv && projq_has_dump_layout(h, k)) ? 1 : 0;
+      const FLayout Lq = projq_layout(h, k, which);
       FProjArgs fa{};
-      fa.soa = obs_soa[k]; fa.cinert = ci; fa.cvel = cv;
-      fa.F = N.num_in; fa.kb = Kp / kbs_block_k(kind); fa.H = H;
-      fa.ld = ld; fa.n = n; fa.n_pad = np; fa.T = T;
-      fa.w_sb = projq_w(h, k); fa.bias = projq_bias(h, k);
-      fa.x_sb = reinterpret_cast<char*>(x_sb_all[k]); fa.sbb = act_sb_bytes(h, n);
-      fa.items = int(T * np / kPanelRows);
-      { const char* e = getenv("KBS_FPROJ_DBG"); fa.dbg = e ? atoi(e) : 0; }
-      fa.trace = h->trace_buf;
-      const unsigned grid = unsigned(fa.items < h->num_sms ? fa.items : h->num_sms);
-      if (kind == KBS_KIND_TF32)
-        KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (input_proj_fused_kernel<KBS_KIND_TF32><<<grid, kFThreads, kFSmemBytes, st>>>(fa)));
-      else
-        KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (input_proj_fused_kernel<KBS_KIND_F16><<<grid, kFThreads, kFSmemBytes, st>>>(fa)));
-      continue;                       // no MODE_PROJ items for this net (panels = 0)
+      const int kf = kbs_block_k(kind);
+      bool ok = encode_rows_map(&fa.tmap[0], obs_soa[k], ld, T * int64_t(N.num_in), kf);
+      fa.rows_per_step[0] = N.num_in;
+      if (which == 1) {
+        ok = ok && encode_rows_map(&fa.tmap[1], ci, ld, T * int64_t(10 * KBS_NBODY), kf) &&
+             encode_rows_map(&fa.tmap[2], cv, ld, T * int64_t(6 * KBS_NBODY), kf);
+        fa.rows_per_step[1] = 10 * KBS_NBODY; fa.rows_per_step[2] = 6 * KBS_NBODY;
+      }
+      if (ok) {
+        fa.kb = Lq.kb; fa.H = H;
+        for (int b = 0; b < Lq.kb; ++b) { fa.blk_src[b] = Lq.src[b]; fa.blk_row0[b] = Lq.row0[b]; fa.blk_nvalid[b] = Lq.nvalid[b]; }
+        fa.n = n; fa.n_pad = np;
+        fa.w_sb = projq_w(h, k, which); fa.bias = projq_bias(h, k, which);
+        fa.x_sb = reinterpret_cast<char*>(x_sb_all[k]); fa.sbb = act_sb_bytes(h, n);
+        fa.items = int(T * np / kPanelRows);
+        { const char* e = getenv("KBS_FPROJ_DBG"); fa.dbg = e ? atoi(e) : 0; }
+        fa.trace = h->trace_buf;
+        const unsigned grid = unsigned(fa.items < h->num_sms ? fa.items : h->num_sms);
+        if (kind == KBS_KIND_TF32)
+          KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (input_proj_fused_kernel<KBS_KIND_TF32><<<grid, kFThreads, kFSmemBytes, st>>>(fa)));
+        else
+          KBS_LAUNCH(h, KBS_K_PROJ_TC, st, (input_proj_fused_kernel<KBS_KIND_F16><<<grid, kFThreads, kFSmemBytes, st>>>(fa)));
+        continue;                     // no MODE_PROJ items for this net (panels = 0)
+      }
     }
     if (staged || fuse) {
       const int64_t total = T * np * (Kp / 8);
