@@ -1452,26 +1452,32 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
       tc_fence_after();
       const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(half * 128);
 #pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        float v[16], cr[16];
-        tmem_ld16(tq + cc * 16, v);
-        tmem_ld16(tq + 256 + cc * 16, cr);
+      for (int cc = 0; cc < 4; ++cc) {
+        // 32 output columns per pass: all four TMEM loads are in flight before the wait; after the last pass's loads the
+        // accumulators are in registers and TMEM goes back to the MMA issuer before the split + stores
+        float v[32], cr[32];
+        tmem_ld16(tq + cc * 32, v);
+        tmem_ld16(tq + cc * 32 + 16, v + 16);
+        tmem_ld16(tq + 256 + cc * 32, cr);
+        tmem_ld16(tq + 256 + cc * 32 + 16, cr + 16);
         tmem_ld_wait();
-        const float* bs = bias_s + half * 128 + cc * 16;
+        if (cc == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+        }
+        const float* bs = bias_s + half * 128 + cc * 32;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (v[i] + kCorr * cr[i]) + bs[i];
+        for (int i = 0; i < 32; ++i) v[i] = (v[i] + kCorr * cr[i]) + bs[i];
 #pragma unroll
-        for (int c8 = 0; c8 < 2; ++c8) {
+        for (int c8 = 0; c8 < 4; ++c8) {
           const float x0[4] = {v[8 * c8], v[8 * c8 + 1], v[8 * c8 + 2], v[8 * c8 + 3]};
           const float x1[4] = {v[8 * c8 + 4], v[8 * c8 + 5], v[8 * c8 + 6], v[8 * c8 + 7]};
           if (!(a.dbg & 8))
-          sb_store_split8<kPanelRows, KIND>(xo, R, half * 128 + cc * 16 + c8 * 8, a.H / kBlk, sb_split4<KIND>(x0), sb_split4<KIND>(x1),
+          sb_store_split8<kPanelRows, KIND>(xo, R, half * 128 + cc * 32 + c8 * 8, a.H / kBlk, sb_split4<KIND>(x0), sb_split4<KIND>(x1),
                                             false);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
     }
     if (tr && warp == kFEpiWarp0 && lane == 0) tr[8] = tw[0];
   }
@@ -2271,7 +2277,7 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
     if (r_out) { r_out->x_sb_all[k] = fuse ? obs_sb[k] : x_sb_all[k]; r_out->x_is_obs[k] = fuse; }
     const char* staged_env = getenv("KBS_PROJ_STAGED");            // A/B + cross-check: pack kernel + MODE_PROJ launch
     // FP16-split datapath only: with 3xTF32 operands (16-row boxes, 31 K blocks) a second engine in the same process gave
-    // run-to-run differences of ~1e-4 in 16 rows of one panel (tools/_dbg_tf32.py) -- not understood yet, so that
+    // run-to-run differences of ~1e-4 in 16 rows of one panel (A/B against KBS_PROJ_STAGED=1 on (T, N) = (6, 132), (1, 260)) -- not understood yet, so that
     // datapath keeps the staged form (KBS_FPROJ_TF32=1 enables the kernel for debugging).
     const char* tf32_env = getenv("KBS_FPROJ_TF32");
     const bool kind_ok = kind == KBS_KIND_F16 || (tf32_env && atoi(tf32_env));
