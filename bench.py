@@ -369,7 +369,9 @@ def run_b200(a):
     # (the 368-row cinert / cvel dump goes straight from the state into pack); command + lagged-gravity scans: the switch
     # draw, done, IMU quaternion in, 16 command rows + 3 gravity rows out (the new-command uniforms are read only at a
     # switch).  All within 5 % of ncu's dram__bytes per launch (profiles/r01_s4_phase_a_and_persist.md).
-    hbm_bytes = {"obs_kernel": 1210, "pack_kernels": 3788 + 650, "proj_tc_kernel": 480 * 4 + H * 4,
+    # pack: the actor's 65 observation rows -> its 128-wide split operand (the critic's rows go straight into the projection
+    # kernel: 475 rows read, H split outputs written)
+    hbm_bytes = {"obs_kernel": 1210, "pack_kernels": 65 * 4 + 128 * 4, "proj_tc_kernel": 475 * 4 + H * 4,
                  "reward_terms_kernel": 340, "command_kernel": 100, "terminate_kernel": 46, "gae_kernel": 18}
     for k, b in hbm_bytes.items():
         if k in breakdown and breakdown[k]["ms"] > 0:
