@@ -520,7 +520,14 @@ def run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world)
 
 if __name__ == "__main__":
     args = parse()
+    # stdout carries exactly ONE line, the JSON: everything libraries write to file descriptor 1 on the way (NCCL prints
+    # "NCCL version ..." there when its communicator comes up) goes to stderr instead
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_json_fd, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    sys.stdout.flush()
