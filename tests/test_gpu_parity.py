@@ -428,7 +428,8 @@ def test_policy_step(dev, path, N):
 
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("T,N,hidden", [(16, 32, 256), (6, 130, 256), (5, 50, 128), (7, 1100, 256), (1, 300, 256),
-                                        (70, 40, 256)])   # 70 steps: three 32-step chunks of the command / reward scans
+                                        (70, 40, 256),    # 70 steps: three 32-step chunks of the command / reward scans
+                                        (2, 1, 256), (3, 5, 256)])   # ld = 4 / 8: TMA boxes far wider than the env axis
 def test_rollout_fused(dev, path, T, N, hidden):
     """BASELINE config 1 shape (num_envs = 32, short rollout): the fused control step over T recorded steps."""
     res = Hn.run_rollout_case(seed=800 + N, T=T, N=N, hidden=hidden, device=dev, gemm_path=path)
