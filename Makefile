@@ -21,3 +21,11 @@ $(OUT): $(OBJS)
 clean:
 	rm -f $(OBJS) $(OUT)
 .PHONY: all clean
+
+# Optional: XLA-FFI (jax.ffi) handlers over the C-ABI.  Needs jaxlib's headers, which this image does not have:
+#   make ffi JAX_INCLUDE=$(python -c "import jax.ffi; print(jax.ffi.include_dir())")
+ffi: $(OUT)
+	@test -n "$(JAX_INCLUDE)" || (echo "set JAX_INCLUDE to jax.ffi.include_dir()"; exit 1)
+	$(NVCC) -O2 -std=c++17 -x cu $(ARCH) -Iinclude -I$(JAX_INCLUDE) -Xcompiler -fPIC -shared \
+	  $(SRC)/kbs_xla_ffi.cc -o $(PKG)/libkbs_xla_ffi.so -L$(PKG) -lkbotstep -Xlinker -rpath -Xlinker '$$ORIGIN' -lcudart
+.PHONY: ffi

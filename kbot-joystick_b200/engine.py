@@ -83,6 +83,11 @@ class KbotStep:
     def launches(self) -> int:
         return int(self.lib.kbs_launch_count(self._h))
 
+    @property
+    def handle_address(self) -> int:
+        """The kbs_handle* as an integer: the `handle` attribute of the XLA-FFI calls (jax_ffi.py, csrc/kbs_xla_ffi.cc)."""
+        return int(self._h.value)
+
     def device_status(self) -> int:
         """0 = healthy; != 0 = a dependency wait of the persistent rollout kernel timed out (synchronises)."""
         v = C.c_int(0)

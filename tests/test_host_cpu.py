@@ -260,3 +260,21 @@ def test_checkpoint_leaf_stream_round_trip(tmp_path):
                 np.testing.assert_array_equal(got["layers"][l][k], ref["layers"][l][k])
     with pytest.raises(AssertionError):
         ck.load_policy(path, hidden=256, depth=2)            # wrong architecture is refused, not silently reshaped
+
+
+def test_xla_ffi_shim_sources_agree():
+    """The (uncompiled here: no jaxlib) XLA-FFI shim: jax_ffi.py imports without jax and registers exactly the handler
+    symbols csrc/kbs_xla_ffi.cc defines; every handler forwards to an entry point include/kbotstep.h declares."""
+    import re
+    from pathlib import Path
+
+    import kbot_joystick_b200.jax_ffi as kf
+
+    root = Path(__file__).resolve().parent.parent
+    cc = (root / "kbot-joystick_b200" / "csrc" / "kbs_xla_ffi.cc").read_text()
+    header = (root / "include" / "kbotstep.h").read_text()
+    defined = set(re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),", cc))
+    assert defined == set(kf._TARGETS.values()), (defined, kf._TARGETS)
+    for target in kf._TARGETS:
+        assert re.search(rf"\bint {target}\(", header), target
+        assert f"{target}(H(handle)" in cc, target
