@@ -1233,8 +1233,8 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
 //             critic come straight from the recorded cinert / cvel arrays, train.py:1405-1413), 4-deep ring: ~48 KB of HBM
 //             reads in flight per SM (the register-staged MODE_PROJ_SOA had ~16 KB: 4x slower);
 //   warp 2    weight producer: the 32 KB W_in block (one 256-column tile = all H outputs, L2-resident) into the operand ring;
-//   warps 12-19  converters: thread = (env row, half of the K block); 16 floats from the raw stage (conflict-free column
-//             reads) -> hi / lo split -> two chunks of the A block in UMMA layout -> fence.proxy.async -> arrive;
+//   warps 12-19  converters, two sets of 4 warps on alternate stages: thread = env row; 32 floats from the raw stage
+//             (conflict-free column reads) -> hi / lo split -> the A block in UMMA layout -> fence.proxy.async -> arrive;
 //   warp 0    MMA issuer: the persistent kernel's scheme (3 x N = 256 MMAs per k-step, main + correction accumulators);
 //   warps 4-11   epilogue: TMEM -> + bias -> split -> SB stores (16-byte chunks, 512 B per warp).
 // Requires H == 256 (one tile).  KBS_PROJ_STAGED=1 restores pack + MODE_PROJ.
@@ -1294,8 +1294,8 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
   const int ppt = int(a.n_pad / kPanelRows);                     // panels per step
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFStagesRaw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kFConvWarps); }
-    for (int s = 0; s < kFStagesOp; ++s) { mbar_init(&full[s], 1 + kFConvWarps); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kFStagesRaw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kFConvWarps / 2); }
+    for (int s = 0; s < kFStagesOp; ++s) { mbar_init(&full[s], 1 + kFConvWarps / 2); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1); mbar_init(acc_empty, kFEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1357,44 +1357,46 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
     }
     __syncwarp();
   } else if (warp >= kFConvWarp0 && warp < kFConvWarp0 + kFConvWarps) {
-    // ===== converters: 8 warps; thread = (env row of the panel, half of the block's 4 chunks).  MEASURED: with 4 warps doing
-    // whole rows the converters were busy 81 % of the kernel (~1.4 K cycles per stage against 880 of MMA work). =====
+    // ===== converters: two sets of 4 warps on ALTERNATE stages; thread = env row of the panel, whole K block.  MEASURED:
+    // one set of 4 (or 8 half-block) warps on every stage is busy ~1.1-1.4 K cycles per stage (load, split, store, proxy
+    // fence, barrier round trips: a latency chain) against 880 cycles of MMA issue; two stages in flight hide it. =====
     const int cw = warp - kFConvWarp0;
-    const int r = (cw & 3) * 32 + lane, ch0 = (cw >> 2) * 2;         // chunks ch0, ch0 + 1
-    constexpr int kHalf = kFeat / 2;
+    const int set = cw >> 2;
+    const int r = (cw & 3) * 32 + lane;
     uint32_t g = 0;
     for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
       const int64_t e0 = int64_t(item % ppt) * kPanelRows;
       const bool valid = e0 + r < a.n;
       for (int b = 0; b < a.kb; ++b, ++g) {
+        if (int(g & 1) != set) continue;
         const int sr = g % kFStagesRaw, s = g % kFStagesOp;
         FTR_WAIT(0, mbar_wait(&raw_full[sr], (g / kFStagesRaw) & 1));
-        const float* rf = reinterpret_cast<const float*>(raw + size_t(sr) * kFRawBytes) + (ch0 * kE) * kPanelRows + r;
-        const int nv = int(a.blk_nvalid[b]) - ch0 * kE;         // real rows among this thread's kHalf
-        float x[kHalf];
+        const float* rf = reinterpret_cast<const float*>(raw + size_t(sr) * kFRawBytes) + r;
+        const int nv = int(a.blk_nvalid[b]);
+        float x[kFeat];
 #pragma unroll
-        for (int i = 0; i < kHalf; ++i) x[i] = (valid && i < nv && !(a.dbg & 1)) ? rf[i * kPanelRows] : 0.0f;
+        for (int i = 0; i < kFeat; ++i) x[i] = (valid && i < nv && !(a.dbg & 1)) ? rf[i * kPanelRows] : 0.0f;
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[sr]);
         FTR_WAIT(1, mbar_wait(&empty[s], ((g / kFStagesOp) & 1) ^ 1));
         uint8_t* sa = op + size_t(s) * kFOpBytes;
         if (!(a.dbg & 1))
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {                        // chunk ch0 + c of the block: [part][chunk][row][16 B]
+        for (int c = 0; c < 4; ++c) {                        // chunk c of the block: [part][chunk][row][16 B]
           uint4 hi, lo;
           if (KIND == KBS_KIND_F16) {
-            const float x0[4] = {x[(8 * c) % kHalf], x[(8 * c + 1) % kHalf], x[(8 * c + 2) % kHalf], x[(8 * c + 3) % kHalf]};
-            const float x1[4] = {x[(8 * c + 4) % kHalf], x[(8 * c + 5) % kHalf], x[(8 * c + 6) % kHalf], x[(8 * c + 7) % kHalf]};
+            const float x0[4] = {x[(8 * c) % kFeat], x[(8 * c + 1) % kFeat], x[(8 * c + 2) % kFeat], x[(8 * c + 3) % kFeat]};
+            const float x1[4] = {x[(8 * c + 4) % kFeat], x[(8 * c + 5) % kFeat], x[(8 * c + 6) % kFeat], x[(8 * c + 7) % kFeat]};
             const KbsSplit4 s0 = sb_split4<KIND>(x0), s1 = sb_split4<KIND>(x1);
             hi = make_uint4(s0.hi.x, s0.hi.y, s1.hi.x, s1.hi.y);
             lo = make_uint4(s0.lo.x, s0.lo.y, s1.lo.x, s1.lo.y);
           } else {
-            const float x0[4] = {x[(4 * c) % kHalf], x[(4 * c + 1) % kHalf], x[(4 * c + 2) % kHalf], x[(4 * c + 3) % kHalf]};
+            const float x0[4] = {x[(4 * c) % kFeat], x[(4 * c + 1) % kFeat], x[(4 * c + 2) % kFeat], x[(4 * c + 3) % kFeat]};
             const KbsSplit4 s0 = sb_split4<KIND>(x0);
             hi = s0.hi; lo = s0.lo;
           }
-          *reinterpret_cast<uint4*>(sa + (ch0 + c) * 2048 + r * 16) = hi;
-          *reinterpret_cast<uint4*>(sa + 8192 + (ch0 + c) * 2048 + r * 16) = lo;
+          *reinterpret_cast<uint4*>(sa + c * 2048 + r * 16) = hi;
+          *reinterpret_cast<uint4*>(sa + 8192 + c * 2048 + r * 16) = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
