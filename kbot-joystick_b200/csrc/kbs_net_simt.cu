@@ -117,7 +117,7 @@ gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
 // 8 x 8 outputs per thread (two 4-wide strips per axis), global loads of slab k+1 issued before the FMAs of slab k
 // (register staging + double-buffered shared memory: one barrier per slab).  M % 128 == 0, N % 128 == 0.
 constexpr int LBM = 128, LBN = 128;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 gemm_tn_large_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                      int M, int64_t K) {
   __shared__ __align__(16) float As[2][BK][LBM];

@@ -604,7 +604,7 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
   const int H = h->p.hidden_size, depth = h->p.depth;
   const int64_t T = b->T, ld = b->ld, rows = T * n;
   const size_t sH = size_t(n) * H;
-  const int splits = 8;
+  const int splits = 16;   // 8 x 2 x 16 = 256 CTAs of the large-tile weight-gradient GEMM: two per SM (128 registers)
   const int chunks = int((rows + 511) / 512);
   const int kp_max = round_up_i(KBS_CRITIC_OBS, 64);
   const bool tc = h->p.gemm_path != KBS_GEMM_SIMT_FP32;
