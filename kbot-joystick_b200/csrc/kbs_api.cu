@@ -88,7 +88,8 @@ constexpr int kOutLd = 64;  // row stride of the trunk output buffer
 
 // Fused rollout on the tensor-core path.  The state is recorded, so everything that does not depend on the networks
 // is evaluated for all T steps first (terminations, command law, lagged gravity, observations, input projections:
-// big HBM-/FFMA-bound launches), then the recurrence runs 3 launches per step (2 LSTM layers for both nets + head).
+// big HBM-bound launches), then the whole recurrence runs as ONE persistent kernel (kbs_tc_rollout_recurrent; the per-step
+// form -- 2 LSTM layer launches for both nets + a head launch per step -- stays behind KBS_TC_PER_STEP=1).
 int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStream_t st) {
   const int64_t ld = io->state.ld, T = io->T;
   const bool critic = io->value != nullptr;
@@ -689,7 +690,8 @@ int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n, void* stre
     }
     return KBS_OK;
   }
-  // tensor-core form: input projections of all T steps in one launch, then 3 launches per step
+  // tensor-core form: input projections of all T steps (critic: one launch; actor: folded into layer 0), then the persistent
+  // recurrence kernel with the stored actions (log-prob / entropy / std of the stored action instead of sampling)
   const size_t sbf = size_t(kbs_tc_sb_floats(h, n));
   const size_t ws_f = kbs_tc_rollout_ws_floats(h, n), xsb_f = size_t(T) * sbf;
   const size_t osb_a_f = size_t(kbs_tc_obs_sb_floats(h, KBS_NET_ACTOR, n, T));

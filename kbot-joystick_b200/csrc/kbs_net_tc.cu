@@ -2260,10 +2260,10 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
   const int H = h->p.hidden_size, kind = tc_kind(h);
   int proj_nets = 0;
   const int64_t np = pad_rows(n);
-  // Default: pack kernel -> SB staging buffer -> bulk copies.  KBS_PROJ_FUSED=1: the projection kernel's producer warps
-  // read the SoA observations themselves (MODE_PROJ_SOA).  MEASURED: 3.87 ms instead of 0.45 + 0.49 ms per 100-step
-  // rollout -- 128 threads x 32 register-staged loads are ~16 KB in flight per SM where HBM latency needs ~90 KB; the
-  // fused form needs an asynchronous (bulk-copy) first stage, which is round-2 work.
+  // Default: input_proj_fused_kernel (FP16-split datapath, H = 256) straight from the SoA observations.  Otherwise the staged
+  // form: pack kernel -> SB staging buffer -> MODE_PROJ launch.  KBS_PROJ_FUSED=1 (historical): the MODE_PROJ kernel's own
+  // producer warps read the SoA observations into registers (MODE_PROJ_SOA) -- MEASURED 3.87 ms instead of 0.45 + 0.49 ms per
+  // 100-step rollout: 128 threads x 32 register-staged loads are ~16 KB in flight per SM where HBM latency needs ~90 KB.
   static int staged = -1;
   if (staged < 0) { const char* e = getenv("KBS_PROJ_FUSED"); staged = (e && atoi(e)) ? 0 : 1; }
   LayerArgs2 a2{};
