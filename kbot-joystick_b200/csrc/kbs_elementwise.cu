@@ -1161,44 +1161,45 @@ command_scan_body(const kbs_params& P, int k, float* __restrict__ command /*[T+1
                     const float* __restrict__ u_arms, const uint8_t* __restrict__ done, int64_t T, int64_t ld, int64_t n) {
   const int64_t e = int64_t(blockIdx.x) * kThreads + threadIdx.x;
   if (e >= n) return;
-  // thread = (env, command row k = blockIdx.y): 16x the threads of a one-thread-per-env walk (4 096 envs alone fill only
-  // 32 SMs and the kernel is pure latency).  The command after step t is new(t*) at the LAST switch t* <= t (the new value
-  // does not depend on the previous one, train.py:768-785), so a 32-step chunk is: 64 independent loads -> a switch bit
-  // mask -> the (rare: p ~ 0.014 per step) switch values, loaded only at the set bits -> 32 coalesced stores.
+  // thread = (env, command row k): 16x the threads of a one-thread-per-env walk (4 096 envs alone fill only 32 SMs and
+  // the kernel is pure latency).  Nothing a step reads depends on the recurrence (the new command is a function of that
+  // step's mode / uniform only, train.py:768-785), so every input of 10 steps is loaded unconditionally first -- 40
+  // independent loads in flight per thread, ~30 MB per 4 096 x 100 in total -- and the scan itself touches registers only.
+  // (Loading the mode / uniform only at a switch, p ~ 0.014 per step, saved bytes nobody needed saved and cost two
+  // dependent round trips per switch in a divergent warp: 82 us per launch.)
   float c = command[k * ld + e];
-  for (int64_t t0 = 0; t0 < T; t0 += 32) {
-    unsigned mask = 0;
+  constexpr int kB = 10;     // 40 loads in flight; keeps the combined phase_a_scans_kernel at 4 CTAs per SM (one wave)
+  const float lo = k < 6 ? P.cmd_lo[k] : P.arm_lo[k - 6], hi = k < 6 ? P.cmd_hi[k] : P.arm_hi[k - 6];
+  for (int64_t t0 = 0; t0 < T; t0 += kB) {
+    bool sw[kB];
+    int m[kB];
+    float u[kB];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < kB; ++i) {
       const int64_t t = t0 + i < T ? t0 + i : T - 1;
-      const bool sw = (done[t * ld + e] != 0) || (u_switch[t * ld + e] < P.switch_prob);
-      mask |= (sw && t0 + i < T) ? (1u << i) : 0u;
+      sw[i] = (done[t * ld + e] != 0) || (u_switch[t * ld + e] < P.switch_prob);
+      m[i] = mode[t * ld + e];
+      u[i] = k < 6 ? u6[(t * 6 + k) * ld + e] : u_arms[(t * 10 + (k - 6)) * ld + e];
     }
-    int i = 0;
-    while (true) {
-      // steps before the next switch keep c
-      const int nxt = mask ? __ffs(mask) - 1 : 32;
-      for (; i < nxt; ++i) {
-        if (t0 + i >= T) break;
-        command[((t0 + i + 1) * KBS_NUM_COMMANDS + k) * ld + e] = c;
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+      const int64_t t = t0 + i;
+      if (t >= T) break;
+      if (sw[i]) {
+        if (k < 6) {
+          const float v = lo + u[i] * (hi - lo);
+          bool on;
+          if (k == 0) on = (m[i] == 0) || (m[i] == 3);
+          else if (k == 1) on = (m[i] == 1) || (m[i] == 3);
+          else if (k == 2) on = (m[i] == 2) || (m[i] == 3);
+          else on = (m[i] == 4);
+          c = on ? v : 0.0f;
+        } else {
+          const float arm = (lo + u[i] * (hi - lo)) * ((u[i] < 0.5f) ? 1.0f : 0.0f);
+          c = (m[i] == 3 || m[i] == 4) ? arm : 0.0f;
+        }
       }
-      if (nxt == 32 || t0 + nxt >= T) break;
-      mask &= mask - 1;
-      const int64_t t = t0 + nxt;
-      const int m = mode[t * ld + e];
-      if (k < 6) {
-        const float v = P.cmd_lo[k] + u6[(t * 6 + k) * ld + e] * (P.cmd_hi[k] - P.cmd_lo[k]);
-        bool on;
-        if (k == 0) on = (m == 0) || (m == 3);
-        else if (k == 1) on = (m == 1) || (m == 3);
-        else if (k == 2) on = (m == 2) || (m == 3);
-        else on = (m == 4);
-        c = on ? v : 0.0f;
-      } else {
-        const float u = u_arms[(t * 10 + (k - 6)) * ld + e];
-        const float arm = (P.arm_lo[k - 6] + u * (P.arm_hi[k - 6] - P.arm_lo[k - 6])) * ((u < 0.5f) ? 1.0f : 0.0f);
-        c = (m == 3 || m == 4) ? arm : 0.0f;
-      }
+      command[((t + 1) * KBS_NUM_COMMANDS + k) * ld + e] = c;
     }
   }
 }
@@ -1258,7 +1259,7 @@ pg_scan_kernel(const __grid_constant__ kbs_params P, const float* __restrict__ s
 }
 // Both scans of the fused rollout's phase A in one launch (they only depend on `done`): blockIdx.y = 0..15 command rows,
 // 16 = the lagged-gravity scan -- two latency-bound kernels side by side instead of back to back.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 phase_a_scans_kernel(const __grid_constant__ kbs_params P, float* __restrict__ command, const float* __restrict__ u_switch,
                      const int32_t* __restrict__ mode, const float* __restrict__ u6, const float* __restrict__ u_arms,
                      const uint8_t* __restrict__ done, const float* __restrict__ sensordata, const float* __restrict__ lag_p,
