@@ -1378,7 +1378,14 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
         for (int i = 0; i < kFeat; ++i) x[i] = (valid && i < nv && !(a.dbg & 1)) ? rf[i * kPanelRows] : 0.0f;
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[sr]);
-        FTR_WAIT(1, mbar_wait(&empty[s], ((g / kFStagesOp) & 1) ^ 1));
+        // Stage g reuses the operand slot of stage g - 3.  Its generic-proxy stores land ~50 cycles after the barrier flips,
+        // and MEASURED (tools/fproj_stress.py, 3xTF32 operands, whose converters outrun the MMAs and sit on this wait):
+        // releasing them on empty[s] -- the tcgen05.commit of stage g - 3 -- gave one wrong 32-row x 1-stage contribution
+        // in ~3 % of the launches (0 / 384 with the wait below): the commit's arrival does not cover the tail of the
+        // operand reads against a writer this fast (the bulk copies of the other kernels arrive >= 1 us later and never
+        // see it).  So a slot is rewritten only after the commit of stage g - 2: commits complete in order, which puts a
+        // whole stage of MMA time between the last read and the first store.
+        if (g >= 2) { const uint32_t gp = g - 2; FTR_WAIT(1, mbar_wait(&empty[gp % kFStagesOp], (gp / kFStagesOp) & 1)); }
         uint8_t* sa = op + size_t(s) * kFOpBytes;
         if (!(a.dbg & 1))
 #pragma unroll
@@ -2278,12 +2285,7 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
     LayerArgs& a = a2.net[k];
     if (r_out) { r_out->x_sb_all[k] = fuse ? obs_sb[k] : x_sb_all[k]; r_out->x_is_obs[k] = fuse; }
     const char* staged_env = getenv("KBS_PROJ_STAGED");            // A/B + cross-check: pack kernel + MODE_PROJ launch
-    // FP16-split datapath only: with 3xTF32 operands (16-row boxes, 31 K blocks) a second engine in the same process gave
-    // run-to-run differences of ~1e-4 in 16 rows of one panel (A/B against KBS_PROJ_STAGED=1 on (T, N) = (6, 132), (1, 260)) -- not understood yet, so that
-    // datapath keeps the staged form (KBS_FPROJ_TF32=1 enables the kernel for debugging).
-    const char* tf32_env = getenv("KBS_FPROJ_TF32");
-    const bool kind_ok = kind == KBS_KIND_F16 || (tf32_env && atoi(tf32_env));
-    if (!fuse && staged && kind_ok && projq_shape(h) && !(staged_env && atoi(staged_env)) && tensor_map_encode_fn()) {
+    if (!fuse && staged && projq_shape(h) && !(staged_env && atoi(staged_env)) && tensor_map_encode_fn()) {
       // straight from the SoA observations (input_proj_fused_kernel): no staging buffer, one launch per net
       const int which = (ci && cv && projq_has_dump_layout(h, k)) ? 1 : 0;
       const FLayout Lq = projq_layout(h, k, which);

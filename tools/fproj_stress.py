@@ -12,8 +12,6 @@ dev = torch.device("cuda:0")
 kind = sys.argv[1] if len(sys.argv) > 1 else "f16"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 path = L.GEMM_TC_2XF16 if kind == "f16" else L.GEMM_TC_3XTF32
-if kind != "f16":
-    os.environ["KBS_FPROJ_TF32"] = "1"
 for (T, N) in [(1, 260), (6, 132), (20, 4096)]:
     b = Batch(778, T, N, dev)
     ref = None
