@@ -305,6 +305,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
             x[i] = __ldcs(p + e);
           }
         }
+        // NOTE (historical path, KBS_PROJ_FUSED=1 only): generic stores this close behind the reader's tcgen05.commit can
+        // race with the tail of its operand reads -- input_proj_fused_kernel waits one stage longer for that reason.
         mbar_wait(&empty[s], ((g / kStages) & 1) ^ 1);
         uint8_t* sa = smem + size_t(s) * kStageBytes;
         if (pw == 0 && lane == 0) {
