@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KBS_VERSION 100
+#define KBS_VERSION 101
 #define KBS_NUM_JOINTS 20
 #define KBS_NUM_COMMANDS 16
 #define KBS_ACTOR_OBS 65    /* train.py:1290-1295 */
@@ -45,6 +45,8 @@ extern "C" {
 #define KBS_E_ALIGN (-3)      /* pointer not 16-byte aligned or ld % 4 != 0 */
 #define KBS_E_STATE (-4)      /* weights not packed / handle not ready */
 #define KBS_E_PARAM (-5)      /* bad scalar parameter */
+#define KBS_E_DEVICE (-6)     /* the device health word is non-zero (kbs_device_status): a persistent kernel's dependency
+                                 wait timed out, or an FP16-split operand left its range; sticky until kbs_device_status_reset */
 
 enum { KBS_NET_ACTOR = 0, KBS_NET_CRITIC = 1 };
 /* GEMM datapath for the LSTM/MLP contractions.  All are sm_100a CUDA in this library (no vendor library, no
@@ -225,11 +227,50 @@ typedef struct kbs_net_grads {
 int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo_batch* batch, const kbs_net_grads* actor,
                  const kbs_net_grads* critic, float* log_probs, float* values, float* entropy, float* stats_out,
                  int64_t n_envs, void* stream);
-/* Replaces: optax.adam (train.py:1057-1063: scale_by_adam, eps_root = 0, then -learning_rate) on one flat parameter
- * array: g = grad * grad_scale (1 / world_size after a sum all-reduce, or a global-norm clip factor);
+/* Replaces: optax.adam -- the adam_weight_decay == 0.0 branch of get_optimizer (train.py:1062-1063; NOT the branch the launch
+ * config takes: see kbs_adamw_step): scale_by_adam, eps_root = 0, then -learning_rate, on one flat parameter array: g = grad * grad_scale (1 / world_size after a sum all-reduce, or a global-norm clip factor);
  * m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2; p -= lr (m / (1 - b1^step)) / (sqrt(v / (1 - b2^step)) + eps).  step >= 1. */
 int kbs_adam_step(kbs_handle* h, float* param, const float* grad, float* m, float* v, int64_t count, float lr, float b1,
                   float b2, float eps, float grad_scale, int64_t step, void* stream);
+
+/* Replaces: optax.adamw (train.py:1062-1065: the launch config keeps adam_weight_decay = 1e-5, train.py:99-102, so
+ * get_optimizer returns optax.adamw(lr, weight_decay): scale_by_adam(b1, b2, eps, eps_root = 0) -> add_decayed_weights(wd)
+ * -> scale by -lr) and ksim's gradient clipping around optimizer.update [U: global-norm clip to `max_grad_norm`, update
+ * skipped when the norm is not finite].  One flat parameter array:
+ *   g = grad * grad_scale * clip,  clip = min(1, max_grad_norm / max(norm * grad_scale, 1e-6))  (1 when grad_norm is NULL
+ *       or max_grad_norm <= 0);  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
+ *   p -= lr ((m / (1 - b1^step)) / (sqrt(v / (1 - b2^step)) + eps) + weight_decay p)
+ * grad_norm: device, 1 float = the global L2 norm of `grad` (kbs_grad_norm), or NULL.  A non-finite norm leaves p, m, v
+ * and the step counter untouched.  step_dev: device int64 = number of updates applied so far (read, then advanced by one
+ * when the update is applied), so that the whole update can be replayed as one CUDA graph; NULL = use `step` (>= 1). */
+typedef struct kbs_adamw_params {
+  float lr, b1, b2, eps, weight_decay, grad_scale, max_grad_norm;
+} kbs_adamw_params;
+int kbs_adamw_default_params(kbs_adamw_params* p);   /* lr 5e-4, b1 0.9, b2 0.999, eps 1e-8, wd 1e-5 [R]; clip 10.0 [U] */
+int kbs_adamw_step(kbs_handle* h, float* param, const float* grad, float* m, float* v, int64_t count,
+                   const kbs_adamw_params* o, const float* grad_norm, int64_t* step_dev, int64_t step, void* stream);
+/* Replaces: optax.global_norm over the gradient pytree: norm_out (device, 1 float) = sqrt(sum grad^2), accumulated in
+ * double in a fixed order (bitwise reproducible; identical on every rank after the all-reduce). */
+int kbs_grad_norm(kbs_handle* h, const float* grad, int64_t count, float* norm_out, void* stream);
+
+/* Pins the handle's scratch allocation: while locked, a call that would have to grow (free + reallocate) the scratch
+ * returns KBS_E_STATE instead -- a captured CUDA graph holds pointers into it (ppo.PpoUpdater.capture). */
+int kbs_scratch_lock(kbs_handle* h, int on);
+
+/* Replaces: the per-episode randomisation of ksim.PositionActuators (train.py:1097-1105: kp_scale = kd_scale = 1.4,
+ * torque_limit_scale_low = 0.5, action_bias_scale = 0.02 rad, torque_bias_scale = 0.0 N m; fork b-vm/ksim [U]: the sampling
+ * law below is this library's reading, every scale is a parameter).  Randomness explicit: u [5][20][ld] U[0,1) rows for
+ * (kp, kd, tau_limit, action_bias, torque_bias).
+ *   kp  = kp_nominal  * (1/kp_scale + u (kp_scale - 1/kp_scale));   kd likewise with kd_scale
+ *   tau_limit = ctrl_limit * (low + u (1 - low));   action_bias = (2u - 1) action_bias_scale;  torque_bias likewise
+ * reset u8 [ld] or NULL: only envs with reset != 0 are resampled (episode boundaries), the others keep their values.
+ * Writes the kp / kd / tau_limit / action_bias / torque_bias arrays of *ep ([20][ld] each; NULL = skipped). */
+typedef struct kbs_actuator_rand_params {
+  float kp_scale, kd_scale, torque_limit_scale_low, action_bias_scale, torque_bias_scale;
+} kbs_actuator_rand_params;
+int kbs_actuator_rand_default_params(kbs_actuator_rand_params* p);
+int kbs_sample_actuator_randomization(kbs_handle* h, const kbs_actuator_rand_params* rp, const float* u, const uint8_t* reset,
+                                      const kbs_episode_view* ep, int64_t ld, int64_t n_envs, void* stream);
 
 /* Replaces: COMDistanceObservation.observe (train.py:509-659): distance between subtree_com[2].xy and the centroid of the
  * convex hull (Andrew's monotone chain) of the floor-contact points, -1 when fewer than 3 distinct contact.geom2 values.
@@ -376,6 +417,20 @@ typedef struct kbs_ppo_io {
   float* action_std;        /* [T][20][ld]  PPOVariables.action_std train.py:1487, or NULL */
   float* mean;              /* [T][20][ld]  dist.mean() (for the mirror loss), or NULL */
   int64_t T, ld;
+  /* aux_losses of PPOVariables (train.py:1462-1481, 1488-1491): the actor and the critic run a second time on the MIRRORED
+   * observations (kbs_mirror_observations: mirror_obs + mirror_cmd followed by the run_actor / run_critic concatenations)
+   * with their own carries, and
+   *   action_mirror_loss = mean_j (mean - mirror_joints(mean_mirrored))^2 * actor_mirror_loss_scale
+   *   value_mirror_loss  = (value - value_mirrored)^2 * critic_mirror_loss_scale
+   * All NULL = not evaluated.  The launch config scales both by 0.0 (train.py:1771-1772); the defaults are 1.0 / 0.01. */
+  const float* actor_obs_mirror;   /* [T][65][ld] */
+  const float* critic_obs_mirror;  /* [T][475][ld] or NULL (then value_mirror_loss is not written) */
+  float* actor_mirror_carry;       /* AoS [depth][2][n][H] in/out  (carry["actor_mirror"]) */
+  float* critic_mirror_carry;      /* AoS [depth][2][n][H] in/out  (carry["critic_mirror"]) */
+  float* lpf_mirror;               /* [20][ld] in/out              (carry["lpf_params_mirror"]) */
+  float* action_mirror_loss;       /* [T][ld] */
+  float* value_mirror_loss;        /* [T][ld] */
+  float actor_mirror_loss_scale, critic_mirror_loss_scale;
 } kbs_ppo_io;
 int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n_envs, void* stream);
 
@@ -386,6 +441,15 @@ int64_t kbs_launch_count(const kbs_handle* h);
  * steps as one persistent kernel whose CTAs wait on each other's progress counters; a wait that times out is recorded
  * here instead of hanging).  Synchronises with the device.  *status_out == 0: healthy. */
 int kbs_device_status(kbs_handle* h, int* status_out);
+/* Status bits: 1 / 2 = a dependency wait of an LSTM / head item timed out (the kernel then drains without waiting: its
+ * outputs are garbage); 0x100 = a value handed to the FP16-split tensor-core datapath was non-finite or >= 65504 in
+ * magnitude (it would silently become inf: use KBS_GEMM_TC_3XTF32 / KBS_GEMM_SIMT_FP32 for such inputs).  The word is
+ * sticky; the fused entry points (kbs_rollout, kbs_ppo_variables, kbs_policy_step, kbs_ppo_grad) copy it to the host after
+ * their kernels and return KBS_E_DEVICE at the next call that finds it set.  Reset: synchronises and clears it. */
+#define KBS_STATUS_TIMEOUT_LSTM 1
+#define KBS_STATUS_TIMEOUT_HEAD 2
+#define KBS_STATUS_F16_RANGE 0x100
+int kbs_device_status_reset(kbs_handle* h);
 
 /* Per-kernel device timing for bench.py's roofline line: while enabled, every kernel launch of this handle is
  * bracketed by CUDA events on its launch stream (up to 8192 launches; do not enable during stream capture).

@@ -84,7 +84,18 @@ class KbsRolloutIO(C.Structure):
 
 class KbsPpoIO(C.Structure):
     _fields_ = [(k, _vp) for k in ("actor_obs", "critic_obs", "action", "done", "actor_carry", "critic_carry", "lpf",
-                                   "log_probs", "values", "entropy", "action_std", "mean")] + [("T", _i64), ("ld", _i64)]
+                                   "log_probs", "values", "entropy", "action_std", "mean")] + [("T", _i64), ("ld", _i64)] + [
+        (k, _vp) for k in ("actor_obs_mirror", "critic_obs_mirror", "actor_mirror_carry", "critic_mirror_carry", "lpf_mirror",
+                           "action_mirror_loss", "value_mirror_loss")] + [("actor_mirror_loss_scale", _f),
+                                                                          ("critic_mirror_loss_scale", _f)]
+
+
+class KbsAdamwParams(C.Structure):
+    _fields_ = [(k, _f) for k in ("lr", "b1", "b2", "eps", "weight_decay", "grad_scale", "max_grad_norm")]
+
+
+class KbsActuatorRandParams(C.Structure):
+    _fields_ = [(k, _f) for k in ("kp_scale", "kd_scale", "torque_limit_scale_low", "action_bias_scale", "torque_bias_scale")]
 
 
 class KbsPpoLossParams(C.Structure):
@@ -113,7 +124,11 @@ EXPORTS = (
     "kbs_weights_pack", "kbs_observations", "kbs_command_update", "kbs_actor_step", "kbs_critic_step",
     "kbs_torque", "kbs_terminate", "kbs_rewards", "kbs_gae", "kbs_policy_step", "kbs_rollout", "kbs_ppo_variables",
     "kbs_launch_count", "kbs_device_status", "kbs_mirror_observations", "kbs_mirror_joints", "kbs_upload_state", "kbs_com_distance", "kbs_ppo_loss_default_params", "kbs_ppo_loss", "kbs_ppo_grad", "kbs_adam_step", "kbs_torque_substeps", "kbs_profile_enable", "kbs_profile_read", "kbs_kernel_name", "kbs_debug_tc_gates", "kbs_debug_tc_trace", "kbs_debug_tc_trace_attach",
+    "kbs_adamw_default_params", "kbs_adamw_step", "kbs_grad_norm", "kbs_scratch_lock", "kbs_actuator_rand_default_params",
+    "kbs_sample_actuator_randomization", "kbs_device_status_reset",
 )
+VERSION = 101
+STATUS_TIMEOUT_LSTM, STATUS_TIMEOUT_HEAD, STATUS_F16_RANGE = 1, 2, 0x100
 NUM_KERNEL_IDS = 18
 
 _lib = None
@@ -146,6 +161,13 @@ def load() -> C.CDLL:
     lib.kbs_ppo_grad.argtypes = [_vp, P(KbsPpoLossParams), P(KbsPpoBatch), P(KbsNetGrads), P(KbsNetGrads), _vp, _vp, _vp, _vp,
                                  _i64, _vp]
     lib.kbs_adam_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i64, _vp]
+    lib.kbs_adamw_default_params.argtypes = [P(KbsAdamwParams)]
+    lib.kbs_adamw_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, P(KbsAdamwParams), _vp, _vp, _i64, _vp]
+    lib.kbs_grad_norm.argtypes = [_vp, _vp, _i64, _vp, _vp]
+    lib.kbs_scratch_lock.argtypes = [_vp, C.c_int]
+    lib.kbs_device_status_reset.argtypes = [_vp]
+    lib.kbs_actuator_rand_default_params.argtypes = [P(KbsActuatorRandParams)]
+    lib.kbs_sample_actuator_randomization.argtypes = [_vp, P(KbsActuatorRandParams), _vp, _vp, P(KbsEpisodeView), _i64, _i64, _vp]
     lib.kbs_torque_substeps.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, P(KbsEpisodeView), _vp, C.c_int32, C.c_float, C.c_float,
                                         _i64, _i64, _vp]
     lib.kbs_com_distance.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _i64, _i64, _vp]

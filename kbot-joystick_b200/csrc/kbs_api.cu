@@ -97,8 +97,8 @@ int rollout_fused_tc(kbs_handle* h, const kbs_rollout_io* io, int64_t n, cudaStr
   // recurrence of the previous chunk runs on the caller's stream (KBS_ROLLOUT_CHUNKS = 2..8).  MEASURED: slower
   // (9.97 vs 8.89 ms per 100-step rollout): the persistent recurrence kernel wants every SM to itself, so the
   // concurrent kernels delay its CTAs more than they hide.  Default = 1 chunk: phase A first, then the recurrence.
-  static int chunks_cfg = 0;
-  if (!chunks_cfg) {
+  int chunks_cfg = 1;
+  {
     const char* e = getenv("KBS_ROLLOUT_CHUNKS");
     chunks_cfg = e ? atoi(e) : 1;
     if (chunks_cfg < 1 || chunks_cfg > kKbsMaxChunks) chunks_cfg = 1;
@@ -186,8 +186,35 @@ int kbs_side_stream_init(kbs_handle* h) {
   return 0;
 }
 
+int kbs_status_init(kbs_handle* h) {
+  if (h->persist_status) return KBS_OK;
+  KBS_CUDA_TRY(cudaMalloc(&h->persist_status, 256));
+  KBS_CUDA_TRY(cudaMemset(h->persist_status, 0, 256));
+  KBS_CUDA_TRY(cudaHostAlloc(&h->status_host, 64, cudaHostAllocDefault));
+  *h->status_host = 0u;
+  return KBS_OK;
+}
+
+// refresh the pinned host copy of the (sticky) device health word once the work enqueued so far on `st` has run
+int kbs_status_publish(kbs_handle* h, cudaStream_t st) {
+  if (!h->persist_status) return KBS_OK;
+  KBS_CUDA_TRY(cudaMemcpyAsync(h->status_host, h->persist_status, 4, cudaMemcpyDeviceToHost, st));
+  return KBS_OK;
+}
+
+// entry check of the fused entry points: the handle belongs to one device (its kernels' shared-memory opt-in, its
+// weights and scratch live there), and a health word left non-zero by an earlier call is an error, not a silent result
+int kbs_enter(kbs_handle* h) {
+  int dev = -1;
+  KBS_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != h->device) return KBS_E_STATE;
+  if (h->status_host && *reinterpret_cast<volatile unsigned int*>(h->status_host) != 0u) return KBS_E_DEVICE;
+  return KBS_OK;
+}
+
 int kbs_scratch_reserve(kbs_handle* h, size_t floats) {
   if (floats <= h->scratch_floats) return KBS_OK;
+  if (h->scratch_locked) return KBS_E_STATE;       // a captured graph holds pointers into the current allocation
   if (h->scratch) { KBS_CUDA_TRY(cudaFree(h->scratch)); h->scratch = nullptr; h->scratch_floats = 0; }
   const size_t want = floats + floats / 8 + 1024;
   KBS_CUDA_TRY(cudaMalloc(&h->scratch, want * sizeof(float)));
@@ -207,6 +234,7 @@ const char* kbs_error_string(int code) {
     case KBS_E_ALIGN: return "pointer not 16-byte aligned or ld % 4 != 0";
     case KBS_E_STATE: return "handle not ready (weights not packed, or datapath unavailable)";
     case KBS_E_PARAM: return "bad scalar parameter";
+    case KBS_E_DEVICE: return "device health word set (dependency-wait timeout or FP16-split operand out of range): kbs_device_status";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown kbs error";
   }
 }
@@ -289,7 +317,9 @@ int kbs_destroy(kbs_handle* h) {
   }
   cudaFree(h->scratch);
   cudaFree(h->persist_status);
+  if (h->status_host) cudaFreeHost(h->status_host);
   cudaFree(h->loss_ticket);
+  cudaFree(h->norm_partial);
   if (h->side_stream) {
     cudaStreamDestroy(h->side_stream);
     cudaStreamDestroy(h->aux_stream);
@@ -318,8 +348,25 @@ int kbs_device_status(kbs_handle* h, int* status_out) {
   *status_out = 0;
   if (!h->persist_status) return KBS_OK;
   unsigned int v = 0;
-  KBS_CUDA_TRY(cudaMemcpy(&v, h->persist_status, 4, cudaMemcpyDeviceToHost));   // synchronises with the device
+  KBS_CUDA_TRY(cudaDeviceSynchronize());
+  KBS_CUDA_TRY(cudaMemcpy(&v, h->persist_status, 4, cudaMemcpyDeviceToHost));
+  *h->status_host = v;
   *status_out = int(v);
+  return KBS_OK;
+}
+
+int kbs_device_status_reset(kbs_handle* h) {
+  REQ(h);
+  if (!h->persist_status) return KBS_OK;
+  KBS_CUDA_TRY(cudaDeviceSynchronize());
+  KBS_CUDA_TRY(cudaMemset(h->persist_status, 0, 4));
+  *h->status_host = 0u;
+  return KBS_OK;
+}
+
+int kbs_scratch_lock(kbs_handle* h, int on) {
+  REQ(h);
+  h->scratch_locked = on != 0;
   return KBS_OK;
 }
 
@@ -384,6 +431,7 @@ const char* kbs_kernel_name(int id) {
 int kbs_weights_pack(kbs_handle* h, int net, const kbs_net_weights* w, void* stream) {
   REQ(h); REQ(w);
   if (net != KBS_NET_ACTOR && net != KBS_NET_CRITIC) return KBS_E_PARAM;
+  { int dev = -1; KBS_CUDA_TRY(cudaGetDevice(&dev)); if (dev != h->device) return KBS_E_STATE; }
   REQ(w->w_in); REQ(w->b_in); REQ(w->w_out); REQ(w->b_out);
   for (int l = 0; l < h->p.depth; ++l) { REQ(w->w_ih[l]); REQ(w->w_hh[l]); REQ(w->b[l]); }
   cudaStream_t st = (cudaStream_t)stream;
@@ -593,6 +641,7 @@ int kbs_policy_step(kbs_handle* h, const float* joint_angles, const float* joint
   REQ(h); REQ(joint_angles); REQ(joint_vel); REQ(projected_gravity); REQ(gyro); REQ(command); REQ(carry_in);
   REQ(carry_out); REQ(action_out);
   if (n <= 0) return KBS_E_SHAPE;
+  { const int rc0 = kbs_enter(h); if (rc0) return rc0; }
   cudaStream_t st = (cudaStream_t)stream;
   const int H = h->p.hidden_size, d2 = 2 * h->p.depth;
   const int64_t ld = round_up4(n);
@@ -651,31 +700,26 @@ int kbs_policy_step(kbs_handle* h, const float* joint_angles, const float* joint
   return kbs_launch_policy_unpack(h, carry, lpf, mean, carry_out, action_out, ld, n, st);
 }
 
-int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n, void* stream) {
-  REQ(h); REQ(io);
-  REQ(io->actor_obs); REQ(io->action); REQ(io->done); REQ(io->actor_carry); REQ(io->lpf); REQ(io->log_probs);
-  REQ(io->entropy);
-  if (io->T <= 0) return KBS_E_SHAPE;
-  int rc = check_ld(io->ld, n);
-  if (rc) return rc;
+// One pass of _ppo_scan_fn's networks over a stored trajectory (actor [+ critic]); `base` = first float of the handle's
+// scratch this pass may use (the mirror pass of kbs_ppo_variables keeps its intermediate outputs below it).
+static int ppo_variables_pass(kbs_handle* h, const kbs_ppo_io* io, int64_t n, cudaStream_t st, size_t base, size_t* end_out,
+                              bool dry) {
+  int rc;
   const bool critic = io->critic_obs != nullptr;
-  if (critic) { REQ(io->critic_carry); REQ(io->values); }
-  AL(io->actor_obs); AL(io->critic_obs); AL(io->action); AL(io->lpf); AL(io->log_probs); AL(io->values); AL(io->entropy);
-  AL(io->action_std); AL(io->mean);
-  cudaStream_t st = (cudaStream_t)stream;
   const int64_t ld = io->ld, T = io->T;
-  if (h->p.gemm_path == KBS_GEMM_SIMT_FP32 || io->mean) {
-    // stage-by-stage form (exact-fp32 datapath, or when dist.mean() is wanted): T x (actor step, critic step)
+  if (h->p.gemm_path == KBS_GEMM_SIMT_FP32) {
+    // stage-by-stage form (exact-fp32 datapath): T x (actor step, critic step)
     const size_t ts = trunk_scratch_floats(h, n);
-    if ((rc = kbs_scratch_reserve(h, ts + size_t(n) * kOutLd))) return rc;
+    if (end_out) *end_out = ts + size_t(n) * kOutLd;          // the trunk's workspace layout starts at the scratch base
+    if (dry) return KBS_OK;
     float* out_rm = h->scratch + ts;
     for (int64_t t = 0; t < T; ++t) {
       const uint8_t* done_t = io->done + t * ld;
       if ((rc = trunk(h, KBS_NET_ACTOR, io->actor_obs + t * KBS_ACTOR_OBS * ld, ld, io->actor_carry, done_t, out_rm, n, st)))
         return rc;
       kbs_actor_out o{};
-      o.log_prob = io->log_probs + t * ld;
-      o.entropy = io->entropy + t * ld;
+      o.log_prob = io->log_probs ? io->log_probs + t * ld : nullptr;
+      o.entropy = io->entropy ? io->entropy + t * ld : nullptr;
       o.std = io->action_std ? io->action_std + t * KBS_NUM_JOINTS * ld : nullptr;
       o.mean = io->mean ? io->mean + t * KBS_NUM_JOINTS * ld : nullptr;
       if ((rc = kbs_launch_actor_head(h, out_rm, kOutLd, io->actor_obs + t * KBS_ACTOR_OBS * ld, ld, io->lpf, nullptr,
@@ -691,13 +735,14 @@ int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n, void* stre
     return KBS_OK;
   }
   // tensor-core form: input projections of all T steps (critic: one launch; actor: folded into layer 0), then the persistent
-  // recurrence kernel with the stored actions (log-prob / entropy / std of the stored action instead of sampling)
+  // recurrence kernel with the stored actions (log-prob / entropy / std / mean of the stored action instead of sampling)
   const size_t sbf = size_t(kbs_tc_sb_floats(h, n));
   const size_t ws_f = kbs_tc_rollout_ws_floats(h, n), xsb_f = size_t(T) * sbf;
   const size_t osb_a_f = size_t(kbs_tc_obs_sb_floats(h, KBS_NET_ACTOR, n, T));
   const size_t osb_c_f = critic ? size_t(kbs_tc_obs_sb_floats(h, KBS_NET_CRITIC, n, T)) : 0;
-  if ((rc = kbs_scratch_reserve(h, ws_f + xsb_f * (critic ? 2 : 1) + osb_a_f + osb_c_f + 64))) return rc;
-  float* ws = h->scratch;
+  if (end_out) *end_out = base + ws_f + xsb_f * (critic ? 2 : 1) + osb_a_f + osb_c_f + 64;
+  if (dry) return KBS_OK;
+  float* ws = h->scratch + base;
   float* xsb_a = ws + ws_f;
   float* xsb_c = critic ? xsb_a + xsb_f : nullptr;
   float* osb_a = xsb_a + xsb_f * (critic ? 2 : 1);
@@ -713,9 +758,86 @@ int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n, void* stre
   r.carry[0] = io->actor_carry; r.carry[1] = io->critic_carry;
   r.done = io->done; r.actor_obs = io->actor_obs; r.lpf = io->lpf;
   r.action_in = io->action; r.log_prob = io->log_probs; r.entropy = io->entropy; r.action_std = io->action_std;
+  r.mean = io->mean;
   r.value = io->values;
   r.ws = ws;
   return kbs_tc_rollout_recurrent(h, r, st);
+}
+
+int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n, void* stream) {
+  REQ(h); REQ(io);
+  REQ(io->actor_obs); REQ(io->action); REQ(io->done); REQ(io->actor_carry); REQ(io->lpf); REQ(io->log_probs);
+  REQ(io->entropy);
+  if (io->T <= 0) return KBS_E_SHAPE;
+  int rc = check_ld(io->ld, n);
+  if (rc) return rc;
+  if ((rc = kbs_enter(h))) return rc;
+  const bool critic = io->critic_obs != nullptr;
+  if (critic) { REQ(io->critic_carry); REQ(io->values); }
+  AL(io->actor_obs); AL(io->critic_obs); AL(io->action); AL(io->lpf); AL(io->log_probs); AL(io->values); AL(io->entropy);
+  AL(io->action_std); AL(io->mean);
+  const bool mirror = io->actor_obs_mirror != nullptr;
+  if (mirror) {
+    REQ(io->actor_mirror_carry); REQ(io->lpf_mirror); REQ(io->action_mirror_loss);
+    if (io->critic_obs_mirror) { REQ(io->critic_mirror_carry); REQ(io->value_mirror_loss); if (!critic) return KBS_E_NULL; }
+    AL(io->actor_obs_mirror); AL(io->critic_obs_mirror); AL(io->lpf_mirror); AL(io->action_mirror_loss); AL(io->value_mirror_loss);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ld = io->ld, T = io->T;
+  const bool tc = h->p.gemm_path != KBS_GEMM_SIMT_FP32;
+  if (tc && io->mean && !kbs_tc_persistent_available(h, n, T, critic ? 2 : 1)) return KBS_E_SHAPE;
+  // scratch: [mirror intermediates: mean, mean_m [T][20][ld], value_m, lp_m, ent_m [T][ld]] | pass workspace.  The exact-fp32
+  // trunk addresses its workspace from the scratch base, so there the intermediates sit behind it instead.
+  const size_t mir_f = mirror ? (2 * size_t(T) * KBS_NUM_JOINTS * ld + 3 * size_t(T) * ld + 255) / 256 * 256 : 0;
+  size_t pass_end = 0;
+  if ((rc = ppo_variables_pass(h, io, n, st, tc ? mir_f : 0, &pass_end, true))) return rc;
+  if ((rc = kbs_scratch_reserve(h, pass_end + (tc ? 0 : mir_f) + 64))) return rc;
+  float* mir = mirror ? (tc ? h->scratch : h->scratch + pass_end) : nullptr;
+  kbs_ppo_io a = *io;
+  if (mirror && !a.mean) a.mean = mir;
+  if ((rc = ppo_variables_pass(h, &a, n, st, tc ? mir_f : 0, nullptr, false))) return rc;
+  if (!mirror) return KBS_OK;
+  // the mirrored passes (train.py:1462-1481): same networks, mirrored observations, their own carries
+  float* mean_m = mir + size_t(T) * KBS_NUM_JOINTS * ld;
+  float* value_m = mean_m + size_t(T) * KBS_NUM_JOINTS * ld;
+  float* lp_m = value_m + size_t(T) * ld;
+  float* ent_m = lp_m + size_t(T) * ld;
+  kbs_ppo_io m = *io;
+  m.actor_obs = io->actor_obs_mirror; m.critic_obs = io->critic_obs_mirror;
+  m.actor_carry = io->actor_mirror_carry; m.critic_carry = io->critic_mirror_carry; m.lpf = io->lpf_mirror;
+  m.log_probs = lp_m; m.entropy = ent_m; m.values = io->critic_obs_mirror ? value_m : nullptr; m.action_std = nullptr;
+  m.mean = mean_m;
+  if ((rc = ppo_variables_pass(h, &m, n, st, tc ? mir_f : 0, nullptr, false))) return rc;
+  return kbs_launch_mirror_loss(h, a.mean, mean_m, io->values, value_m, io->action_mirror_loss,
+                                io->critic_obs_mirror ? io->value_mirror_loss : nullptr, io->actor_mirror_loss_scale,
+                                io->critic_mirror_loss_scale, T, ld, n, st);
+}
+
+int kbs_adamw_default_params(kbs_adamw_params* p) {
+  REQ(p);
+  p->lr = 5e-4f; p->b1 = 0.9f; p->b2 = 0.999f; p->eps = 1e-8f;   /* train.py:95-98, optax.adamw defaults */
+  p->weight_decay = 1e-5f;                                       /* train.py:99-102 */
+  p->grad_scale = 1.0f;
+  p->max_grad_norm = 10.0f;                                      /* ksim RLConfig global gradient clip [U] */
+  return KBS_OK;
+}
+
+int kbs_actuator_rand_default_params(kbs_actuator_rand_params* p) {
+  REQ(p);
+  p->kp_scale = 1.4f; p->kd_scale = 1.4f; p->torque_limit_scale_low = 0.5f; p->action_bias_scale = 0.02f;   /* train.py:1097-1105 */
+  p->torque_bias_scale = 0.0f;
+  return KBS_OK;
+}
+
+int kbs_sample_actuator_randomization(kbs_handle* h, const kbs_actuator_rand_params* rp, const float* u, const uint8_t* reset,
+                                      const kbs_episode_view* ep, int64_t ld, int64_t n, void* stream) {
+  REQ(h); REQ(rp); REQ(u); REQ(ep);
+  int rc = check_ld(ld, n);
+  if (rc) return rc;
+  if (!(rp->kp_scale > 0.0f) || !(rp->kd_scale > 0.0f)) return KBS_E_PARAM;
+  AL(u); AL(ep->kp); AL(ep->kd); AL(ep->tau_limit); AL(ep->action_bias); AL(ep->torque_bias);
+  if (reinterpret_cast<uintptr_t>(reset) & 3u) return KBS_E_ALIGN;
+  return kbs_launch_actuator_rand(h, *rp, u, reset, *ep, ld, n, (cudaStream_t)stream);
 }
 
 int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n, void* stream) {
@@ -723,6 +845,7 @@ int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n, void* stream
   if (io->T <= 0) return KBS_E_SHAPE;
   int rc = check_state(&io->state, n, true);
   if (rc) return rc;
+  if ((rc = kbs_enter(h))) return rc;
   REQ(io->state.time); REQ(io->command); REQ(io->actor_carry); REQ(io->lpf); REQ(io->action); REQ(io->ctrl);
   REQ(io->done); REQ(io->success); REQ(io->cmd_mode); REQ(io->cmd_u6); REQ(io->cmd_u_arms); REQ(io->u_switch);
   if (io->value) { REQ(io->critic_carry); REQ(io->state.cinert); REQ(io->state.cvel); REQ(io->state.actuator_force); }

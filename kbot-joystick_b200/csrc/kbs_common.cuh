@@ -70,8 +70,13 @@ struct kbs_handle {
   cudaStream_t aux_stream = nullptr;          // chunked observation / input-projection phase of the fused rollout
   cudaEvent_t ev_pre = nullptr, ev_chunk[8] = {};
   cudaEvent_t ev_lstm[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr};
+  double* norm_partial = nullptr;             // kbs_grad_norm: per-block partial sums of squares
   unsigned int* loss_ticket = nullptr;        // "last block" counter of ppo_loss_kernel
-  unsigned int* persist_status = nullptr;     // device word set by rollout_persist_kernel when a dependency wait times out
+  unsigned int* persist_status = nullptr;     // device health word (KBS_STATUS_*): sticky, OR-accumulated by the kernels
+  unsigned int* status_host = nullptr;        // pinned host copy, refreshed by an async D2H after the fused entry points' kernels
+  bool tc_attr_set = false;                   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: once per handle
+  bool head_attr_set = false;
+  bool scratch_locked = false;                // kbs_scratch_lock: growing the scratch is an error (a CUDA graph holds pointers)
   long long* trace_buf = nullptr;
   int64_t trace_step = -1;
   int trace_layer = 0;
@@ -93,6 +98,11 @@ struct KbsLaunchScope {
 #define KBS_LAUNCH(h, id, st, ...) do { KbsLaunchScope _ls((h), (id), (st)); __VA_ARGS__; } while (0)
 
 int kbs_side_stream_init(kbs_handle* h);   // kbs_api.cu: lazily creates side_stream + events (returns cudaError_t)
+// device health word (kbs_api.cu): allocate on first use; enqueue its copy to the pinned host word behind the kernels of a
+// fused entry point; entry check = wrong current device or a sticky status -> error code
+int kbs_status_init(kbs_handle* h);
+int kbs_status_publish(kbs_handle* h, cudaStream_t st);
+int kbs_enter(kbs_handle* h);
 // scratch management (kbs_api.cu)
 int kbs_scratch_reserve(kbs_handle* h, size_t floats);
 
@@ -125,6 +135,11 @@ int kbs_launch_torque(kbs_handle* h, const float* action, const kbs_state_view& 
 int kbs_launch_torque_substeps(kbs_handle* h, const float* action, float* prev_action, const float* u_drop, const float* latency,
                                const float* q_sub, const float* qd_sub, const kbs_episode_view* ep, float* ctrl, int S, float sub_dt,
                                float drop_prob, int64_t ld, int64_t n, cudaStream_t st);
+int kbs_launch_mirror_loss(kbs_handle* h, const float* mean, const float* mean_m, const float* value, const float* value_m,
+                           float* action_loss, float* value_loss, float scale_a, float scale_c, int64_t T, int64_t ld, int64_t n,
+                           cudaStream_t st);
+int kbs_launch_actuator_rand(kbs_handle* h, const kbs_actuator_rand_params& rp, const float* u, const uint8_t* reset,
+                             const kbs_episode_view& ep, int64_t ld, int64_t n, cudaStream_t st);
 int kbs_launch_terminate(kbs_handle* h, const kbs_state_view& s, int32_t* codes, uint8_t* done, uint8_t* success,
                          float* pre, int64_t n, cudaStream_t st, int64_t T = 1);
 int kbs_launch_rewards(kbs_handle* h, const kbs_traj_view& tr, const kbs_reward_carry& carry, float* total,
@@ -180,6 +195,7 @@ struct KbsTcRolloutArgs {
   const float* action_in;     // [T][20][ld] stored actions whose log-prob is wanted, or nullptr (log-prob of own sample)
   float* entropy;             // [T][ld] or nullptr
   float* action_std;          // [T][20][ld] or nullptr
+  float* mean;                // [T][20][ld] dist.mean() or nullptr (persistent kernel only)
   float* ws;                  // kbs_tc_rollout_ws_floats
   int64_t chunk_len;          // > 0: before step t with t % chunk_len == 0, wait for chunk_events[t / chunk_len]
   cudaEvent_t* chunk_events;  //      (the input projections of that chunk of steps, produced on another stream)
@@ -321,6 +337,22 @@ __device__ __forceinline__ void sb_store_split8(void* __restrict__ sb, int64_t r
     *reinterpret_cast<uint4*>(base + sb_chunk_offset<R, KIND>(row, k, kblocks, 1)) =
         zero ? z4 : make_uint4(a.lo.x, a.lo.y, b.lo.x, b.lo.y);
   }
+}
+// FP16-split operands must stay finite and below the largest half (65504): anything else would silently become inf in the
+// hi plane.  Callers OR the per-thread result over the warp and set KBS_STATUS_F16_RANGE in the handle's health word.
+template <int KIND, int NV>
+__device__ __forceinline__ bool sb_out_of_range(const float (&x)[NV]) {
+  if (KIND != KBS_KIND_F16) return false;
+  float m = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) m = fmaxf(m, fabsf(x[i]));      // fmaxf drops NaNs: test them separately
+  bool bad = !(m < 65504.0f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) bad = bad || (x[i] != x[i]);
+  return bad;
+}
+__device__ __forceinline__ void sb_flag_range(unsigned int* status, bool bad) {
+  if (bad && status) atomicOr(status, unsigned(KBS_STATUS_F16_RANGE));       // rare: a predicated-off branch otherwise
 }
 // store 4 consecutive K values (k % 4 == 0)
 template <int R, int KIND, bool WB = false>

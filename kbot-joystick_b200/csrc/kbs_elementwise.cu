@@ -453,6 +453,70 @@ mirror_joints_kernel(const float* __restrict__ in, float* __restrict__ out, int6
   kbs_st4(out + t * KBS_NUM_JOINTS * ld, j, ld, n0, v);
 }
 
+// aux_losses of PPOVariables (train.py:1462-1481): action_mirror_loss = mean_j (mean - mirror_joints(mean_m))^2 * scale_a,
+// value_mirror_loss = (value - value_m)^2 * scale_c (the mean over the value's single element).  [T][.][ld] arrays;
+// grid = (env groups, T).
+__global__ void __launch_bounds__(kThreads)
+mirror_loss_kernel(const float* __restrict__ mean, const float* __restrict__ mean_m, const float* __restrict__ value,
+                   const float* __restrict__ value_m, float* __restrict__ action_loss, float* __restrict__ value_loss,
+                   float scale_a, float scale_c, int64_t ld, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  const int64_t t = blockIdx.y;
+  if (action_loss) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
+      float a[4], b[4];
+      kbs_ld4(mean + t * KBS_NUM_JOINTS * ld, j, ld, n0, a);
+      kbs_ld4(mean_m + t * KBS_NUM_JOINTS * ld, mirror_src_joint(j), ld, n0, b);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) { const float d = a[l] - (-b[l]); acc[l] = acc[l] + d * d; }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) acc[l] = (acc[l] / float(KBS_NUM_JOINTS)) * scale_a;
+    kbs_st4(action_loss, t, ld, n0, acc);
+  }
+  if (value_loss) {
+    float v[4], vm[4], o[4];
+    kbs_ld4(value, t, ld, n0, v);
+    kbs_ld4(value_m, t, ld, n0, vm);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) { const float d = v[l] - vm[l]; o[l] = (d * d) * scale_c; }
+    kbs_st4(value_loss, t, ld, n0, o);
+  }
+}
+
+// Per-episode actuator randomisation of ksim.PositionActuators (train.py:1097-1105; sampling law [U], see kbotstep.h):
+// u [5][20][ld] uniforms for (kp, kd, tau_limit, action_bias, torque_bias); grid = (env groups, 20 joints).
+__global__ void __launch_bounds__(kThreads)
+actuator_rand_kernel(const __grid_constant__ kbs_params P, const kbs_actuator_rand_params R, const float* __restrict__ u,
+                     const uint8_t* __restrict__ reset, const kbs_episode_view ep, int64_t ld, int64_t n) {
+  const int64_t n0 = (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4;
+  if (n0 >= n) return;
+  const int j = blockIdx.y;
+  bool rs[4] = {true, true, true, true};
+  if (reset) {
+    const uchar4 r4 = *reinterpret_cast<const uchar4*>(reset + n0);
+    rs[0] = r4.x != 0; rs[1] = r4.y != 0; rs[2] = r4.z != 0; rs[3] = r4.w != 0;
+  }
+  auto put = [&](float* dst, int which, float lo, float hi, float nominal) {
+    if (!dst) return;
+    float uu[4], o[4];
+    kbs_ld4(u + int64_t(which) * KBS_NUM_JOINTS * ld, j, ld, n0, uu);
+    if (reset) kbs_ld4(dst, j, ld, n0, o);
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if (rs[l]) o[l] = nominal * (lo + uu[l] * (hi - lo));
+    kbs_st4(dst, j, ld, n0, o);
+  };
+  put(const_cast<float*>(ep.kp), 0, 1.0f / R.kp_scale, R.kp_scale, P.kp[j]);
+  put(const_cast<float*>(ep.kd), 1, 1.0f / R.kd_scale, R.kd_scale, P.kd[j]);
+  put(const_cast<float*>(ep.tau_limit), 2, R.torque_limit_scale_low, 1.0f, P.ctrl_limit[j]);
+  put(const_cast<float*>(ep.action_bias), 3, -R.action_bias_scale, R.action_bias_scale, 1.0f);
+  put(const_cast<float*>(ep.torque_bias), 4, -R.torque_bias_scale, R.torque_bias_scale, 1.0f);
+}
+
 // =====================================================================================================
 // O12: COMDistanceObservation (train.py:509-659): >= 3 distinct contact.geom2 values -> distance between the centroid of the
 // convex hull of the floor-contact points (xy; non-floor rows become the origin and stay in the set, as written) and
@@ -1383,6 +1447,24 @@ int kbs_launch_torque(kbs_handle* h, const float* action, const kbs_state_view& 
   kbs_episode_view e{};
   if (ep) e = *ep;
   KBS_LAUNCH(h, KBS_K_TORQUE, st, (torque_kernel<<<groups4(n), kThreads, 0, st>>>(h->p, action, s, e, ctrl, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_mirror_loss(kbs_handle* h, const float* mean, const float* mean_m, const float* value, const float* value_m,
+                           float* action_loss, float* value_loss, float scale_a, float scale_c, int64_t T, int64_t ld, int64_t n,
+                           cudaStream_t st) {
+  KBS_LAUNCH(h, KBS_K_ADV_NORM, st,
+             (mirror_loss_kernel<<<dim3(groups4(n), unsigned(T)), kThreads, 0, st>>>(mean, mean_m, value, value_m, action_loss,
+                                                                                    value_loss, scale_a, scale_c, ld, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_actuator_rand(kbs_handle* h, const kbs_actuator_rand_params& rp, const float* u, const uint8_t* reset,
+                             const kbs_episode_view& ep, int64_t ld, int64_t n, cudaStream_t st) {
+  KBS_LAUNCH(h, KBS_K_TORQUE, st,
+             (actuator_rand_kernel<<<dim3(groups4(n), KBS_NUM_JOINTS), kThreads, 0, st>>>(h->p, rp, u, reset, ep, ld, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

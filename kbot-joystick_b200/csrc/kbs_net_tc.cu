@@ -210,6 +210,7 @@ struct LayerArgs {
   int F; int64_t soa_ld, n_env, n_pad;
   int ldo;                // MODE_PLAIN: row stride of `raw` (floats)
   float oscale;           // MODE_PLAIN: output multiplier (power of two: undoes the operand pre-scaling of small gradients)
+  unsigned int* status;   // health word: KBS_STATUS_F16_RANGE when a projection output leaves the FP16-split range (or nullptr)
 };
 struct LayerArgs2 { LayerArgs net[2]; };   // actor / critic share one launch
 
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
       if (a.mode == MODE_PROJ || a.mode == MODE_PROJ_SOA) {
         const int col0 = w.tile * kTileCols + c2 * 64;
         if (col0 < H) {
+          sb_flag_range(a.status, sb_out_of_range<KIND, 64>(v));
 #pragma unroll
           for (int i = 0; i < 64; i += 4) {
             const float o[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
@@ -758,6 +760,7 @@ struct PArgs {
   kbs_episode_view ep;
   float* action; float* log_prob; float* ctrl; float* value;
   const float* action_in; float* entropy; float* std;
+  float* mean;                     // [T][20][ld] dist.mean() = the low-pass-filtered mean (mirror loss), or nullptr
   int dbg;                         // profiling only (KBS_PERSIST_DBG): 1 = ignore dependencies (wrong results, timing probe)
   unsigned int* status;            // != 0: a dependency wait timed out (bug / lost CTA)
   long long* trace;                // per CTA [8]: total cycles, poller wait cycles, items, issuer wait-for-stage cycles,
@@ -783,8 +786,14 @@ __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Blocks until the counters item `it` depends on have reached their targets; returns cycles spent.
-__device__ __forceinline__ long long p_wait_deps(const PArgs& a, const PItem& it) {
+// Blocks until the counters item `it` depends on have reached their targets; returns cycles spent.  Bounded in WALL-CLOCK
+// time (globaltimer: independent of the SM clock): after kPWaitTimeoutNs without progress the CTA records
+// KBS_STATUS_TIMEOUT_* in the health word and -- like every other CTA that then sees the word set -- stops waiting
+// altogether (`drain`): the launch finishes quickly with garbage results instead of hanging the GPU, and the entry point
+// that launched it reports KBS_E_DEVICE at the next call (kbs_enter).
+constexpr unsigned long long kPWaitTimeoutNs = 2000000000ull;
+__device__ __forceinline__ long long p_wait_deps(const PArgs& a, const PItem& it, bool& drain) {
+  if (drain) return 0;
   const PNet& N = a.net[it.net];
   const unsigned int full_l = unsigned(a.tiles * kEpiWarpsP), full_h = unsigned(kEpiWarpsP);
   const unsigned int* fp[3]; unsigned int tg[3]; int nd = 0;
@@ -805,10 +814,17 @@ __device__ __forceinline__ long long p_wait_deps(const PArgs& a, const PItem& it
   for (int i = nd; i < 3; ++i) { fp[i] = fp[0]; tg[i] = 0u; }   // fixed three independent loads per poll
   const long long c0 = clock64();
   unsigned int polls = 0;
+  unsigned long long t0 = 0;
   while (true) {
     const unsigned int v0 = ld_volatile_u32(fp[0]), v1 = ld_volatile_u32(fp[1]), v2 = ld_volatile_u32(fp[2]);
     if (v0 >= tg[0] && v1 >= tg[1] && v2 >= tg[2]) break;
-    if (++polls > (1u << 22)) { atomicExch(a.status, 1u + unsigned(it.kind)); break; }
+    if ((++polls & 1023u) == 0u) {
+      if (ld_volatile_u32(a.status) & 3u) { drain = true; break; }          // another CTA gave up: drain
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kPWaitTimeoutNs) { atomicOr(a.status, 1u + unsigned(it.kind)); drain = true; break; }
+    }
   }
   __threadfence();                                            // acquire: the counted stores are visible
   return clock64() - c0;
@@ -889,10 +905,11 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
       // counter polls and the fence stay off the load pipeline's critical path; publishes "items 0..j-1 may start" =====
       int j = 0;
       long long waited = 0;
+      bool drain = false;
       for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
         const PItem it = p_decode(args, gi);
         if (!it.valid) continue;
-        if (!(args.dbg & 1)) waited += p_wait_deps(args, it);
+        if (!(args.dbg & 1)) waited += p_wait_deps(args, it, drain);
         *dep_seq = ++j;
       }
       if (tr) { tr[1] = waited; tr[2] = j; }
@@ -1178,6 +1195,7 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
               s_log = s_log + logf(sd);
               if (args.action) args.action[t * KBS_NUM_JOINTS * ld + o] = act;
               if (args.std) args.std[t * KBS_NUM_JOINTS * ld + o] = sd;
+              if (args.mean) args.mean[t * KBS_NUM_JOINTS * ld + o] = yn;
               if (args.ctrl) {                         // PositionActuators.get_ctrl (train.py:1091-1105)
                 const float target = args.ep.action_bias ? __fadd_rn(act, in_ab[jj]) : act;
                 float tau = __fsub_rn(__fmul_rn(in_kp[jj], __fsub_rn(target, in_q[jj])), __fmul_rn(in_kd[jj], in_qd[jj]));
@@ -1267,6 +1285,7 @@ struct FProjArgs {
   char* x_sb;              // out [T] x sbb
   size_t sbb;
   int items;               // T * n_pad / 128
+  unsigned int* status;    // health word: KBS_STATUS_F16_RANGE when an input or an output leaves the FP16-split range
   int dbg;                 // profiling only (KBS_FPROJ_DBG): 1 converters skip load + split, 2 no MMAs, 4 no raw copies,
                            // 8 no epilogue stores
   long long* trace;        // per CTA [16] at trace + (148 + blockIdx.x) * 16: total cycles, items, then wait cycles of
@@ -1366,6 +1385,7 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
     const int set = cw >> 2;
     const int r = (cw & 3) * 32 + lane;
     uint32_t g = 0;
+    bool bad = false;                                   // an input outside the FP16-split range (raw physical quantities)
     for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
       const int64_t e0 = int64_t(item % ppt) * kPanelRows;
       const bool valid = e0 + r < a.n;
@@ -1378,6 +1398,7 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
         float x[kFeat];
 #pragma unroll
         for (int i = 0; i < kFeat; ++i) x[i] = (valid && i < nv && !(a.dbg & 1)) ? rf[i * kPanelRows] : 0.0f;
+        bad = bad || sb_out_of_range<KIND, kFeat>(x);
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[sr]);
         // Stage g reuses the operand slot of stage g - 3.  Its generic-proxy stores land ~50 cycles after the barrier flips,
@@ -1412,6 +1433,7 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
         if (lane == 0) mbar_arrive(&full[s]);
       }
     }
+    sb_flag_range(a.status, bad);
     if (tr && warp == kFConvWarp0 && lane == 0) { tr[4] = tw[0]; tr[5] = tw[1]; }
   } else if (warp == 0) {
     // ===== MMA issuer =====
@@ -1480,6 +1502,7 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
         const float* bs = bias_s + half * 128 + cc * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = (v[i] + kCorr * cr[i]) + bs[i];
+        sb_flag_range(a.status, sb_out_of_range<KIND, 32>(v));
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           const float x0[4] = {v[8 * c8], v[8 * c8 + 1], v[8 * c8 + 2], v[8 * c8 + 3]};
@@ -1664,6 +1687,7 @@ struct CarryJobs {
   void* blk[8];
   int mode[8];
   int64_t ld_rm;     // row stride of the row-major side (H for the ABI carries, the record width for flat carries)
+  unsigned int* status;   // health word (FP16-split range of the caller's hidden carries)
 };
 // Both sides coalesced: a block moves a 32-row x 32-group tile (group = 8 consecutive units = 32 B) through shared
 // memory -- on the row-major side a warp touches 1 KB of ONE row (flat carry records are 4 KB apart: one row per lane
@@ -1704,6 +1728,7 @@ carry_convert_kernel(const __grid_constant__ CarryJobs J, int64_t n, int64_t n_p
         *reinterpret_cast<float4*>(fb + fb_offset(row, kg * 8 + 4, H)) = b;
       } else {
         const float x0[4] = {a.x, a.y, a.z, a.w}, x1[4] = {b.x, b.y, b.z, b.w};
+        sb_flag_range(J.status, sb_out_of_range<KIND, 4>(x0) || sb_out_of_range<KIND, 4>(x1));
         sb_store_split8<kPanelRows, KIND>(J.blk[j], row, kg * 8, H / kbs_block_k(KIND), sb_split4<KIND>(x0), sb_split4<KIND>(x1),
                                           false);
       }
@@ -1737,7 +1762,8 @@ carry_convert_kernel(const __grid_constant__ CarryJobs J, int64_t n, int64_t n_p
 template <int KIND>
 __global__ void __launch_bounds__(256)
 pack_soa_sb_kernel(const float* __restrict__ soa, int F, int64_t ld, char* __restrict__ sb, int64_t n, int64_t n_pad,
-                   int Kp, int64_t T, const float* __restrict__ cinert, const float* __restrict__ cvel) {
+                   int Kp, int64_t T, const float* __restrict__ cinert, const float* __restrict__ cvel,
+                   unsigned int* __restrict__ status) {
   const int kq = Kp / 8;
   const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
   const int64_t rows = T * n_pad;
@@ -1763,6 +1789,7 @@ pack_soa_sb_kernel(const float* __restrict__ soa, int F, int64_t ld, char* __res
       x[i] = __ldcs(p + e);
     }
   }
+  sb_flag_range(status, sb_out_of_range<KIND, 8>(x));
   const float x0[4] = {x[0], x[1], x[2], x[3]}, x1[4] = {x[4], x[5], x[6], x[7]};
   sb_store_split8<kPanelRows, KIND>(sb, row, kc * 8, Kp / kbs_block_k(KIND), sb_split4<KIND>(x0), sb_split4<KIND>(x1), false);
 }
@@ -1937,15 +1964,14 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
   KbsNet& N = h->net[net];
   const int H = h->p.hidden_size, kind = tc_kind(h);
   if (H % kUnitsPerTile) return KBS_E_SHAPE;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->tc_attr_set) {      // per device (context), so per handle: a handle on another GPU of the same process needs its own opt-in
     KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_tc_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_tc_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
     KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
     KBS_CUDA_TRY(cudaFuncSetAttribute(input_proj_fused_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
     KBS_CUDA_TRY(cudaFuncSetAttribute(input_proj_fused_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
-    attr_set = true;
+    h->tc_attr_set = true;
   }
   const size_t bytes = 2 * layer_image_bytes(h) * h->p.depth + proj_image_bytes(h, net) + head_image_bytes(h) +
                        fused_image_bytes(h, net) + projq_image_bytes(h, net);
@@ -2267,6 +2293,7 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
                           int64_t ld, int64_t n, int64_t T, cudaStream_t st, const float* cinert, const float* cvel,
                           KbsTcRolloutArgs* r_out) {
   const int H = h->p.hidden_size, kind = tc_kind(h);
+  { const int rc0 = kbs_status_init(h); if (rc0) return rc0; }
   int proj_nets = 0;
   const int64_t np = pad_rows(n);
   // Default: input_proj_fused_kernel (FP16-split datapath, H = 256) straight from the SoA observations.  Otherwise the staged
@@ -2307,6 +2334,7 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
         fa.w_sb = projq_w(h, k, which); fa.bias = projq_bias(h, k, which);
         fa.x_sb = reinterpret_cast<char*>(x_sb_all[k]); fa.sbb = act_sb_bytes(h, n);
         fa.items = int(T * np / kPanelRows);
+        fa.status = h->persist_status;
         { const char* e = getenv("KBS_FPROJ_DBG"); fa.dbg = e ? atoi(e) : 0; }
         fa.trace = h->trace_buf;
         const unsigned grid = unsigned(fa.items < h->num_sms ? fa.items : h->num_sms);
@@ -2321,9 +2349,9 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
       const int64_t total = T * np * (Kp / 8);
       const unsigned gb = unsigned((total + 255) / 256);
       if (kind == KBS_KIND_TF32)
-        KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv)));
+        KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv, h->persist_status)));
       else
-        KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv)));
+        KBS_LAUNCH(h, KBS_K_PACK, st, (pack_soa_sb_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(obs_soa[k], N.num_in, ld, osb, n, np, Kp, T, ci, cv, h->persist_status)));
       a.mode = MODE_PROJ;
       if (fuse) continue;            // the packed observations ARE layer 0's input operand: no projection items (panels = 0)
     } else {
@@ -2337,6 +2365,7 @@ int kbs_tc_input_proj_all(kbs_handle* h, int nets, const float* const* obs_soa, 
     a.w_sb = proj_w(h, k);
     a.bias_t = proj_bias(h, k);
     a.x_next_sb = reinterpret_cast<char*>(x_sb_all[k]);
+    a.status = h->persist_status;
     a.n = T * np;                    // every staged row is written (pad rows carry the bias: harmless, never read back)
     a.H = H; a.kb_x = Kp / kbs_block_k(kind); a.kb_h = 0;
     a.panels = int(T * np / kPanelRows); a.tiles = proj_cols(h) / kTileCols;
@@ -2362,11 +2391,11 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
   const int nets = r.with_critic ? 2 : 1;
   for (int k = 0; k < nets; ++k)
     if (!h->net[k].packed || !h->net[k].tc_image) return KBS_E_STATE;
-  static bool attr_set = false;
+  { const int rc0 = kbs_status_init(h); if (rc0) return rc0; }
   const int head_smem = (kHeadEnvs * (H + 4) + KBS_ACTOR_OUT * H + kHeadEnvs * 41 + 4 * 32 * 2) * 4;
-  if (!attr_set) {
+  if (!h->head_attr_set) {
     KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
+    h->head_attr_set = true;
   }
   const int64_t n = r.n, ld = r.ld, np = pad_rows(n);
   const size_t sbb = act_sb_bytes(h, n), per_net = rollout_ws_per_net_bytes(h, n);
@@ -2384,11 +2413,13 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
   const int legacy = legacy_env ? atoi(legacy_env) : 0;
   const bool persistent = !legacy && kbs_tc_persistent_available(h, n, r.T, nets);
   if ((r.x_is_obs[0] || r.x_is_obs[1]) && !persistent) return KBS_E_STATE;         // folded input projection: persistent only
+  if (r.mean && !persistent) return KBS_E_STATE;                                   // dist.mean() output: persistent kernel only
   if (r.carry_ld && (!persistent || nets * depth * 2 > 8 || H % 8)) return KBS_E_STATE;   // flat carries: persistent kernel only
   const size_t slot_f = r.carry_ld ? size_t(H) : size_t(n) * H;                  // floats between carry slots
   if (nets * depth * 2 <= 8 && H % 8 == 0) {                       // ABI carry: h -> SB (parity 0), c -> FB; one launch
     CarryJobs J{};
     J.ld_rm = r.carry_ld ? r.carry_ld : H;
+    J.status = h->persist_status;
     int j = 0;
     for (int k = 0; k < nets; ++k)
       for (int l = 0; l < depth; ++l) {
@@ -2406,7 +2437,10 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
   const int panels = int(np / kPanelRows), tiles = H / kUnitsPerTileP;
   if (persistent) {
     // ---- persistent recurrence: one cooperative launch for all T steps (rollout_persist_kernel) ----
-    if (!h->persist_status) KBS_CUDA_TRY(cudaMalloc(&h->persist_status, 256));
+    // Phase A produced on the aux stream in chunks (KBS_ROLLOUT_CHUNKS > 1): this kernel reads the operands of ALL T
+    // steps, so every chunk must have landed before it starts (the per-step loop below waits chunk by chunk instead).
+    if (r.chunk_len > 0)
+      for (int64_t c = 0; c * r.chunk_len < r.T; ++c) KBS_CUDA_TRY(cudaStreamWaitEvent(st, r.chunk_events[c], 0));
     PArgs a{};
     for (int k = 0; k < nets; ++k) {
       PNet& N = a.net[k];
@@ -2419,7 +2453,6 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
       N.w_head = head_w(h, k); N.bias_head = head_bias(h, k);
       KBS_CUDA_TRY(cudaMemsetAsync(flags[k], 0, rollout_flag_bytes(h, n), st));
     }
-    KBS_CUDA_TRY(cudaMemsetAsync(h->persist_status, 0, 4, st));
     a.nets = nets; a.depth = depth; a.H = H; a.panels = panels; a.tiles = tiles;
     a.n = n; a.ld = ld; a.T = r.T; a.sbb = sbb;
     a.done = r.done;
@@ -2429,7 +2462,7 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     a.qd = r.qvel ? r.qvel + size_t(6) * ld : nullptr;
     a.ep = r.ep;
     a.action = r.action; a.log_prob = r.log_prob; a.ctrl = (r.ctrl && r.qpos && r.qvel) ? r.ctrl : nullptr; a.value = r.value;
-    a.action_in = r.action_in; a.entropy = r.entropy; a.std = r.action_std;
+    a.action_in = r.action_in; a.entropy = r.entropy; a.std = r.action_std; a.mean = r.mean;
     a.status = h->persist_status;
     { const char* e = getenv("KBS_PERSIST_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.trace = h->trace_buf;
@@ -2451,9 +2484,11 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     else
       KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<KBS_KIND_F16>, h->p, a)));
     KBS_CUDA_TRY(le);
+    { const int rc0 = kbs_status_publish(h, st); if (rc0) return rc0; }
     if (nets * depth * 2 <= 8 && H % 8 == 0) {                       // FB state -> ABI carry; one launch
       CarryJobs J{};
       J.ld_rm = r.carry_ld ? r.carry_ld : H;
+      J.status = nullptr;
       int j = 0;
       for (int k = 0; k < nets; ++k) {
         float* dst = (r.carry_ld && r.carry_out[k]) ? r.carry_out[k] : r.carry[k];

@@ -419,6 +419,67 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   p[i] = p[i] - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);       // optax.scale_by_adam (eps_root = 0) then -lr
 }
 
+// optax.adamw (train.py:1064-1065) with ksim's gradient clipping folded in [U]: see kbs_adamw_step in kbotstep.h.
+// norm / step_dev may be nullptr.  Every thread derives the same clip factor and bias corrections from the same device
+// words, so the update is a pure elementwise map (bitwise identical on every rank).
+__global__ void __launch_bounds__(kT)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t count,
+             const kbs_adamw_params o, const float* __restrict__ norm, const long long* __restrict__ step_dev, long long step) {
+  const int64_t i = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (i >= count) return;
+  float scale = o.grad_scale;
+  if (norm) {
+    const float nn = norm[0] * o.grad_scale;                     // norm of the gradient the optimiser sees
+    if (!(fabsf(nn) <= 3.0e38f)) return;                         // NaN / inf: ksim skips the update, optimiser state untouched
+    if (o.max_grad_norm > 0.0f && nn > o.max_grad_norm) scale = scale * (o.max_grad_norm / fmaxf(nn, 1e-6f));
+  }
+  const float s = float(step_dev ? step_dev[0] + 1 : step);
+  const float bc1 = 1.0f - powf(o.b1, s), bc2 = 1.0f - powf(o.b2, s);
+  const float gi = g[i] * scale;
+  const float mi = o.b1 * m[i] + (1.0f - o.b1) * gi;
+  const float vi = o.b2 * v[i] + (1.0f - o.b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float pi = p[i];
+  p[i] = pi - o.lr * ((mi / bc1) / (sqrtf(vi / bc2) + o.eps) + o.weight_decay * pi);
+}
+__global__ void step_advance_kernel(long long* step_dev, const float* __restrict__ norm, float grad_scale) {
+  if (norm && !(fabsf(norm[0] * grad_scale) <= 3.0e38f)) return;
+  step_dev[0] = step_dev[0] + 1;
+}
+
+// sum of squares in double, fixed shape: kNormBlocks blocks x kT threads, grid-stride, fixed-order tree per block, then
+// one block adds the kNormBlocks partials in order
+constexpr int kNormBlocks = 296;
+__global__ void __launch_bounds__(kT)
+sumsq_partial_kernel(const float* __restrict__ g, int64_t count, double* __restrict__ partial) {
+  __shared__ double sh[kT];
+  double a = 0.0;
+  for (int64_t i = int64_t(blockIdx.x) * kT + threadIdx.x; i < count; i += int64_t(kNormBlocks) * kT) {
+    const double x = double(g[i]);
+    a += x * x;
+  }
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = kT / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(kT)
+sumsq_final_kernel(const double* __restrict__ partial, float* __restrict__ norm_out) {
+  __shared__ double sh[kT];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < kNormBlocks; i += kT) a += partial[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = kT / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) norm_out[0] = float(sqrt(sh[0]));
+}
+
 unsigned blocks(int64_t n) { return unsigned((n + kT - 1) / kT); }
 
 struct NetWork {      // per-net workspace (floats), carved from the handle's scratch
@@ -600,6 +661,7 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
   if (b->T <= 0 || n <= 0 || b->ld < n || (b->ld & 3)) return KBS_E_SHAPE;
   for (int k = 0; k < 2; ++k)
     if (!h->net[k].packed) return KBS_E_STATE;
+  { const int rc0 = kbs_enter(h); if (rc0) return rc0; }
   cudaStream_t st = (cudaStream_t)stream;
   const int H = h->p.hidden_size, depth = h->p.depth;
   const int64_t T = b->T, ld = b->ld, rows = T * n;
@@ -700,6 +762,31 @@ int kbs_adam_step(kbs_handle* h, float* param, const float* grad, float* m, floa
   cudaStream_t st = (cudaStream_t)stream;
   const float bc1 = 1.0f - powf(b1, float(step)), bc2 = 1.0f - powf(b2, float(step));
   KBS_LAUNCH(h, KBS_K_ADV_NORM, st, (adam_kernel<<<blocks(count), kT, 0, st>>>(param, grad, m, v, count, lr, b1, b2, eps, grad_scale, bc1, bc2)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_adamw_step(kbs_handle* h, float* param, const float* grad, float* m, float* v, int64_t count, const kbs_adamw_params* o,
+                   const float* grad_norm, int64_t* step_dev, int64_t step, void* stream) {
+  if (!h || !param || !grad || !m || !v || !o) return KBS_E_NULL;
+  if (count <= 0 || (!step_dev && step <= 0)) return KBS_E_SHAPE;
+  if (!(o->b1 >= 0.0f && o->b1 < 1.0f) || !(o->b2 >= 0.0f && o->b2 < 1.0f) || !(o->eps >= 0.0f)) return KBS_E_PARAM;
+  cudaStream_t st = (cudaStream_t)stream;
+  static_assert(sizeof(long long) == sizeof(int64_t), "step counter width");
+  long long* sd = reinterpret_cast<long long*>(step_dev);
+  KBS_LAUNCH(h, KBS_K_ADV_NORM, st, (adamw_kernel<<<blocks(count), kT, 0, st>>>(param, grad, m, v, count, *o, grad_norm, sd, (long long)step)));
+  if (sd) KBS_LAUNCH(h, KBS_K_ADV_NORM, st, (step_advance_kernel<<<1, 1, 0, st>>>(sd, grad_norm, o->grad_scale)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_grad_norm(kbs_handle* h, const float* grad, int64_t count, float* norm_out, void* stream) {
+  if (!h || !grad || !norm_out) return KBS_E_NULL;
+  if (count <= 0) return KBS_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->norm_partial) KBS_CUDA_TRY(cudaMalloc(&h->norm_partial, sizeof(double) * kNormBlocks));
+  KBS_LAUNCH(h, KBS_K_ADV_NORM, st, (sumsq_partial_kernel<<<kNormBlocks, kT, 0, st>>>(grad, count, h->norm_partial)));
+  KBS_LAUNCH(h, KBS_K_ADV_NORM, st, (sumsq_final_kernel<<<1, kT, 0, st>>>(h->norm_partial, norm_out)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

@@ -94,6 +94,13 @@ class KbotStep:
         L.check(self.lib.kbs_device_status(self._h, C.byref(v)), "kbs_device_status")
         return int(v.value)
 
+    def device_status_reset(self) -> None:
+        L.check(self.lib.kbs_device_status_reset(self._h), "kbs_device_status_reset")
+
+    def scratch_lock(self, on: bool) -> None:
+        """While locked, a call that would have to reallocate the library's scratch fails instead (CUDA-graph safety)."""
+        L.check(self.lib.kbs_scratch_lock(self._h, 1 if on else 0), "kbs_scratch_lock")
+
     def profile(self, on: bool) -> None:
         L.check(self.lib.kbs_profile_enable(self._h, 1 if on else 0), "kbs_profile_enable")
 
@@ -186,6 +193,36 @@ class KbotStep:
         """optax.adam on one flat parameter tensor (train.py:1057-1063)."""
         L.check(self.lib.kbs_adam_step(self._h, L.ptr(param), L.ptr(grad), L.ptr(m), L.ptr(v), param.numel(), lr, b1, b2, eps,
                                        grad_scale, step, _stream()), "kbs_adam_step")
+
+    def grad_norm(self, grad, out=None):
+        """optax.global_norm of one flat gradient tensor -> device tensor [1] (deterministic, double accumulation)."""
+        if out is None:
+            out = torch.empty((1,), device=grad.device)
+        L.check(self.lib.kbs_grad_norm(self._h, L.ptr(grad), grad.numel(), L.ptr(out), _stream()), "kbs_grad_norm")
+        return out
+
+    def adamw_step(self, param, grad, m, v, step: int = 0, grad_norm=None, step_dev=None, **opt) -> None:
+        """optax.adamw (train.py:1064-1065) + ksim's global-norm clip / non-finite skip [U] on one flat parameter tensor.
+        opt: lr, b1, b2, eps, weight_decay, grad_scale, max_grad_norm (kbs_adamw_params; defaults = the launch config).
+        step_dev: device int64 [1] counter of applied updates (advanced here) or None -> `step` (>= 1) is used."""
+        o = L.KbsAdamwParams()
+        L.check(self.lib.kbs_adamw_default_params(C.byref(o)), "kbs_adamw_default_params")
+        for k, val in opt.items():
+            setattr(o, k, val)
+        L.check(self.lib.kbs_adamw_step(self._h, L.ptr(param), L.ptr(grad), L.ptr(m), L.ptr(v), param.numel(), C.byref(o),
+                                        L.ptr(grad_norm), L.ptr(step_dev), step, _stream()), "kbs_adamw_step")
+
+    def sample_actuator_randomization(self, u, episode: dict, reset=None, n_envs: int | None = None, **scales) -> None:
+        """Per-episode PositionActuators randomisation (train.py:1097-1105): u [5, 20, ld] uniforms -> episode["kp"], ["kd"],
+        ["tau_limit"], ["action_bias"], ["torque_bias"] ([20, ld] each, written where reset != 0 / everywhere)."""
+        ld = u.shape[-1]
+        rp = L.KbsActuatorRandParams()
+        L.check(self.lib.kbs_actuator_rand_default_params(C.byref(rp)), "kbs_actuator_rand_default_params")
+        for k, val in scales.items():
+            setattr(rp, k, val)
+        ev = _view(L.KbsEpisodeView, EPISODE_ROWS, episode)
+        L.check(self.lib.kbs_sample_actuator_randomization(self._h, C.byref(rp), L.ptr(u), L.ptr(reset), C.byref(ev), ld,
+                                                           n_envs or ld, _stream()), "kbs_sample_actuator_randomization")
 
     def com_distance(self, geom1, geom2, pos, subtree_com_base, out=None, n_envs: int | None = None):
         """COMDistanceObservation (train.py:509-659) for T steps: geom1/geom2 int32 [T, ncon, ld], pos [T, 3 ncon, ld],
@@ -323,8 +360,11 @@ class KbotStep:
         return action, carry_out
 
     def ppo_variables(self, actor_obs, action, done, actor_carry, lpf, critic_obs=None, critic_carry=None,
-                      want_std: bool = True, want_mean: bool = False, n_envs: int | None = None) -> dict:
-        """get_ppo_variables on a stored trajectory (train.py:1510-1524): returns log_probs/values/entropy/action_std."""
+                      want_std: bool = True, want_mean: bool = False, n_envs: int | None = None, mirror: dict | None = None) -> dict:
+        """get_ppo_variables on a stored trajectory (train.py:1510-1524): returns log_probs/values/entropy/action_std.
+        mirror (aux_losses, train.py:1462-1481): {"actor_obs", "critic_obs" (mirrored concatenations from
+        mirror_observations), "actor_carry", "critic_carry", "lpf" (the *_mirror carries, in/out), "actor_scale",
+        "critic_scale"} -> out["action_mirror_loss"], out["value_mirror_loss"] [T, ld]."""
         T, _, ld = actor_obs.shape
         dev = actor_obs.device
         out = {"log_probs": torch.empty((T, ld), device=dev), "entropy": torch.empty((T, ld), device=dev),
@@ -332,6 +372,15 @@ class KbotStep:
                "action_std": torch.empty((T, 20, ld), device=dev) if want_std else None,
                "mean": torch.empty((T, 20, ld), device=dev) if want_mean else None}
         io = L.KbsPpoIO()
+        if mirror is not None:
+            out["action_mirror_loss"] = torch.empty((T, ld), device=dev)
+            out["value_mirror_loss"] = torch.empty((T, ld), device=dev) if mirror.get("critic_obs") is not None else None
+            io.actor_obs_mirror, io.critic_obs_mirror = L.ptr(mirror["actor_obs"]), L.ptr(mirror.get("critic_obs"))
+            io.actor_mirror_carry, io.critic_mirror_carry = L.ptr(mirror["actor_carry"]), L.ptr(mirror.get("critic_carry"))
+            io.lpf_mirror = L.ptr(mirror["lpf"])
+            io.action_mirror_loss, io.value_mirror_loss = L.ptr(out["action_mirror_loss"]), L.ptr(out["value_mirror_loss"])
+            io.actor_mirror_loss_scale = mirror.get("actor_scale", 1.0)       # train.py:115-122 defaults (launch: 0.0)
+            io.critic_mirror_loss_scale = mirror.get("critic_scale", 0.01)
         io.actor_obs, io.critic_obs, io.action, io.done = L.ptr(actor_obs), L.ptr(critic_obs), L.ptr(action), L.ptr(done)
         io.actor_carry, io.critic_carry, io.lpf = L.ptr(actor_carry), L.ptr(critic_carry), L.ptr(lpf)
         io.log_probs, io.values, io.entropy = L.ptr(out["log_probs"]), L.ptr(out["values"]), L.ptr(out["entropy"])

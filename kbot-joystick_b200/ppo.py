@@ -1,7 +1,10 @@
 """PPO minibatch update on top of the C-ABI (BASELINE configs[3]): kbs_ppo_grad -> gradient all-reduce over
-NCCL (the only collective of the path: environments are sharded, weights replicated) -> kbs_adam_step -> re-pack.
+NCCL (the only collective of the path: environments are sharded, weights replicated) -> kbs_grad_norm -> kbs_adamw_step
+-> re-pack.
 
-Mirrors ksim's PPOTask.update_model for this Task (train.py:1057-1063 optimiser, 1763-1770 hyper-parameters): torch is
+Mirrors ksim's PPOTask.update_model for this Task: the optimiser is optax.adamw(5e-4, weight_decay = 1e-5) -- the branch
+get_optimizer takes with the launch configuration (train.py:1059-1065, 95-102, 1761-1791) -- wrapped in ksim's global-norm
+gradient clip and non-finite-update skip [U: parameterised, `max_grad_norm`]; hyper-parameters train.py:1763-1770.  torch is
 allocation, streams and torch.distributed only."""
 from __future__ import annotations
 
@@ -49,10 +52,10 @@ def allreduce_sum_(flat: torch.Tensor) -> int:
 
 
 class PpoUpdater:
-    """grad -> all-reduce -> Adam -> re-pack, for the actor and the critic."""
+    """grad -> all-reduce -> global norm -> AdamW (clip folded in) -> re-pack, for the actor and the critic."""
 
     def __init__(self, engine, w_actor: dict, w_critic: dict, lr: float = 5e-4, b1: float = 0.9, b2: float = 0.999,
-                 eps: float = 1e-8, **loss_hyper):
+                 eps: float = 1e-8, weight_decay: float = 1e-5, max_grad_norm: float = 10.0, **loss_hyper):
         dev = torch.device("cuda", torch.cuda.current_device())
         self.eng = engine
         self.pa, self.pc = NetParams(w_actor, dev), NetParams(w_critic, dev)
@@ -61,8 +64,9 @@ class PpoUpdater:
         self.m, self.v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
         self.param = torch.cat([self.pa.flat, self.pc.flat])
         self.pa.flat, self.pc.flat = self.param[:self.pa.flat.numel()], self.param[self.pa.flat.numel():]
-        self.step_count = 0
-        self.opt = dict(lr=lr, b1=b1, b2=b2, eps=eps)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)   # updates applied so far (device-side: graph-replayable)
+        self.norm = torch.zeros(1, device=dev)                            # global L2 norm of the (summed) gradient
+        self.opt = dict(lr=lr, b1=b1, b2=b2, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
         self.loss_hyper = loss_hyper
         self._repack()
 
@@ -83,6 +87,7 @@ class PpoUpdater:
         with torch.cuda.graph(self._graph):
             self._graph_out = self.grads(batch, n_envs)
         self._graph_batch = batch
+        self.eng.scratch_lock(True)        # the graph holds pointers into the library's scratch: it must not be reallocated
 
     def update(self, batch: dict, n_envs: int) -> dict:
         if getattr(self, "_graph", None) is not None and batch is self._graph_batch:
@@ -91,7 +96,12 @@ class PpoUpdater:
         else:
             out = self.grads(batch, n_envs)
         world = allreduce_sum_(self.grad)                   # the PPO gradient all-reduce (NVLink / NVSwitch via NCCL)
-        self.step_count += 1
-        self.eng.adam_step(self.param, self.grad, self.m, self.v, self.step_count, grad_scale=1.0 / world, **self.opt)
+        self.eng.grad_norm(self.grad, out=self.norm)        # of the SUM; kbs_adamw_step applies grad_scale = 1 / world to it
+        self.eng.adamw_step(self.param, self.grad, self.m, self.v, grad_norm=self.norm, step_dev=self.step_dev,
+                            grad_scale=1.0 / world, **self.opt)
         self._repack()
         return out
+
+    @property
+    def step_count(self) -> int:
+        return int(self.step_dev.item())

@@ -743,6 +743,49 @@ def position_actuator_substeps(action, prev_action, u_drop, latency, q_sub, qd_s
     return np.stack(out), applied
 
 
+def actuator_randomization(u, kp_scale=1.4, kd_scale=1.4, torque_limit_scale_low=0.5, action_bias_scale=0.02,
+                           torque_bias_scale=0.0):
+    """[U fork] per-episode randomisation of ksim.PositionActuators (arguments [R] train.py:1097-1105; the sampling law is
+    oracle-defined, reference-unverified -- tools/verify_against_ref.py item `position_actuators`):
+      kp = kp_nominal U(1/kp_scale, kp_scale), kd likewise, tau_limit = ctrl_limit U(low, 1),
+      action_bias = U(-s_a, s_a), torque_bias = U(-s_t, s_t);  u [5, ..., 20] uniforms in [0, 1)."""
+    dt = u.dtype
+    c = lambda v: np.asarray(v, dt)
+
+    def lerp(uu, lo, hi, nominal):
+        return nominal * (c(lo) + uu * (c(hi) - c(lo)))
+
+    return {"kp": lerp(u[0], c(1.0) / c(kp_scale), kp_scale, KP64.astype(dt)),
+            "kd": lerp(u[1], c(1.0) / c(kd_scale), kd_scale, KD64.astype(dt)),
+            "tau_limit": lerp(u[2], torque_limit_scale_low, 1.0, CTRL_LIMIT64.astype(dt)),
+            "action_bias": lerp(u[3], -action_bias_scale, action_bias_scale, c(1.0)),
+            "torque_bias": lerp(u[4], -torque_bias_scale, torque_bias_scale, c(1.0))}
+
+
+# --------------------------------------------------------------------------------------
+# Optimiser [R] train.py:1059-1077 (launch config: adam_weight_decay = 1e-5 -> optax.adamw) + ksim's clipping [U]
+# --------------------------------------------------------------------------------------
+
+
+def adamw_update(param, grad, m, v, step: int, lr=5e-4, b1=0.9, b2=0.999, eps=1e-8, weight_decay=1e-5, grad_scale=1.0,
+                 max_grad_norm=10.0):
+    """optax.adamw(lr, weight_decay) = chain(scale_by_adam(b1, b2, eps, eps_root = 0), add_decayed_weights(wd),
+    scale_by_learning_rate(lr)) applied with eqx.apply_updates, in float64 on flat arrays; `step` = count + 1 (>= 1).
+    Around it ksim's update [U]: global-norm clip to max_grad_norm (<= 0: off), and no update at all (state untouched)
+    when the norm is not finite.  Returns (param, m, v, applied)."""
+    g = np.asarray(grad, np.float64) * grad_scale
+    norm = float(np.sqrt(np.sum(g * g)))
+    if not np.isfinite(norm):
+        return np.asarray(param, np.float64), np.asarray(m, np.float64), np.asarray(v, np.float64), False
+    if max_grad_norm > 0 and norm > max_grad_norm:
+        g = g * (max_grad_norm / max(norm, 1e-6))
+    m2 = b1 * np.asarray(m, np.float64) + (1 - b1) * g
+    v2 = b2 * np.asarray(v, np.float64) + (1 - b2) * g * g
+    mh, vh = m2 / (1 - b1 ** step), v2 / (1 - b2 ** step)
+    p64 = np.asarray(param, np.float64)
+    return p64 - lr * (mh / (np.sqrt(vh) + eps) + weight_decay * p64), m2, v2, True
+
+
 # --------------------------------------------------------------------------------------
 # Terminations Z1  train.py:1258-1269, 817-823
 # --------------------------------------------------------------------------------------

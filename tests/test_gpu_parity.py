@@ -683,8 +683,8 @@ def test_ppo_grad_against_autograd(dev, T, N, hidden, path):
     e.close()
 
 
-def test_ppo_update_adam_step_decreases_loss(dev):
-    """optax.adam step (kbs_adam_step) on the flat parameter vector: matches the closed form on the first step and a few
+def test_ppo_update_adamw_step_decreases_loss(dev):
+    """optax.adamw step (kbs_adamw_step) on the flat parameter vector: matches the closed form on the first step and a few
     updates on a fixed minibatch decrease the PPO loss."""
     from kbot_joystick_b200.ppo import PpoUpdater
 
@@ -701,8 +701,9 @@ def test_ppo_update_adam_step_decreases_loss(dev):
     p0 = up.param.clone()
     first = up.update(batch, N)
     g = up.grad.clone()
-    # first Adam step: m/(1-b1) = g, v/(1-b2) = g^2  ->  delta = -lr g / (|g| + eps)
-    expect = p0 - 1e-3 * g / (g.abs() + 1e-8)
+    # first AdamW step: m/(1-b1) = g, v/(1-b2) = g^2  ->  delta = -lr (g / (|g| + eps) + wd p)   (|g|_2 << the clip norm)
+    assert float(up.norm) < 10.0 and up.step_count == 1
+    expect = p0 - 1e-3 * (g / (g.abs() + 1e-8) + 1e-5 * p0)
     assert torch.allclose(up.param, expect, rtol=1e-5, atol=1e-7)
     losses = [float(first["stats"][0])]
     for _ in range(6):
@@ -711,9 +712,183 @@ def test_ppo_update_adam_step_decreases_loss(dev):
     e.close()
 
 
+@pytest.mark.parametrize("count", [1, 1000, 2250537])
+def test_adamw_and_grad_norm_against_float64(eng, dev, count):
+    """kbs_grad_norm + kbs_adamw_step against the float64 restatement of optax.adamw + ksim's clip (oracle.adamw_update) and
+    against torch.optim.AdamW (decoupled decay = optax.adamw semantics) over several steps: unclipped, clipped, device-side
+    step counter, and the non-finite skip (parameters, moments and the counter untouched)."""
+    rng = np.random.default_rng(count)
+    p0 = rng.normal(0, 0.3, count).astype(np.float32)
+    opt = dict(lr=5e-4, b1=0.9, b2=0.999, eps=1e-8, weight_decay=1e-5)
+    for max_norm, gscale in ((0.0, 1.0), (0.5, 0.125)):
+        param = torch.from_numpy(p0.copy()).to(dev)
+        m, v = torch.zeros_like(param), torch.zeros_like(param)
+        step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+        norm = torch.zeros(1, device=dev)
+        rp, rm, rv = p0.astype(np.float64), np.zeros(count), np.zeros(count)
+        tp = torch.from_numpy(p0.astype(np.float64)).requires_grad_(True)
+        topt = torch.optim.AdamW([tp], lr=opt["lr"], betas=(opt["b1"], opt["b2"]), eps=opt["eps"], weight_decay=opt["weight_decay"])
+        for step in range(1, 6):
+            g = (rng.normal(0, 1.0, count) * (0.02 if step != 3 else 3.0)).astype(np.float32)
+            gd = torch.from_numpy(g).to(dev)
+            eng.grad_norm(gd, out=norm)
+            ref_norm = np.sqrt(np.sum(g.astype(np.float64) ** 2))
+            assert abs(float(norm) - ref_norm) <= 2e-7 * ref_norm + 1e-30          # double accumulation, one fp32 rounding
+            n2 = eng.grad_norm(gd)
+            assert torch.equal(n2, norm)                                           # fixed reduction order: bitwise reproducible
+            eng.adamw_step(param, gd, m, v, grad_norm=norm, step_dev=step_dev, grad_scale=gscale, max_grad_norm=max_norm, **opt)
+            rp, rm, rv, applied = O.adamw_update(rp, g, rm, rv, step, grad_scale=gscale, max_grad_norm=max_norm, **opt)
+            assert applied and int(step_dev) == step
+            ge = g.astype(np.float64) * gscale
+            ne = ref_norm * gscale
+            if max_norm > 0 and ne > max_norm:
+                ge = ge * (max_norm / ne)
+            tp.grad = torch.from_numpy(ge)
+            topt.step()
+            close(param.cpu().numpy(), rp, f"adamw param step {step}", rtol=1e-6, atol=2e-7)
+            close(m.cpu().numpy(), rm, f"adamw m step {step}", rtol=1e-5, atol=1e-9)
+            close(v.cpu().numpy(), rv, f"adamw v step {step}", rtol=1e-5, atol=1e-12)
+            np.testing.assert_allclose(rp, tp.detach().numpy(), rtol=0, atol=1e-12)   # the restatement == torch AdamW
+        # non-finite gradient: ksim skips the update; nothing moves, the counter does not advance
+        before = (param.clone(), m.clone(), v.clone())
+        g = rng.normal(0, 0.02, count).astype(np.float32)
+        g[count // 2] = np.inf
+        gd = torch.from_numpy(g).to(dev)
+        eng.grad_norm(gd, out=norm)
+        assert not np.isfinite(float(norm))
+        eng.adamw_step(param, gd, m, v, grad_norm=norm, step_dev=step_dev, grad_scale=gscale, max_grad_norm=max_norm, **opt)
+        assert int(step_dev) == 5
+        assert torch.equal(param, before[0]) and torch.equal(m, before[1]) and torch.equal(v, before[2])
+    # weight_decay = 0, no norm, host-side step: the optax.adam branch (kbs_adam_step) and kbs_adamw_step agree bitwise
+    g = torch.from_numpy(rng.normal(0, 0.02, count).astype(np.float32)).to(dev)
+    pa, pb = torch.from_numpy(p0.copy()).to(dev), torch.from_numpy(p0.copy()).to(dev)
+    ma, va, mb, vb = (torch.zeros_like(pa) for _ in range(4))
+    eng.adam_step(pa, g, ma, va, 3)
+    eng.adamw_step(pb, g, mb, vb, step=3, weight_decay=0.0, max_grad_norm=0.0)
+    close(pb.cpu().numpy(), pa.cpu().numpy(), "adamw(wd=0) vs adam", rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("N", [3, 64, 1001])
+def test_actuator_randomization_sampler(eng, dev, N):
+    """8f-2: per-episode PositionActuators randomisation (train.py:1097-1105; sampling law [U]) -> the kp / kd / tau_limit /
+    action_bias / torque_bias arrays kbs_torque consumes; partial resample with a reset mask."""
+    ld = (N + 3) // 4 * 4
+    rng = np.random.default_rng(N)
+    u = rng.random((5, N, 20)).astype(np.float32)
+    ref = O.actuator_randomization(u)
+    ud = synth.to_soa(u, 1, dev)
+    ep = {k: torch.full((20, ld), float("nan"), device=dev) for k in ("kp", "kd", "tau_limit", "action_bias", "torque_bias")}
+    eng.sample_actuator_randomization(ud, ep, n_envs=N)
+    for k in ep:
+        close(S(ep[k], N, (20,)), ref[k], k, atol=1e-7)
+    assert (S(ep["tau_limit"], N, (20,)) <= np.asarray(O.CTRL_LIMIT64, np.float32) + 1e-4).all()
+    assert (np.abs(S(ep["action_bias"], N, (20,))) <= 0.02 + 1e-7).all() and (S(ep["torque_bias"], N, (20,)) == 0).all()
+    # second draw, only where reset: the other environments keep their episode's values
+    u2 = rng.random((5, N, 20)).astype(np.float32)
+    reset = rng.random(N) < 0.4
+    ref2 = O.actuator_randomization(u2)
+    eng.sample_actuator_randomization(synth.to_soa(u2, 1, dev), ep, reset=synth.to_soa(reset.astype(np.uint8), 0, dev), n_envs=N)
+    for k in ep:
+        close(S(ep[k], N, (20,)), np.where(reset[:, None], ref2[k], ref[k]), k + " (masked)", atol=1e-7)
+    # and the torque map accepts them
+    act = synth.to_soa(rng.normal(0, 0.5, (N, 20)).astype(np.float32), 0, dev)
+    b = Batch(5, 1, N, dev)
+    ctrl = eng.torque(act, b.state_at(0), ep, n_envs=N)
+    st = b.np_state_at(0)
+    want = {k: np.where(reset[:, None], ref2[k], ref[k]) for k in ref}
+    close(S(ctrl, N, (20,)), O.position_actuator_torque(S(act, N, (20,)), st["qpos"][:, 7:], st["qvel"][:, 6:], want["kp"],
+                                                       want["kd"], want["tau_limit"], want["action_bias"], want["torque_bias"]),
+          "ctrl with sampled gains", atol=1e-4)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_checkpoint_bytes_to_policy_step(dev, path, tmp_path):
+    """8f-4 (convert.py:36-39, 84-119): an eqx leaf stream on disk -> checkpoint.load_policy -> kbs_weights_pack ->
+    kbs_policy_step, against oracle.policy_step on the weights that were serialised (init_fn() = zero carry)."""
+    from kbot_joystick_b200 import checkpoint
+    from kbot_joystick_b200.engine import KbotStep
+
+    H, N = 256, 300
+    wa, wc = synth.make_weights(501, 65, 40, H, 2), synth.make_weights(502, 475, 1, H, 2)
+    static = (np.asarray(65), np.asarray(40), np.asarray(0.01, np.float32))       # 0-d static fields ride along, as eqx writes them
+    path_ckpt = tmp_path / "model.eqx"
+    checkpoint.write_leaves(checkpoint.weights_to_leaves(wa, wc, static, static[:2]), path_ckpt)
+    la, lc = checkpoint.load_policy(path_ckpt, hidden=H, depth=2)
+    e = KbotStep(hidden_size=H, depth=2, gemm_path=path)
+    e.pack_weights(L.NET_ACTOR, synth.weights_to_device(la, dev))
+    e.pack_weights(L.NET_CRITIC, synth.weights_to_device(lc, dev))
+    p = O.OracleParams()
+    b = Batch(17, 3, N, dev)
+    flat = np.zeros((N, 2 * 2 * H + 20), np.float32)              # init_fn(): convert.py:67-72
+    flat_d = torch.from_numpy(flat).to(dev)
+    for t in range(3):
+        o, _ = O.get_observations(b.np_state_at(t), b.np_noise_at(t), b.np["episode"], None, P)
+        args = (o["noisy_biased_joint_position"], o["noisy_joint_velocity"], o["noisy_imu_projected_gravity"],
+                o["noisy_imu_gyro"], b.cmd0_np)
+        act, flat = O.policy_step(wa, *args, flat, p)
+        act_d, flat_d = e.policy_step(*(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in args), flat_d)
+        close(act_d.cpu().numpy(), act, f"policy action from checkpoint t={t}")
+        close(flat_d.cpu().numpy(), flat, f"policy carry from checkpoint t={t}")
+    e.close()
+
+
+def test_f16_split_range_guard_sets_status(dev):
+    """An input beyond the FP16 planes' range (|x| >= 65504 or non-finite) on the 2xFP16-split datapath must not pass
+    silently as inf: the health word gets KBS_STATUS_F16_RANGE, the next fused call fails with KBS_E_DEVICE until reset."""
+    T, N = 2, 200
+    b = Batch(31, T, N, dev)
+    e, wa, wc = Hn.make_engine(gemm_path=L.GEMM_TC_2XF16, device=dev)
+    io = Hn.rollout_buffers(b, 256, 2, True)
+    e.rollout(io, N)
+    assert e.device_status() == 0
+    bad = {k: v.clone() for k, v in b.state.items()}
+    bad["cinert"][1, 57, 5] = 1.0e5                              # a raw critic input (train.py:1405): beyond the half range
+    io2 = dict(io)
+    io2["state"] = bad
+    e.rollout(io2, N)
+    st = e.device_status()
+    assert st & L.STATUS_F16_RANGE and not (st & 3), st
+    with pytest.raises(RuntimeError, match="health word"):
+        e.rollout(io, N)
+    e.device_status_reset()
+    e.rollout(io, N)
+    assert e.device_status() == 0
+    e.close()
+    # the 3xTF32 datapath carries the same value without complaint
+    e3, _, _ = Hn.make_engine(gemm_path=L.GEMM_TC_3XTF32, device=dev)
+    io3 = Hn.rollout_buffers(b, 256, 2, True)
+    io3["state"] = bad
+    e3.rollout(io3, N)
+    assert e3.device_status() == 0 and torch.isfinite(io3["value"]).all()
+    e3.close()
+
+
+def test_rollout_phase_a_chunks_on_aux_stream(dev, monkeypatch):
+    """KBS_ROLLOUT_CHUNKS > 1 produces phase A on the handle's aux stream: the persistent kernel must wait for every chunk
+    (it reads the operands of all T steps).  Same results as the single-stream default, bit for bit."""
+    T, N = 12, 2048
+    outs = []
+    monkeypatch.setenv("KBS_NO_FUSED_INPUT", "1")      # chunked phase A keeps the actor's projection launch: same form for both
+    for chunks in ("1", "3"):
+        monkeypatch.setenv("KBS_ROLLOUT_CHUNKS", chunks)
+        b = Batch(41, T, N, dev)
+        e, wa, wc = Hn.make_engine(gemm_path=L.GEMM_TC_2XF16, device=dev)
+        io = Hn.rollout_buffers(b, 256, 2, True)
+        for _ in range(3):                                       # repeated: a race would not lose every time
+            io["command"][1:].zero_()
+            io["actor_carry"].zero_(); io["critic_carry"].zero_(); io["lpf"].zero_(); io["pg_carry"].zero_()
+            e.rollout(io, N)
+        torch.cuda.synchronize()
+        assert e.device_status() == 0
+        outs.append({k: io[k].clone() for k in ("action", "log_prob", "value", "ctrl", "actor_obs", "actor_carry")})
+        e.close()
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
 def test_error_codes(eng, dev):
     lib = L.load()
-    assert lib.kbs_version() == 100
+    assert lib.kbs_version() == 101
     p = L.default_params()
     p.hidden_size = 100
     h = C.c_void_p()
@@ -747,7 +922,8 @@ def test_ppo_variables(dev, path, T, N, hidden):
     """get_ppo_variables (train.py:1435-1524) on a stored trajectory: log_probs / values / entropy / action_std and the
     final carries, incl. the done-resets; the mirror pass is the same call on mirrored observations."""
     e, wa, wc = Hn.make_engine(hidden=hidden, gemm_path=path, device=dev)
-    p = O.OracleParams(hidden_size=hidden)
+    # mirror-loss scales: the config defaults (train.py:115-122); the launch config multiplies both by 0.0 (train.py:1771-1772)
+    p = O.OracleParams(hidden_size=hidden, actor_mirror_loss_scale=1.0, critic_mirror_loss_scale=0.01)
     b = Batch(1000 + N, T, N, dev)
     rng = np.random.default_rng(4)
     obs_list = [O.get_observations(b.np_state_at(t), b.np_noise_at(t), b.np["episode"], None, P)[0] for t in range(T)]
@@ -783,6 +959,28 @@ def test_ppo_variables(dev, path, T, N, hidden):
     mout, _, _, _ = run(m_list, m_cmd, True)
     close(S(mout["mean"], N, (20,)), ref["mirror_mean"], "mirrored dist.mean()")
     close(S(mout["values"], N), ref["mirror_value"], "mirrored value", atol=1e-5)
+    # aux_losses as library outputs (train.py:1462-1481, 1488-1491): one call, the mirrored passes with their own carries
+    a_obs = synth.to_soa(np.stack([O.actor_obs_from_dict(o, c) for o, c in zip(obs_list, cmd)]), 1, dev)
+    c_obs = synth.to_soa(np.stack([O.critic_obs_from_dict(o, c) for o, c in zip(obs_list, cmd)]), 1, dev)
+    am_obs = synth.to_soa(np.stack([O.actor_obs_from_dict(o, c) for o, c in zip(m_list, m_cmd)]), 1, dev)
+    cm_obs = synth.to_soa(np.stack([O.critic_obs_from_dict(o, c) for o, c in zip(m_list, m_cmd)]), 1, dev)
+    z = lambda: torch.zeros((2, 2, N, hidden), device=dev)
+    mir = {"actor_obs": am_obs, "critic_obs": cm_obs, "actor_carry": z(), "critic_carry": z(),
+           "lpf": torch.zeros((20, b.ld), device=dev), "actor_scale": p.actor_mirror_loss_scale,
+           "critic_scale": p.critic_mirror_loss_scale}
+    ac, cc, lpf = z(), z(), torch.zeros((20, b.ld), device=dev)
+    full = e.ppo_variables(a_obs, synth.to_soa(act.astype(np.float32), 1, dev), synth.to_soa(done.astype(np.uint8), 1, dev),
+                           ac, lpf, c_obs, cc, n_envs=N, mirror=mir)
+    assert e.device_status() == 0
+    close(S(full["log_probs"], N), ref["log_probs"][..., 0], "log_probs (aux call)", atol=1e-4)
+    close(S(full["values"], N), ref["values"], "values (aux call)", atol=1e-5)
+    close(S(full["action_mirror_loss"], N), ref["action_mirror_loss"], "action_mirror_loss", rtol=1e-4, atol=1e-6)
+    close(S(full["value_mirror_loss"], N), ref["value_mirror_loss"], "value_mirror_loss", rtol=1e-4, atol=2e-7)
+    assert float(np.abs(ref["action_mirror_loss"]).max()) > 1e-3 and float(np.abs(ref["value_mirror_loss"]).max()) > 1e-6
+    close(Hn.carry_to_np(mir["actor_carry"], N), c_end["actor_mirror"], "actor_mirror carry")
+    close(Hn.carry_to_np(mir["critic_carry"], N), c_end["critic_mirror"], "critic_mirror carry", atol=1e-5)
+    close(S(mir["lpf"], N, (20,)), c_end["lpf_params_mirror"], "lpf_params_mirror")
+    close(Hn.carry_to_np(ac, N), c_end["actor"], "actor carry (aux call)")
     e.close()
 
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"declared in kbotstep.h but not exported: {missing}"
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
-    assert lib.kbs_version() == 100
+    assert lib.kbs_version() == 101
     assert b"aligned" in lib.kbs_error_string(-3)
     nm = subprocess.run(["nm", "-D", "--defined-only", os.fspath(L.LIB_PATH)], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (kbs_\w+)", nm))
@@ -87,9 +87,10 @@ def test_ctypes_structs_match_header(lib_built):
                        ("kbs_reward_carry", L.KbsRewardCarry), ("kbs_rollout_io", L.KbsRolloutIO),
                        ("kbs_ppo_io", L.KbsPpoIO), ("kbs_ppo_loss_params", L.KbsPpoLossParams),
                        ("kbs_ppo_loss_io", L.KbsPpoLossIO), ("kbs_ppo_batch", L.KbsPpoBatch),
-                       ("kbs_net_grads", L.KbsNetGrads)):
+                       ("kbs_net_grads", L.KbsNetGrads), ("kbs_adamw_params", L.KbsAdamwParams),
+                       ("kbs_actuator_rand_params", L.KbsActuatorRandParams)):
         assert c_fields(cname) == [f[0] for f in cls._fields_], cname
-    assert C.sizeof(L.KbsStateView) == 11 * 8 and C.sizeof(L.KbsPpoIO) == 14 * 8
+    assert C.sizeof(L.KbsStateView) == 11 * 8 and C.sizeof(L.KbsPpoIO) == 22 * 8    # 14 + 7 pointers + two floats
 
 
 def test_product_fails_loudly_without_gpu_or_library(lib_built, monkeypatch):

@@ -2,7 +2,7 @@
 (`python -m torch.distributed.run --nproc-per-node N tools/bench_ppo_update.py`, or plain `python` for N = 1): every rank
 owns `--envs` stored trajectories of `--T` steps (train.py:1764-1766: batch_size 512, rollout 100 steps), computes the
 gradients of the PPO loss (kbs_ppo_grad), all-reduces the 2.25 M-float gradient over NVLink / NVSwitch (NCCL) and applies
-Adam (kbs_adam_step).  Prints one JSON line from rank 0 (CUDA events, max over ranks)."""
+AdamW with the global-norm clip (kbs_grad_norm + kbs_adamw_step).  Prints one JSON line from rank 0 (CUDA events, max over ranks)."""
 import argparse, json, os, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -69,7 +69,7 @@ if world > 1:
     assert float(hi - lo) == 0.0, "replicas diverged"
 if rank == 0:
     msf = float(ms.item())
-    print(json.dumps({"config": "configs[3] PPO minibatch update (kbs_ppo_grad + NCCL all-reduce + kbs_adam_step)", "n_gpus": world,
+    print(json.dumps({"config": "configs[3] PPO minibatch update (kbs_ppo_grad + NCCL all-reduce + kbs_grad_norm + kbs_adamw_step)", "n_gpus": world,
                       "trajectories_per_gpu": N, "T": T, "ms_per_update": msf, "env_steps_per_s": world * N * T / (msf * 1e-3),
                       "grad_floats": int(up.grad.numel()), "loss": float(st["stats"][0]), "datapath": "tcgen05 2xFP16-split recurrent GEMMs + fp32 FFMA batched GEMMs", "launch": "cuda-graph replay" if a.graph else "eager"}),
           flush=True)
