@@ -244,7 +244,8 @@ int kbs_adam_step(kbs_handle* h, float* param, const float* grad, float* m, floa
  * and the step counter untouched.  step_dev: device int64 = number of updates applied so far (read, then advanced by one
  * when the update is applied), so that the whole update can be replayed as one CUDA graph; NULL = use `step` (>= 1). */
 typedef struct kbs_adamw_params {
-  float lr, b1, b2, eps, weight_decay, grad_scale, max_grad_norm;
+  double b1, b2;   /* doubles: optax forms (1 - b) in Python double precision and only then rounds to fp32 (1.0f - 0.999f != 0.001f) */
+  float lr, eps, weight_decay, grad_scale, max_grad_norm;
 } kbs_adamw_params;
 int kbs_adamw_default_params(kbs_adamw_params* p);   /* lr 5e-4, b1 0.9, b2 0.999, eps 1e-8, wd 1e-5 [R]; clip 10.0 [U] */
 int kbs_adamw_step(kbs_handle* h, float* param, const float* grad, float* m, float* v, int64_t count,

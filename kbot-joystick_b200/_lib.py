@@ -91,7 +91,8 @@ class KbsPpoIO(C.Structure):
 
 
 class KbsAdamwParams(C.Structure):
-    _fields_ = [(k, _f) for k in ("lr", "b1", "b2", "eps", "weight_decay", "grad_scale", "max_grad_norm")]
+    _fields_ = [("b1", C.c_double), ("b2", C.c_double)] + [(k, _f) for k in ("lr", "eps", "weight_decay", "grad_scale",
+                                                                            "max_grad_norm")]
 
 
 class KbsActuatorRandParams(C.Structure):

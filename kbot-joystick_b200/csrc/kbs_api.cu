@@ -815,7 +815,7 @@ int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n, void* stre
 
 int kbs_adamw_default_params(kbs_adamw_params* p) {
   REQ(p);
-  p->lr = 5e-4f; p->b1 = 0.9f; p->b2 = 0.999f; p->eps = 1e-8f;   /* train.py:95-98, optax.adamw defaults */
+  p->lr = 5e-4f; p->b1 = 0.9; p->b2 = 0.999; p->eps = 1e-8f;   /* train.py:95-98, optax.adamw defaults */
   p->weight_decay = 1e-5f;                                       /* train.py:99-102 */
   p->grad_scale = 1.0f;
   p->max_grad_norm = 10.0f;                                      /* ksim RLConfig global gradient clip [U] */

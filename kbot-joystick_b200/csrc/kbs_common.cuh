@@ -76,6 +76,7 @@ struct kbs_handle {
   unsigned int* status_host = nullptr;        // pinned host copy, refreshed by an async D2H after the fused entry points' kernels
   bool tc_attr_set = false;                   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: once per handle
   bool head_attr_set = false;
+  bool bptt_attr_set = false;
   bool scratch_locked = false;                // kbs_scratch_lock: growing the scratch is an error (a CUDA graph holds pointers)
   long long* trace_buf = nullptr;
   int64_t trace_step = -1;
@@ -196,6 +197,11 @@ struct KbsTcRolloutArgs {
   float* entropy;             // [T][ld] or nullptr
   float* action_std;          // [T][20][ld] or nullptr
   float* mean;                // [T][20][ld] dist.mean() or nullptr (persistent kernel only)
+  // save != 0 (forward pass of the PPO update; FP16-split persistent kernel only): every step keeps its operands and
+  // activations for the backward pass -- xmid_hist [depth][T] x sb, hsb_hist [depth][T + 1] x sb, c_hist [depth][T + 1] x np*H,
+  // save_g [T][depth][4] x np*H, sraw [T][20][ld]; carry[] may be nullptr (zeros); the final carries are not written back.
+  int save;
+  char* xmid_hist[2]; char* hsb_hist[2]; float* c_hist[2]; float* save_g[2]; float* sraw;
   float* ws;                  // kbs_tc_rollout_ws_floats
   int64_t chunk_len;          // > 0: before step t with t % chunk_len == 0, wait for chunk_events[t / chunk_len]
   cudaEvent_t* chunk_events;  //      (the input projections of that chunk of steps, produced on another stream)
@@ -219,6 +225,31 @@ int kbs_tc_gates_fwd(kbs_handle* h, int net, int layer, const void* x_sb, const 
 int kbs_tc_pack_bwd(kbs_handle* h, int net, cudaStream_t st);
 int kbs_tc_bwd_gemm(kbs_handle* h, int net, int layer, const void* dG_sb, float* out, int64_t n, float out_scale, cudaStream_t st);
 size_t kbs_tc_rows_sb_bytes(const kbs_handle* h, int64_t n, int K);
+// weight-gradient GEMMs C = A^T B over K = all stored rows (split-K tcgen05; operands = transposed split-blocked buffers)
+struct KbsTnPlan { int kb_split, ksplit, kb_total; size_t col_bytes; };
+KbsTnPlan kbs_tc_tn_plan(const kbs_handle* h, int64_t rows);
+int kbs_tc_pack_tn(kbs_handle* h, const KbsTnPlan& plan, bool b_operand, const float* src, int64_t ld, int col0, int ncols,
+                   int ncols_pad, int64_t rows, char* dst, float scale, int ones_col, cudaStream_t st, int64_t n_step = 0,
+                   int64_t np_step = 0);
+int kbs_tc_gemm_tn(kbs_handle* h, const KbsTnPlan& plan, const char* a_t, int m_panels, int m_valid, const char* b_t, int n_tiles,
+                   const char* ones_blk, const float* zero_bias, float* partial, float out_scale, cudaStream_t st);
+int kbs_tc_ones_block(kbs_handle* h, char* blk, cudaStream_t st);
+// the same operands from the per-step split-blocked buffers the persistent kernels keep (K' = t np + row), FP16 kind:
+// source K blocks [blk0, blk0 + nblk) of every step -> nblk / 4 panels (A) or tiles (B) at dst
+int kbs_tc_sb_to_tn(kbs_handle* h, const KbsTnPlan& plan, bool b_operand, const char* src, size_t step_bytes, int kb_src, int blk0,
+                    int nblk, int64_t n, int64_t T, char* dst, cudaStream_t st);
+int kbs_tc_soa_to_tn(kbs_handle* h, const KbsTnPlan& plan, const float* soa, int F, int64_t ld, int64_t n, int64_t T, int ncols_pad,
+                     bool ones, char* dst, cudaStream_t st);
+// backward recurrence of the PPO update as one persistent kernel (bptt_persist_kernel)
+struct KbsBpttNet {
+  char* dG; const float* save_g; const float* c_hist; const float* dh_top; float* dx; char* dx0; float* dc; unsigned int* flags;
+};
+struct KbsBpttArgs { KbsBpttNet net[2]; int nets; int64_t n, ld, T; const uint8_t* done; float gscale; };
+size_t kbs_tc_bptt_flag_bytes(const kbs_handle* h, int64_t n);
+bool kbs_tc_bptt_available(const kbs_handle* h, int64_t n, int64_t T);
+int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& a, cudaStream_t st);
+int kbs_tc_tn_reduce(kbs_handle* h, const KbsTnPlan& plan, const float* partial, int m_panels, int ldc, int col0, int nrows,
+                     int ncols, float* dst, int ld_dst, cudaStream_t st);
 int kbs_tc_kind_of(const kbs_handle* h);
 int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,
                        float* ws, int64_t n, cudaStream_t st);

@@ -175,6 +175,11 @@ __device__ __forceinline__ float sig_mul_tanh(float a, float b) {
   return copysignf((1.0f - eb) * fast_rcp((1.0f + ea) * (1.0f + eb)), b);
 }
 
+__device__ __forceinline__ float tanhf_(float x) {
+  const float e = fast_ex2(-2.885390081777927f * fabsf(x));            // e^-2|x| <= 1
+  return copysignf((1.0f - e) * fast_rcp(1.0f + e), x);
+}
+
 // fp32 "FB" blocked layout of a [rows][H] state matrix: [panel][H/4][128 rows][4 floats] -- a thread that owns one row
 // reads/writes 16 B at consecutive addresses across the warp (the row-major ABI layout costs one sector per lane).
 __device__ __forceinline__ size_t fb_offset(int64_t row, int k, int H) {
@@ -211,16 +216,31 @@ struct LayerArgs {
   int ldo;                // MODE_PLAIN: row stride of `raw` (floats)
   float oscale;           // MODE_PLAIN: output multiplier (power of two: undoes the operand pre-scaling of small gradients)
   unsigned int* status;   // health word: KBS_STATUS_F16_RANGE when a projection output leaves the FP16-split range (or nullptr)
+  // split-K (MODE_PLAIN, the weight-gradient GEMMs of the PPO update: K = all T x n stored rows): the K blocks of a panel /
+  // tile are cut into `ksplit` runs of kb_x blocks, one work item each, every run into its own output slab
+  // (raw + ks * raw_split_stride) -- a fixed-order reduction kernel adds the slabs (no atomics: bitwise reproducible, and a
+  // run stays short enough for the tensor core's truncating accumulation).  kb_stride = K blocks between consecutive
+  // panels / tiles of the operands (0 = kb_x + kb_h, the unsplit layout).
+  int ksplit, kb_stride;
+  size_t raw_split_stride;
+  // ones tile: B tile index `ones_tile` (>= 0) is not read from w_sb but is the single block `ones_block` for every K
+  // block: column 0 = 1.0, the rest 0 -- its output column 0 is the column sum of A (the bias gradients).
+  int ones_tile;
+  const char* ones_block;
 };
 struct LayerArgs2 { LayerArgs net[2]; };   // actor / critic share one launch
 
-struct WorkItem { int net, panel, tile; };
+struct WorkItem { int net, panel, tile, ks; };
+__host__ __device__ __forceinline__ int net_items(const LayerArgs& a) { return a.panels * a.tiles * (a.ksplit > 1 ? a.ksplit : 1); }
 __device__ __forceinline__ WorkItem decode_item(const LayerArgs2& args, int item) {
-  const int n0 = args.net[0].panels * args.net[0].tiles;
+  const int n0 = net_items(args.net[0]);
   WorkItem w;
   w.net = item >= n0 ? 1 : 0;
-  const int r = item - (w.net ? n0 : 0);
+  int r = item - (w.net ? n0 : 0);
   const int tiles = args.net[w.net].tiles;
+  const int per_split = args.net[w.net].panels * tiles;
+  w.ks = r / per_split;         // split-K: the items of one K run are adjacent (its A / B blocks are shared through L2)
+  r -= w.ks * per_split;
   w.panel = r / tiles;          // consecutive items share the activation panel (L2 reuse of A across its tiles)
   w.tile = r - w.panel * tiles;
   return w;
@@ -240,7 +260,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_init + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = args.net[0].panels * args.net[0].tiles + args.net[1].panels * args.net[1].tiles;
+  const int n_items = net_items(args.net[0]) + net_items(args.net[1]);
   long long* tr = args.net[0].trace ? args.net[0].trace + size_t(blockIdx.x) * 8 : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = clock64();
   // CTA 0 only: per-stage stamps of the first 64 stages: [0] producer saw empty, [1] producer issued, [2] MMA saw full,
@@ -346,9 +366,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
         const WorkItem w = decode_item(args, item);
         const LayerArgs& a = args.net[w.net];
         const int kb_x = a.kb_x, kb_total = a.kb_x + a.kb_h;
-        const char* xa = a.x_sb + size_t(w.panel) * kb_x * kABlockBytes;
+        const int kbs = a.kb_stride ? a.kb_stride : kb_total;          // split-K: blocks between panels / tiles
+        const char* xa = a.x_sb + (size_t(w.panel) * (a.kb_stride ? a.kb_stride : kb_x) + size_t(w.ks) * kb_x) * kABlockBytes;
         const char* ha = a.h_sb_in + size_t(w.panel) * a.kb_h * kABlockBytes;
-        const char* wb = a.w_sb + size_t(w.tile) * kb_total * kBBlockBytes;
+        const bool ones = a.ones_block != nullptr && w.tile == a.ones_tile;
+        const char* wb = ones ? a.ones_block : a.w_sb + (size_t(w.tile) * kbs + size_t(w.ks) * kb_total) * kBBlockBytes;
         for (int b = 0; b < kb_total; ++b, ++g) {
           if (int(g % kProducers) != warp - kIssuers) continue;
           const int s = g % kStages;
@@ -362,7 +384,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
           __syncwarp(0x3);
           uint8_t* sa = smem + size_t(s) * kStageBytes;
           const char* src = lane == 0 ? ((b < kb_x) ? xa + size_t(b) * kABlockBytes : ha + size_t(b - kb_x) * kABlockBytes)
-                                      : wb + size_t(b) * kBBlockBytes;
+                                      : wb + (ones ? size_t(0) : size_t(b) * kBBlockBytes);
           bulk_g2s(sa + lane * kABlockBytes, src, cp_bytes, &full[s]);    // kABlockBytes == kBBlockBytes
           if (tr2 && g < 64 && lane == 0) tr2[64 + g] = clock64();
         }
@@ -487,7 +509,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) lstm_layer_tc_kernel(const __gr
           }
         }
       } else if (a.mode == MODE_PLAIN) {
-        float* o = a.raw + R * a.ldo + w.tile * kTileCols + c2 * 64;
+        float* o = a.raw + size_t(w.ks) * a.raw_split_stride + R * a.ldo + w.tile * kTileCols + c2 * 64;
 #pragma unroll
         for (int i = 0; i < 64; i += 4)
           *reinterpret_cast<float4*>(o + i) = make_float4(a.oscale * v[i], a.oscale * v[i + 1], a.oscale * v[i + 2], a.oscale * v[i + 3]);
@@ -745,6 +767,12 @@ struct PNet {
   const char* w_head;              // [128][H] SB, rows >= num_out zero
   const float* bias_head;          // [128]
   unsigned int* flags;             // [depth + 1][panels] completion counters (zeroed before the launch)
+  // SAVE instantiation (forward pass of the PPO update, kbs_ppo_grad): nothing is ping-ponged, every step keeps its
+  // operands and activations for the backward pass --
+  //   xmid [depth][T] x sbb, hsb [depth][T + 1] x sbb (slot t = what step t reads), c_hist [depth][T + 1] x np*H (FB; slot t =
+  //   the cell state step t reads, i.e. reset where done_{t-1}), save_g [T][depth][4 gates i,f,g,o] x np*H (FB, activated).
+  float* c_hist;
+  float* save_g;
 };
 struct PArgs {
   PNet net[2];
@@ -761,6 +789,8 @@ struct PArgs {
   float* action; float* log_prob; float* ctrl; float* value;
   const float* action_in; float* entropy; float* std;
   float* mean;                     // [T][20][ld] dist.mean() = the low-pass-filtered mean (mirror loss), or nullptr
+  float* sraw;                     // [T][20][ld] pre-softplus std output of the actor head (backward pass of the update), or nullptr
+  int hist;                        // 1 = SAVE instantiation: per-step buffers, no write-after-read dependencies
   int dbg;                         // profiling only (KBS_PERSIST_DBG): 1 = ignore dependencies (wrong results, timing probe)
   unsigned int* status;            // != 0: a dependency wait timed out (bug / lost CTA)
   long long* trace;                // per CTA [8]: total cycles, poller wait cycles, items, issuer wait-for-stage cycles,
@@ -802,7 +832,7 @@ __device__ __forceinline__ long long p_wait_deps(const PArgs& a, const PItem& it
     const int l = it.layer;
     if (t >= 1) { fp[nd] = N.flags + l * a.panels + it.panel; tg[nd++] = t * full_l; }              // h_{t-1}, c_{t-1}
     if (l >= 1) { fp[nd] = N.flags + (l - 1) * a.panels + it.panel; tg[nd++] = (t + 1) * full_l; }  // x_t from layer l-1
-    if (t >= 2) {   // xmid[l][t & 1] was last read by the consumer of this layer's output at step t - 2
+    if (t >= 2 && !a.hist) {   // xmid[l][t & 1] was last read by the consumer of this layer's output at step t - 2
       fp[nd] = N.flags + (l + 1) * a.panels + it.panel;
       tg[nd++] = (t - 1) * (l + 1 == a.depth ? full_h : full_l);
     }
@@ -830,7 +860,7 @@ __device__ __forceinline__ long long p_wait_deps(const PArgs& a, const PItem& it
   return clock64() - c0;
 }
 
-template <int KIND>
+template <int KIND, bool SAVE>
 __global__ void __launch_bounds__(kThreadsP, 1)
 rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_constant__ PArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -931,12 +961,13 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
         if (args.dbg & 8) poff = size_t(blockIdx.x % args.panels) * kb * kABlockBytes;   // probe: no two CTAs share a panel at a time
         const char* xa; const char* ha; const char* wb;
         if (it.kind == 0) {
-          xa = it.layer == 0 ? N.x_sb_all + size_t(it.t) * N.x0_stride + poff / kb * kb_x
-                             : N.xmid + size_t((it.layer - 1) * 2 + (it.t & 1)) * args.sbb + poff;
-          ha = N.hsb + size_t(it.layer * 2 + (it.t & 1)) * args.sbb + poff;
+          const size_t xs = SAVE ? size_t(it.layer - 1) * size_t(args.T) + size_t(it.t) : size_t((it.layer - 1) * 2 + (it.t & 1));
+          const size_t hs = SAVE ? size_t(it.layer) * size_t(args.T + 1) + size_t(it.t) : size_t(it.layer * 2 + (it.t & 1));
+          xa = it.layer == 0 ? N.x_sb_all + size_t(it.t) * N.x0_stride + poff / kb * kb_x : N.xmid + xs * args.sbb + poff;
+          ha = N.hsb + hs * args.sbb + poff;
           wb = N.w_sb[it.layer] + size_t((args.dbg & 16) ? (blockIdx.x + it.t) % args.tiles : it.tile) * kb_total * kBBlockBytesP;
         } else {
-          xa = N.xmid + size_t((args.depth - 1) * 2 + (it.t & 1)) * args.sbb + poff;
+          xa = N.xmid + (SAVE ? size_t(args.depth - 1) * size_t(args.T) + size_t(it.t) : size_t((args.depth - 1) * 2 + (it.t & 1))) * args.sbb + poff;
           ha = xa;
           wb = N.w_head;
         }
@@ -1065,7 +1096,10 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
       // dependencies of this item are satisfied once the poller says so (acquire through shared memory)
       while (*dep_seq < j + 1) { }
       __threadfence_block();
-      float* cst = N.fb + size_t(it.layer) * 2 * size_t(args.panels) * kPanelRows * H;      // c of this layer (kind 0 only)
+      const size_t npH = size_t(args.panels) * kPanelRows * H;
+      float* cst = SAVE ? N.c_hist + (size_t(it.layer) * size_t(args.T + 1) + size_t(it.kind == 0 ? it.t : 0)) * npH
+                        : N.fb + size_t(it.layer) * 2 * npH;                                 // c this step reads (kind 0 only)
+      float* cdst = SAVE ? cst + npH : cst;                                                 // ... and the one it writes
       float4 cpre[4];
       if (it.kind == 0 && live) {
 #pragma unroll
@@ -1098,14 +1132,38 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] += bs[i];
         if (live && !(args.dbg & 2)) {
-          char* x_out = N.xmid + size_t(it.layer * 2 + (it.t & 1)) * args.sbb;
-          char* h_out = N.hsb + size_t(it.layer * 2 + ((it.t + 1) & 1)) * args.sbb;
-          float* h_carry = (it.t == int(args.T) - 1) ? cst + size_t(args.panels) * kPanelRows * H : nullptr;
+          char* x_out = N.xmid + (SAVE ? size_t(it.layer) * size_t(args.T) + size_t(it.t) : size_t(it.layer * 2 + (it.t & 1))) * args.sbb;
+          char* h_out = N.hsb + (SAVE ? size_t(it.layer) * size_t(args.T + 1) + size_t(it.t + 1)
+                                      : size_t(it.layer * 2 + ((it.t + 1) & 1))) * args.sbb;
+          float* h_carry = (!SAVE && it.t == int(args.T) - 1) ? cst + npH : nullptr;
+          float* sg = SAVE ? N.save_g + (size_t(it.t) * args.depth + it.layer) * 4 * npH : nullptr;
           // 8 hidden units = exactly one 16-byte SB chunk per plane (FP16 kind): every store below is a full 16 B per
           // lane, 512 contiguous bytes per warp (8-byte half-chunk stores cost the operand pipeline 2.5 K cycles per item)
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             float hn[8], cn[8];
+            if (SAVE) {
+              // the backward pass wants the four activated gates: evaluate them separately and keep them (FB layout)
+              float ai[8], af[8], ag[8], ao[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int u = hf * 8 + i;
+                const float cprev = (&cpre[u >> 2].x)[u & 3];
+                ai[i] = sigmoidf_(v[u]); af[i] = sigmoidf_(v[16 + u]); ag[i] = tanhf_(v[32 + u]); ao[i] = sigmoidf_(v[48 + u]);
+                cn[i] = af[i] * cprev + ai[i] * ag[i];
+                hn[i] = ao[i] * tanhf_(cn[i]);
+                if (rst) cn[i] = 0.0f;
+              }
+              const size_t o0 = fb_offset(R, u0 + hf * 8, H), o1 = fb_offset(R, u0 + hf * 8 + 4, H);
+              *reinterpret_cast<float4*>(sg + o0) = make_float4(ai[0], ai[1], ai[2], ai[3]);
+              *reinterpret_cast<float4*>(sg + o1) = make_float4(ai[4], ai[5], ai[6], ai[7]);
+              *reinterpret_cast<float4*>(sg + npH + o0) = make_float4(af[0], af[1], af[2], af[3]);
+              *reinterpret_cast<float4*>(sg + npH + o1) = make_float4(af[4], af[5], af[6], af[7]);
+              *reinterpret_cast<float4*>(sg + 2 * npH + o0) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+              *reinterpret_cast<float4*>(sg + 2 * npH + o1) = make_float4(ag[4], ag[5], ag[6], ag[7]);
+              *reinterpret_cast<float4*>(sg + 3 * npH + o0) = make_float4(ao[0], ao[1], ao[2], ao[3]);
+              *reinterpret_cast<float4*>(sg + 3 * npH + o1) = make_float4(ao[4], ao[5], ao[6], ao[7]);
+            } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int u = hf * 8 + i;
@@ -1116,14 +1174,15 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
               hn[i] = sig_mul_tanh(go, cn[i]);
               if (rst) cn[i] = 0.0f;
             }
+            }
             if (!((args.dbg & 4) && hn[0] != 12345.0f)) {
               const int uu = u0 + hf * 8;
               const float h0[4] = {hn[0], hn[1], hn[2], hn[3]}, h1[4] = {hn[4], hn[5], hn[6], hn[7]};
               const KbsSplit4 s0 = sb_split4<KIND>(h0), s1 = sb_split4<KIND>(h1);   // one split serves both consumers
               sb_store_split8<kPanelRows, KIND>(x_out, R, uu, kb, s0, s1, false);   // next layer / head input (un-reset)
               sb_store_split8<kPanelRows, KIND>(h_out, R, uu, kb, s0, s1, rst);     // recurrent input (reset where done)
-              *reinterpret_cast<float4*>(cst + fb_offset(R, uu, H)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-              *reinterpret_cast<float4*>(cst + fb_offset(R, uu + 4, H)) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+              *reinterpret_cast<float4*>(cdst + fb_offset(R, uu, H)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+              *reinterpret_cast<float4*>(cdst + fb_offset(R, uu + 4, H)) = make_float4(cn[4], cn[5], cn[6], cn[7]);
               if (h_carry) {
                 const float z = rst ? 0.0f : 1.0f;
                 *reinterpret_cast<float4*>(h_carry + fb_offset(R, uu, H)) = make_float4(z * hn[0], z * hn[1], z * hn[2], z * hn[3]);
@@ -1196,6 +1255,7 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
               if (args.action) args.action[t * KBS_NUM_JOINTS * ld + o] = act;
               if (args.std) args.std[t * KBS_NUM_JOINTS * ld + o] = sd;
               if (args.mean) args.mean[t * KBS_NUM_JOINTS * ld + o] = yn;
+              if (SAVE && args.sraw) args.sraw[t * KBS_NUM_JOINTS * ld + o] = sraw;
               if (args.ctrl) {                         // PositionActuators.get_ctrl (train.py:1091-1105)
                 const float target = args.ep.action_bias ? __fadd_rn(act, in_ab[jj]) : act;
                 float tau = __fsub_rn(__fmul_rn(in_kp[jj], __fsub_rn(target, in_q[jj])), __fmul_rn(in_kd[jj], in_qd[jj]));
@@ -1242,6 +1302,347 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
+}
+
+// ---- persistent BPTT kernel: the backward recurrence of the PPO update in ONE launch -----------------------------------------
+// Replaces, for one minibatch: the T x depth x {cell_bwd8_kernel launch + lstm_layer_tc_kernel(MODE_PLAIN) launch} sequence of
+// kbs_ppo_grad (jax.grad through xax.scan(_ppo_scan_fn), train.py:1435-1524).  Same scaffolding as rollout_persist_kernel (one
+// CTA per SM, wavefront of work items, monotone completion counters in global memory, poller / publisher warps).  Items, per
+// (net, layer l, step s, 128-env panel, 128-column tile):
+//   H tile: acc = dG(l, s+1) . W_hh  (the gradient reaching h_s through the recurrence; K = 4H)   -- tensor core
+//           epilogue = the LSTM cell's backward at step s for the tile's 128 hidden units: dh = dh_in + keep_s acc,
+//           dc = keep_s dc_rec + dh o (1 - tanh^2 c_s), gate gradients -> dG(l, s) written as the (pre-scaled) split operand
+//           of the next GEMMs, dc_rec <- dc f.  dh_in = dx(l+1, s) from the layer above, or the head's gradient (top layer).
+//   X tile: dx(l, s) = dG(l, s) . W_ih  (gradient wrt the layer's input): fp32 for the layer below, or, for layer 0, the
+//           split operand the input-projection weight gradient is built from.
+// Slot order: H(l, s) in slot (T-1-s) + 2 (depth-1-l), X(l, s) one slot later (it needs dG(l, s) = both H tiles), and
+// H(l-1, s) one slot after that (it needs dx(l, s)); dG(l, T) is a zero operand, so step T-1 is a regular item.
+// The weight gradients are NOT accumulated here: dG / x / h are kept for every step and contracted over all T x n rows
+// by the split-K GEMMs (kbs_tc_gemm_tn).
+constexpr int kBStages = 6;
+constexpr int kBSmemBytes = kBStages * kStageBytes + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int kBEpiWarps = 16;
+constexpr int kBThreads = 32 * (1 + 1 + kBEpiWarps + 2);
+struct BNet {
+  const char* w_bwd[kPMaxDepth];   // per layer: 2 H/128 tiles of 128 output columns of [dx | dh], K = 4H (pack_bwd_weights_kernel)
+  char* dG;                        // [depth][T + 1] x sb4: slot s = dG(l, s) (scaled by gscale); slot T = zeros (memset by the host)
+  const float* save_g;             // forward pass: [T][depth][4] x np*H activated gates (FB)
+  const float* c_hist;             // forward pass: [depth][T + 1] x np*H (FB): slot s = the cell state step s read
+  const float* dh_top;             // [T * n][H] row-major: gradient wrt the top layer's output (from the output head)
+  float* dx;                       // [depth][T] x np*H (FB): gradient wrt the input of layer l >= 1 at step s
+  char* dx0;                       // [T] x sbb: the same for layer 0, as split operand (scaled by gscale)
+  float* dc;                       // [depth] x np*H (FB): gradient wrt the cell carry, running (zeroed by the host)
+  unsigned int* flags;             // [depth][2 (H, X)][panels] completion counters (zeroed by the host)
+};
+struct BArgs {
+  BNet net[2];
+  int nets, depth, H, panels;
+  int64_t n, ld, T;
+  size_t sbb, sb4;                 // bytes of one [np][H] / [np][4H] split operand
+  const uint8_t* done;             // [T][ld]
+  float gscale, inv_gscale;
+  unsigned int* status;
+  int dbg;
+};
+struct BItem { int kind, net, layer, panel, tile, s; bool valid; };
+__device__ __forceinline__ BItem b_decode(const BArgs& a, int g) {
+  const int th = a.H / kTileCols;                      // tiles per half of the [dx | dh] output
+  const int per_panel = a.depth * 2 * th, per_net = a.panels * per_panel, C = a.nets * per_net;
+  const int sigma = g / C;
+  int i = g - sigma * C;
+  BItem it;
+  it.net = i / per_net; i -= it.net * per_net;
+  it.panel = i / per_panel;
+  const int q = i - it.panel * per_panel;
+  it.layer = q / (2 * th);
+  const int k = q - it.layer * 2 * th;
+  it.kind = k >= th ? 1 : 0;
+  it.tile = k - it.kind * th;
+  const int base = sigma - 2 * (a.depth - 1 - it.layer);
+  it.s = int(a.T) - 1 - base + it.kind;
+  it.valid = base >= 0 && it.s >= 0 && it.s <= int(a.T) - 1;
+  return it;
+}
+__device__ __forceinline__ void b_wait_deps(const BArgs& a, const BItem& it, bool& drain) {
+  if (drain) return;
+  const BNet& N = a.net[it.net];
+  const unsigned int per = unsigned((a.H / kTileCols) * kBEpiWarps);
+  const unsigned int* fp[2]; unsigned int tg[2]; int nd = 0;
+  const unsigned int T = unsigned(a.T), s = unsigned(it.s);
+  const int l = it.layer;
+  if (it.kind == 0) {
+    if (s + 1 < T) { fp[nd] = N.flags + (l * 2 + 0) * a.panels + it.panel; tg[nd++] = (T - 1 - s) * per; }          // dG(l, s+1), dc
+    if (l + 1 < a.depth) { fp[nd] = N.flags + ((l + 1) * 2 + 1) * a.panels + it.panel; tg[nd++] = (T - s) * per; }  // dx(l+1, s)
+  } else {
+    fp[nd] = N.flags + (l * 2 + 0) * a.panels + it.panel; tg[nd++] = (T - s) * per;                                 // dG(l, s)
+  }
+  if (nd == 0) return;
+  if (nd == 1) { fp[1] = fp[0]; tg[1] = 0u; }
+  unsigned int polls = 0;
+  unsigned long long t0 = 0;
+  while (true) {
+    const unsigned int v0 = ld_volatile_u32(fp[0]), v1 = ld_volatile_u32(fp[1]);
+    if (v0 >= tg[0] && v1 >= tg[1]) break;
+    if ((++polls & 1023u) == 0u) {
+      if (ld_volatile_u32(a.status) & 3u) { drain = true; break; }
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kPWaitTimeoutNs) { atomicOr(a.status, unsigned(KBS_STATUS_TIMEOUT_LSTM)); drain = true; break; }
+    }
+  }
+  __threadfence();
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid_constant__ BArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBStages * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kBStages;
+  uint64_t* acc_full = bars + 2 * kBStages;     // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  volatile int* dep_seq = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  unsigned int* epi_done = reinterpret_cast<unsigned int*>(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = args.H, th = H / kTileCols;
+  const int per_slot = args.nets * args.panels * args.depth * 2 * th;
+  const int n_g = (int(args.T) + 2 * (args.depth - 1) + 1) * per_slot;
+  constexpr int kBlk = kbs_block_k(KIND);
+  const int kb4 = 4 * H / kBlk;                  // K blocks of every item
+  const size_t npH = size_t(args.panels) * kPanelRows * H;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kBEpiWarps); }
+    *dep_seq = 0;
+    *epi_done = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 2 + kBEpiWarps + 1) {
+    if (lane == 0) {
+      // ===== publisher (see rollout_persist_kernel) =====
+      int j = 0;
+      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+        const BItem it = b_decode(args, gi);
+        if (!it.valid) continue;
+        ++j;
+        const unsigned int want = unsigned(j) * kBEpiWarps;
+        unsigned int seen;
+        do {
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(epi_done)) : "memory");
+        } while (seen < want);
+        __threadfence();
+        atomicAdd(args.net[it.net].flags + (it.layer * 2 + it.kind) * args.panels + it.panel, unsigned(kBEpiWarps));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2 + kBEpiWarps) {
+    if (lane == 0) {
+      // ===== dependency poller =====
+      int j = 0;
+      bool drain = false;
+      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+        const BItem it = b_decode(args, gi);
+        if (!it.valid) continue;
+        if (!(args.dbg & 1)) b_wait_deps(args, it, drain);
+        *dep_seq = ++j;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane < 2) {
+      // ===== producers: lane 0 = the dG block (activation side), lane 1 = the weight block of the stage =====
+      uint32_t g = 0;
+      int j = 0;
+      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+        const BItem it = b_decode(args, gi);
+        if (!it.valid) continue;
+        const BNet& N = args.net[it.net];
+        const int slot = it.s + (it.kind == 0 ? 1 : 0);
+        const char* xa = N.dG + (size_t(it.layer) * size_t(args.T + 1) + size_t(slot)) * args.sb4 + size_t(it.panel) * kb4 * kABlockBytes;
+        const char* wb = N.w_bwd[it.layer] + size_t(it.kind == 0 ? th + it.tile : it.tile) * kb4 * kBBlockBytes;
+        ++j;
+        bool need_dep = true;
+        for (int b = 0; b < kb4; ++b, ++g) {
+          const int s = g % kBStages;
+          if (lane == 0) {
+            mbar_wait(&empty[s], ((g / kBStages) & 1) ^ 1);
+            mbar_expect_tx(&full[s], uint32_t(kABlockBytes + kBBlockBytes));
+          }
+          __syncwarp(0x3);
+          uint8_t* sa = smem + size_t(s) * kStageBytes;
+          if (lane == 0 && need_dep) {
+            while (*dep_seq < j) { }
+            __threadfence_block();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            need_dep = false;
+          }
+          const char* src = lane == 0 ? xa + size_t(b) * kABlockBytes : wb + size_t(b) * kBBlockBytes;
+          bulk_g2s(sa + lane * kABlockBytes, src, uint32_t(kABlockBytes), &full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 0) {
+    // ===== MMA issuer: per k-step  dG_hi . [W_hi | W_lo]^T (N = 256: main | correction columns) + dG_lo . W_hi^T (N = 128) =====
+    uint32_t g = 0;
+    int j = 0;
+    for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+      const BItem it = b_decode(args, gi);
+      if (!it.valid) continue;
+      const int buf = j & 1;
+      mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_main = tmem_base + buf * (2 * kTileCols), d_corr = d_main + kTileCols;
+      for (int b = 0; b < kb4; ++b, ++g) {
+        const int s = g % kBStages;
+        mbar_wait(&full[s], (g / kBStages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
+        const uint32_t sb = sa + kABlockBytes;
+        const uint64_t a_hi = umma_desc(sa, 2048, 128), a_lo = umma_desc(sa + 8192, 2048, 128);
+        const uint64_t b_all = umma_desc(sb, 4096, 128);
+        if (elect_one()) {
+          umma<KIND, 2 * kTileCols>(d_main, a_hi, b_all, b != 0);
+          umma<KIND, kTileCols>(d_corr, a_lo, b_all, 1);
+          umma<KIND, 2 * kTileCols>(d_main, a_hi + (4096 >> 4), b_all + (8192 >> 4), 1);
+          umma<KIND, kTileCols>(d_corr, a_lo + (4096 >> 4), b_all + (8192 >> 4), 1);
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
+      ++j;
+    }
+  } else {
+    // ===== epilogue: 16 warps; warp % 4 = TMEM lane quarter (rows), grp = which 32 of the tile's 128 columns (hidden units) =====
+    const int ew = warp - 2;
+    const int q4 = warp & 3, grp = ew >> 2;
+    const int r = q4 * 32 + lane;
+    constexpr float kCorr = (KIND == KBS_KIND_F16) ? (1.0f / kKbsF16LoScale) : 1.0f;
+    const int64_t ld = args.ld;
+    int j = 0;
+    bool bad = false;
+    for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+      const BItem it = b_decode(args, gi);
+      if (!it.valid) continue;
+      const BNet& N = args.net[it.net];
+      const int64_t R = int64_t(it.panel) * kPanelRows + r;
+      const bool live = R < args.n;
+      const int buf = j & 1;
+      const int u0 = it.tile * kTileCols + grp * 32;          // first of this thread's 32 units (columns of the half)
+      while (*dep_seq < j + 1) { }
+      __threadfence_block();
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * kTileCols) + grp * 32);
+      float v[32];
+      {
+        float cr[32];
+        tmem_ld32(tq, v);
+        tmem_ld32(tq + kTileCols, cr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += kCorr * cr[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (live && it.kind == 1) {
+        // ---- X tile: dx(l, s) ----
+        if (it.layer == 0) {
+          char* dst = N.dx0 + size_t(it.s) * args.sbb;       // stays scaled: it is the A^T operand of the dW_in GEMM
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            const float x0[4] = {v[8 * c8], v[8 * c8 + 1], v[8 * c8 + 2], v[8 * c8 + 3]};
+            const float x1[4] = {v[8 * c8 + 4], v[8 * c8 + 5], v[8 * c8 + 6], v[8 * c8 + 7]};
+            bad = bad || sb_out_of_range<KIND, 4>(x0) || sb_out_of_range<KIND, 4>(x1);
+            sb_store_split8<kPanelRows, KIND>(dst, R, u0 + 8 * c8, H / kBlk, sb_split4<KIND>(x0), sb_split4<KIND>(x1), false);
+          }
+        } else {
+          float* dst = N.dx + (size_t(it.layer) * size_t(args.T) + size_t(it.s)) * npH;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            *reinterpret_cast<float4*>(dst + fb_offset(R, u0 + 4 * c4, H)) =
+                make_float4(args.inv_gscale * v[4 * c4], args.inv_gscale * v[4 * c4 + 1], args.inv_gscale * v[4 * c4 + 2],
+                            args.inv_gscale * v[4 * c4 + 3]);
+        }
+      } else if (live) {
+        // ---- H tile: the cell's backward at step s for units u0 .. u0 + 31 ----
+        const size_t s = size_t(it.s);
+        const float keep = args.done[s * ld + R] ? 0.0f : 1.0f;
+        const float* sg = N.save_g + (s * args.depth + it.layer) * 4 * npH;
+        const float* cin = N.c_hist + (size_t(it.layer) * size_t(args.T + 1) + s) * npH;
+        float* dcp = N.dc + size_t(it.layer) * npH;
+        const bool top = it.layer + 1 == args.depth;
+        const float* dxu = top ? N.dh_top + (s * size_t(args.n) + size_t(R)) * H
+                               : N.dx + (size_t(it.layer + 1) * size_t(args.T) + s) * npH;
+        char* dGo = N.dG + (size_t(it.layer) * size_t(args.T + 1) + s) * args.sb4;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {                     // unrolled: v[] must stay in registers
+          const int u = u0 + 8 * c8;
+          float gi[8], gf[8], gg[8], go[8], ci[8], dhi[8], dcr[8];
+          auto ld8fb = [&](const float* base, float (&o)[8], bool coherent) {
+            const float4* p0 = reinterpret_cast<const float4*>(base + fb_offset(R, u, H));
+            const float4* p1 = reinterpret_cast<const float4*>(base + fb_offset(R, u + 4, H));
+            const float4 a = coherent ? __ldcg(p0) : __ldg(p0), b = coherent ? __ldcg(p1) : __ldg(p1);
+            o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+          };
+          ld8fb(sg, gi, false); ld8fb(sg + npH, gf, false); ld8fb(sg + 2 * npH, gg, false); ld8fb(sg + 3 * npH, go, false);
+          ld8fb(cin, ci, false);
+          ld8fb(dcp, dcr, true);
+          if (top) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(dxu + u)), b = __ldg(reinterpret_cast<const float4*>(dxu + u + 4));
+            dhi[0] = a.x; dhi[1] = a.y; dhi[2] = a.z; dhi[3] = a.w; dhi[4] = b.x; dhi[5] = b.y; dhi[6] = b.z; dhi[7] = b.w;
+          } else {
+            ld8fb(dxu, dhi, true);
+          }
+          float di[8], df[8], dg[8], dob[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float c = gf[i] * ci[i] + gi[i] * gg[i];                 // c_s, as the forward pass formed it
+            const float tc = tanhf_(c);
+            const float dh = dhi[i] + keep * (args.inv_gscale * v[8 * c8 + i]);
+            const float dc = keep * dcr[i] + dh * go[i] * (1.0f - tc * tc);
+            di[i] = args.gscale * (dc * gg[i] * gi[i] * (1.0f - gi[i]));
+            df[i] = args.gscale * (dc * ci[i] * gf[i] * (1.0f - gf[i]));
+            dg[i] = args.gscale * (dc * gi[i] * (1.0f - gg[i] * gg[i]));
+            dob[i] = args.gscale * (dh * tc * go[i] * (1.0f - go[i]));
+            dcr[i] = dc * gf[i];
+          }
+          *reinterpret_cast<float4*>(dcp + fb_offset(R, u, H)) = make_float4(dcr[0], dcr[1], dcr[2], dcr[3]);
+          *reinterpret_cast<float4*>(dcp + fb_offset(R, u + 4, H)) = make_float4(dcr[4], dcr[5], dcr[6], dcr[7]);
+          auto st8 = [&](int gate, const float (&x)[8]) {
+            const float x0[4] = {x[0], x[1], x[2], x[3]}, x1[4] = {x[4], x[5], x[6], x[7]};
+            bad = bad || sb_out_of_range<KIND, 4>(x0) || sb_out_of_range<KIND, 4>(x1);
+            sb_store_split8<kPanelRows, KIND>(dGo, R, gate * H + u, 4 * H / kBlk, sb_split4<KIND>(x0), sb_split4<KIND>(x1), false);
+          };
+          st8(0, di); st8(1, df); st8(2, dg); st8(3, dob);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(epi_done)) : "memory");
+      ++j;
+    }
+    sb_flag_range(args.status, bad);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
 // ---- input projection straight from the env-major SoA observations ("async" form of MODE_PROJ_SOA) -------------------------
@@ -1794,13 +2195,180 @@ pack_soa_sb_kernel(const float* __restrict__ soa, int F, int64_t ld, char* __res
   sb_store_split8<kPanelRows, KIND>(sb, row, kc * 8, Kp / kbs_block_k(KIND), sb_split4<KIND>(x0), sb_split4<KIND>(x1), false);
 }
 
+// ---- operands of the weight-gradient GEMMs (C = A^T B over K = all stored rows) ---------------------------------------------
+// fp32 row-major src [rows][ld], columns [col0, col0 + ncols)  ->  TRANSPOSED split-blocked operand: operand "row" = source
+// column j (128 per panel / tile), K = source row.  One thread = one 16-byte chunk per plane: E consecutive source rows of
+// one column (lanes = consecutive columns: coalesced reads of a row, 512 contiguous bytes per store instruction).
+// Source rows >= rows (K padding) and columns >= ncols (panel padding) are zero; column `ones_col` (>= 0) is the constant 1
+// (its product with A^T is A's column sum).  WB: B-operand block layout [chunk][hi|lo][row][16 B], else [hi|lo][chunk][row][16 B].
+template <int KIND, bool WB>
+__global__ void __launch_bounds__(256)
+pack_tn_kernel(const float* __restrict__ src, int64_t ld, int col0, int ncols, int ncols_pad, int64_t rows, int kb_total,
+               char* __restrict__ dst, float scale, int ones_col, unsigned int* __restrict__ status, int64_t n_step, int64_t np_step) {
+  constexpr int E = kbs_chunk_elems(KIND);
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t chunks = int64_t(kb_total) * 4;
+  if (idx >= chunks * ncols_pad) return;
+  const int j = int(idx % ncols_pad);
+  const int64_t kc = idx / ncols_pad;
+  const int64_t r0 = kc * E;
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = 0.0f;
+  // np_step != 0: K' = t np_step + e addresses source row t n_step + e (e < n_step; the rest of a step's panel padding is
+  // zero) -- the K indexing of the per-step operands the persistent kernels keep
+  auto src_row = [&](int64_t k) -> int64_t {
+    if (np_step == 0) return k < rows ? k : -1;
+    const int64_t t = k / np_step, e = k - t * np_step;
+    return (e < n_step && t * n_step + e < rows) ? t * n_step + e : -1;
+  };
+  if (j < ncols) {
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const int64_t sr = src_row(r0 + i);
+      if (sr >= 0) x[i] = __ldcs(src + sr * ld + col0 + j) * scale;
+    }
+  } else if (j == ones_col) {
+#pragma unroll
+    for (int i = 0; i < E; ++i)
+      if (src_row(r0 + i) >= 0) x[i] = 1.0f;
+  }
+  sb_flag_range(status, sb_out_of_range<KIND, 8>(x));
+  uint4 hi, lo;
+  const float x0[4] = {x[0], x[1], x[2], x[3]};
+  const KbsSplit4 s0 = sb_split4<KIND>(x0);
+  if (KIND == KBS_KIND_F16) {
+    const float x1[4] = {x[4], x[5], x[6], x[7]};
+    const KbsSplit4 s1 = sb_split4<KIND>(x1);
+    hi = make_uint4(s0.hi.x, s0.hi.y, s1.hi.x, s1.hi.y);
+    lo = make_uint4(s0.lo.x, s0.lo.y, s1.lo.x, s1.lo.y);
+  } else {
+    hi = s0.hi; lo = s0.lo;
+  }
+  *reinterpret_cast<uint4*>(dst + sb_chunk_offset<kTileCols, KIND, WB>(j, int(r0), kb_total, 0)) = hi;
+  *reinterpret_cast<uint4*>(dst + sb_chunk_offset<kTileCols, KIND, WB>(j, int(r0), kb_total, 1)) = lo;
+}
+
+// The same operand from what the persistent kernels keep: per-step split-blocked buffers [T] x step_bytes, each [np rows][K]
+// K-major (kb_src K blocks per 128-row panel).  One thread = one core matrix of one plane: 8 rows x 8 consecutive K values
+// (128 contiguous bytes) -> transposed in registers -> 8 operand rows (features) x one 16-byte chunk of 8 consecutive K' =
+// t np + row (128 contiguous bytes again).  The planes are copied as they are (no re-split: the GEMM sees bit-identical
+// operand values).  Rows >= n of a step (panel padding: never written by the producers) become zero.  FP16 kind only.
+template <bool WB>
+__global__ void __launch_bounds__(256)
+sb_to_tn_kernel(const char* __restrict__ src, size_t step_bytes, int kb_src, int blk0, int nblk, int64_t n, int panels, int64_t T,
+                char* __restrict__ dst, int kb_total, size_t col_bytes) {
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t total = T * panels * int64_t(nblk) * 2 * 4 * 16;
+  if (idx >= total) return;
+  int64_t q = idx;
+  const int r8 = int(q % 16); q /= 16;
+  const int c = int(q % 4); q /= 4;
+  const int plane = int(q % 2); q /= 2;
+  const int b = int(q % nblk); q /= nblk;
+  const int pnl = int(q % panels);
+  const int64_t t = q / panels;
+  const char* sp = src + size_t(t) * step_bytes + ((((size_t(pnl) * kb_src + size_t(blk0 + b)) * 2 + plane) * 4 + c) * kPanelRows + size_t(r8) * 8) * 16;
+  uint4 in[8];
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    in[rr] = *reinterpret_cast<const uint4*>(sp + rr * 16);
+    if (int64_t(pnl) * kPanelRows + r8 * 8 + rr >= n) in[rr] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  const int64_t kp = (t * panels + pnl) * kPanelRows + r8 * 8;          // K' of the chunk's first row
+  const int64_t kbq = kp / 32;
+  const int cq = int((kp / 8) & 3);
+  const int j0 = b * 32 + c * 8;                                          // operand row of feature 0 of the core matrix
+  char* dp = dst + size_t(j0 / kTileCols) * col_bytes;
+  const int rowj = j0 % kTileCols;
+  const size_t off = WB ? (((size_t(kbq) * 4 + cq) * 2 + plane) * kTileCols + rowj) * 16
+                        : (((size_t(kbq) * 2 + plane) * 4 + cq) * kTileCols + rowj) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const unsigned sel = (i & 1) ? 0x7632u : 0x5410u;
+    uint4 o;
+    o.x = __byte_perm((&in[0].x)[i >> 1], (&in[1].x)[i >> 1], sel);
+    o.y = __byte_perm((&in[2].x)[i >> 1], (&in[3].x)[i >> 1], sel);
+    o.z = __byte_perm((&in[4].x)[i >> 1], (&in[5].x)[i >> 1], sel);
+    o.w = __byte_perm((&in[6].x)[i >> 1], (&in[7].x)[i >> 1], sel);
+    *reinterpret_cast<uint4*>(dp + off + size_t(i) * 16) = o;
+  }
+}
+
+// ... and from env-major SoA observations [T][F][ld] (K' = t np + env; envs >= n zero; column F = ones when `ones`): the B
+// operand of the input-projection weight gradient.  Lanes run along the envs (coalesced reads).  FP16 kind only.
+__global__ void __launch_bounds__(256)
+soa_to_tn_kernel(const float* __restrict__ soa, int F, int64_t ld, int64_t n, int64_t np, int64_t T, int ncols_pad, int ones,
+                 char* __restrict__ dst, int kb_total, size_t col_bytes, unsigned int* __restrict__ status) {
+  const int64_t chunks = T * np / 8;
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= chunks * ncols_pad) return;
+  const int64_t kc = idx % chunks;
+  const int j = int(idx / chunks);
+  const int64_t kp = kc * 8, t = kp / np, e = kp - t * np;
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = 0.0f;
+  if (j < F) {
+    const float* p = soa + (t * F + j) * ld + e;
+    if (e + 8 <= n) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p + 4));
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (e + i < n) x[i] = p[i];
+    }
+  } else if (ones && j == F) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (e + i < n) x[i] = 1.0f;
+  }
+  sb_flag_range(status, sb_out_of_range<KBS_KIND_F16, 8>(x));
+  const float x0[4] = {x[0], x[1], x[2], x[3]}, x1[4] = {x[4], x[5], x[6], x[7]};
+  const KbsSplit4 s0 = sb_split4<KBS_KIND_F16>(x0), s1 = sb_split4<KBS_KIND_F16>(x1);
+  char* dp = dst + size_t(j / kTileCols) * col_bytes;
+  *reinterpret_cast<uint4*>(dp + sb_chunk_offset<kTileCols, KBS_KIND_F16, true>(j % kTileCols, int(kp), kb_total, 0)) =
+      make_uint4(s0.hi.x, s0.hi.y, s1.hi.x, s1.hi.y);
+  *reinterpret_cast<uint4*>(dp + sb_chunk_offset<kTileCols, KBS_KIND_F16, true>(j % kTileCols, int(kp), kb_total, 1)) =
+      make_uint4(s0.lo.x, s0.lo.y, s1.lo.x, s1.lo.y);
+}
+
+// one B block whose column 0 is the constant 1 (hi plane) and everything else 0: the "ones tile" of the TN GEMMs
+template <int KIND>
+__global__ void __launch_bounds__(256) ones_block_kernel(char* __restrict__ blk) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;                 // one 16-byte chunk each: 2 * 4 * 128 chunks
+  if (idx >= 2 * 4 * kTileCols) return;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  // WB block layout [chunk][hi|lo][row][16 B]: row 0 of the hi plane of every chunk = ones
+  const int row = idx % kTileCols, part = (idx / kTileCols) & 1;
+  if (row == 0 && part == 0) {
+    if (KIND == KBS_KIND_F16) { const uint32_t o = 0x3C003C00u; v = make_uint4(o, o, o, o); }
+    else { const uint32_t o = __float_as_uint(1.0f); v = make_uint4(o, o, o, o); }
+  }
+  *reinterpret_cast<uint4*>(blk + size_t(idx) * 16) = v;
+}
+
+// dst[r][c] = sum_s partial[s][r][col0 + c]   (s in order: deterministic)
+__global__ void __launch_bounds__(256)
+tn_reduce_kernel(const float* __restrict__ partial, int ksplit, size_t split_stride, int ldc, int col0, int nrows, int ncols,
+                 float* __restrict__ dst, int ld_dst) {
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= int64_t(nrows) * ncols) return;
+  const int r = int(idx / ncols), c = int(idx % ncols);
+  const float* p = partial + size_t(r) * ldc + col0 + c;
+  float a = 0.0f;
+  for (int sidx = 0; sidx < ksplit; ++sidx) a += p[size_t(sidx) * split_stride];
+  dst[size_t(r) * ld_dst + c] = a;
+}
+
 inline int64_t pad_rows(int64_t n) { return (n + kPanelRows - 1) / kPanelRows * kPanelRows; }
 inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 
 // persistent launch: one CTA per SM (or per item if there are fewer items)
 template <int KIND>
 cudaError_t launch_layer_k(const LayerArgs2& a2, int num_sms, cudaStream_t st) {
-  const int items = a2.net[0].panels * a2.net[0].tiles + a2.net[1].panels * a2.net[1].tiles;
+  const int items = net_items(a2.net[0]) + net_items(a2.net[1]);
   const int grid = items < num_sms ? items : num_sms;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -1967,8 +2535,9 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
   if (!h->tc_attr_set) {      // per device (context), so per handle: a handle on another GPU of the same process needs its own opt-in
     KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_tc_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_tc_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
-    KBS_CUDA_TRY(cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
+    KBS_CUDA_TRY((cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_TF32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes)));
+    KBS_CUDA_TRY((cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes)));
+    KBS_CUDA_TRY((cudaFuncSetAttribute(rollout_persist_kernel<KBS_KIND_F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes)));
     KBS_CUDA_TRY(cudaFuncSetAttribute(input_proj_fused_kernel<KBS_KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
     KBS_CUDA_TRY(cudaFuncSetAttribute(input_proj_fused_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
     h->tc_attr_set = true;
@@ -2260,6 +2829,180 @@ int kbs_tc_bwd_gemm(kbs_handle* h, int net, int layer, const void* dG_sb, float*
   return KBS_OK;
 }
 
+// ---- weight-gradient GEMMs: C = out_scale * A^T B over K = `rows` stored rows, on the tensor cores, split-K ----------------
+KbsTnPlan kbs_tc_tn_plan(const kbs_handle* h, int64_t rows) {
+  KbsTnPlan p{};
+  const int bk = kbs_block_k(tc_kind(h));
+  const int64_t kb_raw = (rows + bk - 1) / bk;
+  // <= 3200 rows (FP16: 100 blocks) per accumulation run, at least 16 runs when there is enough work to split
+  int64_t per = (kb_raw + 15) / 16;
+  const int64_t cap = 3200 / bk;
+  if (per > cap) per = cap;
+  if (per < 1) per = 1;
+  p.kb_split = int(per);
+  p.ksplit = int((kb_raw + per - 1) / per);
+  p.kb_total = p.kb_split * p.ksplit;
+  p.col_bytes = size_t(p.kb_total) * kABlockBytes;          // bytes of one 128-column panel / tile of a transposed operand
+  return p;
+}
+
+int kbs_tc_pack_tn(kbs_handle* h, const KbsTnPlan& plan, bool b_operand, const float* src, int64_t ld, int col0, int ncols,
+                   int ncols_pad, int64_t rows, char* dst, float scale, int ones_col, cudaStream_t st, int64_t n_step,
+                   int64_t np_step) {
+  if (ncols_pad % kTileCols) return KBS_E_SHAPE;
+  { const int rc0 = kbs_status_init(h); if (rc0) return rc0; }
+  const int kind = tc_kind(h);
+  // one launch per 128-column panel / tile: each has its own [kb_total] block run
+  for (int c = 0; c < ncols_pad; c += kTileCols) {
+    const int nc = ncols - c < kTileCols ? (ncols - c > 0 ? ncols - c : 0) : kTileCols;
+    const int oc = (ones_col >= c && ones_col < c + kTileCols) ? ones_col - c : -1;
+    const int64_t total = int64_t(plan.kb_total) * 4 * kTileCols;
+    const unsigned gb = unsigned((total + 255) / 256);
+    char* d = dst + size_t(c / kTileCols) * plan.col_bytes;
+#define KBS_PACK_TN(K_, WB_) KBS_LAUNCH(h, KBS_K_PACK, st, (pack_tn_kernel<K_, WB_><<<gb, 256, 0, st>>>( \
+        src, ld, col0 + c, nc, kTileCols, rows, plan.kb_total, d, scale, oc, h->persist_status, n_step, np_step)))
+    if (kind == KBS_KIND_TF32) { if (b_operand) KBS_PACK_TN(KBS_KIND_TF32, true); else KBS_PACK_TN(KBS_KIND_TF32, false); }
+    else { if (b_operand) KBS_PACK_TN(KBS_KIND_F16, true); else KBS_PACK_TN(KBS_KIND_F16, false); }
+#undef KBS_PACK_TN
+  }
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+// partial [ksplit][m_panels * 128][ldc] with ldc = (n_tiles + ones) * 128; zero_bias: >= ldc zero floats; ones_blk: the ones block
+int kbs_tc_gemm_tn(kbs_handle* h, const KbsTnPlan& plan, const char* a_t, int m_panels, int m_valid, const char* b_t, int n_tiles,
+                   const char* ones_blk, const float* zero_bias, float* partial, float out_scale, cudaStream_t st) {
+  const int kind = tc_kind(h);
+  const int tiles = n_tiles + (ones_blk ? 1 : 0);
+  if (tiles * kTileCols > kMaxBias || m_panels < 1) return KBS_E_SHAPE;
+  LayerArgs2 a2{};
+  LayerArgs& a = a2.net[0];
+  a.x_sb = a_t; a.h_sb_in = a_t;
+  a.w_sb = b_t;
+  a.bias_t = zero_bias;
+  a.raw = partial; a.ldo = tiles * kTileCols; a.oscale = out_scale;
+  a.mode = MODE_PLAIN;
+  a.n = m_valid;
+  a.H = 0; a.kb_x = plan.kb_split; a.kb_h = 0;
+  a.panels = m_panels; a.tiles = tiles;
+  a.ksplit = plan.ksplit; a.kb_stride = plan.kb_total;
+  a.raw_split_stride = size_t(m_panels) * kPanelRows * size_t(a.ldo);
+  a.ones_tile = ones_blk ? n_tiles : -1; a.ones_block = ones_blk;
+  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(h, kind, a2, st)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_tc_ones_block(kbs_handle* h, char* blk, cudaStream_t st) {
+  if (tc_kind(h) == KBS_KIND_TF32) KBS_LAUNCH(h, KBS_K_PACK, st, (ones_block_kernel<KBS_KIND_TF32><<<4, 256, 0, st>>>(blk)));
+  else KBS_LAUNCH(h, KBS_K_PACK, st, (ones_block_kernel<KBS_KIND_F16><<<4, 256, 0, st>>>(blk)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_tc_sb_to_tn(kbs_handle* h, const KbsTnPlan& plan, bool b_operand, const char* src, size_t step_bytes, int kb_src, int blk0,
+                    int nblk, int64_t n, int64_t T, char* dst, cudaStream_t st) {
+  if (tc_kind(h) != KBS_KIND_F16 || nblk % 4) return KBS_E_STATE;
+  const int panels = int(pad_rows(n) / kPanelRows);
+  const int64_t kb_used = (T * panels * kPanelRows + 31) / 32;
+  if (kb_used > plan.kb_total) return KBS_E_SHAPE;
+  if (kb_used < plan.kb_total)                   // K padding behind the last stored row: zero in every panel / tile
+    for (int c = 0; c < nblk / 4; ++c)
+      KBS_CUDA_TRY(cudaMemsetAsync(dst + size_t(c) * plan.col_bytes + size_t(kb_used) * kABlockBytes, 0,
+                                   size_t(plan.kb_total - kb_used) * kABlockBytes, st));
+  const int64_t total = T * panels * int64_t(nblk) * 2 * 4 * 16;
+  const unsigned gb = unsigned((total + 255) / 256);
+  if (b_operand)
+    KBS_LAUNCH(h, KBS_K_PACK, st, (sb_to_tn_kernel<true><<<gb, 256, 0, st>>>(src, step_bytes, kb_src, blk0, nblk, n, panels, T, dst,
+                                                                           plan.kb_total, plan.col_bytes)));
+  else
+    KBS_LAUNCH(h, KBS_K_PACK, st, (sb_to_tn_kernel<false><<<gb, 256, 0, st>>>(src, step_bytes, kb_src, blk0, nblk, n, panels, T, dst,
+                                                                            plan.kb_total, plan.col_bytes)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_tc_soa_to_tn(kbs_handle* h, const KbsTnPlan& plan, const float* soa, int F, int64_t ld, int64_t n, int64_t T, int ncols_pad,
+                     bool ones, char* dst, cudaStream_t st) {
+  if (tc_kind(h) != KBS_KIND_F16 || ncols_pad % kTileCols || F + (ones ? 1 : 0) > ncols_pad) return KBS_E_STATE;
+  { const int rc0 = kbs_status_init(h); if (rc0) return rc0; }
+  const int64_t np = pad_rows(n);
+  const int64_t kb_used = (T * np + 31) / 32;
+  if (kb_used > plan.kb_total) return KBS_E_SHAPE;
+  if (kb_used < plan.kb_total)
+    for (int c = 0; c < ncols_pad / kTileCols; ++c)
+      KBS_CUDA_TRY(cudaMemsetAsync(dst + size_t(c) * plan.col_bytes + size_t(kb_used) * kABlockBytes, 0,
+                                   size_t(plan.kb_total - kb_used) * kABlockBytes, st));
+  const int64_t total = (T * np / 8) * ncols_pad;
+  KBS_LAUNCH(h, KBS_K_PACK, st, (soa_to_tn_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(
+                                    soa, F, ld, n, np, T, ncols_pad, ones ? 1 : 0, dst, plan.kb_total, plan.col_bytes, h->persist_status)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+// ---- backward recurrence of the PPO update: one persistent launch ----
+size_t kbs_tc_bptt_flag_bytes(const kbs_handle* h, int64_t n) {
+  return (size_t(h->p.depth) * 2 * size_t(pad_rows(n) / kPanelRows) * 4 + 255) / 256 * 256;
+}
+bool kbs_tc_bptt_available(const kbs_handle* h, int64_t n, int64_t T) {
+  const int H = h->p.hidden_size, depth = h->p.depth;
+  if (tc_kind(h) != KBS_KIND_F16 || !persist_shape_ok(h) || H % kTileCols) return false;
+  if (!kbs_tc_persistent_available(h, n, T, 2)) return false;
+  const int64_t panels = pad_rows(n) / kPanelRows;
+  return (T + 2 * depth) * 2 * panels * depth * 2 * (H / kTileCols) < (int64_t(1) << 31);
+}
+int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
+  const int H = h->p.hidden_size, depth = h->p.depth;
+  if (!kbs_tc_bptt_available(h, b.n, b.T)) return KBS_E_STATE;
+  { const int rc0 = kbs_status_init(h); if (rc0) return rc0; }
+  if (!h->bptt_attr_set) {
+    KBS_CUDA_TRY(cudaFuncSetAttribute(bptt_persist_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
+    h->bptt_attr_set = true;
+  }
+  const int64_t np = pad_rows(b.n);
+  BArgs a{};
+  for (int k = 0; k < b.nets; ++k) {
+    const KbsNet& Nn = h->net[k];
+    if (!Nn.packed || !Nn.tc_bwd_image) return KBS_E_STATE;
+    BNet& N = a.net[k];
+    for (int l = 0; l < depth; ++l) N.w_bwd[l] = reinterpret_cast<const char*>(Nn.tc_bwd_image) + bwd_layer_bytes(h) * l;
+    N.dG = b.net[k].dG; N.save_g = b.net[k].save_g; N.c_hist = b.net[k].c_hist; N.dh_top = b.net[k].dh_top;
+    N.dx = b.net[k].dx; N.dx0 = b.net[k].dx0; N.dc = b.net[k].dc; N.flags = b.net[k].flags;
+  }
+  a.nets = b.nets; a.depth = depth; a.H = H; a.panels = int(np / kPanelRows);
+  a.n = b.n; a.ld = b.ld; a.T = b.T;
+  a.sbb = kbs_sb_bytes_kind(KBS_KIND_F16, np, H); a.sb4 = kbs_sb_bytes_kind(KBS_KIND_F16, np, 4 * H);
+  a.done = b.done; a.gscale = b.gscale; a.inv_gscale = 1.0f / b.gscale;
+  a.status = h->persist_status;
+  { const char* e = getenv("KBS_PERSIST_DBG"); a.dbg = e ? atoi(e) : 0; }
+  const int64_t per_slot = int64_t(b.nets) * a.panels * depth * 2 * (H / kTileCols);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(per_slot < h->num_sms ? per_slot : h->num_sms));
+  cfg.blockDim = dim3(kBThreads);
+  cfg.dynamicSmemBytes = kBSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;      // every CTA must be resident: they wait on each other's counters
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaSuccess;
+  KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, bptt_persist_kernel<KBS_KIND_F16>, a)));
+  KBS_CUDA_TRY(le);
+  { const int rc0 = kbs_status_publish(h, st); if (rc0) return rc0; }
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_tc_tn_reduce(kbs_handle* h, const KbsTnPlan& plan, const float* partial, int m_panels, int ldc, int col0, int nrows,
+                     int ncols, float* dst, int ld_dst, cudaStream_t st) {
+  const int64_t total = int64_t(nrows) * ncols;
+  KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st, (tn_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(
+                                         partial, plan.ksplit, size_t(m_panels) * kPanelRows * size_t(ldc), ldc, col0, nrows, ncols, dst, ld_dst)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
 size_t kbs_tc_rows_sb_bytes(const kbs_handle* h, int64_t n, int K) { return kbs_sb_bytes_kind(tc_kind(h), pad_rows(n), K); }
 int kbs_tc_kind_of(const kbs_handle* h) { return tc_kind(h); }
 
@@ -2410,8 +3153,13 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     flags[k] = reinterpret_cast<unsigned int*>(fb[k] + 2 * size_t(depth) * fbf);
   }
   const char* legacy_env = getenv("KBS_TC_PER_STEP");          // A/B and cross-check against the per-step launches
-  const int legacy = legacy_env ? atoi(legacy_env) : 0;
+  const int legacy = (legacy_env && !r.save) ? atoi(legacy_env) : 0;
   const bool persistent = !legacy && kbs_tc_persistent_available(h, n, r.T, nets);
+  if (r.save) {                                                // forward pass of the PPO update: per-step history buffers
+    if (!persistent || kind != KBS_KIND_F16 || r.carry_ld) return KBS_E_STATE;
+    for (int k = 0; k < nets; ++k) { hsb[k] = r.hsb_hist[k]; xmid[k] = r.xmid_hist[k]; }
+  }
+  const size_t hstep = r.save ? size_t(r.T + 1) : 2;           // slots per layer of hsb / c_hist
   if ((r.x_is_obs[0] || r.x_is_obs[1]) && !persistent) return KBS_E_STATE;         // folded input projection: persistent only
   if (r.mean && !persistent) return KBS_E_STATE;                                   // dist.mean() output: persistent kernel only
   if (r.carry_ld && (!persistent || nets * depth * 2 > 8 || H % 8)) return KBS_E_STATE;   // flat carries: persistent kernel only
@@ -2423,10 +3171,17 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     int j = 0;
     for (int k = 0; k < nets; ++k)
       for (int l = 0; l < depth; ++l) {
-        J.rm[j] = r.carry[k] + (size_t(l) * 2 + 0) * slot_f; J.blk[j] = hsb[k] + sbb * (2 * l); J.mode[j++] = 0;
-        J.rm[j] = r.carry[k] + (size_t(l) * 2 + 1) * slot_f; J.blk[j] = fb[k] + fbf * (2 * l); J.mode[j++] = 1;
+        char* h_dst = hsb[k] + sbb * (hstep * l);
+        float* c_dst = r.save ? r.c_hist[k] + fbf * (hstep * l) : fb[k] + fbf * (2 * l);
+        if (!r.carry[k]) {                                     // get_initial_model_carry: zeros
+          KBS_CUDA_TRY(cudaMemsetAsync(h_dst, 0, sbb, st));
+          KBS_CUDA_TRY(cudaMemsetAsync(c_dst, 0, fbf * sizeof(float), st));
+          continue;
+        }
+        J.rm[j] = r.carry[k] + (size_t(l) * 2 + 0) * slot_f; J.blk[j] = h_dst; J.mode[j++] = 0;
+        J.rm[j] = r.carry[k] + (size_t(l) * 2 + 1) * slot_f; J.blk[j] = c_dst; J.mode[j++] = 1;
       }
-    carry_convert(h, J, j, n, np, H, st);
+    if (j) carry_convert(h, J, j, n, np, H, st);
   } else {
     for (int k = 0; k < nets; ++k)
       for (int l = 0; l < depth; ++l) {
@@ -2448,6 +3203,7 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
       N.kb_x0 = r.x_is_obs[k] ? fused_kp(h, k) / kbs_block_k(kind) : H / kbs_block_k(kind);
       N.x0_stride = r.x_is_obs[k] ? kbs_sb_bytes_kind(kind, np, fused_kp(h, k)) : sbb;
       N.hsb = hsb[k]; N.xmid = xmid[k]; N.fb = fb[k]; N.flags = flags[k];
+      N.c_hist = r.save ? r.c_hist[k] : nullptr; N.save_g = r.save ? r.save_g[k] : nullptr;
       for (int l = 0; l < depth; ++l) { N.w_sb[l] = layer_w_p(h, k, l); N.bias_t[l] = layer_bias_p(h, k, l); }
       if (r.x_is_obs[k]) { N.w_sb[0] = fused_w(h, k); N.bias_t[0] = fused_bias(h, k); }
       N.w_head = head_w(h, k); N.bias_head = head_bias(h, k);
@@ -2463,6 +3219,7 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     a.ep = r.ep;
     a.action = r.action; a.log_prob = r.log_prob; a.ctrl = (r.ctrl && r.qpos && r.qvel) ? r.ctrl : nullptr; a.value = r.value;
     a.action_in = r.action_in; a.entropy = r.entropy; a.std = r.action_std; a.mean = r.mean;
+    a.sraw = r.save ? r.sraw : nullptr; a.hist = r.save ? 1 : 0;
     a.status = h->persist_status;
     { const char* e = getenv("KBS_PERSIST_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.trace = h->trace_buf;
@@ -2479,12 +3236,15 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     cfg.attrs = at;
     cfg.numAttrs = 1;
     cudaError_t le = cudaSuccess;
-    if (kind == KBS_KIND_TF32)
-      KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<KBS_KIND_TF32>, h->p, a)));
+    if (r.save)
+      KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<KBS_KIND_F16, true>, h->p, a)));
+    else if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<KBS_KIND_TF32, false>, h->p, a)));
     else
-      KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<KBS_KIND_F16>, h->p, a)));
+      KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<KBS_KIND_F16, false>, h->p, a)));
     KBS_CUDA_TRY(le);
     { const int rc0 = kbs_status_publish(h, st); if (rc0) return rc0; }
+    if (r.save) { KBS_LAUNCH_CHECK(); return KBS_OK; }       // the update does not need the final carries
     if (nets * depth * 2 <= 8 && H % 8 == 0) {                       // FB state -> ABI carry; one launch
       CarryJobs J{};
       J.ld_rm = r.carry_ld ? r.carry_ld : H;

@@ -382,6 +382,73 @@ actor_head_fwd_bwd_warp_kernel(const __grid_constant__ kbs_params P, kbs_ppo_los
   }
 }
 
+// Backward half of the actor head for the persistent update path: the forward pass (rollout_persist_kernel<SAVE>) already
+// produced log-prob / entropy / std / filtered mean / raw std output per step ([T][.][ld]); one warp per env (lane = joint)
+// walks the steps backwards through the loss gradient, the Gaussian, softplus + clamp and the low-pass filter's recurrence
+// (done-resets included).  dout [T*n][64] row-major: columns 0..19 = d loss / d mean output, 20..39 = d / d std output, rest 0.
+__global__ void __launch_bounds__(128)
+actor_head_bwd_warp_kernel(const __grid_constant__ kbs_params P, kbs_ppo_loss_params L, const float* __restrict__ action,
+                           const uint8_t* __restrict__ done, const float* __restrict__ old_lp, const float* __restrict__ adv,
+                           const float* __restrict__ y_s, const float* __restrict__ sd_s, const float* __restrict__ sraw_s,
+                           const float* __restrict__ log_prob, float* __restrict__ dout, int64_t T, int64_t ld, int64_t n) {
+  const int64_t e = int64_t(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (e >= n) return;
+  const int j = threadIdx.x & 31;
+  const bool act = j < KBS_NUM_JOINTS;
+  const float inv = 1.0f / (float(T) * float(n));
+  float gy = 0.0f;
+  for (int64_t t = T - 1; t >= 0; --t) {
+    const float lr = log_prob[t * ld + e] - old_lp[t * ld + e];
+    const float lrc = fminf(fmaxf(lr, -L.log_clip_value), L.log_clip_value);
+    const float r = expf(lrc);
+    const float a = adv[t * ld + e];
+    const float dr = (fabsf(lr) <= L.log_clip_value) ? r : 0.0f;
+    const bool inside = r >= 1.0f - L.clip_param && r <= 1.0f + L.clip_param;
+    const float rc = fminf(fmaxf(r, 1.0f - L.clip_param), 1.0f + L.clip_param);
+    const float dpol = (inside || r * a < rc * a) ? a * dr : 0.0f;
+    const float glp = -inv * dpol, gent = -inv * L.entropy_coef;
+    const float keep = done[t * ld + e] ? 0.0f : 1.0f;
+    float* d = dout + (t * n + e) * 64;
+    if (act) {
+      const int64_t so = (t * KBS_NUM_JOINTS + j) * ld + e;
+      const float sd = sd_s[so], yy = y_s[so];
+      const float z = (action[so] - yy) / sd;
+      const float dmu = glp * z / sd;
+      const float dsd = (glp * (z * z - 1.0f) + gent) / sd;
+      const float sraw = sraw_s[so];
+      const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
+      const bool clamped = (sp + P.min_std) * P.var_scale > P.max_std;
+      d[KBS_NUM_JOINTS + j] = clamped ? 0.0f : dsd * P.var_scale * sigm(sraw);
+      gy = dmu + (1.0f - P.lpf_alpha) * keep * gy;
+      d[j] = P.lpf_alpha * gy;
+    }
+    if (j < 24) d[2 * KBS_NUM_JOINTS + j] = 0.0f;
+  }
+}
+
+// ... and of the critic head: values [T][ld] came from the forward pass
+__global__ void __launch_bounds__(kT)
+critic_head_bwd_kernel(kbs_ppo_loss_params L, const float* __restrict__ values, const float* __restrict__ old_values,
+                       const float* __restrict__ targets, float* __restrict__ dout, int64_t T, int64_t ld, int64_t n) {
+  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
+  if (idx >= T * n) return;
+  const int64_t t = idx / n, e = idx - t * n;
+  const float v = values[t * ld + e];
+  const float tgt = targets[t * ld + e];
+  const float err = tgt - v;
+  float dval = -err;
+  if (L.use_clipped_value_loss) {
+    const float vo = old_values[t * ld + e];
+    const float dv = v - vo;
+    const float errc = tgt - (vo + fminf(fmaxf(dv, -L.clip_param), L.clip_param));
+    if (fabsf(dv) > L.clip_param) dval = (err * err > errc * errc) ? -err : 0.0f;
+  }
+  float* d = dout + idx * 64;
+  d[0] = L.value_loss_coef * dval / (float(T) * float(n));
+#pragma unroll
+  for (int j = 1; j < 64; ++j) d[j] = 0.0f;
+}
+
 // Critic head: value_t = out[t][e][0]; dout[.][0] = d loss / d value (clipped value loss), other columns zero.
 __global__ void __launch_bounds__(kT)
 critic_head_fwd_bwd_kernel(kbs_ppo_loss_params L, const float* __restrict__ out, const float* __restrict__ old_values,
@@ -434,10 +501,12 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     if (o.max_grad_norm > 0.0f && nn > o.max_grad_norm) scale = scale * (o.max_grad_norm / fmaxf(nn, 1e-6f));
   }
   const float s = float(step_dev ? step_dev[0] + 1 : step);
-  const float bc1 = 1.0f - powf(o.b1, s), bc2 = 1.0f - powf(o.b2, s);
+  // optax.scale_by_adam: decay and (1 - decay) are Python doubles rounded to fp32 separately; bias correction 1 - decay^count in fp32
+  const float b1 = float(o.b1), b2 = float(o.b2), omb1 = float(1.0 - o.b1), omb2 = float(1.0 - o.b2);
+  const float bc1 = 1.0f - powf(b1, s), bc2 = 1.0f - powf(b2, s);
   const float gi = g[i] * scale;
-  const float mi = o.b1 * m[i] + (1.0f - o.b1) * gi;
-  const float vi = o.b2 * v[i] + (1.0f - o.b2) * gi * gi;
+  const float mi = b1 * m[i] + omb1 * gi;
+  const float vi = b2 * v[i] + omb2 * (gi * gi);
   m[i] = mi; v[i] = vi;
   const float pi = p[i];
   p[i] = pi - o.lr * ((mi / bc1) / (sqrtf(vi / bc2) + o.eps) + o.weight_decay * pi);
@@ -491,7 +560,10 @@ struct NetWork {      // per-net workspace (floats), carved from the handle's sc
   float* w_ihT[KBS_MAX_DEPTH]; float* w_hhT[KBS_MAX_DEPTH]; float* w_outT;
   // tensor-core path: the same activations as split-blocked MMA operands ([T] x per-step buffers)
   char* x0_sb; char* hs_sb[KBS_MAX_DEPTH]; char* h_in_sb[KBS_MAX_DEPTH]; char* dG_sb;
+  // weight-gradient GEMMs on the tensor cores: transposed split-blocked operands (K = all T x n rows), split-K slabs
+  char* tn_a; char* tn_b; float* tn_partial; float* tn_zero; char* tn_ones;
 };
+constexpr int kTnMaxTiles = 8;     // B tiles of 128 columns per TN GEMM (LSTM layer: [x | h] = 4 + the ones tile)
 
 size_t net_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n, bool tc) {
   const size_t H = size_t(h->p.hidden_size), rows = size_t(T) * size_t(n);
@@ -503,6 +575,9 @@ size_t net_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n, bool 
   if (tc) {
     const size_t sbH = kbs_tc_rows_sb_bytes(h, n, int(H)) / 4, sb4H = kbs_tc_rows_sb_bytes(h, n, int(4 * H)) / 4;
     f += size_t(T) * sbH * (1 + 2 * depth) + sb4H + 1024;
+    const KbsTnPlan plan = kbs_tc_tn_plan(h, int64_t(rows));
+    const size_t m_panels = 4 * H / 128, b_tiles = (kp > 2 * H ? kp : 2 * H) / 128 + 1;
+    f += (m_panels + b_tiles) * plan.col_bytes / 4 + size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128) + 1024 + 4096 + 4096;
   }
   return f + 4096;
 }
@@ -610,6 +685,47 @@ int run_net_k(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry
       }
     }
   }
+  if (tc && (4 * H) % 128 == 0 && H % 128 == 0) {
+    // ---- weight gradients on the tensor cores: dW = dG^T [x | h] etc. as split-K tcgen05 GEMMs over all T x n rows ----
+    // Both operands are re-packed with K = row index (pack_tn_kernel); dG-like operands are pre-scaled by the same power of
+    // two as in the recurrent GEMMs and the GEMM's output scale undoes it; every slab covers <= 3 200 rows and the slabs are
+    // added in a fixed order (tn_reduce_kernel): deterministic.  Bias gradients come out of the same GEMM through a tile of
+    // ones (column sum of dG).
+    const KbsTnPlan plan = kbs_tc_tn_plan(h, rows);
+    const float inv = 1.0f / gscale;
+    KBS_CUDA_TRY(cudaMemsetAsync(w.tn_zero, 0, 1024 * sizeof(float), st));
+    if ((rc = kbs_tc_ones_block(h, w.tn_ones, st))) return rc;
+    for (int l = 0; l < depth; ++l) {
+      const float* x_l = l == 0 ? w.x0 : w.hs[l - 1];
+      const int mp = 4 * H / 128, ldc = (2 * H / 128 + 1) * 128;
+      if ((rc = kbs_tc_pack_tn(h, plan, false, w.dG[l], 4 * H, 0, 4 * H, 4 * H, rows, w.tn_a, gscale, -1, st))) return rc;
+      if ((rc = kbs_tc_pack_tn(h, plan, true, x_l, H, 0, H, H, rows, w.tn_b, 1.0f, -1, st))) return rc;
+      if ((rc = kbs_tc_pack_tn(h, plan, true, w.h_in[l], H, 0, H, H, rows, w.tn_b + size_t(H / 128) * plan.col_bytes, 1.0f, -1, st)))
+        return rc;
+      if ((rc = kbs_tc_gemm_tn(h, plan, w.tn_a, mp, 4 * H, w.tn_b, 2 * H / 128, w.tn_ones, w.tn_zero, w.tn_partial, inv, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w.tn_partial, mp, ldc, 0, 4 * H, H, g->w_ih[l], H, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w.tn_partial, mp, ldc, H, 4 * H, H, g->w_hh[l], H, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w.tn_partial, mp, ldc, 2 * H, 4 * H, 1, g->b[l], 1, st))) return rc;
+    }
+    {   // dW_in [H][num_in], db_in [H]: A = dx of layer 0, B = the observation rows with a ones column behind the last feature
+      const int kpp = round_up_i(N.num_in + 1, 128), mp = H / 128;
+      if ((rc = kbs_tc_pack_tn(h, plan, false, w.dxh0, 2 * H, 0, H, H, rows, w.tn_a, gscale, -1, st))) return rc;
+      if ((rc = kbs_tc_pack_tn(h, plan, true, w.obs_rm, kp, 0, N.num_in, kpp, rows, w.tn_b, 1.0f, N.num_in, st))) return rc;
+      if ((rc = kbs_tc_gemm_tn(h, plan, w.tn_a, mp, H, w.tn_b, kpp / 128, nullptr, w.tn_zero, w.tn_partial, inv, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w.tn_partial, mp, kpp, 0, H, N.num_in, g->w_in, N.num_in, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w.tn_partial, mp, kpp, N.num_in, H, 1, g->b_in, 1, st))) return rc;
+    }
+    {   // dW_out [num_out][H], db_out: A = d loss / d out (64 columns, rows >= num_out zero), B = top-layer output + ones tile
+      const int ldc = (H / 128 + 1) * 128;
+      if ((rc = kbs_tc_pack_tn(h, plan, false, w.dout, 64, 0, 64, 128, rows, w.tn_a, gscale, -1, st))) return rc;
+      if ((rc = kbs_tc_pack_tn(h, plan, true, w.hs[depth - 1], H, 0, H, H, rows, w.tn_b, 1.0f, -1, st))) return rc;
+      if ((rc = kbs_tc_gemm_tn(h, plan, w.tn_a, 1, N.num_out, w.tn_b, H / 128, w.tn_ones, w.tn_zero, w.tn_partial, inv, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w.tn_partial, 1, ldc, 0, N.num_out, H, g->w_out, H, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w.tn_partial, 1, ldc, H, N.num_out, 1, g->b_out, 1, st))) return rc;
+    }
+    KBS_LAUNCH_CHECK();
+    return KBS_OK;
+  }
   // weight gradients: sums over all (t, env) rows
   const int chunks = int((rows + 511) / 512);
   auto colsum = [&](const float* X, int ldx, int cols, float* out) {
@@ -647,6 +763,172 @@ int run_net(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0,
   return run_net_k<KBS_KIND_F16>(h, net, b, carry0, w, gates_pre, dc_rec, part, splits, n, st, backward, g, tc);
 }
 
+// ---- the persistent form of kbs_ppo_grad (FP16-split datapath) ---------------------------------------------------------
+// forward: input projections (tensor core, straight from the SoA observations) -> rollout_persist_kernel<SAVE> (ALL T steps
+// of both networks, output heads included, one launch; keeps operands + activated gates) -> head backward (loss gradient)
+// -> dh_top = dout W_out -> bptt_persist_kernel (the whole backward recurrence of both networks, one launch) -> weight
+// gradients as split-K tcgen05 GEMMs over all T x n rows, operands = the kept per-step buffers re-packed with K = row.
+struct PersistWork {
+  char* x_sb; char* xmid; char* hsb; float* c_hist; float* save_g; char* dG; float* dx; char* dx0; float* dc;
+  float* dh_top; float* dout; float* w_outT; unsigned int* bflags;
+  char* tn_a; char* tn_b; float* tn_partial; float* tn_zero; char* tn_ones;
+};
+
+size_t persist_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n) {
+  const size_t H = size_t(h->p.hidden_size), depth = size_t(h->p.depth);
+  const size_t np = size_t((n + 127) / 128 * 128), npH = np * H, rows = size_t(T) * size_t(n);
+  const size_t sbf = kbs_tc_rows_sb_bytes(h, n, int(H)) / 4, sb4f = kbs_tc_rows_sb_bytes(h, n, int(4 * H)) / 4;
+  const KbsTnPlan plan = kbs_tc_tn_plan(h, int64_t(T) * int64_t(np));
+  const size_t kpp = size_t(round_up_i(h->net[net].num_in + 1, 128));
+  const size_t m_panels = 4 * H / 128, b_tiles = (kpp > 2 * H ? kpp : 2 * H) / 128 + 1;
+  size_t f = size_t(T) * sbf /*x_sb*/ + depth * size_t(T) * sbf /*xmid*/ + depth * size_t(T + 1) * sbf /*hsb*/ +
+             depth * size_t(T + 1) * npH /*c_hist*/ + size_t(T) * depth * 4 * npH /*save_g*/ + depth * size_t(T + 1) * sb4f /*dG*/ +
+             depth * size_t(T) * npH /*dx*/ + size_t(T) * sbf /*dx0*/ + depth * npH /*dc*/ + rows * H /*dh_top*/ + rows * 64 /*dout*/ +
+             64 * H + kbs_tc_bptt_flag_bytes(h, n) / 4;
+  f += (m_panels + b_tiles) * plan.col_bytes / 4 + size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128) + 1024 + 4096;
+  return f + 64 * 32;       // carve() rounds every piece up to 64 floats
+}
+
+int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_ppo_batch& b, const kbs_net_grads* const* grads,
+                        float* log_probs, float* values, float* entropy, float* stats_out, int64_t n, cudaStream_t st) {
+  const int H = h->p.hidden_size, depth = h->p.depth;
+  const int64_t T = b.T, ld = b.ld, rows = T * n, np = (n + 127) / 128 * 128;
+  const size_t npH = size_t(np) * H;
+  const size_t sbb = kbs_tc_rows_sb_bytes(h, n, H), sb4 = kbs_tc_rows_sb_bytes(h, n, 4 * H);
+  const size_t ws_f = kbs_tc_rollout_ws_floats(h, n);
+  const size_t osb_f[2] = {size_t(kbs_tc_obs_sb_floats(h, 0, n, T)), size_t(kbs_tc_obs_sb_floats(h, 1, n, T))};
+  const size_t head_f = 3 * size_t(T) * KBS_NUM_JOINTS * ld + size_t(KBS_NUM_JOINTS) * ld + 64;
+  const size_t total = ws_f + osb_f[0] + osb_f[1] + head_f + persist_work_floats(h, 0, T, n) + persist_work_floats(h, 1, T, n) +
+                       size_t(16) * 4096 + 8192;
+  int rc = kbs_scratch_reserve(h, total);
+  if (rc) return rc;
+  float* p = h->scratch;
+  float* ws = carve(p, ws_f);
+  float* osb[2] = {carve(p, osb_f[0]), carve(p, osb_f[1])};
+  float* y_s = carve(p, size_t(T) * KBS_NUM_JOINTS * ld);
+  float* sd_s = carve(p, size_t(T) * KBS_NUM_JOINTS * ld);
+  float* sraw_s = carve(p, size_t(T) * KBS_NUM_JOINTS * ld);
+  float* lpf = carve(p, size_t(KBS_NUM_JOINTS) * ld);
+  double* loss_part = reinterpret_cast<double*>(carve(p, 8192));
+  const KbsTnPlan plan = kbs_tc_tn_plan(h, T * np);
+  PersistWork w[2];
+  for (int k = 0; k < 2; ++k) {
+    const size_t kpp = size_t(round_up_i(h->net[k].num_in + 1, 128));
+    const size_t m_panels = size_t(4 * H / 128), b_tiles = (kpp > size_t(2 * H) ? kpp : size_t(2 * H)) / 128 + 1;
+    w[k].x_sb = reinterpret_cast<char*>(carve(p, size_t(T) * sbb / 4));
+    w[k].xmid = reinterpret_cast<char*>(carve(p, size_t(depth) * T * sbb / 4));
+    w[k].hsb = reinterpret_cast<char*>(carve(p, size_t(depth) * (T + 1) * sbb / 4));
+    w[k].c_hist = carve(p, size_t(depth) * (T + 1) * npH);
+    w[k].save_g = carve(p, size_t(T) * depth * 4 * npH);
+    w[k].dG = reinterpret_cast<char*>(carve(p, size_t(depth) * (T + 1) * sb4 / 4));
+    w[k].dx = carve(p, size_t(depth) * T * npH);
+    w[k].dx0 = reinterpret_cast<char*>(carve(p, size_t(T) * sbb / 4));
+    w[k].dc = carve(p, size_t(depth) * npH);
+    w[k].dh_top = carve(p, size_t(rows) * H);
+    w[k].dout = carve(p, size_t(rows) * 64);
+    w[k].w_outT = carve(p, size_t(64) * H);
+    w[k].bflags = reinterpret_cast<unsigned int*>(carve(p, kbs_tc_bptt_flag_bytes(h, n) / 4));
+    w[k].tn_a = reinterpret_cast<char*>(carve(p, m_panels * plan.col_bytes / 4));
+    w[k].tn_b = reinterpret_cast<char*>(carve(p, b_tiles * plan.col_bytes / 4));
+    w[k].tn_partial = carve(p, size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128));
+    w[k].tn_zero = carve(p, 1024);
+    w[k].tn_ones = reinterpret_cast<char*>(carve(p, 4096));
+  }
+  // ---- forward ----
+  KbsTcRolloutArgs r{};
+  {
+    const float* obs_soa[2] = {b.actor_obs, b.critic_obs};
+    float* xsb[2] = {reinterpret_cast<float*>(w[0].x_sb), reinterpret_cast<float*>(w[1].x_sb)};
+    if ((rc = kbs_tc_input_proj_all(h, 2, obs_soa, osb, xsb, ld, n, T, st, nullptr, nullptr, nullptr))) return rc;
+    r.x_sb_all[0] = xsb[0]; r.x_sb_all[1] = xsb[1];
+  }
+  r.n = n; r.ld = ld; r.T = T; r.with_critic = true;
+  r.carry[0] = const_cast<float*>(b.actor_carry0); r.carry[1] = const_cast<float*>(b.critic_carry0);
+  r.done = b.done; r.actor_obs = b.actor_obs;
+  // the low-pass state: a private copy of lpf0 (the kernel advances it in place)
+  if (b.lpf0) KBS_CUDA_TRY(cudaMemcpyAsync(lpf, b.lpf0, size_t(KBS_NUM_JOINTS) * ld * 4, cudaMemcpyDeviceToDevice, st));
+  else KBS_CUDA_TRY(cudaMemsetAsync(lpf, 0, size_t(KBS_NUM_JOINTS) * ld * 4, st));
+  r.lpf = lpf;
+  r.action_in = b.action; r.log_prob = log_probs; r.entropy = entropy; r.action_std = sd_s; r.mean = y_s; r.value = values;
+  r.ws = ws;
+  r.save = 1; r.sraw = sraw_s;
+  for (int k = 0; k < 2; ++k) { r.xmid_hist[k] = w[k].xmid; r.hsb_hist[k] = w[k].hsb; r.c_hist[k] = w[k].c_hist; r.save_g[k] = w[k].save_g; }
+  if ((rc = kbs_tc_rollout_recurrent(h, r, st))) return rc;
+  // ---- heads: d loss / d out ----
+  KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
+             (actor_head_bwd_warp_kernel<<<unsigned((n + 3) / 4), 128, 0, st>>>(h->p, L, b.action, b.done, b.old_log_probs, b.advantages,
+                                                                               y_s, sd_s, sraw_s, log_probs, w[0].dout, T, ld, n)));
+  KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
+             (critic_head_bwd_kernel<<<blocks(rows), kT, 0, st>>>(L, values, b.old_values, b.value_targets, w[1].dout, T, ld, n)));
+  float gscale = 16.0f;
+  while (gscale < 16.0f * float(rows)) gscale *= 2.0f;
+  KbsBpttArgs ba{};
+  for (int k = 0; k < 2; ++k) {
+    const KbsNet& N = h->net[k];
+    KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(64) * H), kT, 0, st>>>(N.w_out, 64, H, w[k].w_outT)));
+    if ((rc = kbs_simt_gemm_nt(h, w[k].dout, 64, w[k].w_outT, 64, nullptr, w[k].dh_top, H, rows, H, 64, 0, st))) return rc;
+    if ((rc = kbs_tc_pack_bwd(h, k, st))) return rc;
+    KBS_CUDA_TRY(cudaMemsetAsync(w[k].dc, 0, size_t(depth) * npH * 4, st));
+    KBS_CUDA_TRY(cudaMemsetAsync(w[k].bflags, 0, kbs_tc_bptt_flag_bytes(h, n), st));
+    for (int l = 0; l < depth; ++l)          // dG(l, T) = 0: the operand of the first backward step's recurrent GEMM
+      KBS_CUDA_TRY(cudaMemsetAsync(w[k].dG + (size_t(l) * (T + 1) + T) * sb4, 0, sb4, st));
+    KbsBpttNet& B = ba.net[k];
+    B.dG = w[k].dG; B.save_g = w[k].save_g; B.c_hist = w[k].c_hist; B.dh_top = w[k].dh_top; B.dx = w[k].dx; B.dx0 = w[k].dx0;
+    B.dc = w[k].dc; B.flags = w[k].bflags;
+  }
+  ba.nets = 2; ba.n = n; ba.ld = ld; ba.T = T; ba.done = b.done; ba.gscale = gscale;
+  if ((rc = kbs_tc_bptt(h, ba, st))) return rc;
+  // ---- weight gradients ----
+  const float inv = 1.0f / gscale;
+  const int kbH = H / 32, kb4 = 4 * H / 32;
+  for (int k = 1; k >= 0; --k) {             // critic first: its gradients are final first (see ppo.py: the all-reduce of a
+    const KbsNet& N = h->net[k];             // network can start while the other network's GEMMs run)
+    const kbs_net_grads* g = grads[k];
+    KBS_CUDA_TRY(cudaMemsetAsync(w[k].tn_zero, 0, 1024 * sizeof(float), st));
+    if ((rc = kbs_tc_ones_block(h, w[k].tn_ones, st))) return rc;
+    for (int l = 0; l < depth; ++l) {
+      const int mp = 4 * H / 128, ldc = (2 * H / 128 + 1) * 128;
+      const char* x_hist = l == 0 ? w[k].x_sb : w[k].xmid + size_t(l - 1) * T * sbb;
+      if ((rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dG + size_t(l) * (T + 1) * sb4, sb4, kb4, 0, kb4, n, T, w[k].tn_a, st))) return rc;
+      if ((rc = kbs_tc_sb_to_tn(h, plan, true, x_hist, sbb, kbH, 0, kbH, n, T, w[k].tn_b, st))) return rc;
+      if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].hsb + size_t(l) * (T + 1) * sbb, sbb, kbH, 0, kbH, n, T,
+                                w[k].tn_b + size_t(H / 128) * plan.col_bytes, st)))
+        return rc;
+      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, mp, 4 * H, w[k].tn_b, 2 * H / 128, w[k].tn_ones, w[k].tn_zero, w[k].tn_partial, inv, st)))
+        return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 0, 4 * H, H, g->w_ih[l], H, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, H, 4 * H, H, g->w_hh[l], H, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 2 * H, 4 * H, 1, g->b[l], 1, st))) return rc;
+    }
+    {   // dW_in, db_in
+      const int kpp = round_up_i(N.num_in + 1, 128), mp = H / 128;
+      if ((rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dx0, sbb, kbH, 0, kbH, n, T, w[k].tn_a, st))) return rc;
+      if ((rc = kbs_tc_soa_to_tn(h, plan, k == 0 ? b.actor_obs : b.critic_obs, N.num_in, ld, n, T, kpp, true, w[k].tn_b, st))) return rc;
+      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, mp, H, w[k].tn_b, kpp / 128, nullptr, w[k].tn_zero, w[k].tn_partial, inv, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, kpp, 0, H, N.num_in, g->w_in, N.num_in, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, kpp, N.num_in, H, 1, g->b_in, 1, st))) return rc;
+    }
+    {   // dW_out, db_out: A = d loss / d out (row-major, K' = t np + env), B = the top layer's outputs + ones tile
+      const int ldc = (H / 128 + 1) * 128;
+      if ((rc = kbs_tc_pack_tn(h, plan, false, w[k].dout, 64, 0, 64, 128, rows, w[k].tn_a, gscale, -1, st, n, np))) return rc;
+      if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].xmid + size_t(depth - 1) * T * sbb, sbb, kbH, 0, kbH, n, T, w[k].tn_b, st))) return rc;
+      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, 1, N.num_out, w[k].tn_b, H / 128, w[k].tn_ones, w[k].tn_zero, w[k].tn_partial, inv, st)))
+        return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, 0, N.num_out, H, g->w_out, H, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, H, N.num_out, 1, g->b_out, 1, st))) return rc;
+    }
+  }
+  {
+    kbs_ppo_loss_io io{};
+    io.log_probs = log_probs; io.old_log_probs = b.old_log_probs; io.advantages = b.advantages; io.values = values;
+    io.old_values = b.old_values; io.value_targets = b.value_targets; io.entropy = entropy; io.out = stats_out;
+    io.T = T; io.ld = ld;
+    if ((rc = kbs_launch_ppo_loss_at(h, L, io, n, loss_part, st))) return rc;
+  }
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -663,6 +945,15 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
     if (!h->net[k].packed) return KBS_E_STATE;
   { const int rc0 = kbs_enter(h); if (rc0) return rc0; }
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // FP16-split datapath: the persistent form (2 launches for the whole forward + backward recurrence); KBS_PPO_PER_STEP=1
+    // keeps the per-step launch sequence below (A/B, and the cross-check of the persistent kernels)
+    const char* e = getenv("KBS_PPO_PER_STEP");
+    if (!(e && atoi(e)) && h->p.gemm_path == KBS_GEMM_TC_2XF16 && h->p.depth <= 2 && kbs_tc_bptt_available(h, n, b->T)) {
+      const kbs_net_grads* gr[2] = {actor, critic};
+      return ppo_grad_persistent(h, *params, *b, gr, log_probs, values, entropy, stats_out, n, st);
+    }
+  }
   const int H = h->p.hidden_size, depth = h->p.depth;
   const int64_t T = b->T, ld = b->ld, rows = T * n;
   const size_t sH = size_t(n) * H;
@@ -714,6 +1005,13 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
         w[k].h_in_sb[l] = reinterpret_cast<char*>(carve(p, size_t(T) * sbH));
       }
       w[k].dG_sb = reinterpret_cast<char*>(carve(p, sb4H));
+      const KbsTnPlan plan = kbs_tc_tn_plan(h, rows);
+      const size_t m_panels = size_t(4 * H / 128), b_tiles = size_t((int(kp) > 2 * H ? int(kp) : 2 * H) / 128 + 1);
+      w[k].tn_a = reinterpret_cast<char*>(carve(p, m_panels * plan.col_bytes / 4));
+      w[k].tn_b = reinterpret_cast<char*>(carve(p, b_tiles * plan.col_bytes / 4));
+      w[k].tn_partial = carve(p, size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128));
+      w[k].tn_zero = carve(p, 1024);
+      w[k].tn_ones = reinterpret_cast<char*>(carve(p, 4096));
     }
   }
   // The two networks share nothing until the loss statistics: the critic runs on the handle's side stream, forked from
@@ -770,7 +1068,7 @@ int kbs_adamw_step(kbs_handle* h, float* param, const float* grad, float* m, flo
                    const float* grad_norm, int64_t* step_dev, int64_t step, void* stream) {
   if (!h || !param || !grad || !m || !v || !o) return KBS_E_NULL;
   if (count <= 0 || (!step_dev && step <= 0)) return KBS_E_SHAPE;
-  if (!(o->b1 >= 0.0f && o->b1 < 1.0f) || !(o->b2 >= 0.0f && o->b2 < 1.0f) || !(o->eps >= 0.0f)) return KBS_E_PARAM;
+  if (!(o->b1 >= 0.0 && o->b1 < 1.0) || !(o->b2 >= 0.0 && o->b2 < 1.0) || !(o->eps >= 0.0f)) return KBS_E_PARAM;
   cudaStream_t st = (cudaStream_t)stream;
   static_assert(sizeof(long long) == sizeof(int64_t), "step counter width");
   long long* sd = reinterpret_cast<long long*>(step_dev);

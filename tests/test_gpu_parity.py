@@ -643,7 +643,26 @@ def _ppo_batch(rng, T, N, H, p, wa, wc):
 @pytest.mark.parametrize("T,N,hidden", [(5, 24, 128), (7, 70, 256), (4, 300, 256)])
 def test_ppo_grad_against_autograd(dev, T, N, hidden, path):
     """8f-1: back-propagation through time through both LSTMs, the projections, the actor head (incl. the low-pass filter's
-    recurrence and the done-resets) and the PPO loss, against torch.autograd (float64) on the same minibatch."""
+    recurrence and the done-resets) and the PPO loss, against torch.autograd (float64) on the same minibatch.  On the
+    FP16-split datapath this is the persistent form (rollout_persist_kernel<SAVE> + bptt_persist_kernel + split-K tcgen05
+    weight-gradient GEMMs); the other two datapaths keep the per-step launch sequence."""
+    _ppo_grad_case(dev, T, N, hidden, path)
+
+
+@pytest.mark.parametrize("T,N,hidden", [(7, 70, 256), (33, 300, 256), (6, 130, 128)])
+def test_ppo_grad_per_step_launches_against_autograd(dev, T, N, hidden, monkeypatch):
+    """The per-step launch sequence of the FP16-split datapath (KBS_PPO_PER_STEP=1): the cross-check of the persistent form."""
+    monkeypatch.setenv("KBS_PPO_PER_STEP", "1")
+    _ppo_grad_case(dev, T, N, hidden, L.GEMM_TC_2XF16)
+
+
+@pytest.mark.parametrize("T,N", [(33, 300), (100, 512)])
+def test_ppo_grad_persistent_longer_rollouts(dev, T, N):
+    """The persistent update at the reference's rollout length (T = 100, 512 trajectories: train.py:1764-1766)."""
+    _ppo_grad_case(dev, T, N, 256, L.GEMM_TC_2XF16)
+
+
+def _ppo_grad_case(dev, T, N, hidden, path):
     import ppo_grad_torch as G
 
     e, wa, wc = Hn.make_engine(hidden=hidden, gemm_path=path, device=dev)
@@ -664,6 +683,7 @@ def test_ppo_grad_against_autograd(dev, T, N, hidden, path):
              "value_targets": d(b["value_targets"]), "old_values": d(b["old_values"])}
     out = e.ppo_grad(batch, ga, gc, n_envs=N)
     torch.cuda.synchronize()
+    assert e.device_status() == 0
     close(S(out["log_probs"], N), lp_ref, "log_probs", atol=1e-4)
     close(S(out["values"], N), val_ref, "values", atol=1e-5)
     close(out["stats"].cpu().numpy(), np.array((loss,) + stats, np.float32), "loss stats", rtol=2e-5, atol=1e-5)
@@ -851,6 +871,8 @@ def test_f16_split_range_guard_sets_status(dev):
     with pytest.raises(RuntimeError, match="health word"):
         e.rollout(io, N)
     e.device_status_reset()
+    for k in ("actor_carry", "critic_carry", "lpf", "pg_carry"):    # the poisoned run left inf / NaN in the carries it advanced
+        io[k].zero_()
     e.rollout(io, N)
     assert e.device_status() == 0
     e.close()

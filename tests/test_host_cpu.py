@@ -76,7 +76,7 @@ def test_ctypes_structs_match_header(lib_built):
             decl = decl.strip()
             if not decl:
                 continue
-            names = re.sub(r"^(const\s+)?(kbs_\w+|float|int32_t|int64_t|uint8_t)\s*\*?\s*", "", decl)
+            names = re.sub(r"^(const\s+)?(kbs_\w+|float|double|int32_t|int64_t|uint8_t)\s*\*?\s*", "", decl)
             for nm in names.split(","):
                 out.append(re.sub(r"[\*\s]|\[.*?\]", "", nm))
         return out

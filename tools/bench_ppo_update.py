@@ -38,8 +38,10 @@ rn = lambda *s, sc=1.0: torch.randn(s, generator=g, **f32) * sc
 batch = {"actor_obs": rn(T, 65, ld, sc=0.7), "critic_obs": rn(T, 475, ld, sc=0.7), "action": rn(T, 20, ld, sc=0.3),
          "done": (torch.rand((T, ld), generator=g, device=dev) < 0.01).to(torch.uint8),
          "old_log_probs": rn(T, ld) - 20.0, "advantages": rn(T, ld), "value_targets": rn(T, ld, sc=0.5), "old_values": rn(T, ld, sc=0.5)}
-out = up.grads(batch, N)                         # old log-probs / values near the current policy, as in a real update
-batch["old_log_probs"], batch["old_values"] = out["log_probs"] + rn(T, ld, sc=0.1), out["values"] + rn(T, ld, sc=0.2)
+# old log-probs / values near the current policy, as in a real update: taken from a forward-only pass (kbs_ppo_variables)
+fwd = eng.ppo_variables(batch["actor_obs"], batch["action"], batch["done"], torch.zeros((2, 2, N, H), **f32), torch.zeros((20, ld), **f32),
+                        batch["critic_obs"], torch.zeros((2, 2, N, H), **f32), want_std=False, n_envs=N)
+batch["old_log_probs"], batch["old_values"] = fwd["log_probs"] + rn(T, ld, sc=0.1), fwd["values"] + rn(T, ld, sc=0.2)
 
 
 def sync():
@@ -67,11 +69,12 @@ if world > 1:
     lo, hi = chk.clone(), chk.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert float(hi - lo) == 0.0, "replicas diverged"
+assert eng.device_status() == 0, "device health word set during the update"
 if rank == 0:
     msf = float(ms.item())
     print(json.dumps({"config": "configs[3] PPO minibatch update (kbs_ppo_grad + NCCL all-reduce + kbs_grad_norm + kbs_adamw_step)", "n_gpus": world,
                       "trajectories_per_gpu": N, "T": T, "ms_per_update": msf, "env_steps_per_s": world * N * T / (msf * 1e-3),
-                      "grad_floats": int(up.grad.numel()), "loss": float(st["stats"][0]), "datapath": "tcgen05 2xFP16-split recurrent GEMMs + fp32 FFMA batched GEMMs", "launch": "cuda-graph replay" if a.graph else "eager"}),
+                      "grad_floats": int(up.grad.numel()), "loss": float(st["stats"][0]), "datapath": "persistent tcgen05 forward (SAVE) + BPTT kernels, split-K tcgen05 weight-gradient GEMMs (2xFP16-split)", "launch": "cuda-graph replay" if a.graph else "eager"}),
           flush=True)
 eng.close()
 if world > 1:

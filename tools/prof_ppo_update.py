@@ -16,6 +16,9 @@ rn = lambda *s, sc=1.0: torch.randn(s, generator=g, **f32) * sc
 batch = {"actor_obs": rn(T, 65, ld, sc=0.7), "critic_obs": rn(T, 475, ld, sc=0.7), "action": rn(T, 20, ld, sc=0.3),
          "done": (torch.rand((T, ld), generator=g, device=dev) < 0.01).to(torch.uint8),
          "old_log_probs": rn(T, ld) - 20.0, "advantages": rn(T, ld), "value_targets": rn(T, ld, sc=0.5), "old_values": rn(T, ld, sc=0.5)}
+fwd = eng.ppo_variables(batch["actor_obs"], batch["action"], batch["done"], torch.zeros((2, 2, N, H), **f32), torch.zeros((20, ld), **f32),
+                        batch["critic_obs"], torch.zeros((2, 2, N, H), **f32), want_std=False, n_envs=N)
+batch["old_log_probs"], batch["old_values"] = fwd["log_probs"] + rn(T, ld, sc=0.1), fwd["values"] + rn(T, ld, sc=0.2)
 for _ in range(2):
     up.grads(batch, N)
 torch.cuda.synchronize()
