@@ -29,3 +29,9 @@ ffi: $(OUT)
 	$(NVCC) -O2 -std=c++17 -x cu $(ARCH) -Iinclude -I$(JAX_INCLUDE) -Xcompiler -fPIC -shared \
 	  $(SRC)/kbs_xla_ffi.cc -o $(PKG)/libkbs_xla_ffi.so -L$(PKG) -lkbotstep -Xlinker -rpath -Xlinker '$$ORIGIN' -lcudart
 .PHONY: ffi
+
+# Type-check the XLA-FFI shim without jaxlib: g++ against the stub FFI surface in tests/ffi_stub (every handler is
+# static_asserted against its binding); run by tests/test_host_cpu.py.
+ffi-check:
+	g++ -std=c++17 -fsyntax-only -Wall -Itests/ffi_stub -Iinclude -I/usr/local/cuda/include -x c++ $(SRC)/kbs_xla_ffi.cc
+.PHONY: ffi-check

@@ -227,6 +227,11 @@ typedef struct kbs_net_grads {
 int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo_batch* batch, const kbs_net_grads* actor,
                  const kbs_net_grads* critic, float* log_probs, float* values, float* entropy, float* stats_out,
                  int64_t n_envs, void* stream);
+/* Overlap hook for the gradient all-reduce (the only collective of the path): kbs_ppo_grad finishes the critic's gradients
+ * before the actor's; when `critic_ready` (a cudaEvent_t) is set, the next kbs_ppo_grad calls record it on their stream at
+ * that point, so the caller can start reducing the critic's gradients on another stream while the actor's weight-gradient
+ * GEMMs still run.  NULL clears it.  (The torch datapaths without the persistent kernels record it at the end.) */
+int kbs_ppo_grad_set_events(kbs_handle* h, void* critic_ready);
 /* Replaces: optax.adam -- the adam_weight_decay == 0.0 branch of get_optimizer (train.py:1062-1063; NOT the branch the launch
  * config takes: see kbs_adamw_step): scale_by_adam, eps_root = 0, then -learning_rate, on one flat parameter array: g = grad * grad_scale (1 / world_size after a sum all-reduce, or a global-norm clip factor);
  * m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2; p -= lr (m / (1 - b1^step)) / (sqrt(v / (1 - b2^step)) + eps).  step >= 1. */
@@ -467,7 +472,7 @@ int kbs_debug_tc_trace(kbs_handle* h, long long* trace_out, int64_t n_envs, void
 /* Same stamps for LSTM layer `layer` at step `step` of subsequent kbs_rollout calls (trace_out NULL detaches). */
 int kbs_debug_tc_trace_attach(kbs_handle* h, long long* trace_out, int64_t step, int layer);
 
-#define KBS_NUM_KERNEL_IDS 17
+#define KBS_NUM_KERNEL_IDS 21
 int kbs_profile_enable(kbs_handle* h, int on);
 int kbs_profile_read(kbs_handle* h, int max_ids, double* total_ms, int64_t* launches);
 const char* kbs_kernel_name(int id);

@@ -2859,7 +2859,7 @@ int kbs_tc_pack_tn(kbs_handle* h, const KbsTnPlan& plan, bool b_operand, const f
     const int64_t total = int64_t(plan.kb_total) * 4 * kTileCols;
     const unsigned gb = unsigned((total + 255) / 256);
     char* d = dst + size_t(c / kTileCols) * plan.col_bytes;
-#define KBS_PACK_TN(K_, WB_) KBS_LAUNCH(h, KBS_K_PACK, st, (pack_tn_kernel<K_, WB_><<<gb, 256, 0, st>>>( \
+#define KBS_PACK_TN(K_, WB_) KBS_LAUNCH(h, KBS_K_PACK_TN, st, (pack_tn_kernel<K_, WB_><<<gb, 256, 0, st>>>( \
         src, ld, col0 + c, nc, kTileCols, rows, plan.kb_total, d, scale, oc, h->persist_status, n_step, np_step)))
     if (kind == KBS_KIND_TF32) { if (b_operand) KBS_PACK_TN(KBS_KIND_TF32, true); else KBS_PACK_TN(KBS_KIND_TF32, false); }
     else { if (b_operand) KBS_PACK_TN(KBS_KIND_F16, true); else KBS_PACK_TN(KBS_KIND_F16, false); }
@@ -2888,7 +2888,7 @@ int kbs_tc_gemm_tn(kbs_handle* h, const KbsTnPlan& plan, const char* a_t, int m_
   a.ksplit = plan.ksplit; a.kb_stride = plan.kb_total;
   a.raw_split_stride = size_t(m_panels) * kPanelRows * size_t(a.ldo);
   a.ones_tile = ones_blk ? n_tiles : -1; a.ones_block = ones_blk;
-  KBS_LAUNCH(h, KBS_K_LSTM_TC, st, (launch_layer(h, kind, a2, st)));
+  KBS_LAUNCH(h, KBS_K_GEMM_TN, st, (launch_layer(h, kind, a2, st)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }
@@ -2913,10 +2913,10 @@ int kbs_tc_sb_to_tn(kbs_handle* h, const KbsTnPlan& plan, bool b_operand, const 
   const int64_t total = T * panels * int64_t(nblk) * 2 * 4 * 16;
   const unsigned gb = unsigned((total + 255) / 256);
   if (b_operand)
-    KBS_LAUNCH(h, KBS_K_PACK, st, (sb_to_tn_kernel<true><<<gb, 256, 0, st>>>(src, step_bytes, kb_src, blk0, nblk, n, panels, T, dst,
+    KBS_LAUNCH(h, KBS_K_PACK_TN, st, (sb_to_tn_kernel<true><<<gb, 256, 0, st>>>(src, step_bytes, kb_src, blk0, nblk, n, panels, T, dst,
                                                                            plan.kb_total, plan.col_bytes)));
   else
-    KBS_LAUNCH(h, KBS_K_PACK, st, (sb_to_tn_kernel<false><<<gb, 256, 0, st>>>(src, step_bytes, kb_src, blk0, nblk, n, panels, T, dst,
+    KBS_LAUNCH(h, KBS_K_PACK_TN, st, (sb_to_tn_kernel<false><<<gb, 256, 0, st>>>(src, step_bytes, kb_src, blk0, nblk, n, panels, T, dst,
                                                                             plan.kb_total, plan.col_bytes)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
@@ -2934,7 +2934,7 @@ int kbs_tc_soa_to_tn(kbs_handle* h, const KbsTnPlan& plan, const float* soa, int
       KBS_CUDA_TRY(cudaMemsetAsync(dst + size_t(c) * plan.col_bytes + size_t(kb_used) * kABlockBytes, 0,
                                    size_t(plan.kb_total - kb_used) * kABlockBytes, st));
   const int64_t total = (T * np / 8) * ncols_pad;
-  KBS_LAUNCH(h, KBS_K_PACK, st, (soa_to_tn_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(
+  KBS_LAUNCH(h, KBS_K_PACK_TN, st, (soa_to_tn_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(
                                     soa, F, ld, n, np, T, ncols_pad, ones ? 1 : 0, dst, plan.kb_total, plan.col_bytes, h->persist_status)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
@@ -2987,7 +2987,7 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   cudaError_t le = cudaSuccess;
-  KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, bptt_persist_kernel<KBS_KIND_F16>, a)));
+  KBS_LAUNCH(h, KBS_K_BPTT_TC, st, (le = cudaLaunchKernelEx(&cfg, bptt_persist_kernel<KBS_KIND_F16>, a)));
   KBS_CUDA_TRY(le);
   { const int rc0 = kbs_status_publish(h, st); if (rc0) return rc0; }
   KBS_LAUNCH_CHECK();
@@ -2997,7 +2997,7 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
 int kbs_tc_tn_reduce(kbs_handle* h, const KbsTnPlan& plan, const float* partial, int m_panels, int ldc, int col0, int nrows,
                      int ncols, float* dst, int ld_dst, cudaStream_t st) {
   const int64_t total = int64_t(nrows) * ncols;
-  KBS_LAUNCH(h, KBS_K_GEMM_SIMT, st, (tn_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(
+  KBS_LAUNCH(h, KBS_K_PACK_TN, st, (tn_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(
                                          partial, plan.ksplit, size_t(m_panels) * kPanelRows * size_t(ldc), ldc, col0, nrows, ncols, dst, ld_dst)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;

@@ -917,6 +917,7 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, 0, N.num_out, H, g->w_out, H, st))) return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, H, N.num_out, 1, g->b_out, 1, st))) return rc;
     }
+    if (k == 1 && h->ev_critic_ready) KBS_CUDA_TRY(cudaEventRecord(h->ev_critic_ready, st));   // the critic's gradients are final
   }
   {
     kbs_ppo_loss_io io{};
@@ -1042,6 +1043,7 @@ int kbs_ppo_grad(kbs_handle* h, const kbs_ppo_loss_params* params, const kbs_ppo
   if ((rc = run_net(h, KBS_NET_ACTOR, *b, nullptr, w[0], gates_pre[0], dc_rec[0], part[0], splits, n, st, true, actor)))
     return rc;
   KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[0], 0));       // join: values + critic gradients are complete
+  if (h->ev_critic_ready) KBS_CUDA_TRY(cudaEventRecord(h->ev_critic_ready, st));
   // loss statistics (same kernel as kbs_ppo_loss; partials in the actor's reduction scratch, free again by now)
   {
     kbs_ppo_loss_io io{};
@@ -1075,6 +1077,12 @@ int kbs_adamw_step(kbs_handle* h, float* param, const float* grad, float* m, flo
   KBS_LAUNCH(h, KBS_K_ADV_NORM, st, (adamw_kernel<<<blocks(count), kT, 0, st>>>(param, grad, m, v, count, *o, grad_norm, sd, (long long)step)));
   if (sd) KBS_LAUNCH(h, KBS_K_ADV_NORM, st, (step_advance_kernel<<<1, 1, 0, st>>>(sd, grad_norm, o->grad_scale)));
   KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_ppo_grad_set_events(kbs_handle* h, void* critic_ready) {
+  if (!h) return KBS_E_NULL;
+  h->ev_critic_ready = (cudaEvent_t)critic_ready;
   return KBS_OK;
 }
 

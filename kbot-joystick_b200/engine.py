@@ -116,14 +116,16 @@ class KbotStep:
         return out
 
     # ---- weights -------------------------------------------------------------------------------------
-    def pack_weights(self, net: int, w: dict) -> None:
-        """w: eqx-layout CUDA tensors {w_in,b_in,w_out,b_out, layers:[{w_ih,w_hh,b}]} (train.py:847-1004)."""
+    def pack_weights(self, net: int, w: dict, sync: bool = True) -> None:
+        """w: eqx-layout CUDA tensors {w_in,b_in,w_out,b_out, layers:[{w_ih,w_hh,b}]} (train.py:847-1004).  sync=False: only
+        enqueue (stream-ordered; required inside CUDA-graph capture)."""
         s = L.KbsNetWeights()
         s.w_in, s.b_in, s.w_out, s.b_out = (L.ptr(w[k]) for k in ("w_in", "b_in", "w_out", "b_out"))
         for i, lw in enumerate(w["layers"]):
             s.w_ih[i], s.w_hh[i], s.b[i] = L.ptr(lw["w_ih"]), L.ptr(lw["w_hh"]), L.ptr(lw["b"])
         L.check(self.lib.kbs_weights_pack(self._h, net, C.byref(s), _stream()), "kbs_weights_pack")
-        torch.cuda.current_stream().synchronize()
+        if sync:
+            torch.cuda.current_stream().synchronize()
 
     # ---- stages --------------------------------------------------------------------------------------
     def observations(self, state: dict, command, noise: dict | None = None, episode: dict | None = None,
@@ -157,7 +159,8 @@ class KbotStep:
         L.check(self.lib.kbs_ppo_loss(self._h, C.byref(lp), C.byref(io), n_envs or ld, _stream()), "kbs_ppo_loss")
         return out
 
-    def ppo_grad(self, batch: dict, grads_actor: dict, grads_critic: dict, n_envs: int | None = None, **hyper) -> dict:
+    def ppo_grad(self, batch: dict, grads_actor: dict, grads_critic: dict, n_envs: int | None = None, critic_ready=None,
+                 **hyper) -> dict:
         """Gradients of the PPO minibatch loss (kbs_ppo_grad).  batch: actor_obs [T,65,ld], critic_obs [T,475,ld],
         action [T,20,ld], done u8 [T,ld], old_log_probs / advantages / value_targets / old_values [T,ld], optional
         actor_carry0 / critic_carry0 [depth,2,n,H], lpf0 [20,ld].  grads_*: eqx-layout dicts of CUDA tensors (written).
@@ -182,6 +185,10 @@ class KbotStep:
             return s
 
         ga, gc = gview(grads_actor), gview(grads_critic)
+        # critic_ready: a torch.cuda.Event the library records on the stream once the critic's gradients are final (its
+        # all-reduce can then overlap the actor's weight-gradient GEMMs)
+        L.check(self.lib.kbs_ppo_grad_set_events(self._h, critic_ready.cuda_event if critic_ready is not None else None),
+                "kbs_ppo_grad_set_events")
         out = {"stats": torch.empty((4,), device=dev), "log_probs": torch.empty((T, ld), device=dev),
                "values": torch.empty((T, ld), device=dev), "entropy": torch.empty((T, ld), device=dev)}
         L.check(self.lib.kbs_ppo_grad(self._h, C.byref(lp), C.byref(b), C.byref(ga), C.byref(gc), L.ptr(out["log_probs"]),

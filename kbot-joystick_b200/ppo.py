@@ -52,7 +52,12 @@ def allreduce_sum_(flat: torch.Tensor) -> int:
 
 
 class PpoUpdater:
-    """grad -> all-reduce -> global norm -> AdamW (clip folded in) -> re-pack, for the actor and the critic."""
+    """grad -> all-reduce -> global norm -> AdamW (clip folded in) -> re-pack, for the actor and the critic.
+
+    Overlap: kbs_ppo_grad finishes the critic's gradients first and records an event when they are final; the critic's
+    slice of the flat gradient is all-reduced on a communication stream while the actor's weight-gradient GEMMs still run,
+    the actor's slice follows.  With `capture()` the WHOLE update -- gradients, both all-reduces, norm, AdamW, re-pack --
+    is one CUDA graph (the step counter lives on the device)."""
 
     def __init__(self, engine, w_actor: dict, w_critic: dict, lr: float = 5e-4, b1: float = 0.9, b2: float = 0.999,
                  eps: float = 1e-8, weight_decay: float = 1e-5, max_grad_norm: float = 10.0, **loss_hyper):
@@ -60,47 +65,66 @@ class PpoUpdater:
         self.eng = engine
         self.pa, self.pc = NetParams(w_actor, dev), NetParams(w_critic, dev)
         n = self.pa.flat.numel() + self.pc.flat.numel()
-        self.grad = torch.zeros(n, device=dev)            # [actor | critic]: one all-reduce for both nets
+        self.grad = torch.zeros(n, device=dev)            # [actor | critic]
         self.m, self.v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
         self.param = torch.cat([self.pa.flat, self.pc.flat])
-        self.pa.flat, self.pc.flat = self.param[:self.pa.flat.numel()], self.param[self.pa.flat.numel():]
+        self.na = self.pa.flat.numel()
+        self.pa.flat, self.pc.flat = self.param[:self.na], self.param[self.na:]
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)   # updates applied so far (device-side: graph-replayable)
         self.norm = torch.zeros(1, device=dev)                            # global L2 norm of the (summed) gradient
         self.opt = dict(lr=lr, b1=b1, b2=b2, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
         self.loss_hyper = loss_hyper
-        self._repack()
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self.ev_critic, self.ev_comm = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_critic.record()            # torch creates the cudaEvent_t lazily: make the handle exist before the library sees it
+        self._graph = None
+        self._repack(sync=True)
 
-    def _repack(self):
-        self.eng.pack_weights(L.NET_ACTOR, self.pa.as_dict())
-        self.eng.pack_weights(L.NET_CRITIC, self.pc.as_dict())
+    def _repack(self, sync: bool = False):
+        self.eng.pack_weights(L.NET_ACTOR, self.pa.as_dict(), sync=sync)
+        self.eng.pack_weights(L.NET_CRITIC, self.pc.as_dict(), sync=sync)
 
-    def grads(self, batch: dict, n_envs: int) -> dict:
-        na = self.pa.flat.numel()
-        return self.eng.ppo_grad(batch, self.pa.as_dict(self.grad[:na]), self.pc.as_dict(self.grad[na:]), n_envs=n_envs,
-                                 **self.loss_hyper)
+    def grads(self, batch: dict, n_envs: int, critic_ready=None) -> dict:
+        return self.eng.ppo_grad(batch, self.pa.as_dict(self.grad[:self.na]), self.pc.as_dict(self.grad[self.na:]), n_envs=n_envs,
+                                 critic_ready=critic_ready, **self.loss_hyper)
 
-    def capture(self, batch: dict, n_envs: int) -> None:
-        """Record kbs_ppo_grad on `batch` (~3 000 kernel launches for T = 100) as ONE CUDA graph; later update() calls with the
-        same batch object replay it (refill the batch tensors in place between updates).  Call after one eager update."""
-        torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._graph_out = self.grads(batch, n_envs)
-        self._graph_batch = batch
-        self.eng.scratch_lock(True)        # the graph holds pointers into the library's scratch: it must not be reallocated
+    def _step(self, batch: dict, n_envs: int) -> dict:
+        """One whole update, enqueued on the current stream (+ the communication stream, forked from / joined into it)."""
+        import torch.distributed as dist
 
-    def update(self, batch: dict, n_envs: int) -> dict:
-        if getattr(self, "_graph", None) is not None and batch is self._graph_batch:
-            self._graph.replay()
-            out = self._graph_out
-        else:
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if world == 1:
             out = self.grads(batch, n_envs)
-        world = allreduce_sum_(self.grad)                   # the PPO gradient all-reduce (NVLink / NVSwitch via NCCL)
+        else:
+            cur = torch.cuda.current_stream()
+            out = self.grads(batch, n_envs, critic_ready=self.ev_critic)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(self.ev_critic)          # the critic's gradients are final: reduce them now
+                dist.all_reduce(self.grad[self.na:], op=dist.ReduceOp.SUM)
+                self.ev_comm.record(self.comm_stream)
+            dist.all_reduce(self.grad[:self.na], op=dist.ReduceOp.SUM)   # the actor's slice, behind its GEMMs
+            cur.wait_event(self.ev_comm)
         self.eng.grad_norm(self.grad, out=self.norm)        # of the SUM; kbs_adamw_step applies grad_scale = 1 / world to it
         self.eng.adamw_step(self.param, self.grad, self.m, self.v, grad_norm=self.norm, step_dev=self.step_dev,
                             grad_scale=1.0 / world, **self.opt)
         self._repack()
         return out
+
+    def capture(self, batch: dict, n_envs: int) -> None:
+        """Record one whole update on `batch` as ONE CUDA graph; later update() calls with the same batch object replay it
+        (refill the batch tensors in place between updates).  Call after at least one eager update (allocations, NCCL)."""
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_out = self._step(batch, n_envs)
+        self._graph_batch = batch
+        self.eng.scratch_lock(True)        # the graph holds pointers into the library's scratch: it must not be reallocated
+
+    def update(self, batch: dict, n_envs: int) -> dict:
+        if self._graph is not None and batch is self._graph_batch:
+            self._graph.replay()
+            return self._graph_out
+        return self._step(batch, n_envs)
 
     @property
     def step_count(self) -> int:

@@ -296,3 +296,22 @@ def test_ppo_loss_known_answers():
     np.testing.assert_allclose(val, 0.5 * 0.8 ** 2, rtol=1e-6)
     _, _, val, _, _ = O.ppo_loss(lp, lp, one, one, 0 * one, one, one, use_clipped_value_loss=False)
     assert val == 0.0
+
+
+def test_reference_goldens_when_present():
+    """tests/golden/ref_*.npz are outputs of the REAL reference packages (tools/verify_against_ref.py --dump, run wherever
+    jax / ksim / xax / equinox / distrax import).  None can be produced in this image, so until someone commits them this
+    test skips and parity stays UNPINNED; once present, every one of them must match the oracle's restatement."""
+    import importlib.util
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("verify_against_ref", root / "tools" / "verify_against_ref.py")
+    V = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(V)
+    rep = V.check(root / "tests" / "golden")
+    pinned = {k: v for k, v in rep.items() if v["status"] != "unverified"}
+    if not pinned:
+        pytest.skip("no reference goldens committed: parity unpinned (oracle-defined, reference-unverified)")
+    bad = {k: v for k, v in pinned.items() if v["status"] != "verified"}
+    assert not bad, bad

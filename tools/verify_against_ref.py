@@ -414,8 +414,8 @@ def check_item(name: str, z) -> tuple[bool, str]:
         loc, sc, a = z["in_loc"], z["in_scale"], z["in_a"]
         worst["log_prob"] = _err(O.mvn_log_prob(loc, sc, a), z["out_log_prob"], 1e-5, 1e-4)
         worst["entropy"] = _err(O.mvn_entropy(sc), z["out_entropy"], 1e-5, 1e-5)
-        worst["mode"] = _err(loc, z["out_mode"], 0, 0) if np.array_equal(loc, z["out_mode"]) else float("inf")
-        worst["stddev"] = _err(sc, z["out_stddev"], 1e-6, 0)
+        worst["mode"] = 0.0 if np.array_equal(loc, z["out_mode"]) else float("inf")
+        worst["stddev"] = _err(sc, z["out_stddev"], 1e-6, 1e-12)
         worst["sample"] = _err(loc + sc * z["out_sample_eps"], z["out_sample"], 1e-5, 1e-6)
     elif name == "softplus":
         worst["softplus"] = _err(O.softplus(z["in_x"]), z["out_softplus"], 1e-5, 1e-7)
