@@ -38,7 +38,8 @@ struct KbsNet {
   // tcgen05 path: one contiguous image of UMMA-ready operand tiles (see kbs_net_tc.cu)
   float* tc_image = nullptr;
   size_t tc_image_floats = 0;
-  float* tc_bwd_image = nullptr;   // PPO update: [W_ih | W_hh] transposed per layer as MMA operand (kbs_tc_pack_bwd)
+  float* tc_bwd_image = nullptr;   // PPO update: [W_ih | W_hh] transposed per layer as MMA operand (kbs_tc_pack_bwd), 128-column tiles
+  float* tc_bwd_image64 = nullptr; // ... and in the 64-column tiles of bptt_persist_kernel
 };
 
 // kernel ids of the per-kernel CUDA-event profiler (kbs_profile_*): one id per __global__ of the library
@@ -223,7 +224,7 @@ int kbs_tc_debug_trace(kbs_handle* h, long long* trace_out, float* ws, int64_t n
 // tensor-core GEMMs of the PPO update
 int kbs_tc_gates_fwd(kbs_handle* h, int net, int layer, const void* x_sb, const void* h_sb, float* gates_out, int64_t n,
                      cudaStream_t st);
-int kbs_tc_pack_bwd(kbs_handle* h, int net, cudaStream_t st);
+int kbs_tc_pack_bwd(kbs_handle* h, int net, cudaStream_t st, int tile = 128);
 int kbs_tc_bwd_gemm(kbs_handle* h, int net, int layer, const void* dG_sb, float* out, int64_t n, float out_scale, cudaStream_t st);
 size_t kbs_tc_rows_sb_bytes(const kbs_handle* h, int64_t n, int K);
 // weight-gradient GEMMs C = A^T B over K = all stored rows (split-K tcgen05; operands = transposed split-blocked buffers)

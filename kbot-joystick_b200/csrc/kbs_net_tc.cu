@@ -1107,6 +1107,7 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
       }
       const uint8_t* done_t = args.done ? args.done + size_t(it.t) * ld : nullptr;
       const bool rst = live && done_t && done_t[R];
+      bool published = false;                   // SAVE: LSTM items signal before their (unread) activation stores
       const long long ew0 = tr ? clock64() : 0;
       mbar_wait(&acc_full[0], j & 1);
       const long long ew1 = tr ? clock64() : 0;
@@ -1136,7 +1137,6 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
           char* h_out = N.hsb + (SAVE ? size_t(it.layer) * size_t(args.T + 1) + size_t(it.t + 1)
                                       : size_t(it.layer * 2 + ((it.t + 1) & 1))) * args.sbb;
           float* h_carry = (!SAVE && it.t == int(args.T) - 1) ? cst + npH : nullptr;
-          float* sg = SAVE ? N.save_g + (size_t(it.t) * args.depth + it.layer) * 4 * npH : nullptr;
           // 8 hidden units = exactly one 16-byte SB chunk per plane (FP16 kind): every store below is a full 16 B per
           // lane, 512 contiguous bytes per warp (8-byte half-chunk stores cost the operand pipeline 2.5 K cycles per item)
 #pragma unroll
@@ -1154,15 +1154,13 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
                 hn[i] = ao[i] * tanhf_(cn[i]);
                 if (rst) cn[i] = 0.0f;
               }
-              const size_t o0 = fb_offset(R, u0 + hf * 8, H), o1 = fb_offset(R, u0 + hf * 8 + 4, H);
-              *reinterpret_cast<float4*>(sg + o0) = make_float4(ai[0], ai[1], ai[2], ai[3]);
-              *reinterpret_cast<float4*>(sg + o1) = make_float4(ai[4], ai[5], ai[6], ai[7]);
-              *reinterpret_cast<float4*>(sg + npH + o0) = make_float4(af[0], af[1], af[2], af[3]);
-              *reinterpret_cast<float4*>(sg + npH + o1) = make_float4(af[4], af[5], af[6], af[7]);
-              *reinterpret_cast<float4*>(sg + 2 * npH + o0) = make_float4(ag[0], ag[1], ag[2], ag[3]);
-              *reinterpret_cast<float4*>(sg + 2 * npH + o1) = make_float4(ag[4], ag[5], ag[6], ag[7]);
-              *reinterpret_cast<float4*>(sg + 3 * npH + o0) = make_float4(ao[0], ao[1], ao[2], ao[3]);
-              *reinterpret_cast<float4*>(sg + 3 * npH + o1) = make_float4(ao[4], ao[5], ao[6], ao[7]);
+              // the activated gates replace the pre-activations in v[]: they are stored AFTER the item is published (nothing
+              // in this launch reads them; the next step is waiting for h and c)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int u = hf * 8 + i;
+                v[u] = ai[i]; v[16 + u] = af[i]; v[32 + u] = ag[i]; v[48 + u] = ao[i];
+              }
             } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -1189,6 +1187,21 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
                 *reinterpret_cast<float4*>(h_carry + fb_offset(R, uu + 4, H)) = make_float4(z * hn[4], z * hn[5], z * hn[6], z * hn[7]);
               }
             }
+          }
+        }
+        if (SAVE) {
+          // publish now (h, x, c are stored), then keep the activated gates for the backward pass
+          __syncwarp();
+          if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(epi_done)) : "memory");
+          published = true;
+          if (live && !(args.dbg & 2)) {
+            float* sg = N.save_g + (size_t(it.t) * args.depth + it.layer) * 4 * npH;
+#pragma unroll
+            for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(sg + gate * npH + fb_offset(R, u0 + 4 * q, H)) =
+                    make_float4(v[16 * gate + 4 * q], v[16 * gate + 4 * q + 1], v[16 * gate + 4 * q + 2], v[16 * gate + 4 * q + 3]);
           }
         }
       } else {
@@ -1282,7 +1295,7 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
       const long long ew2 = tr ? clock64() : 0;
       __syncwarp();
       long long ewf = 0;
-      if (lane == 0) {
+      if (lane == 0 && !published) {
         asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(epi_done)) : "memory");
         if (tr) ewf = clock64();
       }
@@ -1319,8 +1332,15 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
 // H(l-1, s) one slot after that (it needs dx(l, s)); dG(l, T) is a zero operand, so step T-1 is a regular item.
 // The weight gradients are NOT accumulated here: dG / x / h are kept for every step and contracted over all T x n rows
 // by the split-K GEMMs (kbs_tc_gemm_tn).
-constexpr int kBStages = 6;
-constexpr int kBSmemBytes = kBStages * kStageBytes + 256 /*barriers*/ + 1024 /*align*/;
+// Tile = 128 envs x kBT = 64 output columns.  MEASURED (tools/ppo_trace.py, 512 trajectories): with one item per CTA and slot
+// the kernel is bound by what ONE SM can pull from L2 (~60 B/clk): an item streams its whole dG panel (128 x 4H, 512 KB) plus
+// its weight tile, 1 MB at 128 columns.  Narrow tiles put more SMs (128 instead of 64 per slot) on the same slot: 768 KB per
+// item, and half the epilogue per thread.  (MMA issue is not the limit here: 2 instructions per k-step either way.)
+constexpr int kBT = 64;
+constexpr int kBBBlockBytes = 2 * 4 * kBT * 16;          // [chunk][hi|lo][64 rows][16 B] = 8 KB
+constexpr int kBStageBytes = kABlockBytes + kBBBlockBytes;   // 24 KB
+constexpr int kBStages = 8;
+constexpr int kBSmemBytes = kBStages * kBStageBytes + 256 /*barriers*/ + 1024 /*align*/;
 constexpr int kBEpiWarps = 16;
 constexpr int kBThreads = 32 * (1 + 1 + kBEpiWarps + 2);
 struct BNet {
@@ -1343,10 +1363,11 @@ struct BArgs {
   float gscale, inv_gscale;
   unsigned int* status;
   int dbg;
+  long long* trace;                // per CTA [16]: see tools/ppo_trace.py
 };
 struct BItem { int kind, net, layer, panel, tile, s; bool valid; };
 __device__ __forceinline__ BItem b_decode(const BArgs& a, int g) {
-  const int th = a.H / kTileCols;                      // tiles per half of the [dx | dh] output
+  const int th = a.H / kBT;                      // tiles per half of the [dx | dh] output
   const int per_panel = a.depth * 2 * th, per_net = a.panels * per_panel, C = a.nets * per_net;
   const int sigma = g / C;
   int i = g - sigma * C;
@@ -1363,10 +1384,11 @@ __device__ __forceinline__ BItem b_decode(const BArgs& a, int g) {
   it.valid = base >= 0 && it.s >= 0 && it.s <= int(a.T) - 1;
   return it;
 }
-__device__ __forceinline__ void b_wait_deps(const BArgs& a, const BItem& it, bool& drain) {
-  if (drain) return;
+__device__ __forceinline__ long long b_wait_deps(const BArgs& a, const BItem& it, bool& drain) {
+  if (drain) return 0;
+  const long long c0 = clock64();
   const BNet& N = a.net[it.net];
-  const unsigned int per = unsigned((a.H / kTileCols) * kBEpiWarps);
+  const unsigned int per = unsigned((a.H / kBT) * kBEpiWarps);
   const unsigned int* fp[2]; unsigned int tg[2]; int nd = 0;
   const unsigned int T = unsigned(a.T), s = unsigned(it.s);
   const int l = it.layer;
@@ -1376,7 +1398,7 @@ __device__ __forceinline__ void b_wait_deps(const BArgs& a, const BItem& it, boo
   } else {
     fp[nd] = N.flags + (l * 2 + 0) * a.panels + it.panel; tg[nd++] = (T - s) * per;                                 // dG(l, s)
   }
-  if (nd == 0) return;
+  if (nd == 0) return 0;
   if (nd == 1) { fp[1] = fp[0]; tg[1] = 0u; }
   unsigned int polls = 0;
   unsigned long long t0 = 0;
@@ -1392,13 +1414,35 @@ __device__ __forceinline__ void b_wait_deps(const BArgs& a, const BItem& it, boo
     }
   }
   __threadfence();
+  return clock64() - c0;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// The forward pass's saves of an H tile (4 activated gates + the cell state the step read: 5 x 16 units per thread) come from
+// HBM (1 GB per update: far beyond L2).  They are known long before the item can start, so the epilogue warps request them
+// one item ahead: by the time the accumulators are ready the lines sit in L2 (~2 K cycles of DRAM latency per batch of
+// loads otherwise, four batches in a row on the critical path of every backward step).
+__device__ __forceinline__ void b_prefetch_saves(const BArgs& a, const BItem& it, int r, int grp, size_t npH) {
+  if (it.kind != 0) return;
+  const BNet& N = a.net[it.net];
+  const int64_t R = int64_t(it.panel) * kPanelRows + r;
+  if (R >= a.n) return;
+  const int u0 = it.tile * kBT + grp * (kBT / 4);
+  const float* sg = N.save_g + (size_t(it.s) * a.depth + it.layer) * 4 * npH;
+  const float* cin = N.c_hist + (size_t(it.layer) * size_t(a.T + 1) + size_t(it.s)) * npH;
+#pragma unroll
+  for (int q = 0; q < kBT / 16; ++q) {
+    const size_t o = fb_offset(R, u0 + 4 * q, a.H);
+    prefetch_l2(sg + o); prefetch_l2(sg + npH + o); prefetch_l2(sg + 2 * npH + o); prefetch_l2(sg + 3 * npH + o);
+    prefetch_l2(cin + o);
+  }
 }
 
 template <int KIND>
 __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid_constant__ BArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBStages * kBStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kBStages;
   uint64_t* acc_full = bars + 2 * kBStages;     // [2]
@@ -1408,12 +1452,16 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
   unsigned int* epi_done = reinterpret_cast<unsigned int*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = args.H, th = H / kTileCols;
+  const int H = args.H, th = H / kBT;
   const int per_slot = args.nets * args.panels * args.depth * 2 * th;
   const int n_g = (int(args.T) + 2 * (args.depth - 1) + 1) * per_slot;
   constexpr int kBlk = kbs_block_k(KIND);
   const int kb4 = 4 * H / kBlk;                  // K blocks of every item
   const size_t npH = size_t(args.panels) * kPanelRows * H;
+  long long* tr = args.trace ? args.trace + size_t(blockIdx.x) * 16 : nullptr;
+  const long long t_start = clock64();
+  unsigned long long gt_start = 0;
+  if (tr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kBStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -1454,12 +1502,14 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
       // ===== dependency poller =====
       int j = 0;
       bool drain = false;
+      long long waited = 0;
       for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
         const BItem it = b_decode(args, gi);
         if (!it.valid) continue;
-        if (!(args.dbg & 1)) b_wait_deps(args, it, drain);
+        if (!(args.dbg & 1)) waited += b_wait_deps(args, it, drain);
         *dep_seq = ++j;
       }
+      if (tr) { tr[1] = waited; tr[2] = j; }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -1473,25 +1523,25 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
         const BNet& N = args.net[it.net];
         const int slot = it.s + (it.kind == 0 ? 1 : 0);
         const char* xa = N.dG + (size_t(it.layer) * size_t(args.T + 1) + size_t(slot)) * args.sb4 + size_t(it.panel) * kb4 * kABlockBytes;
-        const char* wb = N.w_bwd[it.layer] + size_t(it.kind == 0 ? th + it.tile : it.tile) * kb4 * kBBlockBytes;
+        const char* wb = N.w_bwd[it.layer] + size_t(it.kind == 0 ? th + it.tile : it.tile) * kb4 * kBBBlockBytes;
         ++j;
         bool need_dep = true;
         for (int b = 0; b < kb4; ++b, ++g) {
           const int s = g % kBStages;
           if (lane == 0) {
             mbar_wait(&empty[s], ((g / kBStages) & 1) ^ 1);
-            mbar_expect_tx(&full[s], uint32_t(kABlockBytes + kBBlockBytes));
+            mbar_expect_tx(&full[s], uint32_t(kABlockBytes + kBBBlockBytes));
           }
           __syncwarp(0x3);
-          uint8_t* sa = smem + size_t(s) * kStageBytes;
+          uint8_t* sa = smem + size_t(s) * kBStageBytes;
           if (lane == 0 && need_dep) {
             while (*dep_seq < j) { }
             __threadfence_block();
             asm volatile("fence.proxy.async;" ::: "memory");
             need_dep = false;
           }
-          const char* src = lane == 0 ? xa + size_t(b) * kABlockBytes : wb + size_t(b) * kBBlockBytes;
-          bulk_g2s(sa + lane * kABlockBytes, src, uint32_t(kABlockBytes), &full[s]);
+          const char* src = lane == 0 ? xa + size_t(b) * kABlockBytes : wb + size_t(b) * kBBBlockBytes;
+          bulk_g2s(sa + lane * kABlockBytes, src, lane == 0 ? uint32_t(kABlockBytes) : uint32_t(kBBBlockBytes), &full[s]);
         }
       }
     }
@@ -1500,26 +1550,33 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
     // ===== MMA issuer: per k-step  dG_hi . [W_hi | W_lo]^T (N = 256: main | correction columns) + dG_lo . W_hi^T (N = 128) =====
     uint32_t g = 0;
     int j = 0;
+    long long w_full = 0, w_acc = 0;
     for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
       const BItem it = b_decode(args, gi);
       if (!it.valid) continue;
       const int buf = j & 1;
+      const long long e0 = tr ? clock64() : 0;
       mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
+      if (tr) w_acc += clock64() - e0;
       tc_fence_after();
-      const uint32_t d_main = tmem_base + buf * (2 * kTileCols), d_corr = d_main + kTileCols;
+      const uint32_t d_main = tmem_base + buf * (2 * kBT), d_corr = d_main + kBT;
       for (int b = 0; b < kb4; ++b, ++g) {
         const int s = g % kBStages;
+        const long long f0 = tr ? clock64() : 0;
         mbar_wait(&full[s], (g / kBStages) & 1);
+        if (tr) w_full += clock64() - f0;
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
+        const uint32_t sa = smem_u32(smem + size_t(s) * kBStageBytes);
         const uint32_t sb = sa + kABlockBytes;
         const uint64_t a_hi = umma_desc(sa, 2048, 128), a_lo = umma_desc(sa + 8192, 2048, 128);
-        const uint64_t b_all = umma_desc(sb, 4096, 128);
+        // B block [chunk][hi|lo][kBT rows][16 B]: chunk stride (LBO) 2 kBT 16 B, k-step (2 chunks) twice that
+        const uint64_t b_all = umma_desc(sb, 2 * kBT * 16, 128);
+        constexpr uint64_t kBStep = uint64_t(4 * kBT * 16) >> 4;
         if (elect_one()) {
-          umma<KIND, 2 * kTileCols>(d_main, a_hi, b_all, b != 0);
-          umma<KIND, kTileCols>(d_corr, a_lo, b_all, 1);
-          umma<KIND, 2 * kTileCols>(d_main, a_hi + (4096 >> 4), b_all + (8192 >> 4), 1);
-          umma<KIND, kTileCols>(d_corr, a_lo + (4096 >> 4), b_all + (8192 >> 4), 1);
+          umma<KIND, 2 * kBT>(d_main, a_hi, b_all, b != 0);
+          umma<KIND, kBT>(d_corr, a_lo, b_all, 1);
+          umma<KIND, 2 * kBT>(d_main, a_hi + (4096 >> 4), b_all + kBStep, 1);
+          umma<KIND, kBT>(d_corr, a_lo + (4096 >> 4), b_all + kBStep, 1);
           umma_commit(&empty[s]);
         }
         __syncwarp();
@@ -1528,8 +1585,12 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
       __syncwarp();
       ++j;
     }
+    if (tr && lane == 0) { tr[3] = w_full; tr[4] = w_acc; }
   } else {
-    // ===== epilogue: 16 warps; warp % 4 = TMEM lane quarter (rows), grp = which 32 of the tile's 128 columns (hidden units) =====
+    // ===== epilogue: 16 warps; warp % 4 = TMEM lane quarter (rows), grp = which 16 of the tile's 64 columns (hidden units).
+    // The accumulators are pulled 8 columns at a time, right where they are used (TMEM is double-buffered and a CTA rarely
+    // has a second item in the same slot, so holding the buffer through the epilogue costs nothing and keeps the register
+    // footprint of a batch -- 7 x 8 operands -- below the spill line). =====
     const int ew = warp - 2;
     const int q4 = warp & 3, grp = ew >> 2;
     const int r = q4 * 32 + lane;
@@ -1537,111 +1598,126 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
     const int64_t ld = args.ld;
     int j = 0;
     bool bad = false;
+    {   // the first item's saves
+      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+        const BItem it0 = b_decode(args, gi);
+        if (it0.valid) { b_prefetch_saves(args, it0, r, grp, npH); break; }
+      }
+    }
     for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
       const BItem it = b_decode(args, gi);
       if (!it.valid) continue;
+      {   // request the NEXT item's saves now: a whole item of lead time
+        for (int gn = gi + int(gridDim.x); gn < n_g; gn += gridDim.x) {
+          const BItem itn = b_decode(args, gn);
+          if (itn.valid) { b_prefetch_saves(args, itn, r, grp, npH); break; }
+        }
+      }
       const BNet& N = args.net[it.net];
       const int64_t R = int64_t(it.panel) * kPanelRows + r;
       const bool live = R < args.n;
       const int buf = j & 1;
-      const int u0 = it.tile * kTileCols + grp * 32;          // first of this thread's 32 units (columns of the half)
+      const int u0 = it.tile * kBT + grp * (kBT / 4);         // first of this thread's 16 units (columns of the half)
       while (*dep_seq < j + 1) { }
       __threadfence_block();
+      const size_t s = size_t(it.s);
+      const float keep = (live && it.kind == 0 && args.done[s * ld + R]) ? 0.0f : 1.0f;
+      const float* sg = N.save_g + (s * args.depth + it.layer) * 4 * npH;
+      const float* cin = N.c_hist + (size_t(it.layer) * size_t(args.T + 1) + s) * npH;
+      float* dcp = N.dc + size_t(it.layer) * npH;
+      const bool top = it.layer + 1 == args.depth;
+      const float* dxu = top ? N.dh_top + (s * size_t(args.n) + size_t(live ? R : 0)) * H
+                             : N.dx + (size_t(it.layer + 1) * size_t(args.T) + s) * npH;
+      char* dGo = N.dG + (size_t(it.layer) * size_t(args.T + 1) + s) * args.sb4;
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * kTileCols) + grp * 32);
-      float v[32];
-      {
-        float cr[32];
-        tmem_ld32(tq, v);
-        tmem_ld32(tq + kTileCols, cr);
-        tmem_ld_wait();
+      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * kBT) + grp * (kBT / 4));
+#pragma unroll 1
+      for (int c8 = 0; c8 < kBT / 32; ++c8) {
+        const int u = u0 + 8 * c8;
+        float v[8];
+        {
+          float cr[8];
+          tmem_ld8(tq + 8 * c8, v);
+          tmem_ld8(tq + kBT + 8 * c8, cr);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += kCorr * cr[i];
+          for (int i = 0; i < 8; ++i) v[i] += kCorr * cr[i];
+        }
+        if (!live) continue;
+        if (it.kind == 1) {
+          // ---- X tile: dx(l, s) ----
+          if (it.layer == 0) {
+            char* dst = N.dx0 + s * args.sbb;                  // stays scaled: it is the A^T operand of the dW_in GEMM
+            const float x0[4] = {v[0], v[1], v[2], v[3]}, x1[4] = {v[4], v[5], v[6], v[7]};
+            bad = bad || sb_out_of_range<KIND, 4>(x0) || sb_out_of_range<KIND, 4>(x1);
+            sb_store_split8<kPanelRows, KIND>(dst, R, u, H / kBlk, sb_split4<KIND>(x0), sb_split4<KIND>(x1), false);
+          } else {
+            float* dst = N.dx + (size_t(it.layer) * size_t(args.T) + s) * npH;
+            const float g = args.inv_gscale;
+            *reinterpret_cast<float4*>(dst + fb_offset(R, u, H)) = make_float4(g * v[0], g * v[1], g * v[2], g * v[3]);
+            *reinterpret_cast<float4*>(dst + fb_offset(R, u + 4, H)) = make_float4(g * v[4], g * v[5], g * v[6], g * v[7]);
+          }
+          continue;
+        }
+        // ---- H tile: the cell's backward at step s for units u .. u + 7 ----
+        float gi[8], gf[8], gg[8], go[8], ci[8], dhi[8], dcr[8];
+        auto ld8fb = [&](const float* base, float (&o)[8], bool coherent) {
+          const float4* p0 = reinterpret_cast<const float4*>(base + fb_offset(R, u, H));
+          const float4* p1 = reinterpret_cast<const float4*>(base + fb_offset(R, u + 4, H));
+          const float4 a = coherent ? __ldcg(p0) : __ldg(p0), b = coherent ? __ldcg(p1) : __ldg(p1);
+          o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+        };
+        ld8fb(sg, gi, false); ld8fb(sg + npH, gf, false); ld8fb(sg + 2 * npH, gg, false); ld8fb(sg + 3 * npH, go, false);
+        ld8fb(cin, ci, false);
+        ld8fb(dcp, dcr, true);
+        if (top) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(dxu + u)), b = __ldg(reinterpret_cast<const float4*>(dxu + u + 4));
+          dhi[0] = a.x; dhi[1] = a.y; dhi[2] = a.z; dhi[3] = a.w; dhi[4] = b.x; dhi[5] = b.y; dhi[6] = b.z; dhi[7] = b.w;
+        } else {
+          ld8fb(dxu, dhi, true);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float c = gf[i] * ci[i] + gi[i] * gg[i];                 // c_s, as the forward pass formed it
+          const float tc = tanhf_(c);
+          const float dh = dhi[i] + keep * (args.inv_gscale * v[i]);
+          const float dc = keep * dcr[i] + dh * go[i] * (1.0f - tc * tc);
+          dcr[i] = dc * gf[i];
+          const float di = args.gscale * (dc * gg[i] * gi[i] * (1.0f - gi[i]));
+          const float df = args.gscale * (dc * ci[i] * gf[i] * (1.0f - gf[i]));
+          const float dg = args.gscale * (dc * gi[i] * (1.0f - gg[i] * gg[i]));
+          const float dob = args.gscale * (dh * tc * go[i] * (1.0f - go[i]));
+          gi[i] = di; gf[i] = df; gg[i] = dg; go[i] = dob;              // the gate gradients replace the gates
+        }
+        *reinterpret_cast<float4*>(dcp + fb_offset(R, u, H)) = make_float4(dcr[0], dcr[1], dcr[2], dcr[3]);
+        *reinterpret_cast<float4*>(dcp + fb_offset(R, u + 4, H)) = make_float4(dcr[4], dcr[5], dcr[6], dcr[7]);
+        auto st8 = [&](int gate, const float (&x)[8]) {
+          const float x0[4] = {x[0], x[1], x[2], x[3]}, x1[4] = {x[4], x[5], x[6], x[7]};
+          bad = bad || sb_out_of_range<KIND, 4>(x0) || sb_out_of_range<KIND, 4>(x1);
+          sb_store_split8<kPanelRows, KIND>(dGo, R, gate * H + u, 4 * H / kBlk, sb_split4<KIND>(x0), sb_split4<KIND>(x1), false);
+        };
+        st8(0, gi); st8(1, gf); st8(2, gg); st8(3, go);
       }
+      // the accumulator buffer goes back to the MMA issuer, then the item is published
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      if (live && it.kind == 1) {
-        // ---- X tile: dx(l, s) ----
-        if (it.layer == 0) {
-          char* dst = N.dx0 + size_t(it.s) * args.sbb;       // stays scaled: it is the A^T operand of the dW_in GEMM
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            const float x0[4] = {v[8 * c8], v[8 * c8 + 1], v[8 * c8 + 2], v[8 * c8 + 3]};
-            const float x1[4] = {v[8 * c8 + 4], v[8 * c8 + 5], v[8 * c8 + 6], v[8 * c8 + 7]};
-            bad = bad || sb_out_of_range<KIND, 4>(x0) || sb_out_of_range<KIND, 4>(x1);
-            sb_store_split8<kPanelRows, KIND>(dst, R, u0 + 8 * c8, H / kBlk, sb_split4<KIND>(x0), sb_split4<KIND>(x1), false);
-          }
-        } else {
-          float* dst = N.dx + (size_t(it.layer) * size_t(args.T) + size_t(it.s)) * npH;
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            *reinterpret_cast<float4*>(dst + fb_offset(R, u0 + 4 * c4, H)) =
-                make_float4(args.inv_gscale * v[4 * c4], args.inv_gscale * v[4 * c4 + 1], args.inv_gscale * v[4 * c4 + 2],
-                            args.inv_gscale * v[4 * c4 + 3]);
-        }
-      } else if (live) {
-        // ---- H tile: the cell's backward at step s for units u0 .. u0 + 31 ----
-        const size_t s = size_t(it.s);
-        const float keep = args.done[s * ld + R] ? 0.0f : 1.0f;
-        const float* sg = N.save_g + (s * args.depth + it.layer) * 4 * npH;
-        const float* cin = N.c_hist + (size_t(it.layer) * size_t(args.T + 1) + s) * npH;
-        float* dcp = N.dc + size_t(it.layer) * npH;
-        const bool top = it.layer + 1 == args.depth;
-        const float* dxu = top ? N.dh_top + (s * size_t(args.n) + size_t(R)) * H
-                               : N.dx + (size_t(it.layer + 1) * size_t(args.T) + s) * npH;
-        char* dGo = N.dG + (size_t(it.layer) * size_t(args.T + 1) + s) * args.sb4;
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {                     // unrolled: v[] must stay in registers
-          const int u = u0 + 8 * c8;
-          float gi[8], gf[8], gg[8], go[8], ci[8], dhi[8], dcr[8];
-          auto ld8fb = [&](const float* base, float (&o)[8], bool coherent) {
-            const float4* p0 = reinterpret_cast<const float4*>(base + fb_offset(R, u, H));
-            const float4* p1 = reinterpret_cast<const float4*>(base + fb_offset(R, u + 4, H));
-            const float4 a = coherent ? __ldcg(p0) : __ldg(p0), b = coherent ? __ldcg(p1) : __ldg(p1);
-            o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
-          };
-          ld8fb(sg, gi, false); ld8fb(sg + npH, gf, false); ld8fb(sg + 2 * npH, gg, false); ld8fb(sg + 3 * npH, go, false);
-          ld8fb(cin, ci, false);
-          ld8fb(dcp, dcr, true);
-          if (top) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(dxu + u)), b = __ldg(reinterpret_cast<const float4*>(dxu + u + 4));
-            dhi[0] = a.x; dhi[1] = a.y; dhi[2] = a.z; dhi[3] = a.w; dhi[4] = b.x; dhi[5] = b.y; dhi[6] = b.z; dhi[7] = b.w;
-          } else {
-            ld8fb(dxu, dhi, true);
-          }
-          float di[8], df[8], dg[8], dob[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float c = gf[i] * ci[i] + gi[i] * gg[i];                 // c_s, as the forward pass formed it
-            const float tc = tanhf_(c);
-            const float dh = dhi[i] + keep * (args.inv_gscale * v[8 * c8 + i]);
-            const float dc = keep * dcr[i] + dh * go[i] * (1.0f - tc * tc);
-            di[i] = args.gscale * (dc * gg[i] * gi[i] * (1.0f - gi[i]));
-            df[i] = args.gscale * (dc * ci[i] * gf[i] * (1.0f - gf[i]));
-            dg[i] = args.gscale * (dc * gi[i] * (1.0f - gg[i] * gg[i]));
-            dob[i] = args.gscale * (dh * tc * go[i] * (1.0f - go[i]));
-            dcr[i] = dc * gf[i];
-          }
-          *reinterpret_cast<float4*>(dcp + fb_offset(R, u, H)) = make_float4(dcr[0], dcr[1], dcr[2], dcr[3]);
-          *reinterpret_cast<float4*>(dcp + fb_offset(R, u + 4, H)) = make_float4(dcr[4], dcr[5], dcr[6], dcr[7]);
-          auto st8 = [&](int gate, const float (&x)[8]) {
-            const float x0[4] = {x[0], x[1], x[2], x[3]}, x1[4] = {x[4], x[5], x[6], x[7]};
-            bad = bad || sb_out_of_range<KIND, 4>(x0) || sb_out_of_range<KIND, 4>(x1);
-            sb_store_split8<kPanelRows, KIND>(dGo, R, gate * H + u, 4 * H / kBlk, sb_split4<KIND>(x0), sb_split4<KIND>(x1), false);
-          };
-          st8(0, di); st8(1, df); st8(2, dg); st8(3, dob);
-        }
+      if (lane == 0) {
+        mbar_arrive(&acc_empty[buf]);
+        asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(epi_done)) : "memory");
       }
-      __syncwarp();
-      if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(epi_done)) : "memory");
       ++j;
     }
     sb_flag_range(args.status, bad);
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) {
+    unsigned long long gt_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
+    tr[0] = clock64() - t_start;
+    tr[15] = (long long)(gt_end - gt_start);
+  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
@@ -2762,7 +2838,7 @@ int kbs_tc_gates_fwd(kbs_handle* h, int net, int layer, const void* x_sb, const 
 }
 
 // backward weights of one layer: Wb [2H][4H], Wb[c][k] = W_ih[k][c] (c < H) | W_hh[k][c - H]: [dx | dh] = dG . Wb^T
-template <int KIND>
+template <int KIND, int TILE>
 __global__ void __launch_bounds__(256)
 pack_bwd_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, char* __restrict__ w_sb,
                         float* __restrict__ bias_t, int H) {
@@ -2773,7 +2849,7 @@ pack_bwd_weights_kernel(const float* __restrict__ w_ih, const float* __restrict_
   const float* w = col < H ? w_ih : w_hh;
   const int c = col < H ? col : col - H;
   const float x[4] = {w[size_t(k) * H + c], w[size_t(k + 1) * H + c], w[size_t(k + 2) * H + c], w[size_t(k + 3) * H + c]};
-  sb_store4<kTileCols, KIND, true>(w_sb, col, k, 4 * H / kbs_block_k(KIND), x);
+  sb_store4<TILE, KIND, true>(w_sb, col, k, 4 * H / kbs_block_k(KIND), x);
   if (k == 0) bias_t[col] = 0.0f;
 }
 
@@ -2783,22 +2859,25 @@ static size_t bwd_layer_bytes(const kbs_handle* h) {
 }
 
 // (re)builds the backward operand image of `net` from its current fp32 weights (call after every weight update)
-int kbs_tc_pack_bwd(kbs_handle* h, int net, cudaStream_t st) {
+int kbs_tc_pack_bwd(kbs_handle* h, int net, cudaStream_t st, int tile) {
   KbsNet& N = h->net[net];
   if (!N.packed) return KBS_E_STATE;
   const int H = h->p.hidden_size, kind = tc_kind(h);
-  if ((2 * H) % kTileCols || (4 * H) % kbs_block_k(kind)) return KBS_E_SHAPE;
+  if ((2 * H) % kTileCols || (4 * H) % kbs_block_k(kind) || (tile != kTileCols && (tile != kBT || kind != KBS_KIND_F16))) return KBS_E_SHAPE;
   const size_t bytes = bwd_layer_bytes(h) * h->p.depth;
-  if (!N.tc_bwd_image) KBS_CUDA_TRY(cudaMalloc(&N.tc_bwd_image, bytes));
+  float*& image = tile == kBT ? N.tc_bwd_image64 : N.tc_bwd_image;     // same bytes per layer for either tile width
+  if (!image) KBS_CUDA_TRY(cudaMalloc(&image, bytes));
   for (int l = 0; l < h->p.depth; ++l) {
-    char* w = reinterpret_cast<char*>(N.tc_bwd_image) + bwd_layer_bytes(h) * l;
+    char* w = reinterpret_cast<char*>(image) + bwd_layer_bytes(h) * l;
     float* bias = reinterpret_cast<float*>(w + kbs_sb_bytes_kind(kind, 2 * H, 4 * H));
     const int64_t total = int64_t(2 * H) * (4 * H / 4);
     const unsigned gb = unsigned((total + 255) / 256);
-    if (kind == KBS_KIND_TF32)
-      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_bwd_weights_kernel<KBS_KIND_TF32><<<gb, 256, 0, st>>>(N.w_ih[l], N.w_hh[l], w, bias, H)));
+    if (tile == kBT)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_bwd_weights_kernel<KBS_KIND_F16, kBT><<<gb, 256, 0, st>>>(N.w_ih[l], N.w_hh[l], w, bias, H)));
+    else if (kind == KBS_KIND_TF32)
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_bwd_weights_kernel<KBS_KIND_TF32, kTileCols><<<gb, 256, 0, st>>>(N.w_ih[l], N.w_hh[l], w, bias, H)));
     else
-      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_bwd_weights_kernel<KBS_KIND_F16><<<gb, 256, 0, st>>>(N.w_ih[l], N.w_hh[l], w, bias, H)));
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_bwd_weights_kernel<KBS_KIND_F16, kTileCols><<<gb, 256, 0, st>>>(N.w_ih[l], N.w_hh[l], w, bias, H)));
   }
   KBS_LAUNCH_CHECK();
   return KBS_OK;
@@ -2946,10 +3025,10 @@ size_t kbs_tc_bptt_flag_bytes(const kbs_handle* h, int64_t n) {
 }
 bool kbs_tc_bptt_available(const kbs_handle* h, int64_t n, int64_t T) {
   const int H = h->p.hidden_size, depth = h->p.depth;
-  if (tc_kind(h) != KBS_KIND_F16 || !persist_shape_ok(h) || H % kTileCols) return false;
+  if (tc_kind(h) != KBS_KIND_F16 || !persist_shape_ok(h) || H % kTileCols || H % kBT) return false;
   if (!kbs_tc_persistent_available(h, n, T, 2)) return false;
   const int64_t panels = pad_rows(n) / kPanelRows;
-  return (T + 2 * depth) * 2 * panels * depth * 2 * (H / kTileCols) < (int64_t(1) << 31);
+  return (T + 2 * depth) * 2 * panels * depth * 2 * (H / kBT) < (int64_t(1) << 31);
 }
 int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
   const int H = h->p.hidden_size, depth = h->p.depth;
@@ -2963,9 +3042,9 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
   BArgs a{};
   for (int k = 0; k < b.nets; ++k) {
     const KbsNet& Nn = h->net[k];
-    if (!Nn.packed || !Nn.tc_bwd_image) return KBS_E_STATE;
+    if (!Nn.packed || !Nn.tc_bwd_image64) return KBS_E_STATE;
     BNet& N = a.net[k];
-    for (int l = 0; l < depth; ++l) N.w_bwd[l] = reinterpret_cast<const char*>(Nn.tc_bwd_image) + bwd_layer_bytes(h) * l;
+    for (int l = 0; l < depth; ++l) N.w_bwd[l] = reinterpret_cast<const char*>(Nn.tc_bwd_image64) + bwd_layer_bytes(h) * l;
     N.dG = b.net[k].dG; N.save_g = b.net[k].save_g; N.c_hist = b.net[k].c_hist; N.dh_top = b.net[k].dh_top;
     N.dx = b.net[k].dx; N.dx0 = b.net[k].dx0; N.dc = b.net[k].dc; N.flags = b.net[k].flags;
   }
@@ -2975,7 +3054,8 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
   a.done = b.done; a.gscale = b.gscale; a.inv_gscale = 1.0f / b.gscale;
   a.status = h->persist_status;
   { const char* e = getenv("KBS_PERSIST_DBG"); a.dbg = e ? atoi(e) : 0; }
-  const int64_t per_slot = int64_t(b.nets) * a.panels * depth * 2 * (H / kTileCols);
+  a.trace = h->trace_buf ? h->trace_buf + 2 * 148 * 16 : nullptr;  // third region of the debug buffer (forward kernel, input projection, this)
+  const int64_t per_slot = int64_t(b.nets) * a.panels * depth * 2 * (H / kBT);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(per_slot < h->num_sms ? per_slot : h->num_sms));
   cfg.blockDim = dim3(kBThreads);

@@ -772,6 +772,10 @@ struct PersistWork {
   char* x_sb; char* xmid; char* hsb; float* c_hist; float* save_g; char* dG; float* dx; char* dx0; float* dc;
   float* dh_top; float* dout; float* w_outT; unsigned int* bflags;
   char* tn_a; char* tn_b; float* tn_partial; float* tn_zero; char* tn_ones;
+  // B operands (forward-pass products) are transposed on the side stream while the backward kernel runs: one buffer each
+  char* tnb_layer[KBS_MAX_DEPTH];   // [x_l | h_in_l]: 2 H / 128 tiles
+  char* tnb_top;                    // top layer's outputs: H / 128 tiles
+  char* tnb_obs;                    // observations + ones column: kpp / 128 tiles
 };
 
 size_t persist_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n) {
@@ -786,7 +790,8 @@ size_t persist_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n) {
              depth * size_t(T) * npH /*dx*/ + size_t(T) * sbf /*dx0*/ + depth * npH /*dc*/ + rows * H /*dh_top*/ + rows * 64 /*dout*/ +
              64 * H + kbs_tc_bptt_flag_bytes(h, n) / 4;
   f += (m_panels + b_tiles) * plan.col_bytes / 4 + size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128) + 1024 + 4096;
-  return f + 64 * 32;       // carve() rounds every piece up to 64 floats
+  f += (depth * (2 * H / 128) + H / 128 + kpp / 128) * plan.col_bytes / 4;
+  return f + 64 * 40;       // carve() rounds every piece up to 64 floats
 }
 
 int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_ppo_batch& b, const kbs_net_grads* const* grads,
@@ -833,6 +838,9 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     w[k].tn_partial = carve(p, size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128));
     w[k].tn_zero = carve(p, 1024);
     w[k].tn_ones = reinterpret_cast<char*>(carve(p, 4096));
+    for (int l = 0; l < depth; ++l) w[k].tnb_layer[l] = reinterpret_cast<char*>(carve(p, size_t(2 * H / 128) * plan.col_bytes / 4));
+    w[k].tnb_top = reinterpret_cast<char*>(carve(p, size_t(H / 128) * plan.col_bytes / 4));
+    w[k].tnb_obs = reinterpret_cast<char*>(carve(p, kpp / 128 * plan.col_bytes / 4));
   }
   // ---- forward ----
   KbsTcRolloutArgs r{};
@@ -854,6 +862,34 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
   r.save = 1; r.sraw = sraw_s;
   for (int k = 0; k < 2; ++k) { r.xmid_hist[k] = w[k].xmid; r.hsb_hist[k] = w[k].hsb; r.c_hist[k] = w[k].c_hist; r.save_g[k] = w[k].save_g; }
   if ((rc = kbs_tc_rollout_recurrent(h, r, st))) return rc;
+  // ---- B operands of the weight-gradient GEMMs: everything the forward pass produced, re-packed with K = row on the
+  // handle's side stream WHILE the backward kernel runs (it occupies one SM per work item of a slot: 64 of 148 at 512
+  // trajectories); joined before the GEMMs ----
+  const int kbH = H / 32, kb4 = 4 * H / 32;
+  { const int rc0 = kbs_side_stream_init(h); if (rc0) return rc0; }
+  // KBS_PPO_SIDE_PACK=0: keep them on the caller's stream (A/B: the concurrent re-packing competes with the latency-bound
+  // backward kernel for L2 / HBM)
+  static int side_pack = -1;
+  if (side_pack < 0) { const char* e = getenv("KBS_PPO_SIDE_PACK"); side_pack = e ? atoi(e) : 1; }
+  cudaStream_t ss = side_pack ? h->side_stream : st;
+  if (side_pack) {
+    KBS_CUDA_TRY(cudaEventRecord(h->ev_pre, st));
+    KBS_CUDA_TRY(cudaStreamWaitEvent(ss, h->ev_pre, 0));
+  }
+  for (int k = 1; k >= 0; --k) {
+    const KbsNet& N = h->net[k];
+    const int kpp = round_up_i(N.num_in + 1, 128);
+    for (int l = 0; l < depth; ++l) {
+      const char* x_hist = l == 0 ? w[k].x_sb : w[k].xmid + size_t(l - 1) * T * sbb;
+      if ((rc = kbs_tc_sb_to_tn(h, plan, true, x_hist, sbb, kbH, 0, kbH, n, T, w[k].tnb_layer[l], ss))) return rc;
+      if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].hsb + size_t(l) * (T + 1) * sbb, sbb, kbH, 0, kbH, n, T,
+                                w[k].tnb_layer[l] + size_t(H / 128) * plan.col_bytes, ss)))
+        return rc;
+    }
+    if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].xmid + size_t(depth - 1) * T * sbb, sbb, kbH, 0, kbH, n, T, w[k].tnb_top, ss))) return rc;
+    if ((rc = kbs_tc_soa_to_tn(h, plan, k == 0 ? b.actor_obs : b.critic_obs, N.num_in, ld, n, T, kpp, true, w[k].tnb_obs, ss))) return rc;
+  }
+  if (side_pack) KBS_CUDA_TRY(cudaEventRecord(h->ev_head[0], ss));
   // ---- heads: d loss / d out ----
   KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
              (actor_head_bwd_warp_kernel<<<unsigned((n + 3) / 4), 128, 0, st>>>(h->p, L, b.action, b.done, b.old_log_probs, b.advantages,
@@ -867,7 +903,7 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     const KbsNet& N = h->net[k];
     KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(64) * H), kT, 0, st>>>(N.w_out, 64, H, w[k].w_outT)));
     if ((rc = kbs_simt_gemm_nt(h, w[k].dout, 64, w[k].w_outT, 64, nullptr, w[k].dh_top, H, rows, H, 64, 0, st))) return rc;
-    if ((rc = kbs_tc_pack_bwd(h, k, st))) return rc;
+    if ((rc = kbs_tc_pack_bwd(h, k, st, 64))) return rc;
     KBS_CUDA_TRY(cudaMemsetAsync(w[k].dc, 0, size_t(depth) * npH * 4, st));
     KBS_CUDA_TRY(cudaMemsetAsync(w[k].bflags, 0, kbs_tc_bptt_flag_bytes(h, n), st));
     for (int l = 0; l < depth; ++l)          // dG(l, T) = 0: the operand of the first backward step's recurrent GEMM
@@ -878,9 +914,9 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
   }
   ba.nets = 2; ba.n = n; ba.ld = ld; ba.T = T; ba.done = b.done; ba.gscale = gscale;
   if ((rc = kbs_tc_bptt(h, ba, st))) return rc;
+  if (side_pack) KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[0], 0));       // join: the B operands are ready
   // ---- weight gradients ----
   const float inv = 1.0f / gscale;
-  const int kbH = H / 32, kb4 = 4 * H / 32;
   for (int k = 1; k >= 0; --k) {             // critic first: its gradients are final first (see ppo.py: the all-reduce of a
     const KbsNet& N = h->net[k];             // network can start while the other network's GEMMs run)
     const kbs_net_grads* g = grads[k];
@@ -888,13 +924,9 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     if ((rc = kbs_tc_ones_block(h, w[k].tn_ones, st))) return rc;
     for (int l = 0; l < depth; ++l) {
       const int mp = 4 * H / 128, ldc = (2 * H / 128 + 1) * 128;
-      const char* x_hist = l == 0 ? w[k].x_sb : w[k].xmid + size_t(l - 1) * T * sbb;
       if ((rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dG + size_t(l) * (T + 1) * sb4, sb4, kb4, 0, kb4, n, T, w[k].tn_a, st))) return rc;
-      if ((rc = kbs_tc_sb_to_tn(h, plan, true, x_hist, sbb, kbH, 0, kbH, n, T, w[k].tn_b, st))) return rc;
-      if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].hsb + size_t(l) * (T + 1) * sbb, sbb, kbH, 0, kbH, n, T,
-                                w[k].tn_b + size_t(H / 128) * plan.col_bytes, st)))
-        return rc;
-      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, mp, 4 * H, w[k].tn_b, 2 * H / 128, w[k].tn_ones, w[k].tn_zero, w[k].tn_partial, inv, st)))
+      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, mp, 4 * H, w[k].tnb_layer[l], 2 * H / 128, w[k].tn_ones, w[k].tn_zero, w[k].tn_partial,
+                               inv, st)))
         return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 0, 4 * H, H, g->w_ih[l], H, st))) return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, H, 4 * H, H, g->w_hh[l], H, st))) return rc;
@@ -903,16 +935,14 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     {   // dW_in, db_in
       const int kpp = round_up_i(N.num_in + 1, 128), mp = H / 128;
       if ((rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dx0, sbb, kbH, 0, kbH, n, T, w[k].tn_a, st))) return rc;
-      if ((rc = kbs_tc_soa_to_tn(h, plan, k == 0 ? b.actor_obs : b.critic_obs, N.num_in, ld, n, T, kpp, true, w[k].tn_b, st))) return rc;
-      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, mp, H, w[k].tn_b, kpp / 128, nullptr, w[k].tn_zero, w[k].tn_partial, inv, st))) return rc;
+      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, mp, H, w[k].tnb_obs, kpp / 128, nullptr, w[k].tn_zero, w[k].tn_partial, inv, st))) return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, kpp, 0, H, N.num_in, g->w_in, N.num_in, st))) return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, kpp, N.num_in, H, 1, g->b_in, 1, st))) return rc;
     }
     {   // dW_out, db_out: A = d loss / d out (row-major, K' = t np + env), B = the top layer's outputs + ones tile
       const int ldc = (H / 128 + 1) * 128;
       if ((rc = kbs_tc_pack_tn(h, plan, false, w[k].dout, 64, 0, 64, 128, rows, w[k].tn_a, gscale, -1, st, n, np))) return rc;
-      if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].xmid + size_t(depth - 1) * T * sbb, sbb, kbH, 0, kbH, n, T, w[k].tn_b, st))) return rc;
-      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, 1, N.num_out, w[k].tn_b, H / 128, w[k].tn_ones, w[k].tn_zero, w[k].tn_partial, inv, st)))
+      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, 1, N.num_out, w[k].tnb_top, H / 128, w[k].tn_ones, w[k].tn_zero, w[k].tn_partial, inv, st)))
         return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, 0, N.num_out, H, g->w_out, H, st))) return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, H, N.num_out, 1, g->b_out, 1, st))) return rc;
