@@ -245,8 +245,13 @@ int kbs_tc_soa_to_tn(kbs_handle* h, const KbsTnPlan& plan, const float* soa, int
 // backward recurrence of the PPO update as one persistent kernel (bptt_persist_kernel)
 struct KbsBpttNet {
   char* dG; const float* save_g; const float* c_hist; const float* dh_top; float* dx; char* dx0; float* dc; unsigned int* flags;
+  char* tn_dG[KBS_MAX_DEPTH];      // optional: per layer, the K = row re-pack of dG (written by the kernel's transposer CTAs)
 };
-struct KbsBpttArgs { KbsBpttNet net[2]; int nets; int64_t n, ld, T; const uint8_t* done; float gscale; };
+struct KbsBpttArgs {
+  KbsBpttNet net[2]; int nets; int64_t n, ld, T; const uint8_t* done; float gscale;
+  const KbsTnPlan* tn_plan;        // with tn_dG: layout of the re-packed operands
+  bool* transposed_out;            // set to whether the kernel re-packed dG itself (enough idle SMs) or the caller has to
+};
 size_t kbs_tc_bptt_flag_bytes(const kbs_handle* h, int64_t n);
 bool kbs_tc_bptt_available(const kbs_handle* h, int64_t n, int64_t T);
 int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& a, cudaStream_t st);

@@ -1353,6 +1353,7 @@ struct BNet {
   char* dx0;                       // [T] x sbb: the same for layer 0, as split operand (scaled by gscale)
   float* dc;                       // [depth] x np*H (FB): gradient wrt the cell carry, running (zeroed by the host)
   unsigned int* flags;             // [depth][2 (H, X)][panels] completion counters (zeroed by the host)
+  char* tn_dG[kPMaxDepth];         // n_tctas > 0: per layer, dG re-packed with K = t np + row (A^T operand of the dW GEMMs)
 };
 struct BArgs {
   BNet net[2];
@@ -1364,6 +1365,13 @@ struct BArgs {
   unsigned int* status;
   int dbg;
   long long* trace;                // per CTA [16]: see tools/ppo_trace.py
+  // tn != 0: the X tiles re-pack dG on the fly into the K = row operand layout of the weight-gradient GEMMs (sb_to_tn_kernel's
+  // job: 0.85 ms of separate launches and 1.7 GB of HBM traffic after this kernel).  The dG panel an X tile multiplies
+  // passes through its shared memory anyway; while the MMAs of the item run, the (idle) epilogue warps transpose the stages
+  // -- the th X tiles of a panel take every th-th K block each -- and write them out.  MEASURED alternative: 12 / 20 extra
+  // "transposer" CTAs chasing the completion counters were too slow (10.6 / 7.9 ms per update instead of 6.3).
+  int tn, tn_kb_total;
+  size_t tn_col_bytes;
 };
 struct BItem { int kind, net, layer, panel, tile, s; bool valid; };
 __device__ __forceinline__ BItem b_decode(const BArgs& a, int g) {
@@ -1464,7 +1472,8 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
   if (tr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kBStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // empty[s]: the MMA commit, + (tn) the four epilogue warps that look at the stage for the on-the-fly re-pack
+    for (int s = 0; s < kBStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], args.tn ? 5 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kBEpiWarps); }
     *dep_seq = 0;
     *epi_done = 0u;
@@ -1478,12 +1487,13 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_cc = int(gridDim.x);
 
   if (warp == 2 + kBEpiWarps + 1) {
     if (lane == 0) {
       // ===== publisher (see rollout_persist_kernel) =====
       int j = 0;
-      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+      for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
         const BItem it = b_decode(args, gi);
         if (!it.valid) continue;
         ++j;
@@ -1503,7 +1513,7 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
       int j = 0;
       bool drain = false;
       long long waited = 0;
-      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+      for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
         const BItem it = b_decode(args, gi);
         if (!it.valid) continue;
         if (!(args.dbg & 1)) waited += b_wait_deps(args, it, drain);
@@ -1517,7 +1527,7 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
       // ===== producers: lane 0 = the dG block (activation side), lane 1 = the weight block of the stage =====
       uint32_t g = 0;
       int j = 0;
-      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+      for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
         const BItem it = b_decode(args, gi);
         if (!it.valid) continue;
         const BNet& N = args.net[it.net];
@@ -1551,7 +1561,7 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
     uint32_t g = 0;
     int j = 0;
     long long w_full = 0, w_acc = 0;
-    for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+    for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
       const BItem it = b_decode(args, gi);
       if (!it.valid) continue;
       const int buf = j & 1;
@@ -1598,17 +1608,18 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
     const int64_t ld = args.ld;
     int j = 0;
     bool bad = false;
+    uint32_t gstage = 0;                  // ring position of the current item's first stage (as the producer / issuer count)
     {   // the first item's saves
-      for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+      for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
         const BItem it0 = b_decode(args, gi);
         if (it0.valid) { b_prefetch_saves(args, it0, r, grp, npH); break; }
       }
     }
-    for (int gi = blockIdx.x; gi < n_g; gi += gridDim.x) {
+    for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
       const BItem it = b_decode(args, gi);
       if (!it.valid) continue;
       {   // request the NEXT item's saves now: a whole item of lead time
-        for (int gn = gi + int(gridDim.x); gn < n_g; gn += gridDim.x) {
+        for (int gn = gi + n_cc; gn < n_g; gn += n_cc) {
           const BItem itn = b_decode(args, gn);
           if (itn.valid) { b_prefetch_saves(args, itn, r, grp, npH); break; }
         }
@@ -1629,6 +1640,47 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
       const float* dxu = top ? N.dh_top + (s * size_t(args.n) + size_t(live ? R : 0)) * H
                              : N.dx + (size_t(it.layer + 1) * size_t(args.T) + s) * npH;
       char* dGo = N.dG + (size_t(it.layer) * size_t(args.T + 1) + s) * args.sb4;
+      if (args.tn) {
+        // stage g of the ring belongs to warp group g % 4 (= grp): wait until it has landed, re-pack it if this X tile owns
+        // the K block, release it (every stage gets exactly four such arrivals, whoever owns it)
+        for (int b = 0; b < kb4; ++b) {
+          const uint32_t g = gstage + uint32_t(b);
+          if (int(g & 3u) != grp) continue;
+          const int st = int(g % kBStages);
+          mbar_wait(&full[st], (g / kBStages) & 1);
+          if (it.kind == 1 && (b % th) == it.tile) {
+            const uint8_t* sa = smem + size_t(st) * kBStageBytes;       // A block [hi|lo][chunk][128 rows][16 B]
+            const int cm = (ew & 3) * 32 + lane;                        // one of the block's 128 core matrices (8 rows x 8 K)
+            const int r8 = cm & 15, c = (cm >> 4) & 3, plane = cm >> 6;
+            const uint8_t* sp = sa + ((size_t(plane) * 4 + c) * kPanelRows + size_t(r8) * 8) * 16;
+            uint4 in[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              in[rr] = *reinterpret_cast<const uint4*>(sp + rr * 16);
+              if (int64_t(it.panel) * kPanelRows + r8 * 8 + rr >= args.n) in[rr] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            const int64_t kp = (int64_t(it.s) * args.panels + it.panel) * kPanelRows + r8 * 8;    // K' of the chunk's first row
+            const int64_t kbq = kp / 32;
+            const int cq = int((kp / 8) & 3);
+            const int j0 = b * 32 + c * 8;                                                        // operand row of its first K value
+            char* dp = N.tn_dG[it.layer] + size_t(j0 / kTileCols) * args.tn_col_bytes +
+                       (((size_t(kbq) * 2 + plane) * 4 + cq) * kTileCols + size_t(j0 % kTileCols)) * 16;
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const unsigned sel = (i8 & 1) ? 0x7632u : 0x5410u;
+              uint4 o;
+              o.x = __byte_perm((&in[0].x)[i8 >> 1], (&in[1].x)[i8 >> 1], sel);
+              o.y = __byte_perm((&in[2].x)[i8 >> 1], (&in[3].x)[i8 >> 1], sel);
+              o.z = __byte_perm((&in[4].x)[i8 >> 1], (&in[5].x)[i8 >> 1], sel);
+              o.w = __byte_perm((&in[6].x)[i8 >> 1], (&in[7].x)[i8 >> 1], sel);
+              *reinterpret_cast<uint4*>(dp + size_t(i8) * 16) = o;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        gstage += uint32_t(kb4);
+      }
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * kBT) + grp * (kBT / 4));
@@ -3047,6 +3099,7 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
     for (int l = 0; l < depth; ++l) N.w_bwd[l] = reinterpret_cast<const char*>(Nn.tc_bwd_image64) + bwd_layer_bytes(h) * l;
     N.dG = b.net[k].dG; N.save_g = b.net[k].save_g; N.c_hist = b.net[k].c_hist; N.dh_top = b.net[k].dh_top;
     N.dx = b.net[k].dx; N.dx0 = b.net[k].dx0; N.dc = b.net[k].dc; N.flags = b.net[k].flags;
+    for (int l = 0; l < depth; ++l) N.tn_dG[l] = b.net[k].tn_dG[l];
   }
   a.nets = b.nets; a.depth = depth; a.H = H; a.panels = int(np / kPanelRows);
   a.n = b.n; a.ld = b.ld; a.T = b.T;
@@ -3056,8 +3109,17 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
   { const char* e = getenv("KBS_PERSIST_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.trace = h->trace_buf ? h->trace_buf + 2 * 148 * 16 : nullptr;  // third region of the debug buffer (forward kernel, input projection, this)
   const int64_t per_slot = int64_t(b.nets) * a.panels * depth * 2 * (H / kBT);
+  const int n_cc = int(per_slot < h->num_sms ? per_slot : h->num_sms);
+  // The X tiles re-pack dG for the weight-gradient GEMMs on the fly when a CTA has (about) one item per slot: its epilogue
+  // warps are idle during the MMAs then.  With many items per CTA and slot the epilogue of item j overlaps the MMAs of item
+  // j + 1 and must not be held up: the caller runs kbs_tc_sb_to_tn after the kernel instead (*transposed_out says which).
+  int tn = (b.tn_plan && b.net[0].tn_dG[0] && per_slot <= 2 * int64_t(h->num_sms)) ? 1 : 0;
+  { const char* e = getenv("KBS_BPTT_TN"); if (e && b.tn_plan && b.net[0].tn_dG[0]) tn = atoi(e) ? 1 : 0; }
+  a.tn = tn;
+  if (tn) { a.tn_kb_total = b.tn_plan->kb_total; a.tn_col_bytes = b.tn_plan->col_bytes; }
+  if (b.transposed_out) *b.transposed_out = tn != 0;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(per_slot < h->num_sms ? per_slot : h->num_sms));
+  cfg.gridDim = dim3(unsigned(n_cc));
   cfg.blockDim = dim3(kBThreads);
   cfg.dynamicSmemBytes = kBSmemBytes;
   cfg.stream = st;

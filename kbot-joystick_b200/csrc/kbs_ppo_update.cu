@@ -776,6 +776,7 @@ struct PersistWork {
   char* tnb_layer[KBS_MAX_DEPTH];   // [x_l | h_in_l]: 2 H / 128 tiles
   char* tnb_top;                    // top layer's outputs: H / 128 tiles
   char* tnb_obs;                    // observations + ones column: kpp / 128 tiles
+  char* tna_dG[KBS_MAX_DEPTH];      // A operands: dG of each layer re-packed (by the backward kernel's transposer CTAs): 4 H / 128 panels
 };
 
 size_t persist_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n) {
@@ -790,7 +791,7 @@ size_t persist_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n) {
              depth * size_t(T) * npH /*dx*/ + size_t(T) * sbf /*dx0*/ + depth * npH /*dc*/ + rows * H /*dh_top*/ + rows * 64 /*dout*/ +
              64 * H + kbs_tc_bptt_flag_bytes(h, n) / 4;
   f += (m_panels + b_tiles) * plan.col_bytes / 4 + size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128) + 1024 + 4096;
-  f += (depth * (2 * H / 128) + H / 128 + kpp / 128) * plan.col_bytes / 4;
+  f += (depth * (2 * H / 128) + H / 128 + kpp / 128 + depth * (4 * H / 128)) * plan.col_bytes / 4;
   return f + 64 * 40;       // carve() rounds every piece up to 64 floats
 }
 
@@ -841,6 +842,7 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     for (int l = 0; l < depth; ++l) w[k].tnb_layer[l] = reinterpret_cast<char*>(carve(p, size_t(2 * H / 128) * plan.col_bytes / 4));
     w[k].tnb_top = reinterpret_cast<char*>(carve(p, size_t(H / 128) * plan.col_bytes / 4));
     w[k].tnb_obs = reinterpret_cast<char*>(carve(p, kpp / 128 * plan.col_bytes / 4));
+    for (int l = 0; l < depth; ++l) w[k].tna_dG[l] = reinterpret_cast<char*>(carve(p, size_t(4 * H / 128) * plan.col_bytes / 4));
   }
   // ---- forward ----
   KbsTcRolloutArgs r{};
@@ -911,8 +913,18 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     KbsBpttNet& B = ba.net[k];
     B.dG = w[k].dG; B.save_g = w[k].save_g; B.c_hist = w[k].c_hist; B.dh_top = w[k].dh_top; B.dx = w[k].dx; B.dx0 = w[k].dx0;
     B.dc = w[k].dc; B.flags = w[k].bflags;
+    const int64_t kb_used = (T * np + 31) / 32;
+    for (int l = 0; l < depth; ++l) {
+      B.tn_dG[l] = w[k].tna_dG[l];
+      if (kb_used < plan.kb_total)                 // K padding behind the last stored row
+        for (int c = 0; c < 4 * H / 128; ++c)
+          KBS_CUDA_TRY(cudaMemsetAsync(w[k].tna_dG[l] + size_t(c) * plan.col_bytes + size_t(kb_used) * 16384, 0,
+                                       size_t(plan.kb_total - kb_used) * 16384, st));
+    }
   }
   ba.nets = 2; ba.n = n; ba.ld = ld; ba.T = T; ba.done = b.done; ba.gscale = gscale;
+  bool dG_transposed = false;
+  ba.tn_plan = &plan; ba.transposed_out = &dG_transposed;
   if ((rc = kbs_tc_bptt(h, ba, st))) return rc;
   if (side_pack) KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[0], 0));       // join: the B operands are ready
   // ---- weight gradients ----
@@ -924,9 +936,11 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     if ((rc = kbs_tc_ones_block(h, w[k].tn_ones, st))) return rc;
     for (int l = 0; l < depth; ++l) {
       const int mp = 4 * H / 128, ldc = (2 * H / 128 + 1) * 128;
-      if ((rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dG + size_t(l) * (T + 1) * sb4, sb4, kb4, 0, kb4, n, T, w[k].tn_a, st))) return rc;
-      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, mp, 4 * H, w[k].tnb_layer[l], 2 * H / 128, w[k].tn_ones, w[k].tn_zero, w[k].tn_partial,
-                               inv, st)))
+      if (!dG_transposed &&
+          (rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dG + size_t(l) * (T + 1) * sb4, sb4, kb4, 0, kb4, n, T, w[k].tna_dG[l], st)))
+        return rc;
+      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tna_dG[l], mp, 4 * H, w[k].tnb_layer[l], 2 * H / 128, w[k].tn_ones, w[k].tn_zero,
+                               w[k].tn_partial, inv, st)))
         return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 0, 4 * H, H, g->w_ih[l], H, st))) return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, H, 4 * H, H, g->w_hh[l], H, st))) return rc;
