@@ -312,7 +312,7 @@ int kbs_destroy(kbs_handle* h) {
   if (!h) return KBS_OK;
   for (int k = 0; k < 2; ++k) {
     KbsNet& N = h->net[k];
-    cudaFree(N.w_in); cudaFree(N.b_in); cudaFree(N.w_out); cudaFree(N.b_out); cudaFree(N.tc_image); cudaFree(N.tc_bwd_image); cudaFree(N.tc_bwd_image64);
+    cudaFree(N.w_in); cudaFree(N.b_in); cudaFree(N.w_out); cudaFree(N.b_out); cudaFree(N.tc_image); cudaFree(N.tc_bwd_image); cudaFree(N.tc_bwd_image64); cudaFree(N.tc_fwd8_image);
     for (int l = 0; l < KBS_MAX_DEPTH; ++l) { cudaFree(N.w_ih[l]); cudaFree(N.w_hh[l]); cudaFree(N.b[l]); }
   }
   cudaFree(h->scratch);

@@ -40,6 +40,7 @@ struct KbsNet {
   size_t tc_image_floats = 0;
   float* tc_bwd_image = nullptr;   // PPO update: [W_ih | W_hh] transposed per layer as MMA operand (kbs_tc_pack_bwd), 128-column tiles
   float* tc_bwd_image64 = nullptr; // ... and in the 64-column tiles of bptt_persist_kernel
+  float* tc_fwd8_image = nullptr;  // LSTM weights in 128-column tiles of 8-unit groups (lstm_fwd_save_kernel, FP16 kind)
 };
 
 // kernel ids of the per-kernel CUDA-event profiler (kbs_profile_*): one id per __global__ of the library
@@ -78,6 +79,7 @@ struct kbs_handle {
   bool tc_attr_set = false;                   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: once per handle
   bool head_attr_set = false;
   bool bptt_attr_set = false;
+  bool fwd_save_attr_set = false;
   cudaEvent_t ev_critic_ready = nullptr;      // caller's event (kbs_ppo_grad_set_events): recorded when the critic's gradients are final
   bool scratch_locked = false;                // kbs_scratch_lock: growing the scratch is an error (a CUDA graph holds pointers)
   long long* trace_buf = nullptr;
@@ -252,6 +254,19 @@ struct KbsBpttArgs {
   const KbsTnPlan* tn_plan;        // with tn_dG: layout of the re-packed operands
   bool* transposed_out;            // set to whether the kernel re-packed dG itself (enough idle SMs) or the caller has to
 };
+// forward recurrence of the PPO update (lstm_fwd_save_kernel): LSTM stacks only, everything kept for the backward pass
+struct KbsFwdSaveNet {
+  const char* x0; char* xmid; char* hsb; float* c_hist; float* save_g; float* h_top_rm; unsigned int* flags;
+  const float* carry0;             // ABI [depth][2][n][H] or nullptr (zeros)
+  char* tn_xh[KBS_MAX_DEPTH];      // optional: per layer, the K = row re-pack of [x | h_in] (B operand of the dW GEMMs)
+};
+struct KbsFwdSaveArgs {
+  KbsFwdSaveNet net[2]; int nets; int64_t n, ld, T; const uint8_t* done;
+  const KbsTnPlan* tn_plan; bool* transposed_out;
+};
+size_t kbs_tc_fwd_save_flag_bytes(const kbs_handle* h, int64_t n);
+bool kbs_tc_fwd_save_available(const kbs_handle* h, int64_t n, int64_t T);
+int kbs_tc_fwd_save(kbs_handle* h, const KbsFwdSaveArgs& f, cudaStream_t st);
 size_t kbs_tc_bptt_flag_bytes(const kbs_handle* h, int64_t n);
 bool kbs_tc_bptt_available(const kbs_handle* h, int64_t n, int64_t T);
 int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& a, cudaStream_t st);

@@ -1641,12 +1641,12 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
                              : N.dx + (size_t(it.layer + 1) * size_t(args.T) + s) * npH;
       char* dGo = N.dG + (size_t(it.layer) * size_t(args.T + 1) + s) * args.sb4;
       if (args.tn) {
-        // stage g of the ring belongs to warp group g % 4 (= grp): wait until it has landed, re-pack it if this X tile owns
+        // ring slot st belongs to warp group st % 4 (= grp): wait until the stage has landed, re-pack it if this X tile owns
         // the K block, release it (every stage gets exactly four such arrivals, whoever owns it)
         for (int b = 0; b < kb4; ++b) {
           const uint32_t g = gstage + uint32_t(b);
-          if (int(g & 3u) != grp) continue;
           const int st = int(g % kBStages);
+          if ((st & 3) != grp) continue;            // by ring slot: the same warps watch every phase of a barrier (see lstm_fwd_save_kernel)
           mbar_wait(&full[st], (g / kBStages) & 1);
           if (it.kind == 1 && (b % th) == it.tile) {
             const uint8_t* sa = smem + size_t(st) * kBStageBytes;       // A block [hi|lo][chunk][128 rows][16 B]
@@ -1770,6 +1770,366 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
     tr[0] = clock64() - t_start;
     tr[15] = (long long)(gt_end - gt_start);
   }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// ---- persistent forward kernel of the PPO update (SAVE pass): narrow tiles -------------------------------------------------
+// The forward recurrence of kbs_ppo_grad at minibatch size (512 trajectories = 4 panels): rollout_persist_kernel<SAVE> with
+// its 128 x 256 tiles put 64 LSTM items in a slot and each SM streamed 768 KB per item from L2 at the ~60 B/clk one SM gets
+// (34.7 K cycles per slot, tools/ppo_trace.py).  This kernel is the same wavefront with 128 x 128 tiles (32 hidden units x 4
+// gates, 8-unit column groups): 128 items per slot on 128 SMs, 512 KB per item, 8 units per epilogue thread.  It computes the
+// LSTM stacks only -- the output heads of the update are one batched GEMM + a per-env scan afterwards (the low-pass filter's
+// recurrence does not feed the LSTMs) -- and keeps for the backward pass: the per-step operands (xmid / hsb), the cell states,
+// the activated gates, the top layer's outputs (row-major, for the head GEMM), and (tn) the K = row re-pack of [x | h_in],
+// the B operand of the weight-gradient GEMMs, written from the stages in shared memory while the MMAs run.
+constexpr int kSStages = 6;
+constexpr int kSSmemBytes = kSStages * kStageBytes + 2 * kMaxBias * kPMaxDepth * 4 + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int kSEpiWarps = 16;
+constexpr int kSThreads = 32 * (1 + 1 + kSEpiWarps + 2);
+constexpr int kSGU = 8;                     // units per column group: tile column = grp * 32 + gate * 8 + uu
+struct SNet {
+  const char* x0; size_t x0_stride;        // [T] x x0_stride: layer-0 inputs (the input projection of every step)
+  char* xmid;                              // [depth][T] x sbb: un-reset output of layer l at step t
+  char* hsb;                               // [depth][T + 1] x sbb: slot t = the hidden state step t reads (reset where done)
+  float* c_hist;                           // [depth][T + 1] x np*H (FB): slot t = the cell state step t reads
+  float* save_g;                           // [T][depth][4] x np*H (FB): activated gates i, f, g, o
+  float* h_top_rm;                         // [T * n][H] row-major: the top layer's outputs (head GEMM)
+  const char* w[kPMaxDepth];               // per layer: H / 32 tiles of 128 gate columns (8-unit groups), K = 2H, WB blocks
+  const float* bias[kPMaxDepth];           // [4H] in tile-column order
+  unsigned int* flags;                     // [depth][panels] completion counters (zeroed by the host)
+  char* tn_xh[kPMaxDepth];                 // tn: per layer, [x | h_in] re-packed with K = t np + row (2 H / 128 tiles, WB blocks)
+};
+struct SArgs {
+  SNet net[2];
+  int nets, depth, H, panels;
+  int64_t n, ld, T;
+  size_t sbb;
+  const uint8_t* done;                     // [T][ld]
+  unsigned int* status;
+  int dbg, tn, tn_kb_total;
+  size_t tn_col_bytes;
+};
+struct SItem { int net, layer, panel, tile, t; bool valid; };
+__device__ __forceinline__ SItem s_decode(const SArgs& a, int g) {
+  const int tiles = a.H / 32;
+  const int per_panel = a.depth * tiles, per_net = a.panels * per_panel, C = a.nets * per_net;
+  const int sigma = g / C;
+  int i = g - sigma * C;
+  SItem it;
+  it.net = i / per_net; i -= it.net * per_net;
+  it.panel = i / per_panel;
+  const int q = i - it.panel * per_panel;
+  it.layer = q / tiles;
+  it.tile = q - it.layer * tiles;
+  it.t = sigma - it.layer;
+  it.valid = it.t >= 0 && it.t < int(a.T);
+  return it;
+}
+__device__ __forceinline__ void s_wait_deps(const SArgs& a, const SItem& it, bool& drain) {
+  if (drain) return;
+  const SNet& N = a.net[it.net];
+  const unsigned int per = unsigned((a.H / 32) * kSEpiWarps);
+  const unsigned int* fp[2]; unsigned int tg[2]; int nd = 0;
+  const unsigned int t = unsigned(it.t);
+  if (t >= 1) { fp[nd] = N.flags + it.layer * a.panels + it.panel; tg[nd++] = t * per; }                 // h_{t-1}, c_{t-1}
+  if (it.layer >= 1) { fp[nd] = N.flags + (it.layer - 1) * a.panels + it.panel; tg[nd++] = (t + 1) * per; }   // x_t
+  if (nd == 0) return;
+  if (nd == 1) { fp[1] = fp[0]; tg[1] = 0u; }
+  unsigned int polls = 0;
+  unsigned long long t0 = 0;
+  while (true) {
+    const unsigned int v0 = ld_volatile_u32(fp[0]), v1 = ld_volatile_u32(fp[1]);
+    if (v0 >= tg[0] && v1 >= tg[1]) break;
+    if ((++polls & 1023u) == 0u) {
+      if (ld_volatile_u32(a.status) & 3u) { drain = true; break; }
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kPWaitTimeoutNs) { atomicOr(a.status, unsigned(KBS_STATUS_TIMEOUT_LSTM)); drain = true; break; }
+    }
+  }
+  __threadfence();
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kSThreads, 1) lstm_fwd_save_kernel(const __grid_constant__ SArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* bias_s = reinterpret_cast<float*>(smem + kSStages * kStageBytes);          // [net][layer][kMaxBias]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * kPMaxDepth * kMaxBias);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kSStages;
+  uint64_t* acc_full = bars + 2 * kSStages;     // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  volatile int* dep_seq = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  unsigned int* epi_done = reinterpret_cast<unsigned int*>(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = args.H, tiles = H / 32;
+  const int per_slot = args.nets * args.panels * args.depth * tiles;
+  const int n_g = (int(args.T) + args.depth - 1) * per_slot;
+  constexpr int kBlk = kbs_block_k(KIND);
+  const int kb = H / kBlk;                       // K blocks of each half ([x | h]) of an item
+  const size_t npH = size_t(args.panels) * kPanelRows * H;
+  const int n_cc = int(gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], args.tn ? 5 : 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kSEpiWarps); }
+    *dep_seq = 0;
+    *epi_done = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 2 + kSEpiWarps + 1) {
+    if (lane == 0) {
+      // ===== publisher (see rollout_persist_kernel) =====
+      int j = 0;
+      for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
+        const SItem it = s_decode(args, gi);
+        if (!it.valid) continue;
+        ++j;
+        const unsigned int want = unsigned(j) * kSEpiWarps;
+        unsigned int seen;
+        do {
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(epi_done)) : "memory");
+        } while (seen < want);
+        __threadfence();
+        atomicAdd(args.net[it.net].flags + it.layer * args.panels + it.panel, unsigned(kSEpiWarps));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2 + kSEpiWarps) {
+    if (lane == 0) {
+      // ===== dependency poller =====
+      int j = 0;
+      bool drain = false;
+      for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
+        const SItem it = s_decode(args, gi);
+        if (!it.valid) continue;
+        if (!(args.dbg & 1)) s_wait_deps(args, it, drain);
+        *dep_seq = ++j;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane < 2) {
+      // ===== producers: lane 0 = the activation block ([x | h_in]), lane 1 = the weight block of the stage =====
+      uint32_t g = 0;
+      int j = 0;
+      for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
+        const SItem it = s_decode(args, gi);
+        if (!it.valid) continue;
+        const SNet& N = args.net[it.net];
+        const size_t poff = size_t(it.panel) * kb * kABlockBytes;
+        const char* xa = it.layer == 0 ? N.x0 + size_t(it.t) * N.x0_stride + poff
+                                       : N.xmid + (size_t(it.layer - 1) * size_t(args.T) + size_t(it.t)) * args.sbb + poff;
+        const char* ha = N.hsb + (size_t(it.layer) * size_t(args.T + 1) + size_t(it.t)) * args.sbb + poff;
+        const char* wb = N.w[it.layer] + size_t(it.tile) * (2 * kb) * kBBlockBytes;
+        ++j;
+        bool need_dep = true;
+        for (int b = 0; b < 2 * kb; ++b, ++g) {
+          const int s = g % kSStages;
+          if (lane == 0) {
+            mbar_wait(&empty[s], ((g / kSStages) & 1) ^ 1);
+            mbar_expect_tx(&full[s], uint32_t(kABlockBytes + kBBlockBytes));
+          }
+          __syncwarp(0x3);
+          uint8_t* sa = smem + size_t(s) * kStageBytes;
+          if (lane == 0 && need_dep) {
+            while (*dep_seq < j) { }
+            __threadfence_block();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            need_dep = false;
+          }
+          const char* src = lane == 0 ? (b < kb ? xa + size_t(b) * kABlockBytes : ha + size_t(b - kb) * kABlockBytes)
+                                      : wb + size_t(b) * kBBlockBytes;
+          bulk_g2s(sa + lane * kABlockBytes, src, uint32_t(kABlockBytes), &full[s]);      // kABlockBytes == kBBlockBytes
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 0) {
+    // ===== MMA issuer: per k-step  a_hi . [W_hi | W_lo]^T (N = 256: main | correction columns) + a_lo . W_hi^T (N = 128) =====
+    uint32_t g = 0;
+    int j = 0;
+    for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
+      const SItem it = s_decode(args, gi);
+      if (!it.valid) continue;
+      const int buf = j & 1;
+      mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_main = tmem_base + buf * (2 * kTileCols), d_corr = d_main + kTileCols;
+      for (int b = 0; b < 2 * kb; ++b, ++g) {
+        const int s = g % kSStages;
+        mbar_wait(&full[s], (g / kSStages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
+        const uint32_t sb = sa + kABlockBytes;
+        const uint64_t a_hi = umma_desc(sa, 2048, 128), a_lo = umma_desc(sa + 8192, 2048, 128);
+        const uint64_t b_all = umma_desc(sb, 4096, 128);
+        if (elect_one()) {
+          umma<KIND, 2 * kTileCols>(d_main, a_hi, b_all, b != 0);
+          umma<KIND, kTileCols>(d_corr, a_lo, b_all, 1);
+          umma<KIND, 2 * kTileCols>(d_main, a_hi + (4096 >> 4), b_all + (8192 >> 4), 1);
+          umma<KIND, kTileCols>(d_corr, a_lo + (4096 >> 4), b_all + (8192 >> 4), 1);
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
+      ++j;
+    }
+  } else {
+    // ===== epilogue: 16 warps; warp % 4 = TMEM lane quarter (rows), grp = which 8 of the tile's 32 hidden units =====
+    const int ew = warp - 2;
+    {
+      const int et = threadIdx.x - 64;
+      for (int k = 0; k < args.nets; ++k)
+        for (int l = 0; l < args.depth; ++l)
+          for (int i = et * 4; i < 4 * H; i += 32 * kSEpiWarps * 4)
+            *reinterpret_cast<float4*>(bias_s + (k * kPMaxDepth + l) * kMaxBias + i) =
+                *reinterpret_cast<const float4*>(args.net[k].bias[l] + i);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kSEpiWarps) : "memory");
+    }
+    const int q4 = warp & 3, grp = ew >> 2;
+    const int r = q4 * 32 + lane;
+    constexpr float kCorr = (KIND == KBS_KIND_F16) ? (1.0f / kKbsF16LoScale) : 1.0f;
+    const int64_t ld = args.ld;
+    int j = 0;
+    uint32_t gstage = 0;
+    for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
+      const SItem it = s_decode(args, gi);
+      if (!it.valid) continue;
+      const SNet& N = args.net[it.net];
+      const int64_t R = int64_t(it.panel) * kPanelRows + r;
+      const bool live = R < args.n;
+      const int buf = j & 1;
+      const int u0 = it.tile * 32 + grp * kSGU;               // first of this thread's 8 hidden units
+      while (*dep_seq < j + 1) { }
+      __threadfence_block();
+      const size_t t = size_t(it.t);
+      const float* cin = N.c_hist + (size_t(it.layer) * size_t(args.T + 1) + t) * npH;
+      float4 c0, c1;
+      if (live) {
+        c0 = __ldcg(reinterpret_cast<const float4*>(cin + fb_offset(R, u0, H)));
+        c1 = __ldcg(reinterpret_cast<const float4*>(cin + fb_offset(R, u0 + 4, H)));
+      }
+      const bool rst = live && args.done[t * ld + R];
+      if (args.tn) {
+        // on-the-fly re-pack of the item's [x | h_in] stages (see bptt_persist_kernel): ring slot st belongs to warp group st % 4
+        for (int b = 0; b < 2 * kb; ++b) {
+          const uint32_t g = gstage + uint32_t(b);
+          const int st = int(g % kSStages);
+          // ownership by ring SLOT, not by stage number: a barrier must always be watched by the same warps, which then see
+          // every one of its phases in order -- a parity wait on a barrier that is still a whole phase behind returns at once
+          // (kSStages = 6 is not a multiple of 4: owners by stage number read slots that had not landed yet, ~1 in 400 panels)
+          if ((st & 3) != grp) continue;
+          mbar_wait(&full[st], (g / kSStages) & 1);
+          if ((b % tiles) == it.tile) {
+            const uint8_t* sa = smem + size_t(st) * kStageBytes;
+            const int cm = (ew & 3) * 32 + lane;
+            const int r8 = cm & 15, c = (cm >> 4) & 3, plane = cm >> 6;
+            const uint8_t* sp = sa + ((size_t(plane) * 4 + c) * kPanelRows + size_t(r8) * 8) * 16;
+            uint4 in[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              in[rr] = *reinterpret_cast<const uint4*>(sp + rr * 16);
+              if (int64_t(it.panel) * kPanelRows + r8 * 8 + rr >= args.n) in[rr] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            const int64_t kp = (int64_t(it.t) * args.panels + it.panel) * kPanelRows + r8 * 8;
+            const int64_t kbq = kp / 32;
+            const int cq = int((kp / 8) & 3);
+            const int j0 = b * 32 + c * 8;                      // column of [x | h_in]: x blocks first, then h blocks
+            char* dp = N.tn_xh[it.layer] + size_t(j0 / kTileCols) * args.tn_col_bytes +
+                       (((size_t(kbq) * 4 + cq) * 2 + plane) * kTileCols + size_t(j0 % kTileCols)) * 16;    // WB block layout
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const unsigned sel = (i8 & 1) ? 0x7632u : 0x5410u;
+              uint4 o;
+              o.x = __byte_perm((&in[0].x)[i8 >> 1], (&in[1].x)[i8 >> 1], sel);
+              o.y = __byte_perm((&in[2].x)[i8 >> 1], (&in[3].x)[i8 >> 1], sel);
+              o.z = __byte_perm((&in[4].x)[i8 >> 1], (&in[5].x)[i8 >> 1], sel);
+              o.w = __byte_perm((&in[6].x)[i8 >> 1], (&in[7].x)[i8 >> 1], sel);
+              *reinterpret_cast<uint4*>(dp + size_t(i8) * 16) = o;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        gstage += uint32_t(2 * kb);
+      }
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * kTileCols) + grp * 32);
+      float v[32];
+      {
+        float cr[32];
+        tmem_ld32(tq, v);
+        tmem_ld32(tq + kTileCols, cr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += kCorr * cr[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      const float* bs = bias_s + (it.net * kPMaxDepth + it.layer) * kMaxBias + it.tile * kTileCols + grp * 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += bs[i];
+      if (live) {
+        float hn[8], cn[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float cprev = i < 4 ? (&c0.x)[i] : (&c1.x)[i - 4];
+          const float ai = sigmoidf_(v[i]), af = sigmoidf_(v[8 + i]), ag = tanhf_(v[16 + i]), ao = sigmoidf_(v[24 + i]);
+          cn[i] = af * cprev + ai * ag;                           // c' = s(f) c + s(i) tanh(g)   (eqx LSTMCell)
+          hn[i] = ao * tanhf_(cn[i]);                             // h' = s(o) tanh(c')
+          if (rst) cn[i] = 0.0f;
+          v[i] = ai; v[8 + i] = af; v[16 + i] = ag; v[24 + i] = ao;   // the activated gates, kept for the backward pass
+        }
+        const float h0[4] = {hn[0], hn[1], hn[2], hn[3]}, h1[4] = {hn[4], hn[5], hn[6], hn[7]};
+        const KbsSplit4 s0 = sb_split4<KIND>(h0), s1 = sb_split4<KIND>(h1);
+        char* x_out = N.xmid + (size_t(it.layer) * size_t(args.T) + t) * args.sbb;
+        char* h_out = N.hsb + (size_t(it.layer) * size_t(args.T + 1) + t + 1) * args.sbb;
+        float* cdst = N.c_hist + (size_t(it.layer) * size_t(args.T + 1) + t + 1) * npH;
+        sb_store_split8<kPanelRows, KIND>(h_out, R, u0, kb, s0, s1, rst);      // what step t + 1 reads (reset where done)
+        *reinterpret_cast<float4*>(cdst + fb_offset(R, u0, H)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        *reinterpret_cast<float4*>(cdst + fb_offset(R, u0 + 4, H)) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+        sb_store_split8<kPanelRows, KIND>(x_out, R, u0, kb, s0, s1, false);    // what the layer above reads (un-reset)
+        if (it.layer + 1 == args.depth) {
+          float* hr = N.h_top_rm + (t * size_t(args.n) + size_t(R)) * H + u0;
+          *reinterpret_cast<float4*>(hr) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          *reinterpret_cast<float4*>(hr + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        }
+      }
+      // publish (h, c, x are stored), then keep the activated gates: nothing in this launch reads them
+      __syncwarp();
+      if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(epi_done)) : "memory");
+      if (live) {
+        float* sg = N.save_g + (t * args.depth + it.layer) * 4 * npH;
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate) {
+          *reinterpret_cast<float4*>(sg + gate * npH + fb_offset(R, u0, H)) = make_float4(v[8 * gate], v[8 * gate + 1], v[8 * gate + 2], v[8 * gate + 3]);
+          *reinterpret_cast<float4*>(sg + gate * npH + fb_offset(R, u0 + 4, H)) =
+              make_float4(v[8 * gate + 4], v[8 * gate + 5], v[8 * gate + 6], v[8 * gate + 7]);
+        }
+      }
+      ++j;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
@@ -2055,7 +2415,7 @@ __global__ void __launch_bounds__(kFThreads, 1) input_proj_fused_kernel(const __
 // eqx LSTMCell weights [4H][H] x2 + bias [4H]  ->  gate-interleaved SB tiles (hi/lo) + interleaved bias.
 // tile j (128 columns = 32 hidden units), column c = half * 64 + gate * 16 + uu  ->  unit = 32 j + 16 half + uu:
 // an epilogue thread that owns 16 units finds their i, f, g, o pre-activations in 64 CONSECUTIVE TMEM columns.
-template <int KIND, int TILE>
+template <int KIND, int TILE, int GU = 16>
 __global__ void __launch_bounds__(256)
 pack_lstm_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b,
                          char* __restrict__ w_sb, float* __restrict__ bias_t, int H, int Kx, int ldx) {
@@ -2067,8 +2427,8 @@ pack_lstm_weights_kernel(const float* __restrict__ w_ih, const float* __restrict
   const int col_g = int(idx / kq);                        // global packed column: tile * TILE + c
   const int k = int(idx % kq) * 4;
   const int tile = col_g / TILE, c = col_g % TILE;
-  const int grp = c / 64, gate = (c % 64) / 16, uu = c % 16;      // [16-unit group][gate i,f,g,o][unit]
-  const int u = tile * (TILE / 4) + grp * 16 + uu;
+  const int grp = c / (4 * GU), gate = (c % (4 * GU)) / GU, uu = c % GU;      // [GU-unit group][gate i,f,g,o][unit]
+  const int u = tile * (TILE / 4) + grp * GU + uu;
   const int row = gate * H + u;                           // eqx row (i,f,g,o blocks of H)
   const float* src = (k < Kx) ? w_ih + size_t(row) * ldx + k : w_hh + size_t(row) * H + (k - Kx);
   const float x[4] = {src[0], src[1], src[2], src[3]};
@@ -2683,6 +3043,13 @@ int kbs_tc_pack(kbs_handle* h, int net, cudaStream_t st) {
     else
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_F16, kTileCols><<<gb, 256, 0, st>>>(
                                         N.w_ih[l], N.w_hh[l], N.b[l], layer_w(h, net, l), layer_bias(h, net, l), H, H, H)));
+    if (kind == KBS_KIND_F16 && H % 32 == 0) {     // 128-column tiles in 8-unit groups: lstm_fwd_save_kernel (PPO update)
+      if (!N.tc_fwd8_image) KBS_CUDA_TRY(cudaMalloc(&N.tc_fwd8_image, layer_image_bytes(h) * h->p.depth));
+      char* w8 = reinterpret_cast<char*>(N.tc_fwd8_image) + layer_image_bytes(h) * l;
+      KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_F16, kTileCols, kSGU><<<gb, 256, 0, st>>>(
+                                        N.w_ih[l], N.w_hh[l], N.b[l], w8,
+                                        reinterpret_cast<float*>(w8 + kbs_sb_bytes_kind(kind, 4 * H, 2 * H)), H, H, H)));
+    }
     if (!persist_shape_ok(h)) continue;
     if (kind == KBS_KIND_TF32)
       KBS_LAUNCH(h, KBS_K_PACK, st, (pack_lstm_weights_kernel<KBS_KIND_TF32, kTileColsP><<<gb, 256, 0, st>>>(
@@ -3130,6 +3497,83 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
   cfg.numAttrs = 1;
   cudaError_t le = cudaSuccess;
   KBS_LAUNCH(h, KBS_K_BPTT_TC, st, (le = cudaLaunchKernelEx(&cfg, bptt_persist_kernel<KBS_KIND_F16>, a)));
+  KBS_CUDA_TRY(le);
+  { const int rc0 = kbs_status_publish(h, st); if (rc0) return rc0; }
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+// ---- forward recurrence of the PPO update: lstm_fwd_save_kernel ----
+size_t kbs_tc_fwd_save_flag_bytes(const kbs_handle* h, int64_t n) {
+  return (size_t(h->p.depth) * size_t(pad_rows(n) / kPanelRows) * 4 + 255) / 256 * 256;
+}
+bool kbs_tc_fwd_save_available(const kbs_handle* h, int64_t n, int64_t T) {
+  const int H = h->p.hidden_size, depth = h->p.depth;
+  if (tc_kind(h) != KBS_KIND_F16 || H % 32 || H > kMaxBias / 4 || depth > kPMaxDepth) return false;
+  const int64_t panels = pad_rows(n) / kPanelRows;
+  return (T + depth) * 2 * panels * depth * (H / 32) < (int64_t(1) << 31);
+}
+int kbs_tc_fwd_save(kbs_handle* h, const KbsFwdSaveArgs& f, cudaStream_t st) {
+  const int H = h->p.hidden_size, depth = h->p.depth;
+  if (!kbs_tc_fwd_save_available(h, f.n, f.T)) return KBS_E_STATE;
+  { const int rc0 = kbs_status_init(h); if (rc0) return rc0; }
+  if (!h->fwd_save_attr_set) {
+    KBS_CUDA_TRY(cudaFuncSetAttribute(lstm_fwd_save_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBytes));
+    h->fwd_save_attr_set = true;
+  }
+  const int64_t n = f.n, np = pad_rows(n);
+  const size_t sbb = act_sb_bytes(h, n), fbf = size_t(np) * H;
+  SArgs a{};
+  CarryJobs J{};
+  J.ld_rm = H; J.status = h->persist_status;
+  int jobs = 0;
+  for (int k = 0; k < f.nets; ++k) {
+    const KbsNet& Nn = h->net[k];
+    if (!Nn.packed || !Nn.tc_fwd8_image) return KBS_E_STATE;
+    SNet& N = a.net[k];
+    N.x0 = f.net[k].x0; N.x0_stride = sbb; N.xmid = f.net[k].xmid; N.hsb = f.net[k].hsb; N.c_hist = f.net[k].c_hist;
+    N.save_g = f.net[k].save_g; N.h_top_rm = f.net[k].h_top_rm; N.flags = f.net[k].flags;
+    for (int l = 0; l < depth; ++l) {
+      const char* w8 = reinterpret_cast<const char*>(Nn.tc_fwd8_image) + layer_image_bytes(h) * l;
+      N.w[l] = w8;
+      N.bias[l] = reinterpret_cast<const float*>(w8 + kbs_sb_bytes_kind(KBS_KIND_F16, 4 * H, 2 * H));
+      N.tn_xh[l] = f.net[k].tn_xh[l];
+      // the carries the first step reads: ABI layout [depth][2][n][H], or zeros (get_initial_model_carry)
+      char* h_dst = f.net[k].hsb + sbb * (size_t(l) * (f.T + 1));
+      float* c_dst = f.net[k].c_hist + fbf * (size_t(l) * (f.T + 1));
+      if (!f.net[k].carry0) {
+        KBS_CUDA_TRY(cudaMemsetAsync(h_dst, 0, sbb, st));
+        KBS_CUDA_TRY(cudaMemsetAsync(c_dst, 0, fbf * sizeof(float), st));
+      } else {
+        float* c0 = const_cast<float*>(f.net[k].carry0);
+        J.rm[jobs] = c0 + (size_t(l) * 2 + 0) * size_t(n) * H; J.blk[jobs] = h_dst; J.mode[jobs++] = 0;
+        J.rm[jobs] = c0 + (size_t(l) * 2 + 1) * size_t(n) * H; J.blk[jobs] = c_dst; J.mode[jobs++] = 1;
+      }
+    }
+    KBS_CUDA_TRY(cudaMemsetAsync(f.net[k].flags, 0, kbs_tc_fwd_save_flag_bytes(h, n), st));
+  }
+  if (jobs) carry_convert(h, J, jobs, n, np, H, st);
+  a.nets = f.nets; a.depth = depth; a.H = H; a.panels = int(np / kPanelRows);
+  a.n = n; a.ld = f.ld; a.T = f.T; a.sbb = sbb; a.done = f.done; a.status = h->persist_status;
+  { const char* e = getenv("KBS_PERSIST_DBG"); a.dbg = e ? atoi(e) : 0; }
+  const int64_t per_slot = int64_t(f.nets) * a.panels * depth * (H / 32);
+  int tn = (f.tn_plan && f.net[0].tn_xh[0] && per_slot <= 2 * int64_t(h->num_sms)) ? 1 : 0;
+  { const char* e = getenv("KBS_FWD_TN"); if (e && f.tn_plan && f.net[0].tn_xh[0]) tn = atoi(e) ? 1 : 0; }
+  a.tn = tn;
+  if (tn) { a.tn_kb_total = f.tn_plan->kb_total; a.tn_col_bytes = f.tn_plan->col_bytes; }
+  if (f.transposed_out) *f.transposed_out = tn != 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(per_slot < h->num_sms ? per_slot : h->num_sms));
+  cfg.blockDim = dim3(kSThreads);
+  cfg.dynamicSmemBytes = kSSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaSuccess;
+  KBS_LAUNCH(h, KBS_K_ROLLOUT_TC, st, (le = cudaLaunchKernelEx(&cfg, lstm_fwd_save_kernel<KBS_KIND_F16>, a)));
   KBS_CUDA_TRY(le);
   { const int rc0 = kbs_status_publish(h, st); if (rc0) return rc0; }
   KBS_LAUNCH_CHECK();

@@ -771,6 +771,7 @@ int run_net(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0,
 struct PersistWork {
   char* x_sb; char* xmid; char* hsb; float* c_hist; float* save_g; char* dG; float* dx; char* dx0; float* dc;
   float* dh_top; float* dout; float* w_outT; unsigned int* bflags;
+  float* h_top_rm; float* out; unsigned int* fflags;      // narrow-tile forward: top-layer outputs, head GEMM output, counters
   char* tn_a; char* tn_b; float* tn_partial; float* tn_zero; char* tn_ones;
   // B operands (forward-pass products) are transposed on the side stream while the backward kernel runs: one buffer each
   char* tnb_layer[KBS_MAX_DEPTH];   // [x_l | h_in_l]: 2 H / 128 tiles
@@ -789,7 +790,7 @@ size_t persist_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n) {
   size_t f = size_t(T) * sbf /*x_sb*/ + depth * size_t(T) * sbf /*xmid*/ + depth * size_t(T + 1) * sbf /*hsb*/ +
              depth * size_t(T + 1) * npH /*c_hist*/ + size_t(T) * depth * 4 * npH /*save_g*/ + depth * size_t(T + 1) * sb4f /*dG*/ +
              depth * size_t(T) * npH /*dx*/ + size_t(T) * sbf /*dx0*/ + depth * npH /*dc*/ + rows * H /*dh_top*/ + rows * 64 /*dout*/ +
-             64 * H + kbs_tc_bptt_flag_bytes(h, n) / 4;
+             64 * H + kbs_tc_bptt_flag_bytes(h, n) / 4 + rows * H /*h_top_rm*/ + rows * 64 /*out*/ + kbs_tc_fwd_save_flag_bytes(h, n) / 4;
   f += (m_panels + b_tiles) * plan.col_bytes / 4 + size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128) + 1024 + 4096;
   f += (depth * (2 * H / 128) + H / 128 + kpp / 128 + depth * (4 * H / 128)) * plan.col_bytes / 4;
   return f + 64 * 40;       // carve() rounds every piece up to 64 floats
@@ -834,6 +835,9 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     w[k].dout = carve(p, size_t(rows) * 64);
     w[k].w_outT = carve(p, size_t(64) * H);
     w[k].bflags = reinterpret_cast<unsigned int*>(carve(p, kbs_tc_bptt_flag_bytes(h, n) / 4));
+    w[k].h_top_rm = carve(p, size_t(rows) * H);
+    w[k].out = carve(p, size_t(rows) * 64);
+    w[k].fflags = reinterpret_cast<unsigned int*>(carve(p, kbs_tc_fwd_save_flag_bytes(h, n) / 4));
     w[k].tn_a = reinterpret_cast<char*>(carve(p, m_panels * plan.col_bytes / 4));
     w[k].tn_b = reinterpret_cast<char*>(carve(p, b_tiles * plan.col_bytes / 4));
     w[k].tn_partial = carve(p, size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128));
@@ -845,25 +849,58 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     for (int l = 0; l < depth; ++l) w[k].tna_dG[l] = reinterpret_cast<char*>(carve(p, size_t(4 * H / 128) * plan.col_bytes / 4));
   }
   // ---- forward ----
-  KbsTcRolloutArgs r{};
+  // narrow-tile kernel (lstm_fwd_save_kernel: LSTM stacks only, heads as a batched GEMM + per-env scan afterwards) unless
+  // KBS_PPO_FWD_WIDE=1 asks for rollout_persist_kernel<SAVE> (128 x 256 tiles, heads fused: the first version, kept for A/B)
+  static int wide_cfg = -1;
+  if (wide_cfg < 0) { const char* e = getenv("KBS_PPO_FWD_WIDE"); wide_cfg = e ? atoi(e) : 0; }
+  const bool narrow = !wide_cfg && kbs_tc_fwd_save_available(h, n, T);
+  bool xh_transposed = false;
   {
     const float* obs_soa[2] = {b.actor_obs, b.critic_obs};
     float* xsb[2] = {reinterpret_cast<float*>(w[0].x_sb), reinterpret_cast<float*>(w[1].x_sb)};
     if ((rc = kbs_tc_input_proj_all(h, 2, obs_soa, osb, xsb, ld, n, T, st, nullptr, nullptr, nullptr))) return rc;
-    r.x_sb_all[0] = xsb[0]; r.x_sb_all[1] = xsb[1];
   }
-  r.n = n; r.ld = ld; r.T = T; r.with_critic = true;
-  r.carry[0] = const_cast<float*>(b.actor_carry0); r.carry[1] = const_cast<float*>(b.critic_carry0);
-  r.done = b.done; r.actor_obs = b.actor_obs;
-  // the low-pass state: a private copy of lpf0 (the kernel advances it in place)
-  if (b.lpf0) KBS_CUDA_TRY(cudaMemcpyAsync(lpf, b.lpf0, size_t(KBS_NUM_JOINTS) * ld * 4, cudaMemcpyDeviceToDevice, st));
-  else KBS_CUDA_TRY(cudaMemsetAsync(lpf, 0, size_t(KBS_NUM_JOINTS) * ld * 4, st));
-  r.lpf = lpf;
-  r.action_in = b.action; r.log_prob = log_probs; r.entropy = entropy; r.action_std = sd_s; r.mean = y_s; r.value = values;
-  r.ws = ws;
-  r.save = 1; r.sraw = sraw_s;
-  for (int k = 0; k < 2; ++k) { r.xmid_hist[k] = w[k].xmid; r.hsb_hist[k] = w[k].hsb; r.c_hist[k] = w[k].c_hist; r.save_g[k] = w[k].save_g; }
-  if ((rc = kbs_tc_rollout_recurrent(h, r, st))) return rc;
+  if (narrow) {
+    KbsFwdSaveArgs fa{};
+    for (int k = 0; k < 2; ++k) {
+      KbsFwdSaveNet& F = fa.net[k];
+      F.x0 = w[k].x_sb; F.xmid = w[k].xmid; F.hsb = w[k].hsb; F.c_hist = w[k].c_hist; F.save_g = w[k].save_g;
+      F.h_top_rm = w[k].h_top_rm; F.flags = w[k].fflags; F.carry0 = k == 0 ? b.actor_carry0 : b.critic_carry0;
+      for (int l = 0; l < depth; ++l) F.tn_xh[l] = w[k].tnb_layer[l];
+      const int64_t kb_used = (T * np + 31) / 32;
+      if (kb_used < plan.kb_total)                 // K padding behind the last stored row
+        for (int l = 0; l < depth; ++l)
+          for (int c = 0; c < 2 * H / 128; ++c)
+            KBS_CUDA_TRY(cudaMemsetAsync(w[k].tnb_layer[l] + size_t(c) * plan.col_bytes + size_t(kb_used) * 16384, 0,
+                                         size_t(plan.kb_total - kb_used) * 16384, st));
+    }
+    fa.nets = 2; fa.n = n; fa.ld = ld; fa.T = T; fa.done = b.done; fa.tn_plan = &plan; fa.transposed_out = &xh_transposed;
+    if ((rc = kbs_tc_fwd_save(h, fa, st))) return rc;
+    // heads: out = W_out h_top + b for all T x n rows, then forward + loss gradient + backward of the head per env
+    for (int k = 0; k < 2; ++k)
+      if ((rc = kbs_simt_gemm_nt(h, w[k].h_top_rm, H, h->net[k].w_out, H, h->net[k].b_out, w[k].out, 64, rows, 64, H, 0, st))) return rc;
+    KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
+               (actor_head_fwd_bwd_warp_kernel<<<unsigned((n + 3) / 4), 128, 0, st>>>(
+                   h->p, L, w[0].out, b.actor_obs, b.action, b.done, b.lpf0, b.old_log_probs, b.advantages, y_s, sd_s, log_probs, entropy,
+                   w[0].dout, T, ld, n)));
+    KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
+               (critic_head_fwd_bwd_kernel<<<blocks(rows), kT, 0, st>>>(L, w[1].out, b.old_values, b.value_targets, values, w[1].dout, T, ld, n)));
+  } else {
+    KbsTcRolloutArgs r{};
+    r.x_sb_all[0] = reinterpret_cast<float*>(w[0].x_sb); r.x_sb_all[1] = reinterpret_cast<float*>(w[1].x_sb);
+    r.n = n; r.ld = ld; r.T = T; r.with_critic = true;
+    r.carry[0] = const_cast<float*>(b.actor_carry0); r.carry[1] = const_cast<float*>(b.critic_carry0);
+    r.done = b.done; r.actor_obs = b.actor_obs;
+    // the low-pass state: a private copy of lpf0 (the kernel advances it in place)
+    if (b.lpf0) KBS_CUDA_TRY(cudaMemcpyAsync(lpf, b.lpf0, size_t(KBS_NUM_JOINTS) * ld * 4, cudaMemcpyDeviceToDevice, st));
+    else KBS_CUDA_TRY(cudaMemsetAsync(lpf, 0, size_t(KBS_NUM_JOINTS) * ld * 4, st));
+    r.lpf = lpf;
+    r.action_in = b.action; r.log_prob = log_probs; r.entropy = entropy; r.action_std = sd_s; r.mean = y_s; r.value = values;
+    r.ws = ws;
+    r.save = 1; r.sraw = sraw_s;
+    for (int k = 0; k < 2; ++k) { r.xmid_hist[k] = w[k].xmid; r.hsb_hist[k] = w[k].hsb; r.c_hist[k] = w[k].c_hist; r.save_g[k] = w[k].save_g; }
+    if ((rc = kbs_tc_rollout_recurrent(h, r, st))) return rc;
+  }
   // ---- B operands of the weight-gradient GEMMs: everything the forward pass produced, re-packed with K = row on the
   // handle's side stream WHILE the backward kernel runs (it occupies one SM per work item of a slot: 64 of 148 at 512
   // trajectories); joined before the GEMMs ----
@@ -881,23 +918,29 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
   for (int k = 1; k >= 0; --k) {
     const KbsNet& N = h->net[k];
     const int kpp = round_up_i(N.num_in + 1, 128);
-    for (int l = 0; l < depth; ++l) {
+    for (int l = 0; l < depth && !xh_transposed; ++l) {
       const char* x_hist = l == 0 ? w[k].x_sb : w[k].xmid + size_t(l - 1) * T * sbb;
       if ((rc = kbs_tc_sb_to_tn(h, plan, true, x_hist, sbb, kbH, 0, kbH, n, T, w[k].tnb_layer[l], ss))) return rc;
       if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].hsb + size_t(l) * (T + 1) * sbb, sbb, kbH, 0, kbH, n, T,
                                 w[k].tnb_layer[l] + size_t(H / 128) * plan.col_bytes, ss)))
         return rc;
     }
-    if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].xmid + size_t(depth - 1) * T * sbb, sbb, kbH, 0, kbH, n, T, w[k].tnb_top, ss))) return rc;
+    if (narrow) {
+      if ((rc = kbs_tc_pack_tn(h, plan, true, w[k].h_top_rm, H, 0, H, H, rows, w[k].tnb_top, 1.0f, -1, ss, n, np))) return rc;
+    } else if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].xmid + size_t(depth - 1) * T * sbb, sbb, kbH, 0, kbH, n, T, w[k].tnb_top, ss))) {
+      return rc;
+    }
     if ((rc = kbs_tc_soa_to_tn(h, plan, k == 0 ? b.actor_obs : b.critic_obs, N.num_in, ld, n, T, kpp, true, w[k].tnb_obs, ss))) return rc;
   }
   if (side_pack) KBS_CUDA_TRY(cudaEventRecord(h->ev_head[0], ss));
-  // ---- heads: d loss / d out ----
-  KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
-             (actor_head_bwd_warp_kernel<<<unsigned((n + 3) / 4), 128, 0, st>>>(h->p, L, b.action, b.done, b.old_log_probs, b.advantages,
-                                                                               y_s, sd_s, sraw_s, log_probs, w[0].dout, T, ld, n)));
-  KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
-             (critic_head_bwd_kernel<<<blocks(rows), kT, 0, st>>>(L, values, b.old_values, b.value_targets, w[1].dout, T, ld, n)));
+  // ---- heads: d loss / d out (the narrow forward's head kernels already produced it) ----
+  if (!narrow) {
+    KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
+               (actor_head_bwd_warp_kernel<<<unsigned((n + 3) / 4), 128, 0, st>>>(h->p, L, b.action, b.done, b.old_log_probs, b.advantages,
+                                                                                 y_s, sd_s, sraw_s, log_probs, w[0].dout, T, ld, n)));
+    KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
+               (critic_head_bwd_kernel<<<blocks(rows), kT, 0, st>>>(L, values, b.old_values, b.value_targets, w[1].dout, T, ld, n)));
+  }
   float gscale = 16.0f;
   while (gscale < 16.0f * float(rows)) gscale *= 2.0f;
   KbsBpttArgs ba{};

@@ -688,11 +688,14 @@ def _ppo_grad_case(dev, T, N, hidden, path):
     close(S(out["values"], N), val_ref, "values", atol=1e-5)
     close(out["stats"].cpu().numpy(), np.array((loss,) + stats, np.float32), "loss stats", rtol=2e-5, atol=1e-5)
 
+    bad = []
+
     def check(name, got, ref):
         got = got.cpu().numpy()
         scale = np.abs(ref).max()
         err = np.abs(got - ref).max()
-        assert np.isfinite(got).all() and err <= 3e-4 * scale + 1e-9, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+        if not (np.isfinite(got).all() and err <= 3e-4 * scale + 1e-9):
+            bad.append(f"{name}: max err {err:.3e} vs scale {scale:.3e}")
 
     for nm, g, r in (("actor", ga, ga_ref), ("critic", gc, gc_ref)):
         for k in ("w_in", "b_in", "w_out", "b_out"):
@@ -701,6 +704,7 @@ def _ppo_grad_case(dev, T, N, hidden, path):
             for k in ("w_ih", "w_hh", "b"):
                 check(f"{nm}.layers[{l}].{k}", g["layers"][l][k], r["layers"][l][k])
     e.close()
+    assert not bad, bad
 
 
 def test_ppo_update_adamw_step_decreases_loss(dev):
