@@ -777,6 +777,7 @@ struct PNet {
 struct PArgs {
   PNet net[2];
   int nets, depth, H, panels, tiles;
+  int gpanels;                     // panels per group of the item order (p_decode); = panels: one group
   int64_t n, ld, T;
   size_t sbb;
   const uint8_t* done;             // [T][ld] or nullptr
@@ -798,17 +799,25 @@ struct PArgs {
 };
 
 struct PItem { int kind, net, layer, panel, tile; int t; bool valid; };
+// Global item order: panel GROUP (gpanels consecutive panels of both nets), then slot, then (net, panel, layer | head, tile).
+// A group runs its whole T-step wavefront before the next group starts (panels are independent): the h / x / c working set
+// in flight is gpanels x nets x ~1.5 MB instead of every panel's (96 MB at 4 096 envs: it cycled through the 126 MB L2 once
+// per control step, and every activation store of the rollout went to HBM and back: 9 GB per launch against ~1 GB algorithmic).
 __device__ __forceinline__ PItem p_decode(const PArgs& a, int g) {
-  const int lt = a.depth * a.tiles, per_panel = lt + 1, per_net = a.panels * per_panel, C = a.nets * per_net;
+  const int lt = a.depth * a.tiles, per_panel = lt + 1, per_net = a.gpanels * per_panel, C = a.nets * per_net;
+  const int per_group = (int(a.T) + a.depth) * C;
+  const int grp = g / per_group;
+  g -= grp * per_group;
   const int s = g / C;
   int i = g - s * C;
   PItem it;
   it.net = i / per_net; i -= it.net * per_net;
-  it.panel = i / per_panel;
-  const int q = i - it.panel * per_panel;
+  const int pl = i / per_panel;
+  it.panel = grp * a.gpanels + pl;
+  const int q = i - pl * per_panel;
   if (q < lt) { it.kind = 0; it.layer = q / a.tiles; it.tile = q - it.layer * a.tiles; it.t = s - it.layer; }
   else { it.kind = 1; it.layer = a.depth; it.tile = 0; it.t = s - a.depth; }
-  it.valid = it.t >= 0 && it.t < int(a.T);
+  it.valid = it.t >= 0 && it.t < int(a.T) && it.panel < a.panels;
   return it;
 }
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
@@ -879,8 +888,8 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
   unsigned int* epi_done = reinterpret_cast<unsigned int*>(tmem_slot + 2);  // epilogue warps that have stored their share (monotone)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_slot = args.nets * args.panels * (args.depth * args.tiles + 1);
-  const int n_g = (int(args.T) + args.depth) * per_slot;
+  const int per_slot = args.nets * args.gpanels * (args.depth * args.tiles + 1);
+  const int n_g = ((args.panels + args.gpanels - 1) / args.gpanels) * (int(args.T) + args.depth) * per_slot;
   const int H = args.H;
   constexpr int kBlk = kbs_block_k(KIND);
   const int kb = H / kBlk;
@@ -3797,6 +3806,17 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     }
     a.nets = nets; a.depth = depth; a.H = H; a.panels = panels; a.tiles = tiles;
     a.n = n; a.ld = ld; a.T = r.T; a.sbb = sbb;
+    {
+      // panel groups (p_decode).  MEASURED (4 096 envs x 100 steps, profiles/r02_persist_groups.md): grouping trades L2
+      // residency for items in flight, and the kernel needs the items: 8 / 11 / 16 / 17 panels per group = 6.82 / 5.90 / 5.25 /
+      // 4.74 ms against 4.69 ms ungrouped (with ~2 items per CTA and slot the wavefront becomes dependency-latency-bound).
+      // The DRAM traffic of the ungrouped order (9 GB per launch) is not what bounds the kernel.  Default: one group;
+      // KBS_PERSIST_GROUP = panels per group for experiments.
+      int gp = panels;
+      const char* e = getenv("KBS_PERSIST_GROUP");
+      if (e) { const int v = atoi(e); gp = (v <= 0 || v > panels) ? panels : v; }
+      a.gpanels = gp;
+    }
     a.done = r.done;
     a.arm_cmd = r.actor_obs + size_t(55) * ld;
     a.lpf = r.lpf; a.eps = r.eps_action;
@@ -3810,7 +3830,7 @@ int kbs_tc_rollout_recurrent(kbs_handle* h, const KbsTcRolloutArgs& r, cudaStrea
     { const char* e = getenv("KBS_PERSIST_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.trace = h->trace_buf;
     cudaLaunchConfig_t cfg{};
-    const int64_t per_slot = int64_t(nets) * panels * (depth * tiles + 1);
+    const int64_t per_slot = int64_t(nets) * a.gpanels * (depth * tiles + 1);
     cfg.gridDim = dim3(unsigned(per_slot < h->num_sms ? per_slot : h->num_sms));
     { const char* e = getenv("KBS_PERSIST_GRID"); if (e && atoi(e) > 0 && atoi(e) < int(cfg.gridDim.x)) cfg.gridDim.x = unsigned(atoi(e)); }   // profiling only
     cfg.blockDim = dim3(kThreadsP);
