@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--graph", action="store_true",
                     help="replay the step as one CUDA graph instead of launching eagerly (measured slower: 10.9 vs 10.0 ms)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the PPO minibatch-update leg (BASELINE configs[3])")
+    ap.add_argument("--ppo-traj", type=int, default=512, help="stored trajectories per GPU and update (train.py:1764 batch_size)")
+    ap.add_argument("--ppo-large", type=int, default=8192,
+                    help="second PPO leg: 65 536 envs / 8 GPUs = 8 192 trajectories per GPU in one update (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -398,19 +402,151 @@ def run_b200(a):
         t = time_oracle(a, a.cpu_seconds)
         cpu = {k: t[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # ---- BASELINE configs[3]: the PPO minibatch update (the only collective of the path) ------------------------------
+    ppo = None
+    if not a.no_ppo and a.gemm == "f16":
+        eng.close()
+        del d, io
+        torch.cuda.empty_cache()
+        try:
+            ppo = run_ppo_update(a, dev, world, barrier, max_ranks, peaks, a.ppo_traj)
+            free, _tot = torch.cuda.mem_get_info()
+            free = -max_ranks(-float(free))                  # the same decision on every rank (the leg has collectives)
+            if a.ppo_large and free > 130e9:
+                big = run_ppo_update(a, dev, world, barrier, max_ranks, peaks, a.ppo_large, steps=3)
+                ppo["large"] = big
+            elif a.ppo_large:
+                ppo["large"] = {"skipped": "needs ~100 GB of free device memory, %.0f GB free" % (free / 1e9)}
+        except Exception as ex:  # noqa: BLE001  the rollout numbers above must survive a failure here
+            print(f"[bench] PPO update leg failed: {ex!r}", file=sys.stderr)
+            ppo = {"error": repr(ex)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"f16": "f32 (tcgen05 2xFP16-split GEMMs, fp32 accumulate)",
                           "tf32": "f32 (tcgen05 3xTF32 GEMMs, fp32 accumulate)", "simt": "f32"}[a.gemm],
                 "data": "synthetic", "config": config_dict(a, world), "clocks": ck, "gpu_launches": launches,
-                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernel_breakdown_ms": breakdown,
+                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernel_breakdown_ms": breakdown, "ppo_update": ppo,
                 "profile_overflow": overflow, "gemm_path": a.gemm, "launch_mode": launch_mode,
                 "cpu_enqueue_ms_per_step": cpu_enqueue_ms}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_ppo_update(a, dev, world, barrier, max_ranks, peaks, n_traj, steps=8, breakdown=True):
+    """BASELINE configs[3]: one PPO minibatch update per GPU on `n_traj` stored trajectories of T steps -- gradients of the
+    PPO loss by BPTT through both LSTM stacks (kbs_ppo_grad: persistent tcgen05 forward + backward kernels, split-K
+    weight-gradient GEMMs), the gradient all-reduce over NCCL (the path's only collective), global-norm clip + AdamW
+    (train.py:1059-1065) and the weight re-pack; the whole update replayed as ONE CUDA graph.  Timed with CUDA events, max
+    over ranks; the all-reduce is also timed alone against the measured 725 GB/s bus bandwidth (B200_PROFILING.md)."""
+    import torch
+    import torch.distributed as dist
+
+    from kbot_joystick_b200 import _lib as L
+    from kbot_joystick_b200 import synth
+    from kbot_joystick_b200.engine import KbotStep
+    from kbot_joystick_b200.ppo import PpoUpdater
+
+    H, T, N = a.hidden, a.T, n_traj
+    ld = (N + 3) // 4 * 4
+    rank = int(os.environ.get("RANK", "0"))
+    eng = KbotStep(hidden_size=H, depth=2, gemm_path=L.GEMM_TC_2XF16)
+    up = PpoUpdater(eng, synth.make_weights(77, 65, 40, H, 2), synth.make_weights(78, 475, 1, H, 2))      # same weights on every rank
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    f32 = dict(device=dev, dtype=torch.float32)
+    rn = lambda *s, sc=1.0: torch.randn(s, generator=g, **f32) * sc      # noqa: E731
+    batch = {"actor_obs": rn(T, 65, ld, sc=0.7), "critic_obs": rn(T, 475, ld, sc=0.7), "action": rn(T, 20, ld, sc=0.3),
+             "done": (torch.rand((T, ld), generator=g, device=dev) < 0.01).to(torch.uint8),
+             "old_log_probs": rn(T, ld) - 20.0, "advantages": rn(T, ld), "value_targets": rn(T, ld, sc=0.5),
+             "old_values": rn(T, ld, sc=0.5)}
+    # old log-probs / values near the current policy, as in a real update (forward-only pass: kbs_ppo_variables)
+    z = lambda: torch.zeros((2, 2, N, H), **f32)      # noqa: E731
+    fwd = eng.ppo_variables(batch["actor_obs"], batch["action"], batch["done"], z(), torch.zeros((20, ld), **f32),
+                            batch["critic_obs"], z(), want_std=False, n_envs=N)
+    batch["old_log_probs"], batch["old_values"] = fwd["log_probs"] + rn(T, ld, sc=0.1), fwd["values"] + rn(T, ld, sc=0.2)
+    del fwd
+    for _ in range(2):
+        up.update(batch, N)
+    launches0 = eng.launches
+    up.update(batch, N)
+    launches_per_update = eng.launches - launches0
+    mode = "cuda-graph replay (gradients + all-reduce + clip + AdamW + re-pack)"
+    try:
+        up.capture(batch, N)
+        up.update(batch, N)
+    except Exception as ex:  # noqa: BLE001
+        print(f"[bench] PPO update: CUDA graph capture failed ({ex!r}); timing eager launches", file=sys.stderr)
+        up._graph = None
+        mode = "eager"
+        torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = up.update(batch, N)
+    e1.record()
+    barrier()
+    ms = max_ranks(e0.elapsed_time(e1) / steps)
+    assert eng.device_status() == 0, "device health word set during the PPO update"
+    assert torch.isfinite(up.param).all() and torch.isfinite(out["stats"]).all()
+    res = {"trajectories_per_gpu": N, "T": T, "ms_per_update": ms, "env_steps_per_s": world * N * T / (ms * 1e-3),
+           "updates_timed": steps, "launch_mode": mode, "kernel_launches_per_update": launches_per_update,
+           "grad_floats": int(up.grad.numel()), "optimizer": "adamw lr 5e-4 wd 1e-5 + global-norm clip (train.py:1059-1065)",
+           "loss": float(out["stats"][0])}
+    if world > 1:                                  # the collective alone: 9 MB fp32 sum over NVLink / NVSwitch
+        buf = up.grad.clone()
+        for _ in range(3):
+            dist.all_reduce(buf)
+        barrier()
+        e0.record()
+        for _ in range(20):
+            dist.all_reduce(buf)
+        e1.record()
+        barrier()
+        us = max_ranks(e0.elapsed_time(e1) / 20) * 1e3
+        nbytes = buf.numel() * 4
+        res["allreduce"] = {"bytes": nbytes, "us": us, "bus_gbs": 2 * (world - 1) / world * nbytes / (us * 1e-6) / 1e9,
+                            "bus_gbs_reference": 725.0, "note": "9 MB: latency-bound, overlapped: the critic's slice is reduced on a "
+                            "second stream while the actor's weight-gradient GEMMs run (ppo.PpoUpdater._step)"}
+        chk = up.param.double().sum().reshape(1).clone()          # replicas must stay bitwise identical
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        res["replicas_identical"] = bool(float(hi - lo) == 0.0)
+    if breakdown:
+        # per-kernel CUDA-event pass (eager, same minibatch) -> roofline of the two recurrence kernels.  ALGORITHMIC FLOPs:
+        # forward 2 nets x 2 layers x 2 (2H)(4H) per row; backward [dx | dh] = dG [W_ih | W_hh]: the same count; weight
+        # gradients dG^T [x | h]: the same again (+ input / output projections); fp32-accurate tensor peak = sustained bf16 / 3.
+        eng.scratch_lock(False)
+        eng.profile(True)
+        up.grads(batch, N)
+        torch.cuda.synchronize()
+        prof = eng.profile_read()
+        eng.profile(False)
+        prof.pop("_overflow", None)
+        peak = peaks.get("bf16_tflops_sustained", 1400.0) / 3.0
+        rows = N * T
+        lstm = 2 * 2 * 2 * (2 * H) * (4 * H) * rows
+        flops = {"rollout_persist_kernel": lstm, "bptt_persist_kernel": lstm,
+                 "gemm_tn_tc_kernel": lstm + 2 * rows * H * (65 + 475) + 2 * rows * H * 41}
+        kb = {}
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            kb[k] = {"ms": round(v[0], 4), "launches": v[1]}
+            if k in flops and v[0] > 0:
+                ach = flops[k] / (v[0] * 1e-3) / 1e12
+                kb[k].update({"tflops": round(ach, 1), "frac_of_fp32_accurate_tensor_peak": round(ach / peak, 3)})
+        res["kernel_breakdown_ms"] = kb
+        res["roofline_note"] = ("rollout_persist_kernel here = lstm_fwd_save_kernel (forward with saved activations); at 512 "
+                                "trajectories a slot of the wavefront holds 128 work items = one per SM: both recurrence kernels "
+                                "are bound by the dependency chain of a slot (operand fill at ~60 B/clk/SM + epilogue + publish / "
+                                "poll hop), not by the tensor pipe; peak = sustained bf16 / 3 = %.0f TFLOP/s" % peak)
+    eng.close()
+    del up, batch
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world):

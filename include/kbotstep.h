@@ -472,7 +472,7 @@ int kbs_debug_tc_trace(kbs_handle* h, long long* trace_out, int64_t n_envs, void
 /* Same stamps for LSTM layer `layer` at step `step` of subsequent kbs_rollout calls (trace_out NULL detaches). */
 int kbs_debug_tc_trace_attach(kbs_handle* h, long long* trace_out, int64_t step, int layer);
 
-#define KBS_NUM_KERNEL_IDS 21
+#define KBS_NUM_KERNEL_IDS 22
 int kbs_profile_enable(kbs_handle* h, int on);
 int kbs_profile_read(kbs_handle* h, int max_ids, double* total_ms, int64_t* launches);
 const char* kbs_kernel_name(int id);

@@ -130,7 +130,7 @@ EXPORTS = (
 )
 VERSION = 101
 STATUS_TIMEOUT_LSTM, STATUS_TIMEOUT_HEAD, STATUS_F16_RANGE = 1, 2, 0x100
-NUM_KERNEL_IDS = 21
+NUM_KERNEL_IDS = 22
 
 _lib = None
 
