@@ -438,6 +438,18 @@ def test_rollout_fused(dev, path, T, N, hidden):
     assert res["launches"] > 0
 
 
+@pytest.mark.parametrize("path", [pytest.param(L.GEMM_TC_2XF16, id="tc2xf16"), pytest.param(L.GEMM_TC_3XTF32, id="tc3xtf32")])
+@pytest.mark.parametrize("T,N", [(100, 4096), (256, 512)])
+def test_rollout_fused_at_reference_length_against_oracle(dev, path, T, N):
+    """the fused rollout against the ORACLE (not kernel-vs-kernel) at BASELINE configs[1]'s full size
+    (4 096 envs x the reference's 100-step rollout, train.py:1763-1766, 1776) and at configs[2]'s 256 steps: the truncating
+    tcgen05 accumulation is the error that grows with T (tools/error_growth.py prints its distribution over time,
+    profiles/r02_error_growth.md)."""
+    res = Hn.run_rollout_case(seed=4000 + N + T, T=T, N=N, hidden=256, device=dev, gemm_path=path)
+    bad = {k: v for k, v in res["errors"].items() if not v <= 1.0}
+    assert not bad, f"scaled errors > 1: {bad} (all: {res['errors']})"
+
+
 @pytest.mark.parametrize("T,N", [(12, 2048), (40, 4096)])
 def test_rollout_persistent_vs_per_step_launches(dev, T, N, monkeypatch):
     """Size-independent property at BASELINE configs[1] scale: the persistent recurrence kernel (one launch, CTAs
