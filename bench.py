@@ -357,9 +357,16 @@ def run_b200(a):
             peak = 72.0                                           # fp32 FFMA: 148 SMs x 128 lanes x 2 x ~1.9 GHz
             note = "fp32 FFMA path: peak = nominal FFMA rate (interim SIMT datapath)"
         ach = flops_per_launch / (dom_ms / dom_n * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_s4_phase_a_and_persist.md);
-        # only valid for the configuration that capture was taken on
-        traffic = 9.01e9 if (dom_name == "rollout_persist_kernel" and (N, T, H, a.gemm) == (4096, 100, 256, "f16")) else None
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of this exact
+        # configuration (profiles/r02_ncu_traffic.json <- tools/ncu_r02.sh); None for a configuration that was not captured
+        traffic = None
+        try:
+            art = json.loads((ROOT / "profiles" / "r02_ncu_traffic.json").read_text())
+            rec = art.get(dom_name, {}).get(f"N{N}_T{T}_H{H}_{a.gemm}")
+            if rec:
+                traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+        except Exception:  # noqa: BLE001
+            traffic = None
         roof = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic, "launches": dom_n, "avg_launch_us": 1e3 * dom_ms / dom_n,
                 "share_of_step": dom_ms / tot_prof, "peak_source": which, "note": note}
