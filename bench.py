@@ -205,6 +205,65 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# NUMA placement of a rank (the e2e leg is bound by host memory / PCIe: pinned staging must live next to the rank's GPU)
+# ------------------------------------------------------------------------------------------------------------------
+
+def bind_to_gpu_numa_node(local):
+    """Pin this process (and, by first touch + a preferred-node policy, its pinned host buffers) to the NUMA node of GPU
+    `local`.  r01: with 8 ranks the end-to-end leg stopped at ~175 GB/s aggregate H2D because every rank staged through
+    whatever node the launcher started it on.  Best effort: returns what it did; never raises."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import ctypes
+
+        import torch
+
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text().strip())
+        info["pci"] = bus
+        cpus = set()
+        if node >= 0:
+            for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        else:
+            # containers often hide the PCI device's numa_node (-1): ask NVML for the GPU's ideal CPUs / memory node instead
+            import pynvml as nv
+
+            nv.nvmlInit()
+            hdl = nv.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            words = (os.cpu_count() + 63) // 64
+            for w, bits in enumerate(nv.nvmlDeviceGetCpuAffinity(hdl, words)):
+                cpus.update(64 * w + b for b in range(64) if (int(bits) >> b) & 1)
+            try:
+                nodes = nv.nvmlDeviceGetMemoryAffinity(hdl, 4, nv.NVML_AFFINITY_SCOPE_NODE)
+                ids = [64 * w + b for w, bits in enumerate(nodes) for b in range(64) if (int(bits) >> b) & 1]
+                node = ids[0] if ids else -1
+            except Exception:  # noqa: BLE001
+                node = -1
+            info["source"] = "nvml"
+            if not cpus:
+                return info
+        use = cpus & os.sched_getaffinity(0)
+        if use:
+            os.sched_setaffinity(0, use)
+            info["cpus"] = len(use)
+        info["numa_node"] = node if node >= 0 else None
+        if node < 0:
+            return info
+        try:                                       # set_mempolicy(MPOL_PREFERRED, {node}): x86-64 syscall 238
+            mask = ctypes.c_ulong(1 << node)
+            rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(65))
+            info["mempolicy"] = "preferred" if rc == 0 else "errno %d" % ctypes.get_errno()
+        except Exception as ex:  # noqa: BLE001
+            info["mempolicy"] = repr(ex)
+    except Exception as ex:  # noqa: BLE001
+        info["error"] = repr(ex)
+    return info
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------------
 
@@ -224,6 +283,7 @@ def run_b200(a):
         raise SystemExit("bench.py --impl b200 needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -396,7 +456,12 @@ def run_b200(a):
     if not a.no_e2e:
         clocks2 = Clocks(local)                            # the e2e loop is a timed region too: keep sampling through it
         clocks2.start()
-        e2e = run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world)
+        # headline e2e: the rollout's randomness is drawn ON THE DEVICE (kbs_generate_rollout_noise -- what jax.random does
+        # inside the reference's jitted rollout), so only the recorded physics state crosses PCIe; e2e_host_noise keeps r01's
+        # form (every PRNG-derived array uploaded from the host: the parity-test configuration)
+        e2e = run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world, device_noise=True)
+        e2e["host_noise_variant"] = run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world, device_noise=False)
+        e2e["numa"] = numa
         ck2 = clocks2.finish()
         allv = sorted(clocks.samples + clocks2.samples)
         ck = {"sm_mhz": allv[len(allv) // 2] if allv else None, "sm_max_mhz": ck_dev["sm_max_mhz"],
@@ -556,7 +621,7 @@ def run_ppo_update(a, dev, world, barrier, max_ranks, peaks, n_traj, steps=8, br
     return res
 
 
-def run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world):
+def run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world, device_noise=True):
     """Same step with every input in pinned host memory.  The recorded state is uploaded in chunks of time steps on
     a copy stream while the compute stream runs kbs_rollout on the chunks already resident (the C-ABI takes plain
     device pointers + T, so a chunk is just an offset view); results come back with a D2H copy."""
@@ -573,14 +638,15 @@ def run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world)
         h2d += t.numel() * t.element_size()
         return h
 
-    for grp in ("state", "noise"):
+    for grp in ("state",) if device_noise else ("state", "noise"):
         host[grp] = {k: pin(v) for k, v in io[grp].items()}
     # what kbs_upload_state moves instead of the whole state: measured by a dry call on the copy stream
     h2d -= sum(v.numel() * v.element_size() for v in io["state"].values())
     h2d += eng.upload_state(host["state"], io["state"])
     torch.cuda.synchronize()
-    for k in ("eps_action", "u_switch", "cmd_mode", "cmd_u6", "cmd_u_arms"):
-        host[k] = pin(io[k])
+    if not device_noise:
+        for k in ("eps_action", "u_switch", "cmd_mode", "cmd_u6", "cmd_u_arms"):
+            host[k] = pin(io[k])
     host["episode"] = {k: pin(v) for k, v in io["episode"].items()}
     outs = {"adv": adv, "tgt": tgt, "total": total, "done": io["done"], "action": io["action"], "log_prob": io["log_prob"],
             "value": io["value"]}
@@ -625,16 +691,20 @@ def run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world)
                 # recorded state: only the 473 of 676 MuJoCo rows the path reads cross PCIe (kbs_upload_state)
                 eng.upload_state({k: v[t0:t1] for k, v in host["state"].items()},
                                  {k: v[t0:t1] for k, v in cur["state"].items()}, stream=copy_s.cuda_stream)
-                for k, v in host["noise"].items():
-                    cur["noise"][k][t0:t1].copy_(v[t0:t1], non_blocking=True)
-                for k in INPUTS:
-                    cur[k][t0:t1].copy_(host[k][t0:t1], non_blocking=True)
+                if not device_noise:
+                    for k, v in host["noise"].items():
+                        cur["noise"][k][t0:t1].copy_(v[t0:t1], non_blocking=True)
+                    for k in INPUTS:
+                        cur[k][t0:t1].copy_(host[k][t0:t1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_s)
                 evs.append(ev)
         for i, t0 in enumerate(range(0, T, chunk)):
             comp_s.wait_event(evs[i])
-            eng.rollout(sub_io(cur, t0, t0 + chunk), N)
+            sub = sub_io(cur, t0, t0 + chunk)
+            if device_noise:
+                eng.generate_rollout_noise(sub, N, seed=1234, step0=(count[0] - 1) * T + t0)
+            eng.rollout(sub, N)
         eng.rewards(cur["state"], io["command"][:T], io["ctrl"], io["done"], rcarry, total=total, n_envs=N)
         eng.gae(io["value"], total, io["done"], io["success"], adv=adv, targets=tgt, n_envs=N)
         io["command"][0].copy_(io["command"][T])
@@ -657,7 +727,9 @@ def run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world)
     ms = max_ranks(e0.elapsed_time(e1)) / k
     assert torch.isfinite(host_out["adv"]).all()
     return {"value": world * N * T / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": ms, "steps": k, "pipeline": f"H2D in {chunk}-step chunks on a copy stream (state: only the 473 of 676 rows the path reads) into "
+            "ms_per_step": ms, "steps": k,
+            "noise": "drawn on the device (kbs_generate_rollout_noise, Philox4x32-10)" if device_noise else "uploaded from the host",
+            "pipeline": f"H2D in {chunk}-step chunks on a copy stream (state: only the 473 of 676 rows the path reads) into "
                         f"double-buffered device inputs, overlapped with kbs_rollout on the chunks already resident"}
 
 

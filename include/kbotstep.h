@@ -403,6 +403,17 @@ typedef struct kbs_rollout_io {
 
 int kbs_rollout(kbs_handle* h, const kbs_rollout_io* io, int64_t n_envs, void* stream);
 
+/* Replaces: the jax.random draws the reference makes ON THE DEVICE during a rollout -- observation noise (train.py:1160, 1162,
+ * 1176, 1194), the action sample (train.py:1564), the command resampling (train.py:725-737, 752-753, 782-783) -- for callers
+ * that do not need bit parity with JAX's threefry streams (parity mode hands these arrays to kbs_rollout explicitly).
+ * Counter-based Philox4x32-10: value (row r, step step0 + t, env e) depends only on (seed, r, step0 + t, e), so any split of a
+ * rollout into calls gives the same numbers.  Fills, for T steps (any pointer may be NULL = skipped):
+ *   noise->eps_jpos, eps_jvel [T][20][ld] U(-1,1); eps_gyro, eps_pg [T][3][ld] N(0,1); eps_action [T][20][ld] N(0,1);
+ *   u_switch [T][ld] U[0,1); cmd_mode int32 [T][ld] in 0..5; cmd_u6 [T][6][ld], cmd_u_arms [T][10][ld] U[0,1). */
+int kbs_generate_rollout_noise(kbs_handle* h, uint64_t seed, int64_t step0, const kbs_noise_view* noise, float* eps_action,
+                               float* u_switch, int32_t* cmd_mode, float* cmd_u6, float* cmd_u_arms, int64_t T, int64_t ld,
+                               int64_t n_envs, void* stream);
+
 /* Replaces: get_ppo_variables -> xax.scan(_ppo_scan_fn) (train.py:1435-1524): on a STORED trajectory, re-run actor and
  * critic step by step from `*_carry`, carries reset to initial where done[t] (train.py:1502-1506), and return what
  * ksim.PPOVariables holds.  The observations are the stored ones (Trajectory.obs): actor_obs [T][65][ld] is the

@@ -126,7 +126,7 @@ EXPORTS = (
     "kbs_torque", "kbs_terminate", "kbs_rewards", "kbs_gae", "kbs_policy_step", "kbs_rollout", "kbs_ppo_variables",
     "kbs_launch_count", "kbs_device_status", "kbs_mirror_observations", "kbs_mirror_joints", "kbs_upload_state", "kbs_com_distance", "kbs_ppo_loss_default_params", "kbs_ppo_loss", "kbs_ppo_grad", "kbs_adam_step", "kbs_torque_substeps", "kbs_profile_enable", "kbs_profile_read", "kbs_kernel_name", "kbs_debug_tc_gates", "kbs_debug_tc_trace", "kbs_debug_tc_trace_attach",
     "kbs_adamw_default_params", "kbs_adamw_step", "kbs_grad_norm", "kbs_scratch_lock", "kbs_actuator_rand_default_params",
-    "kbs_sample_actuator_randomization", "kbs_device_status_reset", "kbs_ppo_grad_set_events",
+    "kbs_sample_actuator_randomization", "kbs_device_status_reset", "kbs_ppo_grad_set_events", "kbs_generate_rollout_noise",
 )
 VERSION = 101
 STATUS_TIMEOUT_LSTM, STATUS_TIMEOUT_HEAD, STATUS_F16_RANGE = 1, 2, 0x100
@@ -165,6 +165,7 @@ def load() -> C.CDLL:
     lib.kbs_adamw_default_params.argtypes = [P(KbsAdamwParams)]
     lib.kbs_adamw_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, P(KbsAdamwParams), _vp, _vp, _i64, _vp]
     lib.kbs_ppo_grad_set_events.argtypes = [_vp, _vp]
+    lib.kbs_generate_rollout_noise.argtypes = [_vp, C.c_uint64, _i64, P(KbsNoiseView), _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]
     lib.kbs_grad_norm.argtypes = [_vp, _vp, _i64, _vp, _vp]
     lib.kbs_scratch_lock.argtypes = [_vp, C.c_int]
     lib.kbs_device_status_reset.argtypes = [_vp]

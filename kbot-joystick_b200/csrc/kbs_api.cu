@@ -813,6 +813,19 @@ int kbs_ppo_variables(kbs_handle* h, const kbs_ppo_io* io, int64_t n, void* stre
                                 io->critic_mirror_loss_scale, T, ld, n, st);
 }
 
+int kbs_generate_rollout_noise(kbs_handle* h, uint64_t seed, int64_t step0, const kbs_noise_view* noise, float* eps_action,
+                               float* u_switch, int32_t* cmd_mode, float* cmd_u6, float* cmd_u_arms, int64_t T, int64_t ld, int64_t n,
+                               void* stream) {
+  REQ(h);
+  if (T <= 0 || T > 65535) return KBS_E_SHAPE;
+  int rc = check_ld(ld, n);
+  if (rc) return rc;
+  if (noise) { AL(noise->eps_jpos); AL(noise->eps_jvel); AL(noise->eps_gyro); AL(noise->eps_pg); }
+  AL(eps_action); AL(u_switch); AL(cmd_mode); AL(cmd_u6); AL(cmd_u_arms);
+  return kbs_launch_rollout_noise(h, seed, step0, noise, eps_action, u_switch, cmd_mode, cmd_u6, cmd_u_arms, T, ld, n,
+                                  (cudaStream_t)stream);
+}
+
 int kbs_adamw_default_params(kbs_adamw_params* p) {
   REQ(p);
   p->lr = 5e-4f; p->b1 = 0.9; p->b2 = 0.999; p->eps = 1e-8f;   /* train.py:95-98, optax.adamw defaults */

@@ -145,6 +145,8 @@ int kbs_launch_mirror_loss(kbs_handle* h, const float* mean, const float* mean_m
                            cudaStream_t st);
 int kbs_launch_actuator_rand(kbs_handle* h, const kbs_actuator_rand_params& rp, const float* u, const uint8_t* reset,
                              const kbs_episode_view& ep, int64_t ld, int64_t n, cudaStream_t st);
+int kbs_launch_rollout_noise(kbs_handle* h, uint64_t seed, int64_t step0, const kbs_noise_view* nz, float* eps_action, float* u_switch,
+                             int32_t* cmd_mode, float* cmd_u6, float* cmd_u_arms, int64_t T, int64_t ld, int64_t n, cudaStream_t st);
 int kbs_launch_terminate(kbs_handle* h, const kbs_state_view& s, int32_t* codes, uint8_t* done, uint8_t* success,
                          float* pre, int64_t n, cudaStream_t st, int64_t T = 1);
 int kbs_launch_rewards(kbs_handle* h, const kbs_traj_view& tr, const kbs_reward_carry& carry, float* total,

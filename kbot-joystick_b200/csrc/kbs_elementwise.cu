@@ -518,6 +518,72 @@ actuator_rand_kernel(const __grid_constant__ kbs_params P, const kbs_actuator_ra
 }
 
 // =====================================================================================================
+// Device-side randomness of a rollout (kbs_generate_rollout_noise): counter-based Philox4x32-10.
+// counter = (step lo, step hi, env group, row), key = seed: 4 x 32 bits per call = the 4 consecutive envs of a float4.
+// =====================================================================================================
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+struct NoiseRows {
+  float* base[9];        // eps_jpos, eps_jvel, eps_gyro, eps_pg, eps_action, u_switch, cmd_mode (as int32), cmd_u6, cmd_u_arms
+  int rows[9];           // rows per step of each array
+  int kind[9];           // 0 U(-1,1), 1 N(0,1), 2 U[0,1), 3 int 0..5
+  int first[10];         // prefix sums: global row index of each array's row 0
+};
+__global__ void __launch_bounds__(kThreads)
+rollout_noise_kernel(const __grid_constant__ NoiseRows R, uint64_t seed, int64_t step0, int64_t ld, int64_t n) {
+  const int64_t grp = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  const int64_t n0 = grp * 4;
+  if (n0 >= n) return;
+  const int gr = blockIdx.y;                       // global row
+  int a = 0;
+#pragma unroll
+  for (int i = 1; i < 9; ++i) a += (gr >= R.first[i]) ? 1 : 0;
+  if (!R.base[a]) return;
+  const int row = gr - R.first[a];
+  const int64_t t = blockIdx.z;
+  const uint64_t step = uint64_t(step0 + t);
+  const uint4 x = philox4x32_10(make_uint4(uint32_t(step), uint32_t(step >> 32), uint32_t(grp), uint32_t(gr)),
+                                make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+  float v[4];
+  const int kind = R.kind[a];
+  if (kind == 1) {
+    // Box-Muller on (w0, w1) and (w2, w3): u1 in (0, 1], u2 in [0, 1)
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const float u1 = (float(w[2 * p] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+      const float u2 = float(w[2 * p + 1] >> 8) * (1.0f / 16777216.0f);
+      const float rr = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      v[2 * p] = rr * cs; v[2 * p + 1] = rr * sn;
+    }
+  } else {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float u = float(w[l] >> 8) * (1.0f / 16777216.0f);      // [0, 1)
+      v[l] = kind == 0 ? 2.0f * u - 1.0f : u;
+    }
+  }
+  float* dst = R.base[a] + (t * R.rows[a] + row) * ld + n0;
+  if (kind == 3) {
+    int4 m;
+    m.x = min(int(v[0] * 6.0f), 5); m.y = min(int(v[1] * 6.0f), 5); m.z = min(int(v[2] * 6.0f), 5); m.w = min(int(v[3] * 6.0f), 5);
+    *reinterpret_cast<int4*>(dst) = m;
+  } else {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// =====================================================================================================
 // O12: COMDistanceObservation (train.py:509-659): >= 3 distinct contact.geom2 values -> distance between the centroid of the
 // convex hull of the floor-contact points (xy; non-floor rows become the origin and stay in the set, as written) and
 // subtree_com[2].xy, else -1.  Andrew's monotone chain exactly as the reference runs it (lexicographic stable sort, pop
@@ -1465,6 +1531,23 @@ int kbs_launch_actuator_rand(kbs_handle* h, const kbs_actuator_rand_params& rp, 
                              const kbs_episode_view& ep, int64_t ld, int64_t n, cudaStream_t st) {
   KBS_LAUNCH(h, KBS_K_TORQUE, st,
              (actuator_rand_kernel<<<dim3(groups4(n), KBS_NUM_JOINTS), kThreads, 0, st>>>(h->p, rp, u, reset, ep, ld, n)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+int kbs_launch_rollout_noise(kbs_handle* h, uint64_t seed, int64_t step0, const kbs_noise_view* nz, float* eps_action, float* u_switch,
+                             int32_t* cmd_mode, float* cmd_u6, float* cmd_u_arms, int64_t T, int64_t ld, int64_t n, cudaStream_t st) {
+  NoiseRows R{};
+  float* bases[9] = {nz ? const_cast<float*>(nz->eps_jpos) : nullptr, nz ? const_cast<float*>(nz->eps_jvel) : nullptr,
+                     nz ? const_cast<float*>(nz->eps_gyro) : nullptr, nz ? const_cast<float*>(nz->eps_pg) : nullptr, eps_action, u_switch,
+                     reinterpret_cast<float*>(cmd_mode), cmd_u6, cmd_u_arms};
+  const int rows[9] = {20, 20, 3, 3, 20, 1, 1, 6, 10};
+  const int kind[9] = {0, 0, 1, 1, 1, 2, 3, 2, 2};
+  int acc = 0;
+  for (int i = 0; i < 9; ++i) { R.base[i] = bases[i]; R.rows[i] = rows[i]; R.kind[i] = kind[i]; R.first[i] = acc; acc += rows[i]; }
+  R.first[9] = acc;
+  KBS_LAUNCH(h, KBS_K_COMMAND, st,
+             (rollout_noise_kernel<<<dim3(groups4(n), unsigned(acc), unsigned(T)), kThreads, 0, st>>>(R, seed, step0, ld, n)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

@@ -396,6 +396,17 @@ class KbotStep:
         L.check(self.lib.kbs_ppo_variables(self._h, C.byref(io), n_envs or ld, _stream()), "kbs_ppo_variables")
         return out
 
+    def generate_rollout_noise(self, io: dict, n_envs: int, seed: int, step0: int = 0) -> None:
+        """Fill the randomness of a kbs_rollout_io (io["noise"], eps_action, u_switch, cmd_mode, cmd_u6, cmd_u_arms) on the device
+        with counter-based Philox draws (kbs_generate_rollout_noise): what jax.random does inside the reference's jitted rollout.
+        Parity tests pass these arrays explicitly instead."""
+        ld = io["u_switch"].shape[-1]
+        T = io["u_switch"].shape[0]
+        nv = _view(L.KbsNoiseView, NOISE_ROWS, io.get("noise"))
+        L.check(self.lib.kbs_generate_rollout_noise(self._h, seed, step0, C.byref(nv), L.ptr(io.get("eps_action")), L.ptr(io.get("u_switch")),
+                                                    L.ptr(io.get("cmd_mode")), L.ptr(io.get("cmd_u6")), L.ptr(io.get("cmd_u_arms")), T, ld,
+                                                    n_envs, _stream()), "kbs_generate_rollout_noise")
+
     def rollout(self, io: dict, n_envs: int) -> None:
         """io: tensors named as the fields of kbs_rollout_io (state/noise/episode are nested dicts)."""
         r = L.KbsRolloutIO()

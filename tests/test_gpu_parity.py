@@ -924,6 +924,87 @@ def test_rollout_phase_a_chunks_on_aux_stream(dev, monkeypatch):
         assert torch.equal(outs[0][k], outs[1][k]), k
 
 
+def test_generate_rollout_noise_statistics_and_counter_property(eng, dev):
+    """kbs_generate_rollout_noise (device-side Philox draws for callers that do not need JAX-threefry bit parity): ranges and
+    moments of every array, determinism, and the counter property -- (seed, row, step, env) alone decides a value, so any
+    split of a rollout into calls gives the same numbers; a rollout then runs on them."""
+    T, N = 16, 4096
+    ld = N
+
+    def bufs():
+        f = dict(device=dev, dtype=torch.float32)
+        return {"noise": {"eps_jpos": torch.full((T, 20, ld), 9.0, **f), "eps_jvel": torch.full((T, 20, ld), 9.0, **f),
+                          "eps_gyro": torch.full((T, 3, ld), 9.0, **f), "eps_pg": torch.full((T, 3, ld), 9.0, **f)},
+                "eps_action": torch.full((T, 20, ld), 9.0, **f), "u_switch": torch.full((T, ld), 9.0, **f),
+                "cmd_mode": torch.full((T, ld), 9, device=dev, dtype=torch.int32), "cmd_u6": torch.full((T, 6, ld), 9.0, **f),
+                "cmd_u_arms": torch.full((T, 10, ld), 9.0, **f)}
+
+    a = bufs()
+    eng.generate_rollout_noise(a, N, seed=1234, step0=0)
+    for k in ("eps_jpos", "eps_jvel"):
+        x = a["noise"][k]
+        assert float(x.min()) >= -1.0 and float(x.max()) < 1.0
+        assert abs(float(x.mean())) < 5e-3 and abs(float(x.var()) - 1.0 / 3.0) < 5e-3
+    for x in (a["noise"]["eps_gyro"], a["noise"]["eps_pg"], a["eps_action"]):
+        assert torch.isfinite(x).all()
+        assert abs(float(x.mean())) < 1e-2 and abs(float(x.var()) - 1.0) < 2e-2
+        assert abs(float((x ** 4).mean()) - 3.0) < 0.15                     # Gaussian kurtosis
+        assert 4.0 < float(x.abs().max()) < 7.0                             # tails present, Box-Muller bounded by sqrt(-2 ln 2^-24)
+    for k in ("u_switch", "cmd_u6", "cmd_u_arms"):
+        assert float(a[k].min()) >= 0.0 and float(a[k].max()) < 1.0 and abs(float(a[k].mean()) - 0.5) < 5e-3
+    m = a["cmd_mode"]
+    assert int(m.min()) == 0 and int(m.max()) == 5
+    freq = torch.bincount(m.flatten(), minlength=6).float() / m.numel()
+    assert float((freq - 1.0 / 6.0).abs().max()) < 5e-3
+    # rows / steps / envs are decorrelated
+    g = a["eps_action"]
+    assert abs(float((g[0, 0] * g[0, 1]).mean())) < 0.05 and abs(float((g[0, 0] * g[1, 0]).mean())) < 0.05
+    assert abs(float((g[0, 0, :-1] * g[0, 0, 1:]).mean())) < 0.05
+    # deterministic, and the counter property: steps 5..15 regenerated on their own are the same numbers
+    b = bufs()
+    eng.generate_rollout_noise(b, N, seed=1234, step0=0)
+    assert all(torch.equal(a["noise"][k], b["noise"][k]) for k in a["noise"]) and torch.equal(a["cmd_mode"], b["cmd_mode"])
+    T2 = T - 5
+    c = {k: (v[:T2] if k != "noise" else {kk: vv[:T2] for kk, vv in v.items()}) for k, v in bufs().items()}
+    c = {k: (v.contiguous() if k != "noise" else {kk: vv.contiguous() for kk, vv in v.items()}) for k, v in c.items()}
+    eng.generate_rollout_noise(c, N, seed=1234, step0=5)
+    assert torch.equal(c["eps_action"], a["eps_action"][5:]) and torch.equal(c["noise"]["eps_pg"], a["noise"]["eps_pg"][5:])
+    assert torch.equal(c["cmd_u_arms"], a["cmd_u_arms"][5:]) and torch.equal(c["cmd_mode"], a["cmd_mode"][5:])
+    d = bufs()
+    eng.generate_rollout_noise(d, N, seed=1235, step0=0)
+    assert not torch.equal(d["eps_action"], a["eps_action"])
+    # ragged n: nothing beyond ld is touched, envs < n are filled
+    e2 = bufs()
+    eng.generate_rollout_noise(e2, 4093, seed=7, step0=0)
+    assert float(e2["u_switch"][:, :4093].max()) < 1.0
+
+
+def test_rollout_on_device_generated_noise(dev):
+    """The fused rollout consuming kbs_generate_rollout_noise output: the e2e configuration of bench.py (no noise upload)."""
+    T, N = 6, 300
+    b = Batch(77, T, N, dev)
+    e, wa, wc = Hn.make_engine(gemm_path=L.GEMM_TC_2XF16, device=dev)
+    io = Hn.rollout_buffers(b, 256, 2, True)
+    io["noise"] = {k: torch.empty_like(v) for k, v in io["noise"].items()}
+    for k in ("eps_action", "u_switch", "cmd_mode", "cmd_u6", "cmd_u_arms"):
+        io[k] = torch.empty_like(io[k])
+    e.generate_rollout_noise(io, N, seed=99, step0=0)
+    e.rollout(io, N)
+    torch.cuda.synchronize()
+    assert e.device_status() == 0
+    # the oracle on the SAME device-generated randomness: parity holds whatever produced the noise
+    nz = {k: S(v, N, (v.shape[1],)) for k, v in io["noise"].items()}
+    nz["eps_action"] = S(io["eps_action"], N, (20,))
+    cr = {"u_switch": S(io["u_switch"], N), "mode": S(io["cmd_mode"], N), "u6": S(io["cmd_u6"], N, (6,)), "u_arms": S(io["cmd_u_arms"], N, (10,))}
+    p = O.OracleParams()
+    carry = {"actor": np.zeros((N, 2, 2, 256), np.float32), "critic": np.zeros((N, 2, 2, 256), np.float32),
+             "lpf_params": np.zeros((N, 20), np.float32)}
+    ref = O.rollout_control_steps(wa, wc, b.np["state"], nz, b.np["episode"], cr, b.cmd0_np, carry, np.zeros((N, 3), np.float32), p)
+    errs = Hn.compare_rollout(io, ref, N, True)
+    assert all(v <= 1.0 for v in errs.values()), errs
+    e.close()
+
+
 def test_error_codes(eng, dev):
     lib = L.load()
     assert lib.kbs_version() == 101
