@@ -462,6 +462,27 @@ def run_b200(a):
         e2e = run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world, device_noise=True)
         e2e["host_noise_variant"] = run_e2e(a, eng, io, rcarry, total, adv, tgt, dev, barrier, max_ranks, world, device_noise=False)
         e2e["numa"] = numa
+        # the roofline of the end-to-end leg is the host link: one large pinned H2D copy per rank, all ranks at once
+        try:
+            hb = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+            db = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            db.copy_(hb, non_blocking=True)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(8):
+                db.copy_(hb, non_blocking=True)
+            c1.record()
+            barrier()
+            link = 8 * hb.numel() / (max_ranks(c0.elapsed_time(c1)) * 1e-3) / 1e9
+            e2e["host_link"] = {"h2d_gbs_per_gpu_all_ranks_copying": link,
+                                "e2e_h2d_gbs_per_gpu": e2e["h2d_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9,
+                                "note": "plain 256 MB pinned cudaMemcpyAsync H2D on every rank simultaneously: what the platform's "
+                                        "PCIe / host-memory path gives each GPU at this rank count"}
+            e2e["host_link"]["frac"] = e2e["host_link"]["e2e_h2d_gbs_per_gpu"] / link
+            del hb, db
+        except Exception as ex:  # noqa: BLE001
+            e2e["host_link"] = {"error": repr(ex)}
         ck2 = clocks2.finish()
         allv = sorted(clocks.samples + clocks2.samples)
         ck = {"sm_mhz": allv[len(allv) // 2] if allv else None, "sm_max_mhz": ck_dev["sm_max_mhz"],
