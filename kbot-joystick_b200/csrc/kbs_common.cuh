@@ -250,6 +250,7 @@ int kbs_tc_soa_to_tn(kbs_handle* h, const KbsTnPlan& plan, const float* soa, int
 struct KbsBpttNet {
   char* dG; const float* save_g; const float* c_hist; const float* dh_top; float* dx; char* dx0; float* dc; unsigned int* flags;
   char* tn_dG[KBS_MAX_DEPTH];      // optional: per layer, the K = row re-pack of dG (written by the kernel's transposer CTAs)
+  const float* dv; const float* w_out;   // dh_top == nullptr: one-row output layer, dh_top = dv [T * n] x w_out [H] (rank 1)
 };
 struct KbsBpttArgs {
   KbsBpttNet net[2]; int nets; int64_t n, ld, T; const uint8_t* done; float gscale;

@@ -1358,6 +1358,8 @@ struct BNet {
   const float* save_g;             // forward pass: [T][depth][4] x np*H activated gates (FB)
   const float* c_hist;             // forward pass: [depth][T + 1] x np*H (FB): slot s = the cell state step s read
   const float* dh_top;             // [T * n][H] row-major: gradient wrt the top layer's output (from the output head)
+  const float* dv;                 // instead of dh_top for a one-row output layer (the critic): d loss / d out [T * n] ...
+  const float* w_out;              // ... and that row [H]: dh_top = dv w_out is formed in the epilogue
   float* dx;                       // [depth][T] x np*H (FB): gradient wrt the input of layer l >= 1 at step s
   char* dx0;                       // [T] x sbb: the same for layer 0, as split operand (scaled by gscale)
   float* dc;                       // [depth] x np*H (FB): gradient wrt the cell carry, running (zeroed by the host)
@@ -1732,7 +1734,12 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
         ld8fb(sg, gi, false); ld8fb(sg + npH, gf, false); ld8fb(sg + 2 * npH, gg, false); ld8fb(sg + 3 * npH, go, false);
         ld8fb(cin, ci, false);
         ld8fb(dcp, dcr, true);
-        if (top) {
+        if (top && N.dv) {
+          const float d = __ldg(N.dv + s * size_t(args.n) + size_t(R));
+          const float4 a = __ldg(reinterpret_cast<const float4*>(N.w_out + u)), b = __ldg(reinterpret_cast<const float4*>(N.w_out + u + 4));
+          dhi[0] = d * a.x; dhi[1] = d * a.y; dhi[2] = d * a.z; dhi[3] = d * a.w;
+          dhi[4] = d * b.x; dhi[5] = d * b.y; dhi[6] = d * b.z; dhi[7] = d * b.w;
+        } else if (top) {
           const float4 a = __ldg(reinterpret_cast<const float4*>(dxu + u)), b = __ldg(reinterpret_cast<const float4*>(dxu + u + 4));
           dhi[0] = a.x; dhi[1] = a.y; dhi[2] = a.z; dhi[3] = a.w; dhi[4] = b.x; dhi[5] = b.y; dhi[6] = b.z; dhi[7] = b.w;
         } else {
@@ -3487,6 +3494,8 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
     BNet& N = a.net[k];
     for (int l = 0; l < depth; ++l) N.w_bwd[l] = reinterpret_cast<const char*>(Nn.tc_bwd_image64) + bwd_layer_bytes(h) * l;
     N.dG = b.net[k].dG; N.save_g = b.net[k].save_g; N.c_hist = b.net[k].c_hist; N.dh_top = b.net[k].dh_top;
+    N.dv = b.net[k].dv; N.w_out = b.net[k].w_out;
+    if (!N.dh_top && !(N.dv && N.w_out)) return KBS_E_NULL;
     N.dx = b.net[k].dx; N.dx0 = b.net[k].dx0; N.dc = b.net[k].dc; N.flags = b.net[k].flags;
     for (int l = 0; l < depth; ++l) N.tn_dG[l] = b.net[k].tn_dG[l];
   }

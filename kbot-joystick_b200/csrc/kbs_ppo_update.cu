@@ -310,6 +310,10 @@ actor_head_fwd_bwd_kernel(const __grid_constant__ kbs_params P, kbs_ppo_loss_par
 
 // The same head with one WARP per env (lane j = joint j, log-prob / entropy by warp shuffles): the one-thread-per-env form
 // above was 3.5 ms of an 18 ms update (512 threads walking 2 x T steps x 20 joints of libm math and strided loads).
+// The steps are taken in chunks of kHC: every input of a chunk is loaded first (none depends on the filter's recurrence), then
+// the chunk's steps run out of registers -- one L2 round trip per chunk instead of per step (there are only ~3 warps per SM at
+// 512 envs, so nothing else hides the latency: 0.24 -> 0.07 ms per 512 x 100).  Same operations in the same order as before.
+constexpr int kHC = 10;
 __global__ void __launch_bounds__(128)
 actor_head_fwd_bwd_warp_kernel(const __grid_constant__ kbs_params P, kbs_ppo_loss_params L, const float* __restrict__ out,
                                const float* __restrict__ actor_obs, const float* __restrict__ action,
@@ -323,62 +327,97 @@ actor_head_fwd_bwd_warp_kernel(const __grid_constant__ kbs_params P, kbs_ppo_los
   const bool act = j < KBS_NUM_JOINTS;
   const int jj = act ? j : 0;
   constexpr float kHalfLog2Pi = 0.918938533204672742f;
+  const float jb = P.joint_bias[jj];
   float y = (act && lpf0) ? lpf0[jj * ld + e] : 0.0f;
-  for (int64_t t = 0; t < T; ++t) {
-    const float* o = out + (t * n + e) * 64;
-    float tz = 0.0f, tl = 0.0f;
-    if (act) {
-      const float sraw = o[KBS_NUM_JOINTS + j];
-      const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
-      const float sd = fminf((sp + P.min_std) * P.var_scale, P.max_std);
-      float m = o[j] + P.joint_bias[j];
-      if (j >= 10) m = m + actor_obs[(t * KBS_ACTOR_OBS + 55 + (j - 10)) * ld + e];
-      y = y + P.lpf_alpha * (m - y);
-      const int64_t so = (t * KBS_NUM_JOINTS + j) * ld + e;
-      y_s[so] = y;
-      sd_s[so] = sd;
-      const float z = (action[so] - y) / sd;
-      tz = -0.5f * z * z - kHalfLog2Pi;
-      tl = logf(sd);
+  for (int64_t t0 = 0; t0 < T; t0 += kHC) {
+    float om[kHC], os[kHC], ob[kHC], ac[kHC];
+    uint8_t dn[kHC];
+#pragma unroll
+    for (int i = 0; i < kHC; ++i) {
+      const int64_t t = (t0 + i < T) ? t0 + i : T - 1;
+      const float* o = out + (t * n + e) * 64;
+      om[i] = o[jj];
+      os[i] = o[KBS_NUM_JOINTS + jj];
+      ob[i] = j >= 10 && act ? actor_obs[(t * KBS_ACTOR_OBS + 55 + (j - 10)) * ld + e] : 0.0f;
+      ac[i] = action[(t * KBS_NUM_JOINTS + jj) * ld + e];
+      dn[i] = done[t * ld + e];
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) { tz += __shfl_xor_sync(0xffffffffu, tz, s); tl += __shfl_xor_sync(0xffffffffu, tl, s); }
-    if (j == 0) {
-      log_prob[t * ld + e] = tz - tl;
-      entropy[t * ld + e] = tl + float(KBS_NUM_JOINTS) * (0.5f + kHalfLog2Pi);
+    for (int i = 0; i < kHC; ++i) {
+      const int64_t t = t0 + i;
+      if (t >= T) break;
+      float tz = 0.0f, tl = 0.0f;
+      if (act) {
+        const float sraw = os[i];
+        const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
+        const float sd = fminf((sp + P.min_std) * P.var_scale, P.max_std);
+        float m = om[i] + jb;
+        if (j >= 10) m = m + ob[i];
+        y = y + P.lpf_alpha * (m - y);
+        const int64_t so = (t * KBS_NUM_JOINTS + j) * ld + e;
+        y_s[so] = y;
+        sd_s[so] = sd;
+        const float z = (ac[i] - y) / sd;
+        tz = -0.5f * z * z - kHalfLog2Pi;
+        tl = logf(sd);
+      }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) { tz += __shfl_xor_sync(0xffffffffu, tz, s); tl += __shfl_xor_sync(0xffffffffu, tl, s); }
+      if (j == 0) {
+        log_prob[t * ld + e] = tz - tl;
+        entropy[t * ld + e] = tl + float(KBS_NUM_JOINTS) * (0.5f + kHalfLog2Pi);
+      }
+      if (dn[i]) y = 0.0f;
     }
-    if (done[t * ld + e]) y = 0.0f;
   }
   __syncwarp();
   const float inv = 1.0f / (float(T) * float(n));
   float gy = 0.0f;
-  for (int64_t t = T - 1; t >= 0; --t) {
-    const float lr = log_prob[t * ld + e] - old_lp[t * ld + e];
-    const float lrc = fminf(fmaxf(lr, -L.log_clip_value), L.log_clip_value);
-    const float r = expf(lrc);
-    const float a = adv[t * ld + e];
-    const float dr = (fabsf(lr) <= L.log_clip_value) ? r : 0.0f;
-    const bool inside = r >= 1.0f - L.clip_param && r <= 1.0f + L.clip_param;
-    const float rc = fminf(fmaxf(r, 1.0f - L.clip_param), 1.0f + L.clip_param);
-    const float dpol = (inside || r * a < rc * a) ? a * dr : 0.0f;
-    const float glp = -inv * dpol, gent = -inv * L.entropy_coef;
-    const float keep = done[t * ld + e] ? 0.0f : 1.0f;
-    const float* o = out + (t * n + e) * 64;
-    float* d = dout + (t * n + e) * 64;
-    if (act) {
-      const int64_t so = (t * KBS_NUM_JOINTS + j) * ld + e;
-      const float sd = sd_s[so], yy = y_s[so];
-      const float z = (action[so] - yy) / sd;
-      const float dmu = glp * z / sd;
-      const float dsd = (glp * (z * z - 1.0f) + gent) / sd;
-      const float sraw = o[KBS_NUM_JOINTS + j];
-      const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
-      const bool clamped = (sp + P.min_std) * P.var_scale > P.max_std;
-      d[KBS_NUM_JOINTS + j] = clamped ? 0.0f : dsd * P.var_scale * sigm(sraw);
-      gy = dmu + (1.0f - P.lpf_alpha) * keep * gy;
-      d[j] = P.lpf_alpha * gy;
+  for (int64_t t1 = T; t1 > 0; t1 -= kHC) {             // chunk = steps t1 - 1 down to t1 - kHC
+    float lp[kHC], ol[kHC], av[kHC], sdv[kHC], yv[kHC], ac[kHC], os[kHC];
+    uint8_t dn[kHC];
+#pragma unroll
+    for (int i = 0; i < kHC; ++i) {
+      const int64_t t = (t1 - 1 - i >= 0) ? t1 - 1 - i : 0;
+      const int64_t so = (t * KBS_NUM_JOINTS + jj) * ld + e;
+      lp[i] = log_prob[t * ld + e];
+      ol[i] = old_lp[t * ld + e];
+      av[i] = adv[t * ld + e];
+      dn[i] = done[t * ld + e];
+      sdv[i] = sd_s[so];
+      yv[i] = y_s[so];
+      ac[i] = action[so];
+      os[i] = out[(t * n + e) * 64 + KBS_NUM_JOINTS + jj];
     }
-    if (j < 24) d[2 * KBS_NUM_JOINTS + j] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kHC; ++i) {
+      const int64_t t = t1 - 1 - i;
+      if (t < 0) break;
+      const float lr = lp[i] - ol[i];
+      const float lrc = fminf(fmaxf(lr, -L.log_clip_value), L.log_clip_value);
+      const float r = expf(lrc);
+      const float a = av[i];
+      const float dr = (fabsf(lr) <= L.log_clip_value) ? r : 0.0f;
+      const bool inside = r >= 1.0f - L.clip_param && r <= 1.0f + L.clip_param;
+      const float rc = fminf(fmaxf(r, 1.0f - L.clip_param), 1.0f + L.clip_param);
+      const float dpol = (inside || r * a < rc * a) ? a * dr : 0.0f;
+      const float glp = -inv * dpol, gent = -inv * L.entropy_coef;
+      const float keep = dn[i] ? 0.0f : 1.0f;
+      float* d = dout + (t * n + e) * 64;
+      if (act) {
+        const float sd = sdv[i], yy = yv[i];
+        const float z = (ac[i] - yy) / sd;
+        const float dmu = glp * z / sd;
+        const float dsd = (glp * (z * z - 1.0f) + gent) / sd;
+        const float sraw = os[i];
+        const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
+        const bool clamped = (sp + P.min_std) * P.var_scale > P.max_std;
+        d[KBS_NUM_JOINTS + j] = clamped ? 0.0f : dsd * P.var_scale * sigm(sraw);
+        gy = dmu + (1.0f - P.lpf_alpha) * keep * gy;
+        d[j] = P.lpf_alpha * gy;
+      }
+      if (j < 24) d[2 * KBS_NUM_JOINTS + j] = 0.0f;
+    }
   }
 }
 
@@ -472,6 +511,46 @@ critic_head_fwd_bwd_kernel(kbs_ppo_loss_params L, const float* __restrict__ out,
   d[0] = L.value_loss_coef * dval / (float(T) * float(n));
 #pragma unroll
   for (int j = 1; j < 64; ++j) d[j] = 0.0f;
+}
+
+// Critic head of the persistent update in one pass: value = w_out . h_top + b_out (the output layer has ONE row: a GEMV, not
+// the padded 64-column GEMM), the clipped value loss' gradient, dout row (column 0 = d loss / d value: the A operand of the
+// dW_out GEMM) and dv [T * n] -- the backward kernel forms dh_top = dv w_out itself (rank 1), so neither `out` nor `dh_top` of
+// the critic exist.  One warp per (t, env) row.
+__global__ void __launch_bounds__(256)
+critic_value_head_kernel(kbs_ppo_loss_params L, const float* __restrict__ h_top, const float* __restrict__ w_out,
+                         const float* __restrict__ b_out, const float* __restrict__ old_values, const float* __restrict__ targets,
+                         float* __restrict__ values, float* __restrict__ dout, float* __restrict__ dv, int H, int64_t T, int64_t ld,
+                         int64_t n) {
+  const int64_t idx = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (idx >= T * n) return;
+  const int lane = threadIdx.x & 31;
+  const float* hr = h_top + idx * H;
+  float acc = 0.0f;
+  for (int c = lane * 4; c < H; c += 128) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(hr + c)), w = __ldg(reinterpret_cast<const float4*>(w_out + c));
+    acc = fmaf(a.x, w.x, acc); acc = fmaf(a.y, w.y, acc); acc = fmaf(a.z, w.z, acc); acc = fmaf(a.w, w.w, acc);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  const int64_t t = idx / n, e = idx - t * n;
+  const float v = acc + b_out[0];
+  float dval = 0.0f;
+  if (lane == 0) {
+    values[t * ld + e] = v;
+    const float tgt = targets[t * ld + e];
+    const float err = tgt - v;
+    dval = -err;                                              // d (0.5 err^2) / d v
+    if (L.use_clipped_value_loss) {
+      const float vo = old_values[t * ld + e];
+      const float d = v - vo;
+      const float errc = tgt - (vo + fminf(fmaxf(d, -L.clip_param), L.clip_param));
+      if (fabsf(d) > L.clip_param) dval = (err * err > errc * errc) ? -err : 0.0f;   // the clipped branch has no gradient
+    }
+    dval = L.value_loss_coef * dval / (float(T) * float(n));
+    dv[idx] = dval;
+  }
+  reinterpret_cast<float2*>(dout + idx * 64)[lane] = make_float2(dval, 0.0f);       // lanes > 0 hold 0
 }
 
 __global__ void __launch_bounds__(kT)
@@ -855,6 +934,44 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
   if (wide_cfg < 0) { const char* e = getenv("KBS_PPO_FWD_WIDE"); wide_cfg = e ? atoi(e) : 0; }
   const bool narrow = !wide_cfg && kbs_tc_fwd_save_available(h, n, T);
   bool xh_transposed = false;
+  const int kbH = H / 32, kb4 = 4 * H / 32;
+  const int64_t kb_used = (T * np + 31) / 32;
+  // ---- side stream: everything that does not depend on this call's forward pass runs beside it (the two persistent kernels
+  // occupy one SM per work item of a slot -- 128 of 148 at 512 trajectories -- and the ~20 small launches below would
+  // otherwise sit between them on the critical path): the observations re-packed with K = row (B operand of the dW_in GEMM),
+  // W_out^T, the backward kernel's weight tiles, its zeroed carries / counters / dG(l, T), the K padding of the re-packed
+  // operands.  KBS_PPO_SIDE_PACK=0 keeps one stream (A/B).
+  { const int rc0 = kbs_side_stream_init(h); if (rc0) return rc0; }
+  static int side_pack = -1;
+  if (side_pack < 0) { const char* e = getenv("KBS_PPO_SIDE_PACK"); side_pack = e ? atoi(e) : 1; }
+  cudaStream_t ss = side_pack ? h->side_stream : st;
+  if (side_pack) {
+    KBS_CUDA_TRY(cudaEventRecord(h->ev_pre, st));
+    KBS_CUDA_TRY(cudaStreamWaitEvent(ss, h->ev_pre, 0));
+  }
+  float gscale = 16.0f;
+  while (gscale < 16.0f * float(rows)) gscale *= 2.0f;
+  const bool rank1_critic = narrow && h->net[1].num_out == 1;      // the critic's output layer is one row: GEMV + rank-1 dh_top
+  for (int k = 1; k >= 0; --k) {
+    const KbsNet& N = h->net[k];
+    const int kpp = round_up_i(N.num_in + 1, 128);
+    if ((rc = kbs_tc_soa_to_tn(h, plan, k == 0 ? b.actor_obs : b.critic_obs, N.num_in, ld, n, T, kpp, true, w[k].tnb_obs, ss))) return rc;
+    if (!(k == 1 && rank1_critic))
+      KBS_LAUNCH(h, KBS_K_PACK, ss, (transpose_kernel<<<blocks(int64_t(64) * H), kT, 0, ss>>>(N.w_out, 64, H, w[k].w_outT)));
+    if ((rc = kbs_tc_pack_bwd(h, k, ss, 64))) return rc;
+    KBS_CUDA_TRY(cudaMemsetAsync(w[k].dc, 0, size_t(depth) * npH * 4, ss));
+    KBS_CUDA_TRY(cudaMemsetAsync(w[k].bflags, 0, kbs_tc_bptt_flag_bytes(h, n), ss));
+    for (int l = 0; l < depth; ++l)          // dG(l, T) = 0: the operand of the first backward step's recurrent GEMM
+      KBS_CUDA_TRY(cudaMemsetAsync(w[k].dG + (size_t(l) * (T + 1) + T) * sb4, 0, sb4, ss));
+    if (kb_used < plan.kb_total)               // K padding behind the last stored row of the re-packed dG
+      for (int l = 0; l < depth; ++l)
+        for (int c = 0; c < 4 * H / 128; ++c)
+          KBS_CUDA_TRY(cudaMemsetAsync(w[k].tna_dG[l] + size_t(c) * plan.col_bytes + size_t(kb_used) * 16384, 0,
+                                       size_t(plan.kb_total - kb_used) * 16384, ss));
+    KBS_CUDA_TRY(cudaMemsetAsync(w[k].tn_zero, 0, 1024 * sizeof(float), ss));
+    if ((rc = kbs_tc_ones_block(h, w[k].tn_ones, ss))) return rc;
+  }
+  if (side_pack) KBS_CUDA_TRY(cudaEventRecord(h->ev_lstm[0], ss));
   {
     const float* obs_soa[2] = {b.actor_obs, b.critic_obs};
     float* xsb[2] = {reinterpret_cast<float*>(w[0].x_sb), reinterpret_cast<float*>(w[1].x_sb)};
@@ -867,7 +984,6 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
       F.x0 = w[k].x_sb; F.xmid = w[k].xmid; F.hsb = w[k].hsb; F.c_hist = w[k].c_hist; F.save_g = w[k].save_g;
       F.h_top_rm = w[k].h_top_rm; F.flags = w[k].fflags; F.carry0 = k == 0 ? b.actor_carry0 : b.critic_carry0;
       for (int l = 0; l < depth; ++l) F.tn_xh[l] = w[k].tnb_layer[l];
-      const int64_t kb_used = (T * np + 31) / 32;
       if (kb_used < plan.kb_total)                 // K padding behind the last stored row
         for (int l = 0; l < depth; ++l)
           for (int c = 0; c < 2 * H / 128; ++c)
@@ -877,14 +993,21 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     fa.nets = 2; fa.n = n; fa.ld = ld; fa.T = T; fa.done = b.done; fa.tn_plan = &plan; fa.transposed_out = &xh_transposed;
     if ((rc = kbs_tc_fwd_save(h, fa, st))) return rc;
     // heads: out = W_out h_top + b for all T x n rows, then forward + loss gradient + backward of the head per env
-    for (int k = 0; k < 2; ++k)
-      if ((rc = kbs_simt_gemm_nt(h, w[k].h_top_rm, H, h->net[k].w_out, H, h->net[k].b_out, w[k].out, 64, rows, 64, H, 0, st))) return rc;
+    if ((rc = kbs_simt_gemm_nt(h, w[0].h_top_rm, H, h->net[0].w_out, H, h->net[0].b_out, w[0].out, 64, rows, 64, H, 0, st))) return rc;
     KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
                (actor_head_fwd_bwd_warp_kernel<<<unsigned((n + 3) / 4), 128, 0, st>>>(
                    h->p, L, w[0].out, b.actor_obs, b.action, b.done, b.lpf0, b.old_log_probs, b.advantages, y_s, sd_s, log_probs, entropy,
                    w[0].dout, T, ld, n)));
-    KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
-               (critic_head_fwd_bwd_kernel<<<blocks(rows), kT, 0, st>>>(L, w[1].out, b.old_values, b.value_targets, values, w[1].dout, T, ld, n)));
+    if (rank1_critic) {
+      KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
+                 (critic_value_head_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(L, w[1].h_top_rm, h->net[1].w_out, h->net[1].b_out,
+                                                                                    b.old_values, b.value_targets, values, w[1].dout,
+                                                                                    w[1].out /*dv*/, H, T, ld, n)));
+    } else {
+      if ((rc = kbs_simt_gemm_nt(h, w[1].h_top_rm, H, h->net[1].w_out, H, h->net[1].b_out, w[1].out, 64, rows, 64, H, 0, st))) return rc;
+      KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
+                 (critic_head_fwd_bwd_kernel<<<blocks(rows), kT, 0, st>>>(L, w[1].out, b.old_values, b.value_targets, values, w[1].dout, T, ld, n)));
+    }
   } else {
     KbsTcRolloutArgs r{};
     r.x_sb_all[0] = reinterpret_cast<float*>(w[0].x_sb); r.x_sb_all[1] = reinterpret_cast<float*>(w[1].x_sb);
@@ -900,24 +1023,20 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     r.save = 1; r.sraw = sraw_s;
     for (int k = 0; k < 2; ++k) { r.xmid_hist[k] = w[k].xmid; r.hsb_hist[k] = w[k].hsb; r.c_hist[k] = w[k].c_hist; r.save_g[k] = w[k].save_g; }
     if ((rc = kbs_tc_rollout_recurrent(h, r, st))) return rc;
+    KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
+               (actor_head_bwd_warp_kernel<<<unsigned((n + 3) / 4), 128, 0, st>>>(h->p, L, b.action, b.done, b.old_log_probs, b.advantages,
+                                                                                 y_s, sd_s, sraw_s, log_probs, w[0].dout, T, ld, n)));
+    KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
+               (critic_head_bwd_kernel<<<blocks(rows), kT, 0, st>>>(L, values, b.old_values, b.value_targets, w[1].dout, T, ld, n)));
   }
-  // ---- B operands of the weight-gradient GEMMs: everything the forward pass produced, re-packed with K = row on the
-  // handle's side stream WHILE the backward kernel runs (it occupies one SM per work item of a slot: 64 of 148 at 512
-  // trajectories); joined before the GEMMs ----
-  const int kbH = H / 32, kb4 = 4 * H / 32;
-  { const int rc0 = kbs_side_stream_init(h); if (rc0) return rc0; }
-  // KBS_PPO_SIDE_PACK=0: keep them on the caller's stream (A/B: the concurrent re-packing competes with the latency-bound
-  // backward kernel for L2 / HBM)
-  static int side_pack = -1;
-  if (side_pack < 0) { const char* e = getenv("KBS_PPO_SIDE_PACK"); side_pack = e ? atoi(e) : 1; }
-  cudaStream_t ss = side_pack ? h->side_stream : st;
+  // ---- side stream, second part: what the forward pass produced and the weight-gradient GEMMs read with K = row (the
+  // top layer's outputs; [x | h_in] of every layer unless the forward kernel re-packed them itself), while the backward
+  // kernel runs; joined before the GEMMs ----
   if (side_pack) {
-    KBS_CUDA_TRY(cudaEventRecord(h->ev_pre, st));
-    KBS_CUDA_TRY(cudaStreamWaitEvent(ss, h->ev_pre, 0));
+    KBS_CUDA_TRY(cudaEventRecord(h->ev_lstm[1], st));
+    KBS_CUDA_TRY(cudaStreamWaitEvent(ss, h->ev_lstm[1], 0));
   }
   for (int k = 1; k >= 0; --k) {
-    const KbsNet& N = h->net[k];
-    const int kpp = round_up_i(N.num_in + 1, 128);
     for (int l = 0; l < depth && !xh_transposed; ++l) {
       const char* x_hist = l == 0 ? w[k].x_sb : w[k].xmid + size_t(l - 1) * T * sbb;
       if ((rc = kbs_tc_sb_to_tn(h, plan, true, x_hist, sbb, kbH, 0, kbH, n, T, w[k].tnb_layer[l], ss))) return rc;
@@ -930,82 +1049,74 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     } else if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].xmid + size_t(depth - 1) * T * sbb, sbb, kbH, 0, kbH, n, T, w[k].tnb_top, ss))) {
       return rc;
     }
-    if ((rc = kbs_tc_soa_to_tn(h, plan, k == 0 ? b.actor_obs : b.critic_obs, N.num_in, ld, n, T, kpp, true, w[k].tnb_obs, ss))) return rc;
+    // A operand of the dW_out GEMM: d loss / d out (row-major, K' = t np + env)
+    if ((rc = kbs_tc_pack_tn(h, plan, false, w[k].dout, 64, 0, 64, 128, rows, w[k].tn_a, gscale, -1, ss, n, np))) return rc;
   }
   if (side_pack) KBS_CUDA_TRY(cudaEventRecord(h->ev_head[0], ss));
-  // ---- heads: d loss / d out (the narrow forward's head kernels already produced it) ----
-  if (!narrow) {
-    KBS_LAUNCH(h, KBS_K_ACTOR_HEAD, st,
-               (actor_head_bwd_warp_kernel<<<unsigned((n + 3) / 4), 128, 0, st>>>(h->p, L, b.action, b.done, b.old_log_probs, b.advantages,
-                                                                                 y_s, sd_s, sraw_s, log_probs, w[0].dout, T, ld, n)));
-    KBS_LAUNCH(h, KBS_K_CRITIC_HEAD, st,
-               (critic_head_bwd_kernel<<<blocks(rows), kT, 0, st>>>(L, values, b.old_values, b.value_targets, w[1].dout, T, ld, n)));
-  }
-  float gscale = 16.0f;
-  while (gscale < 16.0f * float(rows)) gscale *= 2.0f;
+  // ---- backward recurrence ----
+  if (side_pack) KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_lstm[0], 0));        // join: W_out^T, backward weight tiles, zeroed state
   KbsBpttArgs ba{};
   for (int k = 0; k < 2; ++k) {
-    const KbsNet& N = h->net[k];
-    KBS_LAUNCH(h, KBS_K_PACK, st, (transpose_kernel<<<blocks(int64_t(64) * H), kT, 0, st>>>(N.w_out, 64, H, w[k].w_outT)));
-    if ((rc = kbs_simt_gemm_nt(h, w[k].dout, 64, w[k].w_outT, 64, nullptr, w[k].dh_top, H, rows, H, 64, 0, st))) return rc;
-    if ((rc = kbs_tc_pack_bwd(h, k, st, 64))) return rc;
-    KBS_CUDA_TRY(cudaMemsetAsync(w[k].dc, 0, size_t(depth) * npH * 4, st));
-    KBS_CUDA_TRY(cudaMemsetAsync(w[k].bflags, 0, kbs_tc_bptt_flag_bytes(h, n), st));
-    for (int l = 0; l < depth; ++l)          // dG(l, T) = 0: the operand of the first backward step's recurrent GEMM
-      KBS_CUDA_TRY(cudaMemsetAsync(w[k].dG + (size_t(l) * (T + 1) + T) * sb4, 0, sb4, st));
     KbsBpttNet& B = ba.net[k];
-    B.dG = w[k].dG; B.save_g = w[k].save_g; B.c_hist = w[k].c_hist; B.dh_top = w[k].dh_top; B.dx = w[k].dx; B.dx0 = w[k].dx0;
-    B.dc = w[k].dc; B.flags = w[k].bflags;
-    const int64_t kb_used = (T * np + 31) / 32;
-    for (int l = 0; l < depth; ++l) {
-      B.tn_dG[l] = w[k].tna_dG[l];
-      if (kb_used < plan.kb_total)                 // K padding behind the last stored row
-        for (int c = 0; c < 4 * H / 128; ++c)
-          KBS_CUDA_TRY(cudaMemsetAsync(w[k].tna_dG[l] + size_t(c) * plan.col_bytes + size_t(kb_used) * 16384, 0,
-                                       size_t(plan.kb_total - kb_used) * 16384, st));
+    if (k == 1 && rank1_critic) {
+      B.dh_top = nullptr; B.dv = w[1].out; B.w_out = h->net[1].w_out;
+    } else {
+      if ((rc = kbs_simt_gemm_nt(h, w[k].dout, 64, w[k].w_outT, 64, nullptr, w[k].dh_top, H, rows, H, 64, 0, st))) return rc;
+      B.dh_top = w[k].dh_top;
     }
+    B.dG = w[k].dG; B.save_g = w[k].save_g; B.c_hist = w[k].c_hist; B.dx = w[k].dx; B.dx0 = w[k].dx0;
+    B.dc = w[k].dc; B.flags = w[k].bflags;
+    for (int l = 0; l < depth; ++l) B.tn_dG[l] = w[k].tna_dG[l];
   }
   ba.nets = 2; ba.n = n; ba.ld = ld; ba.T = T; ba.done = b.done; ba.gscale = gscale;
   bool dG_transposed = false;
   ba.tn_plan = &plan; ba.transposed_out = &dG_transposed;
   if ((rc = kbs_tc_bptt(h, ba, st))) return rc;
   if (side_pack) KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[0], 0));       // join: the B operands are ready
-  // ---- weight gradients ----
+  // ---- weight gradients: the two networks' GEMM chains are independent (own operands, own partial slabs): the critic's
+  // runs on the side stream beside the actor's, so the small launches of one (dW_in / dW_out: 32-128 CTAs, the fixed-order
+  // reductions) fill the SMs the other leaves idle; the critic's gradients are final first (ppo.py starts its all-reduce) ----
   const float inv = 1.0f / gscale;
-  for (int k = 1; k >= 0; --k) {             // critic first: its gradients are final first (see ppo.py: the all-reduce of a
-    const KbsNet& N = h->net[k];             // network can start while the other network's GEMMs run)
+  if (side_pack) {
+    KBS_CUDA_TRY(cudaEventRecord(h->ev_head[1], st));
+    KBS_CUDA_TRY(cudaStreamWaitEvent(ss, h->ev_head[1], 0));
+  }
+  for (int k = 1; k >= 0; --k) {
+    const KbsNet& N = h->net[k];
     const kbs_net_grads* g = grads[k];
-    KBS_CUDA_TRY(cudaMemsetAsync(w[k].tn_zero, 0, 1024 * sizeof(float), st));
-    if ((rc = kbs_tc_ones_block(h, w[k].tn_ones, st))) return rc;
+    cudaStream_t sk = k == 1 ? ss : st;
     for (int l = 0; l < depth; ++l) {
       const int mp = 4 * H / 128, ldc = (2 * H / 128 + 1) * 128;
       if (!dG_transposed &&
-          (rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dG + size_t(l) * (T + 1) * sb4, sb4, kb4, 0, kb4, n, T, w[k].tna_dG[l], st)))
+          (rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dG + size_t(l) * (T + 1) * sb4, sb4, kb4, 0, kb4, n, T, w[k].tna_dG[l], sk)))
         return rc;
       if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tna_dG[l], mp, 4 * H, w[k].tnb_layer[l], 2 * H / 128, w[k].tn_ones, w[k].tn_zero,
-                               w[k].tn_partial, inv, st)))
+                               w[k].tn_partial, inv, sk)))
         return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 0, 4 * H, H, g->w_ih[l], H, st))) return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, H, 4 * H, H, g->w_hh[l], H, st))) return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 2 * H, 4 * H, 1, g->b[l], 1, st))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 0, 4 * H, H, g->w_ih[l], H, sk))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, H, 4 * H, H, g->w_hh[l], H, sk))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 2 * H, 4 * H, 1, g->b[l], 1, sk))) return rc;
+    }
+    {   // dW_out, db_out: A = d loss / d out (packed on the side stream above), B = the top layer's outputs + ones tile
+      const int ldc = (H / 128 + 1) * 128;
+      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, 1, N.num_out, w[k].tnb_top, H / 128, w[k].tn_ones, w[k].tn_zero, w[k].tn_partial, inv, sk)))
+        return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, 0, N.num_out, H, g->w_out, H, sk))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, H, N.num_out, 1, g->b_out, 1, sk))) return rc;
     }
     {   // dW_in, db_in
       const int kpp = round_up_i(N.num_in + 1, 128), mp = H / 128;
-      if ((rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dx0, sbb, kbH, 0, kbH, n, T, w[k].tn_a, st))) return rc;
-      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, mp, H, w[k].tnb_obs, kpp / 128, nullptr, w[k].tn_zero, w[k].tn_partial, inv, st))) return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, kpp, 0, H, N.num_in, g->w_in, N.num_in, st))) return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, kpp, N.num_in, H, 1, g->b_in, 1, st))) return rc;
+      if ((rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dx0, sbb, kbH, 0, kbH, n, T, w[k].tn_a, sk))) return rc;
+      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, mp, H, w[k].tnb_obs, kpp / 128, nullptr, w[k].tn_zero, w[k].tn_partial, inv, sk))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, kpp, 0, H, N.num_in, g->w_in, N.num_in, sk))) return rc;
+      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, kpp, N.num_in, H, 1, g->b_in, 1, sk))) return rc;
     }
-    {   // dW_out, db_out: A = d loss / d out (row-major, K' = t np + env), B = the top layer's outputs + ones tile
-      const int ldc = (H / 128 + 1) * 128;
-      if ((rc = kbs_tc_pack_tn(h, plan, false, w[k].dout, 64, 0, 64, 128, rows, w[k].tn_a, gscale, -1, st, n, np))) return rc;
-      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, 1, N.num_out, w[k].tnb_top, H / 128, w[k].tn_ones, w[k].tn_zero, w[k].tn_partial, inv, st)))
-        return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, 0, N.num_out, H, g->w_out, H, st))) return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, H, N.num_out, 1, g->b_out, 1, st))) return rc;
+    if (k == 1) {
+      if (h->ev_critic_ready) KBS_CUDA_TRY(cudaEventRecord(h->ev_critic_ready, sk));   // the critic's gradients are final
+      if (side_pack) KBS_CUDA_TRY(cudaEventRecord(h->ev_chunk[0], ss));
     }
-    if (k == 1 && h->ev_critic_ready) KBS_CUDA_TRY(cudaEventRecord(h->ev_critic_ready, st));   // the critic's gradients are final
   }
+  if (side_pack) KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk[0], 0));        // join: both networks' gradients are final
   {
     kbs_ppo_loss_io io{};
     io.log_probs = log_probs; io.old_log_probs = b.old_log_probs; io.advantages = b.advantages; io.values = values;

@@ -75,14 +75,26 @@ class PpoUpdater:
         self.opt = dict(lr=lr, b1=b1, b2=b2, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
         self.loss_hyper = loss_hyper
         self.comm_stream = torch.cuda.Stream(device=dev)
-        self.ev_critic, self.ev_comm = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_critic, self.ev_comm, self.ev_fork = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.ev_critic.record()            # torch creates the cudaEvent_t lazily: make the handle exist before the library sees it
         self._graph = None
         self._repack(sync=True)
 
     def _repack(self, sync: bool = False):
-        self.eng.pack_weights(L.NET_ACTOR, self.pa.as_dict(), sync=sync)
-        self.eng.pack_weights(L.NET_CRITIC, self.pc.as_dict(), sync=sync)
+        """Re-pack both networks' MMA weight images from the flat parameters.  Inside an update (sync=False) the critic's ~15
+        small launches run on the communication stream beside the actor's (per-network buffers only)."""
+        if sync:
+            self.eng.pack_weights(L.NET_ACTOR, self.pa.as_dict(), sync=True)
+            self.eng.pack_weights(L.NET_CRITIC, self.pc.as_dict(), sync=True)
+            return
+        cur = torch.cuda.current_stream()
+        self.ev_fork.record(cur)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(self.ev_fork)
+            self.eng.pack_weights(L.NET_CRITIC, self.pc.as_dict(), sync=False)
+            self.ev_comm.record(self.comm_stream)
+        self.eng.pack_weights(L.NET_ACTOR, self.pa.as_dict(), sync=False)
+        cur.wait_event(self.ev_comm)
 
     def grads(self, batch: dict, n_envs: int, critic_ready=None) -> dict:
         return self.eng.ppo_grad(batch, self.pa.as_dict(self.grad[:self.na]), self.pc.as_dict(self.grad[self.na:]), n_envs=n_envs,
