@@ -80,6 +80,7 @@ struct kbs_handle {
   bool head_attr_set = false;
   bool bptt_attr_set = false;
   bool fwd_save_attr_set = false;
+  bool dw_attr_set = false;
   cudaEvent_t ev_critic_ready = nullptr;      // caller's event (kbs_ppo_grad_set_events): recorded when the critic's gradients are final
   bool scratch_locked = false;                // kbs_scratch_lock: growing the scratch is an error (a CUDA graph holds pointers)
   long long* trace_buf = nullptr;
@@ -246,6 +247,11 @@ int kbs_tc_sb_to_tn(kbs_handle* h, const KbsTnPlan& plan, bool b_operand, const 
                     int nblk, int64_t n, int64_t T, char* dst, cudaStream_t st);
 int kbs_tc_soa_to_tn(kbs_handle* h, const KbsTnPlan& plan, const float* soa, int F, int64_t ld, int64_t n, int64_t T, int ncols_pad,
                      bool ones, char* dst, cudaStream_t st);
+// the four big weight-gradient GEMMs of an update straight from the kept per-step operands (dw_gemm_kernel: MN-major UMMA
+// operands, no K = row re-pack); partial = the K-major GEMM's slabs [ksplit][4H][2H + 128]
+bool kbs_tc_dw_direct_available(const kbs_handle* h, int64_t n);
+int kbs_tc_dw_direct(kbs_handle* h, const KbsTnPlan& plan, const char* dG, const char* x_hist, const char* h_hist, int64_t n, int64_t T,
+                     float* partial, float out_scale, cudaStream_t st);
 // backward recurrence of the PPO update as one persistent kernel (bptt_persist_kernel)
 struct KbsBpttNet {
   char* dG; const float* save_g; const float* c_hist; const float* dh_top; float* dx; char* dx0; float* dc; unsigned int* flags;

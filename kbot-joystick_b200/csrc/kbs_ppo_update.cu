@@ -933,6 +933,8 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
   static int wide_cfg = -1;
   if (wide_cfg < 0) { const char* e = getenv("KBS_PPO_FWD_WIDE"); wide_cfg = e ? atoi(e) : 0; }
   const bool narrow = !wide_cfg && kbs_tc_fwd_save_available(h, n, T);
+  // the four layer GEMMs read dG / x / h_in in place (dw_gemm_kernel) when the shapes allow: nothing is re-packed for them
+  const bool dw_direct = kbs_tc_dw_direct_available(h, n);
   bool xh_transposed = false;
   const int kbH = H / 32, kb4 = 4 * H / 32;
   const int64_t kb_used = (T * np + 31) / 32;
@@ -990,7 +992,8 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
             KBS_CUDA_TRY(cudaMemsetAsync(w[k].tnb_layer[l] + size_t(c) * plan.col_bytes + size_t(kb_used) * 16384, 0,
                                          size_t(plan.kb_total - kb_used) * 16384, st));
     }
-    fa.nets = 2; fa.n = n; fa.ld = ld; fa.T = T; fa.done = b.done; fa.tn_plan = &plan; fa.transposed_out = &xh_transposed;
+    fa.nets = 2; fa.n = n; fa.ld = ld; fa.T = T; fa.done = b.done; fa.tn_plan = dw_direct ? nullptr : &plan;
+    fa.transposed_out = &xh_transposed;
     if ((rc = kbs_tc_fwd_save(h, fa, st))) return rc;
     // heads: out = W_out h_top + b for all T x n rows, then forward + loss gradient + backward of the head per env
     if ((rc = kbs_simt_gemm_nt(h, w[0].h_top_rm, H, h->net[0].w_out, H, h->net[0].b_out, w[0].out, 64, rows, 64, H, 0, st))) return rc;
@@ -1037,7 +1040,7 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     KBS_CUDA_TRY(cudaStreamWaitEvent(ss, h->ev_lstm[1], 0));
   }
   for (int k = 1; k >= 0; --k) {
-    for (int l = 0; l < depth && !xh_transposed; ++l) {
+    for (int l = 0; l < depth && !xh_transposed && !dw_direct; ++l) {
       const char* x_hist = l == 0 ? w[k].x_sb : w[k].xmid + size_t(l - 1) * T * sbb;
       if ((rc = kbs_tc_sb_to_tn(h, plan, true, x_hist, sbb, kbH, 0, kbH, n, T, w[k].tnb_layer[l], ss))) return rc;
       if ((rc = kbs_tc_sb_to_tn(h, plan, true, w[k].hsb + size_t(l) * (T + 1) * sbb, sbb, kbH, 0, kbH, n, T,
@@ -1070,7 +1073,7 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
   }
   ba.nets = 2; ba.n = n; ba.ld = ld; ba.T = T; ba.done = b.done; ba.gscale = gscale;
   bool dG_transposed = false;
-  ba.tn_plan = &plan; ba.transposed_out = &dG_transposed;
+  ba.tn_plan = dw_direct ? nullptr : &plan; ba.transposed_out = &dG_transposed;
   if ((rc = kbs_tc_bptt(h, ba, st))) return rc;
   if (side_pack) KBS_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_head[0], 0));       // join: the B operands are ready
   // ---- weight gradients: the two networks' GEMM chains are independent (own operands, own partial slabs): the critic's
@@ -1087,12 +1090,19 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     cudaStream_t sk = k == 1 ? ss : st;
     for (int l = 0; l < depth; ++l) {
       const int mp = 4 * H / 128, ldc = (2 * H / 128 + 1) * 128;
-      if (!dG_transposed &&
-          (rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dG + size_t(l) * (T + 1) * sb4, sb4, kb4, 0, kb4, n, T, w[k].tna_dG[l], sk)))
-        return rc;
-      if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tna_dG[l], mp, 4 * H, w[k].tnb_layer[l], 2 * H / 128, w[k].tn_ones, w[k].tn_zero,
-                               w[k].tn_partial, inv, sk)))
-        return rc;
+      if (dw_direct) {
+        const char* x_hist = l == 0 ? w[k].x_sb : w[k].xmid + size_t(l - 1) * T * sbb;
+        if ((rc = kbs_tc_dw_direct(h, plan, w[k].dG + size_t(l) * (T + 1) * sb4, x_hist, w[k].hsb + size_t(l) * (T + 1) * sbb, n, T,
+                                   w[k].tn_partial, inv, sk)))
+          return rc;
+      } else {
+        if (!dG_transposed &&
+            (rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dG + size_t(l) * (T + 1) * sb4, sb4, kb4, 0, kb4, n, T, w[k].tna_dG[l], sk)))
+          return rc;
+        if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tna_dG[l], mp, 4 * H, w[k].tnb_layer[l], 2 * H / 128, w[k].tn_ones, w[k].tn_zero,
+                                 w[k].tn_partial, inv, sk)))
+          return rc;
+      }
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 0, 4 * H, H, g->w_ih[l], H, sk))) return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, H, 4 * H, H, g->w_hh[l], H, sk))) return rc;
       if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 2 * H, 4 * H, 1, g->b[l], 1, sk))) return rc;
