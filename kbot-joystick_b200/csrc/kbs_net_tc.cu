@@ -3621,16 +3621,17 @@ int kbs_tc_fwd_save(kbs_handle* h, const KbsFwdSaveArgs& f, cudaStream_t st) {
 // the recurrence kernels at 512) is not needed for the four big GEMMs of an update.
 // Work item = (128 gate rows of dG, 256 columns of x or of h_in | the bias column, one accumulation run of <= 3 200 rows),
 // ordered run-major so that the items in flight share their operands in L2.
-// Stage = 64 rows: 4-D TMA boxes {64 rows x 16 B, 4 chunks, 4 | 8 blocks, 1 (step, panel)} land as [block][chunk][row][16 B]
-// per plane = 16 core matrices (A) / 32 (B) along MN at a uniform 1 KB, 8-row groups 128 B apart.  Per 16-row k-step three
+// Stage = 32 rows: 4-D TMA boxes {32 rows x 16 B, 4 chunks, 4 | 8 blocks, 1 (step, panel)} land as [block][chunk][row][16 B]
+// per plane = 16 core matrices (A) / 32 (B) along MN at a uniform 512 B, 8-row groups 128 B apart.  Per 16-row k-step three
 // N = 256 MMAs: hi.hi -> main, hi.lo + lo.hi -> correction columns (the truncating accumulator, profiles/r01_tc_accumulation.md).
 // The bias gradient (column sums of dG) is a third kind of item: B = a constant block with a one in feature 0, N = 16.
 // Partial sums go to the same [run][4H][2H + 128] slabs the K-major GEMM writes: tn_reduce_kernel adds them in fixed order.
-constexpr int kDwRows = 64;
-constexpr int kDwAPlane = 128 * kDwRows * 2, kDwBPlane = 256 * kDwRows * 2;          // 16 KB, 32 KB
-constexpr int kDwStageBytes = 2 * kDwAPlane + 2 * kDwBPlane;                         // 96 KB
-constexpr int kDwStages = 2;
-constexpr int kDwOnesBytes = 2 * kDwRows * 16;                                       // 2 chunks x 64 rows x 16 B
+constexpr int kDwRows = 32;                                                          // K' rows per stage
+constexpr int kDwParts = kPanelRows / kDwRows;                                       // stages per (step, panel) unit
+constexpr int kDwAPlane = 128 * kDwRows * 2, kDwBPlane = 256 * kDwRows * 2;          // 8 KB, 16 KB
+constexpr int kDwStageBytes = 2 * kDwAPlane + 2 * kDwBPlane;                         // 48 KB
+constexpr int kDwStages = 4;          // (2 stages of 64 rows: a stage's load could only start behind the MMAs of the stage before the last)
+constexpr int kDwOnesBytes = 2 * kDwRows * 16;                                       // 2 chunks x kDwRows rows x 16 B
 constexpr int kDwSmemBytes = kDwStages * kDwStageBytes + kDwOnesBytes + 256 + 1024;
 constexpr int kDwThreads = 32 * 6;                                                   // issuer, producer, 4 epilogue warps
 struct alignas(64) DwArgs {
@@ -3674,7 +3675,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
     mbar_init(acc_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // the bias item's B operand: [2 chunks][64 rows][16 B], feature 0 of every row = 1.0 (fp16), everything else 0
+  // the bias item's B operand: [2 chunks][kDwRows rows][16 B], feature 0 of every row = 1.0 (fp16), everything else 0
   for (int i = threadIdx.x; i < kDwOnesBytes / 16; i += kDwThreads)
     reinterpret_cast<uint4*>(ones)[i] = i < kDwRows ? make_uint4(0x3C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -3704,7 +3705,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         int m, nt, run; decode(it, m, nt, run);
         const int u0 = run * args.units_per_run, u1 = min(u0 + args.units_per_run, args.units);
         for (int u = u0; u < u1; ++u)
-          for (int half = 0; half < 2; ++half, ++g) {
+          for (int half = 0; half < kDwParts; ++half, ++g) {
             const int s = g % kDwStages;
             mbar_wait(&empty[s], ((g / kDwStages) & 1) ^ 1);
             uint8_t* st = smem + size_t(s) * kDwStageBytes;
@@ -3731,12 +3732,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
       mbar_wait(acc_empty, (j & 1) ^ 1);
       tc_fence_after();
       uint32_t first = 0;
-      for (int q = 0; q < 2 * (u1 - u0); ++q, ++g) {
+      for (int q = 0; q < kDwParts * (u1 - u0); ++q, ++g) {
         const int s = g % kDwStages;
         mbar_wait(&full[s], (g / kDwStages) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + size_t(s) * kDwStageBytes);
-        // MN-major, no swizzle: LBO = distance of the 8-row groups (128 B), SBO = distance of the 8-feature chunks (64 rows x 16 B)
+        // MN-major, no swizzle: LBO = distance of the 8-row groups (128 B), SBO = distance of the 8-feature chunks (kDwRows x 16 B)
         const uint64_t a_hi = umma_desc(sa, 128, kDwRows * 16), a_lo = umma_desc(sa + kDwAPlane, 128, kDwRows * 16);
         const uint64_t b_hi = nt < 2 ? umma_desc(sa + 2 * kDwAPlane, 128, kDwRows * 16) : umma_desc(smem_u32(ones), 128, kDwRows * 16);
         const uint64_t b_lo = umma_desc(sa + 2 * kDwAPlane + kDwBPlane, 128, kDwRows * 16);
@@ -3810,7 +3811,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
 }
 
 // 4-D map over per-step split-blocked buffers (one plane), 32-bit elements: {128 rows x 4 words (one chunk: contiguous), 4 chunks,
-// kb blocks, slots * panels}; box = {64 rows x 4 words, 4, box_kb, 1}.  (With the 16 bytes of a row as the innermost dimension
+// kb blocks, slots * panels}; box = {kDwRows rows x 4 words, 4, box_kb, 1}.  (With the 16 bytes of a row as the innermost dimension
 // the copy engine moved 16-byte lines: the GEMM ran at a quarter of the speed.)
 static bool encode_sb_plane_map(CUtensorMap* m, const char* base, int kb, int64_t units, int box_kb) {
   KbsTensorMapEncodeFn fn = tensor_map_encode_fn();

@@ -6,7 +6,8 @@ from kbot_joystick_b200 import _lib as L, synth
 from kbot_joystick_b200.engine import KbotStep
 from kbot_joystick_b200.ppo import PpoUpdater
 dev = torch.device("cuda:0")
-H, N, T = 256, 512, 100
+import os
+H, N, T = 256, int(os.environ.get("PROF_ENVS", "512")), 100
 ld = N
 eng = KbotStep(hidden_size=H, depth=2, gemm_path=L.GEMM_TC_2XF16)
 up = PpoUpdater(eng, synth.make_weights(77, 65, 40, H, 2), synth.make_weights(78, 475, 1, H, 2))
