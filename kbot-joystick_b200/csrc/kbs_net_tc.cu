@@ -1457,6 +1457,12 @@ __device__ __forceinline__ void b_prefetch_saves(const BArgs& a, const BItem& it
   }
 }
 
+__device__ __forceinline__ void b_ld8fb(const float* base, int64_t R, int u, int H, float (&o)[8], bool coherent) {
+  const float4* p0 = reinterpret_cast<const float4*>(base + fb_offset(R, u, H));
+  const float4* p1 = reinterpret_cast<const float4*>(base + fb_offset(R, u + 4, H));
+  const float4 a = coherent ? __ldcg(p0) : __ldg(p0), b = coherent ? __ldcg(p1) : __ldg(p1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
 template <int KIND>
 __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid_constant__ BArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -1692,6 +1698,14 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
         }
         gstage += uint32_t(kb4);
       }
+      // H tile: the forward pass's saves of the first 8 units are requested before the wait for the accumulator (they depend on
+      // nothing of this kernel): their L2 round trip runs under the item's MMAs instead of behind them
+      float qi[8], gf[8], gg[8], go[8], ci[8];
+      const bool hk = it.kind == 0 && live;
+      if (hk) {
+        b_ld8fb(sg, R, u0, H, qi, false); b_ld8fb(sg + npH, R, u0, H, gf, false); b_ld8fb(sg + 2 * npH, R, u0, H, gg, false);
+        b_ld8fb(sg + 3 * npH, R, u0, H, go, false); b_ld8fb(cin, R, u0, H, ci, false);
+      }
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * kBT) + grp * (kBT / 4));
@@ -1724,16 +1738,12 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
           continue;
         }
         // ---- H tile: the cell's backward at step s for units u .. u + 7 ----
-        float gi[8], gf[8], gg[8], go[8], ci[8], dhi[8], dcr[8];
-        auto ld8fb = [&](const float* base, float (&o)[8], bool coherent) {
-          const float4* p0 = reinterpret_cast<const float4*>(base + fb_offset(R, u, H));
-          const float4* p1 = reinterpret_cast<const float4*>(base + fb_offset(R, u + 4, H));
-          const float4 a = coherent ? __ldcg(p0) : __ldg(p0), b = coherent ? __ldcg(p1) : __ldg(p1);
-          o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
-        };
-        ld8fb(sg, gi, false); ld8fb(sg + npH, gf, false); ld8fb(sg + 2 * npH, gg, false); ld8fb(sg + 3 * npH, go, false);
-        ld8fb(cin, ci, false);
-        ld8fb(dcp, dcr, true);
+        float dhi[8], dcr[8];
+        if (c8 > 0) {
+          b_ld8fb(sg, R, u, H, qi, false); b_ld8fb(sg + npH, R, u, H, gf, false); b_ld8fb(sg + 2 * npH, R, u, H, gg, false);
+          b_ld8fb(sg + 3 * npH, R, u, H, go, false); b_ld8fb(cin, R, u, H, ci, false);
+        }
+        b_ld8fb(dcp, R, u, H, dcr, true);
         if (top && N.dv) {
           const float d = __ldg(N.dv + s * size_t(args.n) + size_t(R));
           const float4 a = __ldg(reinterpret_cast<const float4*>(N.w_out + u)), b = __ldg(reinterpret_cast<const float4*>(N.w_out + u + 4));
@@ -1743,20 +1753,20 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
           const float4 a = __ldg(reinterpret_cast<const float4*>(dxu + u)), b = __ldg(reinterpret_cast<const float4*>(dxu + u + 4));
           dhi[0] = a.x; dhi[1] = a.y; dhi[2] = a.z; dhi[3] = a.w; dhi[4] = b.x; dhi[5] = b.y; dhi[6] = b.z; dhi[7] = b.w;
         } else {
-          ld8fb(dxu, dhi, true);
+          b_ld8fb(dxu, R, u, H, dhi, true);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float c = gf[i] * ci[i] + gi[i] * gg[i];                 // c_s, as the forward pass formed it
+          const float c = gf[i] * ci[i] + qi[i] * gg[i];                 // c_s, as the forward pass formed it
           const float tc = tanhf_(c);
           const float dh = dhi[i] + keep * (args.inv_gscale * v[i]);
           const float dc = keep * dcr[i] + dh * go[i] * (1.0f - tc * tc);
           dcr[i] = dc * gf[i];
-          const float di = args.gscale * (dc * gg[i] * gi[i] * (1.0f - gi[i]));
+          const float di = args.gscale * (dc * gg[i] * qi[i] * (1.0f - qi[i]));
           const float df = args.gscale * (dc * ci[i] * gf[i] * (1.0f - gf[i]));
-          const float dg = args.gscale * (dc * gi[i] * (1.0f - gg[i] * gg[i]));
+          const float dg = args.gscale * (dc * qi[i] * (1.0f - gg[i] * gg[i]));
           const float dob = args.gscale * (dh * tc * go[i] * (1.0f - go[i]));
-          gi[i] = di; gf[i] = df; gg[i] = dg; go[i] = dob;              // the gate gradients replace the gates
+          qi[i] = di; gf[i] = df; gg[i] = dg; go[i] = dob;              // the gate gradients replace the gates
         }
         *reinterpret_cast<float4*>(dcp + fb_offset(R, u, H)) = make_float4(dcr[0], dcr[1], dcr[2], dcr[3]);
         *reinterpret_cast<float4*>(dcp + fb_offset(R, u + 4, H)) = make_float4(dcr[4], dcr[5], dcr[6], dcr[7]);
@@ -1765,7 +1775,7 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
           bad = bad || sb_out_of_range<KIND, 4>(x0) || sb_out_of_range<KIND, 4>(x1);
           sb_store_split8<kPanelRows, KIND>(dGo, R, gate * H + u, 4 * H / kBlk, sb_split4<KIND>(x0), sb_split4<KIND>(x1), false);
         };
-        st8(0, gi); st8(1, gf); st8(2, gg); st8(3, go);
+        st8(0, qi); st8(1, gf); st8(2, gg); st8(3, go);
       }
       // the accumulator buffer goes back to the MMA issuer, then the item is published
       tc_fence_before();
