@@ -230,6 +230,7 @@ int kbs_tc_debug_trace(kbs_handle* h, long long* trace_out, float* ws, int64_t n
 int kbs_tc_gates_fwd(kbs_handle* h, int net, int layer, const void* x_sb, const void* h_sb, float* gates_out, int64_t n,
                      cudaStream_t st);
 int kbs_tc_pack_bwd(kbs_handle* h, int net, cudaStream_t st, int tile = 128);
+int kbs_tc_bptt_tile(const kbs_handle* h, int64_t n);   // tile width kbs_tc_bptt will use for n trajectories (64 | 128): pack for it
 int kbs_tc_bwd_gemm(kbs_handle* h, int net, int layer, const void* dG_sb, float* out, int64_t n, float out_scale, cudaStream_t st);
 size_t kbs_tc_rows_sb_bytes(const kbs_handle* h, int64_t n, int K);
 // weight-gradient GEMMs C = A^T B over K = all stored rows (split-K tcgen05; operands = transposed split-blocked buffers)

@@ -1345,11 +1345,14 @@ rollout_persist_kernel(const __grid_constant__ kbs_params P, const __grid_consta
 // the kernel is bound by what ONE SM can pull from L2 (~60 B/clk): an item streams its whole dG panel (128 x 4H, 512 KB) plus
 // its weight tile, 1 MB at 128 columns.  Narrow tiles put more SMs (128 instead of 64 per slot) on the same slot: 768 KB per
 // item, and half the epilogue per thread.  (MMA issue is not the limit here: 2 instructions per k-step either way.)
-constexpr int kBT = 64;
-constexpr int kBBBlockBytes = 2 * 4 * kBT * 16;          // [chunk][hi|lo][64 rows][16 B] = 8 KB
-constexpr int kBStageBytes = kABlockBytes + kBBBlockBytes;   // 24 KB
-constexpr int kBStages = 8;
-constexpr int kBSmemBytes = kBStages * kBStageBytes + 256 /*barriers*/ + 1024 /*align*/;
+// BT = 128 is a second instantiation kept for A/B (kbs_tc_bptt_tile).
+constexpr int kBT = 64;                                   // the narrow tile (and the width kbs_tc_pack_bwd's second image is for)
+template <int BT> struct BTile {
+  static constexpr int kBBlockBytes = 2 * 4 * BT * 16;               // [chunk][hi|lo][BT rows][16 B] = 8 / 16 KB
+  static constexpr int kStageBytes = kABlockBytes + kBBlockBytes;    // 24 / 32 KB
+  static constexpr int kStages = BT == 64 ? 8 : 6;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + 1024 /*align*/;
+};
 constexpr int kBEpiWarps = 16;
 constexpr int kBThreads = 32 * (1 + 1 + kBEpiWarps + 2);
 struct BNet {
@@ -1385,8 +1388,9 @@ struct BArgs {
   size_t tn_col_bytes;
 };
 struct BItem { int kind, net, layer, panel, tile, s; bool valid; };
+template <int BT>
 __device__ __forceinline__ BItem b_decode(const BArgs& a, int g) {
-  const int th = a.H / kBT;                      // tiles per half of the [dx | dh] output
+  const int th = a.H / BT;                      // tiles per half of the [dx | dh] output
   const int per_panel = a.depth * 2 * th, per_net = a.panels * per_panel, C = a.nets * per_net;
   const int sigma = g / C;
   int i = g - sigma * C;
@@ -1403,11 +1407,12 @@ __device__ __forceinline__ BItem b_decode(const BArgs& a, int g) {
   it.valid = base >= 0 && it.s >= 0 && it.s <= int(a.T) - 1;
   return it;
 }
+template <int BT>
 __device__ __forceinline__ long long b_wait_deps(const BArgs& a, const BItem& it, bool& drain) {
   if (drain) return 0;
   const long long c0 = clock64();
   const BNet& N = a.net[it.net];
-  const unsigned int per = unsigned((a.H / kBT) * kBEpiWarps);
+  const unsigned int per = unsigned((a.H / BT) * kBEpiWarps);
   const unsigned int* fp[2]; unsigned int tg[2]; int nd = 0;
   const unsigned int T = unsigned(a.T), s = unsigned(it.s);
   const int l = it.layer;
@@ -1441,16 +1446,17 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // HBM (1 GB per update: far beyond L2).  They are known long before the item can start, so the epilogue warps request them
 // one item ahead: by the time the accumulators are ready the lines sit in L2 (~2 K cycles of DRAM latency per batch of
 // loads otherwise, four batches in a row on the critical path of every backward step).
+template <int BT>
 __device__ __forceinline__ void b_prefetch_saves(const BArgs& a, const BItem& it, int r, int grp, size_t npH) {
   if (it.kind != 0) return;
   const BNet& N = a.net[it.net];
   const int64_t R = int64_t(it.panel) * kPanelRows + r;
   if (R >= a.n) return;
-  const int u0 = it.tile * kBT + grp * (kBT / 4);
+  const int u0 = it.tile * BT + grp * (BT / 4);
   const float* sg = N.save_g + (size_t(it.s) * a.depth + it.layer) * 4 * npH;
   const float* cin = N.c_hist + (size_t(it.layer) * size_t(a.T + 1) + size_t(it.s)) * npH;
 #pragma unroll
-  for (int q = 0; q < kBT / 16; ++q) {
+  for (int q = 0; q < BT / 16; ++q) {
     const size_t o = fb_offset(R, u0 + 4 * q, a.H);
     prefetch_l2(sg + o); prefetch_l2(sg + npH + o); prefetch_l2(sg + 2 * npH + o); prefetch_l2(sg + 3 * npH + o);
     prefetch_l2(cin + o);
@@ -1463,21 +1469,21 @@ __device__ __forceinline__ void b_ld8fb(const float* base, int64_t R, int u, int
   const float4 a = coherent ? __ldcg(p0) : __ldg(p0), b = coherent ? __ldcg(p1) : __ldg(p1);
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
-template <int KIND>
+template <int KIND, int BT>
 __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid_constant__ BArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBStages * kBStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BTile<BT>::kStages * BTile<BT>::kStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kBStages;
-  uint64_t* acc_full = bars + 2 * kBStages;     // [2]
+  uint64_t* empty = bars + BTile<BT>::kStages;
+  uint64_t* acc_full = bars + 2 * BTile<BT>::kStages;     // [2]
   uint64_t* acc_empty = acc_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   volatile int* dep_seq = reinterpret_cast<volatile int*>(tmem_slot + 1);
   unsigned int* epi_done = reinterpret_cast<unsigned int*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = args.H, th = H / kBT;
+  const int H = args.H, th = H / BT;
   const int per_slot = args.nets * args.panels * args.depth * 2 * th;
   const int n_g = (int(args.T) + 2 * (args.depth - 1) + 1) * per_slot;
   constexpr int kBlk = kbs_block_k(KIND);
@@ -1490,7 +1496,7 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
 
   if (threadIdx.x == 0) {
     // empty[s]: the MMA commit, + (tn) the four epilogue warps that look at the stage for the on-the-fly re-pack
-    for (int s = 0; s < kBStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], args.tn ? 5 : 1); }
+    for (int s = 0; s < BTile<BT>::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], args.tn ? 5 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kBEpiWarps); }
     *dep_seq = 0;
     *epi_done = 0u;
@@ -1511,7 +1517,7 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
       // ===== publisher (see rollout_persist_kernel) =====
       int j = 0;
       for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
-        const BItem it = b_decode(args, gi);
+        const BItem it = b_decode<BT>(args, gi);
         if (!it.valid) continue;
         ++j;
         const unsigned int want = unsigned(j) * kBEpiWarps;
@@ -1531,9 +1537,9 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
       bool drain = false;
       long long waited = 0;
       for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
-        const BItem it = b_decode(args, gi);
+        const BItem it = b_decode<BT>(args, gi);
         if (!it.valid) continue;
-        if (!(args.dbg & 1)) waited += b_wait_deps(args, it, drain);
+        if (!(args.dbg & 1)) waited += b_wait_deps<BT>(args, it, drain);
         *dep_seq = ++j;
       }
       if (tr) { tr[1] = waited; tr[2] = j; }
@@ -1545,30 +1551,30 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
       uint32_t g = 0;
       int j = 0;
       for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
-        const BItem it = b_decode(args, gi);
+        const BItem it = b_decode<BT>(args, gi);
         if (!it.valid) continue;
         const BNet& N = args.net[it.net];
         const int slot = it.s + (it.kind == 0 ? 1 : 0);
         const char* xa = N.dG + (size_t(it.layer) * size_t(args.T + 1) + size_t(slot)) * args.sb4 + size_t(it.panel) * kb4 * kABlockBytes;
-        const char* wb = N.w_bwd[it.layer] + size_t(it.kind == 0 ? th + it.tile : it.tile) * kb4 * kBBBlockBytes;
+        const char* wb = N.w_bwd[it.layer] + size_t(it.kind == 0 ? th + it.tile : it.tile) * kb4 * BTile<BT>::kBBlockBytes;
         ++j;
         bool need_dep = true;
         for (int b = 0; b < kb4; ++b, ++g) {
-          const int s = g % kBStages;
+          const int s = g % BTile<BT>::kStages;
           if (lane == 0) {
-            mbar_wait(&empty[s], ((g / kBStages) & 1) ^ 1);
-            mbar_expect_tx(&full[s], uint32_t(kABlockBytes + kBBBlockBytes));
+            mbar_wait(&empty[s], ((g / BTile<BT>::kStages) & 1) ^ 1);
+            mbar_expect_tx(&full[s], uint32_t(kABlockBytes + BTile<BT>::kBBlockBytes));
           }
           __syncwarp(0x3);
-          uint8_t* sa = smem + size_t(s) * kBStageBytes;
+          uint8_t* sa = smem + size_t(s) * BTile<BT>::kStageBytes;
           if (lane == 0 && need_dep) {
             while (*dep_seq < j) { }
             __threadfence_block();
             asm volatile("fence.proxy.async;" ::: "memory");
             need_dep = false;
           }
-          const char* src = lane == 0 ? xa + size_t(b) * kABlockBytes : wb + size_t(b) * kBBBlockBytes;
-          bulk_g2s(sa + lane * kABlockBytes, src, lane == 0 ? uint32_t(kABlockBytes) : uint32_t(kBBBlockBytes), &full[s]);
+          const char* src = lane == 0 ? xa + size_t(b) * kABlockBytes : wb + size_t(b) * BTile<BT>::kBBlockBytes;
+          bulk_g2s(sa + lane * kABlockBytes, src, lane == 0 ? uint32_t(kABlockBytes) : uint32_t(BTile<BT>::kBBlockBytes), &full[s]);
         }
       }
     }
@@ -1579,31 +1585,31 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
     int j = 0;
     long long w_full = 0, w_acc = 0;
     for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
-      const BItem it = b_decode(args, gi);
+      const BItem it = b_decode<BT>(args, gi);
       if (!it.valid) continue;
       const int buf = j & 1;
       const long long e0 = tr ? clock64() : 0;
       mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
       if (tr) w_acc += clock64() - e0;
       tc_fence_after();
-      const uint32_t d_main = tmem_base + buf * (2 * kBT), d_corr = d_main + kBT;
+      const uint32_t d_main = tmem_base + buf * (2 * BT), d_corr = d_main + BT;
       for (int b = 0; b < kb4; ++b, ++g) {
-        const int s = g % kBStages;
+        const int s = g % BTile<BT>::kStages;
         const long long f0 = tr ? clock64() : 0;
-        mbar_wait(&full[s], (g / kBStages) & 1);
+        mbar_wait(&full[s], (g / BTile<BT>::kStages) & 1);
         if (tr) w_full += clock64() - f0;
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + size_t(s) * kBStageBytes);
+        const uint32_t sa = smem_u32(smem + size_t(s) * BTile<BT>::kStageBytes);
         const uint32_t sb = sa + kABlockBytes;
         const uint64_t a_hi = umma_desc(sa, 2048, 128), a_lo = umma_desc(sa + 8192, 2048, 128);
-        // B block [chunk][hi|lo][kBT rows][16 B]: chunk stride (LBO) 2 kBT 16 B, k-step (2 chunks) twice that
-        const uint64_t b_all = umma_desc(sb, 2 * kBT * 16, 128);
-        constexpr uint64_t kBStep = uint64_t(4 * kBT * 16) >> 4;
+        // B block [chunk][hi|lo][BT rows][16 B]: chunk stride (LBO) 2 BT 16 B, k-step (2 chunks) twice that
+        const uint64_t b_all = umma_desc(sb, 2 * BT * 16, 128);
+        constexpr uint64_t kBStep = uint64_t(4 * BT * 16) >> 4;
         if (elect_one()) {
-          umma<KIND, 2 * kBT>(d_main, a_hi, b_all, b != 0);
-          umma<KIND, kBT>(d_corr, a_lo, b_all, 1);
-          umma<KIND, 2 * kBT>(d_main, a_hi + (4096 >> 4), b_all + kBStep, 1);
-          umma<KIND, kBT>(d_corr, a_lo + (4096 >> 4), b_all + kBStep, 1);
+          umma<KIND, 2 * BT>(d_main, a_hi, b_all, b != 0);
+          umma<KIND, BT>(d_corr, a_lo, b_all, 1);
+          umma<KIND, 2 * BT>(d_main, a_hi + (4096 >> 4), b_all + kBStep, 1);
+          umma<KIND, BT>(d_corr, a_lo + (4096 >> 4), b_all + kBStep, 1);
           umma_commit(&empty[s]);
         }
         __syncwarp();
@@ -1628,24 +1634,24 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
     uint32_t gstage = 0;                  // ring position of the current item's first stage (as the producer / issuer count)
     {   // the first item's saves
       for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
-        const BItem it0 = b_decode(args, gi);
-        if (it0.valid) { b_prefetch_saves(args, it0, r, grp, npH); break; }
+        const BItem it0 = b_decode<BT>(args, gi);
+        if (it0.valid) { b_prefetch_saves<BT>(args, it0, r, grp, npH); break; }
       }
     }
     for (int gi = blockIdx.x; gi < n_g; gi += n_cc) {
-      const BItem it = b_decode(args, gi);
+      const BItem it = b_decode<BT>(args, gi);
       if (!it.valid) continue;
       {   // request the NEXT item's saves now: a whole item of lead time
         for (int gn = gi + n_cc; gn < n_g; gn += n_cc) {
-          const BItem itn = b_decode(args, gn);
-          if (itn.valid) { b_prefetch_saves(args, itn, r, grp, npH); break; }
+          const BItem itn = b_decode<BT>(args, gn);
+          if (itn.valid) { b_prefetch_saves<BT>(args, itn, r, grp, npH); break; }
         }
       }
       const BNet& N = args.net[it.net];
       const int64_t R = int64_t(it.panel) * kPanelRows + r;
       const bool live = R < args.n;
       const int buf = j & 1;
-      const int u0 = it.tile * kBT + grp * (kBT / 4);         // first of this thread's 16 units (columns of the half)
+      const int u0 = it.tile * BT + grp * (BT / 4);         // first of this thread's 16 units (columns of the half)
       while (*dep_seq < j + 1) { }
       __threadfence_block();
       const size_t s = size_t(it.s);
@@ -1662,11 +1668,11 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
         // the K block, release it (every stage gets exactly four such arrivals, whoever owns it)
         for (int b = 0; b < kb4; ++b) {
           const uint32_t g = gstage + uint32_t(b);
-          const int st = int(g % kBStages);
+          const int st = int(g % BTile<BT>::kStages);
           if ((st & 3) != grp) continue;            // by ring slot: the same warps watch every phase of a barrier (see lstm_fwd_save_kernel)
-          mbar_wait(&full[st], (g / kBStages) & 1);
+          mbar_wait(&full[st], (g / BTile<BT>::kStages) & 1);
           if (it.kind == 1 && (b % th) == it.tile) {
-            const uint8_t* sa = smem + size_t(st) * kBStageBytes;       // A block [hi|lo][chunk][128 rows][16 B]
+            const uint8_t* sa = smem + size_t(st) * BTile<BT>::kStageBytes;       // A block [hi|lo][chunk][128 rows][16 B]
             const int cm = (ew & 3) * 32 + lane;                        // one of the block's 128 core matrices (8 rows x 8 K)
             const int r8 = cm & 15, c = (cm >> 4) & 3, plane = cm >> 6;
             const uint8_t* sp = sa + ((size_t(plane) * 4 + c) * kPanelRows + size_t(r8) * 8) * 16;
@@ -1708,15 +1714,15 @@ __global__ void __launch_bounds__(kBThreads, 1) bptt_persist_kernel(const __grid
       }
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * kBT) + grp * (kBT / 4));
+      const uint32_t tq = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(buf * (2 * BT) + grp * (BT / 4));
 #pragma unroll 1
-      for (int c8 = 0; c8 < kBT / 32; ++c8) {
+      for (int c8 = 0; c8 < BT / 32; ++c8) {
         const int u = u0 + 8 * c8;
         float v[8];
         {
           float cr[8];
           tmem_ld8(tq + 8 * c8, v);
-          tmem_ld8(tq + kBT + 8 * c8, cr);
+          tmem_ld8(tq + BT + 8 * c8, cr);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] += kCorr * cr[i];
@@ -3488,21 +3494,36 @@ bool kbs_tc_bptt_available(const kbs_handle* h, int64_t n, int64_t T) {
   const int64_t panels = pad_rows(n) / kPanelRows;
   return (T + 2 * depth) * 2 * panels * depth * 2 * (H / kBT) < (int64_t(1) << 31);
 }
+// tile width of bptt_persist_kernel: 64 columns.  The 128-column instantiation (KBS_BPTT_TILE=128; the caller packs the
+// weights for whichever this returns) was meant for large minibatches, where every SM has several items per slot and tcgen05
+// issue -- 2 instructions per k-step whatever the width -- could bound an item; MEASURED at 8 192 x 100: 20.1 ms against 19.9 ms
+// with 64 columns (the cell's backward in the epilogue, 32 units per thread, takes as long as the item's MMAs), so it stays
+// an A/B option.
+int kbs_tc_bptt_tile(const kbs_handle* h, int64_t n) {
+  (void)h; (void)n;
+  const char* e = getenv("KBS_BPTT_TILE");
+  return (e && atoi(e) == kTileCols) ? kTileCols : kBT;
+}
 int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
   const int H = h->p.hidden_size, depth = h->p.depth;
   if (!kbs_tc_bptt_available(h, b.n, b.T)) return KBS_E_STATE;
   { const int rc0 = kbs_status_init(h); if (rc0) return rc0; }
   if (!h->bptt_attr_set) {
-    KBS_CUDA_TRY(cudaFuncSetAttribute(bptt_persist_kernel<KBS_KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
+    KBS_CUDA_TRY((cudaFuncSetAttribute(bptt_persist_kernel<KBS_KIND_F16, kBT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       BTile<kBT>::kSmemBytes)));
+    KBS_CUDA_TRY((cudaFuncSetAttribute(bptt_persist_kernel<KBS_KIND_F16, kTileCols>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       BTile<kTileCols>::kSmemBytes)));
     h->bptt_attr_set = true;
   }
+  const int bt = kbs_tc_bptt_tile(h, b.n);
   const int64_t np = pad_rows(b.n);
   BArgs a{};
   for (int k = 0; k < b.nets; ++k) {
     const KbsNet& Nn = h->net[k];
-    if (!Nn.packed || !Nn.tc_bwd_image64) return KBS_E_STATE;
+    const float* image = bt == kBT ? Nn.tc_bwd_image64 : Nn.tc_bwd_image;
+    if (!Nn.packed || !image) return KBS_E_STATE;
     BNet& N = a.net[k];
-    for (int l = 0; l < depth; ++l) N.w_bwd[l] = reinterpret_cast<const char*>(Nn.tc_bwd_image64) + bwd_layer_bytes(h) * l;
+    for (int l = 0; l < depth; ++l) N.w_bwd[l] = reinterpret_cast<const char*>(image) + bwd_layer_bytes(h) * l;
     N.dG = b.net[k].dG; N.save_g = b.net[k].save_g; N.c_hist = b.net[k].c_hist; N.dh_top = b.net[k].dh_top;
     N.dv = b.net[k].dv; N.w_out = b.net[k].w_out;
     if (!N.dh_top && !(N.dv && N.w_out)) return KBS_E_NULL;
@@ -3516,7 +3537,7 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
   a.status = h->persist_status;
   { const char* e = getenv("KBS_PERSIST_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.trace = h->trace_buf ? h->trace_buf + 2 * 148 * 16 : nullptr;  // third region of the debug buffer (forward kernel, input projection, this)
-  const int64_t per_slot = int64_t(b.nets) * a.panels * depth * 2 * (H / kBT);
+  const int64_t per_slot = int64_t(b.nets) * a.panels * depth * 2 * (H / bt);
   const int n_cc = int(per_slot < h->num_sms ? per_slot : h->num_sms);
   // The X tiles re-pack dG for the weight-gradient GEMMs on the fly when a CTA has (about) one item per slot: its epilogue
   // warps are idle during the MMAs then.  With many items per CTA and slot the epilogue of item j overlaps the MMAs of item
@@ -3529,7 +3550,7 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(n_cc));
   cfg.blockDim = dim3(kBThreads);
-  cfg.dynamicSmemBytes = kBSmemBytes;
+  cfg.dynamicSmemBytes = bt == kBT ? BTile<kBT>::kSmemBytes : BTile<kTileCols>::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeCooperative;      // every CTA must be resident: they wait on each other's counters
@@ -3537,7 +3558,8 @@ int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& b, cudaStream_t st) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   cudaError_t le = cudaSuccess;
-  KBS_LAUNCH(h, KBS_K_BPTT_TC, st, (le = cudaLaunchKernelEx(&cfg, bptt_persist_kernel<KBS_KIND_F16>, a)));
+  if (bt == kBT) KBS_LAUNCH(h, KBS_K_BPTT_TC, st, (le = cudaLaunchKernelEx(&cfg, bptt_persist_kernel<KBS_KIND_F16, kBT>, a)));
+  else KBS_LAUNCH(h, KBS_K_BPTT_TC, st, (le = cudaLaunchKernelEx(&cfg, bptt_persist_kernel<KBS_KIND_F16, kTileCols>, a)));
   KBS_CUDA_TRY(le);
   { const int rc0 = kbs_status_publish(h, st); if (rc0) return rc0; }
   KBS_LAUNCH_CHECK();

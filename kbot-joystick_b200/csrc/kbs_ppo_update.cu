@@ -960,7 +960,7 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     if ((rc = kbs_tc_soa_to_tn(h, plan, k == 0 ? b.actor_obs : b.critic_obs, N.num_in, ld, n, T, kpp, true, w[k].tnb_obs, ss))) return rc;
     if (!(k == 1 && rank1_critic))
       KBS_LAUNCH(h, KBS_K_PACK, ss, (transpose_kernel<<<blocks(int64_t(64) * H), kT, 0, ss>>>(N.w_out, 64, H, w[k].w_outT)));
-    if ((rc = kbs_tc_pack_bwd(h, k, ss, 64))) return rc;
+    if ((rc = kbs_tc_pack_bwd(h, k, ss, kbs_tc_bptt_tile(h, n)))) return rc;
     KBS_CUDA_TRY(cudaMemsetAsync(w[k].dc, 0, size_t(depth) * npH * 4, ss));
     KBS_CUDA_TRY(cudaMemsetAsync(w[k].bflags, 0, kbs_tc_bptt_flag_bytes(h, n), ss));
     for (int l = 0; l < depth; ++l)          // dG(l, T) = 0: the operand of the first backward step's recurrent GEMM
