@@ -617,11 +617,13 @@ def run_ppo_update(a, dev, world, barrier, max_ranks, peaks, n_traj, steps=8, br
         # forward 2 nets x 2 layers x 2 (2H)(4H) per row; backward [dx | dh] = dG [W_ih | W_hh]: the same count; weight
         # gradients dG^T [x | h]: the same again (+ input / output projections); fp32-accurate tensor peak = sustained bf16 / 3.
         eng.scratch_lock(False)
+        os.environ["KBS_PPO_SIDE_PACK"] = "0"      # one stream for this pass: the events around a launch then time that launch alone
         eng.profile(True)
         up.grads(batch, N)
         torch.cuda.synchronize()
         prof = eng.profile_read()
         eng.profile(False)
+        os.environ.pop("KBS_PPO_SIDE_PACK", None)
         prof.pop("_overflow", None)
         peak = peaks.get("bf16_tflops_sustained", 1400.0) / 3.0
         rows = N * T
@@ -637,7 +639,7 @@ def run_ppo_update(a, dev, world, barrier, max_ranks, peaks, n_traj, steps=8, br
         res["kernel_breakdown_ms"] = kb
         res["roofline_note"] = ("rollout_persist_kernel here = lstm_fwd_save_kernel (forward with saved activations); at 512 "
                                 "trajectories a slot of the wavefront holds 128 work items = one per SM: both recurrence kernels "
-                                "are bound by the dependency chain of a slot (operand fill at ~60 B/clk/SM + epilogue + publish / "
+                                "are bound by the dependency chain of a slot (tcgen05 issue + operand fill + epilogue + publish / "
                                 "poll hop), not by the tensor pipe; peak = sustained bf16 / 3 = %.0f TFLOP/s" % peak)
     eng.close()
     del up, batch

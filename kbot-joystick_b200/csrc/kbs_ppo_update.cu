@@ -944,8 +944,8 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
   // W_out^T, the backward kernel's weight tiles, its zeroed carries / counters / dG(l, T), the K padding of the re-packed
   // operands.  KBS_PPO_SIDE_PACK=0 keeps one stream (A/B).
   { const int rc0 = kbs_side_stream_init(h); if (rc0) return rc0; }
-  static int side_pack = -1;
-  if (side_pack < 0) { const char* e = getenv("KBS_PPO_SIDE_PACK"); side_pack = e ? atoi(e) : 1; }
+  int side_pack = 1;          // read per call: a profiling pass can ask for one stream (serial per-kernel times)
+  { const char* e = getenv("KBS_PPO_SIDE_PACK"); if (e) side_pack = atoi(e); }
   cudaStream_t ss = side_pack ? h->side_stream : st;
   if (side_pack) {
     KBS_CUDA_TRY(cudaEventRecord(h->ev_pre, st));

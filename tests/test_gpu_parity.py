@@ -668,6 +668,41 @@ def test_ppo_grad_per_step_launches_against_autograd(dev, T, N, hidden, monkeypa
     _ppo_grad_case(dev, T, N, hidden, L.GEMM_TC_2XF16)
 
 
+@pytest.mark.parametrize("T,N", [(9, 256), (26, 384)])
+def test_ppo_grad_in_place_weight_gradients_vs_repacked(dev, T, N, monkeypatch):
+    """dw_gemm_kernel (dG / x / h_in read in place as MN-major UMMA operands, whole panels only) against the K-major GEMM on
+    re-packed operands (KBS_DW_DIRECT=0): the same split products over the same accumulation runs -- the gradients must agree
+    far below the tolerance against autograd (which both forms are also held to)."""
+    _ppo_grad_case(dev, T, N, 256, L.GEMM_TC_2XF16)
+    e, wa, wc = Hn.make_engine(hidden=256, gemm_path=L.GEMM_TC_2XF16, device=dev)
+    p = O.OracleParams(hidden_size=256)
+    b = _ppo_batch(np.random.default_rng(7 + N), T, N, 256, p, wa, wc)
+    d = lambda a, dt=None: synth.to_soa(a if dt is None else a.astype(dt), 1, dev)
+    batch = {"actor_obs": d(b["actor_obs"]), "critic_obs": d(b["critic_obs"]), "action": d(b["action"]),
+             "done": d(b["done"], np.uint8), "old_log_probs": d(b["old_log_probs"]), "advantages": d(b["advantages"]),
+             "value_targets": d(b["value_targets"]), "old_values": d(b["old_values"])}
+
+    def grads():
+        z = lambda a: torch.full(a.shape, float("nan"), device=dev)
+        mk = lambda w: {"w_in": z(w["w_in"]), "b_in": z(w["b_in"]), "w_out": z(w["w_out"]), "b_out": z(w["b_out"]),
+                        "layers": [{k: z(l[k]) for k in ("w_ih", "w_hh", "b")} for l in w["layers"]]}
+        ga, gc = mk(wa), mk(wc)
+        e.ppo_grad(batch, ga, gc, n_envs=N)
+        torch.cuda.synchronize()
+        assert e.device_status() == 0
+        return [g["layers"][l][k].clone() for g in (ga, gc) for l in range(2) for k in ("w_ih", "w_hh", "b")]
+
+    direct = grads()
+    monkeypatch.setenv("KBS_DW_DIRECT", "0")
+    repacked = grads()
+    monkeypatch.delenv("KBS_DW_DIRECT")
+    e.close()
+    for a, r in zip(direct, repacked):
+        assert torch.isfinite(a).all()
+        scale = float(r.abs().max())
+        assert float((a - r).abs().max()) <= 2e-6 * scale + 1e-12, (float((a - r).abs().max()), scale)
+
+
 @pytest.mark.parametrize("T,N", [(33, 300), (100, 512)])
 def test_ppo_grad_persistent_longer_rollouts(dev, T, N):
     """The persistent update at the reference's rollout length (T = 100, 512 trajectories: train.py:1764-1766)."""
