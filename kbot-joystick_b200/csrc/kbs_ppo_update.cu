@@ -65,31 +65,6 @@ cell_fwd_save_kernel(const float* __restrict__ gates_pre, const float* __restric
   }
 }
 
-// LSTMCell backward at step t.  dh_in: gradient wrt h_t from above (next layer's dx or the head); dh_rec / dc_rec:
-// gradients wrt the carries step t+1 read (they see keep_t h_t, keep_t c_t).  Writes dG [n][4H] (pre-activation
-// gradients, eqx order) and overwrites dc_rec with the gradient wrt c_in of this step.
-__global__ void __launch_bounds__(kT)
-cell_bwd_kernel(const float* __restrict__ dh_in, const float* __restrict__ dh_rec, float* __restrict__ dc_rec,
-                const float* __restrict__ ga, const float* __restrict__ cs, const float* __restrict__ c_in,
-                const uint8_t* __restrict__ done, float* __restrict__ dG, int H, int64_t n) {
-  const int64_t idx = int64_t(blockIdx.x) * kT + threadIdx.x;
-  if (idx >= n * H) return;
-  const int64_t e = idx / H;
-  const int k = int(idx - e * H);
-  const float keep = (done && done[e]) ? 0.0f : 1.0f;
-  const float* a = ga + e * 4 * H;
-  const float i = a[k], f = a[H + k], g = a[2 * H + k], o = a[3 * H + k];
-  const float tc = tanhf(cs[idx]);
-  const float dh = dh_in[idx] + keep * dh_rec[idx];
-  const float dc = keep * dc_rec[idx] + dh * o * (1.0f - tc * tc);
-  float* d = dG + e * 4 * H;
-  d[k] = dc * g * i * (1.0f - i);
-  d[H + k] = dc * c_in[idx] * f * (1.0f - f);
-  d[2 * H + k] = dc * i * (1.0f - g * g);
-  d[3 * H + k] = dh * tc * o * (1.0f - o);
-  dc_rec[idx] = dc * f;
-}
-
 // ---- tensor-core variant of the recurrent part: the same cell math, 8 hidden units per thread, and the operands of the
 // next GEMM written in the split-blocked MMA layout by the producing kernel (kbs_common.cuh) ----
 __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
@@ -227,85 +202,6 @@ copy_block_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst
   if (idx >= int64_t(rows) * cols) return;
   const int r = int(idx / cols), c = int(idx % cols);
   dst[idx] = src[size_t(r) * ld + c];
-}
-
-// Actor head: forward over t (std, mean, low-pass, log-prob / entropy of the stored action, train.py:924-939, 1452,
-// 1486), then the loss gradient and the backward pass of the head including the reverse scan of the low-pass filter.
-// One thread per env (the filter is a recurrence in time; 20 joints per thread).
-//   out [T*n][64] row-major (mean rows 0..19, std rows 20..39); dout same shape (written; columns >= 40 zero)
-//   y_s, sd_s [T][20][ld] scratch (filtered mean, std); log_prob, entropy [T][ld] out
-__global__ void __launch_bounds__(128)
-actor_head_fwd_bwd_kernel(const __grid_constant__ kbs_params P, kbs_ppo_loss_params L, const float* __restrict__ out,
-                          const float* __restrict__ actor_obs, const float* __restrict__ action, const uint8_t* __restrict__ done,
-                          const float* __restrict__ lpf0, const float* __restrict__ old_lp, const float* __restrict__ adv,
-                          float* __restrict__ y_s, float* __restrict__ sd_s, float* __restrict__ log_prob,
-                          float* __restrict__ entropy, float* __restrict__ dout, int64_t T, int64_t ld, int64_t n) {
-  const int64_t e = int64_t(blockIdx.x) * 128 + threadIdx.x;
-  if (e >= n) return;
-  constexpr float kHalfLog2Pi = 0.918938533204672742f;
-  float y[KBS_NUM_JOINTS];
-#pragma unroll
-  for (int j = 0; j < KBS_NUM_JOINTS; ++j) y[j] = lpf0 ? lpf0[j * ld + e] : 0.0f;
-  for (int64_t t = 0; t < T; ++t) {
-    const float* o = out + (t * n + e) * 64;
-    float s_z = 0.0f, s_log = 0.0f;
-#pragma unroll
-    for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
-      const float sraw = o[KBS_NUM_JOINTS + j];
-      const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
-      const float sd = fminf((sp + P.min_std) * P.var_scale, P.max_std);
-      float m = o[j] + P.joint_bias[j];
-      if (j >= 10) m = m + actor_obs[(t * KBS_ACTOR_OBS + 55 + (j - 10)) * ld + e];
-      y[j] = y[j] + P.lpf_alpha * (m - y[j]);
-      const int64_t so = (t * KBS_NUM_JOINTS + j) * ld + e;
-      y_s[so] = y[j];
-      sd_s[so] = sd;
-      const float z = (action[so] - y[j]) / sd;
-      s_z = s_z + (-0.5f * z * z - kHalfLog2Pi);
-      s_log = s_log + logf(sd);
-    }
-    log_prob[t * ld + e] = s_z - s_log;
-    entropy[t * ld + e] = s_log + float(KBS_NUM_JOINTS) * (0.5f + kHalfLog2Pi);
-    if (done[t * ld + e]) {
-#pragma unroll
-      for (int j = 0; j < KBS_NUM_JOINTS; ++j) y[j] = 0.0f;
-    }
-  }
-  // backward
-  const float inv = 1.0f / (float(T) * float(n));
-  float gy[KBS_NUM_JOINTS];
-#pragma unroll
-  for (int j = 0; j < KBS_NUM_JOINTS; ++j) gy[j] = 0.0f;
-  for (int64_t t = T - 1; t >= 0; --t) {
-    const float lr = log_prob[t * ld + e] - old_lp[t * ld + e];
-    const float lrc = fminf(fmaxf(lr, -L.log_clip_value), L.log_clip_value);
-    const float r = expf(lrc);
-    const float a = adv[t * ld + e];
-    const float dr = (fabsf(lr) <= L.log_clip_value) ? r : 0.0f;                        // d r / d log_prob
-    const bool inside = r >= 1.0f - L.clip_param && r <= 1.0f + L.clip_param;
-    const float rc = fminf(fmaxf(r, 1.0f - L.clip_param), 1.0f + L.clip_param);
-    const float dpol = (inside || r * a < rc * a) ? a * dr : 0.0f;                      // d policy / d log_prob
-    const float glp = -inv * dpol, gent = -inv * L.entropy_coef;                        // d loss / d log_prob, d entropy
-    const float keep = done[t * ld + e] ? 0.0f : 1.0f;
-    const float* o = out + (t * n + e) * 64;
-    float* d = dout + (t * n + e) * 64;
-#pragma unroll
-    for (int j = 0; j < KBS_NUM_JOINTS; ++j) {
-      const int64_t so = (t * KBS_NUM_JOINTS + j) * ld + e;
-      const float sd = sd_s[so], yy = y_s[so];
-      const float z = (action[so] - yy) / sd;
-      const float dmu = glp * z / sd;
-      const float dsd = (glp * (z * z - 1.0f) + gent) / sd;
-      const float sraw = o[KBS_NUM_JOINTS + j];
-      const float sp = fmaxf(sraw, 0.0f) + log1pf(expf(-fabsf(sraw)));
-      const bool clamped = (sp + P.min_std) * P.var_scale > P.max_std;
-      d[KBS_NUM_JOINTS + j] = clamped ? 0.0f : dsd * P.var_scale * sigm(sraw);
-      gy[j] = dmu + (1.0f - P.lpf_alpha) * keep * gy[j];      // y_{t+1} = (1 - alpha) keep_t y_t + alpha m_{t+1}
-      d[j] = P.lpf_alpha * gy[j];
-    }
-#pragma unroll
-    for (int j = 2 * KBS_NUM_JOINTS; j < 64; ++j) d[j] = 0.0f;
-  }
 }
 
 // The same head with one WARP per env (lane j = joint j, log-prob / entropy by warp shuffles): the one-thread-per-env form
@@ -642,7 +538,6 @@ struct NetWork {      // per-net workspace (floats), carved from the handle's sc
   // weight-gradient GEMMs on the tensor cores: transposed split-blocked operands (K = all T x n rows), split-K slabs
   char* tn_a; char* tn_b; float* tn_partial; float* tn_zero; char* tn_ones;
 };
-constexpr int kTnMaxTiles = 8;     // B tiles of 128 columns per TN GEMM (LSTM layer: [x | h] = 4 + the ones tile)
 
 size_t net_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n, bool tc) {
   const size_t H = size_t(h->p.hidden_size), rows = size_t(T) * size_t(n);
@@ -851,7 +746,7 @@ struct PersistWork {
   char* x_sb; char* xmid; char* hsb; float* c_hist; float* save_g; char* dG; float* dx; char* dx0; float* dc;
   float* dh_top; float* dout; float* w_outT; unsigned int* bflags;
   float* h_top_rm; float* out; unsigned int* fflags;      // narrow-tile forward: top-layer outputs, head GEMM output, counters
-  char* tn_a; char* tn_b; float* tn_partial; float* tn_zero; char* tn_ones;
+  char* tn_a; float* tn_partial; float* tn_zero; char* tn_ones;
   // B operands (forward-pass products) are transposed on the side stream while the backward kernel runs: one buffer each
   char* tnb_layer[KBS_MAX_DEPTH];   // [x_l | h_in_l]: 2 H / 128 tiles
   char* tnb_top;                    // top layer's outputs: H / 128 tiles
@@ -870,7 +765,7 @@ size_t persist_work_floats(const kbs_handle* h, int net, int64_t T, int64_t n) {
              depth * size_t(T + 1) * npH /*c_hist*/ + size_t(T) * depth * 4 * npH /*save_g*/ + depth * size_t(T + 1) * sb4f /*dG*/ +
              depth * size_t(T) * npH /*dx*/ + size_t(T) * sbf /*dx0*/ + depth * npH /*dc*/ + rows * H /*dh_top*/ + rows * 64 /*dout*/ +
              64 * H + kbs_tc_bptt_flag_bytes(h, n) / 4 + rows * H /*h_top_rm*/ + rows * 64 /*out*/ + kbs_tc_fwd_save_flag_bytes(h, n) / 4;
-  f += (m_panels + b_tiles) * plan.col_bytes / 4 + size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128) + 1024 + 4096;
+  f += m_panels * plan.col_bytes / 4 + size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128) + 1024 + 4096;
   f += (depth * (2 * H / 128) + H / 128 + kpp / 128 + depth * (4 * H / 128)) * plan.col_bytes / 4;
   return f + 64 * 40;       // carve() rounds every piece up to 64 floats
 }
@@ -918,7 +813,6 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
     w[k].out = carve(p, size_t(rows) * 64);
     w[k].fflags = reinterpret_cast<unsigned int*>(carve(p, kbs_tc_fwd_save_flag_bytes(h, n) / 4));
     w[k].tn_a = reinterpret_cast<char*>(carve(p, m_panels * plan.col_bytes / 4));
-    w[k].tn_b = reinterpret_cast<char*>(carve(p, b_tiles * plan.col_bytes / 4));
     w[k].tn_partial = carve(p, size_t(plan.ksplit) * m_panels * 128 * (b_tiles * 128));
     w[k].tn_zero = carve(p, 1024);
     w[k].tn_ones = reinterpret_cast<char*>(carve(p, 4096));
