@@ -635,19 +635,7 @@ def test_ppo_loss(eng, dev, T, N, clipped):
     assert torch.equal(out, again), "the reduction order is fixed: bitwise reproducible"
 
 
-def _ppo_batch(rng, T, N, H, p, wa, wc):
-    """A stored minibatch with old log-probs / values taken near the current policy (so both clip branches occur)."""
-    import ppo_grad_torch as G
-
-    f = np.float32
-    b = {"actor_obs": rng.normal(0, 0.7, (T, N, 65)).astype(f), "critic_obs": rng.normal(0, 0.7, (T, N, 475)).astype(f),
-         "action": (0.3 * rng.normal(size=(T, N, 20))).astype(f), "done": rng.random((T, N)) < 0.12,
-         "advantages": rng.normal(size=(T, N)).astype(f), "value_targets": rng.normal(0, 0.5, (T, N)).astype(f),
-         "old_log_probs": np.zeros((T, N), f), "old_values": np.zeros((T, N), f)}
-    _, _, _, _, lp, val = G.ppo_minibatch_grads(wa, wc, b, p)
-    b["old_log_probs"] = (lp + rng.normal(0, 0.15, (T, N))).astype(f)
-    b["old_values"] = (val + rng.normal(0, 0.25, (T, N))).astype(f)
-    return b
+_ppo_batch = Hn.ppo_batch
 
 
 @pytest.mark.parametrize("path", [pytest.param(L.GEMM_SIMT_FP32, id="simt"), pytest.param(L.GEMM_TC_2XF16, id="tc2xf16"),
@@ -710,47 +698,7 @@ def test_ppo_grad_persistent_longer_rollouts(dev, T, N):
 
 
 def _ppo_grad_case(dev, T, N, hidden, path):
-    import ppo_grad_torch as G
-
-    e, wa, wc = Hn.make_engine(hidden=hidden, gemm_path=path, device=dev)
-    p = O.OracleParams(hidden_size=hidden)
-    rng = np.random.default_rng(90 + N)
-    b = _ppo_batch(rng, T, N, hidden, p, wa, wc)
-    loss, stats, ga_ref, gc_ref, lp_ref, val_ref = G.ppo_minibatch_grads(wa, wc, b, p)
-
-    def zeros_like_w(w):
-        z = lambda a: torch.full(a.shape, float("nan"), device=dev)
-        return {"w_in": z(w["w_in"]), "b_in": z(w["b_in"]), "w_out": z(w["w_out"]), "b_out": z(w["b_out"]),
-                "layers": [{k: z(l[k]) for k in ("w_ih", "w_hh", "b")} for l in w["layers"]]}
-
-    ga, gc = zeros_like_w(wa), zeros_like_w(wc)
-    d = lambda a, dt=None: synth.to_soa(a if dt is None else a.astype(dt), 1, dev)
-    batch = {"actor_obs": d(b["actor_obs"]), "critic_obs": d(b["critic_obs"]), "action": d(b["action"]),
-             "done": d(b["done"], np.uint8), "old_log_probs": d(b["old_log_probs"]), "advantages": d(b["advantages"]),
-             "value_targets": d(b["value_targets"]), "old_values": d(b["old_values"])}
-    out = e.ppo_grad(batch, ga, gc, n_envs=N)
-    torch.cuda.synchronize()
-    assert e.device_status() == 0
-    close(S(out["log_probs"], N), lp_ref, "log_probs", atol=1e-4)
-    close(S(out["values"], N), val_ref, "values", atol=1e-5)
-    close(out["stats"].cpu().numpy(), np.array((loss,) + stats, np.float32), "loss stats", rtol=2e-5, atol=1e-5)
-
-    bad = []
-
-    def check(name, got, ref):
-        got = got.cpu().numpy()
-        scale = np.abs(ref).max()
-        err = np.abs(got - ref).max()
-        if not (np.isfinite(got).all() and err <= 3e-4 * scale + 1e-9):
-            bad.append(f"{name}: max err {err:.3e} vs scale {scale:.3e}")
-
-    for nm, g, r in (("actor", ga, ga_ref), ("critic", gc, gc_ref)):
-        for k in ("w_in", "b_in", "w_out", "b_out"):
-            check(f"{nm}.{k}", g[k], r[k])
-        for l in range(2):
-            for k in ("w_ih", "w_hh", "b"):
-                check(f"{nm}.layers[{l}].{k}", g["layers"][l][k], r["layers"][l][k])
-    e.close()
+    bad = Hn.run_ppo_grad_case(dev, T, N, hidden, path)
     assert not bad, bad
 
 
