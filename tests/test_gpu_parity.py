@@ -450,6 +450,44 @@ def test_rollout_fused_at_reference_length_against_oracle(dev, path, T, N):
     assert not bad, f"scaled errors > 1: {bad} (all: {res['errors']})"
 
 
+def test_rollout_configs2_size_by_env_tiling(dev):
+    """BASELINE configs[2] (16 384 envs x 256 steps) at full size through a size-independent property: environments are
+    independent, so a batch made of 32 copies of a 512-env batch (which IS compared with the oracle at T = 256 above) must
+    give, bit for bit, 32 copies of that batch's results -- whatever the panel a copy lands in, the order the 128-env panels
+    are scheduled in, and the 256-step depth of the dependency counters."""
+    T, N0, R = 256, 512, 32
+    b = Batch(5150, T, N0, dev)
+    small = Hn.rollout_buffers(b, 256, 2)
+    e, _, _ = Hn.make_engine(gemm_path=L.GEMM_TC_2XF16, device=dev)
+    e.rollout(small, N0)
+    torch.cuda.synchronize()
+    assert e.device_status() == 0
+
+    def tile(v):
+        if isinstance(v, dict):
+            return {k: tile(x) for k, x in v.items()}
+        if torch.is_tensor(v) and v.shape[-1] == N0:
+            return v.repeat(*([1] * (v.dim() - 1)), R)
+        return v
+
+    fresh = Hn.rollout_buffers(b, 256, 2)                  # untouched inputs / zeroed outputs of the same batch
+    big = {k: tile(v) for k, v in fresh.items() if k not in ("actor_carry", "critic_carry")}
+    for k in ("actor_carry", "critic_carry"):
+        big[k] = torch.zeros((2, 2, N0 * R, 256), device=dev)
+    del fresh
+    e.rollout(big, N0 * R)
+    torch.cuda.synchronize()
+    assert e.device_status() == 0
+    for k in ("action", "log_prob", "value", "ctrl", "done", "success", "term_codes", "actor_obs", "lpf", "pg_carry", "command"):
+        got = big[k].reshape(*big[k].shape[:-1], R, N0)
+        ref = small[k].unsqueeze(-2).expand_as(got)
+        assert torch.equal(got, ref), f"{k}: a copy of the batch differs from the 512-env run"
+    for k in ("actor_carry", "critic_carry"):
+        got = big[k].reshape(2, 2, R, N0, 256)
+        assert torch.equal(got, small[k].unsqueeze(2).expand_as(got)), k
+    e.close()
+
+
 @pytest.mark.parametrize("T,N", [(12, 2048), (40, 4096)])
 def test_rollout_persistent_vs_per_step_launches(dev, T, N, monkeypatch):
     """Size-independent property at BASELINE configs[1] scale: the persistent recurrence kernel (one launch, CTAs
@@ -689,6 +727,46 @@ def test_ppo_grad_in_place_weight_gradients_vs_repacked(dev, T, N, monkeypatch):
         assert torch.isfinite(a).all()
         scale = float(r.abs().max())
         assert float((a - r).abs().max()) <= 2e-6 * scale + 1e-12, (float((a - r).abs().max()), scale)
+
+
+def test_ppo_grad_large_minibatch_by_tiling(dev):
+    """BASELINE configs[3]'s per-GPU share of the 65 536-env batch (8 192 trajectories x 100 steps) through a size-independent
+    property: the loss is a mean over trajectories, so a minibatch made of 16 copies of a 512-trajectory minibatch (compared
+    with autograd above) has the same gradient.  At this size the recurrence kernels run many items per CTA and slot and the
+    weight-gradient GEMMs 256 accumulation runs: only the order of the fp32 sums differs."""
+    T, N0, R, H = 100, 512, 16, 256
+    e, wa, wc = Hn.make_engine(hidden=H, gemm_path=L.GEMM_TC_2XF16, device=dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    rn = lambda *s, sc=1.0: torch.randn(s, generator=g, device=dev) * sc
+    small = {"actor_obs": rn(T, 65, N0, sc=0.7), "critic_obs": rn(T, 475, N0, sc=0.7), "action": rn(T, 20, N0, sc=0.3),
+             "done": (torch.rand((T, N0), generator=g, device=dev) < 0.02).to(torch.uint8),
+             "advantages": rn(T, N0), "value_targets": rn(T, N0, sc=0.5)}
+    z = lambda n: torch.zeros((2, 2, n, H), device=dev)
+    fwd = e.ppo_variables(small["actor_obs"], small["action"], small["done"], z(N0), torch.zeros((20, N0), device=dev),
+                          small["critic_obs"], z(N0), want_std=False, n_envs=N0)
+    small["old_log_probs"] = fwd["log_probs"] + rn(T, N0, sc=0.1)
+    small["old_values"] = fwd["values"] + rn(T, N0, sc=0.2)
+
+    def grads(batch, n):
+        mk = lambda w: {"w_in": torch.zeros_like(w["w_in"]), "b_in": torch.zeros_like(w["b_in"]), "w_out": torch.zeros_like(w["w_out"]),
+                        "b_out": torch.zeros_like(w["b_out"]),
+                        "layers": [{k: torch.zeros_like(l[k]) for k in ("w_ih", "w_hh", "b")} for l in w["layers"]]}
+        ga, gc = mk(synth.weights_to_device(wa, dev)), mk(synth.weights_to_device(wc, dev))
+        out = e.ppo_grad(batch, ga, gc, n_envs=n)
+        torch.cuda.synchronize()
+        assert e.device_status() == 0
+        flat = [x[k] for x in (ga, gc) for k in ("w_in", "b_in", "w_out", "b_out")]
+        flat += [x["layers"][l][k] for x in (ga, gc) for l in range(2) for k in ("w_ih", "w_hh", "b")]
+        return [t.clone() for t in flat], out["stats"].clone()
+
+    ref, ref_stats = grads(small, N0)
+    big = {k: v.repeat(*([1] * (v.dim() - 1)), R) for k, v in small.items()}
+    got, got_stats = grads(big, N0 * R)
+    e.close()
+    assert torch.allclose(got_stats, ref_stats, rtol=2e-5, atol=1e-6), (got_stats, ref_stats)
+    for a, r in zip(got, ref):
+        scale = float(r.abs().max())
+        assert torch.isfinite(a).all() and float((a - r).abs().max()) <= 2e-5 * scale + 1e-12, (float((a - r).abs().max()), scale)
 
 
 @pytest.mark.parametrize("T,N", [(33, 300), (100, 512)])
