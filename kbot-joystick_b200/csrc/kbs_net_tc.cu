@@ -3719,15 +3719,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // items run-major: the 3 m_tiles items of a run (2 m_tiles tiles of 256 columns + m_tiles bias items) are taken by neighbouring
-  // CTAs at the same time, so each dG tile is fetched from HBM once for its three readers and each [x | h] tile once for its
-  // m_tiles readers (gate-tile-major order streamed every operand from HBM per item: 1.4 GB instead of 0.3 GB per GEMM)
-  const int per_run = args.m_tiles * 3, n_items = per_run * args.ksplit;
+  // Item order: all 256-column items first, run-major (the 2 m_tiles of a run are taken by neighbouring CTAs at the same time, so
+  // each dG tile is fetched from HBM once for its readers and each [x | h] tile once for its m_tiles readers: gate-tile-major
+  // order streamed every operand from HBM per item, 1.4 GB instead of 0.3 GB per GEMM), then the bias items (about half the
+  // cost of a big one), run-major as well.  With round-robin over the CTAs the cheap items land on the CTAs that got one big
+  // item less: at 16 runs 148 CTAs carry at most 2 big + 1 bias item instead of 3 big ones.
+  const int per_run = args.m_tiles * 2, n_big = per_run * args.ksplit, n_items = n_big + args.m_tiles * args.ksplit;
   auto decode = [&](int it, int& m, int& nt, int& run) {
-    run = it / per_run;
-    const int q = it - run * per_run;
-    if (q < 2 * args.m_tiles) { m = q >> 1; nt = q & 1; }
-    else { m = q - 2 * args.m_tiles; nt = 2; }
+    if (it < n_big) { run = it / per_run; const int q = it - run * per_run; m = q >> 1; nt = q & 1; }
+    else { const int j = it - n_big; run = j / args.m_tiles; m = j - run * args.m_tiles; nt = 2; }
   };
   if (warp == 1) {
     if (lane == 0) {
