@@ -282,6 +282,8 @@ bool kbs_tc_bptt_available(const kbs_handle* h, int64_t n, int64_t T);
 int kbs_tc_bptt(kbs_handle* h, const KbsBpttArgs& a, cudaStream_t st);
 int kbs_tc_tn_reduce(kbs_handle* h, const KbsTnPlan& plan, const float* partial, int m_panels, int ldc, int col0, int nrows,
                      int ncols, float* dst, int ld_dst, cudaStream_t st);
+int kbs_tc_tn_reduce_multi(kbs_handle* h, const KbsTnPlan& plan, const float* partial, int m_panels, int ldc, int nrows, int nseg,
+                           const int (*seg)[3], float* const* dst, cudaStream_t st);
 int kbs_tc_kind_of(const kbs_handle* h);
 int kbs_tc_debug_gates(kbs_handle* h, int net, int layer, const float* x_rm, const float* h_rm, float* gates_out,
                        float* ws, int64_t n, cudaStream_t st);

@@ -2893,6 +2893,21 @@ tn_reduce_kernel(const float* __restrict__ partial, int ksplit, size_t split_str
   dst[size_t(r) * ld_dst + c] = a;
 }
 
+// the same for up to three column ranges of the slabs at once (w_ih | w_hh | bias of a layer: one pass instead of three launches)
+struct TnSegs { int col0[3], ncols[3], ld_dst[3]; float* dst[3]; int nseg, total_cols; };
+__global__ void __launch_bounds__(256)
+tn_reduce_multi_kernel(const float* __restrict__ partial, int ksplit, size_t split_stride, int ldc, int nrows, TnSegs sg) {
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= int64_t(nrows) * sg.total_cols) return;
+  const int r = int(idx / sg.total_cols);
+  int c = int(idx % sg.total_cols), k = 0;
+  while (k + 1 < sg.nseg && c >= sg.ncols[k]) { c -= sg.ncols[k]; ++k; }
+  const float* p = partial + size_t(r) * ldc + sg.col0[k] + c;
+  float a = 0.0f;
+  for (int sidx = 0; sidx < ksplit; ++sidx) a += p[size_t(sidx) * split_stride];
+  sg.dst[k][size_t(r) * sg.ld_dst[k] + c] = a;
+}
+
 inline int64_t pad_rows(int64_t n) { return (n + kPanelRows - 1) / kPanelRows * kPanelRows; }
 inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -3901,6 +3916,23 @@ int kbs_tc_tn_reduce(kbs_handle* h, const KbsTnPlan& plan, const float* partial,
   const int64_t total = int64_t(nrows) * ncols;
   KBS_LAUNCH(h, KBS_K_TN_REDUCE, st, (tn_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(
                                          partial, plan.ksplit, size_t(m_panels) * kPanelRows * size_t(ldc), ldc, col0, nrows, ncols, dst, ld_dst)));
+  KBS_LAUNCH_CHECK();
+  return KBS_OK;
+}
+
+// several column ranges of the same slabs in one launch: seg = {col0, ncols, ld_dst} x nseg, dst[nseg]
+int kbs_tc_tn_reduce_multi(kbs_handle* h, const KbsTnPlan& plan, const float* partial, int m_panels, int ldc, int nrows, int nseg,
+                           const int (*seg)[3], float* const* dst, cudaStream_t st) {
+  if (nseg < 1 || nseg > 3) return KBS_E_SHAPE;
+  TnSegs sg{};
+  sg.nseg = nseg;
+  for (int k = 0; k < nseg; ++k) {
+    sg.col0[k] = seg[k][0]; sg.ncols[k] = seg[k][1]; sg.ld_dst[k] = seg[k][2]; sg.dst[k] = dst[k];
+    sg.total_cols += seg[k][1];
+  }
+  const int64_t total = int64_t(nrows) * sg.total_cols;
+  KBS_LAUNCH(h, KBS_K_TN_REDUCE, st, (tn_reduce_multi_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(
+                                         partial, plan.ksplit, size_t(m_panels) * kPanelRows * size_t(ldc), ldc, nrows, sg)));
   KBS_LAUNCH_CHECK();
   return KBS_OK;
 }

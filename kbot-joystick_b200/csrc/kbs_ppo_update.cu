@@ -997,23 +997,27 @@ int ppo_grad_persistent(kbs_handle* h, const kbs_ppo_loss_params& L, const kbs_p
                                  w[k].tn_partial, inv, sk)))
           return rc;
       }
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 0, 4 * H, H, g->w_ih[l], H, sk))) return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, H, 4 * H, H, g->w_hh[l], H, sk))) return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, ldc, 2 * H, 4 * H, 1, g->b[l], 1, sk))) return rc;
+      {
+        const int sg3[3][3] = {{0, H, H}, {H, H, H}, {2 * H, 1, 1}};
+        float* const dst3[3] = {g->w_ih[l], g->w_hh[l], g->b[l]};
+        if ((rc = kbs_tc_tn_reduce_multi(h, plan, w[k].tn_partial, mp, ldc, 4 * H, 3, sg3, dst3, sk))) return rc;
+      }
     }
     {   // dW_out, db_out: A = d loss / d out (packed on the side stream above), B = the top layer's outputs + ones tile
       const int ldc = (H / 128 + 1) * 128;
       if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, 1, N.num_out, w[k].tnb_top, H / 128, w[k].tn_ones, w[k].tn_zero, w[k].tn_partial, inv, sk)))
         return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, 0, N.num_out, H, g->w_out, H, sk))) return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, 1, ldc, H, N.num_out, 1, g->b_out, 1, sk))) return rc;
+      const int sg2[2][3] = {{0, H, H}, {H, 1, 1}};
+      float* const dst2[2] = {g->w_out, g->b_out};
+      if ((rc = kbs_tc_tn_reduce_multi(h, plan, w[k].tn_partial, 1, ldc, N.num_out, 2, sg2, dst2, sk))) return rc;
     }
     {   // dW_in, db_in
       const int kpp = round_up_i(N.num_in + 1, 128), mp = H / 128;
       if ((rc = kbs_tc_sb_to_tn(h, plan, false, w[k].dx0, sbb, kbH, 0, kbH, n, T, w[k].tn_a, sk))) return rc;
       if ((rc = kbs_tc_gemm_tn(h, plan, w[k].tn_a, mp, H, w[k].tnb_obs, kpp / 128, nullptr, w[k].tn_zero, w[k].tn_partial, inv, sk))) return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, kpp, 0, H, N.num_in, g->w_in, N.num_in, sk))) return rc;
-      if ((rc = kbs_tc_tn_reduce(h, plan, w[k].tn_partial, mp, kpp, N.num_in, H, 1, g->b_in, 1, sk))) return rc;
+      const int sg2[2][3] = {{0, N.num_in, N.num_in}, {N.num_in, 1, 1}};
+      float* const dst2[2] = {g->w_in, g->b_in};
+      if ((rc = kbs_tc_tn_reduce_multi(h, plan, w[k].tn_partial, mp, kpp, H, 2, sg2, dst2, sk))) return rc;
     }
     if (k == 1) {
       if (h->ev_critic_ready) KBS_CUDA_TRY(cudaEventRecord(h->ev_critic_ready, sk));   // the critic's gradients are final
