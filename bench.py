@@ -380,7 +380,9 @@ def run_b200(a):
 
     # ---- per-kernel pass (CUDA events around every launch, same step) -> roofline of the dominant kernel ----------
     eng.profile(True)
-    n_prof = 3                                    # averaged over three steps (one step alone carries the box's power-state noise)
+    # the same loop again, instrumented: averaged over as many steps as were timed (at most 20), so that the kernels are measured
+    # in the sustained power state of the timed region (a single step right behind it has read 10-25 % slow on some boxes)
+    n_prof = max(3, min(a.steps, 20))
     for _ in range(n_prof):
         step()
     torch.cuda.synchronize()
