@@ -738,10 +738,16 @@ int run_net(kbs_handle* h, int net, const kbs_ppo_batch& b, const float* carry0,
 }
 
 // ---- the persistent form of kbs_ppo_grad (FP16-split datapath) ---------------------------------------------------------
-// forward: input projections (tensor core, straight from the SoA observations) -> rollout_persist_kernel<SAVE> (ALL T steps
-// of both networks, output heads included, one launch; keeps operands + activated gates) -> head backward (loss gradient)
-// -> dh_top = dout W_out -> bptt_persist_kernel (the whole backward recurrence of both networks, one launch) -> weight
-// gradients as split-K tcgen05 GEMMs over all T x n rows, operands = the kept per-step buffers re-packed with K = row.
+// main stream: input projections (tensor core, straight from the SoA observations) -> lstm_fwd_save_kernel (ALL T steps of both
+// networks' LSTM stacks, one launch; keeps operands, cell states, activated gates) -> heads (actor: FFMA GEMM + one warp per env
+// through the Gaussian / low-pass filter forward and backward; critic: GEMV + value-loss gradient) -> dh_top (actor: FFMA GEMM;
+// critic: rank 1, inside the backward kernel) -> bptt_persist_kernel (the whole backward recurrence of both networks, one
+// launch) -> weight gradients: the four layer GEMMs read dG / x / h_in in place (dw_gemm_kernel), the input / output layers'
+// through K = row re-packed operands (split-K lstm_layer_tc_kernel) -> fixed-order reductions -> loss statistics.
+// side stream: whatever does not depend on the forward pass (observation re-pack, backward weight tiles, zeroed state), then the
+// re-packs of what it produced, then the critic's whole weight-gradient chain beside the actor's.
+// (KBS_PPO_FWD_WIDE=1: rollout_persist_kernel<SAVE> as the forward kernel; ragged n or H != 256: the layer GEMMs fall back to
+// re-packed operands, transposed on the fly by the recurrence kernels.)
 struct PersistWork {
   char* x_sb; char* xmid; char* hsb; float* c_hist; float* save_g; char* dG; float* dx; char* dx0; float* dc;
   float* dh_top; float* dout; float* w_outT; unsigned int* bflags;
