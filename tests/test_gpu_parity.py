@@ -769,6 +769,13 @@ def test_ppo_grad_large_minibatch_by_tiling(dev):
         assert torch.isfinite(a).all() and float((a - r).abs().max()) <= 2e-5 * scale + 1e-12, (float((a - r).abs().max()), scale)
 
 
+@pytest.mark.parametrize("T,N", [(1, 128), (1, 5), (2, 129), (3, 640)])
+def test_ppo_grad_edge_shapes(dev, T, N):
+    """One-step rollouts, a handful of trajectories, a panel plus one row, whole panels with T x panels below one accumulation
+    run (the in-place weight-gradient GEMM then has empty runs to zero-fill)."""
+    _ppo_grad_case(dev, T, N, 256, L.GEMM_TC_2XF16)
+
+
 @pytest.mark.parametrize("T,N", [(33, 300), (100, 512)])
 def test_ppo_grad_persistent_longer_rollouts(dev, T, N):
     """The persistent update at the reference's rollout length (T = 100, 512 trajectories: train.py:1764-1766)."""
